@@ -1,0 +1,402 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (CPU, fp32).  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+The fixtures travel to the GPU box; the reference does not.
+
+Every fixture is a dict of tensors / python scalars saved with torch.save.  Random draws that the
+reference makes inside forward()/train() are captured on a tape (by wrapping torch.randn / torch.rand /
+torch.randint / np.random.rand while the reference runs -- the reference's code itself is untouched)
+so that the oracle and the B200 path can replay exactly the same latents, noise and mixing cut-offs.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+
+from oracle.reference_loader import load_reference, make_config
+
+GOLDEN_DIR = Path(__file__).resolve().parent.parent / "tests" / "golden"
+SMALL_FMAP_MAX = 32      # reference constant stylegan/base.py:17 / progan/base.py:17 patched for small fixtures
+
+
+# --------------------------------------------------------------------------- #
+class Tape:
+    """Records the reference's random draws in call order."""
+
+    def __init__(self):
+        self.events = []
+        self._orig = {}
+
+    def __enter__(self):
+        self._orig = dict(randn=torch.randn, rand=torch.rand, randint=torch.randint, nprand=np.random.rand)
+        tape = self
+
+        def randn(*a, **k):
+            t = tape._orig["randn"](*a, **k)
+            tape.events.append(("randn", t.detach().clone()))
+            return t
+
+        def rand(*a, **k):
+            t = tape._orig["rand"](*a, **k)
+            tape.events.append(("rand", t.detach().clone()))
+            return t
+
+        def randint(*a, **k):
+            t = tape._orig["randint"](*a, **k)
+            tape.events.append(("randint", t.detach().clone()))
+            return t
+
+        def nprand(*a):
+            v = tape._orig["nprand"](*a)
+            tape.events.append(("np_rand", float(v)))
+            return v
+
+        torch.randn, torch.rand, torch.randint, np.random.rand = randn, rand, randint, nprand
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.rand, torch.randint = self._orig["randn"], self._orig["rand"], self._orig["randint"]
+        np.random.rand = self._orig["nprand"]
+        return False
+
+
+def perturb_zero_params(module, gen):
+    """Zero-initialised params (biases, noise_weight) hide whole code paths; perturb them
+    (SURVEY.md section 8c 'Determinism hooks')."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if float(p.abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+
+
+def sd_clone(module):
+    return {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
+def grads_of(module):
+    return {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in module.named_parameters()}
+
+
+# --------------------------------------------------------------------------- #
+def golden_layers(ref):
+    """Per-module forward / backward (/ double-backward for D-side modules)."""
+    cl = ref.custom_layers
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+
+    def rn(*shape):
+        return torch.randn(*shape, generator=g)
+
+    # Conv2dEx variants (custom_layers.py:147-211)
+    conv_cases = {
+        "conv3x3": dict(ni=32, nf=64, ks=3, padding=1, gain_sq_base=2., lrmul=1., include_bias=True, hw=8, n=4),
+        "conv3x3_nobias": dict(ni=64, nf=32, ks=3, padding=1, gain_sq_base=2., lrmul=1., include_bias=False, hw=16, n=2),
+        "conv1x1_torgb": dict(ni=32, nf=3, ks=1, padding=0, gain_sq_base=1., lrmul=1., include_bias=True, hw=16, n=4),
+        "conv1x1_fromrgb": dict(ni=3, nf=32, ks=1, padding=0, gain_sq_base=2., lrmul=1., include_bias=True, hw=16, n=4),
+        "conv4x4_valid": dict(ni=32, nf=32, ks=4, padding=0, gain_sq_base=2., lrmul=1., include_bias=True, hw=4, n=8),
+        "conv3x3_c33": dict(ni=33, nf=32, ks=3, padding=1, gain_sq_base=2., lrmul=1., include_bias=True, hw=4, n=8),
+        "conv3x3_lrmul": dict(ni=16, nf=16, ks=3, padding=1, gain_sq_base=2., lrmul=.5, include_bias=True, hw=8, n=2),
+    }
+    for name, c in conv_cases.items():
+        torch.manual_seed(hash(name) % 1000)
+        m = cl.Conv2dEx(ni=c["ni"], nf=c["nf"], ks=c["ks"], stride=1, padding=c["padding"], init="He",
+                        init_type="StyleGAN", gain_sq_base=c["gain_sq_base"], equalized_lr=True,
+                        lrmul=c["lrmul"], include_bias=c["include_bias"])
+        perturb_zero_params(m, g)
+        x = rn(c["n"], c["ni"], c["hw"], c["hw"]).requires_grad_(True)
+        y = m(x)
+        gy = rn(*y.shape)
+        gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+        # double backward: d/dtheta of sum(gx * v) (the R1 pattern), plus first-order param grads
+        v = rn(*gx.shape)
+        (gx * v).sum().backward(retain_graph=True)
+        gg_w = m.conv2d.weight.grad.clone()
+        m.zero_grad()
+        y.backward(gy)
+        out[name] = dict(cfg=c, sd=sd_clone(m), wscale=float(m.wscale), x=x.detach(), y=y.detach(), gy=gy,
+                         gx=gx.detach(), v=v, gg_w=gg_w, grads=grads_of(m))
+
+    # LinearEx (custom_layers.py:230-291)
+    lin_cases = {
+        "linear_mapping": dict(nin=32, nout=32, gain_sq_base=2., lrmul=.01, n=8),
+        "linear_style": dict(nin=32, nout=128, gain_sq_base=1., lrmul=1., n=8),
+        "linear_dhead": dict(nin=32, nout=1, gain_sq_base=1., lrmul=1., n=8),
+        "linear_progan_fc": dict(nin=32, nout=512, gain_sq_base=2. / 16, lrmul=1., n=4),
+    }
+    for name, c in lin_cases.items():
+        torch.manual_seed(hash(name) % 1000)
+        m = cl.LinearEx(nin_feat=c["nin"], nout_feat=c["nout"], init="He", init_type="StyleGAN",
+                        gain_sq_base=c["gain_sq_base"], equalized_lr=True, lrmul=c["lrmul"])
+        perturb_zero_params(m, g)
+        x = rn(c["n"], c["nin"]).requires_grad_(True)
+        y = m(x)
+        gy = rn(*y.shape)
+        gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+        v = rn(*gx.shape)
+        (gx * v).sum().backward(retain_graph=True)
+        gg_w = m.linear.weight.grad.clone()
+        m.zero_grad()
+        y.backward(gy)
+        out[name] = dict(cfg=c, sd=sd_clone(m), wscale=float(m.wscale), x=x.detach(), y=y.detach(), gy=gy,
+                         gx=gx.detach(), v=v, gg_w=gg_w, grads=grads_of(m))
+
+    # Conv2dBias (custom_layers.py:213-226)
+    m = cl.Conv2dBias(nf=16, lrmul=1., device="cpu")
+    perturb_zero_params(m, g)
+    x = rn(2, 16, 4, 4).requires_grad_(True)
+    y = m(x); gy = rn(*y.shape); y.backward(gy)
+    out["conv2dbias"] = dict(sd=sd_clone(m), x=x.detach(), y=y.detach(), gy=gy, gx=x.grad.clone(), grads=grads_of(m))
+
+    # PixelNorm2d (custom_layers.py:81-86), 2-D (latents) and 4-D (ProGAN features)
+    pn = cl.PixelNorm2d()
+    for name, shape in (("pixelnorm_z", (8, 32)), ("pixelnorm_feat", (4, 32, 8, 8))):
+        x = rn(*shape).requires_grad_(True)
+        y = pn(x); gy = rn(*y.shape); y.backward(gy)
+        out[name] = dict(x=x.detach(), y=y.detach(), gy=gy, gx=x.grad.clone())
+
+    # blur (custom_layers.py:36-53): fwd, bwd, and double-bwd (linear -> gg = blur(v))
+    for name, shape in (("blur", (2, 16, 8, 8)), ("blur_odd", (1, 5, 6, 4))):
+        op = cl.get_blur_op("binomial", shape[1])
+        x = rn(*shape).requires_grad_(True)
+        y = op(x); gy = rn(*y.shape).requires_grad_(True)
+        gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+        v = rn(*gx.shape)
+        ggy, = torch.autograd.grad(gx, gy, v)
+        out[name] = dict(x=x.detach(), y=y.detach(), gy=gy.detach(), gx=gx.detach(), v=v, ggy=ggy)
+
+    # minibatch stddev (custom_layers.py:117-140): fwd, bwd, double-bwd wrt x and gy
+    for name, (shape, gs) in dict(mbstd_n8=((8, 16, 4, 4), 4), mbstd_n4=((4, 32, 4, 4), 4),
+                                  mbstd_n6=((6, 8, 4, 4), 4), mbstd_n1=((1, 8, 4, 4), 4),
+                                  mbstd_n16=((16, 16, 4, 4), 4)).items():
+        x = rn(*shape).requires_grad_(True)
+        y = cl.concat_mbstd_layer(x, gs)
+        gy = rn(*y.shape).requires_grad_(True)
+        if shape[0] > 1:
+            gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+            v = rn(*gx.shape)
+            ggx, ggy = torch.autograd.grad(gx, (x, gy), v, allow_unused=True)
+        else:
+            gx, = torch.autograd.grad(y, x, gy)
+            v = rn(*gx.shape); ggx = None; ggy = None
+        out[name] = dict(group_size=gs, x=x.detach(), y=y.detach(), gy=gy.detach(), gx=gx.detach(), v=v,
+                         ggx=ggx, ggy=ggy)
+
+    # InstanceNorm (custom_layers.py:98-99) + the G-layer tail Sequential(bias, lrelu, IN) and AdaIN
+    sa = ref.stylegan_arch
+    nf = 32
+    noise_mod = sa.StyleAddNoise(nf)
+    bias_mod = cl.Conv2dBias(nf, device="cpu")
+    tail = torch.nn.Sequential(bias_mod, torch.nn.LeakyReLU(.2), cl.NormalizeLayer("InstanceNorm", ni=nf))
+    perturb_zero_params(noise_mod, g); perturb_zero_params(bias_mod, g)
+    noise_mod.eval()                                     # honour the supplied noise (architectures.py:113)
+    x = rn(4, nf, 8, 8).requires_grad_(True)
+    noise = rn(4, 1, 8, 8)
+    style = rn(4, 2 * nf).requires_grad_(True)
+    t = tail(noise_mod(x, noise=noise))
+    ysyb = style.view(-1, 2, nf, 1, 1)
+    y = t * (ysyb[:, 0].contiguous().add(1)) + ysyb[:, 1].contiguous()
+    gy = rn(*y.shape)
+    y.backward(gy)
+    out["style_epilogue"] = dict(x=x.detach(), noise=noise, style=style.detach(), y=y.detach(), gy=gy,
+                                 noise_weight=noise_mod.noise_weight.detach().clone(),
+                                 bias=bias_mod.bias.detach().clone(), gx=x.grad.clone(),
+                                 gstyle=style.grad.clone(), g_noise_weight=noise_mod.noise_weight.grad.clone(),
+                                 g_bias=bias_mod.bias.grad.clone())
+
+    # D downsample tail: AvgPool2d(2,2) -> Conv2dBias -> LeakyReLU (progan/architectures.py:267-284) with 2nd order
+    bias_mod = cl.Conv2dBias(16, device="cpu"); perturb_zero_params(bias_mod, g)
+    x = rn(2, 16, 8, 8).requires_grad_(True)
+    y = torch.nn.functional.leaky_relu(bias_mod(torch.nn.functional.avg_pool2d(x, 2, 2)), .2)
+    gy = rn(*y.shape).requires_grad_(True)
+    gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+    v = rn(*gx.shape)
+    ggy, = torch.autograd.grad(gx, gy, v)
+    out["pool_bias_lrelu"] = dict(x=x.detach(), bias=bias_mod.bias.detach().clone(), y=y.detach(),
+                                  gy=gy.detach(), gx=gx.detach(), v=v, ggy=ggy)
+
+    # nearest x2 upsample / avg-pool (resnetgan/learner.py:154-164)
+    x = rn(2, 8, 4, 4).requires_grad_(True)
+    y = torch.nn.Upsample(scale_factor=2, mode="nearest")(x); gy = rn(*y.shape); y.backward(gy)
+    out["upsample2x"] = dict(x=x.detach(), y=y.detach(), gy=gy, gx=x.grad.clone())
+    return out
+
+
+# --------------------------------------------------------------------------- #
+def _patch_small(ref, fmap_max=SMALL_FMAP_MAX):
+    ref.stylegan_base.FMAP_MAX = fmap_max
+    ref.progan_base.FMAP_MAX = fmap_max
+
+
+def _unpatch(ref):
+    ref.stylegan_base.FMAP_MAX = 512
+    ref.progan_base.FMAP_MAX = 512
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def _build_style_learner(ref, res, init_res, bs, **over):
+    cfg = make_config("StyleGAN", res=res, init_res=init_res, batch_size=bs, len_latent=SMALL_FMAP_MAX,
+                      len_dlatent=SMALL_FMAP_MAX, cutoff_trunc_trick=int(np.log2(res)) - 2, **over)
+    with _quiet():
+        L = ref.stylegan_learner.StyleGANLearner(cfg)
+    return L, cfg
+
+
+def golden_style_nets(ref, res=16, bs=4, fade_in=False):
+    """StyleGenerator / StyleDiscriminator forward+backward(+R1) on the reference modules."""
+    _patch_small(ref)
+    try:
+        torch.manual_seed(7 + int(fade_in)); np.random.seed(7)
+        L, cfg = _build_style_learner(ref, res, res // 2 if fade_in else res, bs)
+        G, D = L.gen_model, L.disc_model
+        alpha = 1.0
+        if fade_in:
+            G.increase_scale(); D.increase_scale()
+            G.alpha = 0.3
+            alpha = 0.3
+        gen = torch.Generator().manual_seed(99)
+        perturb_zero_params(G, gen); perturb_zero_params(D, gen)
+        G.train(); D.train()
+        z = torch.randn(bs, cfg.len_latent, generator=gen)
+        with Tape() as tape:
+            img = G(z)
+        w_ewma = G.w_ewma.detach().clone()
+        gimg = torch.randn(img.shape, generator=gen)
+        G.zero_grad(); img.backward(gimg)
+        g_grads = grads_of(G)
+
+        x = torch.rand(bs, 3, res, res, generator=gen) * 2 - 1
+        D.zero_grad()
+        logits = D(x)
+        glog = torch.randn(logits.shape, generator=gen)
+        logits.backward(glog)
+        d_grads = grads_of(D)
+        # R1 on its own (invisible inside the whole loss at random init)
+        D.zero_grad()
+        L.batch_size = bs
+        gp = L.calc_gp(img.detach(), x)
+        gp.backward()
+        d_gp_grads = grads_of(D)
+        # grad of D output wrt image (the G-step path)
+        xi = img.detach().clone().requires_grad_(True)
+        gxi, = torch.autograd.grad(D(xi), xi, glog)
+        return dict(res=res, bs=bs, fade_in=fade_in, alpha=alpha, fmap_max=SMALL_FMAP_MAX,
+                    len_latent=cfg.len_latent, g_sd=sd_clone(G), d_sd=sd_clone(D), z=z, tape=tape.events,
+                    img=img.detach(), w_ewma=w_ewma, gimg=gimg, g_grads=g_grads, x=x, logits=logits.detach(),
+                    glog=glog, d_grads=d_grads, gp=gp.detach(), d_gp_grads=d_gp_grads, d_gx_img=gxi,
+                    lda=cfg.lda)
+    finally:
+        _unpatch(ref)
+
+
+def golden_pro_nets(ref, res=16, bs=4, fade_in=False):
+    _patch_small(ref)
+    try:
+        torch.manual_seed(11 + int(fade_in)); np.random.seed(11)
+        cfg = make_config("ProGAN", res=res, init_res=res // 2 if fade_in else res, batch_size=bs,
+                          len_latent=SMALL_FMAP_MAX)
+        with _quiet():
+            L = ref.progan_learner.ProGANLearner(cfg)
+        G, D = L.gen_model, L.disc_model
+        alpha = 1.0
+        if fade_in:
+            G.increase_scale(); D.increase_scale(); G.alpha = 0.6; alpha = 0.6
+        gen = torch.Generator().manual_seed(5)
+        perturb_zero_params(G, gen); perturb_zero_params(D, gen)
+        G.train(); D.train()
+        z = torch.randn(bs, cfg.len_latent, generator=gen)
+        img = G(z)
+        gimg = torch.randn(img.shape, generator=gen)
+        G.zero_grad(); img.backward(gimg)
+        g_grads = grads_of(G)
+        x = torch.rand(bs, 3, res, res, generator=gen) * 2 - 1
+        D.zero_grad()
+        logits = D(x); glog = torch.randn(logits.shape, generator=gen); logits.backward(glog)
+        d_grads = grads_of(D)
+        D.zero_grad()
+        L.batch_size = bs
+        with Tape() as tape:
+            gp = L.calc_gp(img.detach(), x)          # wgan-gp: draws eps via torch.rand
+        gp.backward()
+        d_gp_grads = grads_of(D)
+        return dict(res=res, bs=bs, fade_in=fade_in, alpha=alpha, fmap_max=SMALL_FMAP_MAX,
+                    len_latent=cfg.len_latent, g_sd=sd_clone(G), d_sd=sd_clone(D), z=z, img=img.detach(),
+                    gimg=gimg, g_grads=g_grads, x=x, logits=logits.detach(), glog=glog, d_grads=d_grads,
+                    gp=gp.detach(), gp_tape=tape.events, d_gp_grads=d_gp_grads, lda=cfg.lda, gamma=cfg.gamma)
+    finally:
+        _unpatch(ref)
+
+
+def golden_train_steps(ref, model="StyleGAN", res=16, bs=4, iters=2):
+    """Whole Learner.train() for `iters` main iterations (D step + G step + Adam + EWMA), unmodified loop."""
+    _patch_small(ref)
+    try:
+        torch.manual_seed(21); np.random.seed(21)
+        if model == "StyleGAN":
+            L, cfg = _build_style_learner(ref, res, res, bs)
+        else:
+            cfg = make_config("ProGAN", res=res, init_res=res, batch_size=bs, len_latent=SMALL_FMAP_MAX)
+            with _quiet():
+                L = ref.progan_learner.ProGANLearner(cfg)
+        gen = torch.Generator().manual_seed(31)
+        perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+        g0, d0 = sd_clone(L.gen_model), sd_clone(L.disc_model)
+        data = torch.rand(iters * bs, 3, res, res, generator=gen) * 2 - 1
+        ds = TensorDataset(data)
+        dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+        losses = []
+        orig_backward = torch.Tensor.backward
+
+        def rec_backward(self, *a, **k):
+            losses.append(float(self.detach()))
+            return orig_backward(self, *a, **k)
+
+        torch.Tensor.backward = rec_backward
+        try:
+            with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+                L.train(dl, num_main_iters=iters)
+        finally:
+            torch.Tensor.backward = orig_backward
+        lagged = {k: v.detach().clone() for k, v in L.lagged_params.items()}
+        out = dict(model=model, res=res, bs=bs, iters=iters, fmap_max=SMALL_FMAP_MAX, len_latent=cfg.len_latent,
+                   g_sd0=g0, d_sd0=d0, data=data, tape=tape.events, losses=losses,
+                   g_sd1=sd_clone(L.gen_model), d_sd1=sd_clone(L.disc_model), lagged=lagged, beta=float(L.beta),
+                   lr=cfg.lr_base * cfg.lr_fctr_dict[res])
+        if model == "StyleGAN":
+            out["w_ewma"] = L.gen_model.w_ewma.detach().clone()
+        return out
+    finally:
+        _unpatch(ref)
+
+
+def main():
+    ref = load_reference()
+    GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
+    jobs = {
+        "layers.pt": lambda: golden_layers(ref),
+        "style_nets_res16.pt": lambda: golden_style_nets(ref, 16, 4, False),
+        "style_nets_res16_fade.pt": lambda: golden_style_nets(ref, 16, 4, True),
+        "pro_nets_res16.pt": lambda: golden_pro_nets(ref, 16, 4, False),
+        "pro_nets_res8_fade.pt": lambda: golden_pro_nets(ref, 8, 4, True),
+        "style_train_res16.pt": lambda: golden_train_steps(ref, "StyleGAN", 16, 4, 2),
+        "pro_train_res8.pt": lambda: golden_train_steps(ref, "ProGAN", 8, 4, 2),
+    }
+    only = sys.argv[1:]
+    for name, fn in jobs.items():
+        if only and name not in only:
+            continue
+        obj = fn()
+        torch.save(obj, GOLDEN_DIR / name)
+        print(f"wrote {name}: {(GOLDEN_DIR / name).stat().st_size / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
