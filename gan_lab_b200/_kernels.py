@@ -1,0 +1,509 @@
+"""Kernel launchers: torch tensors in, torch tensors out, raw pointers across the C-ABI.
+
+Each launcher checks device/dtype/layout, allocates the outputs with torch (the caller owns all
+memory, SURVEY.md section 8b "Ownership") and enqueues the kernel on torch's current stream.
+Feature maps are logical NCHW tensors in torch.channels_last memory format (= NHWC in memory);
+RGB images are plain NCHW-contiguous; conv weights are logical OIHW in channels_last (= KRSC).
+No CPU path: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import LIB, GlbError
+
+ACT_NONE, ACT_LRELU = 0, 1
+IMPL_FP32, IMPL_TF32 = 0, 1
+
+_state = {"conv_impl": "fp32", "launches": 0}
+
+
+def set_conv_impl(mode: str):
+    """'fp32' = exact FFMA implicit GEMM everywhere; 'tf32' = tcgen05 tensor-core kernels wherever the
+    shape is covered (TF32 operands, fp32 accumulation), FFMA kernels for the rest."""
+    assert mode in ("fp32", "tf32")
+    _state["conv_impl"] = mode
+
+
+def get_conv_impl() -> str:
+    return _state["conv_impl"]
+
+
+def launch_count() -> int:
+    return _state["launches"]
+
+
+def _call(name, *args):
+    _state["launches"] += 1
+    LIB.call(name, *args)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise GlbError("gan_lab_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise GlbError(f"gan_lab_b200 kernels are fp32; got {t.dtype}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def nhwc(x: torch.Tensor) -> torch.Tensor:
+    """4-D tensor -> same logical tensor, channels_last memory (no copy if already so)."""
+    assert x.dim() == 4
+    if x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _new_nhwc(n, c, h, w, like):
+    return torch.empty((n, c, h, w), device=like.device, dtype=torch.float32, memory_format=torch.channels_last)
+
+
+def _flat(t):
+    return None if t is None else t.detach().reshape(-1).contiguous()
+
+
+# --------------------------------------------------------------------------- conv family
+def tc_covers(kind: str, N, H, W, Ci, Co, R, S, pad) -> bool:
+    """Host-side mirror of the tcgen05 kernels' shape coverage (csrc/conv_tc.cu)."""
+    if not (R == S == 3 and pad == 1):
+        return False
+    if Ci % 32 or Co % 32 or Ci < 32 or Co < 32:
+        return False
+    # M tile = 128 output pixels laid out as (images x rows x cols) boxes
+    bw = min(W, 16)
+    bh = min(H, 128 // bw)
+    bn = 128 // (bw * bh)
+    if W % bw or H % bh or N % bn:
+        return False
+    return _state.get("tc_enabled", False)
+
+
+def _impl_for(kind, N, H, W, Ci, Co, R, S, pad):
+    if _state["conv_impl"] == "tf32" and tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+        return IMPL_TF32
+    return IMPL_FP32
+
+
+def conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope):
+    _chk(x, w, bias)
+    x, w = nhwc(x), nhwc(w)
+    N, Ci, H, W = x.shape
+    Co, Ci2, R, S = w.shape
+    if Ci != Ci2:
+        raise GlbError(f"conv_fprop: channel mismatch {Ci} vs {Ci2}")
+    Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+    y = _new_nhwc(N, Co, Ho, Wo, x)
+    b = _flat(bias)
+    _call("glb_conv2d_fprop", _p(x), _p(w), _p(b), _p(y), N, H, W, Ci, Co, R, S, pad, float(alpha), float(bias_scale),
+          int(act), float(slope), _impl_for("fprop", N, H, W, Ci, Co, R, S, pad), _stream())
+    return y
+
+
+def conv_dgrad(gy, w, x_hw, pad, alpha):
+    _chk(gy, w)
+    gy, w = nhwc(gy), nhwc(w)
+    N, Co, Ho, Wo = gy.shape
+    Co2, Ci, R, S = w.shape
+    H, W = x_hw
+    if Co != Co2 or Ho != H + 2 * pad - R + 1 or Wo != W + 2 * pad - S + 1:
+        raise GlbError("conv_dgrad: shape mismatch")
+    gx = _new_nhwc(N, Ci, H, W, gy)
+    _call("glb_conv2d_dgrad", _p(gy), _p(w), _p(gx), N, H, W, Ci, Co, R, S, pad, float(alpha),
+          _impl_for("dgrad", N, H, W, Ci, Co, R, S, pad), _stream())
+    return gx
+
+
+def conv_wgrad(x, gy, rs, pad, alpha):
+    _chk(x, gy)
+    x, gy = nhwc(x), nhwc(gy)
+    N, Ci, H, W = x.shape
+    N2, Co, Ho, Wo = gy.shape
+    R, S = rs
+    if N != N2 or Ho != H + 2 * pad - R + 1 or Wo != W + 2 * pad - S + 1:
+        raise GlbError("conv_wgrad: shape mismatch")
+    gw = _new_nhwc(Co, Ci, R, S, x)
+    _call("glb_conv2d_wgrad", _p(x), _p(gy), _p(gw), N, H, W, Ci, Co, R, S, pad, float(alpha),
+          _impl_for("wgrad", N, H, W, Ci, Co, R, S, pad), _stream())
+    return gw
+
+
+# --------------------------------------------------------------------------- linear
+def linear_fwd(x, w, bias, alpha, bias_scale, act, slope):
+    _chk(x, w, bias)
+    x, w = x.contiguous(), w.contiguous()
+    M, K = x.shape
+    Nout, K2 = w.shape
+    if K != K2:
+        raise GlbError(f"linear_fwd: feature mismatch {K} vs {K2}")
+    y = torch.empty((M, Nout), device=x.device, dtype=torch.float32)
+    _call("glb_linear_fwd", _p(x), _p(w), _p(_flat(bias)), _p(y), M, K, Nout, float(alpha), float(bias_scale), int(act),
+          float(slope), _stream())
+    return y
+
+
+def linear_dgrad(gy, w, alpha):
+    _chk(gy, w)
+    gy, w = gy.contiguous(), w.contiguous()
+    M, Nout = gy.shape
+    K = w.shape[1]
+    gx = torch.empty((M, K), device=gy.device, dtype=torch.float32)
+    _call("glb_linear_dgrad", _p(gy), _p(w), _p(gx), M, K, Nout, float(alpha), _stream())
+    return gx
+
+
+def linear_wgrad(x, gy, alpha):
+    _chk(x, gy)
+    x, gy = x.contiguous(), gy.contiguous()
+    M, K = x.shape
+    Nout = gy.shape[1]
+    gw = torch.empty((Nout, K), device=x.device, dtype=torch.float32)
+    _call("glb_linear_wgrad", _p(x), _p(gy), _p(gw), M, K, Nout, float(alpha), _stream())
+    return gw
+
+
+# --------------------------------------------------------------------------- rows helpers
+def _rows(x):
+    """-> (tensor in kernel layout, P, C): 4-D channels_last or 2-D row-major, channel axis contiguous."""
+    if x.dim() == 4:
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        return x, n * h * w, c
+    x = x.contiguous()
+    return x, x.shape[0], x.shape[1]
+
+
+def bias_act_fwd(x, bias, bias_scale, act, slope):
+    _chk(x, bias)
+    x, P, C = _rows(x)
+    y = torch.empty_like(x)
+    _call("glb_bias_act_fwd", _p(x), _p(_flat(bias)), _p(y), P, C, float(bias_scale), int(act), float(slope), _stream())
+    return y
+
+
+def act_bwd(gy, y, want_bias, bias_scale, act, slope):
+    """-> (gx, gbias or None); gx = gy * act'(y)."""
+    _chk(gy, y)
+    y, P, C = _rows(y)
+    gy, _, _ = _rows(gy)
+    gb = torch.zeros(C, device=gy.device, dtype=torch.float32) if want_bias else None
+    if C % 4 == 0 and ((C // 4) > 256 or 256 % (C // 4) == 0):
+        gx = torch.empty_like(gy)
+        _call("glb_act_bwd", _p(gy), _p(y), _p(gx), _p(gb), P, C, float(bias_scale), int(act), float(slope), _stream())
+        return gx, gb
+    raise GlbError(f"act_bwd: unsupported channel count {C}")
+
+
+def colsum(x, scale):
+    _chk(x)
+    x, P, C = _rows(x)
+    out = torch.zeros(C, device=x.device, dtype=torch.float32)
+    _call("glb_colsum", _p(x), _p(out), P, C, float(scale), _stream())
+    return out
+
+
+def axpby(a, b, alpha, beta):
+    _chk(a, b)
+    if a.dim() == 4 and a.shape[1] > 3:
+        a = nhwc(a)
+        b = nhwc(b) if b is not None else None
+    else:
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+    y = torch.empty_like(a)
+    _call("glb_axpby", _p(a), _p(b), _p(y), a.numel(), float(alpha), float(beta), _stream())
+    return y
+
+
+def scale_by(x, s_dev, scale):
+    """y = x * scale * s_dev (device scalar tensor)."""
+    _chk(x, s_dev)
+    if not (x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))):
+        x = x.contiguous()
+    y = torch.empty_like(x)
+    _call("glb_scale_by", _p(x), _p(s_dev.reshape(-1)), _p(y), x.numel(), float(scale), _stream())
+    return y
+
+
+def sumsq(x, scale):
+    _chk(x)
+    if not (x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))):
+        x = x.contiguous()
+    out = torch.zeros((), device=x.device, dtype=torch.float32)
+    _call("glb_sumsq", _p(x), _p(out), x.numel(), float(scale), _stream())
+    return out
+
+
+def gp_norm_fwd(g, gamma, scale):
+    _chk(g)
+    g = g.contiguous()
+    N, C = g.shape[0], g.shape[1]
+    out = torch.zeros((), device=g.device, dtype=torch.float32)
+    _call("glb_gp_norm_fwd", _p(g), _p(out), N, C, g.numel() // (N * C), float(gamma), float(scale), _stream())
+    return out
+
+
+def gp_norm_bwd(g, s_dev, gamma, scale):
+    _chk(g, s_dev)
+    g = g.contiguous()
+    N, C = g.shape[0], g.shape[1]
+    gg = torch.empty_like(g)
+    _call("glb_gp_norm_bwd", _p(g), _p(s_dev.reshape(-1)), _p(gg), N, C, g.numel() // (N * C), float(gamma), float(scale), _stream())
+    return gg
+
+
+def interp_rows(a, b, eps):
+    _chk(a, b, eps)
+    a, b, eps = a.contiguous(), b.contiguous(), eps.reshape(-1).contiguous()
+    out = torch.empty_like(a)
+    _call("glb_interp_rows", _p(a), _p(b), _p(eps), _p(out), a.shape[0], a.numel() // a.shape[0], _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- norms / stencils / resampling
+def pixelnorm_fwd(x, eps):
+    _chk(x)
+    x, P, C = _rows(x)
+    y = torch.empty_like(x)
+    _call("glb_pixelnorm_fwd", _p(x), _p(y), P, C, float(eps), _stream())
+    return y
+
+
+def pixelnorm_bwd(gy, x, eps):
+    _chk(gy, x)
+    x, P, C = _rows(x)
+    gy, _, _ = _rows(gy)
+    gx = torch.empty_like(x)
+    _call("glb_pixelnorm_bwd", _p(gy), _p(x), _p(gx), P, C, float(eps), _stream())
+    return gx
+
+
+def blur3x3(x):
+    _chk(x)
+    x = nhwc(x)
+    N, C, H, W = x.shape
+    y = torch.empty_like(x)
+    _call("glb_blur3x3", _p(x), _p(y), N, H, W, C, _stream())
+    return y
+
+
+def upsample2x_fwd(x):
+    _chk(x)
+    x = nhwc(x)
+    N, C, H, W = x.shape
+    y = _new_nhwc(N, C, 2 * H, 2 * W, x)
+    _call("glb_upsample2x_fwd", _p(x), _p(y), N, H, W, C, _stream())
+    return y
+
+
+def upsample2x_bwd(gy):
+    _chk(gy)
+    gy = nhwc(gy)
+    N, C, H2, W2 = gy.shape
+    gx = _new_nhwc(N, C, H2 // 2, W2 // 2, gy)
+    _call("glb_upsample2x_bwd", _p(gy), _p(gx), N, H2 // 2, W2 // 2, C, _stream())
+    return gx
+
+
+def pool_bias_act_fwd(x, bias, bias_scale, act, slope):
+    _chk(x, bias)
+    x = nhwc(x)
+    N, C, H, W = x.shape
+    y = _new_nhwc(N, C, H // 2, W // 2, x)
+    _call("glb_pool_bias_act_fwd", _p(x), _p(_flat(bias)), _p(y), N, H, W, C, float(bias_scale), int(act), float(slope), _stream())
+    return y
+
+
+def pool_bias_act_bwd(gy, y, want_bias, bias_scale, act, slope):
+    """gy [N,C,H/2,W/2] (+ saved output y or None) -> gx [N,C,H,W] = 0.25 * gy*act'(y) broadcast, gbias."""
+    _chk(gy, y)
+    gy = nhwc(gy)
+    y = nhwc(y) if y is not None else None
+    N, C, Hh, Wh = gy.shape
+    gx = _new_nhwc(N, C, 2 * Hh, 2 * Wh, gy)
+    gb = torch.zeros(C, device=gy.device, dtype=torch.float32) if want_bias else None
+    _call("glb_pool_bias_act_bwd", _p(gy), _p(y), _p(gx), _p(gb), N, 2 * Hh, 2 * Wh, C, float(bias_scale), int(act), float(slope),
+          _stream())
+    return gx, gb
+
+
+# --------------------------------------------------------------------------- StyleGAN G-layer epilogue
+def style_epilogue_fwd(x, noise, noise_weight, bias, style, slope, eps):
+    _chk(x, noise, noise_weight, bias, style)
+    x = nhwc(x)
+    N, C, H, W = x.shape
+    noise_c = noise.contiguous() if noise is not None else None
+    style = style.contiguous()
+    out = torch.empty_like(x)
+    stats = torch.empty(N * 2 * C, device=x.device, dtype=torch.float32)
+    work = torch.empty(LIB.fn("glb_style_epilogue_work_floats")(N, H, W, C), device=x.device, dtype=torch.float32)
+    _call("glb_style_epilogue_fwd", _p(x), _p(noise_c), _p(_flat(noise_weight)), _p(_flat(bias)), _p(style), _p(out), _p(stats),
+          _p(work), N, H, W, C, float(slope), float(eps), _stream())
+    return out, stats
+
+
+def style_epilogue_bwd(gout, x, noise, noise_weight, bias, style, stats, slope):
+    _chk(gout, x, noise, noise_weight, bias, style, stats)
+    x, gout = nhwc(x), nhwc(gout)
+    N, C, H, W = x.shape
+    noise_c = noise.contiguous() if noise is not None else None
+    style = style.contiguous()
+    gx = torch.empty_like(x)
+    gstyle = torch.empty_like(style)
+    g_nw = torch.zeros(C, device=x.device, dtype=torch.float32) if noise_weight is not None else None
+    g_b = torch.zeros(C, device=x.device, dtype=torch.float32) if bias is not None else None
+    work = torch.empty(LIB.fn("glb_style_epilogue_work_floats")(N, H, W, C), device=x.device, dtype=torch.float32)
+    _call("glb_style_epilogue_bwd", _p(gout), _p(x), _p(noise_c), _p(_flat(noise_weight)), _p(_flat(bias)), _p(style), _p(stats),
+          _p(gx), _p(gstyle), _p(g_nw), _p(g_b), _p(work), N, H, W, C, float(slope), _stream())
+    return gx, gstyle, g_nw, g_b
+
+
+# --------------------------------------------------------------------------- minibatch stddev
+def mbstd_fwd(x, group):
+    _chk(x)
+    x = nhwc(x)
+    N, C, H, W = x.shape
+    y = _new_nhwc(N, C + 1, H, W, x)
+    _call("glb_mbstd_fwd", _p(x), _p(y), N, H, W, C, group, _stream())
+    return y
+
+
+def mbstd_bwd(gy, x, group):
+    _chk(gy, x)
+    x, gy = nhwc(x), nhwc(gy)
+    N, C, H, W = x.shape
+    gx = torch.empty_like(x)
+    _call("glb_mbstd_bwd", _p(gy), _p(x), _p(gx), N, H, W, C, group, _stream())
+    return gx
+
+
+def mbstd_bwdbwd(v, gy, x, group):
+    _chk(v, gy, x)
+    x, gy, v = nhwc(x), nhwc(gy), nhwc(v)
+    N, C, H, W = x.shape
+    ggx = torch.empty_like(x)
+    ggy = torch.empty_like(gy)
+    _call("glb_mbstd_bwdbwd", _p(v), _p(gy), _p(x), _p(ggx), _p(ggy), N, H, W, C, group, _stream())
+    return ggx, ggy
+
+
+# --------------------------------------------------------------------------- RGB 1x1 convs
+def rgb_expand(img, w, ws_j, ws_c, C, bias, pool, alpha, bias_scale, act, slope):
+    """img NCHW [N,3,IH,IW] -> NHWC features [N,C,IH/(1+pool),IW/(1+pool)]."""
+    _chk(img, w, bias)
+    img = img.contiguous()
+    w = w.contiguous()
+    N, three, IH, IW = img.shape
+    if three != 3:
+        raise GlbError("rgb_expand: image must have 3 channels")
+    H, W = (IH // 2, IW // 2) if pool else (IH, IW)
+    y = _new_nhwc(N, C, H, W, img)
+    _call("glb_rgb_expand", _p(img), _p(w), ws_j, ws_c, _p(_flat(bias)), _p(y), N, H, W, C, int(pool), float(alpha),
+          float(bias_scale), int(act), float(slope), _stream())
+    return y
+
+
+def rgb_contract(x, w, ws_j, ws_c, bias, pool, alpha, bias_scale):
+    """NHWC features [N,C,H,W] -> img NCHW [N,3,H*(1+pool),W*(1+pool)]."""
+    _chk(x, w, bias)
+    x = nhwc(x)
+    w = w.contiguous()
+    N, C, H, W = x.shape
+    s = 2 if pool else 1
+    img = torch.empty((N, 3, H * s, W * s), device=x.device, dtype=torch.float32)
+    _call("glb_rgb_contract", _p(x), _p(w), ws_j, ws_c, _p(_flat(bias)), _p(img), N, H, W, C, int(pool), float(alpha),
+          float(bias_scale), _stream())
+    return img
+
+
+def rgb_wgrad(img, g, w_shape, ws_j, ws_c, pool, alpha):
+    _chk(img, g)
+    img = img.contiguous()
+    g = nhwc(g)
+    N, C, H, W = g.shape
+    gw = torch.zeros(w_shape, device=g.device, dtype=torch.float32)
+    _call("glb_rgb_wgrad", _p(img), _p(g), _p(gw), ws_j, ws_c, N, H, W, C, int(pool), float(alpha), _stream())
+    return gw
+
+
+def plane_sum(img, scale):
+    _chk(img)
+    img = img.contiguous()
+    N, C = img.shape[0], img.shape[1]
+    out = torch.zeros(C, device=img.device, dtype=torch.float32)
+    _call("glb_plane_sum", _p(img), _p(out), N, C, img.numel() // (N * C), float(scale), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- image-space fade-in
+def fade_up_blend(lo, hi, alpha):
+    _chk(lo, hi)
+    lo, hi = lo.contiguous(), hi.contiguous()
+    N, C, H, W = hi.shape
+    out = torch.empty_like(hi)
+    _call("glb_fade_up_blend", _p(lo), _p(hi), _p(out), N, C, H, W, float(alpha), _stream())
+    return out
+
+
+def fade_up_blend_bwd(gout, alpha):
+    _chk(gout)
+    gout = gout.contiguous()
+    N, C, H, W = gout.shape
+    glo = torch.empty((N, C, H // 2, W // 2), device=gout.device, dtype=torch.float32)
+    ghi = torch.empty_like(gout)
+    _call("glb_fade_up_blend_bwd", _p(gout), _p(glo), _p(ghi), N, C, H, W, float(alpha), _stream())
+    return glo, ghi
+
+
+def fade_real(x, alpha):
+    _chk(x)
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    out = torch.empty_like(x)
+    _call("glb_fade_real", _p(x), _p(out), N, C, H, W, float(alpha), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- losses / misc
+LOSS_KIND = {"wgan": 0, "nonsaturating": 1, "minimax": 2}
+
+
+def d_logit_loss(d_gen, d_real, kind, eps_drift):
+    _chk(d_gen, d_real)
+    d_gen, d_real = d_gen.contiguous(), d_real.contiguous()
+    n = d_gen.numel()
+    loss = torch.empty((), device=d_gen.device, dtype=torch.float32)
+    gg, gr = torch.empty_like(d_gen), torch.empty_like(d_real)
+    _call("glb_d_logit_loss", _p(d_gen), _p(d_real), _p(loss), _p(gg), _p(gr), n, LOSS_KIND[kind], float(eps_drift), _stream())
+    return loss, gg, gr
+
+
+def g_logit_loss(d_out, kind):
+    _chk(d_out)
+    d_out = d_out.contiguous()
+    loss = torch.empty((), device=d_out.device, dtype=torch.float32)
+    g = torch.empty_like(d_out)
+    _call("glb_g_logit_loss", _p(d_out), _p(loss), _p(g), d_out.numel(), LOSS_KIND[kind], _stream())
+    return loss, g
+
+
+def w_ewma_update(w, ewma, beta):
+    """In place on `ewma` (beta == 0 initialises it with the batch mean)."""
+    _chk(w, ewma)
+    w = w.contiguous()
+    _call("glb_w_ewma", _p(w), _p(ewma), w.shape[0], w.shape[1], float(beta), _stream())
+    return ewma
+
+
+def adam_ewma_multi(ptr_table, sizes, T, max_size, hyper, beta1, beta2, eps, wd, ewma_beta, ewma_mode):
+    _call("glb_adam_ewma_multi", _p(ptr_table), _p(sizes), T, max_size, _p(hyper), float(beta1), float(beta2), float(eps),
+          float(wd), float(ewma_beta), int(ewma_mode), _stream())

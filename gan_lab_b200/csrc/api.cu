@@ -1,0 +1,50 @@
+// C-ABI plumbing: error string, version, implementation dispatch of the convolution family.
+#include "common.cuh"
+
+namespace glb {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int conv_fprop_simt(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, float, float, int,
+                    float, cudaStream_t);
+int conv_dgrad_simt(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
+int conv_wgrad_simt(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
+int conv_fprop_tc(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, float, float, int,
+                  float, cudaStream_t);
+int conv_dgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
+int conv_wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
+}  // namespace glb
+
+extern "C" const char* glb_last_error(void) { return glb::g_last_error.c_str(); }
+extern "C" int glb_version(void) { return 100; }
+
+extern "C" int glb_tc_available(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int glb_conv2d_fprop(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
+                                int R, int S, int pad, float alpha, float bias_scale, int act, float slope, int impl,
+                                glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_fprop");
+  if (impl == GLB_IMPL_TF32)
+    return glb::conv_fprop_tc(x, w, bias, y, N, H, W, Ci, Co, R, S, pad, alpha, bias_scale, act, slope, (cudaStream_t)stream);
+  return glb::conv_fprop_simt(x, w, bias, y, N, H, W, Ci, Co, R, S, pad, alpha, bias_scale, act, slope, (cudaStream_t)stream);
+}
+
+extern "C" int glb_conv2d_dgrad(const float* gy, const float* w, float* gx, int N, int H, int W, int Ci, int Co, int R, int S,
+                                int pad, float alpha, int impl, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_dgrad");
+  if (impl == GLB_IMPL_TF32) return glb::conv_dgrad_tc(gy, w, gx, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
+  return glb::conv_dgrad_simt(gy, w, gx, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
+}
+
+extern "C" int glb_conv2d_wgrad(const float* x, const float* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S,
+                                int pad, float alpha, int impl, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_wgrad");
+  if (impl == GLB_IMPL_TF32) return glb::conv_wgrad_tc(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
+  return glb::conv_wgrad_simt(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
+}

@@ -1,0 +1,852 @@
+// Bandwidth-bound "glue" kernels of the G/D training step: fused, 128-bit vectorised, coalesced (NHWC: the
+// channel axis is the contiguous one), warp-shuffle / shared-memory reductions.  Each kernel names the ATen
+// call sites of the reference it replaces; roofline = HBM bandwidth.
+#include "common.cuh"
+
+namespace glb {
+namespace {
+
+constexpr int TPB = 256;
+
+// ------------------------------------------------------------------------------------------------
+// bias + activation (Conv2dBias + LeakyReLU: reference utils/custom_layers.py:222-226 + shared nn.LeakyReLU)
+// ------------------------------------------------------------------------------------------------
+__global__ void bias_act_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ bias, float4* __restrict__ y,
+                                    int64_t n4, int C4, float bias_scale, int act, float slope) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = ldg_stream(x + i);
+    if (bias != nullptr) {
+      const float4 b = __ldg(bias + (i % C4));
+      v.x += bias_scale * b.x; v.y += bias_scale * b.y; v.z += bias_scale * b.z; v.w += bias_scale * b.w;
+    }
+    v.x = act_apply(v.x, act, slope); v.y = act_apply(v.y, act, slope);
+    v.z = act_apply(v.z, act, slope); v.w = act_apply(v.w, act, slope);
+    stg_stream(y + i, v);
+  }
+}
+
+// gx = gy * act'(y); optional per-channel reduction of gx into gbias (atomics after block reduce).
+// Block layout: threads cover (rows x C4) with C4 quads contiguous; requires blockDim % C4 == 0 or C4 % blockDim == 0.
+__global__ void act_bwd_kernel(const float4* __restrict__ gy, const float4* __restrict__ y, float4* __restrict__ gx,
+                               float* __restrict__ gbias, int64_t P, int C4, float bias_scale, int act, float slope) {
+  extern __shared__ float4 red[];
+  const int tid = threadIdx.x;
+  // column-quads handled by this thread: if C4 <= blockDim: one quad (tid % C4), rows strided by blockDim / C4
+  // else: quads tid, tid + blockDim, ... and one row at a time.
+  if (C4 <= (int)blockDim.x) {
+    const int q = tid % C4, rl = tid / C4, rows_per_it = blockDim.x / C4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < rows_per_it) {
+      for (int64_t p = (int64_t)blockIdx.x * rows_per_it + rl; p < P; p += (int64_t)gridDim.x * rows_per_it) {
+        const int64_t i = p * C4 + q;
+        const float4 g = ldg_stream(gy + i);
+        float4 o;
+        if (y != nullptr) {
+          const float4 yy = ldg_stream(y + i);
+          o.x = g.x * act_grad(yy.x, act, slope); o.y = g.y * act_grad(yy.y, act, slope);
+          o.z = g.z * act_grad(yy.z, act, slope); o.w = g.w * act_grad(yy.w, act, slope);
+        } else {
+          o = g;
+        }
+        if (gx != nullptr) stg_stream(gx + i, o);
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+    }
+    if (gbias != nullptr) {
+      red[tid] = s;
+      __syncthreads();
+      if (tid < C4) {
+        float4 t = red[tid];
+        for (int r = 1; r < rows_per_it; ++r) {
+          const float4 u = red[r * C4 + tid];
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        atomicAdd(gbias + 4 * tid + 0, bias_scale * t.x); atomicAdd(gbias + 4 * tid + 1, bias_scale * t.y);
+        atomicAdd(gbias + 4 * tid + 2, bias_scale * t.z); atomicAdd(gbias + 4 * tid + 3, bias_scale * t.w);
+      }
+    }
+  } else {
+    for (int q = tid; q < C4; q += blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
+        const int64_t i = p * C4 + q;
+        const float4 g = ldg_stream(gy + i);
+        float4 o;
+        if (y != nullptr) {
+          const float4 yy = ldg_stream(y + i);
+          o.x = g.x * act_grad(yy.x, act, slope); o.y = g.y * act_grad(yy.y, act, slope);
+          o.z = g.z * act_grad(yy.z, act, slope); o.w = g.w * act_grad(yy.w, act, slope);
+        } else {
+          o = g;
+        }
+        if (gx != nullptr) stg_stream(gx + i, o);
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+      if (gbias != nullptr) {
+        atomicAdd(gbias + 4 * q + 0, bias_scale * s.x); atomicAdd(gbias + 4 * q + 1, bias_scale * s.y);
+        atomicAdd(gbias + 4 * q + 2, bias_scale * s.z); atomicAdd(gbias + 4 * q + 3, bias_scale * s.w);
+      }
+    }
+  }
+}
+
+// scalar fallback of the column sum for C % 4 != 0 (e.g. 3-channel or 1-channel rows)
+__global__ void colsum_scalar_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t P, int C, float scale) {
+  for (int c = blockIdx.y; c < C; c += gridDim.y) {
+    float s = 0.f;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) s += x[p * C + c];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + c, scale * s);
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n,
+                             float alpha, float beta) {
+  const int64_t n4 = n >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t i = t0; i < n4; i += stride) {
+    float4 u = ldg_stream(a4 + i), o;
+    if (b != nullptr) {
+      const float4 v = ldg_stream(b4 + i);
+      o.x = alpha * u.x + beta * v.x; o.y = alpha * u.y + beta * v.y; o.z = alpha * u.z + beta * v.z; o.w = alpha * u.w + beta * v.w;
+    } else {
+      o.x = alpha * u.x; o.y = alpha * u.y; o.z = alpha * u.z; o.w = alpha * u.w;
+    }
+    stg_stream(y4 + i, o);
+  }
+  for (int64_t i = (n4 << 2) + t0; i < n; i += stride) y[i] = alpha * a[i] + (b != nullptr ? beta * b[i] : 0.f);
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, float scale) {
+  __shared__ float red[TPB / 32];
+  float s = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 v = ldg_stream(x4 + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int64_t i = (n4 << 2) + t0; i < n; i += stride) s += x[i] * x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < TPB / 32) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, scale * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PixelNorm (reference utils/custom_layers.py:85-86: pow, mean, add, rsqrt, mul = 5 ATen kernels -> 1)
+// one warp per pixel row; C up to 1024 kept in registers (C4 <= 8 quads per lane), else re-read.
+// ------------------------------------------------------------------------------------------------
+template <int QPL>  // quads per lane
+__global__ void pixelnorm_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t P, int C4, float invC, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < P; p += nwarps) {
+    float4 v[QPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < QPL; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4) {
+        v[i] = ldg_stream(x + p * C4 + q);
+        s += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    s = warp_sum(s);
+    const float r = rsqrtf(s * invC + eps);
+#pragma unroll
+    for (int i = 0; i < QPL; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4) stg_stream(y + p * C4 + q, make_float4(v[i].x * r, v[i].y * r, v[i].z * r, v[i].w * r));
+    }
+  }
+}
+
+// y = x*r, r = (mean(x^2)+eps)^-1/2 ;  gx = r*gy - x * r^3 * mean(gy*x)
+template <int QPL>
+__global__ void pixelnorm_bwd_kernel(const float4* __restrict__ gy, const float4* __restrict__ x, float4* __restrict__ gx,
+                                     int64_t P, int C4, float invC, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < P; p += nwarps) {
+    float4 v[QPL], g[QPL];
+    float s = 0.f, d = 0.f;
+#pragma unroll
+    for (int i = 0; i < QPL; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4) {
+        v[i] = ldg_stream(x + p * C4 + q);
+        g[i] = ldg_stream(gy + p * C4 + q);
+        s += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        d += v[i].x * g[i].x + v[i].y * g[i].y + v[i].z * g[i].z + v[i].w * g[i].w;
+      }
+    }
+    s = warp_sum(s); d = warp_sum(d);
+    const float r = rsqrtf(s * invC + eps);
+    const float k = r * r * r * d * invC;
+#pragma unroll
+    for (int i = 0; i < QPL; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4)
+        stg_stream(gx + p * C4 + q, make_float4(r * g[i].x - k * v[i].x, r * g[i].y - k * v[i].y,
+                                                r * g[i].z - k * v[i].z, r * g[i].w - k * v[i].w));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 binomial blur, NHWC (reference get_blur_op: depthwise F.conv2d groups=C, utils/custom_layers.py:50-51).
+// Each thread produces one channel-quad of one pixel from its 3x3 neighbourhood; neighbouring threads
+// share rows through L1 (the 9 taps of adjacent pixels overlap 6/9), so DRAM traffic stays ~8 B/elem.
+// ------------------------------------------------------------------------------------------------
+__global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4) {
+  const int64_t total = (int64_t)N * H * W * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4);
+    int64_t t = i / C4;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int hh = h + dy;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ww = w + dx;
+        if (ww < 0 || ww >= W) continue;
+        const float k = (float)((2 - (dy != 0)) * (2 - (dx != 0))) * 0.0625f;
+        const float4 v = __ldg(x + (((int64_t)n * H + hh) * W + ww) * C4 + q);
+        acc.x = fmaf(k, v.x, acc.x); acc.y = fmaf(k, v.y, acc.y); acc.z = fmaf(k, v.z, acc.z); acc.w = fmaf(k, v.w, acc.w);
+      }
+    }
+    stg_stream(y + i, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest x2 upsample and its adjoint; 2x2 avg-pool (+bias+act) and its backward
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4) {
+  // one thread per INPUT quad: read once, write 4 output pixels
+  const int64_t total = (int64_t)N * H * W * C4;
+  const int OW = 2 * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4);
+    int64_t t = i / C4;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int64_t n = t / H;
+    const float4 v = ldg_stream(x + i);
+    float4* o = y + ((n * 2 * H + 2 * h) * OW + 2 * w) * C4 + q;
+    stg_stream(o, v); stg_stream(o + C4, v);
+    stg_stream(o + (int64_t)OW * C4, v); stg_stream(o + (int64_t)OW * C4 + C4, v);
+  }
+}
+
+__global__ void pool2x2_kernel(const float4* __restrict__ x, const float4* __restrict__ bias, float4* __restrict__ y,
+                               int N, int H, int W, int C4, float mult, float bias_scale, int act, float slope) {
+  // x [N,H,W,C] -> y [N,H/2,W/2,C]: y = act(mult * sum_2x2(x) + bias_scale*bias); mult = .25 (avg) or 1 (upsample adjoint)
+  const int OH = H / 2, OW = W / 2;
+  const int64_t total = (int64_t)N * OH * OW * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4);
+    int64_t t = i / C4;
+    const int w = (int)(t % OW); t /= OW;
+    const int h = (int)(t % OH);
+    const int64_t n = t / OH;
+    const float4* p = x + ((n * H + 2 * h) * W + 2 * w) * C4 + q;
+    const float4 a = ldg_stream(p), b = ldg_stream(p + C4), c = ldg_stream(p + (int64_t)W * C4), d = ldg_stream(p + (int64_t)W * C4 + C4);
+    float4 v = make_float4(mult * (a.x + b.x + c.x + d.x), mult * (a.y + b.y + c.y + d.y),
+                           mult * (a.z + b.z + c.z + d.z), mult * (a.w + b.w + c.w + d.w));
+    if (bias != nullptr) {
+      const float4 bb = __ldg(bias + q);
+      v.x += bias_scale * bb.x; v.y += bias_scale * bb.y; v.z += bias_scale * bb.z; v.w += bias_scale * bb.w;
+    }
+    v.x = act_apply(v.x, act, slope); v.y = act_apply(v.y, act, slope);
+    v.z = act_apply(v.z, act, slope); v.w = act_apply(v.w, act, slope);
+    stg_stream(y + i, v);
+  }
+}
+
+// gx [N,H,W,C] = 0.25 * gy * act'(y) broadcast to the 2x2 window; gbias += bias_scale * sum(gy*act'(y))
+__global__ void pool_bias_act_bwd_kernel(const float4* __restrict__ gy, const float4* __restrict__ y, float4* __restrict__ gx,
+                                         float* __restrict__ gbias, int N, int H, int W, int C4, float bias_scale, int act,
+                                         float slope) {
+  extern __shared__ float4 red[];
+  const int OH = H / 2, OW = W / 2;
+  const int64_t P = (int64_t)N * OH * OW;
+  const int tid = threadIdx.x;
+  const int lanes = min(C4, (int)blockDim.x);
+  const int rows_per_it = blockDim.x / lanes;
+  const int rl = tid / lanes;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < rows_per_it) {
+    for (int q = tid % lanes; q < C4; q += lanes) {
+      s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t p = (int64_t)blockIdx.x * rows_per_it + rl; p < P; p += (int64_t)gridDim.x * rows_per_it) {
+        const int64_t i = p * C4 + q;
+        const float4 g = ldg_stream(gy + i);
+        float4 o = g;
+        if (y != nullptr) {
+          const float4 yy = ldg_stream(y + i);
+          o.x = g.x * act_grad(yy.x, act, slope); o.y = g.y * act_grad(yy.y, act, slope);
+          o.z = g.z * act_grad(yy.z, act, slope); o.w = g.w * act_grad(yy.w, act, slope);
+        }
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        const int w = (int)(p % OW);
+        const int64_t t = p / OW;
+        const int h = (int)(t % OH);
+        const int64_t n = t / OH;
+        const float4 v = make_float4(.25f * o.x, .25f * o.y, .25f * o.z, .25f * o.w);
+        float4* dst = gx + ((n * H + 2 * h) * W + 2 * w) * C4 + q;
+        stg_stream(dst, v); stg_stream(dst + C4, v);
+        stg_stream(dst + (int64_t)W * C4, v); stg_stream(dst + (int64_t)W * C4 + C4, v);
+      }
+      if (gbias != nullptr && C4 > lanes) {  // wide-channel case: one row per block iteration, direct atomics
+        atomicAdd(gbias + 4 * q + 0, bias_scale * s.x); atomicAdd(gbias + 4 * q + 1, bias_scale * s.y);
+        atomicAdd(gbias + 4 * q + 2, bias_scale * s.z); atomicAdd(gbias + 4 * q + 3, bias_scale * s.w);
+      }
+    }
+  }
+  if (gbias != nullptr && C4 <= lanes) {
+    red[tid] = (rl < rows_per_it) ? s : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (tid < C4) {
+      float4 t = red[tid];
+      for (int r = 1; r < rows_per_it; ++r) {
+        const float4 u = red[r * C4 + tid];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      atomicAdd(gbias + 4 * tid + 0, bias_scale * t.x); atomicAdd(gbias + 4 * tid + 1, bias_scale * t.y);
+      atomicAdd(gbias + 4 * tid + 2, bias_scale * t.z); atomicAdd(gbias + 4 * tid + 3, bias_scale * t.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// image-space fade-in helpers (NCHW)
+// ------------------------------------------------------------------------------------------------
+__global__ void fade_up_blend_kernel(const float* __restrict__ lo, const float* __restrict__ hi, float* __restrict__ out,
+                                     int64_t planes, int H, int W, float alpha) {
+  const int64_t total = planes * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    int64_t t = i / W;
+    const int h = (int)(t % H);
+    const int64_t pl = t / H;
+    const float l = __ldg(lo + (pl * (H / 2) + h / 2) * (W / 2) + w / 2);
+    out[i] = (1.f - alpha) * l + alpha * hi[i];
+  }
+}
+
+__global__ void fade_up_blend_bwd_kernel(const float* __restrict__ gout, float* __restrict__ glo, float* __restrict__ ghi,
+                                         int64_t planes, int H, int W, float alpha) {
+  // one thread per LOW-res pixel
+  const int LH = H / 2, LW = W / 2;
+  const int64_t total = planes * LH * LW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % LW);
+    int64_t t = i / LW;
+    const int h = (int)(t % LH);
+    const int64_t pl = t / LH;
+    const int64_t o = (pl * H + 2 * h) * W + 2 * w;
+    const float a = gout[o], b = gout[o + 1], c = gout[o + W], d = gout[o + W + 1];
+    glo[i] = (1.f - alpha) * (a + b + c + d);
+    ghi[o] = alpha * a; ghi[o + 1] = alpha * b; ghi[o + W] = alpha * c; ghi[o + W + 1] = alpha * d;
+  }
+}
+
+__global__ void fade_real_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t planes, int H, int W, float alpha) {
+  const int LH = H / 2, LW = W / 2;
+  const int64_t total = planes * LH * LW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % LW);
+    int64_t t = i / LW;
+    const int h = (int)(t % LH);
+    const int64_t pl = t / LH;
+    const int64_t o = (pl * H + 2 * h) * W + 2 * w;
+    const float a = x[o], b = x[o + 1], c = x[o + W], d = x[o + W + 1];
+    const float m = (1.f - alpha) * (0.25f * (a + b + c + d));
+    out[o] = m + alpha * a; out[o + 1] = m + alpha * b; out[o + W] = m + alpha * c; out[o + W + 1] = m + alpha * d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// logit losses (single block; n = batch size)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void d_logit_loss_kernel(const float* __restrict__ dg, const float* __restrict__ dr, float* __restrict__ loss,
+                                    float* __restrict__ gg, float* __restrict__ gr, int n, int kind, float eps_drift) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const float inv = 1.f / n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = dg[i], b = dr[i];
+    float l, ga, gb;
+    if (kind == 0) { l = a - b; ga = 1.f; gb = -1.f; }           // wgan: (d_gen - d_real).mean()
+    else { l = softplus_f(a) + softplus_f(-b); ga = sigmoid_f(a); gb = -sigmoid_f(-b); }  // BCE(gen,0)+BCE(real,1)
+    l += eps_drift * b * b; gb += 2.f * eps_drift * b;
+    s += l;
+    gg[i] = ga * inv; gr[i] = gb * inv;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) loss[0] = s * inv;
+  }
+}
+
+__global__ void g_logit_loss_kernel(const float* __restrict__ d, float* __restrict__ loss, float* __restrict__ g, int n, int kind) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const float inv = 1.f / n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = d[i];
+    float l, ga;
+    if (kind == 0) { l = -a; ga = -1.f; }                                  // wgan
+    else if (kind == 1) { l = softplus_f(-a); ga = -sigmoid_f(-a); }       // nonsaturating: BCE(out, 1)
+    else { l = -softplus_f(a); ga = -sigmoid_f(a); }                       // minimax: -BCE(out, 0)
+    s += l;
+    g[i] = ga * inv;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) loss[0] = s * inv;
+  }
+}
+
+__global__ void w_ewma_kernel(const float* __restrict__ w, float* __restrict__ ewma, int M, int K, float beta) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += w[(int64_t)m * K + k];
+  s /= (float)M;
+  ewma[k] = (beta == 0.f) ? s : s * (1.f - beta) + ewma[k] * beta;
+}
+
+// ------------------------------------------------------------------------------------------------
+// minibatch stddev (reference utils/custom_layers.py:117-140); one block per group of `G` samples.
+// location index l runs over D = H*W*C positions of one sample (NHWC order).
+// ------------------------------------------------------------------------------------------------
+constexpr int MB_MAXG = 32;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) t = warp_sum(t);
+  if (threadIdx.x == 0) red[0] = t;
+  __syncthreads();
+  t = red[0];
+  return t;
+}
+
+__global__ void mbstd_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C, int G) {
+  __shared__ float red[32];
+  const int g = blockIdx.x;
+  const int64_t D = (int64_t)HW * C;
+  const float* xg = x + (int64_t)g * G * D;
+  float s = 0.f;
+  if (G > 1) {
+    for (int64_t l = threadIdx.x; l < D; l += blockDim.x) {
+      float mu = 0.f;
+      for (int j = 0; j < G; ++j) mu += xg[j * D + l];
+      mu /= (float)G;
+      float ss = 0.f;
+      for (int j = 0; j < G; ++j) { const float d = xg[j * D + l] - mu; ss += d * d; }
+      s += sqrtf(ss / (float)(G - 1) + 1e-8f);
+    }
+    s = block_sum(s, red) / (float)D;
+  }
+  float* yg = y + (int64_t)g * G * HW * (C + 1);
+  const int64_t tot = (int64_t)G * HW * (C + 1);
+  for (int64_t i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int c = (int)(i % (C + 1));
+    const int64_t px = i / (C + 1);
+    yg[i] = (c < C) ? xg[px * C + c] : s;
+  }
+}
+
+__global__ void mbstd_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, float* __restrict__ gx, int HW, int C,
+                                 int G) {
+  __shared__ float red[32];
+  const int g = blockIdx.x;
+  const int64_t D = (int64_t)HW * C;
+  const float* xg = x + (int64_t)g * G * D;
+  const float* gyg = gy + (int64_t)g * G * HW * (C + 1);
+  float* gxg = gx + (int64_t)g * G * D;
+  float gsd = 0.f;
+  if (G > 1) {
+    for (int64_t px = threadIdx.x; px < (int64_t)G * HW; px += blockDim.x) gsd += gyg[px * (C + 1) + C];
+    gsd = block_sum(gsd, red);
+  }
+  const float a = (G > 1) ? gsd / ((float)(G - 1) * (float)D) : 0.f;
+  for (int64_t l = threadIdx.x; l < D; l += blockDim.x) {
+    const int64_t px = l / C;
+    const int c = (int)(l % C);
+    float xv[MB_MAXG];
+    float mu = 0.f;
+    for (int j = 0; j < G; ++j) { xv[j] = xg[j * D + l]; mu += xv[j]; }
+    mu /= (float)G;
+    float ss = 0.f;
+    for (int j = 0; j < G; ++j) { xv[j] -= mu; ss += xv[j] * xv[j]; }
+    const float inv_sigma = (G > 1) ? rsqrtf(ss / (float)(G - 1) + 1e-8f) : 0.f;
+    for (int j = 0; j < G; ++j)
+      gxg[j * D + l] = gyg[((int64_t)j * HW + px) * (C + 1) + c] + a * xv[j] * inv_sigma;
+  }
+}
+
+// double backward: inputs v (cotangent of gx), gy, x  ->  ggx (wrt x), ggy (wrt gy)
+__global__ void mbstd_bwdbwd_kernel(const float* __restrict__ v, const float* __restrict__ gy, const float* __restrict__ x,
+                                    float* __restrict__ ggx, float* __restrict__ ggy, int HW, int C, int G) {
+  __shared__ float red[32];
+  const int g = blockIdx.x;
+  const int64_t D = (int64_t)HW * C;
+  const float* xg = x + (int64_t)g * G * D;
+  const float* vg = v + (int64_t)g * G * D;
+  const float* gyg = gy + (int64_t)g * G * HW * (C + 1);
+  float* ggxg = ggx + (int64_t)g * G * D;
+  float* ggyg = ggy + (int64_t)g * G * HW * (C + 1);
+  float gsd = 0.f, T = 0.f;
+  const float aD = (G > 1) ? 1.f / ((float)(G - 1) * (float)D) : 0.f;
+  if (G > 1) {
+    for (int64_t px = threadIdx.x; px < (int64_t)G * HW; px += blockDim.x) gsd += gyg[px * (C + 1) + C];
+    gsd = block_sum(gsd, red);
+  }
+  for (int64_t l = threadIdx.x; l < D; l += blockDim.x) {
+    float d[MB_MAXG], vv[MB_MAXG];
+    float mu = 0.f, vbar = 0.f;
+    for (int j = 0; j < G; ++j) { d[j] = xg[j * D + l]; vv[j] = vg[j * D + l]; mu += d[j]; vbar += vv[j]; }
+    mu /= (float)G; vbar /= (float)G;
+    float ss = 0.f, vd = 0.f;
+    for (int j = 0; j < G; ++j) { d[j] -= mu; ss += d[j] * d[j]; vd += vv[j] * d[j]; }
+    if (G > 1) {
+      const float is = rsqrtf(ss / (float)(G - 1) + 1e-8f);
+      const float is3 = is * is * is / (float)(G - 1);
+      T += vd * is * aD;
+      for (int j = 0; j < G; ++j) ggxg[j * D + l] = gsd * aD * ((vv[j] - vbar) * is - vd * d[j] * is3);
+    } else {
+      for (int j = 0; j < G; ++j) ggxg[j * D + l] = 0.f;
+    }
+  }
+  T = block_sum(T, red);
+  const int64_t tot = (int64_t)G * HW * (C + 1);
+  for (int64_t i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int c = (int)(i % (C + 1));
+    const int64_t px = i / (C + 1);
+    ggyg[i] = (c < C) ? vg[px * C + c] : T;
+  }
+}
+
+}  // namespace
+}  // namespace glb
+
+using namespace glb;
+
+#define REQ(cond, msg) do { if (!(cond)) return glb::shape_fail(msg); } while (0)
+
+extern "C" int glb_bias_act_fwd(const float* x, const float* bias, float* y, int64_t P, int C, float bias_scale, int act,
+                                float slope, glb_stream_t stream) {
+  REQ(C % 4 == 0 && P > 0, "bias_act_fwd: C % 4 != 0");
+  const int64_t n4 = P * (C / 4);
+  bias_act_fwd_kernel<<<grid_for(n4, TPB), TPB, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)bias, (float4*)y, n4, C / 4, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("bias_act_fwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_act_bwd(const float* gy, const float* y, float* gx, float* gbias, int64_t P, int C, float bias_scale,
+                           int act, float slope, glb_stream_t stream) {
+  REQ(C % 4 == 0 && P > 0, "act_bwd: C % 4 != 0");
+  const int C4 = C / 4;
+  REQ(C4 > TPB || TPB % C4 == 0, "act_bwd: C/4 must divide 256 or exceed it");
+  const int rows_per_it = C4 <= TPB ? TPB / C4 : 1;
+  int blocks = (int)((P + rows_per_it - 1) / rows_per_it);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  act_bwd_kernel<<<blocks, TPB, TPB * sizeof(float4), (cudaStream_t)stream>>>(
+      (const float4*)gy, (const float4*)y, (float4*)gx, gbias, P, C4, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("act_bwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_colsum(const float* x, float* out, int64_t P, int C, float scale, glb_stream_t stream) {
+  REQ(P > 0 && C > 0, "colsum");
+  if (C % 4 == 0 && (C / 4 > TPB || TPB % (C / 4) == 0))
+    return glb_act_bwd(x, nullptr, nullptr, out, P, C, scale, GLB_ACT_NONE, 0.f, stream);
+  dim3 grid(grid_for(P, TPB, kNumSMs * 2), C < 64 ? C : 64);
+  colsum_scalar_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(x, out, P, C, scale);
+  GLB_CHECK_LAUNCH("colsum");
+  return GLB_OK;
+}
+
+extern "C" int glb_axpby(const float* a, const float* b, float* y, int64_t n, float alpha, float beta, glb_stream_t stream) {
+  REQ(n > 0, "axpby: n");
+  axpby_kernel<<<grid_for((n + 3) / 4, TPB), TPB, 0, (cudaStream_t)stream>>>(a, b, y, n, alpha, beta);
+  GLB_CHECK_LAUNCH("axpby");
+  return GLB_OK;
+}
+
+extern "C" int glb_scale(const float* x, float* y, int64_t n, float scale, glb_stream_t stream) {
+  return glb_axpby(x, nullptr, y, n, scale, 0.f, stream);
+}
+
+extern "C" int glb_sumsq(const float* x, float* out, int64_t n, float scale, glb_stream_t stream) {
+  REQ(n > 0, "sumsq: n");
+  sumsq_kernel<<<grid_for((n + 3) / 4, TPB, kNumSMs * 4), TPB, 0, (cudaStream_t)stream>>>(x, out, n, scale);
+  GLB_CHECK_LAUNCH("sumsq");
+  return GLB_OK;
+}
+
+template <int QPL>
+static int pixelnorm_launch(bool fwd, const float* gy, const float* x, float* out, int64_t P, int C, float eps, cudaStream_t st) {
+  const int64_t warps = P;
+  int blocks = (int)((warps * 32 + TPB - 1) / TPB);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (fwd)
+    pixelnorm_fwd_kernel<QPL><<<blocks, TPB, 0, st>>>((const float4*)x, (float4*)out, P, C / 4, 1.f / C, eps);
+  else
+    pixelnorm_bwd_kernel<QPL><<<blocks, TPB, 0, st>>>((const float4*)gy, (const float4*)x, (float4*)out, P, C / 4, 1.f / C, eps);
+  GLB_CHECK_LAUNCH("pixelnorm");
+  return GLB_OK;
+}
+
+static int pixelnorm_dispatch(bool fwd, const float* gy, const float* x, float* out, int64_t P, int C, float eps, cudaStream_t st) {
+  REQ(C % 4 == 0 && C <= 1024 && P > 0, "pixelnorm: C % 4 != 0 or C > 1024");
+  const int qpl = (C / 4 + 31) / 32;
+  if (qpl <= 1) return pixelnorm_launch<1>(fwd, gy, x, out, P, C, eps, st);
+  if (qpl <= 2) return pixelnorm_launch<2>(fwd, gy, x, out, P, C, eps, st);
+  if (qpl <= 4) return pixelnorm_launch<4>(fwd, gy, x, out, P, C, eps, st);
+  return pixelnorm_launch<8>(fwd, gy, x, out, P, C, eps, st);
+}
+
+extern "C" int glb_pixelnorm_fwd(const float* x, float* y, int64_t P, int C, float eps, glb_stream_t stream) {
+  return pixelnorm_dispatch(true, nullptr, x, y, P, C, eps, (cudaStream_t)stream);
+}
+extern "C" int glb_pixelnorm_bwd(const float* gy, const float* x, float* gx, int64_t P, int C, float eps, glb_stream_t stream) {
+  return pixelnorm_dispatch(false, gy, x, gx, P, C, eps, (cudaStream_t)stream);
+}
+
+extern "C" int glb_blur3x3(const float* x, float* y, int N, int H, int W, int C, glb_stream_t stream) {
+  REQ(C % 4 == 0, "blur3x3: C % 4 != 0");
+  const int64_t total = (int64_t)N * H * W * (C / 4);
+  blur3x3_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4);
+  GLB_CHECK_LAUNCH("blur3x3");
+  return GLB_OK;
+}
+
+extern "C" int glb_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, glb_stream_t stream) {
+  REQ(C % 4 == 0, "upsample2x: C % 4 != 0");
+  const int64_t total = (int64_t)N * H * W * (C / 4);
+  upsample2x_fwd_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4);
+  GLB_CHECK_LAUNCH("upsample2x_fwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_upsample2x_bwd(const float* gy, float* gx, int N, int H, int W, int C, glb_stream_t stream) {
+  REQ(C % 4 == 0, "upsample2x_bwd: C % 4 != 0");
+  const int64_t total = (int64_t)N * H * W * (C / 4);
+  pool2x2_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)gy, nullptr, (float4*)gx, N, 2 * H, 2 * W,
+                                                                        C / 4, 1.f, 0.f, GLB_ACT_NONE, 0.f);
+  GLB_CHECK_LAUNCH("upsample2x_bwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_pool_bias_act_fwd(const float* x, const float* bias, float* y, int N, int H, int W, int C, float bias_scale,
+                                     int act, float slope, glb_stream_t stream) {
+  REQ(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "pool_bias_act_fwd: C % 4 or odd H/W");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
+  pool2x2_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)bias, (float4*)y, N, H, W,
+                                                                        C / 4, 0.25f, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("pool_bias_act_fwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_pool_bias_act_bwd(const float* gy, const float* y, float* gx, float* gbias, int N, int H, int W, int C,
+                                     float bias_scale, int act, float slope, glb_stream_t stream) {
+  REQ(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "pool_bias_act_bwd: C % 4 or odd H/W");
+  const int C4 = C / 4;
+  REQ(C4 > TPB || TPB % C4 == 0, "pool_bias_act_bwd: C/4 must divide 256 or exceed it");
+  const int lanes = C4 < TPB ? C4 : TPB;
+  const int rows_per_it = TPB / lanes;
+  const int64_t P = (int64_t)N * (H / 2) * (W / 2);
+  int blocks = (int)((P + rows_per_it - 1) / rows_per_it);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pool_bias_act_bwd_kernel<<<blocks, TPB, TPB * sizeof(float4), (cudaStream_t)stream>>>(
+      (const float4*)gy, (const float4*)y, (float4*)gx, gbias, N, H, W, C4, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("pool_bias_act_bwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_fade_up_blend(const float* lo, const float* hi, float* out, int N, int C, int H, int W, float alpha,
+                                 glb_stream_t stream) {
+  REQ(H % 2 == 0 && W % 2 == 0, "fade_up_blend: odd H/W");
+  const int64_t total = (int64_t)N * C * H * W;
+  fade_up_blend_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(lo, hi, out, (int64_t)N * C, H, W, alpha);
+  GLB_CHECK_LAUNCH("fade_up_blend");
+  return GLB_OK;
+}
+
+extern "C" int glb_fade_up_blend_bwd(const float* gout, float* glo, float* ghi, int N, int C, int H, int W, float alpha,
+                                     glb_stream_t stream) {
+  REQ(H % 2 == 0 && W % 2 == 0, "fade_up_blend_bwd: odd H/W");
+  const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
+  fade_up_blend_bwd_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(gout, glo, ghi, (int64_t)N * C, H, W, alpha);
+  GLB_CHECK_LAUNCH("fade_up_blend_bwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_fade_real(const float* x, float* out, int N, int C, int H, int W, float alpha, glb_stream_t stream) {
+  REQ(H % 2 == 0 && W % 2 == 0, "fade_real: odd H/W");
+  const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
+  fade_real_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(x, out, (int64_t)N * C, H, W, alpha);
+  GLB_CHECK_LAUNCH("fade_real");
+  return GLB_OK;
+}
+
+extern "C" int glb_d_logit_loss(const float* d_gen, const float* d_real, float* loss, float* g_gen, float* g_real, int n, int kind,
+                                float eps_drift, glb_stream_t stream) {
+  REQ(n > 0 && kind >= 0 && kind <= 2, "d_logit_loss");
+  d_logit_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_gen, d_real, loss, g_gen, g_real, n, kind, eps_drift);
+  GLB_CHECK_LAUNCH("d_logit_loss");
+  return GLB_OK;
+}
+
+extern "C" int glb_g_logit_loss(const float* d_out, float* loss, float* g_out, int n, int kind, glb_stream_t stream) {
+  REQ(n > 0 && kind >= 0 && kind <= 2, "g_logit_loss");
+  g_logit_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_out, loss, g_out, n, kind);
+  GLB_CHECK_LAUNCH("g_logit_loss");
+  return GLB_OK;
+}
+
+extern "C" int glb_w_ewma(const float* w, float* ewma, int M, int K, float beta, glb_stream_t stream) {
+  REQ(M > 0 && K > 0, "w_ewma");
+  w_ewma_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w, ewma, M, K, beta);
+  GLB_CHECK_LAUNCH("w_ewma");
+  return GLB_OK;
+}
+
+extern "C" int glb_mbstd_fwd(const float* x, float* y, int N, int H, int W, int C, int group, glb_stream_t stream) {
+  REQ(group >= 1 && group <= MB_MAXG && N % group == 0, "mbstd: group must divide N and be <= 32");
+  mbstd_fwd_kernel<<<N / group, 512, 0, (cudaStream_t)stream>>>(x, y, H * W, C, group);
+  GLB_CHECK_LAUNCH("mbstd_fwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_mbstd_bwd(const float* gy, const float* x, float* gx, int N, int H, int W, int C, int group, glb_stream_t stream) {
+  REQ(group >= 1 && group <= MB_MAXG && N % group == 0, "mbstd: group must divide N and be <= 32");
+  mbstd_bwd_kernel<<<N / group, 512, 0, (cudaStream_t)stream>>>(gy, x, gx, H * W, C, group);
+  GLB_CHECK_LAUNCH("mbstd_bwd");
+  return GLB_OK;
+}
+
+extern "C" int glb_mbstd_bwdbwd(const float* v, const float* gy, const float* x, float* ggx, float* ggy, int N, int H, int W, int C,
+                                int group, glb_stream_t stream) {
+  REQ(group >= 1 && group <= MB_MAXG && N % group == 0, "mbstd: group must divide N and be <= 32");
+  mbstd_bwdbwd_kernel<<<N / group, 512, 0, (cudaStream_t)stream>>>(v, gy, x, ggx, ggy, H * W, C, group);
+  GLB_CHECK_LAUNCH("mbstd_bwdbwd");
+  return GLB_OK;
+}
+
+// ---- scalar-gradient helpers for the penalties ---------------------------------------------------------
+namespace glb {
+namespace {
+__global__ void scale_by_kernel(const float* __restrict__ x, const float* __restrict__ s_dev, float* __restrict__ y, int64_t n,
+                                float scale) {
+  const float s = scale * __ldg(s_dev);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] * s;
+}
+
+__global__ void gp_norm_fwd_kernel(const float* __restrict__ g, float* __restrict__ out, int N, int C, int64_t HW, float gamma,
+                                   float scale) {
+  __shared__ float red[TPB / 32];
+  float s = 0.f;
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, p = i % HW;
+    float q = 0.f;
+    for (int c = 0; c < C; ++c) { const float v = g[(n * C + c) * HW + p]; q = fmaf(v, v, q); }
+    const float d = sqrtf(q) - gamma;
+    s += d * d;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < TPB / 32) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, scale * s);
+  }
+}
+
+__global__ void gp_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ s_dev, float* __restrict__ gg, int N, int C,
+                                   int64_t HW, float gamma, float scale) {
+  const float up = 2.f * scale * __ldg(s_dev);
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, p = i % HW;
+    float q = 0.f;
+    for (int c = 0; c < C; ++c) { const float v = g[(n * C + c) * HW + p]; q = fmaf(v, v, q); }
+    const float nrm = sqrtf(q);
+    const float k = nrm > 0.f ? up * (nrm - gamma) / nrm : 0.f;
+    for (int c = 0; c < C; ++c) gg[(n * C + c) * HW + p] = k * g[(n * C + c) * HW + p];
+  }
+}
+
+__global__ void interp_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ eps,
+                                   float* __restrict__ out, int N, int64_t per_row) {
+  const int64_t total = (int64_t)N * per_row;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float e = __ldg(eps + i / per_row);
+    out[i] = e * a[i] + (1.f - e) * b[i];
+  }
+}
+}  // namespace
+}  // namespace glb
+
+extern "C" int glb_scale_by(const float* x, const float* s_dev, float* y, int64_t n, float scale, glb_stream_t stream) {
+  REQ(n > 0, "scale_by: n");
+  scale_by_kernel<<<grid_for(n, TPB), TPB, 0, (cudaStream_t)stream>>>(x, s_dev, y, n, scale);
+  GLB_CHECK_LAUNCH("scale_by");
+  return GLB_OK;
+}
+extern "C" int glb_gp_norm_fwd(const float* g, float* out, int N, int C, int64_t HW, float gamma, float scale, glb_stream_t stream) {
+  REQ(N > 0 && C > 0 && HW > 0, "gp_norm_fwd");
+  gp_norm_fwd_kernel<<<grid_for((int64_t)N * HW, TPB, kNumSMs * 4), TPB, 0, (cudaStream_t)stream>>>(g, out, N, C, HW, gamma, scale);
+  GLB_CHECK_LAUNCH("gp_norm_fwd");
+  return GLB_OK;
+}
+extern "C" int glb_gp_norm_bwd(const float* g, const float* s_dev, float* gg, int N, int C, int64_t HW, float gamma, float scale,
+                               glb_stream_t stream) {
+  REQ(N > 0 && C > 0 && HW > 0, "gp_norm_bwd");
+  gp_norm_bwd_kernel<<<grid_for((int64_t)N * HW, TPB), TPB, 0, (cudaStream_t)stream>>>(g, s_dev, gg, N, C, HW, gamma, scale);
+  GLB_CHECK_LAUNCH("gp_norm_bwd");
+  return GLB_OK;
+}
+extern "C" int glb_interp_rows(const float* a, const float* b, const float* eps, float* out, int N, int64_t per_row,
+                               glb_stream_t stream) {
+  REQ(N > 0 && per_row > 0, "interp_rows");
+  interp_rows_kernel<<<grid_for((int64_t)N * per_row, TPB), TPB, 0, (cudaStream_t)stream>>>(a, b, eps, out, N, per_row);
+  GLB_CHECK_LAUNCH("interp_rows");
+  return GLB_OK;
+}

@@ -1,0 +1,236 @@
+// RGB <-> feature 1x1 convolutions (3 channels on one side): pure bandwidth, never a GEMM.
+// fromRGB: reference progan/architectures.py:286-292 (Conv2dEx 1x1 3->C + LeakyReLU); toRGB: stylegan/architectures.py:338-341
+// and progan/architectures.py:150-153 (Conv2dEx 1x1 C->3, gain_sq_base=1).  Images are NCHW (the reference's layout at the
+// model boundary), features NHWC; the fade-in skip branches (avg-pool of the image before prev_fromrgb,
+// progan/architectures.py:312) are folded in through `pool`.
+#include "common.cuh"
+
+namespace glb {
+namespace {
+
+constexpr int TPB = 256;
+
+// y[n,h,w,c] = act(alpha * sum_j img_j * w(j,c) + bias_scale*bias[c]);  H, W = OUTPUT size; img is [N,3,H*(1+pool),W*(1+pool)]
+__global__ void rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, int ws_j, int ws_c,
+                                  const float* __restrict__ bias, float4* __restrict__ y, int N, int H, int W, int C4, int pool,
+                                  float alpha, float bias_scale, int act, float slope) {
+  const int64_t total = (int64_t)N * H * W * C4;
+  const int IH = pool ? 2 * H : H, IW = pool ? 2 * W : W;
+  const int64_t plane = (int64_t)IH * IW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4);
+    int64_t t = i / C4;
+    const int ww = (int)(t % W); t /= W;
+    const int hh = (int)(t % H);
+    const int64_t n = t / H;
+    float v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float* p = img + (n * 3 + j) * plane;
+      if (pool) {
+        const int64_t o = (int64_t)(2 * hh) * IW + 2 * ww;
+        v[j] = 0.25f * (__ldg(p + o) + __ldg(p + o + 1) + __ldg(p + o + IW) + __ldg(p + o + IW + 1));
+      } else {
+        v[j] = __ldg(p + (int64_t)hh * IW + ww);
+      }
+    }
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 4 * q + k;
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) a = fmaf(v[j], __ldg(w + j * ws_j + c * ws_c), a);
+      a *= alpha;
+      if (bias != nullptr) a += bias_scale * __ldg(bias + c);
+      o[k] = act_apply(a, act, slope);
+    }
+    stg_stream(y + i, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// img[n,j,h,w] = alpha * sum_c x[n,h,w,c] * w(j,c) + bias_scale*bias[j]; GS lanes cooperate on one pixel.
+// pool: scatter 0.25*value into the 2x2 window of an image of twice the size (adjoint of the avg-pool).
+template <int GS>
+__global__ void rgb_contract_kernel(const float4* __restrict__ x, const float* __restrict__ w, int ws_j, int ws_c,
+                                    const float* __restrict__ bias, float* __restrict__ img, int N, int H, int W, int C4, int pool,
+                                    float alpha, float bias_scale) {
+  const int64_t P = (int64_t)N * H * W;
+  const int lane = threadIdx.x % GS;
+  const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS, ngrp = ((int64_t)gridDim.x * blockDim.x) / GS;
+  // P is padded up so every lane of a warp takes part in the shuffles
+  const int64_t Ppad = ((P + (32 / GS) - 1) / (32 / GS)) * (32 / GS);
+  for (int64_t p = grp; p < Ppad; p += ngrp) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (p < P) {
+      for (int q = lane; q < C4; q += GS) {
+        const float4 v = ldg_stream(x + p * C4 + q);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * q + k;
+          a0 = fmaf(vv[k], __ldg(w + 0 * ws_j + c * ws_c), a0);
+          a1 = fmaf(vv[k], __ldg(w + 1 * ws_j + c * ws_c), a1);
+          a2 = fmaf(vv[k], __ldg(w + 2 * ws_j + c * ws_c), a2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (p < P && lane < 3) {
+      float a = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+      a *= alpha;
+      if (bias != nullptr) a += bias_scale * __ldg(bias + lane);
+      const int ww = (int)(p % W);
+      int64_t t = p / W;
+      const int hh = (int)(t % H);
+      const int64_t n = t / H;
+      if (pool) {
+        const int OW = 2 * W;
+        float* o = img + ((n * 3 + lane) * (2 * H) + 2 * hh) * (int64_t)OW + 2 * ww;
+        a *= 0.25f;
+        o[0] = a; o[1] = a; o[OW] = a; o[OW + 1] = a;
+      } else {
+        img[((n * 3 + lane) * H + hh) * (int64_t)W + ww] = a;
+      }
+    }
+  }
+}
+
+// gw(j,c) += alpha * sum_p img_j[p] * g[p,c]; thread owns a channel quad, rows strided; block reduce then atomics.
+__global__ void rgb_wgrad_kernel(const float* __restrict__ img, const float4* __restrict__ g, float* __restrict__ gw, int ws_j,
+                                 int ws_c, int N, int H, int W, int C4, int pool, float alpha) {
+  extern __shared__ float4 red[];  // 3 * blockDim
+  const int tid = threadIdx.x;
+  const int lanes = min(C4, (int)blockDim.x), rows = blockDim.x / lanes, rl = tid / lanes;
+  const int64_t P = (int64_t)N * H * W;
+  const int IH = pool ? 2 * H : H, IW = pool ? 2 * W : W;
+  const int64_t plane = (int64_t)IH * IW;
+  for (int q = tid % lanes; q < C4; q += lanes) {
+    float4 s[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t p = (int64_t)blockIdx.x * rows + rl; p < P; p += (int64_t)gridDim.x * rows) {
+      const int ww = (int)(p % W);
+      int64_t t = p / W;
+      const int hh = (int)(t % H);
+      const int64_t n = t / H;
+      const float4 gv = ldg_stream(g + p * C4 + q);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float* ip = img + (n * 3 + j) * plane;
+        float v;
+        if (pool) {
+          const int64_t o = (int64_t)(2 * hh) * IW + 2 * ww;
+          v = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
+        } else {
+          v = __ldg(ip + (int64_t)hh * IW + ww);
+        }
+        s[j].x = fmaf(v, gv.x, s[j].x); s[j].y = fmaf(v, gv.y, s[j].y); s[j].z = fmaf(v, gv.z, s[j].z); s[j].w = fmaf(v, gv.w, s[j].w);
+      }
+    }
+    if (C4 > lanes) {  // wide: direct atomics
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        atomicAdd(gw + j * ws_j + (4 * q + 0) * ws_c, alpha * s[j].x); atomicAdd(gw + j * ws_j + (4 * q + 1) * ws_c, alpha * s[j].y);
+        atomicAdd(gw + j * ws_j + (4 * q + 2) * ws_c, alpha * s[j].z); atomicAdd(gw + j * ws_j + (4 * q + 3) * ws_c, alpha * s[j].w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) red[j * blockDim.x + tid] = s[j];
+      __syncthreads();
+      if (tid < C4) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float4 t = red[j * blockDim.x + tid];
+          for (int r = 1; r < rows; ++r) {
+            const float4 u = red[j * blockDim.x + r * C4 + tid];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+          }
+          atomicAdd(gw + j * ws_j + (4 * tid + 0) * ws_c, alpha * t.x); atomicAdd(gw + j * ws_j + (4 * tid + 1) * ws_c, alpha * t.y);
+          atomicAdd(gw + j * ws_j + (4 * tid + 2) * ws_c, alpha * t.z); atomicAdd(gw + j * ws_j + (4 * tid + 3) * ws_c, alpha * t.w);
+        }
+      }
+    }
+  }
+}
+
+// out[c] += scale * sum_{n,hw} img[n,c,hw]  (bias gradient of toRGB; NCHW planes)
+__global__ void plane_sum_kernel(const float* __restrict__ img, float* __restrict__ out, int N, int C, int64_t HW, float scale) {
+  __shared__ float red[32];
+  const int c = blockIdx.y;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = img + ((int64_t)n * C + c) * HW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) s += p[i];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out + c, scale * s);
+  }
+}
+
+}  // namespace
+}  // namespace glb
+
+using namespace glb;
+#define REQ(cond, msg) do { if (!(cond)) return glb::shape_fail(msg); } while (0)
+
+extern "C" int glb_rgb_expand(const float* img, const float* w, int ws_j, int ws_c, const float* bias, float* y, int N, int H,
+                              int W, int C, int pool, float alpha, float bias_scale, int act, float slope, glb_stream_t stream) {
+  REQ(C % 4 == 0, "rgb_expand: C % 4 != 0");
+  const int64_t total = (int64_t)N * H * W * (C / 4);
+  rgb_expand_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(img, w, ws_j, ws_c, bias, (float4*)y, N, H, W, C / 4,
+                                                                           pool, alpha, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("rgb_expand");
+  return GLB_OK;
+}
+
+extern "C" int glb_rgb_contract(const float* x, const float* w, int ws_j, int ws_c, const float* bias, float* img, int N, int H,
+                                int W, int C, int pool, float alpha, float bias_scale, glb_stream_t stream) {
+  REQ(C % 4 == 0, "rgb_contract: C % 4 != 0");
+  const int C4 = C / 4;
+  const int64_t P = (int64_t)N * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(GS)                                                                                                     \
+  rgb_contract_kernel<GS><<<grid_for(P * GS, TPB), TPB, 0, st>>>((const float4*)x, w, ws_j, ws_c, bias, img, N, H, W, C4, pool, \
+                                                                 alpha, bias_scale)
+  if (C4 >= 32) LAUNCH(32);
+  else if (C4 >= 16) LAUNCH(16);
+  else if (C4 >= 8) LAUNCH(8);
+  else LAUNCH(4);
+#undef LAUNCH
+  GLB_CHECK_LAUNCH("rgb_contract");
+  return GLB_OK;
+}
+
+extern "C" int glb_rgb_wgrad(const float* img, const float* g, float* gw, int ws_j, int ws_c, int N, int H, int W, int C,
+                             int pool, float alpha, glb_stream_t stream) {
+  REQ(C % 4 == 0, "rgb_wgrad: C % 4 != 0");
+  const int C4 = C / 4;
+  REQ(C4 > TPB || TPB % C4 == 0, "rgb_wgrad: C/4 must divide 256 or exceed it");
+  const int lanes = C4 < TPB ? C4 : TPB, rows = TPB / lanes;
+  const int64_t P = (int64_t)N * H * W;
+  int blocks = (int)((P + rows - 1) / rows);
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  rgb_wgrad_kernel<<<blocks, TPB, 3 * TPB * sizeof(float4), (cudaStream_t)stream>>>(img, (const float4*)g, gw, ws_j, ws_c, N, H, W, C4,
+                                                                                   pool, alpha);
+  GLB_CHECK_LAUNCH("rgb_wgrad");
+  return GLB_OK;
+}
+
+extern "C" int glb_plane_sum(const float* img, float* out, int N, int C, int64_t HW, float scale, glb_stream_t stream) {
+  REQ(N > 0 && C > 0 && HW > 0, "plane_sum");
+  dim3 grid(grid_for(HW, TPB, 64), C);
+  plane_sum_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(img, out, N, C, HW, scale);
+  GLB_CHECK_LAUNCH("plane_sum");
+  return GLB_OK;
+}

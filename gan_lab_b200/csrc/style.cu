@@ -1,0 +1,265 @@
+// StyleGAN generator-layer epilogue, fused:  noise injection + bias + leaky-ReLU + InstanceNorm + AdaIN.
+//
+// Reference call sites replaced (paths relative to gan_lab/): StyleAddNoise.forward stylegan/architectures.py:112-119
+// (randn*weight + add), Conv2dBias utils/custom_layers.py:222-226, the shared nn.LeakyReLU, nn.InstanceNorm2d(eps=1e-8)
+// utils/custom_layers.py:99 (native_batch_norm on a reshaped tensor) and the AdaIN modulation
+// stylegan/architectures.py:460-462 / 524-526 (view, select, contiguous, add, mul, add): ~8 ATen kernels per layer.
+//
+//   u = x + nw[c]*noise[n,h,w] + b[c];  t = lrelu(u);  xhat = (t - mu[n,c]) * rstd[n,c];  out = xhat*(ys+1) + yb
+//
+// Plane statistics need all H*W pixels of an (n,c) plane, so forward = stats pass + apply pass (x is re-read
+// from L2 for the layers that fit it); backward likewise = reduction pass + apply pass.  Partial sums are
+// produced per 256-pixel chunk in fp32 and combined in fp64 (deterministic, no atomics on the statistics).
+#include "common.cuh"
+
+namespace glb {
+namespace {
+
+constexpr int TPB = 256;
+constexpr int CHUNK = 256;  // pixels per block
+
+struct SE {
+  int N, HW, C4, chunks;
+  float slope;
+};
+
+__device__ __forceinline__ float4 lrelu4(float4 u, float slope) {
+  return make_float4(u.x > 0.f ? u.x : u.x * slope, u.y > 0.f ? u.y : u.y * slope, u.z > 0.f ? u.z : u.z * slope,
+                     u.w > 0.f ? u.w : u.w * slope);
+}
+
+__device__ __forceinline__ float4 pre_act(const float4 x, float nz, const float4 nw, const float4 b) {
+  return make_float4(x.x + nw.x * nz + b.x, x.y + nw.y * nz + b.y, x.z + nw.z * nz + b.z, x.w + nw.w * nz + b.w);
+}
+
+// reduce (a, b) float4 pairs across the rows of the block that share a channel quad; result valid for tid < C4
+__device__ __forceinline__ void block_rows_reduce(float4& a, float4& b, float4* red, int C4, int rows) {
+  const int tid = threadIdx.x;
+  red[tid] = a;
+  red[TPB + tid] = b;
+  __syncthreads();
+  if (tid < C4) {
+    for (int r = 1; r < rows; ++r) {
+      const float4 u = red[r * C4 + tid], v = red[TPB + r * C4 + tid];
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+    }
+  }
+}
+
+// ---- forward pass 1: per-chunk sum / sum of squares of t ------------------------------------------
+__global__ void __launch_bounds__(TPB) se_fwd_stats_kernel(const float4* __restrict__ x, const float* __restrict__ noise,
+                                                           const float4* __restrict__ nw, const float4* __restrict__ bias,
+                                                           float4* __restrict__ part, SE g) {
+  __shared__ float4 red[2 * TPB];
+  const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  for (int p = p0 + rl; p < p1; p += rows) {
+    const int64_t px = (int64_t)n * g.HW + p;
+    const float nz = noise ? __ldg(noise + px) : 0.f;
+    const float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    ss.x += t.x * t.x; ss.y += t.y * t.y; ss.z += t.z * t.z; ss.w += t.w * t.w;
+  }
+  block_rows_reduce(s, ss, red, g.C4, rows);
+  if (tid < g.C4) {
+    float4* o = part + ((int64_t)(n * g.chunks + chunk) * 2) * g.C4;
+    o[q] = s;
+    o[g.C4 + q] = ss;
+  }
+}
+
+// stats layout: [N][2][C] = (mu plane, rstd plane)
+__global__ void se_fwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int N, int C, int chunks, int HW,
+                                       float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const float* p = part + ((int64_t)(n * chunks + k) * 2) * C;
+    s += (double)p[c];
+    ss += (double)p[C + c];
+  }
+  const double mu = s / HW;
+  double var = ss / HW - mu * mu;
+  if (var < 0.0) var = 0.0;
+  stats[((int64_t)n * 2) * C + c] = (float)mu;
+  stats[((int64_t)n * 2 + 1) * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---- forward pass 2: normalise + modulate ------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) se_fwd_apply_kernel(const float4* __restrict__ x, const float* __restrict__ noise,
+                                                           const float4* __restrict__ nw, const float4* __restrict__ bias,
+                                                           const float4* __restrict__ style, const float4* __restrict__ stats,
+                                                           float4* __restrict__ out, SE g) {
+  const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
+  const float4 ys = __ldg(style + (int64_t)n * 2 * g.C4 + q), yb = __ldg(style + ((int64_t)n * 2 + 1) * g.C4 + q);
+  const float4 sc = make_float4(rs.x * (ys.x + 1.f), rs.y * (ys.y + 1.f), rs.z * (ys.z + 1.f), rs.w * (ys.w + 1.f));
+  for (int p = p0 + rl; p < p1; p += rows) {
+    const int64_t px = (int64_t)n * g.HW + p;
+    const float nz = noise ? __ldg(noise + px) : 0.f;
+    const float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
+    stg_stream(out + px * g.C4 + q, make_float4((t.x - mu.x) * sc.x + yb.x, (t.y - mu.y) * sc.y + yb.y,
+                                                (t.z - mu.z) * sc.z + yb.z, (t.w - mu.w) * sc.w + yb.w));
+  }
+}
+
+// ---- backward pass 1: s1 = sum g, s2 = sum g*xhat per (n,c) chunk ------------------------------------------
+__global__ void __launch_bounds__(TPB) se_bwd_stats_kernel(const float4* __restrict__ gout, const float4* __restrict__ x,
+                                                           const float* __restrict__ noise, const float4* __restrict__ nw,
+                                                           const float4* __restrict__ bias, const float4* __restrict__ stats,
+                                                           float4* __restrict__ part, SE g) {
+  __shared__ float4 red[2 * TPB];
+  const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  for (int p = p0 + rl; p < p1; p += rows) {
+    const int64_t px = (int64_t)n * g.HW + p;
+    const float nz = noise ? __ldg(noise + px) : 0.f;
+    const float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
+    const float4 go = __ldg(gout + px * g.C4 + q);
+    s1.x += go.x; s1.y += go.y; s1.z += go.z; s1.w += go.w;
+    s2.x += go.x * (t.x - mu.x) * rs.x; s2.y += go.y * (t.y - mu.y) * rs.y;
+    s2.z += go.z * (t.z - mu.z) * rs.z; s2.w += go.w * (t.w - mu.w) * rs.w;
+  }
+  block_rows_reduce(s1, s2, red, g.C4, rows);
+  if (tid < g.C4) {
+    float4* o = part + ((int64_t)(n * g.chunks + chunk) * 2) * g.C4;
+    o[q] = s1;
+    o[g.C4 + q] = s2;
+  }
+}
+
+// gstyle[n][c] = s2 (d/d ys), gstyle[n][C+c] = s1 (d/d yb);  means[n][2][C] = ((ys+1)*s1/HW, (ys+1)*s2/HW)
+__global__ void se_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ style, float* __restrict__ gstyle,
+                                       float* __restrict__ means, int N, int C, int chunks, int HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const float* p = part + ((int64_t)(n * chunks + k) * 2) * C;
+    s1 += (double)p[c];
+    s2 += (double)p[C + c];
+  }
+  gstyle[(int64_t)n * 2 * C + c] = (float)s2;
+  gstyle[(int64_t)n * 2 * C + C + c] = (float)s1;
+  const double sc = (double)style[(int64_t)n * 2 * C + c] + 1.0;
+  means[(int64_t)n * 2 * C + c] = (float)(sc * s1 / HW);
+  means[(int64_t)n * 2 * C + C + c] = (float)(sc * s2 / HW);
+}
+
+// ---- backward pass 2: gx, and per-channel g_bias / g_noise_weight ------------------------------------------
+__global__ void __launch_bounds__(TPB) se_bwd_apply_kernel(const float4* __restrict__ gout, const float4* __restrict__ x,
+                                                           const float* __restrict__ noise, const float4* __restrict__ nw,
+                                                           const float4* __restrict__ bias, const float4* __restrict__ style,
+                                                           const float4* __restrict__ stats, const float4* __restrict__ means,
+                                                           float4* __restrict__ gx, float* __restrict__ g_nw,
+                                                           float* __restrict__ g_bias, SE g) {
+  __shared__ float4 red[2 * TPB];
+  const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
+  const float4 ys = __ldg(style + (int64_t)n * 2 * g.C4 + q);
+  const float4 m1 = __ldg(means + (int64_t)n * 2 * g.C4 + q), m2 = __ldg(means + ((int64_t)n * 2 + 1) * g.C4 + q);
+  const float4 sc = make_float4(ys.x + 1.f, ys.y + 1.f, ys.z + 1.f, ys.w + 1.f);
+  float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sn = sb;
+  for (int p = p0 + rl; p < p1; p += rows) {
+    const int64_t px = (int64_t)n * g.HW + p;
+    const float nz = noise ? __ldg(noise + px) : 0.f;
+    const float4 u = pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4);
+    const float4 t = lrelu4(u, g.slope);
+    const float4 go = ldg_stream(gout + px * g.C4 + q);
+    float4 gu;
+    gu.x = rs.x * (sc.x * go.x - m1.x - (t.x - mu.x) * rs.x * m2.x) * (u.x > 0.f ? 1.f : g.slope);
+    gu.y = rs.y * (sc.y * go.y - m1.y - (t.y - mu.y) * rs.y * m2.y) * (u.y > 0.f ? 1.f : g.slope);
+    gu.z = rs.z * (sc.z * go.z - m1.z - (t.z - mu.z) * rs.z * m2.z) * (u.z > 0.f ? 1.f : g.slope);
+    gu.w = rs.w * (sc.w * go.w - m1.w - (t.w - mu.w) * rs.w * m2.w) * (u.w > 0.f ? 1.f : g.slope);
+    stg_stream(gx + px * g.C4 + q, gu);
+    sb.x += gu.x; sb.y += gu.y; sb.z += gu.z; sb.w += gu.w;
+    sn.x += gu.x * nz; sn.y += gu.y * nz; sn.z += gu.z * nz; sn.w += gu.w * nz;
+  }
+  block_rows_reduce(sb, sn, red, g.C4, rows);
+  if (tid < g.C4) {
+    if (g_bias) {
+      atomicAdd(g_bias + 4 * q + 0, sb.x); atomicAdd(g_bias + 4 * q + 1, sb.y);
+      atomicAdd(g_bias + 4 * q + 2, sb.z); atomicAdd(g_bias + 4 * q + 3, sb.w);
+    }
+    if (g_nw) {
+      atomicAdd(g_nw + 4 * q + 0, sn.x); atomicAdd(g_nw + 4 * q + 1, sn.y);
+      atomicAdd(g_nw + 4 * q + 2, sn.z); atomicAdd(g_nw + 4 * q + 3, sn.w);
+    }
+  }
+}
+
+int se_geom(SE& g, int N, int H, int W, int C, float slope) {
+  if (C % 4 != 0 || C / 4 > TPB || TPB % (C / 4) != 0) return shape_fail("style_epilogue: C/4 must divide 256");
+  g.N = N; g.HW = H * W; g.C4 = C / 4; g.chunks = (g.HW + CHUNK - 1) / CHUNK; g.slope = slope;
+  if (N > 65535) return shape_fail("style_epilogue: N > 65535");
+  return GLB_OK;
+}
+
+}  // namespace
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" int64_t glb_style_epilogue_work_floats(int N, int H, int W, int C) {
+  const int64_t chunks = ((int64_t)H * W + CHUNK - 1) / CHUNK;
+  return (int64_t)N * chunks * 2 * C + (int64_t)N * 2 * C;
+}
+
+extern "C" int glb_style_epilogue_fwd(const float* x, const float* noise, const float* noise_weight, const float* bias,
+                                      const float* style, float* out, float* stats, float* work, int N, int H, int W, int C,
+                                      float slope, float eps, glb_stream_t stream) {
+  SE g;
+  if (int rc = se_geom(g, N, H, W, C, slope)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(g.chunks, N);
+  se_fwd_stats_kernel<<<grid, TPB, 0, st>>>((const float4*)x, noise, (const float4*)noise_weight, (const float4*)bias, (float4*)work, g);
+  GLB_CHECK_LAUNCH("se_fwd_stats");
+  se_fwd_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(work, stats, N, C, g.chunks, g.HW, eps);
+  GLB_CHECK_LAUNCH("se_fwd_finalize");
+  se_fwd_apply_kernel<<<grid, TPB, 0, st>>>((const float4*)x, noise, (const float4*)noise_weight, (const float4*)bias,
+                                            (const float4*)style, (const float4*)stats, (float4*)out, g);
+  GLB_CHECK_LAUNCH("se_fwd_apply");
+  return GLB_OK;
+}
+
+extern "C" int glb_style_epilogue_bwd(const float* gout, const float* x, const float* noise, const float* noise_weight,
+                                      const float* bias, const float* style, const float* stats, float* gx, float* gstyle,
+                                      float* g_noise_weight, float* g_bias, float* work, int N, int H, int W, int C, float slope,
+                                      glb_stream_t stream) {
+  SE g;
+  if (int rc = se_geom(g, N, H, W, C, slope)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(g.chunks, N);
+  float* means = work + (int64_t)N * g.chunks * 2 * C;
+  se_bwd_stats_kernel<<<grid, TPB, 0, st>>>((const float4*)gout, (const float4*)x, noise, (const float4*)noise_weight,
+                                            (const float4*)bias, (const float4*)stats, (float4*)work, g);
+  GLB_CHECK_LAUNCH("se_bwd_stats");
+  se_bwd_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(work, style, gstyle, means, N, C, g.chunks, g.HW);
+  GLB_CHECK_LAUNCH("se_bwd_finalize");
+  se_bwd_apply_kernel<<<grid, TPB, 0, st>>>((const float4*)gout, (const float4*)x, noise, (const float4*)noise_weight,
+                                            (const float4*)bias, (const float4*)style, (const float4*)stats, (const float4*)means,
+                                            (float4*)gx, g_noise_weight, g_bias, g);
+  GLB_CHECK_LAUNCH("se_bwd_apply");
+  return GLB_OK;
+}

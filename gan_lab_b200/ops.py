@@ -1,0 +1,630 @@
+"""Differentiable operators over the sm_100a kernels.
+
+Every op is a `torch.autograd.Function` whose backward is written in terms of *other* ops of this
+module, so the set is closed under differentiation: the R1 / WGAN-GP penalty
+(`autograd.grad(..., create_graph=True)` followed by `loss.backward()`, reference
+resnetgan/learner.py:811-825) differentiates straight through the discriminator's custom kernels.
+Generator-only ops (StyleGAN epilogue, PixelNorm, image fade blend) are first-order.
+
+`input_grads_only()` is a hint context for gradient-penalty style calls (`autograd.grad` w.r.t. the
+input image only): inside it, weight/bias gradients that autograd would compute and immediately
+discard are skipped -- what ATen's `convolution_backward` output_mask does for the reference.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _kernels as K
+
+ACT_NONE, ACT_LRELU = K.ACT_NONE, K.ACT_LRELU
+
+_hints = {"input_only": False}
+
+
+@contextlib.contextmanager
+def input_grads_only():
+    old = _hints["input_only"]
+    _hints["input_only"] = True
+    try:
+        yield
+    finally:
+        _hints["input_only"] = old
+
+
+def _param_grads_wanted() -> bool:
+    return not _hints["input_only"]
+
+
+# ----------------------------------------------------------------------------------------- elementwise
+class _Scale(Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        return K.axpby(x, None, s, 0.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Scale.apply(g, ctx.s), None
+
+
+class _Axpby(Function):
+    """a*alpha + b*beta (fade-in blend of feature maps, reference progan/architectures.py:312-313)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta):
+        ctx.ab = (alpha, beta)
+        return K.axpby(a, b, alpha, beta)
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, beta = ctx.ab
+        ga = _Scale.apply(g, alpha) if ctx.needs_input_grad[0] else None
+        gb = _Scale.apply(g, beta) if ctx.needs_input_grad[1] else None
+        return ga, gb, None, None
+
+
+def axpby(a, b, alpha, beta):
+    return _Axpby.apply(a, b, float(alpha), float(beta))
+
+
+class _ActBwd(Function):
+    """(gy, y) -> gx = gy * act'(y)  [+ per-channel sum = bias gradient].  Linear in gy; y is a mask."""
+
+    @staticmethod
+    def forward(ctx, gy, y, want_bias, bias_scale, act, slope):
+        ctx.save_for_backward(y)
+        ctx.cfg = (want_bias, bias_scale, act, slope)
+        ctx.set_materialize_grads(False)
+        gx, gb = K.act_bwd(gy, y, want_bias, bias_scale, act, slope)
+        return gx, gb
+
+    @staticmethod
+    def backward(ctx, ggx, ggb):
+        (y,) = ctx.saved_tensors
+        want_bias, bias_scale, act, slope = ctx.cfg
+        g = ggx
+        if ggb is not None:
+            # someone differentiates the bias gradient itself (never on the training path): d(gb)/d(gy)
+            shape = (1, -1, 1, 1) if y.dim() == 4 else (1, -1)
+            extra = (ggb.view(shape) * bias_scale).expand(y.shape)
+            g = extra if g is None else g + extra
+        if g is None:
+            return None, None, None, None, None, None
+        out, _ = _ActBwd.apply(g.contiguous() if g.dim() != 4 else g, y, False, 1.0, act, slope)
+        return out, None, None, None, None, None
+
+
+def act_bwd(gy, y, want_bias, bias_scale, act, slope):
+    gx, gb = _ActBwd.apply(gy, y, want_bias, bias_scale, act, slope)
+    return gx, (gb if want_bias else None)
+
+
+class _ColSum(Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.shape, ctx.scale, ctx.nd = x.shape, scale, x.dim()
+        return K.colsum(x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        view = (1, -1, 1, 1) if ctx.nd == 4 else (1, -1)
+        return (g.view(view) * ctx.scale).expand(ctx.shape), None
+
+
+class _BiasAct(Function):
+    """y = act(x + bias_scale*bias): reference Conv2dBias + LeakyReLU (utils/custom_layers.py:213-226)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, bias_scale, act, slope):
+        y = K.bias_act_fwd(x, bias, bias_scale, act, slope)
+        ctx.save_for_backward(y)
+        ctx.cfg = (bias_scale, act, slope, bias is not None, None if bias is None else bias.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        bias_scale, act, slope, has_bias, bshape = ctx.cfg
+        want_b = has_bias and ctx.needs_input_grad[1] and _param_grads_wanted()
+        gx, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
+        return gx, (gb.view(bshape) if gb is not None else None), None, None, None
+
+
+def bias_act(x, bias, bias_scale=1.0, act=ACT_NONE, slope=0.2):
+    return _BiasAct.apply(x, bias, float(bias_scale), int(act), float(slope))
+
+
+# ----------------------------------------------------------------------------------------- convolution
+class _ConvFprop(Function):
+    """y = act(alpha * conv(x, w) + bias_scale * bias)   (Conv2dEx.forward, utils/custom_layers.py:202-211)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, pad, alpha, bias_scale, act, slope):
+        y = K.conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope)
+        ctx.cfg = (pad, alpha, bias_scale, act, slope, bias is not None, x.shape, w.shape)
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        pad, alpha, bias_scale, act, slope, has_bias, xshape, wshape = ctx.cfg
+        pg = _param_grads_wanted()
+        want_b = has_bias and ctx.needs_input_grad[2] and pg
+        if act != ACT_NONE:
+            g, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
+        else:
+            g = gy
+            gb = _ColSum.apply(g, bias_scale) if want_b else None
+        gx = _ConvDgrad.apply(g, w, xshape[2], xshape[3], pad, alpha) if ctx.needs_input_grad[0] else None
+        gw = _ConvWgrad.apply(x, g, wshape[2], wshape[3], pad, alpha) if (ctx.needs_input_grad[1] and pg) else None
+        return gx, gw, gb, None, None, None, None, None
+
+
+class _ConvDgrad(Function):
+    """gx = alpha * conv_transpose(gy, w).  Bilinear in (gy, w)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, H, W, pad, alpha):
+        ctx.cfg = (H, W, pad, alpha, w.shape)
+        ctx.save_for_backward(gy, w)
+        return K.conv_dgrad(gy, w, (H, W), pad, alpha)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gy, w = ctx.saved_tensors
+        H, W, pad, alpha, wshape = ctx.cfg
+        g_gy = _ConvFprop.apply(ggx, w, None, pad, alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[0] else None
+        g_w = _ConvWgrad.apply(ggx, gy, wshape[2], wshape[3], pad, alpha) if ctx.needs_input_grad[1] else None
+        return g_gy, g_w, None, None, None, None
+
+
+class _ConvWgrad(Function):
+    """gw = alpha * sum_pixels gy (x) x.  Bilinear in (x, gy)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, R, S, pad, alpha):
+        ctx.cfg = (R, S, pad, alpha, x.shape)
+        ctx.save_for_backward(x, gy)
+        return K.conv_wgrad(x, gy, (R, S), pad, alpha)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        R, S, pad, alpha, xshape = ctx.cfg
+        g_x = _ConvDgrad.apply(gy, ggw, xshape[2], xshape[3], pad, alpha) if ctx.needs_input_grad[0] else None
+        g_gy = _ConvFprop.apply(x, ggw, None, pad, alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[1] else None
+        return g_x, g_gy, None, None, None, None
+
+
+def conv2d(x, w, bias=None, pad=0, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2):
+    return _ConvFprop.apply(x, w, bias, int(pad), float(alpha), float(bias_scale), int(act), float(slope))
+
+
+# ----------------------------------------------------------------------------------------- linear
+class _LinearFwd(Function):
+    """y = act(alpha * x.w^T + bias_scale * bias)   (LinearEx.forward, utils/custom_layers.py:282-291)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, alpha, bias_scale, act, slope):
+        y = K.linear_fwd(x, w, bias, alpha, bias_scale, act, slope)
+        ctx.cfg = (alpha, bias_scale, act, slope, bias is not None)
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        alpha, bias_scale, act, slope, has_bias = ctx.cfg
+        pg = _param_grads_wanted()
+        want_b = has_bias and ctx.needs_input_grad[2] and pg
+        if act != ACT_NONE:
+            g, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
+        else:
+            g = gy
+            gb = _ColSum.apply(g, bias_scale) if want_b else None
+        gx = _LinearDgrad.apply(g, w, alpha) if ctx.needs_input_grad[0] else None
+        gw = _LinearWgrad.apply(x, g, alpha) if (ctx.needs_input_grad[1] and pg) else None
+        return gx, gw, gb, None, None, None, None
+
+
+class _LinearDgrad(Function):
+    @staticmethod
+    def forward(ctx, gy, w, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(gy, w)
+        return K.linear_dgrad(gy, w, alpha)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gy, w = ctx.saved_tensors
+        g_gy = _LinearFwd.apply(ggx, w, None, ctx.alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[0] else None
+        g_w = _LinearWgrad.apply(ggx, gy, ctx.alpha) if ctx.needs_input_grad[1] else None
+        return g_gy, g_w, None
+
+
+class _LinearWgrad(Function):
+    @staticmethod
+    def forward(ctx, x, gy, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(x, gy)
+        return K.linear_wgrad(x, gy, alpha)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        g_x = _LinearDgrad.apply(gy, ggw, ctx.alpha) if ctx.needs_input_grad[0] else None
+        g_gy = _LinearFwd.apply(x, ggw, None, ctx.alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[1] else None
+        return g_x, g_gy, None
+
+
+def linear(x, w, bias=None, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2):
+    return _LinearFwd.apply(x, w, bias, float(alpha), float(bias_scale), int(act), float(slope))
+
+
+# ----------------------------------------------------------------------------------------- stencil / resampling
+class _Blur(Function):
+    """Self-adjoint 3x3 binomial FIR (get_blur_op, utils/custom_layers.py:36-53): fwd = bwd = double-bwd."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.blur3x3(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Blur.apply(g)
+
+
+def blur3x3(x):
+    return _Blur.apply(x)
+
+
+class _Up2(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.upsample2x_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Up2Bwd.apply(g)
+
+
+class _Up2Bwd(Function):
+    @staticmethod
+    def forward(ctx, g):
+        return K.upsample2x_bwd(g)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return _Up2.apply(gg)
+
+
+def upsample2x(x):
+    return _Up2.apply(x)
+
+
+class _AvgPoolBwd(Function):
+    """g [N,C,H/2,W/2] -> 0.25 * nearest-upsample(g): adjoint of the 2x2 average pool."""
+
+    @staticmethod
+    def forward(ctx, g):
+        gx, _ = K.pool_bias_act_bwd(g, None, False, 1.0, ACT_NONE, 0.0)
+        return gx
+
+    @staticmethod
+    def backward(ctx, gg):
+        return _PoolBiasAct.apply(gg, None, 1.0, ACT_NONE, 0.0)
+
+
+class _PoolBiasAct(Function):
+    """y = act(avgpool2(x) + bias_scale*bias): D downsampling tail, reference progan/architectures.py:267-284."""
+
+    @staticmethod
+    def forward(ctx, x, bias, bias_scale, act, slope):
+        y = K.pool_bias_act_fwd(x, bias, bias_scale, act, slope)
+        ctx.cfg = (bias_scale, act, slope, bias is not None, None if bias is None else bias.shape)
+        ctx.save_for_backward(y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        bias_scale, act, slope, has_bias, bshape = ctx.cfg
+        want_b = has_bias and ctx.needs_input_grad[1] and _param_grads_wanted()
+        if act != ACT_NONE:
+            g, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
+        else:
+            g = gy
+            gb = _ColSum.apply(g, bias_scale) if want_b else None
+        gx = _AvgPoolBwd.apply(g) if ctx.needs_input_grad[0] else None
+        return gx, (gb.view(bshape) if gb is not None else None), None, None, None
+
+
+def pool_bias_act(x, bias=None, bias_scale=1.0, act=ACT_NONE, slope=0.2):
+    return _PoolBiasAct.apply(x, bias, float(bias_scale), int(act), float(slope))
+
+
+def avgpool2(x):
+    return _PoolBiasAct.apply(x, None, 1.0, ACT_NONE, 0.0)
+
+
+# ----------------------------------------------------------------------------------------- norms
+class _PixelNorm(Function):
+    """PixelNorm2d (utils/custom_layers.py:81-86); generator-side only -> first order."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        ctx.eps = eps
+        ctx.save_for_backward(x)
+        return K.pixelnorm_fwd(x, eps)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return K.pixelnorm_bwd(gy, x, ctx.eps), None
+
+
+def pixelnorm(x, eps=1e-8):
+    return _PixelNorm.apply(x, float(eps))
+
+
+class _StyleEpilogue(Function):
+    """noise + bias + lrelu + InstanceNorm + AdaIN in one op (stylegan/architectures.py:112-119, 255/263/333,
+    460-462/524-526).  Generator-side only -> first order."""
+
+    @staticmethod
+    def forward(ctx, x, noise, noise_weight, bias, style, slope, eps):
+        out, stats = K.style_epilogue_fwd(x, noise, noise_weight, bias, style, slope, eps)
+        ctx.slope = slope
+        ctx.shapes = (None if noise_weight is None else noise_weight.shape, None if bias is None else bias.shape)
+        ctx.save_for_backward(x, noise, noise_weight, bias, style, stats)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        x, noise, nw, bias, style, stats = ctx.saved_tensors
+        gx, gstyle, g_nw, g_b = K.style_epilogue_bwd(gout, x, noise, nw, bias, style, stats, ctx.slope)
+        nws, bs = ctx.shapes
+        return (gx, None, g_nw.view(nws) if g_nw is not None else None, g_b.view(bs) if g_b is not None else None,
+                gstyle, None, None)
+
+
+def style_epilogue(x, noise, noise_weight, bias, style, slope=0.2, eps=1e-8):
+    return _StyleEpilogue.apply(x, noise, noise_weight, bias, style, float(slope), float(eps))
+
+
+def instance_norm(x, eps=1e-8):
+    """nn.InstanceNorm2d(eps=1e-8, affine=False) through the same fused kernel (identity act, zero style)."""
+    style = x.new_zeros((x.shape[0], 2 * x.shape[1]))
+    return _StyleEpilogue.apply(x, None, None, None, style, 1.0, float(eps))
+
+
+# ----------------------------------------------------------------------------------------- minibatch stddev
+def mbstd_group(n: int, group_size: int) -> int:
+    """Group-size rule of concat_mbstd_layer (utils/custom_layers.py:121-126)."""
+    g = min(n, group_size)
+    if n % g != 0:
+        g = n
+    return g
+
+
+class _Mbstd(Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        ctx.save_for_backward(x)
+        return K.mbstd_fwd(x, group)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return _MbstdBwd.apply(gy, x, ctx.group), None
+
+
+class _MbstdBwd(Function):
+    @staticmethod
+    def forward(ctx, gy, x, group):
+        ctx.group = group
+        ctx.save_for_backward(gy, x)
+        return K.mbstd_bwd(gy, x, group)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, v):
+        gy, x = ctx.saved_tensors
+        ggx, ggy = K.mbstd_bwdbwd(v, gy, x, ctx.group)
+        return ggy, ggx, None
+
+
+def mbstd_concat(x, group_size=4):
+    return _Mbstd.apply(x, mbstd_group(x.shape[0], group_size))
+
+
+# ----------------------------------------------------------------------------------------- RGB 1x1 convs
+class _RgbExpand(Function):
+    """img NCHW (3 ch) -> NHWC features: y = act(alpha * img.w + bias_scale*bias); w element (j,c) at w[j*ws_j+c*ws_c]."""
+
+    @staticmethod
+    def forward(ctx, img, w, bias, ws_j, ws_c, C, pool, alpha, bias_scale, act, slope):
+        y = K.rgb_expand(img, w, ws_j, ws_c, C, bias, pool, alpha, bias_scale, act, slope)
+        ctx.cfg = (ws_j, ws_c, C, pool, alpha, bias_scale, act, slope, bias is not None, w.shape,
+                   None if bias is None else bias.shape)
+        ctx.save_for_backward(img, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        img, w, y = ctx.saved_tensors
+        ws_j, ws_c, C, pool, alpha, bias_scale, act, slope, has_bias, wshape, bshape = ctx.cfg
+        pg = _param_grads_wanted()
+        want_b = has_bias and ctx.needs_input_grad[2] and pg
+        if act != ACT_NONE:
+            g, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
+        else:
+            g = gy
+            gb = _ColSum.apply(g, bias_scale) if want_b else None
+        gimg = _RgbContract.apply(g, w, None, ws_j, ws_c, pool, alpha, 1.0) if ctx.needs_input_grad[0] else None
+        gw = _RgbWgrad.apply(img, g, wshape, ws_j, ws_c, pool, alpha) if (ctx.needs_input_grad[1] and pg) else None
+        return gimg, gw, (gb.view(bshape) if gb is not None else None), None, None, None, None, None, None, None, None
+
+
+class _RgbContract(Function):
+    """NHWC features -> img NCHW (3 ch): img = alpha * sum_c x*w + bias_scale*bias (pool: avg-pool adjoint scatter)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, ws_j, ws_c, pool, alpha, bias_scale):
+        ctx.cfg = (ws_j, ws_c, pool, alpha, bias_scale, bias is not None, w.shape, x.shape[1],
+                   None if bias is None else bias.shape)
+        ctx.save_for_backward(x, w)
+        return K.rgb_contract(x, w, ws_j, ws_c, bias, pool, alpha, bias_scale)
+
+    @staticmethod
+    def backward(ctx, gimg):
+        x, w = ctx.saved_tensors
+        ws_j, ws_c, pool, alpha, bias_scale, has_bias, wshape, C, bshape = ctx.cfg
+        pg = _param_grads_wanted()
+        gx = _RgbExpand.apply(gimg, w, None, ws_j, ws_c, C, pool, alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[0] else None
+        gw = _RgbWgrad.apply(gimg, x, wshape, ws_j, ws_c, pool, alpha) if (ctx.needs_input_grad[1] and pg) else None
+        gb = None
+        if has_bias and ctx.needs_input_grad[2] and pg:
+            gb = K.plane_sum(gimg, bias_scale).view(bshape)
+        return gx, gw, gb, None, None, None, None, None
+
+
+class _RgbWgrad(Function):
+    @staticmethod
+    def forward(ctx, img, g, wshape, ws_j, ws_c, pool, alpha):
+        ctx.cfg = (ws_j, ws_c, pool, alpha, g.shape[1])
+        ctx.save_for_backward(img, g)
+        return K.rgb_wgrad(img, g, wshape, ws_j, ws_c, pool, alpha)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        img, g = ctx.saved_tensors
+        ws_j, ws_c, pool, alpha, C = ctx.cfg
+        g_img = _RgbContract.apply(g, ggw, None, ws_j, ws_c, pool, alpha, 1.0) if ctx.needs_input_grad[0] else None
+        g_g = _RgbExpand.apply(img, ggw, None, ws_j, ws_c, C, pool, alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[1] else None
+        return g_img, g_g, None, None, None, None, None
+
+
+def fromrgb(img, w, bias, alpha, bias_scale=1.0, act=ACT_LRELU, slope=0.2, pool=False):
+    """Conv2dEx 1x1 (3 -> C) [+ lrelu]; weight [C,3,1,1].  pool=True averages 2x2 first (fade-in skip branch)."""
+    C = w.shape[0]
+    return _RgbExpand.apply(img, w, bias, 1, 3, C, bool(pool), float(alpha), float(bias_scale), int(act), float(slope))
+
+
+def torgb(x, w, bias, alpha, bias_scale=1.0):
+    """Conv2dEx 1x1 (C -> 3); weight [3,C,1,1]; output NCHW image."""
+    C = w.shape[1]
+    return _RgbContract.apply(x, w, bias, C, 1, False, float(alpha), float(bias_scale))
+
+
+# ----------------------------------------------------------------------------------------- image-space fade-in
+class _FadeUpBlend(Function):
+    """(1-alpha) * up2x(lo) + alpha * hi on NCHW images (stylegan/architectures.py:482-487). Generator-side."""
+
+    @staticmethod
+    def forward(ctx, lo, hi, alpha):
+        ctx.alpha = alpha
+        return K.fade_up_blend(lo, hi, alpha)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        glo, ghi = K.fade_up_blend_bwd(g, ctx.alpha)
+        return glo, ghi, None
+
+
+def fade_up_blend(lo, hi, alpha):
+    return _FadeUpBlend.apply(lo, hi, float(alpha))
+
+
+def fade_real(x, alpha):
+    """Real-image fade-in (progan/learner.py:770-779) on the device; no gradient."""
+    return K.fade_real(x.detach(), float(alpha))
+
+
+# ----------------------------------------------------------------------------------------- losses
+class _DLogitLoss(Function):
+    @staticmethod
+    def forward(ctx, d_gen, d_real, kind, eps_drift):
+        loss, gg, gr = K.d_logit_loss(d_gen, d_real, kind, eps_drift)
+        ctx.save_for_backward(gg, gr)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gl):
+        gg, gr = ctx.saved_tensors
+        return K.scale_by(gg, gl, 1.0), K.scale_by(gr, gl, 1.0), None, None
+
+
+class _GLogitLoss(Function):
+    @staticmethod
+    def forward(ctx, d_out, kind):
+        loss, g = K.g_logit_loss(d_out, kind)
+        ctx.save_for_backward(g)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return K.scale_by(g, gl, 1.0), None
+
+
+def d_logit_loss(d_gen, d_real, kind="nonsaturating", eps_drift=0.0):
+    """progan/learner.py:791-800 (+ drift term :811-812)."""
+    return _DLogitLoss.apply(d_gen, d_real, kind, float(eps_drift))
+
+
+def g_logit_loss(d_out, kind="nonsaturating"):
+    """progan/learner.py:883-896."""
+    return _GLogitLoss.apply(d_out, kind)
+
+
+class _SumSq(Function):
+    """scale * sum(x^2): the R1/R2 penalty reduction (resnetgan/learner.py:825; norm over channels, mean over N,H,W)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        ctx.save_for_backward(x)
+        return K.sumsq(x, scale)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gl):
+        (x,) = ctx.saved_tensors
+        return K.scale_by(x, gl, 2.0 * ctx.scale), None
+
+
+def sumsq(x, scale):
+    return _SumSq.apply(x, float(scale))
+
+
+class _GpNorm(Function):
+    """scale * sum_{n,h,w} (||g||_2 over channels - gamma)^2   (WGAN-GP, resnetgan/learner.py:817-823)."""
+
+    @staticmethod
+    def forward(ctx, g, gamma, scale):
+        ctx.cfg = (gamma, scale)
+        ctx.save_for_backward(g)
+        return K.gp_norm_fwd(g, gamma, scale)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        gamma, scale = ctx.cfg
+        return K.gp_norm_bwd(g, gl, gamma, scale), None, None
+
+
+def gp_norm(g, gamma, scale):
+    return _GpNorm.apply(g, float(gamma), float(scale))

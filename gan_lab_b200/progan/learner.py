@@ -1,0 +1,326 @@
+"""ProGANLearner: the progressive-growing train loop (reference gan_lab/progan/learner.py:86-1130).
+
+`train()` keeps the reference's loop semantics -- phase bookkeeping (grow / fade-in / stabilise, :560-729),
+D step (:734-816: G forward, fake + real D forwards, logit loss, gradient penalty with double backward, drift
+term, Adam), G step (:854-916: D frozen, G+D forward, loss, backward, Adam, EWMA generator), alpha update and
+LR schedule (:951-956) -- on the sm_100a kernels.  Deliberate deviations (all host-side, none numerical):
+  * the D-step generator forward runs under no_grad (the reference builds and drops the graph, :752-753);
+  * the real-image fade-in blend runs on the device (reference: on the host before upload, :770-779);
+  * per-step `.item()` syncs / tqdm strings are replaced by an optional `log_every`;
+  * no dependency on a pickled data_config (only used for bit-exact PIL resampling and metrics);
+  * Adam + EWMA run as one fused multi-tensor kernel (`optim.FusedAdam`);
+  * with `dp=...` (a `parallel.DataParallel` object) gradients are all-reduced over NCCL before each optimiser step.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from .. import ops
+from .._growth import GrowthState
+from ..resnetgan.learner import GANLearner, LearnerConfigCopy
+from ..utils.latent_utils import gen_rand_latent_vars
+from .architectures import ProGenerator, ProDiscriminator
+
+NONREDEFINABLE_ATTRS = ('model', 'init_res', 'res_samples', 'res_dataset', 'len_latent', 'num_classes',
+                        'class_condition', 'use_auxiliary_classifier', 'model_upsample_type', 'model_downsample_type',
+                        'align_corners', 'blur_type', 'nonlinearity', 'use_equalized_lr', 'normalize_z',
+                        'use_pixelnorm', 'mbstd_group_size', 'use_ewma_gen',)
+REDEFINABLE_FROM_LEARNER_ATTRS = ('batch_size', 'loss', 'gradient_penalty', 'optimizer', 'lr_sched', 'latent_distribution',)
+
+COMPUTE_EWMA_VIA_HALFLIFE = True
+EWMA_SMOOTHING_HALFLIFE = 10.
+EWMA_SMOOTHING_BETA = .999
+
+
+class ProGANLearner(GANLearner):
+    """GAN Learner for ProGAN architectures (and, through StyleGANLearner, StyleGAN)."""
+
+    _model_name = 'ProGAN'
+
+    def __init__(self, config):
+        super(ProGANLearner, self).__init__(config)
+        self.curr_phase_num = 0
+        self.lagged_params = None
+        self._progressively_grow = True
+        self.dp = None
+        if self.model == self._model_name:
+            self.config = LearnerConfigCopy(config, self.__class__.__name__, self._nonredefinable(),
+                                            REDEFINABLE_FROM_LEARNER_ATTRS)
+            self.latent_distribution = self.config.latent_distribution
+            self.state = GrowthState()
+            self._build_models()
+            self._finish_init(config)
+
+    def _nonredefinable(self):
+        return NONREDEFINABLE_ATTRS
+
+    # ------------------------------------------------------------------ construction (reference :116-215)
+    def _build_models(self):
+        c = self.config
+        self.gen_model = ProGenerator(final_res=c.res_samples, len_latent=c.len_latent, upsampler=self.gen_model_upsampler,
+                                      blur_type=c.blur_type, nl=self.nl, num_classes=0, equalized_lr=c.use_equalized_lr,
+                                      normalize_z=c.normalize_z, use_pixelnorm=c.use_pixelnorm, state=self.state)
+        self.disc_model = ProDiscriminator(final_res=c.res_samples, pooler=self.disc_model_downsampler, blur_type=c.blur_type,
+                                           nl=self.nl, num_classes=0, equalized_lr=c.use_equalized_lr,
+                                           mbstd_group_size=c.mbstd_group_size, state=self.state)
+
+    def _finish_init(self, config):
+        c = self.config
+        assert c.init_res <= c.res_samples
+        if c.init_res > 4:
+            _init_res_log2 = int(np.log2(c.init_res))
+            if float(c.init_res) != 2 ** _init_res_log2:
+                raise ValueError('Only resolutions that are powers of 2 are supported.')
+            for _ in range(_init_res_log2 - 2):
+                self.gen_model.increase_scale()
+                self.disc_model.increase_scale()
+            self.gen_model.fade_in_phase = False
+        assert self.gen_model.cls_base is self.disc_model.cls_base
+        self.gen_model.to(c.dev)
+        self.disc_model.to(c.dev)
+        # EWMA generator: the reference deep-copies G (reference :165-174) and keeps `lagged_params`
+        self.gen_model_lagged = None
+        if c.use_ewma_gen:
+            with torch.no_grad():
+                self.gen_model_lagged = copy.deepcopy(self.gen_model)
+        self.batch_size = c.bs_dict[self.gen_model.curr_res]
+        self._loss = config.loss.casefold()
+        self._set_loss()
+        self._set_optimizer()
+        self.eps = c.eps_drift > 0
+
+    def _set_optimizer(self):
+        """reference progan/learner.py:1064-1095: prev_torgb / prev_fromrgb are only optimised while fading in."""
+        adam_gan = self._adam_factory()
+        if self.gen_model.fade_in_phase:
+            self.opt_gen = adam_gan(params=self.gen_model.parameters())
+            self.opt_disc = adam_gan(params=self.disc_model.parameters())
+        else:
+            self.opt_gen = adam_gan(params=self.gen_model.most_parameters(
+                excluded_params=['prev_torgb.conv2d.weight', 'prev_torgb.conv2d.bias']))
+            self.opt_disc = adam_gan(params=self.disc_model.most_parameters(
+                excluded_params=['prev_fromrgb.0.conv2d.weight', 'prev_fromrgb.0.conv2d.bias']))
+        self._attach_ewma()
+
+    def _attach_ewma(self):
+        if getattr(self, 'lagged_params', None) is not None and self.beta is not None:
+            self.opt_gen.attach_ewma(list(self.gen_model.named_parameters()), self.lagged_params, self.beta)
+            self.opt_gen._ewma_started = self._ewma_started
+
+    def _set_scheduler(self):
+        """reference progan/learner.py:1034-1062."""
+        if self._lr_sched == 'resolution dependent':
+            self.scheduler_fn = lambda _: self.config.lr_fctr_dict[self.gen_model.curr_res]
+        elif self._lr_sched == 'linear decay':
+            self.scheduler_fn = lambda main_iter: 1. - (main_iter + self.sched_stop_step) * (1. / self.num_main_iters)
+        elif self._lr_sched == 'custom':
+            self.scheduler_fn = eval(self.config.lr_sched_custom)
+        else:
+            raise ValueError("Currently supported LR Schedulers are: [ 'resolution dependent', 'linear decay', 'custom' ]")
+        self.scheduler_gen = torch.optim.lr_scheduler.LambdaLR(self.opt_gen, self.scheduler_fn, last_epoch=-1)
+        self.scheduler_disc = torch.optim.lr_scheduler.LambdaLR(self.opt_disc, self.scheduler_fn, last_epoch=-1)
+
+    def get_smoothing_ewma_beta(self, half_life):
+        """reference progan/learner.py:1124-1127."""
+        assert isinstance(half_life, float)
+        return .5 ** ((self.batch_size * self.config.gen_bs_mult) / (half_life * 1000.)) if half_life > 0. else 0.
+
+    def _init_lagged(self):
+        """`lagged_params` starts as an alias of the live parameters in the reference (progan/learner.py:472), i.e. the
+        first EWMA update sees lagged == post-Adam param; here the lagged tensors are separate buffers and the
+        fused kernel's first-step mode reproduces that."""
+        self.lagged_params = {n: p for n, p in self.gen_model_lagged.named_parameters()}
+        for p in self.lagged_params.values():
+            p.requires_grad_(False)
+        self._ewma_started = False
+
+    @torch.no_grad()
+    def _update_gen_lagged(self):
+        """The lagged tensors ARE gen_model_lagged's parameters here, so it is always current (reference :234-242)."""
+        return self.gen_model_lagged
+
+    def _sync_lagged_structure(self):
+        """After increase_scale(): give the lagged generator the new blocks (initialised from the live ones) and
+        carry torgb -> prev_torgb over, as reference progan/learner.py:660-686 does on `lagged_params`."""
+        old = {n: p.detach().clone() for n, p in self.gen_model_lagged.named_parameters()}
+        with torch.no_grad():
+            self.gen_model_lagged = copy.deepcopy(self.gen_model)
+            for n, p in self.gen_model_lagged.named_parameters():
+                src = None
+                if n.startswith('prev_torgb.'):
+                    src = old.get(n.replace('prev_torgb.', 'torgb.', 1))
+                elif not n.startswith('torgb.'):
+                    src = old.get(n)
+                if src is not None and src.shape == p.shape:
+                    p.copy_(src)
+        self._init_lagged_keep_started()
+
+    def _init_lagged_keep_started(self):
+        started = getattr(self, '_ewma_started', False)
+        self._init_lagged()
+        self._ewma_started = started
+
+    # ------------------------------------------------------------------ one step each (used by train() and by bench/tests)
+    def _next_real(self, train_dl):
+        batch = next(self.train_dataiter, None)
+        if batch is None:
+            self.curr_epoch_num += 1
+            self.train_dataiter = iter(train_dl)
+            batch = next(self.train_dataiter)
+        xb = batch[0] if isinstance(batch, (list, tuple)) else batch
+        return xb
+
+    def disc_step(self, xb):
+        """One discriminator step on real batch `xb` (reference progan/learner.py:734-816).  Returns the loss tensor."""
+        c = self.config
+        self.disc_model.zero_grad()
+        zb = gen_rand_latent_vars(num_samples=self.batch_size, length=c.len_latent, distribution=self.latent_distribution,
+                                  device=c.dev)
+        with torch.no_grad():
+            _xgenb = self.gen_model(zb).detach()
+        xb = xb.to(c.dev, non_blocking=True)
+        if self.gen_model.fade_in_phase:
+            xb = ops.fade_real(xb, self.gen_model.alpha)
+        discriminative_gen = self.disc_model(_xgenb)
+        discriminative_real = self.disc_model(xb)
+        loss_train_disc = ops.d_logit_loss(discriminative_gen, discriminative_real, self.loss,
+                                           c.eps_drift if self.eps else 0.)
+        if self.gradient_penalty is not None:
+            loss_train_disc = loss_train_disc + self.calc_gp(_xgenb, xb)
+        loss_train_disc.backward()
+        if self.dp is not None:
+            self.dp.allreduce_grads(self.disc_model)
+        self.opt_disc.step()
+        return loss_train_disc.detach()
+
+    def gen_step(self):
+        """One generator step (reference progan/learner.py:854-916).  Returns the loss tensor."""
+        c = self.config
+        self.gen_model.zero_grad()
+        zb = gen_rand_latent_vars(num_samples=self.batch_size * c.gen_bs_mult, length=c.len_latent,
+                                  distribution=self.latent_distribution, device=c.dev)
+        zb.requires_grad_(True)
+        loss_train_gen = ops.g_logit_loss(self.disc_model(self.gen_model(zb)), self.loss)
+        loss_train_gen.backward()
+        if self.dp is not None:
+            self.dp.allreduce_grads(self.gen_model)
+        self.opt_gen.step()      # Adam + EWMA generator in one fused pass
+        if c.use_ewma_gen:
+            self._ewma_started = True
+        return loss_train_gen.detach()
+
+    # ------------------------------------------------------------------ train loop
+    def train(self, train_dl, valid_dl=None, z_valid_dl=None, num_main_iters=None, num_gen_iters=None,
+              num_disc_iters=None, log_every=0):
+        """reference progan/learner.py:418-1030 (signature kept; valid_dl / z_valid_dl accepted and ignored: metrics
+        are outside the hot path)."""
+        c = self.config
+        num_main_iters = c.num_main_iters if num_main_iters is None else num_main_iters
+        num_gen_iters = c.num_gen_iters if num_gen_iters is None else num_gen_iters
+        num_disc_iters = c.num_disc_iters if num_disc_iters is None else num_disc_iters
+        self.num_main_iters = num_main_iters
+        self.dataset_sz = len(train_dl.dataset) if hasattr(train_dl, 'dataset') else None
+
+        self.gen_model.to(c.dev); self.gen_model.train()
+        self.disc_model.to(c.dev); self.disc_model.train()
+        if c.use_ewma_gen:
+            self.gen_model_lagged.to(c.dev); self.gen_model_lagged.train()
+
+        def round_transition():
+            if (c.nimg_transition % self.batch_size) != 0:
+                return self.batch_size * (int(c.nimg_transition / self.batch_size) + 1)
+            return c.nimg_transition
+
+        if self.not_trained_yet or self.pretrained_model:
+            self.nimg_transition = round_transition()
+        if self.not_trained_yet:
+            self.nimg_transition_lst = [self.nimg_transition]
+            self.beta = None
+            if c.use_ewma_gen:
+                self.beta = self.get_smoothing_ewma_beta(half_life=EWMA_SMOOTHING_HALFLIFE) if COMPUTE_EWMA_VIA_HALFLIFE \
+                    else EWMA_SMOOTHING_BETA
+                self._init_lagged()
+                self._attach_ewma()
+            self.train_dataiter = iter(train_dl)
+        if self.sched_bool:
+            self._set_scheduler()
+        if self.gen_model.fade_in_phase and not hasattr(self, 'delta_alpha'):
+            self.delta_alpha = self.batch_size / ((self.nimg_transition / num_disc_iters) - self.batch_size)
+
+        self.last_losses = (None, None)
+        for itr in range(num_main_iters):
+            for p in self.disc_model.parameters():
+                p.requires_grad_(True)
+
+            # ---- phase bookkeeping (reference :560-729) ----
+            if self.gen_model.curr_res < self.gen_model.final_res:
+                if self.curr_img_num == sum(self.nimg_transition_lst):
+                    self.curr_phase_num += 1
+                    if self.curr_phase_num % 2 == 1:
+                        self.gen_model.zero_grad(); self.disc_model.zero_grad()
+                        self.gen_model.increase_scale(); self.disc_model.increase_scale()
+                        assert self.gen_model.cls_base is self.disc_model.cls_base
+                        self.gen_model.to(c.dev); self.disc_model.to(c.dev)
+                        self.batch_size = c.bs_dict[self.gen_model.curr_res]
+                        if c.use_ewma_gen:
+                            self.beta = self.get_smoothing_ewma_beta(half_life=EWMA_SMOOTHING_HALFLIFE) if \
+                                COMPUTE_EWMA_VIA_HALFLIFE else self.beta
+                            self._sync_lagged_structure()
+                        self._set_optimizer()
+                        if self.sched_bool:
+                            self.sched_stop_step += self.scheduler_gen._step_count
+                            self._set_scheduler()
+                        self._set_loss()
+                        if hasattr(train_dl, 'batch_sampler') and train_dl.batch_sampler is not None:
+                            train_dl.batch_sampler.batch_size = self.batch_size
+                        if hasattr(train_dl, 'set_resolution'):
+                            train_dl.set_resolution(self.gen_model.curr_res)
+                            self.train_dataiter = iter(train_dl)
+                        self.nimg_transition = round_transition()
+                        self.delta_alpha = self.batch_size / ((self.nimg_transition / num_disc_iters) - self.batch_size)
+                        self.gen_model.alpha = 0
+                    else:
+                        self._set_optimizer()
+                        if self.sched_bool:
+                            self.sched_stop_step += self.scheduler_gen._step_count
+                            self._set_scheduler()
+                    self.nimg_transition_lst.append(self.nimg_transition)
+            elif self._progressively_grow and self.curr_img_num == sum(self.nimg_transition_lst):
+                # final phase (reference :709-727)
+                self._set_optimizer()
+                if self.sched_bool:
+                    self.sched_stop_step += self.scheduler_gen._step_count
+                    self._set_scheduler()
+                self.curr_phase_num += 1
+                self.nimg_transition_lst.append(np.inf)
+                self._progressively_grow = False
+
+            # ---- train discriminator ----
+            for disc_iter in range(num_disc_iters):
+                loss_d = self.disc_step(self._next_real(train_dl))
+                self.curr_dataset_batch_num += 1
+                self.curr_img_num += self.batch_size
+
+            # ---- train generator ----
+            for p in self.disc_model.parameters():
+                p.requires_grad_(False)
+            for gen_iter in range(num_gen_iters):
+                loss_g = self.gen_step()
+
+            self.last_losses = (loss_d, loss_g)
+            if log_every and (itr % log_every == 0):
+                print(f'itr {itr:7d}  res {self.gen_model.curr_res:4d}  '
+                      f'{"fade-in" if self.gen_model.fade_in_phase else "stab."}  D {float(loss_d):9.4g}  G {float(loss_g):9.4g}')
+
+            if self.gen_model.fade_in_phase:
+                self.gen_model.alpha += self.delta_alpha
+            if self.sched_bool:
+                self.scheduler_gen.step()
+                self.scheduler_disc.step()
+            if self.not_trained_yet:
+                self.not_trained_yet = False
+
+        for p in self.disc_model.parameters():
+            p.requires_grad_(True)
+        return self.last_losses

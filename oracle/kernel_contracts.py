@@ -1,0 +1,327 @@
+"""CPU restatement of every kernel launcher's CONTRACT in gan_lab_b200/_kernels.py.  TEST INFRASTRUCTURE ONLY.
+
+Two uses, both from tests/ only:
+  * `-m gpu`: each CUDA launcher is compared with the function of the same name here on the same inputs
+    (per-kernel parity, fp64 available);
+  * `-m "not gpu"`: `install(monkeypatch)` swaps these in for the launchers so that the host-side logic above
+    the C-ABI (autograd wiring incl. the double backward, module/learner control flow, optimiser tables) is
+    checked on CPU against the golden fixtures.  The product never imports this module and has no such path.
+
+Everything is written with plain torch ops on the reference's arithmetic (cf. oracle/gan_oracle.py).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import gan_oracle as O
+
+ACT_NONE, ACT_LRELU = 0, 1
+
+
+def _act(v, act, slope):
+    return torch.where(v > 0, v, v * slope) if act == ACT_LRELU else v
+
+
+def _dact(y, act, slope):
+    return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, slope)) if act == ACT_LRELU else torch.ones_like(y)
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t.contiguous()
+
+
+def _b(bias, nd):
+    if bias is None:
+        return None
+    return bias.reshape(1, -1, 1, 1) if nd == 4 else bias.reshape(1, -1)
+
+
+# ---- conv / linear -------------------------------------------------------------------------------------
+def conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope):
+    y = alpha * F.conv2d(x, w, None, 1, pad)
+    if bias is not None:
+        y = y + bias_scale * _b(bias, 4)
+    return _cl(_act(y, act, slope))
+
+
+def conv_dgrad(gy, w, x_hw, pad, alpha):
+    n = gy.shape[0]
+    return _cl(alpha * torch.nn.grad.conv2d_input((n, w.shape[1], x_hw[0], x_hw[1]), w, gy, 1, pad))
+
+
+def conv_wgrad(x, gy, rs, pad, alpha):
+    return _cl(alpha * torch.nn.grad.conv2d_weight(x, (gy.shape[1], x.shape[1], rs[0], rs[1]), gy, 1, pad))
+
+
+def linear_fwd(x, w, bias, alpha, bias_scale, act, slope):
+    y = alpha * (x @ w.t())
+    if bias is not None:
+        y = y + bias_scale * bias.reshape(1, -1)
+    return _act(y, act, slope)
+
+
+def linear_dgrad(gy, w, alpha):
+    return alpha * (gy @ w)
+
+
+def linear_wgrad(x, gy, alpha):
+    return alpha * (gy.t() @ x)
+
+
+# ---- elementwise / reductions ---------------------------------------------------------------------------
+def bias_act_fwd(x, bias, bias_scale, act, slope):
+    v = x if bias is None else x + bias_scale * _b(bias, x.dim())
+    return _cl(_act(v, act, slope))
+
+
+def act_bwd(gy, y, want_bias, bias_scale, act, slope):
+    gx = gy * _dact(y, act, slope)
+    dims = (0, 2, 3) if gx.dim() == 4 else (0,)
+    return _cl(gx), (bias_scale * gx.sum(dims) if want_bias else None)
+
+
+def colsum(x, scale):
+    return scale * x.sum((0, 2, 3) if x.dim() == 4 else (0,))
+
+
+def axpby(a, b, alpha, beta):
+    return _cl(alpha * a + (beta * b if b is not None else 0))
+
+
+def scale_by(x, s_dev, scale):
+    return x * (scale * s_dev.reshape(()))
+
+
+def sumsq(x, scale):
+    return scale * (x * x).sum()
+
+
+def gp_norm_fwd(g, gamma, scale):
+    return scale * ((g.pow(2).sum(1).sqrt() - gamma) ** 2).sum()
+
+
+def gp_norm_bwd(g, s_dev, gamma, scale):
+    nrm = g.pow(2).sum(1, keepdim=True).sqrt()
+    k = torch.where(nrm > 0, 2 * scale * (nrm - gamma) / nrm.clamp_min(1e-30), torch.zeros_like(nrm))
+    return g * k * s_dev.reshape(())
+
+
+def interp_rows(a, b, eps):
+    e = eps.reshape(-1, *([1] * (a.dim() - 1)))
+    return e * a + (1 - e) * b
+
+
+def pixelnorm_fwd(x, eps):
+    return _cl(O.pixelnorm(x, eps))
+
+
+def pixelnorm_bwd(gy, x, eps):
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        y = O.pixelnorm(xx, eps)
+    return _cl(torch.autograd.grad(y, xx, gy)[0])
+
+
+def blur3x3(x):
+    return _cl(O.blur3x3(x))
+
+
+def upsample2x_fwd(x):
+    return _cl(O.upsample2x(x))
+
+
+def upsample2x_bwd(gy):
+    return _cl(F.avg_pool2d(gy, 2, 2) * 4)
+
+
+def pool_bias_act_fwd(x, bias, bias_scale, act, slope):
+    v = F.avg_pool2d(x, 2, 2)
+    if bias is not None:
+        v = v + bias_scale * _b(bias, 4)
+    return _cl(_act(v, act, slope))
+
+
+def pool_bias_act_bwd(gy, y, want_bias, bias_scale, act, slope):
+    g = gy * _dact(y, act, slope) if y is not None else gy
+    gx = 0.25 * F.interpolate(g, scale_factor=2, mode="nearest")
+    return _cl(gx), (bias_scale * g.sum((0, 2, 3)) if want_bias else None)
+
+
+# ---- StyleGAN epilogue -----------------------------------------------------------------------------------
+def _se(x, noise, nw, bias, style, slope, eps):
+    u = x
+    if noise is not None:
+        u = u + nw.reshape(1, -1, 1, 1) * noise
+    if bias is not None:
+        u = u + bias.reshape(1, -1, 1, 1)
+    t = torch.where(u > 0, u, u * slope)
+    return O.adain(O.instance_norm(t, eps), style, x.shape[1])
+
+
+def style_epilogue_fwd(x, noise, noise_weight, bias, style, slope, eps):
+    out = _se(x, noise, noise_weight, bias, style, slope, eps)
+    return _cl(out), torch.tensor([float(eps)])     # "stats" is opaque to the caller; the double keeps eps there
+
+
+def style_epilogue_bwd(gout, x, noise, noise_weight, bias, style, stats, slope):
+    eps = float(stats[0])
+    leaves = [x.detach().clone().requires_grad_(True), style.detach().clone().requires_grad_(True)]
+    nw = noise_weight.detach().clone().requires_grad_(True) if noise_weight is not None else None
+    b = bias.detach().clone().requires_grad_(True) if bias is not None else None
+    with torch.enable_grad():
+        out = _se(leaves[0], noise, nw, b, leaves[1], slope, eps)
+    ins = leaves + [t for t in (nw, b) if t is not None]
+    gs = list(torch.autograd.grad(out, ins, gout, allow_unused=True))
+    gx, gstyle = gs[0], gs[1]
+    rest = gs[2:]
+    g_nw = rest.pop(0).reshape(-1) if nw is not None else None
+    g_b = rest.pop(0).reshape(-1) if b is not None else None
+    return _cl(gx), gstyle, g_nw, g_b
+
+
+# ---- minibatch stddev ---------------------------------------------------------------------------------------
+def mbstd_fwd(x, group):
+    return _cl(O.mbstd_concat(x, group))
+
+
+def mbstd_bwd(gy, x, group):
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        y = O.mbstd_concat(xx, group)
+    return _cl(torch.autograd.grad(y, xx, gy)[0])
+
+
+def mbstd_bwdbwd(v, gy, x, group):
+    xx = x.detach().clone().requires_grad_(True)
+    gg = gy.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        y = O.mbstd_concat(xx, group)
+        gx, = torch.autograd.grad(y, xx, gg, create_graph=True)
+    ggx, ggy = torch.autograd.grad(gx, (xx, gg), v, allow_unused=True)
+    if ggx is None:
+        ggx = torch.zeros_like(x)
+    return _cl(ggx), _cl(ggy)
+
+
+# ---- RGB 1x1 convs ---------------------------------------------------------------------------------------------
+def _wmat(w, ws_j, ws_c, C):
+    """-> [3, C] matrix with element (j, c) = w.flat[j*ws_j + c*ws_c]."""
+    flat = w.reshape(-1)
+    j = torch.arange(3).view(3, 1)
+    c = torch.arange(C).view(1, C)
+    return flat[j * ws_j + c * ws_c]
+
+
+def rgb_expand(img, w, ws_j, ws_c, C, bias, pool, alpha, bias_scale, act, slope):
+    m = _wmat(w, ws_j, ws_c, C)                         # [3, C]
+    if pool:
+        img = F.avg_pool2d(img, 2, 2)
+    y = alpha * torch.einsum("njhw,jc->nchw", img, m)
+    if bias is not None:
+        y = y + bias_scale * bias.reshape(1, -1, 1, 1)
+    return _cl(_act(y, act, slope))
+
+
+def rgb_contract(x, w, ws_j, ws_c, bias, pool, alpha, bias_scale):
+    m = _wmat(w, ws_j, ws_c, x.shape[1])
+    img = alpha * torch.einsum("nchw,jc->njhw", x, m)
+    if bias is not None:
+        img = img + bias_scale * bias.reshape(1, -1, 1, 1)
+    if pool:
+        img = 0.25 * F.interpolate(img, scale_factor=2, mode="nearest")
+    return img.contiguous()
+
+
+def rgb_wgrad(img, g, w_shape, ws_j, ws_c, pool, alpha):
+    if pool:
+        img = F.avg_pool2d(img, 2, 2)
+    C = g.shape[1]
+    m = alpha * torch.einsum("njhw,nchw->jc", img, g)    # [3, C]
+    out = torch.zeros(int(np.prod(w_shape)))
+    j = torch.arange(3).view(3, 1)
+    c = torch.arange(C).view(1, C)
+    out[(j * ws_j + c * ws_c).reshape(-1)] = m.reshape(-1)
+    return out.reshape(w_shape)
+
+
+def plane_sum(img, scale):
+    return scale * img.sum((0, 2, 3))
+
+
+# ---- fade-in / losses / misc ---------------------------------------------------------------------------------------
+def fade_up_blend(lo, hi, alpha):
+    return (1 - alpha) * O.upsample2x(lo) + alpha * hi
+
+
+def fade_up_blend_bwd(gout, alpha):
+    return (1 - alpha) * F.avg_pool2d(gout, 2, 2) * 4, alpha * gout
+
+
+def fade_real(x, alpha):
+    return O.fade_real_images(x, alpha)
+
+
+def d_logit_loss(d_gen, d_real, kind, eps_drift):
+    a = d_gen.detach().clone().requires_grad_(True)
+    b = d_real.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        if kind == "wgan":
+            l = (a - b).mean()
+        else:
+            l = F.binary_cross_entropy_with_logits(a, torch.zeros_like(a)) + F.binary_cross_entropy_with_logits(b, torch.ones_like(b))
+        l = l + eps_drift * (b ** 2).mean()
+    ga, gb = torch.autograd.grad(l, (a, b))
+    return l.detach(), ga, gb
+
+
+def g_logit_loss(d_out, kind):
+    a = d_out.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        l = O.gen_loss(a, kind)
+    ga, = torch.autograd.grad(l, a)
+    return l.detach(), ga
+
+
+def w_ewma_update(w, ewma, beta):
+    m = w.mean(0)
+    ewma.copy_(m if beta == 0 else m * (1 - beta) + ewma * beta)
+    return ewma
+
+
+def _from_ptr(ptr, n):
+    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr)))
+
+
+def adam_ewma_multi(ptr_table, sizes, T, max_size, hyper, beta1, beta2, eps, wd, ewma_beta, ewma_mode):
+    lr, bc1, bc2 = float(hyper[0]), float(hyper[1]), float(hyper[2])
+    for t in range(T):
+        pp, gp, mp, vp, lp = [int(v) for v in ptr_table[t]]
+        n = int(sizes[t])
+        p = _from_ptr(pp, n)
+        if gp != 0:
+            g, m, v = _from_ptr(gp, n), _from_ptr(mp, n), _from_ptr(vp, n)
+            if wd != 0:
+                g = g + wd * p
+            m.copy_(beta1 * m + (1 - beta1) * g)
+            v.copy_(beta2 * v + (1 - beta2) * g * g)
+            p.sub_((lr / bc1) * (m / (v.sqrt() / np.sqrt(bc2) + eps)))
+        if ewma_mode != 0 and lp != 0:
+            lag = _from_ptr(lp, n)
+            prev = p if ewma_mode == 2 else lag
+            lag.copy_(p * (1 - ewma_beta) + prev * ewma_beta)
+
+
+ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and f.__module__ == __name__
+       and n not in ("install",)]
+
+
+def install(monkeypatch):
+    """Swap the CUDA launchers of gan_lab_b200._kernels for these CPU contracts (tests only)."""
+    import gan_lab_b200._kernels as K
+    for name in ALL:
+        if hasattr(K, name):
+            monkeypatch.setattr(K, name, globals()[name])
