@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- StyleGAN G+D training throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W              # our arm (sm_100a kernels through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...    # reference arm: the CPU oracle port on host cores
+
+One "step" = one main iteration of the reference's train loop = 1 D step + 1 G step on a synthetic batch
+(cfg2: StyleGAN 128x128, nonsaturating + R1 + drift, noise, InstanceNorm/AdaIN, mixing 0.9, batch 8 per GPU).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CONFIGS = {
+    # name: (model, res, init_res, batch per GPU, fade alpha or None)
+    "cfg2": ("StyleGAN", 128, 128, 8, None),
+    "cfg3": ("StyleGAN", 256, 128, 16, 0.5),
+    "cfg4": ("StyleGAN", 1024, 1024, 16, None),     # bs_dict[1024] = 16 // 4 = 4 per GPU
+    "cfg1": ("ProGAN", 32, 32, 8, None),
+}
+WORKLOAD_NAME = {
+    "cfg2": "StyleGAN 128x128 nonsaturating loss + R1, batch 8 per GPU, fp32 storage (BASELINE.json configs[1])",
+    "cfg3": "StyleGAN 256x256 mid-fade-in (alpha=0.5), batch 16 per GPU",
+    "cfg4": "StyleGAN 1024x1024, batch 4 per GPU",
+    "cfg1": "ProGAN 32x32 fixed resolution, batch 8 (BASELINE.json configs[0])",
+}
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def conv_flops_per_iter(model, res, bs):
+    """Algorithmic conv/linear FLOPs of one main iteration = 4 F_G + 14 F_D."""
+    import math
+    fm = lambda r: min(int(8192 / (2 ** (int(math.log2(r)) - 1))), 512)
+    FG = FD = 0.0
+    r = 4
+    # generator
+    if model == "StyleGAN":
+        FG += 2 * bs * 16 * 512 * 512 * 9                       # layer 1 conv at 4x4 (layer 0 has no conv)
+        FG += 2 * bs * 512 * 512 * 8 * 2                        # mapping network (x2 when mixing fires; count once)
+    else:
+        FG += 2 * bs * 512 * 8192 + 2 * bs * 16 * 512 * 512 * 9
+    while r < res:
+        r *= 2
+        ci, co = fm(r // 2), fm(r)
+        FG += 2 * bs * r * r * co * ci * 9 + 2 * bs * r * r * co * co * 9
+        if model == "StyleGAN":
+            FG += 2 * 2 * bs * 512 * 2 * co
+    FG += 2 * bs * res * res * 3 * fm(res)
+    # discriminator
+    FD += 2 * bs * res * res * 3 * fm(res)
+    r = res
+    while r > 4:
+        c, cn = fm(r), fm(r // 2)
+        FD += 2 * bs * r * r * c * c * 9 + 2 * bs * r * r * cn * c * 9
+        r //= 2
+    FD += 2 * bs * 16 * 512 * 513 * 9 + 2 * bs * 512 * 512 * 16 + 2 * bs * 512
+    return 4 * FG + 14 * FD
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf": 1400.0, "src": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own algorithm on the box's host cores: the CPU oracle port (oracle/train_oracle.py, plain
+    PyTorch fp32 = the ATen kernels the reference itself dispatches to), all host threads.  kind = "port"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.train_oracle import OracleTrainer, IterDraws, sample_gen_draws
+    from oracle import gan_oracle as O
+    model, res, init_res, bs, alpha = CONFIGS[args.config]
+    if args.config == "cfg4":
+        bs = bs // 4
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    total_steps = args.steps + args.warmup
+    sample_bs = bs
+    if total_steps > 8 and bs >= 8:
+        sample_bs = 4            # bounded sample: half batch (keeps one full minibatch-stddev group of 4)
+    gen = torch.Generator().manual_seed(0)
+    g_sd, d_sd = synth_params(model, res, gen)
+    T = OracleTrainer(g_sd, d_sd, model=model, res=res, lr=0.0015, loss="nonsaturating" if model == "StyleGAN" else "wgan",
+                      gp_type="r1" if model == "StyleGAN" else "wgan-gp", ewma_beta=O.ewma_beta(sample_bs),
+                      g_kwargs={} if model == "StyleGAN" else dict(use_pixelnorm=True))
+
+    def one():
+        real = torch.rand(sample_bs, 3, res, res, generator=gen) * 2 - 1
+        eps = torch.rand(sample_bs, 1, 1, 1, generator=gen) if model != "StyleGAN" else None
+        T.main_iter(real, IterDraws(sample_gen_draws(model, res, sample_bs, 512, gen), sample_gen_draws(model, res, sample_bs, 512, gen), eps))
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    val = sample_bs * args.steps / dt
+    sample = f"{args.steps} main iterations (1 D step + 1 G step) at batch {sample_bs} of the {bs}-per-GPU workload, after {args.warmup} warm-up"
+    line = {"impl": "reference", "metric": "StyleGAN G+D train img/s", "value": val, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME[args.config], "note": "CPU oracle port of the reference algorithm on host cores"},
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def synth_params(model, res, gen):
+    """Random-init parameter dicts with the reference's names/shapes/initialiser (N(0,1) weights under equalized LR,
+    zero biases, ones const input), built by instantiating our drop-in modules on CPU (no kernels run)."""
+    import torch
+    import gan_lab_b200._growth as growth
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.progan.learner import ProGANLearner
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    torch.manual_seed(0)
+    cfg = default_config(model, res=res, batch_size=8, dev="cpu", use_ewma_gen=False)
+    L = (StyleGANLearner if model == "StyleGAN" else ProGANLearner)(cfg)
+    return ({k: v.detach().clone().contiguous() for k, v in L.gen_model.state_dict().items()},
+            {k: v.detach().clone().contiguous() for k, v in L.disc_model.state_dict().items()})
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gan_lab_b200 as glb
+    from gan_lab_b200 import _kernels as K
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.progan.learner import ProGANLearner
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: gan_lab_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    glb.set_conv_impl(args.conv_impl)
+
+    model, res, init_res, bs_cfg, alpha = CONFIGS[args.config]
+    torch.manual_seed(0 + rank)
+    import numpy as np
+    np.random.seed(0)                                  # mixing cut-off stream shared by all ranks (SURVEY 8e caveat)
+    cfg = default_config(model, res=res, init_res=init_res, batch_size=bs_cfg, dev=str(dev))
+    L = (StyleGANLearner if model == "StyleGAN" else ProGANLearner)(cfg)
+    if alpha is not None:
+        L.gen_model.increase_scale(); L.disc_model.increase_scale()
+        L.gen_model.alpha = alpha
+        L.batch_size = cfg.bs_dict[res]
+        L._set_optimizer()
+    bs = L.batch_size
+    if world > 1:
+        from gan_lab_b200.parallel import DataParallel
+        L.dp = DataParallel(world)
+        L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
+    L.gen_model.train(); L.disc_model.train()
+    L.beta = L.get_smoothing_ewma_beta(10.)
+    L._init_lagged(); L._attach_ewma()
+
+    # synthetic data: device-resident pool for `value`, pinned host pool for `e2e`
+    n_pool = 8
+    pool_dev = [(torch.rand(bs, 3, res, res, device=dev) * 2 - 1) for _ in range(n_pool)]
+    pool_host = [(torch.rand(bs, 3, res, res) * 2 - 1).pin_memory() for _ in range(n_pool)]
+    flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
+
+    def main_iter(x):
+        for p in L.disc_model.parameters():
+            p.requires_grad_(True)
+        ld = L.disc_step(x)
+        for p in L.disc_model.parameters():
+            p.requires_grad_(False)
+        lg = L.gen_step()
+        return ld, lg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        main_iter(pool_dev[i % n_pool])
+    barrier()
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = K.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        main_iter(pool_dev[i % n_pool])
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    launches = K.launch_count() - l0
+    if sampler:
+        sampler.stop_flag.set(); sampler.join(timeout=2)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+
+    # ---- e2e: public API (Learner.train) with HOST batches; H2D of the batch and D2H of the losses per step ----
+    class HostLoader:
+        dataset = list(range(n_pool * bs))
+        batch_sampler = None
+
+        def __iter__(self):
+            return iter([(x,) for x in pool_host])
+
+    loader = HostLoader()
+    L.not_trained_yet = False                          # keep optimiser/EWMA state from the warm-up
+    L.train_dataiter = iter(loader)
+    L.nimg_transition = getattr(L, "nimg_transition", cfg.nimg_transition)
+    L.nimg_transition_lst = getattr(L, "nimg_transition_lst", [10 ** 12])
+    L.curr_img_num = 0
+    sched, L.sched_bool = L.sched_bool, False
+    barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    if L.gen_model.fade_in_phase:
+        L.delta_alpha = 0.0                            # hold alpha fixed (cfg3: mid-fade-in)
+    host_losses = []
+    # the step's result (both losses) is read back on the host every step, as the reference's tqdm line does
+    L.train(loader, num_main_iters=args.steps, step_callback=lambda i, ld, lg: host_losses.append((ld.item(), lg.item())))
+    ev2[1].record()
+    barrier()
+    ms_e2e = ev2[0].elapsed_time(ev2[1])
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t)
+    L.sched_bool = sched
+
+    # ---- roofline of the dominant kernel family (dense convs), timed live with CUDA events on the launch stream ----
+    roof = conv_roofline(L, pool_dev[0], main_iter, flush) if rank == 0 else None
+
+    if rank == 0:
+        peaks = measured_peaks()
+        imgs = bs * cfg.num_disc_iters * args.steps * world
+        value = imgs / (ms / 1e3)
+        flops = conv_flops_per_iter(model, res, bs)
+        line = {
+            "metric": "StyleGAN G+D train img/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32" if args.conv_impl == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME[args.config], "global_batch": bs * world, "parallelism": f"dp{world}",
+                       "conv_impl": args.conv_impl, "l2": "8-batch input pool; activations per step (>1 GB) exceed the 126 MB L2",
+                       "algorithmic_conv_gflop_per_step_per_gpu": flops / 1e9,
+                       "achieved_conv_tflops_whole_step": flops / (ms / args.steps / 1e3) / 1e12},
+            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": bs * 3 * res * res * 4,
+                    "d2h_bytes_per_step": 8},
+            "gpu_launches": launches,
+            "clocks": sampler.summary() if sampler else None,
+        }
+        if roof is not None:
+            roof["peak"] = peaks["tf"]
+            roof["frac"] = roof["achieved"] / peaks["tf"]
+            roof["peak_source"] = peaks["src"] + " dense bf16 (sustained); TF32 nominal peak is half of bf16"
+            line["roofline"] = roof
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(L, x, main_iter, flush):
+    """Sum of algorithmic FLOPs of every conv-family launch in one main iteration / sum of their device times
+    (CUDA events recorded on the launching stream around each launch, separate pass outside the timed region)."""
+    import torch
+    from gan_lab_b200 import _kernels as K
+    recs = []
+    orig = {}
+
+    def wrap(name, flops_fn):
+        f = getattr(K, name)
+        orig[name] = f
+
+        def g(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = f(*a, **k)
+            e1.record()
+            recs.append((name, flops_fn(a, out), e0, e1))
+            return out
+
+        setattr(K, name, g)
+
+    def f_fprop(a, out):
+        x_, w_ = a[0], a[1]
+        return 2.0 * out.shape[0] * out.shape[2] * out.shape[3] * w_.shape[0] * w_.shape[1] * w_.shape[2] * w_.shape[3]
+
+    def f_dgrad(a, out):
+        gy_, w_ = a[0], a[1]
+        return 2.0 * gy_.shape[0] * gy_.shape[2] * gy_.shape[3] * w_.shape[0] * w_.shape[1] * w_.shape[2] * w_.shape[3]
+
+    def f_wgrad(a, out):
+        gy_ = a[1]
+        return 2.0 * gy_.shape[0] * gy_.shape[2] * gy_.shape[3] * out.numel()
+
+    wrap("conv_fprop", f_fprop); wrap("conv_dgrad", f_dgrad); wrap("conv_wgrad", f_wgrad)
+    try:
+        flush.zero_()
+        main_iter(x)
+        torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(K, n, f)
+    tot_f = sum(r[1] for r in recs)
+    tot_ms = sum(r[2].elapsed_time(r[3]) for r in recs)
+    by = {}
+    for n, fl, e0, e1 in recs:
+        d = by.setdefault(n, [0.0, 0.0, 0])
+        d[0] += fl; d[1] += e0.elapsed_time(e1); d[2] += 1
+    return {"bound": "tensor", "kernel": "conv2d fprop/dgrad/wgrad family (implicit GEMM)", "achieved": tot_f / (tot_ms / 1e3) / 1e12,
+            "unit": "TFLOP/s", "traffic": None, "launches": len(recs), "conv_ms_per_step": tot_ms,
+            "by_kind_tflops": {n: d[0] / (d[1] / 1e3) / 1e12 for n, d in by.items()}}
+
+
+def cpu_baseline(args):
+    """The CPU oracle port timed on this box's host cores on a bounded sample (1 main iteration of the workload)."""
+    import torch
+    from oracle.train_oracle import OracleTrainer, IterDraws, sample_gen_draws
+    from oracle import gan_oracle as O
+    model, res, init_res, bs, alpha = CONFIGS[args.config]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(0)
+    sbs = 4
+    g_sd, d_sd = synth_params(model, res, gen)
+    T = OracleTrainer(g_sd, d_sd, model=model, res=res, lr=0.0015, loss="nonsaturating" if model == "StyleGAN" else "wgan",
+                      gp_type="r1" if model == "StyleGAN" else "wgan-gp", ewma_beta=O.ewma_beta(sbs),
+                      g_kwargs={} if model == "StyleGAN" else dict(use_pixelnorm=True))
+    real = torch.rand(sbs, 3, res, res, generator=gen) * 2 - 1
+    eps = torch.rand(sbs, 1, 1, 1, generator=gen) if model != "StyleGAN" else None
+    t0 = time.perf_counter()
+    T.main_iter(real, IterDraws(sample_gen_draws(model, res, sbs, 512, gen), sample_gen_draws(model, res, sbs, 512, gen), eps))
+    dt = time.perf_counter() - t0
+    return {"value": sbs / dt, "unit": "img/s", "cores": threads, "kind": "port",
+            "sample": f"1 main iteration (D step + G step) at batch {sbs} of the same workload, no warm-up, {threads} torch threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--conv-impl", default=os.environ.get("GLB_CONV_IMPL", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -212,7 +212,7 @@ class ProGANLearner(GANLearner):
 
     # ------------------------------------------------------------------ train loop
     def train(self, train_dl, valid_dl=None, z_valid_dl=None, num_main_iters=None, num_gen_iters=None,
-              num_disc_iters=None, log_every=0):
+              num_disc_iters=None, log_every=0, step_callback=None):
         """reference progan/learner.py:418-1030 (signature kept; valid_dl / z_valid_dl accepted and ignored: metrics
         are outside the hot path)."""
         c = self.config
@@ -309,6 +309,8 @@ class ProGANLearner(GANLearner):
                 loss_g = self.gen_step()
 
             self.last_losses = (loss_d, loss_g)
+            if step_callback is not None:
+                step_callback(itr, loss_d, loss_g)
             if log_every and (itr % log_every == 0):
                 print(f'itr {itr:7d}  res {self.gen_model.curr_res:4d}  '
                       f'{"fade-in" if self.gen_model.fade_in_phase else "stab."}  D {float(loss_d):9.4g}  G {float(loss_g):9.4g}')

@@ -1,0 +1,267 @@
+"""Parity case bodies shared by the CPU host-wiring tests (kernels replaced by their CPU contracts) and the
+GPU parity tests (real sm_100a kernels through the C-ABI).  Expected values: fixtures from the UNMODIFIED reference."""
+import math
+
+import torch
+
+from gan_lab_b200.config import default_config
+from gan_lab_b200.utils import custom_layers as CL
+from gan_lab_b200.utils.latent_utils import TapeSource, set_random_source
+
+
+CONV_CASES = ["conv3x3", "conv3x3_nobias", "conv1x1_torgb", "conv1x1_fromrgb", "conv4x4_valid", "conv3x3_c33",
+              "conv3x3_lrmul"]
+LINEAR_CASES = ["linear_mapping", "linear_style", "linear_dhead", "linear_progan_fc"]
+MBSTD_CASES = ["mbstd_n8", "mbstd_n4", "mbstd_n6", "mbstd_n1", "mbstd_n16"]
+STYLE_NETS = ["style_nets_res16.pt", "style_nets_res16_fade.pt"]
+PRO_NETS = ["pro_nets_res16.pt", "pro_nets_res8_fade.pt"]
+TRAIN_CASES = [("style_train_res16.pt", "StyleGAN"), ("pro_train_res8.pt", "ProGAN")]
+
+
+def _to(g, dev):
+    """Move every tensor of a (nested) fixture to `dev`."""
+    if torch.is_tensor(g):
+        return g.to(dev)
+    if isinstance(g, dict):
+        return {k: _to(v, dev) for k, v in g.items()}
+    if isinstance(g, (list, tuple)):
+        return type(g)(_to(v, dev) for v in g)
+    return g
+
+
+def relerr(a, b):
+    return float((a.detach() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def close(a, b, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(a.detach().contiguous(), b.contiguous(), rtol=rtol, atol=atol)
+
+
+def _load(module, sd):
+    missing, unexpected = module.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+
+
+def case_conv2d_ex_module(golden, dev, name):
+    g = _to(golden("layers.pt")[name], dev)
+    c = g["cfg"]
+    m = CL.Conv2dEx(ni=c["ni"], nf=c["nf"], ks=c["ks"], stride=1, padding=c["padding"], init="He", init_type="StyleGAN",
+                    gain_sq_base=c["gain_sq_base"], equalized_lr=True, lrmul=c["lrmul"], include_bias=c["include_bias"])
+    assert abs(m.wscale - g["wscale"]) < 1e-12
+    _load(m, g["sd"]); m.to(dev)
+    assert m.conv2d.weight.is_contiguous(memory_format=torch.channels_last)
+    x = g["x"].clone().requires_grad_(True)
+    y = m(x)
+    close(y, g["y"])
+    gx, = torch.autograd.grad(y, x, g["gy"], create_graph=True)
+    close(gx, g["gx"])
+    m.zero_grad()
+    (gx * g["v"]).sum().backward(retain_graph=True)          # double backward -> weight
+    close(m.conv2d.weight.grad, g["gg_w"], rtol=1e-3, atol=1e-5)
+    m.zero_grad()
+    y.backward(g["gy"])
+    for k, p in m.named_parameters():
+        close(p.grad, g["grads"][k], rtol=1e-3, atol=1e-5)
+
+
+def case_linear_ex_module(golden, dev, name):
+    g = _to(golden("layers.pt")[name], dev)
+    c = g["cfg"]
+    m = CL.LinearEx(nin_feat=c["nin"], nout_feat=c["nout"], init="He", init_type="StyleGAN",
+                    gain_sq_base=c["gain_sq_base"], equalized_lr=True, lrmul=c["lrmul"])
+    _load(m, g["sd"]); m.to(dev)
+    x = g["x"].clone().requires_grad_(True)
+    y = m(x)
+    close(y, g["y"])
+    gx, = torch.autograd.grad(y, x, g["gy"], create_graph=True)
+    close(gx, g["gx"])
+    m.zero_grad()
+    (gx * g["v"]).sum().backward(retain_graph=True)
+    close(m.linear.weight.grad, g["gg_w"], rtol=1e-3, atol=1e-6)
+    m.zero_grad()
+    y.backward(g["gy"])
+    for k, p in m.named_parameters():
+        close(p.grad, g["grads"][k], rtol=1e-3, atol=1e-6)
+
+
+def case_small_modules(golden, dev):
+    L = _to(golden("layers.pt"), dev)
+    g = L["conv2dbias"]
+    m = CL.Conv2dBias(16, device=dev); _load(m, g["sd"]); m.to(dev)
+    x = g["x"].clone().requires_grad_(True)
+    y = m(x); close(y, g["y"]); y.backward(g["gy"])
+    close(x.grad, g["gx"]); close(m.bias.grad, g["grads"]["bias"])
+    for k in ("pixelnorm_z", "pixelnorm_feat"):
+        g = L[k]
+        x = g["x"].clone().requires_grad_(True)
+        y = CL.PixelNorm2d()(x); close(y, g["y"]); y.backward(g["gy"]); close(x.grad, g["gx"])
+    for k in ("blur", "blur_odd"):
+        g = L[k]
+        if g["x"].shape[1] % 4:
+            continue                    # NHWC glue kernels need C % 4 == 0 (every gan-lab feature map has it)
+        x = g["x"].clone().requires_grad_(True)
+        gy = g["gy"].clone().requires_grad_(True)
+        y = CL.get_blur_op("binomial", x.shape[1])(x); close(y, g["y"])
+        gx, = torch.autograd.grad(y, x, gy, create_graph=True); close(gx, g["gx"])
+        close(torch.autograd.grad(gx, gy, g["v"])[0], g["ggy"])
+    g = L["upsample2x"]
+    x = g["x"].clone().requires_grad_(True)
+    y = CL.Upsample2x()(x); close(y, g["y"]); y.backward(g["gy"]); close(x.grad, g["gx"])
+    g = L["pool_bias_lrelu"]
+    from gan_lab_b200 import ops
+    x = g["x"].clone().requires_grad_(True); gy = g["gy"].clone().requires_grad_(True)
+    y = ops.pool_bias_act(x, g["bias"], 1.0, ops.ACT_LRELU, 0.2); close(y, g["y"])
+    gx, = torch.autograd.grad(y, x, gy, create_graph=True); close(gx, g["gx"])
+    close(torch.autograd.grad(gx, gy, g["v"])[0], g["ggy"])
+
+
+def case_mbstd_module(golden, dev, name):
+    g = _to(golden("layers.pt")[name], dev)
+    x = g["x"].clone().requires_grad_(True)
+    gy = g["gy"].clone().requires_grad_(True)
+    y = CL.concat_mbstd_layer(x, g["group_size"])
+    close(y, g["y"])
+    gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+    close(gx, g["gx"])
+    if x.shape[0] > 1:
+        ggx, ggy = torch.autograd.grad(gx, (x, gy), g["v"])
+        close(ggx, g["ggx"], rtol=1e-3, atol=1e-6); close(ggy, g["ggy"], rtol=1e-3, atol=1e-6)
+
+
+def case_style_epilogue_op(golden, dev):
+    from gan_lab_b200 import ops
+    g = _to(golden("layers.pt")["style_epilogue"], dev)
+    x = g["x"].clone().requires_grad_(True); st = g["style"].clone().requires_grad_(True)
+    nw = g["noise_weight"].clone().requires_grad_(True); b = g["bias"].clone().requires_grad_(True)
+    y = ops.style_epilogue(x, g["noise"], nw, b, st, 0.2, 1e-8)
+    close(y, g["y"], atol=1e-5)
+    y.backward(g["gy"])
+    close(x.grad, g["gx"], rtol=1e-3); close(st.grad, g["gstyle"], rtol=1e-3)
+    close(nw.grad, g["g_noise_weight"], rtol=1e-3); close(b.grad, g["g_bias"], rtol=1e-3)
+
+
+def _grads_ok(module, ref, rtol):
+    for k, p in module.named_parameters():
+        r = ref[k]
+        if r is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert p.grad is not None, k
+            assert relerr(p.grad, r) < rtol, (k, relerr(p.grad, r))
+
+
+def _style_learner(g, fade, dev):
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    res = g["res"]
+    cfg = default_config("StyleGAN", res=res, init_res=res // 2 if fade else res, batch_size=g["bs"], dev=dev,
+                         len_latent=g["len_latent"], len_dlatent=g["len_latent"], cutoff_trunc_trick=int(math.log2(res)) - 2)
+    L = StyleGANLearner(cfg)
+    if fade:
+        L.gen_model.increase_scale(); L.disc_model.increase_scale()
+        L.gen_model.alpha = g["alpha"]
+    return L
+
+
+def case_style_nets_modules(golden, dev, fname):
+    g = _to(golden(fname), dev)
+    L = _style_learner(g, g["fade_in"], dev)
+    G, D = L.gen_model, L.disc_model
+    assert list(G.state_dict().keys()) == list(g["g_sd"].keys())      # same names AND order as the reference
+    assert list(D.state_dict().keys()) == list(g["d_sd"].keys())
+    _load(G, g["g_sd"]); _load(D, g["d_sd"])
+    G.train(); D.train()
+    set_random_source(TapeSource(g["tape"], dev))
+    img = G(g["z"])
+    close(img, g["img"], rtol=1e-4, atol=1e-5)
+    close(G.w_ewma, g["w_ewma"])
+    G.zero_grad(); img.backward(g["gimg"])
+    _grads_ok(G, g["g_grads"], 2e-3)
+    D.zero_grad()
+    logits = D(g["x"])
+    close(logits, g["logits"], rtol=1e-4, atol=1e-5)
+    logits.backward(g["glog"])
+    _grads_ok(D, g["d_grads"], 2e-4)
+    D.zero_grad()
+    L.batch_size = g["bs"]
+    pen = L.calc_gp(g["img"], g["x"])
+    assert relerr(pen, g["gp"]) < 1e-4
+    pen.backward()
+    _grads_ok(D, g["d_gp_grads"], 5e-4)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    xi = g["img"].clone().requires_grad_(True)
+    gxi, = torch.autograd.grad(D(xi), xi, g["glog"])
+    assert relerr(gxi, g["d_gx_img"]) < 2e-4
+
+
+def case_pro_nets_modules(golden, dev, fname):
+    from gan_lab_b200.progan.learner import ProGANLearner
+    g = _to(golden(fname), dev)
+    res = g["res"]
+    cfg = default_config("ProGAN", res=res, init_res=res // 2 if g["fade_in"] else res, batch_size=g["bs"], dev=dev,
+                         len_latent=g["len_latent"])
+    L = ProGANLearner(cfg)
+    G, D = L.gen_model, L.disc_model
+    if g["fade_in"]:
+        G.increase_scale(); D.increase_scale(); G.alpha = g["alpha"]
+    assert list(G.state_dict().keys()) == list(g["g_sd"].keys())
+    assert list(D.state_dict().keys()) == list(g["d_sd"].keys())
+    _load(G, g["g_sd"]); _load(D, g["d_sd"])
+    G.train(); D.train()
+    img = G(g["z"])
+    close(img, g["img"], rtol=1e-4, atol=1e-5)
+    G.zero_grad(); img.backward(g["gimg"]); _grads_ok(G, g["g_grads"], 2e-4)
+    D.zero_grad()
+    logits = D(g["x"]); close(logits, g["logits"], rtol=1e-4, atol=1e-5)
+    logits.backward(g["glog"]); _grads_ok(D, g["d_grads"], 2e-4)
+    D.zero_grad()
+    L.batch_size = g["bs"]
+    set_random_source(TapeSource(g["gp_tape"], dev))
+    pen = L.calc_gp(g["img"], g["x"])
+    assert relerr(pen, g["gp"]) < 1e-4
+    pen.backward(); _grads_ok(D, g["d_gp_grads"], 5e-4)
+
+
+def case_learner_train(golden, dev, fname, model):
+    """Learner.train() for two main iterations (D step, G step, fused Adam, EWMA, w_ewma) vs the reference's."""
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    from gan_lab_b200.progan.learner import ProGANLearner
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    g = _to(golden(fname), dev)
+    res, bs, iters = g["res"], g["bs"], g["iters"]
+    if model == "StyleGAN":
+        cfg = default_config("StyleGAN", res=res, batch_size=bs, dev=dev, len_latent=g["len_latent"],
+                             len_dlatent=g["len_latent"], cutoff_trunc_trick=int(math.log2(res)) - 2)
+        L = StyleGANLearner(cfg)
+    else:
+        cfg = default_config("ProGAN", res=res, batch_size=bs, dev=dev, len_latent=g["len_latent"])
+        L = ProGANLearner(cfg)
+    _load(L.gen_model, g["g_sd0"]); _load(L.disc_model, g["d_sd0"])
+    _load(L.gen_model_lagged, g["g_sd0"])
+    ds = TensorDataset(g["data"])
+    dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+    set_random_source(TapeSource(g["tape"], dev))
+    losses = []
+    orig_d, orig_g = L.disc_step, L.gen_step
+    L.disc_step = lambda xb: losses.append(float(orig_d(xb))) or torch.tensor(losses[-1])
+    L.gen_step = lambda: losses.append(float(orig_g())) or torch.tensor(losses[-1])
+    L.train(dl, num_main_iters=iters)
+    # the first loss is a pure function of the inputs; later ones sit behind Adam(beta1=0) sign-like updates, where
+    # a rounding-level gradient difference moves a parameter by 2*lr -> allow 1e-3 there.
+    for i, (a, b) in enumerate(zip(losses, g["losses"])):
+        assert abs(a - b) < (1e-4 if i == 0 else 1e-3) * max(1.0, abs(b)), (losses, g["losses"])
+
+    def adam_close(mine, ref, what):
+        bad = tot = 0
+        for k, v in ref.items():
+            d = (mine[k].detach() - v).abs()
+            assert float(d.max()) <= 2.001 * g["lr"] * iters + 1e-6, (what, k, float(d.max()))
+            bad += int((d > 2e-5 + 1e-4 * v.abs()).sum()); tot += v.numel()
+        assert bad <= 0.03 * tot, (what, bad, tot)   # scattered +-2*lr sign flips, never concentrated
+
+    adam_close(L.gen_model.state_dict(), g["g_sd1"], "G")
+    adam_close(L.disc_model.state_dict(), g["d_sd1"], "D")
+    adam_close(dict(L.gen_model_lagged.named_parameters()), g["lagged"], "EWMA-G")
+    assert abs(L.beta - g["beta"]) < 1e-12
+    if model == "StyleGAN":
+        close(L.gen_model.w_ewma, g["w_ewma"], rtol=1e-3, atol=1e-5)

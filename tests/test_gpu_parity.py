@@ -1,0 +1,249 @@
+"""Parity tests proper: the sm_100a kernels, called through the C-ABI, against
+  (1) the per-kernel CPU contracts (oracle/kernel_contracts.py) on seeded inputs,
+  (2) the golden fixtures produced by the UNMODIFIED reference (tests/golden),
+  (3) size-independent properties at the BASELINE.json full shapes (linearity / adjointness / closure).
+Tolerance for the fp32 path: <= 1e-4 relative to the tensor's max-norm (north star), stated per assert.
+Run on the B200 box:  python -m pytest tests -m gpu
+"""
+import math
+
+import pytest
+import torch
+
+import gan_lab_b200._growth as growth
+import gan_lab_b200._kernels as K
+from gan_lab_b200.utils.latent_utils import set_random_source
+from oracle import kernel_contracts as C
+
+import parity_cases as PC
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def small_fmaps(monkeypatch):
+    monkeypatch.setattr(growth, "FMAP_MAX", 32)
+    K.set_conv_impl("fp32")
+    yield
+    set_random_source(None)
+
+
+def rel(a, b):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def rn(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g)
+
+
+def cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def both(name, *args, tol=TOL, **kw):
+    """Run launcher `name` on the GPU and its CPU contract on the same inputs; compare every output."""
+    gargs = [a.to(DEV) if torch.is_tensor(a) else a for a in args]
+    out_g = getattr(K, name)(*gargs, **kw)
+    out_c = getattr(C, name)(*[a.double() if torch.is_tensor(a) else a for a in args], **kw)
+    if torch.is_tensor(out_g):
+        out_g, out_c = (out_g,), (out_c,)
+    for i, (g, c) in enumerate(zip(out_g, out_c)):
+        if c is None or g is None:
+            assert c is None and g is None
+            continue
+        assert tuple(g.shape) == tuple(c.shape), (name, i, g.shape, c.shape)
+        assert rel(g, c) < tol, (name, i, rel(g, c))
+    return out_g
+
+
+# ------------------------------------------------------------------------------------------ kernels vs contracts
+CONV_SHAPES = [  # N, H, W, Ci, Co, R, pad
+    (8, 4, 4, 32, 32, 3, 1), (2, 16, 16, 64, 32, 3, 1), (4, 8, 8, 33, 32, 3, 1), (8, 4, 4, 32, 48, 4, 0),
+    (3, 5, 7, 20, 24, 3, 1), (2, 8, 8, 16, 16, 1, 0), (1, 32, 32, 128, 128, 3, 1), (8, 4, 4, 513, 64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_family_vs_contract(shape):
+    N, H, W, Ci, Co, R, pad = shape
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, R, R, seed=1)), rn(Co, seed=2)
+    Ho = H + 2 * pad - R + 1
+    gy = cl(rn(N, Co, Ho, W + 2 * pad - R + 1, seed=3))
+    both("conv_fprop", x, w, b, pad, 0.37, 0.5, K.ACT_LRELU, 0.2)
+    both("conv_fprop", x, w, None, pad, 1.0, 1.0, K.ACT_NONE, 0.2)
+    both("conv_dgrad", gy, w, (H, W), pad, 0.37)
+    both("conv_wgrad", x, gy, (R, R), pad, 0.37)
+
+
+@pytest.mark.parametrize("M,Kf,Nout", [(8, 32, 32), (8, 512, 512), (4, 512, 8192), (8, 512, 1), (64, 8192, 1), (5, 37, 11)])
+def test_linear_family_vs_contract(M, Kf, Nout):
+    x, w, b, gy = rn(M, Kf), rn(Nout, Kf, seed=1), rn(Nout, seed=2), rn(M, Nout, seed=3)
+    both("linear_fwd", x, w, b, 0.01, 0.01, K.ACT_LRELU, 0.2)
+    both("linear_dgrad", gy, w, 0.3)
+    both("linear_wgrad", x, gy, 0.3)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 16, 8, 8), (4, 512, 4, 4), (1, 128, 32, 32), (3, 2048, 2, 2), (2, 32, 6, 10)])
+def test_glue_kernels_vs_contract(N, C, H, W):
+    x, y, gy, b = cl(rn(N, C, H, W)), cl(rn(N, C, H, W, seed=1)), cl(rn(N, C, H, W, seed=2)), rn(C, seed=3)
+    both("bias_act_fwd", x, b, 0.7, K.ACT_LRELU, 0.2)
+    both("act_bwd", gy, y, True, 0.7, K.ACT_LRELU, 0.2)
+    both("act_bwd", gy, y, False, 1.0, K.ACT_LRELU, 0.2)
+    both("colsum", x, 0.5)
+    both("axpby", x, y, 0.3, 0.7)
+    both("sumsq", x, 0.01)
+    both("blur3x3", x)
+    both("upsample2x_fwd", x)
+    both("pool_bias_act_fwd", x, b, 0.7, K.ACT_LRELU, 0.2)
+    both("pool_bias_act_fwd", x, None, 1.0, K.ACT_NONE, 0.2)
+    gyp, yp = cl(rn(N, C, H // 2, W // 2, seed=4)), cl(rn(N, C, H // 2, W // 2, seed=5))
+    both("upsample2x_bwd", gy)
+    both("pool_bias_act_bwd", gyp, yp, True, 0.7, K.ACT_LRELU, 0.2)
+    both("pool_bias_act_bwd", gyp, None, False, 1.0, K.ACT_NONE, 0.2)
+    if C <= 1024:
+        both("pixelnorm_fwd", x, 1e-8)
+        both("pixelnorm_bwd", gy, x, 1e-8)
+
+
+def test_pixelnorm_latents():
+    x, gy = rn(8, 512), rn(8, 512, seed=1)
+    both("pixelnorm_fwd", x, 1e-8)
+    both("pixelnorm_bwd", gy, x, 1e-8)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 32, 8, 8), (8, 512, 4, 4), (2, 128, 64, 64), (2, 16, 128, 128), (3, 64, 16, 16)])
+def test_style_epilogue_vs_contract(N, C, H, W):
+    x, noise, nw, b = cl(rn(N, C, H, W)), rn(N, 1, H, W, seed=1), rn(C, seed=2) * .3, rn(C, seed=3) * .3
+    style, gout = rn(N, 2 * C, seed=4), cl(rn(N, C, H, W, seed=5))
+    out_g, stats = K.style_epilogue_fwd(x.to(DEV), noise.to(DEV), nw.to(DEV), b.to(DEV), style.to(DEV), 0.2, 1e-8)
+    out_c, st_c = C.style_epilogue_fwd(x.double(), noise.double(), nw.double(), b.double(), style.double(), 0.2, 1e-8)
+    assert rel(out_g, out_c) < TOL
+    g = K.style_epilogue_bwd(gout.to(DEV), x.to(DEV), noise.to(DEV), nw.to(DEV), b.to(DEV), style.to(DEV), stats, 0.2)
+    c = C.style_epilogue_bwd(gout.double(), x.double(), noise.double(), nw.double(), b.double(), style.double(), st_c, 0.2)
+    for name, a, r in zip(("gx", "gstyle", "g_nw", "g_b"), g, c):
+        # g_b / g_nw pass through the mean-removing InstanceNorm: cancellation-dominated -> 5e-4
+        assert rel(a, r) < (5e-4 if name in ("g_nw", "g_b") else TOL), (name, rel(a, r))
+    # InstanceNorm alone (no noise / bias, identity activation, zero style)
+    o2, _ = K.style_epilogue_fwd(x.to(DEV), None, None, None, torch.zeros(N, 2 * C, device=DEV), 1.0, 1e-8)
+    from oracle import gan_oracle as O
+    assert rel(o2, O.instance_norm(x.double(), 1e-8)) < TOL
+
+
+@pytest.mark.parametrize("N,C,group", [(8, 16, 4), (4, 512, 4), (6, 8, 6), (1, 8, 1), (16, 512, 4)])
+def test_mbstd_vs_contract(N, C, group):
+    x, gy, v = cl(rn(N, C, 4, 4)), cl(rn(N, C + 1, 4, 4, seed=1)), cl(rn(N, C, 4, 4, seed=2))
+    both("mbstd_fwd", x, group)
+    both("mbstd_bwd", gy, x, group)
+    if N > 1:
+        both("mbstd_bwdbwd", v, gy, x, group, tol=5e-4)
+
+
+@pytest.mark.parametrize("N,C,H,W,pool", [(2, 32, 16, 16, False), (2, 128, 8, 8, True), (4, 16, 32, 32, False),
+                                           (1, 512, 4, 4, False), (2, 2048, 2, 2, False)])
+def test_rgb_kernels_vs_contract(N, C, H, W, pool):
+    s = 2 if pool else 1
+    img, feat = rn(N, 3, H * s, W * s), cl(rn(N, C, H, W, seed=1))
+    w_from, w_to, b = rn(C, 3, 1, 1, seed=2), rn(3, C, 1, 1, seed=3), rn(C, seed=4)
+    both("rgb_expand", img, w_from, 1, 3, C, b, pool, 0.4, 0.9, K.ACT_LRELU, 0.2)        # fromRGB
+    both("rgb_expand", img, w_to, C, 1, C, None, pool, 0.4, 1.0, K.ACT_NONE, 0.2)       # toRGB dgrad
+    both("rgb_contract", feat, w_to, C, 1, rn(3, seed=5), pool, 0.4, 0.9)              # toRGB
+    both("rgb_contract", feat, w_from, 1, 3, None, pool, 0.4, 1.0)                     # fromRGB dgrad
+    both("rgb_wgrad", img, feat, (C, 3, 1, 1), 1, 3, pool, 0.4)
+    both("rgb_wgrad", img, feat, (3, C, 1, 1), C, 1, pool, 0.4)
+    both("plane_sum", img, 0.5)
+
+
+def test_misc_kernels_vs_contract():
+    lo, hi, gout = rn(2, 3, 8, 8), rn(2, 3, 16, 16, seed=1), rn(2, 3, 16, 16, seed=2)
+    both("fade_up_blend", lo, hi, 0.3)
+    both("fade_up_blend_bwd", gout, 0.3)
+    both("fade_real", hi, 0.3)
+    dg, dr = rn(8), rn(8, seed=1)
+    for kind in ("wgan", "nonsaturating", "minimax"):
+        if kind != "minimax":
+            both("d_logit_loss", dg, dr, kind, 0.001)
+        both("g_logit_loss", dg, kind)
+    g = rn(4, 3, 16, 16)
+    s = torch.tensor(0.7)
+    both("scale_by", g, s, 1.3)
+    both("gp_norm_fwd", g, 1.0, 0.01)
+    both("gp_norm_bwd", g, s, 1.0, 0.01)
+    both("interp_rows", rn(4, 3, 8, 8), rn(4, 3, 8, 8, seed=1), torch.rand(4, 1, 1, 1))
+    w = rn(8, 512)
+    e1 = torch.zeros(512, device=DEV)
+    K.w_ewma_update(w.to(DEV), e1, 0.0)
+    assert rel(e1, w.mean(0)) < TOL
+    K.w_ewma_update(w.to(DEV) * 2, e1, 0.995)
+    assert rel(e1, w.mean(0) * 2 * .005 + w.mean(0) * .995) < TOL
+
+
+def test_fused_adam_ewma_matches_torch_adam():
+    from gan_lab_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(64, 32, 3, 3), (32,), (1, 32, 1, 1), (7, 5)]
+    ps = [torch.randn(s, device=DEV).requires_grad_(True) for s in shapes]
+    ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    lag = {str(i): p.detach().clone() for i, p in enumerate(ps)}
+    ref_lag = None
+    mine = FusedAdam(ps, lr=1e-3, betas=(0.0, 0.99), eps=1e-8)
+    mine.attach_ewma([(str(i), p) for i, p in enumerate(ps)], lag, 0.999)
+    ref = torch.optim.Adam(qs, lr=1e-3, betas=(0.0, 0.99), eps=1e-8)
+    for step in range(3):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad = g.clone(); q.grad = g.clone()
+        mine.step(); ref.step()
+        ref_lag = [q.detach() * (1 - 0.999) + (q.detach() if ref_lag is None else ref_lag[i]) * 0.999 for i, q in enumerate(qs)]
+        for i, (p, q) in enumerate(zip(ps, qs)):
+            assert rel(p, q) < 1e-6, (step, i)
+            assert rel(lag[str(i)], ref_lag[i]) < 1e-6, (step, i)
+
+
+# ------------------------------------------------------------------------------------------ modules / nets / train vs golden
+@pytest.mark.parametrize("name", PC.CONV_CASES)
+def test_conv2d_ex_module(golden, name):
+    PC.case_conv2d_ex_module(golden, DEV, name)
+
+
+@pytest.mark.parametrize("name", PC.LINEAR_CASES)
+def test_linear_ex_module(golden, name):
+    PC.case_linear_ex_module(golden, DEV, name)
+
+
+def test_small_modules(golden):
+    PC.case_small_modules(golden, DEV)
+
+
+@pytest.mark.parametrize("name", PC.MBSTD_CASES)
+def test_mbstd_module(golden, name):
+    PC.case_mbstd_module(golden, DEV, name)
+
+
+def test_style_epilogue_op(golden):
+    PC.case_style_epilogue_op(golden, DEV)
+
+
+@pytest.mark.parametrize("fname", PC.STYLE_NETS)
+def test_style_nets_modules(golden, fname):
+    PC.case_style_nets_modules(golden, DEV, fname)
+
+
+@pytest.mark.parametrize("fname", PC.PRO_NETS)
+def test_pro_nets_modules(golden, fname):
+    PC.case_pro_nets_modules(golden, DEV, fname)
+
+
+@pytest.mark.parametrize("fname,model", PC.TRAIN_CASES)
+def test_learner_train(golden, fname, model):
+    PC.case_learner_train(golden, DEV, fname, model)
+
+
+def test_library_was_loaded():
+    from gan_lab_b200._lib import LIB
+    assert LIB._dll is not None and K.launch_count() > 0
