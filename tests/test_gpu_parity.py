@@ -13,7 +13,7 @@ import torch
 import gan_lab_b200._growth as growth
 import gan_lab_b200._kernels as K
 from gan_lab_b200.utils.latent_utils import set_random_source
-from oracle import kernel_contracts as C
+from oracle import kernel_contracts as KC
 
 import parity_cases as PC
 
@@ -49,7 +49,7 @@ def both(name, *args, tol=TOL, **kw):
     """Run launcher `name` on the GPU and its CPU contract on the same inputs; compare every output."""
     gargs = [a.to(DEV) if torch.is_tensor(a) else a for a in args]
     out_g = getattr(K, name)(*gargs, **kw)
-    out_c = getattr(C, name)(*[a.double() if torch.is_tensor(a) else a for a in args], **kw)
+    out_c = getattr(KC, name)(*[a.double() if torch.is_tensor(a) else a for a in args], **kw)
     if torch.is_tensor(out_g):
         out_g, out_c = (out_g,), (out_c,)
     for i, (g, c) in enumerate(zip(out_g, out_c)):
@@ -121,10 +121,10 @@ def test_style_epilogue_vs_contract(N, C, H, W):
     x, noise, nw, b = cl(rn(N, C, H, W)), rn(N, 1, H, W, seed=1), rn(C, seed=2) * .3, rn(C, seed=3) * .3
     style, gout = rn(N, 2 * C, seed=4), cl(rn(N, C, H, W, seed=5))
     out_g, stats = K.style_epilogue_fwd(x.to(DEV), noise.to(DEV), nw.to(DEV), b.to(DEV), style.to(DEV), 0.2, 1e-8)
-    out_c, st_c = C.style_epilogue_fwd(x.double(), noise.double(), nw.double(), b.double(), style.double(), 0.2, 1e-8)
+    out_c, st_c = KC.style_epilogue_fwd(x.double(), noise.double(), nw.double(), b.double(), style.double(), 0.2, 1e-8)
     assert rel(out_g, out_c) < TOL
     g = K.style_epilogue_bwd(gout.to(DEV), x.to(DEV), noise.to(DEV), nw.to(DEV), b.to(DEV), style.to(DEV), stats, 0.2)
-    c = C.style_epilogue_bwd(gout.double(), x.double(), noise.double(), nw.double(), b.double(), style.double(), st_c, 0.2)
+    c = KC.style_epilogue_bwd(gout.double(), x.double(), noise.double(), nw.double(), b.double(), style.double(), st_c, 0.2)
     for name, a, r in zip(("gx", "gstyle", "g_nw", "g_b"), g, c):
         # g_b / g_nw pass through the mean-removing InstanceNorm: cancellation-dominated -> 5e-4
         assert rel(a, r) < (5e-4 if name in ("g_nw", "g_b") else TOL), (name, rel(a, r))
