@@ -73,25 +73,43 @@ def _flat(t):
 
 
 # --------------------------------------------------------------------------- conv family
+_KIND = {"fprop": 0, "dgrad": 1, "wgrad": 2}
+
+
 def tc_covers(kind: str, N, H, W, Ci, Co, R, S, pad) -> bool:
-    """Host-side mirror of the tcgen05 kernels' shape coverage (csrc/conv_tc.cu)."""
-    if not (R == S == 3 and pad == 1):
-        return False
-    if Ci % 32 or Co % 32 or Ci < 32 or Co < 32:
-        return False
-    # M tile = 128 output pixels laid out as (images x rows x cols) boxes
-    bw = min(W, 16)
-    bh = min(H, 128 // bw)
-    bn = 128 // (bw * bh)
-    if W % bw or H % bh or N % bn:
-        return False
-    return _state.get("tc_enabled", False)
+    """Does the tcgen05 kernel of `kind` cover this shape?  Answered by the library itself (csrc/conv_tc.cu)."""
+    return bool(LIB.fn("glb_conv2d_tc_covers")(_KIND[kind], N, H, W, Ci, Co, R, S, pad))
 
 
 def _impl_for(kind, N, H, W, Ci, Co, R, S, pad):
     if _state["conv_impl"] == "tf32" and tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
         return IMPL_TF32
     return IMPL_FP32
+
+
+_wt_cache = {}
+
+
+def weights_updated():
+    """Called by the optimiser after it has rewritten parameters through raw pointers (no torch version bump)."""
+    _wt_cache.clear()
+
+
+def transposed_weight(w):
+    """wt[Ci][R][S][Co] with flipped taps (what the tensor-core dgrad multiplies by).  Cached per weight tensor and
+    version so the re-layout runs once per optimiser step however many backward passes reuse the weight; the entry
+    keeps `w` alive, so its address cannot be recycled for another tensor while the entry exists."""
+    key = (w.data_ptr(), tuple(w.shape))
+    hit = _wt_cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    Co, Ci, R, S = w.shape
+    wt = torch.empty((Ci, Co, R, S), device=w.device, dtype=torch.float32, memory_format=torch.channels_last)
+    _call("glb_conv2d_weight_transpose", _p(w), _p(wt), Co, R, S, Ci, _stream())
+    if len(_wt_cache) >= 96:
+        _wt_cache.clear()
+    _wt_cache[key] = (w._version, wt, w)
+    return wt
 
 
 def conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope):
@@ -118,8 +136,9 @@ def conv_dgrad(gy, w, x_hw, pad, alpha):
     if Co != Co2 or Ho != H + 2 * pad - R + 1 or Wo != W + 2 * pad - S + 1:
         raise GlbError("conv_dgrad: shape mismatch")
     gx = _new_nhwc(N, Ci, H, W, gy)
-    _call("glb_conv2d_dgrad", _p(gy), _p(w), _p(gx), N, H, W, Ci, Co, R, S, pad, float(alpha),
-          _impl_for("dgrad", N, H, W, Ci, Co, R, S, pad), _stream())
+    impl = _impl_for("dgrad", N, H, W, Ci, Co, R, S, pad)
+    wt = transposed_weight(w) if impl == IMPL_TF32 else None
+    _call("glb_conv2d_dgrad", _p(gy), _p(w), _p(wt), _p(gx), N, H, W, Ci, Co, R, S, pad, float(alpha), impl, _stream())
     return gx
 
 

@@ -13,6 +13,9 @@ int conv_fprop_tc(const float*, const float*, const float*, float*, int, int, in
                   float, cudaStream_t);
 int conv_dgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
 int conv_wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
+bool conv_fprop_tc_covers(int, int, int, int, int, int, int, int);
+bool conv_dgrad_tc_covers(int, int, int, int, int, int, int, int);
+bool conv_wgrad_tc_covers(int, int, int, int, int, int, int, int);
 }  // namespace glb
 
 extern "C" const char* glb_last_error(void) { return glb::g_last_error.c_str(); }
@@ -35,10 +38,20 @@ extern "C" int glb_conv2d_fprop(const float* x, const float* w, const float* bia
   return glb::conv_fprop_simt(x, w, bias, y, N, H, W, Ci, Co, R, S, pad, alpha, bias_scale, act, slope, (cudaStream_t)stream);
 }
 
-extern "C" int glb_conv2d_dgrad(const float* gy, const float* w, float* gx, int N, int H, int W, int Ci, int Co, int R, int S,
-                                int pad, float alpha, int impl, glb_stream_t stream) {
+extern "C" int glb_conv2d_tc_covers(int kind, int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return 0;
+  switch (kind) {
+    case 0: return glb::conv_fprop_tc_covers(N, H, W, Ci, Co, R, S, pad) ? 1 : 0;
+    case 1: return glb::conv_dgrad_tc_covers(N, H, W, Ci, Co, R, S, pad) ? 1 : 0;
+    case 2: return glb::conv_wgrad_tc_covers(N, H, W, Ci, Co, R, S, pad) ? 1 : 0;
+  }
+  return 0;
+}
+
+extern "C" int glb_conv2d_dgrad(const float* gy, const float* w, const float* wt, float* gx, int N, int H, int W, int Ci, int Co,
+                                int R, int S, int pad, float alpha, int impl, glb_stream_t stream) {
   if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_dgrad");
-  if (impl == GLB_IMPL_TF32) return glb::conv_dgrad_tc(gy, w, gx, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
+  if (impl == GLB_IMPL_TF32) return glb::conv_dgrad_tc(gy, wt, gx, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
   return glb::conv_dgrad_simt(gy, w, gx, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
 }
 

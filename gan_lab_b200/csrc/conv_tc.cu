@@ -1,10 +1,544 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution family (TF32).  Placeholder until the kernels land.
-#include "common.cuh"
+// tcgen05 / TMEM / TMA implicit-GEMM convolution family (TF32 operands, fp32 accumulate) for sm_100a.
+//
+// Replaces aten::convolution / convolution_backward as dispatched from Conv2dEx (reference
+// utils/custom_layers.py:166-169, 202-211) on the tensor cores.  Layouts as in include/ganlab_b200.h:
+// activations NHWC, weights KRSC.
+//
+// fprop (and dgrad, which is fprop over gy with the flipped/transposed weights of
+// glb_conv2d_weight_transpose):
+//   GEMM  D[m = output pixel][n = co] = sum_{tap=(r,s)} sum_{ci} X[pixel shifted by (r-pad, s-pad)][ci] * W[co][tap][ci]
+//   * M tile = 128 output pixels = a (bn images x bh rows x bw cols) box; for every tap and 32-channel
+//     chunk ONE 4-D TMA box load of the shifted input window lands the A tile in shared memory in the
+//     K-major 128B-swizzled layout tcgen05 wants; TMA's out-of-bounds zero fill implements the padding.
+//   * N tile = BN output channels; the B tile is a 3-D TMA box (32 ci, 1 tap, BN co) of the KRSC weights.
+//   * persistent CTAs (one per SM), warp specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one
+//     thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> alpha/bias/act -> HBM).
+//     smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator stages (tmem_full/empty
+//     mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "tc_common.cuh"
+
 namespace glb {
-int conv_fprop_tc(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, float, float, int,
-                  float, cudaStream_t) { set_error("tcgen05 fprop: shape not covered"); return GLB_ERR_UNSUPPORTED; }
-int conv_dgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t) {
-  set_error("tcgen05 dgrad: shape not covered"); return GLB_ERR_UNSUPPORTED; }
-int conv_wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t) {
-  set_error("tcgen05 wgrad: shape not covered"); return GLB_ERR_UNSUPPORTED; }
+namespace {
+using namespace tc;
+
+struct FpropParams {
+  float* y;
+  const float* bias;
+  int N, Ho, Wo, Co;
+  int Ci, R, S, pad;
+  int bw, bh, bn;  // M-tile box, bw*bh*bn == 128
+  int tiles_w, tiles_h, tiles_n, tiles_co;
+  int num_tiles;
+  float alpha, bias_scale;
+  int act;
+  float slope;
+};
+
+constexpr int kBM = 128;           // MMA M (output pixels per tile)
+constexpr int kChunk = 32;         // channels per K chunk = 128 bytes = one swizzle row
+constexpr int kABytes = kBM * 128; // 16 KB
+
+template <int BN>
+struct FpropCfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 64) ? 64 : 2 * BN;  // power of two >= 32; the epilogue reads 32-column groups
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  using Cfg = FpropCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  const uint32_t bar0 = base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_iters = p.R * p.S * (p.Ci / kChunk);
+  const int chunks = p.Ci / kChunk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int tco = tile % p.tiles_co;
+        int t = tile / p.tiles_co;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int tn = t;
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, co0 = tco * BN;
+        for (int tap = 0; tap < p.R * p.S; ++tap) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+            const uint32_t b_dst = a_dst + kABytes;
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_4d(a_dst, &tmA, full_bar(stage), ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_3d(b_dst, &tmB, full_bar(stage), ch * kChunk, tap, co0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
+            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
+            mma_tf32(d_tmem, ad, bd, idesc, (k | kk) ? 1u : 0u);
+          }
+          mma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> regs -> alpha/bias/act -> global (NHWC) =====================
+    const int q = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
+    const int row = q * 32 + lane;
+    const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rn = row / (p.bw * p.bh);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tco = tile % p.tiles_co;
+      int t = tile / p.tiles_co;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int tn = t;
+      const int w = tw * p.bw + rw, h = th * p.bh + rh, n = tn * p.bn + rn, co0 = tco * BN;
+      const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.N);
+      float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      constexpr int EC = (BN < 32) ? BN : 32;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < EC; j += 4) {
+            float4 o;
+            float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = p.alpha * __uint_as_float(v[j + e]);
+              if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
+              oo[e] = act_apply(a, p.act, p.slope);
+            }
+            *reinterpret_cast<float4*>(out + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int BN>
+int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = FpropCfg<BN>;
+  static bool configured = false;  // per-process, per-instantiation; attribute is sticky for the function
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  conv_fprop_tc_kernel<BN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GLB_CHECK_LAUNCH("conv_fprop_tc_kernel");
+  return GLB_OK;
+}
+
+}  // namespace
+
+// Shapes the tensor-core fprop covers: stride-1 RxS with `pad`, Ci % 32 == 0, Co in {16, 32, 64} or a multiple of 128.
+bool conv_fprop_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  if (Ci % kChunk != 0 || Ci < kChunk) return false;
+  if (!(Co == 16 || Co == 32 || Co == 64 || Co % 128 == 0)) return false;
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  if (Ho <= 0 || Wo <= 0) return false;
+  if (R * S > 25) return false;
+  return true;
+}
+
+int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int R, int S,
+                  int pad, float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
+  if (!conv_fprop_tc_covers(N, H, W, Ci, Co, R, S, pad)) {
+    set_error("tcgen05 fprop: shape not covered (need Ci % 32 == 0 and Co in {16,32,64} or Co % 128 == 0)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  FpropParams p;
+  p.y = y; p.bias = bias;
+  p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1; p.Co = Co;
+  p.Ci = Ci; p.R = R; p.S = S; p.pad = pad;
+  p.bw = next_pow2(p.Wo) < 16 ? next_pow2(p.Wo) : 16;
+  p.bh = next_pow2(p.Ho) < kBM / p.bw ? next_pow2(p.Ho) : kBM / p.bw;
+  p.bn = kBM / (p.bw * p.bh);
+  int BN = Co % 256 == 0 ? 256 : (Co % 128 == 0 ? 128 : Co);
+  p.tiles_w = (p.Wo + p.bw - 1) / p.bw;
+  p.tiles_h = (p.Ho + p.bh - 1) / p.bh;
+  p.tiles_n = (N + p.bn - 1) / p.bn;
+  // few M tiles (low resolutions): narrower N tiles spread the weight stream over more SMs
+  while (BN > 32 && (int64_t)p.tiles_w * p.tiles_h * p.tiles_n * (Co / BN) < kNumSMs / 2) BN >>= 1;
+  p.tiles_co = Co / BN;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+  p.alpha = alpha; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+    const uint32_t box[4] = {(uint32_t)kChunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = make_tmap_f32(&tmA, x, 4, dims, strides, box, "conv input");
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
+    const uint64_t strides[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+    const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)BN};
+    int rc = make_tmap_f32(&tmB, w, 3, dims, strides, box, "conv weight");
+    if (rc) return rc;
+  }
+  switch (BN) {
+    case 256: return launch_fprop<256>(tmA, tmB, p, st);
+    case 128: return launch_fprop<128>(tmA, tmB, p, st);
+    case 64: return launch_fprop<64>(tmA, tmB, p, st);
+    case 32: return launch_fprop<32>(tmA, tmB, p, st);
+    case 16: return launch_fprop<16>(tmA, tmB, p, st);
+  }
+  set_error("tcgen05 fprop: no kernel for this N tile");
+  return GLB_ERR_UNSUPPORTED;
+}
+
+// dgrad = fprop over gy with the flipped / transposed weights wt[Ci][R][S][Co] (glb_conv2d_weight_transpose):
+//   gx[n,h,w,ci] = alpha * sum_{r',s',co} gy[n, h + r' - (R-1-pad), w + s' - (S-1-pad), co] * wt[ci][r'][s'][co]
+int conv_dgrad_tc(const float* gy, const float* wt, float* gx, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                  float alpha, cudaStream_t st) {
+  if (wt == nullptr) {
+    set_error("tcgen05 dgrad needs the transposed weights (glb_conv2d_weight_transpose) in `wt`");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  if (R != S) {
+    set_error("tcgen05 dgrad: square filters only");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  // input of this "fprop" is gy [N,Ho,Wo,Co]; output is gx [N,H,W,Ci]; H = Ho + 2*pad' - R + 1 with pad' = R-1-pad
+  return conv_fprop_tc(gy, wt, nullptr, gx, N, Ho, Wo, Co, Ci, R, S, R - 1 - pad, alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+}
+
+bool conv_dgrad_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  if (R != S || R - 1 - pad < 0) return false;
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  return conv_fprop_tc_covers(N, Ho, Wo, Co, Ci, R, S, R - 1 - pad);
+}
+
+namespace {
+using namespace tc;
+// ------------------------------------------------------------------------------------------------ wgrad
+// gw[co][tap][ci] = alpha * sum_{p = (n,ho,wo)} gy[p][co] * x[p shifted by (r-pad, s-pad)][ci]
+//   GEMM  D[m = co][n = ci] over K = output pixels, one accumulator per (128 co, BN ci, tap) tile, split-K over pixel
+//   blocks across CTAs (partials reduced with red.global.add.v4.f32 into the zero-initialised gw).
+//   Both operands have the channel axis contiguous and K (pixels) strided -> "MN-major" tcgen05 operands: a TMA box
+//   (32 channels, 32 pixels) is one [32 px][128 B] block of the canonical MN-major layout "128B swizzle with 32-byte
+//   atoms" -- the only one tcgen05 accepts for MN-major 32-bit operands (TMA mode SWIZZLE_128B_ATOM_32B; 4-pixel swizzle
+//   period) -- with LBO = 4 KB between 32-channel blocks and SBO = 512 B between groups of 4 pixels.  Channel blocks beyond Co are
+//   zero-filled by TMA (M padded to 128), padding taps likewise.
+struct WgradParams {
+  float* gw;
+  int Co, Ci, RS, S, pad;
+  int N, Ho, Wo;
+  int bw, bh, bn;  // K block = 32 pixels = bn x bh x bw box
+  int tiles_w, tiles_h, tiles_n, num_pb;
+  int splits, pb_per_split;
+  int tiles_co, tiles_ci;
+  float alpha;
+  int atomic;
+};
+
+constexpr int kWgPix = 32;              // pixels per K block
+constexpr int kWgBlkBytes = kWgPix * 128;  // one (32 ch x 32 px) block = 4 KB
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int kABytes = 4 * kWgBlkBytes;
+  static constexpr int kBBytes = (BN / 32) * kWgBlkBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  using Cfg = WgradCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  const uint32_t bar0 = base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int split = t % p.splits; t /= p.splits;
+  const int tci = t % p.tiles_ci; t /= p.tiles_ci;
+  const int tco = t % p.tiles_co; t /= p.tiles_co;
+  const int tap = t;
+  const int r = tap / p.S, s = tap - r * p.S;
+  const int co0 = tco * 128, ci0 = tci * BN;
+  const int pb_begin = split * p.pb_per_split;
+  const int pb_end = min(p.num_pb, pb_begin + p.pb_per_split);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmGy);
+    prefetch_tmap(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        int u = pb;
+        const int tw = u % p.tiles_w; u /= p.tiles_w;
+        const int th = u % p.tiles_h; u /= p.tiles_h;
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = u * p.bn;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+        const uint32_t b_dst = a_dst + Cfg::kABytes;
+        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) tma_load_4d(a_dst + m * kWgBlkBytes, &tmGy, full_bar(stage), co0 + 32 * m, w0, h0, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_4d(b_dst + j * kWgBlkBytes, &tmX, full_bar(stage), ci0 + 32 * j, w0 + s - p.pad, h0 + r - p.pad, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+        for (int kg = 0; kg < kWgPix / 8; ++kg) {  // K = 8 pixels per MMA = one 1 KB swizzle atom per channel block
+          const uint64_t ad = make_smem_desc(a_addr + kg * 1024, kWgBlkBytes, 512, kLayoutSw128Base32);
+          const uint64_t bd = make_smem_desc(b_addr + kg * 1024, kWgBlkBytes, 512, kLayoutSw128Base32);
+          mma_tf32(tmem_base, ad, bd, idesc, (pb > pb_begin || kg > 0) ? 1u : 0u);
+        }
+        mma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int co = co0 + q * 32 + lane;
+    const bool valid = co < p.Co;
+    float* out = p.gw + ((int64_t)co * p.RS + tap) * p.Ci + ci0;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float a0 = p.alpha * __uint_as_float(v[j]), a1 = p.alpha * __uint_as_float(v[j + 1]);
+          const float a2 = p.alpha * __uint_as_float(v[j + 2]), a3 = p.alpha * __uint_as_float(v[j + 3]);
+          if (p.atomic) red_add_v4(out + c + j, a0, a1, a2, a3);
+          else *reinterpret_cast<float4*>(out + c + j) = make_float4(a0, a1, a2, a3);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
+  using Cfg = WgradCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  conv_wgrad_tc_kernel<BN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmGy, tmX, p);
+  GLB_CHECK_LAUNCH("conv_wgrad_tc_kernel");
+  return GLB_OK;
+}
+
+bool conv_wgrad_tc_covers_impl(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  if (Ci % 32 != 0 || Co % 32 != 0) return false;
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  if (Ho <= 0 || Wo <= 0 || R * S > 25) return false;
+  return true;
+}
+
+}  // namespace
+
+bool conv_wgrad_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  return conv_wgrad_tc_covers_impl(N, H, W, Ci, Co, R, S, pad);
+}
+
+int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                  float alpha, cudaStream_t st) {
+  if (!conv_wgrad_tc_covers_impl(N, H, W, Ci, Co, R, S, pad)) {
+    set_error("tcgen05 wgrad: shape not covered (need Ci % 32 == 0 and Co % 32 == 0)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  WgradParams p;
+  p.gw = gw; p.Co = Co; p.Ci = Ci; p.RS = R * S; p.S = S; p.pad = pad;
+  p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1;
+  p.bw = next_pow2(p.Wo) < kWgPix ? next_pow2(p.Wo) : kWgPix;
+  p.bh = next_pow2(p.Ho) < kWgPix / p.bw ? next_pow2(p.Ho) : kWgPix / p.bw;
+  p.bn = kWgPix / (p.bw * p.bh);
+  p.tiles_w = (p.Wo + p.bw - 1) / p.bw;
+  p.tiles_h = (p.Ho + p.bh - 1) / p.bh;
+  p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.num_pb = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
+  p.tiles_co = (Co + 127) / 128;
+  p.tiles_ci = Ci / BN;
+  const int tiles = p.tiles_co * p.tiles_ci * p.RS;
+  int splits = (2 * kNumSMs + tiles - 1) / tiles;           // aim at ~2 CTAs' worth of work items per SM
+  if (splits > p.num_pb) splits = p.num_pb;
+  if (splits < 1) splits = 1;
+  p.pb_per_split = (p.num_pb + splits - 1) / splits;
+  p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;  // every split owns >= 1 pixel block
+  p.alpha = alpha;
+  p.atomic = p.splits > 1 ? 1 : 0;
+  if (p.atomic) GLB_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Co * R * S * Ci, st));
+
+  CUtensorMap tmGy, tmX;
+  const uint32_t box[4] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  {
+    const uint64_t dims[4] = {(uint64_t)Co, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)Co * 4, (uint64_t)p.Wo * Co * 4, (uint64_t)p.Ho * p.Wo * Co * 4};
+    int rc = make_tmap_f32(&tmGy, gy, 4, dims, strides, box, "wgrad gy", true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+    int rc = make_tmap_f32(&tmX, x, 4, dims, strides, box, "wgrad x", true);
+    if (rc) return rc;
+  }
+  const int grid = tiles * p.splits;
+  switch (BN) {
+    case 256: return launch_wgrad<256>(tmGy, tmX, p, grid, st);
+    case 128: return launch_wgrad<128>(tmGy, tmX, p, grid, st);
+    case 64: return launch_wgrad<64>(tmGy, tmX, p, grid, st);
+    case 32: return launch_wgrad<32>(tmGy, tmX, p, grid, st);
+  }
+  return GLB_ERR_UNSUPPORTED;
+}
+
 }  // namespace glb

@@ -85,4 +85,5 @@ class FusedAdam(torch.optim.Optimizer):
                                   group['weight_decay'], beta, mode)
         if self._ewma is not None:
             self._ewma_started = True
+        K.weights_updated()          # parameters were rewritten through raw pointers: drop cached weight re-layouts
         return None

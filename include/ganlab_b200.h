@@ -59,12 +59,16 @@ int glb_tc_available(void);
 int glb_conv2d_fprop(const float* x, const float* w, const float* bias, float* y,
                      int N, int H, int W, int Ci, int Co, int R, int S, int pad,
                      float alpha, float bias_scale, int act, float slope, int impl, glb_stream_t stream);
-int glb_conv2d_dgrad(const float* gy, const float* w, float* gx,
+/* `wt` = the flipped/transposed weights written by glb_conv2d_weight_transpose: required by GLB_IMPL_TF32 (the
+ * tensor-core dgrad is the fprop kernel run over gy with wt), ignored (may be NULL) by GLB_IMPL_FP32, which reads `w`. */
+int glb_conv2d_dgrad(const float* gy, const float* w, const float* wt, float* gx,
                      int N, int H, int W, int Ci, int Co, int R, int S, int pad,
                      float alpha, int impl, glb_stream_t stream);
 int glb_conv2d_wgrad(const float* x, const float* gy, float* gw,
                      int N, int H, int W, int Ci, int Co, int R, int S, int pad,
                      float alpha, int impl, glb_stream_t stream);
+/* 1 if the GLB_IMPL_TF32 kernel of `kind` (0 fprop, 1 dgrad, 2 wgrad) covers this shape (arguments as in the calls above). */
+int glb_conv2d_tc_covers(int kind, int N, int H, int W, int Ci, int Co, int R, int S, int pad);
 /* workspace-free weight re-layout used by the tensor-core dgrad: wt[Ci][R][S][Co] (taps flipped). */
 int glb_conv2d_weight_transpose(const float* w, float* wt, int Co, int R, int S, int Ci, glb_stream_t stream);
 

@@ -80,6 +80,45 @@ def test_conv_family_vs_contract(shape):
     both("conv_wgrad", x, gy, (R, R), pad, 0.37)
 
 
+# TF32 tensor-core path (tcgen05): operands are truncated to 10 mantissa bits, accumulation is fp32.  Stated bound: 3e-3 of
+# the tensor's max-norm (measured ~8e-4 on B200 over K = 288..4608); the fp32 FFMA path above keeps the 1e-4 bar.
+TOL_TF32 = 3e-3
+TC_SHAPES = [  # N, H, W, Ci, Co, R, pad
+    (8, 4, 4, 512, 512, 3, 1), (8, 16, 16, 512, 512, 3, 1), (2, 32, 32, 256, 128, 3, 1), (2, 64, 64, 128, 256, 3, 1),
+    (4, 8, 8, 96, 128, 3, 1), (3, 5, 7, 32, 64, 3, 1), (2, 16, 16, 64, 32, 3, 1), (2, 32, 32, 128, 128, 1, 0),
+    (1, 128, 128, 128, 128, 3, 1),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_family_tf32_vs_contract(shape):
+    N, H, W, Ci, Co, R, pad = shape
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, R, R, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, H + 2 * pad - R + 1, W + 2 * pad - R + 1, seed=3))
+    K.set_conv_impl("tf32")
+    try:
+        assert K.tc_covers("fprop", N, H, W, Ci, Co, R, R, pad) and K.tc_covers("wgrad", N, H, W, Ci, Co, R, R, pad)
+        both("conv_fprop", x, w, b, pad, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_TF32)
+        both("conv_fprop", x, w, None, pad, 1.0, 1.0, K.ACT_NONE, 0.2, tol=TOL_TF32)
+        both("conv_dgrad", gy, w, (H, W), pad, 0.37, tol=TOL_TF32)
+        both("conv_wgrad", x, gy, (R, R), pad, 0.37, tol=TOL_TF32)
+    finally:
+        K.set_conv_impl("fp32")
+
+
+def test_tf32_dgrad_sees_weight_updates():
+    """The tensor-core dgrad multiplies by a cached re-layout of the weight: an in-place update must invalidate it."""
+    K.set_conv_impl("tf32")
+    try:
+        w, gy = cl(rn(64, 64, 3, 3)).to(DEV), cl(rn(2, 64, 8, 8, seed=1)).to(DEV)
+        a = K.conv_dgrad(gy, w, (8, 8), 1, 1.0)
+        w.mul_(2.0)
+        b = K.conv_dgrad(gy, w, (8, 8), 1, 1.0)
+        assert rel(b, a * 2) < 1e-6
+    finally:
+        K.set_conv_impl("fp32")
+
+
 @pytest.mark.parametrize("M,Kf,Nout", [(8, 32, 32), (8, 512, 512), (4, 512, 8192), (8, 512, 1), (64, 8192, 1), (5, 37, 11)])
 def test_linear_family_vs_contract(M, Kf, Nout):
     x, w, b, gy = rn(M, Kf), rn(Nout, Kf, seed=1), rn(Nout, seed=2), rn(M, Nout, seed=3)
