@@ -58,18 +58,27 @@ __global__ void __launch_bounds__(TPB) se_fwd_stats_kernel(const float4* __restr
   const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  // shifted sums: k4 = the chunk's first pixel, so sum((t-k)^2) - sum(t-k)^2/n does not cancel when |mean| >> std
+  // (e.g. the constant-input layer, whose planes are 1 + small noise)
+  float4 k4;
+  {
+    const int64_t px = (int64_t)n * g.HW + p0;
+    k4 = lrelu4(pre_act(__ldg(x + px * g.C4 + q), noise ? __ldg(noise + px) : 0.f, w4, b4), g.slope);
+  }
   for (int p = p0 + rl; p < p1; p += rows) {
     const int64_t px = (int64_t)n * g.HW + p;
     const float nz = noise ? __ldg(noise + px) : 0.f;
-    const float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
+    float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
+    t.x -= k4.x; t.y -= k4.y; t.z -= k4.z; t.w -= k4.w;
     s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
     ss.x += t.x * t.x; ss.y += t.y * t.y; ss.z += t.z * t.z; ss.w += t.w * t.w;
   }
   block_rows_reduce(s, ss, red, g.C4, rows);
   if (tid < g.C4) {
-    float4* o = part + ((int64_t)(n * g.chunks + chunk) * 2) * g.C4;
+    float4* o = part + ((int64_t)(n * g.chunks + chunk) * 3) * g.C4;
     o[q] = s;
     o[g.C4 + q] = ss;
+    o[2 * g.C4 + q] = k4;
   }
 }
 
@@ -79,15 +88,22 @@ __global__ void se_fwd_finalize_kernel(const float* __restrict__ part, float* __
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
-  double s = 0.0, ss = 0.0;
+  // Chan's pairwise combination of the per-chunk (count, mean, M2), in fp64
+  double cnt = 0.0, mu = 0.0, m2 = 0.0;
   for (int k = 0; k < chunks; ++k) {
-    const float* p = part + ((int64_t)(n * chunks + k) * 2) * C;
-    s += (double)p[c];
-    ss += (double)p[C + c];
+    const float* p = part + ((int64_t)(n * chunks + k) * 3) * C;
+    const int rem = HW - k * CHUNK;
+    const double nk = rem < CHUNK ? rem : CHUNK;
+    const double sk = (double)p[c], ssk = (double)p[C + c];
+    const double mk = (double)p[2 * C + c] + sk / nk;
+    double m2k = ssk - sk * sk / nk;
+    if (m2k < 0.0) m2k = 0.0;
+    const double d = mk - mu, tot = cnt + nk;
+    mu += d * nk / tot;
+    m2 += m2k + d * d * cnt * nk / tot;
+    cnt = tot;
   }
-  const double mu = s / HW;
-  double var = ss / HW - mu * mu;
-  if (var < 0.0) var = 0.0;
+  const double var = m2 / HW;
   stats[((int64_t)n * 2) * C + c] = (float)mu;
   stats[((int64_t)n * 2 + 1) * C + c] = (float)(1.0 / sqrt(var + (double)eps));
 }
@@ -223,7 +239,7 @@ using namespace glb;
 
 extern "C" int64_t glb_style_epilogue_work_floats(int N, int H, int W, int C) {
   const int64_t chunks = ((int64_t)H * W + CHUNK - 1) / CHUNK;
-  return (int64_t)N * chunks * 2 * C + (int64_t)N * 2 * C;
+  return (int64_t)N * chunks * 3 * C + (int64_t)N * 2 * C;
 }
 
 extern "C" int glb_style_epilogue_fwd(const float* x, const float* noise, const float* noise_weight, const float* bias,

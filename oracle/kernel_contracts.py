@@ -241,7 +241,7 @@ def rgb_wgrad(img, g, w_shape, ws_j, ws_c, pool, alpha):
         img = F.avg_pool2d(img, 2, 2)
     C = g.shape[1]
     m = alpha * torch.einsum("njhw,nchw->jc", img, g)    # [3, C]
-    out = torch.zeros(int(np.prod(w_shape)))
+    out = torch.zeros(int(np.prod(w_shape)), dtype=m.dtype)
     j = torch.arange(3).view(3, 1)
     c = torch.arange(C).view(1, C)
     out[(j * ws_j + c * ws_c).reshape(-1)] = m.reshape(-1)
