@@ -523,6 +523,10 @@ def w_ewma_update(w, ewma, beta):
     return ewma
 
 
+def adam_hyper_advance(hyper, beta1, beta2):
+    _call("glb_adam_hyper_advance", _p(hyper), float(beta1), float(beta2), _stream())
+
+
 def adam_ewma_multi(ptr_table, sizes, T, max_size, hyper, beta1, beta2, eps, wd, ewma_beta, ewma_mode):
     _call("glb_adam_ewma_multi", _p(ptr_table), _p(sizes), T, max_size, _p(hyper), float(beta1), float(beta2), float(eps),
           float(wd), float(ewma_beta), int(ewma_mode), _stream())

@@ -21,6 +21,7 @@ struct IGemm {
   int N, IH, IW, IC, OH, OW, OC, R, S;
   int dh0, dw0, dsign;  // input row = oh + dh0 + dsign*r
   int M, K;             // M = N*OH*OW, K = R*S*IC
+  int kper;             // k range per split-K slice (multiple of BK)
 };
 
 // MODE 0 = fprop (weight element (oc, r, s, ic) at ((oc*R+r)*S+s)*IC+ic  -> contiguous along k)
@@ -53,7 +54,10 @@ __global__ void __launch_bounds__(NT) igemm_kernel(const float* __restrict__ in,
 
   const int tx = tid % 16, ty = tid / 16;
 
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
+  // split-K: slice z of gridDim.z owns k in [k_begin, k_end); partial tiles are combined with atomicAdd
+  const int k_begin = blockIdx.z * g.kper;
+  const int k_end = min(g.K, k_begin + g.kper);
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
     // ---- A tile ----
     float av[8];
     if (VEC) {
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(NT) igemm_kernel(const float* __restrict__ in,
       for (int j = 0; j < 8; ++j) {
         const int k = k0 + a_kq + j;
         float v = 0.f;
-        if (a_valid && k < g.K) {
+        if (a_valid && k < k_end) {
           const int tap = k / g.IC, ic = k - tap * g.IC;
           const int r = tap / g.S, s = tap - r * g.S;
           const int ih = a_oh + g.dh0 + g.dsign * r, iw = a_ow + g.dw0 + g.dsign * s;
@@ -105,13 +109,13 @@ __global__ void __launch_bounds__(NT) igemm_kernel(const float* __restrict__ in,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k = k0 + b_k + j;
-          bv[j] = (oc < g.OC && k < g.K) ? __ldg(wgt + (int64_t)oc * g.K + k) : 0.f;
+          bv[j] = (oc < g.OC && k < k_end) ? __ldg(wgt + (int64_t)oc * g.K + k) : 0.f;
         }
       }
     } else {
       b_k = tid / 16; b_n = (tid % 16) * 8;
       const int k = k0 + b_k;
-      if (k < g.K) {
+      if (k < k_end) {
         const int tap = k / g.IC, ic = k - tap * g.IC;  // ic indexes the ORIGINAL Co
         const int64_t base = ((int64_t)ic * g.R * g.S + tap) * g.OC + n0 + b_n;
         if (VEC && n0 + b_n + 8 <= g.OC) {
@@ -164,8 +168,12 @@ __global__ void __launch_bounds__(NT) igemm_kernel(const float* __restrict__ in,
       const int n = n0 + tx * 8 + j;
       if (n < g.OC) {
         float v = alpha * acc[i][j];
-        if (bias != nullptr) v += bias_scale * __ldg(bias + n);
-        orow[n] = act_apply(v, act, slope);
+        if (gridDim.z > 1) {
+          atomicAdd(orow + n, v);  // bias / activation are applied by a second pass (see launch_igemm)
+        } else {
+          if (bias != nullptr) v += bias_scale * __ldg(bias + n);
+          orow[n] = act_apply(v, act, slope);
+        }
       }
     }
   }
@@ -282,6 +290,36 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, float* __re
 
 }  // namespace
 
+// Few output tiles and a long reduction (low-resolution layers, e.g. the 513-channel conv after the minibatch-stddev
+// concat: 128 pixels x K = 4617): split K across gridDim.z so the SMs are busy; slices are summed with atomicAdd into
+// the zeroed output and bias / activation run as a second (tiny) elementwise pass.
+template <int MODE>
+int launch_igemm(const float* in, const float* w, const float* bias, float* out, IGemm g, int n_out, bool vec, float alpha,
+                 float bias_scale, int act, float slope, cudaStream_t st) {
+  dim3 grid((g.M + BM - 1) / BM, (n_out + BN - 1) / BN, 1);
+  const int tiles = grid.x * grid.y;
+  int splits = 1;
+  const bool epilogue_pass = (bias != nullptr || act != GLB_ACT_NONE);
+  if (tiles < kNumSMs / 2 && g.K >= 16 * BK && (!epilogue_pass || n_out % 4 == 0)) {
+    splits = (2 * kNumSMs + tiles - 1) / tiles;
+    const int max_splits = g.K / (4 * BK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  g.kper = (((g.K + splits - 1) / splits + BK - 1) / BK) * BK;
+  splits = (g.K + g.kper - 1) / g.kper;
+  grid.z = splits;
+  if (splits > 1) GLB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)g.M * n_out, st));
+  if (vec)
+    igemm_kernel<MODE, true><<<grid, NT, 0, st>>>(in, w, bias, out, g, alpha, bias_scale, act, slope);
+  else
+    igemm_kernel<MODE, false><<<grid, NT, 0, st>>>(in, w, bias, out, g, alpha, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("igemm_kernel");
+  if (splits > 1 && epilogue_pass)
+    return glb_bias_act_fwd(out, bias, out, g.M, n_out, bias_scale, act, slope, (glb_stream_t)st);
+  return GLB_OK;
+}
+
 int conv_fprop_simt(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
                     int R, int S, int pad, float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
   IGemm g;
@@ -289,13 +327,7 @@ int conv_fprop_simt(const float* x, const float* w, const float* bias, float* y,
   g.R = R; g.S = S; g.dh0 = -pad; g.dw0 = -pad; g.dsign = 1;
   if (g.OH <= 0 || g.OW <= 0) return shape_fail("conv output size <= 0");
   g.M = N * g.OH * g.OW; g.K = R * S * Ci;
-  dim3 grid((g.M + BM - 1) / BM, (Co + BN - 1) / BN);
-  if (Ci % 16 == 0)
-    igemm_kernel<0, true><<<grid, NT, 0, st>>>(x, w, bias, y, g, alpha, bias_scale, act, slope);
-  else
-    igemm_kernel<0, false><<<grid, NT, 0, st>>>(x, w, bias, y, g, alpha, bias_scale, act, slope);
-  GLB_CHECK_LAUNCH("igemm_kernel<fprop>");
-  return GLB_OK;
+  return launch_igemm<0>(x, w, bias, y, g, Co, Ci % 16 == 0, alpha, bias_scale, act, slope, st);
 }
 
 int conv_dgrad_simt(const float* gy, const float* w, float* gx, int N, int H, int W, int Ci, int Co, int R, int S,
@@ -306,13 +338,7 @@ int conv_dgrad_simt(const float* gy, const float* w, float* gx, int N, int H, in
   g.N = N; g.IH = OH; g.IW = OW; g.IC = Co; g.OH = H; g.OW = W; g.OC = Ci;
   g.R = R; g.S = S; g.dh0 = pad; g.dw0 = pad; g.dsign = -1;
   g.M = N * H * W; g.K = R * S * Co;
-  dim3 grid((g.M + BM - 1) / BM, (Ci + BN - 1) / BN);
-  if (Co % 16 == 0 && Ci % 4 == 0)
-    igemm_kernel<1, true><<<grid, NT, 0, st>>>(gy, w, nullptr, gx, g, alpha, 0.f, GLB_ACT_NONE, 0.f);
-  else
-    igemm_kernel<1, false><<<grid, NT, 0, st>>>(gy, w, nullptr, gx, g, alpha, 0.f, GLB_ACT_NONE, 0.f);
-  GLB_CHECK_LAUNCH("igemm_kernel<dgrad>");
-  return GLB_OK;
+  return launch_igemm<1>(gy, w, nullptr, gx, g, Ci, Co % 16 == 0 && Ci % 4 == 0, alpha, 0.f, GLB_ACT_NONE, 0.f, st);
 }
 
 int conv_wgrad_simt(const float* x, const float* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S,
@@ -347,13 +373,3 @@ extern "C" int glb_conv2d_weight_transpose(const float* w, float* wt, int Co, in
   return GLB_OK;
 }
 
-extern "C" int glb_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int K, int Nout,
-                              float alpha, float bias_scale, int act, float slope, glb_stream_t stream) {
-  return glb::conv_fprop_simt(x, w, bias, y, M, 1, 1, K, Nout, 1, 1, 0, alpha, bias_scale, act, slope, (cudaStream_t)stream);
-}
-extern "C" int glb_linear_dgrad(const float* gy, const float* w, float* gx, int M, int K, int Nout, float alpha, glb_stream_t stream) {
-  return glb::conv_dgrad_simt(gy, w, gx, M, 1, 1, K, Nout, 1, 1, 0, alpha, (cudaStream_t)stream);
-}
-extern "C" int glb_linear_wgrad(const float* x, const float* gy, float* gw, int M, int K, int Nout, float alpha, glb_stream_t stream) {
-  return glb::conv_wgrad_simt(x, gy, gw, M, 1, 1, K, Nout, 1, 1, 0, alpha, (cudaStream_t)stream);
-}

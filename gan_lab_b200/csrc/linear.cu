@@ -1,0 +1,188 @@
+// Small-batch equalized-LR linear layers (LinearEx, reference utils/custom_layers.py:230-291):
+//   y[M,Nout] = act(alpha * x[M,K] . w[Nout,K]^T + bias_scale * bias)          (aten::addmm + mul)
+// with M = the per-GPU batch (8 .. 16).  These GEMMs move the whole weight matrix for a handful of rows: they are
+// weight-bandwidth / launch bound, not tensor-core work, so they are streaming kernels:
+// every weight element is read exactly once, coalesced, and the M activation rows sit in shared memory.
+// Larger M falls through to the implicit-GEMM kernels (conv_simt.cu).
+#include "common.cuh"
+
+namespace glb {
+
+int conv_fprop_simt(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, float, float, int,
+                    float, cudaStream_t);
+int conv_dgrad_simt(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
+int conv_wgrad_simt(const float*, const float*, float*, int, int, int, int, int, int, int, int, float, cudaStream_t);
+
+namespace {
+
+constexpr int kMaxM = 16;     // rows handled by the streaming kernels
+constexpr int kMaxXs = 8192;  // floats of shared memory for the activation rows (M*K <= 8192)
+
+// ---- forward: one warp per output feature, lanes split K (float4), warp-shuffle reduction ----------------------
+template <int MB>
+__global__ void __launch_bounds__(256) linear_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ y, int M, int K,
+                                                               int Nout, float alpha, float bias_scale, int act, float slope) {
+  extern __shared__ __align__(16) float xs[];  // [M][K]
+  for (int i = threadIdx.x * 4; i < M * K; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(xs + i) = __ldg(reinterpret_cast<const float4*>(x + i));
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n >= Nout) return;
+  float acc[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc[m] = 0.f;
+  const float* wr = w + (int64_t)n * K;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 wv = ldg_stream(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      if (m < M) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + m * K + k);
+        acc[m] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[m]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc[m] = warp_sum(acc[m]);
+  const float b = bias ? bias_scale * __ldg(bias + n) : 0.f;
+#pragma unroll
+  for (int m = 0; m < MB; ++m)
+    if (lane == m && m < M) y[(int64_t)m * Nout + n] = act_apply(alpha * acc[m] + b, act, slope);
+}
+
+// ---- dgrad: gx[m][k] = alpha * sum_n gy[m][n] w[n][k].  Thread = one k quad; block = one slice of n; slices combine
+// with red.add into the zero-initialised gx (a few dozen adds per element).
+template <int MB>
+__global__ void __launch_bounds__(128) linear_dgrad_small_kernel(const float* __restrict__ gy, const float* __restrict__ w,
+                                                                 float* __restrict__ gx, int M, int K, int Nout, int n_per_block,
+                                                                 float alpha) {
+  extern __shared__ __align__(16) float gs[];  // [n_per_block][M]
+  const int n0 = blockIdx.y * n_per_block;
+  const int nn = min(n_per_block, Nout - n0);
+  for (int i = threadIdx.x; i < nn * M; i += blockDim.x) {
+    const int j = i / M, m = i - j * M;
+    gs[i] = __ldg(gy + (int64_t)m * Nout + n0 + j);
+  }
+  __syncthreads();
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (k >= K) return;
+  float4 acc[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < nn; ++j) {
+    const float4 wv = ldg_stream(reinterpret_cast<const float4*>(w + (int64_t)(n0 + j) * K + k));
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      if (m < M) {
+        const float g = gs[j * M + m];
+        acc[m].x = fmaf(g, wv.x, acc[m].x); acc[m].y = fmaf(g, wv.y, acc[m].y);
+        acc[m].z = fmaf(g, wv.z, acc[m].z); acc[m].w = fmaf(g, wv.w, acc[m].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    if (m < M) {
+      float* o = gx + (int64_t)m * K + k;
+      if (gridDim.y == 1) {
+        *reinterpret_cast<float4*>(o) = make_float4(alpha * acc[m].x, alpha * acc[m].y, alpha * acc[m].z, alpha * acc[m].w);
+      } else {
+        atomicAdd(o + 0, alpha * acc[m].x); atomicAdd(o + 1, alpha * acc[m].y);
+        atomicAdd(o + 2, alpha * acc[m].z); atomicAdd(o + 3, alpha * acc[m].w);
+      }
+    }
+  }
+}
+
+// ---- wgrad: gw[n][k] = alpha * sum_m gy[m][n] x[m][k]  (rank-M outer product; pure weight-gradient write stream) ----
+template <int MB>
+__global__ void __launch_bounds__(256) linear_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                 float* __restrict__ gw, int M, int K, int Nout, int rows_per_block,
+                                                                 float alpha) {
+  extern __shared__ __align__(16) float xs[];  // [M][K]
+  for (int i = threadIdx.x * 4; i < M * K; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(xs + i) = __ldg(reinterpret_cast<const float4*>(x + i));
+  __syncthreads();
+  const int n0 = blockIdx.x * rows_per_block;
+  const int K4 = K >> 2;
+  for (int i = threadIdx.x; i < rows_per_block * K4; i += blockDim.x) {
+    const int r = i / K4, k = (i - r * K4) * 4;
+    const int n = n0 + r;
+    if (n >= Nout) break;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      if (m < M) {
+        const float g = __ldg(gy + (int64_t)m * Nout + n);
+        const float4 xv = *reinterpret_cast<const float4*>(xs + m * K + k);
+        acc.x = fmaf(g, xv.x, acc.x); acc.y = fmaf(g, xv.y, acc.y); acc.z = fmaf(g, xv.z, acc.z); acc.w = fmaf(g, xv.w, acc.w);
+      }
+    }
+    stg_stream(reinterpret_cast<float4*>(gw + (int64_t)n * K + k), make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w));
+  }
+}
+
+inline bool small_ok(int M, int K) { return M <= kMaxM && K % 4 == 0 && (int64_t)M * K <= kMaxXs; }
+
+}  // namespace
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" int glb_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int K, int Nout, float alpha,
+                              float bias_scale, int act, float slope, glb_stream_t stream) {
+  if (M <= 0 || K <= 0 || Nout <= 0) return shape_fail("linear_fwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!small_ok(M, K)) return conv_fprop_simt(x, w, bias, y, M, 1, 1, K, Nout, 1, 1, 0, alpha, bias_scale, act, slope, st);
+  const int warps = 8;
+  const dim3 grid((Nout + warps - 1) / warps);
+  const size_t smem = sizeof(float) * (size_t)M * K;
+  if (M <= 8)
+    linear_fwd_small_kernel<8><<<grid, warps * 32, smem, st>>>(x, w, bias, y, M, K, Nout, alpha, bias_scale, act, slope);
+  else
+    linear_fwd_small_kernel<16><<<grid, warps * 32, smem, st>>>(x, w, bias, y, M, K, Nout, alpha, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("linear_fwd_small_kernel");
+  return GLB_OK;
+}
+
+extern "C" int glb_linear_dgrad(const float* gy, const float* w, float* gx, int M, int K, int Nout, float alpha,
+                                glb_stream_t stream) {
+  if (M <= 0 || K <= 0 || Nout <= 0) return shape_fail("linear_dgrad");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!small_ok(M, K)) return conv_dgrad_simt(gy, w, gx, M, 1, 1, K, Nout, 1, 1, 0, alpha, st);
+  const int kblocks = (K / 4 + 127) / 128;
+  int nsplit = (2 * kNumSMs) / kblocks;                       // aim at ~2 blocks per SM
+  if (nsplit > (Nout + 15) / 16) nsplit = (Nout + 15) / 16;   // >= 16 weight rows per block
+  if (nsplit < 1) nsplit = 1;
+  const int n_per_block = (Nout + nsplit - 1) / nsplit;
+  nsplit = (Nout + n_per_block - 1) / n_per_block;
+  if (nsplit > 1) GLB_CUDA(cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)M * K, st));
+  const dim3 grid(kblocks, nsplit);
+  const size_t smem = sizeof(float) * (size_t)n_per_block * M;
+  if (M <= 8)
+    linear_dgrad_small_kernel<8><<<grid, 128, smem, st>>>(gy, w, gx, M, K, Nout, n_per_block, alpha);
+  else
+    linear_dgrad_small_kernel<16><<<grid, 128, smem, st>>>(gy, w, gx, M, K, Nout, n_per_block, alpha);
+  GLB_CHECK_LAUNCH("linear_dgrad_small_kernel");
+  return GLB_OK;
+}
+
+extern "C" int glb_linear_wgrad(const float* x, const float* gy, float* gw, int M, int K, int Nout, float alpha,
+                                glb_stream_t stream) {
+  if (M <= 0 || K <= 0 || Nout <= 0) return shape_fail("linear_wgrad");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!small_ok(M, K)) return conv_wgrad_simt(x, gy, gw, M, 1, 1, K, Nout, 1, 1, 0, alpha, st);
+  int rows_per_block = (int)(((int64_t)Nout + 2 * kNumSMs - 1) / (2 * kNumSMs));
+  const int min_rows = (1024 + K / 4 - 1) / (K / 4);  // >= 4 float4 stores per thread
+  if (rows_per_block < min_rows) rows_per_block = min_rows;
+  const dim3 grid((Nout + rows_per_block - 1) / rows_per_block);
+  const size_t smem = sizeof(float) * (size_t)M * K;
+  if (M <= 8)
+    linear_wgrad_small_kernel<8><<<grid, 256, smem, st>>>(x, gy, gw, M, K, Nout, rows_per_block, alpha);
+  else
+    linear_wgrad_small_kernel<16><<<grid, 256, smem, st>>>(x, gy, gw, M, K, Nout, rows_per_block, alpha);
+  GLB_CHECK_LAUNCH("linear_wgrad_small_kernel");
+  return GLB_OK;
+}

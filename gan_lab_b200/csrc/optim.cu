@@ -46,8 +46,25 @@ __global__ void adam_ewma_kernel(const void* const* __restrict__ ptrs, const int
   }
 }
 
+// hyper = [lr, 1-b1^t, 1-b2^t, t]: advance t by one and refresh the bias corrections on the device, so that a captured
+// (CUDA graph) optimiser step replays with the right step count (torch.optim.Adam computes these on the host).
+__global__ void adam_hyper_advance_kernel(float* __restrict__ hyper, float b1, float b2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float t = hyper[3] + 1.f;
+    hyper[3] = t;
+    hyper[1] = (float)(1.0 - pow((double)b1, (double)t));
+    hyper[2] = (float)(1.0 - pow((double)b2, (double)t));
+  }
+}
+
 }  // namespace
 }  // namespace glb
+
+extern "C" int glb_adam_hyper_advance(float* hyper, float beta1, float beta2, glb_stream_t stream) {
+  glb::adam_hyper_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hyper, beta1, beta2);
+  GLB_CHECK_LAUNCH("adam_hyper_advance_kernel");
+  return GLB_OK;
+}
 
 extern "C" int glb_adam_ewma_multi(const void* const* ptrs, const int64_t* sizes, int T, int64_t max_size, const float* hyper,
                                    float beta1, float beta2, float eps, float wd, float ewma_beta, int ewma_mode,

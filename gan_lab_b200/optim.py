@@ -11,23 +11,33 @@ import torch
 from . import _kernels as K
 
 
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 class FusedAdam(torch.optim.Optimizer):
+    """CUDA-graph safe: the bias corrections live in a device-side `hyper` vector advanced by a one-thread kernel, the
+    pointer tables are staged through pinned memory that stays untouched after a capture (`prepare_capture()`), and
+    nothing in `step()` synchronises the host."""
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super(FusedAdam, self).__init__(params, defaults)
         self._ewma = None          # (named lagged tensors aligned with extra params, beta)
         self._ewma_started = False
-        self._hyper_host = None
-        self._hyper_dev = None
+        self._nsteps = 0
+        self._hyper = {}           # cohort -> {'t': device float[4] = lr, 1-b1^t, 1-b2^t, t ; 'lr': value on the device}
+        self._tab = {}             # (group index, cohort) -> cached device tables of the eager path
+        self._capture_slots = None
 
     def attach_ewma(self, named_params, lagged: dict, beta: float):
         """named_params: iterable of (name, param) whose lagged copies live in `lagged[name]` (same shapes/layout)."""
         self._ewma = (list(named_params), lagged, float(beta))
 
     def _tables(self, group):
-        """-> {step: (rows, sizes)}; rows = (p, g, m, v, lagged) pointers.  torch.optim.Adam keeps a step count
-        per parameter (a parameter that had no gradient in some step lags behind), so rows are grouped by it."""
-        by_step = {}
+        """-> {cohort: (rows, sizes)}; rows = (p, g, m, v, lagged) pointers.  torch.optim.Adam keeps a step count per
+        parameter (a parameter first seen later lags behind), so rows are grouped by the step they joined at."""
+        by = {}
         in_opt = set()
         lag_of = {}
         if self._ewma is not None:
@@ -39,6 +49,7 @@ class FusedAdam(torch.optim.Optimizer):
             st = self.state[p]
             if not st:
                 st['step'] = 0
+                st['cohort'] = self._nsteps
                 st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st['step'] += 1
@@ -47,7 +58,7 @@ class FusedAdam(torch.optim.Optimizer):
                 g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
                 p.grad = g
             lag = lag_of.get(id(p))
-            rows, sizes = by_step.setdefault(st['step'], ([], []))
+            rows, sizes = by.setdefault(st['cohort'], ([], []))
             rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
                          lag.data_ptr() if lag is not None else 0))
             sizes.append(p.numel())
@@ -56,19 +67,72 @@ class FusedAdam(torch.optim.Optimizer):
             named, lagged, _ = self._ewma
             extra = [(n, p) for n, p in named if id(p) not in in_opt]
             if extra:
-                key = next(iter(by_step)) if by_step else 1
-                rows, sizes = by_step.setdefault(key, ([], []))
+                key = next(iter(by)) if by else self._nsteps
+                rows, sizes = by.setdefault(key, ([], []))
                 for n, p in extra:
                     rows.append((p.data_ptr(), 0, 0, 0, lagged[n].data_ptr()))
                     sizes.append(p.numel())
-        return by_step
+        return by
+
+    # -- device-side state ---------------------------------------------------------------------------------------
+    def _hyper_for(self, cohort, dev, lr):
+        h = self._hyper.get(cohort)
+        if h is None:
+            h = {'t': torch.zeros(4, dtype=torch.float32, device=dev), 'lr': None}
+            self._hyper[cohort] = h
+        if h['lr'] != lr:
+            if _capturing():
+                raise RuntimeError("FusedAdam: the learning rate changed inside a CUDA-graph capture; call push_lr() first")
+            h['t'][0:1].fill_(lr)
+            h['lr'] = lr
+        return h['t']
+
+    def push_lr(self):
+        """Write a changed learning rate (LambdaLR edits param_groups on the host) to the device copies; called by
+        the learner before replaying a captured step."""
+        for group in self.param_groups:
+            for h in self._hyper.values():
+                if h['lr'] != group['lr']:
+                    h['t'][0:1].fill_(group['lr'])
+                    h['lr'] = group['lr']
+
+    def prepare_capture(self):
+        """Allocate the device tables a captured step() will point its kernel at.  Their CONTENT (pointers known on the
+        host while capturing) is uploaded by finish_capture() after the capture has ended: a host-to-device copy issued
+        inside a capture would leave capture-mode events in torch's pinned-memory allocator."""
+        n = sum(len(g['params']) for g in self.param_groups) + (len(self._ewma[0]) if self._ewma else 0) + 8
+        dev = self.param_groups[0]['params'][0].device
+        self._capture_slots = [torch.empty(6 * n, dtype=torch.int64, device=dev)
+                               for _ in range(max(1, len(self.param_groups)) * 2)]
+        self._pending_uploads = []
+
+    def finish_capture(self):
+        for devbuf, flat in getattr(self, '_pending_uploads', []):
+            devbuf[:len(flat)].copy_(torch.tensor(flat, dtype=torch.int64))
+        self._pending_uploads = []
+
+    def _upload(self, key, rows, sizes, dev):
+        n = len(rows)
+        flat = [v for r in rows for v in r] + list(sizes)
+        if _capturing():
+            if not self._capture_slots:
+                raise RuntimeError("FusedAdam.step() under CUDA-graph capture needs prepare_capture() first")
+            devbuf = self._capture_slots.pop()
+            self._pending_uploads.append((devbuf, flat))
+            return devbuf[:5 * n], devbuf[5 * n:6 * n]
+        ent = self._tab.get(key)
+        if ent is not None and ent[0] == flat:
+            return ent[1], ent[2]
+        devbuf = torch.tensor(flat, dtype=torch.int64).to(dev, non_blocking=True)
+        self._tab[key] = (flat, devbuf[:5 * n], devbuf[5 * n:6 * n])
+        return devbuf[:5 * n], devbuf[5 * n:6 * n]
 
     @torch.no_grad()
     def step(self, closure=None):
         assert closure is None
-        for group in self.param_groups:
-            by_step = self._tables(group)
-            if not by_step:
+        for gi, group in enumerate(self.param_groups):
+            by = self._tables(group)
+            if not by:
                 continue
             dev = group['params'][0].device
             b1, b2 = group['betas']
@@ -76,13 +140,13 @@ class FusedAdam(torch.optim.Optimizer):
             if self._ewma is not None:
                 beta = self._ewma[2]
                 mode = 1 if self._ewma_started else 2
-            for step, (rows, sizes) in by_step.items():
-                table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
-                szs = torch.tensor(sizes, dtype=torch.int64).to(dev, non_blocking=True)
-                hyper = torch.tensor([group['lr'], 1.0 - b1 ** step, 1.0 - b2 ** step, 0.0],
-                                     dtype=torch.float32).to(dev, non_blocking=True)
+            for cohort, (rows, sizes) in by.items():
+                hyper = self._hyper_for(cohort, dev, group['lr'])
+                K.adam_hyper_advance(hyper, b1, b2)
+                table, szs = self._upload((gi, cohort), rows, sizes, dev)
                 K.adam_ewma_multi(table, szs, len(rows), max(sizes), hyper, b1, b2, group['eps'],
                                   group['weight_decay'], beta, mode)
+        self._nsteps += 1
         if self._ewma is not None:
             self._ewma_started = True
         K.weights_updated()          # parameters were rewritten through raw pointers: drop cached weight re-layouts

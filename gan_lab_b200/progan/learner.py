@@ -41,6 +41,7 @@ class ProGANLearner(GANLearner):
     def __init__(self, config):
         super(ProGANLearner, self).__init__(config)
         self.curr_phase_num = 0
+        self._graph_on, self._graph, self._graph_eager_iters, self._graph_warmup = False, None, 0, 3
         self.lagged_params = None
         self._progressively_grow = True
         self.dp = None
@@ -210,6 +211,79 @@ class ProGANLearner(GANLearner):
             self._ewma_started = True
         return loss_train_gen.detach()
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the two steps
+    # One main iteration is ~1000 kernel launches behind ~50 us of Python each; once the kernels are fast the loop is
+    # launch bound.  With `enable_cuda_graphs()` the D step and the G step (forward, double
+    # backward, fused Adam/EWMA, RNG) are captured once per (resolution, phase, batch size) after a few eager
+    # iterations and replayed; the real batch is copied into a static input buffer, the losses are static tensors.
+    def enable_cuda_graphs(self, enabled=True, warmup_iters=3):
+        self._graph_on = bool(enabled)
+        self._graph_warmup = int(warmup_iters)
+        self._graph = None
+        self._graph_eager_iters = 0
+        if hasattr(self.gen_model, '_use_mixing_reg'):
+            self.gen_model.device_mixing = bool(enabled)   # mixing decision on the device (graph replayable)
+
+    def _graph_key(self):
+        g = self.gen_model
+        return (g.curr_res, bool(g.fade_in_phase), float(g.alpha) if g.fade_in_phase else None, self.batch_size,
+                id(self.opt_disc), id(self.opt_gen), self.loss, self.gradient_penalty)
+
+    def _graphs_allowed(self):
+        if not self._graph_on or self.config.num_disc_iters != 1 or self.config.num_gen_iters != 1:
+            return False
+        if self.gen_model.fade_in_phase and getattr(self, 'delta_alpha', 0.0) != 0.0:
+            return False                      # alpha is a kernel argument that changes every iteration while fading in
+        return str(self.config.dev).startswith('cuda')
+
+    def _capture_graphs(self):
+        from .. import _kernels as K
+        c = self.config
+        res = self.gen_model.curr_res
+        st = {'key': self._graph_key(), 'x': torch.empty(self.batch_size, 3, res, res, device=c.dev)}
+        self.opt_disc.prepare_capture(); self.opt_gen.prepare_capture()
+        self.disc_model.zero_grad(set_to_none=True); self.gen_model.zero_grad(set_to_none=True)
+        for p in self.disc_model.parameters():
+            p.requires_grad_(True)
+        K.weights_updated()
+        gd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gd):
+            st['ld'] = self.disc_step(st['x'])
+        for p in self.disc_model.parameters():
+            p.requires_grad_(False)
+        K.weights_updated()
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg, pool=gd.pool()):
+            st['lg'] = self.gen_step()
+        K.weights_updated()
+        self.opt_disc.finish_capture(); self.opt_gen.finish_capture()
+        st['gd'], st['gg'] = gd, gg
+        return st
+
+    def main_iteration(self, xb):
+        """One D step on real batch `xb` + one G step (the num_disc_iters = num_gen_iters = 1 case); eager for the
+        first `warmup_iters` iterations of a phase, CUDA-graph replay afterwards.  Returns (loss_d, loss_g) tensors."""
+        if self._graphs_allowed():
+            if self._graph is not None and self._graph['key'] != self._graph_key():
+                self._graph, self._graph_eager_iters = None, 0
+            if self._graph is None and self._graph_eager_iters >= self._graph_warmup:
+                self._graph = self._capture_graphs()
+            if self._graph is not None:
+                g = self._graph
+                g['x'].copy_(xb, non_blocking=True)
+                self.opt_disc.push_lr(); self.opt_gen.push_lr()
+                g['gd'].replay()
+                g['gg'].replay()
+                return g['ld'], g['lg']
+            self._graph_eager_iters += 1
+        for p in self.disc_model.parameters():
+            p.requires_grad_(True)
+        loss_d = self.disc_step(xb)
+        for p in self.disc_model.parameters():
+            p.requires_grad_(False)
+        loss_g = self.gen_step()
+        return loss_d, loss_g
+
     # ------------------------------------------------------------------ train loop
     def train(self, train_dl, valid_dl=None, z_valid_dl=None, num_main_iters=None, num_gen_iters=None,
               num_disc_iters=None, log_every=0, step_callback=None):
@@ -296,17 +370,23 @@ class ProGANLearner(GANLearner):
                 self.nimg_transition_lst.append(np.inf)
                 self._progressively_grow = False
 
-            # ---- train discriminator ----
-            for disc_iter in range(num_disc_iters):
-                loss_d = self.disc_step(self._next_real(train_dl))
+            if num_disc_iters == 1 and num_gen_iters == 1:
+                # ---- D step + G step (CUDA-graph replay once warmed up, see main_iteration) ----
+                loss_d, loss_g = self.main_iteration(self._next_real(train_dl))
                 self.curr_dataset_batch_num += 1
                 self.curr_img_num += self.batch_size
+            else:
+                # ---- train discriminator ----
+                for disc_iter in range(num_disc_iters):
+                    loss_d = self.disc_step(self._next_real(train_dl))
+                    self.curr_dataset_batch_num += 1
+                    self.curr_img_num += self.batch_size
 
-            # ---- train generator ----
-            for p in self.disc_model.parameters():
-                p.requires_grad_(False)
-            for gen_iter in range(num_gen_iters):
-                loss_g = self.gen_step()
+                # ---- train generator ----
+                for p in self.disc_model.parameters():
+                    p.requires_grad_(False)
+                for gen_iter in range(num_gen_iters):
+                    loss_g = self.gen_step()
 
             self.last_losses = (loss_d, loss_g)
             if step_callback is not None:

@@ -284,10 +284,24 @@ class StyleGenerator(StyleGAN):
         return self.z_to_w(z2)
 
     # ------------------------------------------------------------------ forward
+    def _device_mixing_ws(self, w1, bs):
+        """Mixing regularisation decided ON THE DEVICE (CUDA-graph replayable; reference :417-422, :505-511 draw the
+        decision and the cut-off with host RNGs, which would bake one outcome into a captured graph): the second
+        latent is always mapped, `fire ~ U(0,1) < pct` and `cutoff ~ randint(1, hi)` are device scalars, and layer n
+        uses w2 iff fire and n >= cutoff.  Same distribution as the reference, different random stream."""
+        hi = 2 * self.scale_stage if self.alpha != 0 else 2 * self.scale_stage - 2
+        w2 = self._second_w(bs, w1.device)
+        fire = torch.rand((), device=w1.device) < self.pct_mixing_reg
+        cut = torch.randint(1, max(hi, 2), (), device=w1.device)
+        layers = torch.arange(len(self.gen_layers), device=w1.device)
+        sel = (fire & (layers >= cut)).view(-1, 1, 1)
+        return torch.where(sel, w2.unsqueeze(0), w1.unsqueeze(0))           # [L, N, len_dlatent]
+
     def forward(self, x, x_mixing=None, style_mixing_stage: int = None, noise=None):
         """reference stylegan/architectures.py:411-528."""
         cutoff_idx = None
-        if self._use_mixing_reg:
+        device_mix = self._use_mixing_reg and self.training and getattr(self, 'device_mixing', False)
+        if self._use_mixing_reg and not device_mix:
             if RANDOM.source.host_uniform() < self.pct_mixing_reg:
                 if self.alpha != 0:
                     cutoff_idx = RANDOM.source.host_randint(1, 2 * self.scale_stage)
@@ -308,6 +322,7 @@ class StyleGenerator(StyleGAN):
             elif self.trunc_cutoff_stage is not None:
                 x = self.w_ewma.expand_as(x) + self.w_eval_psi * (x - self.w_ewma.expand_as(x))
 
+        ws = self._device_mixing_ws(x, bs) if device_mix else None
         out = self.const_input.expand(bs, -1, -1, -1)
 
         if self.fade_in_phase:
@@ -316,18 +331,18 @@ class StyleGenerator(StyleGAN):
                     out = self._layer_conv(layer, out)
                 if n == cutoff_idx:
                     x = self._second_w(bs, x.device)
-                out = self._layer_tail(layer, out, x, noise[n] if noise is not None else None)
+                out = self._layer_tail(layer, out, x if ws is None else ws[n], noise[n] if noise is not None else None)
             skip = self.prev_torgb(out)
             n += 1
             if n == cutoff_idx:
                 x = self._second_w(bs, x.device)
             out = self._layer_conv(self.gen_layers[-2], out)
-            out = self._layer_tail(self.gen_layers[-2], out, x, noise[-2] if noise is not None else None)
+            out = self._layer_tail(self.gen_layers[-2], out, x if ws is None else ws[n], noise[-2] if noise is not None else None)
             n += 1
             if n == cutoff_idx:
                 x = self._second_w(bs, x.device)
             out = self._layer_conv(self.gen_layers[-1], out)
-            out = self._layer_tail(self.gen_layers[-1], out, x, noise[-1] if noise is not None else None)
+            out = self._layer_tail(self.gen_layers[-1], out, x if ws is None else ws[n], noise[-1] if noise is not None else None)
             return ops.fade_up_blend(skip, self.torgb(out), self.alpha)
 
         for n, layer in enumerate(self.gen_layers):
@@ -343,7 +358,7 @@ class StyleGenerator(StyleGAN):
             elif self.use_truncation_trick and not self.training and self.trunc_cutoff_stage is not None and \
                     n == 2 * self.trunc_cutoff_stage:
                 x = (x - self.w_ewma.expand_as(x)).div(self.w_eval_psi) + self.w_ewma.expand_as(x)
-            out = self._layer_tail(layer, out, x, noise[n] if noise is not None else None)
+            out = self._layer_tail(layer, out, x if ws is None else ws[n], noise[n] if noise is not None else None)
         return self.torgb(out)
 
 

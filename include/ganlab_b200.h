@@ -187,8 +187,10 @@ int glb_w_ewma(const float* w, float* ewma, int M, int K, float beta, glb_stream
  * also lagged = p*(1-ewma_beta) + lagged*ewma_beta in the same pass (progan/learner.py:909-916).
  * ptrs: device array of 5*T pointers [p, g, m, v, lagged(or NULL)] per tensor (g == NULL: EWMA only, no Adam);
  * sizes: device int64[T]; ewma_mode 0 = off, 1 = running, 2 = first step (lagged aliases p, progan/learner.py:472);
- * bc1 = 1-beta1^step, bc2 = 1-beta2^step are passed as device scalars in `hyper` (float[4]:
- * lr, bc1, bc2, unused) so the launch is CUDA-graph replayable with a changing step count. */
+ * bc1 = 1-beta1^step, bc2 = 1-beta2^step are read from the device vector `hyper` (float[4]: lr, bc1, bc2, step) so
+ * the launch is CUDA-graph replayable with a changing step count; glb_adam_hyper_advance does step += 1 and
+ * refreshes bc1/bc2 on the device (what torch.optim.Adam computes on the host each step). */
+int glb_adam_hyper_advance(float* hyper, float beta1, float beta2, glb_stream_t stream);
 int glb_adam_ewma_multi(const void* const* ptrs, const int64_t* sizes, int T, int64_t max_size,
                         const float* hyper, float beta1, float beta2, float eps, float wd,
                         float ewma_beta, int ewma_mode, glb_stream_t stream);

@@ -296,8 +296,16 @@ def _from_ptr(ptr, n):
     return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr)))
 
 
+def adam_hyper_advance(hyper, beta1, beta2):
+    t = float(hyper[3]) + 1.0
+    hyper[3] = t
+    hyper[1] = 1.0 - beta1 ** t
+    hyper[2] = 1.0 - beta2 ** t
+
+
 def adam_ewma_multi(ptr_table, sizes, T, max_size, hyper, beta1, beta2, eps, wd, ewma_beta, ewma_mode):
     lr, bc1, bc2 = float(hyper[0]), float(hyper[1]), float(hyper[2])
+    ptr_table = ptr_table.view(-1, 5)
     for t in range(T):
         pp, gp, mp, vp, lp = [int(v) for v in ptr_table[t]]
         n = int(sizes[t])

@@ -283,6 +283,38 @@ def test_learner_train(golden, fname, model):
     PC.case_learner_train(golden, DEV, fname, model)
 
 
+def test_cuda_graph_replay_of_train_steps():
+    """D step + G step captured into CUDA graphs (device-side mixing decision, device-side Adam step count) and replayed:
+    the optimiser state advances per replay, fresh latents/noise are drawn per replay, and everything stays finite."""
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    torch.manual_seed(0)
+    cfg = default_config("StyleGAN", res=16, batch_size=4, dev=DEV, len_latent=32, len_dlatent=32, cutoff_trunc_trick=2)
+    L = StyleGANLearner(cfg)
+    L.gen_model.train(); L.disc_model.train()
+    L.beta = L.get_smoothing_ewma_beta(10.)
+    L._init_lagged(); L._attach_ewma()
+    L.enable_cuda_graphs(True, warmup_iters=2)
+    x = torch.rand(4, 3, 16, 16, device=DEV) * 2 - 1
+    for _ in range(2):
+        L.main_iteration(x)
+    assert L._graph is None
+    ld, lg = L.main_iteration(x)                      # capture + first replay
+    assert L._graph is not None
+    torch.cuda.synchronize()
+    step0 = float(next(iter(L.opt_disc._hyper.values()))['t'][3])
+    w0 = L.disc_model.state_dict()["fromrgb.0.conv2d.weight"].clone()
+    l1 = (float(ld), float(lg))
+    ld, lg = L.main_iteration(x)
+    torch.cuda.synchronize()
+    l2 = (float(ld), float(lg))
+    assert float(next(iter(L.opt_disc._hyper.values()))['t'][3]) == step0 + 1
+    assert not torch.equal(w0, L.disc_model.state_dict()["fromrgb.0.conv2d.weight"])
+    assert all(math.isfinite(v) for v in l1 + l2) and l1 != l2
+    for p in list(L.gen_model.parameters()) + list(L.disc_model.parameters()) + list(L.gen_model_lagged.parameters()):
+        assert torch.isfinite(p).all()
+
+
 def test_library_was_loaded():
     from gan_lab_b200._lib import LIB
     assert LIB._dll is not None and K.launch_count() > 0
