@@ -508,7 +508,10 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   p.tiles_co = (Co + 127) / 128;
   p.tiles_ci = Ci / BN;
   const int tiles = p.tiles_co * p.tiles_ci * p.RS;
-  int splits = (2 * kNumSMs + tiles - 1) / tiles;           // aim at ~2 CTAs' worth of work items per SM
+  // one wave: every CTA pays the 128 x BN red.add epilogue once, so fewer, longer work items win (ncu: with ~2.4 waves
+  // of short items the atomics epilogue cost more than the MMA main loop)
+  int splits = kNumSMs / tiles;
+  if (splits > p.num_pb / 4) splits = p.num_pb / 4;         // >= 4 pixel blocks (128 pixels of K) per work item
   if (splits > p.num_pb) splits = p.num_pb;
   if (splits < 1) splits = 1;
   p.pb_per_split = (p.num_pb + splits - 1) / splits;
