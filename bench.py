@@ -206,6 +206,11 @@ def run_ours(args):
         from gan_lab_b200.parallel import DataParallel
         L.dp = DataParallel(world)
         L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
+    def log(msg):
+        if args.verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    log("models built, parameters broadcast")
     L.gen_model.train(); L.disc_model.train()
     L.beta = L.get_smoothing_ewma_beta(10.)
     L._init_lagged(); L._attach_ewma()
@@ -244,10 +249,12 @@ def run_ours(args):
         l0 = K.launch_count()
         main_iter(pool_dev[i % n_pool])
         launches_per_iter = max(launches_per_iter, K.launch_count() - l0)
+        log(f"eager warm-up iteration {i} done")
     if use_graphs:
         for i in range(3):
             main_iter(pool_dev[i % n_pool])
         assert L._graph is not None, "CUDA graphs were requested but not captured"
+        log("graphs captured and replayed")
     barrier()
 
     # ---- value: inputs resident in HBM -------------------------------------------------------------
@@ -262,6 +269,7 @@ def run_ours(args):
     ev[1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[1])
+    log(f"timed region done: {ms / args.steps:.2f} ms/step")
     launches = launches_per_iter * args.steps   # kernels of this repo per main iteration (counted on an eager iteration) x steps
     if sampler:
         sampler.stop_flag.set(); sampler.join(timeout=2)
@@ -302,6 +310,7 @@ def run_ours(args):
     ms_e2e = float(t)
     L.sched_bool = sched
 
+    log("e2e done")
     # ---- roofline of the dominant kernel family (dense convs), timed live with CUDA events on the launch stream ----
     roof = conv_roofline(L, pool_dev[0], main_iter_eager, flush) if rank == 0 else None
 
@@ -371,12 +380,12 @@ def conv_roofline(L, x, main_iter, flush):
         return 2.0 * gy_.shape[0] * gy_.shape[2] * gy_.shape[3] * out.numel()
 
     wrap("conv_fprop", f_fprop); wrap("conv_dgrad", f_dgrad); wrap("conv_wgrad", f_wgrad)
+    dp, L.dp = L.dp, None          # rank-local pass: no collective may run here (the other ranks are not in it)
     try:
-        with torch.no_grad():
-            pass
         main_iter(x)
         torch.cuda.synchronize()
     finally:
+        L.dp = dp
         for n, f in orig.items():
             setattr(K, n, f)
     by = {}
@@ -439,6 +448,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
     ap.add_argument("--conv-impl", default=os.environ.get("GLB_CONV_IMPL", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="progress lines on stderr")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay of the D/G steps")
     args = ap.parse_args()
     if args.impl == "reference":

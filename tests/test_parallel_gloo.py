@@ -1,0 +1,66 @@
+"""Data-parallel host logic (gan_lab_b200/parallel.py) on CPU: world_size 2, gloo backend.
+
+What is checked is the N>1 plumbing itself -- parameter broadcast, bucketed gradient averaging incl. channels-last
+gradients, parameters without a gradient (prev_torgb / prev_fromrgb outside fade-in), the mean all-reduce used for w_ewma --
+with plain torch modules standing in for the CUDA layers."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gan_lab_b200.parallel import DataParallel
+        torch.manual_seed(100 + rank)                       # different initial weights per rank
+        net = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3, padding=1), torch.nn.Conv2d(8, 8, 3, padding=1),
+                                  torch.nn.Conv2d(8, 3, 1))
+        net[0].weight.data = net[0].weight.data.contiguous(memory_format=torch.channels_last)
+        unused = torch.nn.Parameter(torch.randn(5))        # never receives a gradient
+        net.register_parameter("unused", unused)
+        dp = DataParallel(world, bucket_bytes=1024)         # tiny buckets -> several all-reduces
+        dp.broadcast_params(net)
+        w_after_bcast = [p.detach().clone() for p in net.parameters()]
+        torch.manual_seed(7 + rank)                         # different data per rank
+        x = torch.randn(4, 4, 6, 6)
+        net(x).pow(2).mean().backward()
+        local = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
+        dp.allreduce_grads(net)
+        avg = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
+        t = torch.full((3,), float(rank + 1))
+        dp.allreduce_mean_(t)
+        ret[rank] = dict(bcast=w_after_bcast, local=local, avg=avg, mean=t)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dataparallel_world2_gloo():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    r0, r1 = ret[0], ret[1]
+    for a, b in zip(r0["bcast"], r1["bcast"]):             # rank 0's parameters everywhere
+        assert torch.equal(a, b)
+    for l0, l1, a0, a1 in zip(r0["local"], r1["local"], r0["avg"], r1["avg"]):
+        if l0 is None:
+            assert a0 is None and a1 is None and l1 is None
+            continue
+        assert not torch.equal(l0, l1)
+        want = (l0 + l1) / 2
+        torch.testing.assert_close(a0, want, rtol=1e-6, atol=1e-7)
+        assert torch.equal(a0, a1)
+        assert a0.stride() == l0.stride()                   # layout of the gradient (channels_last) preserved
+    assert torch.allclose(r0["mean"], torch.full((3,), 1.5)) and torch.equal(r0["mean"], r1["mean"])
