@@ -343,7 +343,17 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured NCCL work keeps the communicator busy: drop the graphs first, then tear down; never let a stuck
+        # communicator teardown hang the benchmark after the result line is out.
+        L._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=20)
+        os._exit(0)
 
 
 def conv_roofline(L, x, main_iter, flush):

@@ -28,7 +28,8 @@ struct FpropParams {
   int Ci, R, S, pad;
   int bw, bh, bn;  // M-tile box, bw*bh*bn == 128
   int tiles_w, tiles_h, tiles_n, tiles_co;
-  int num_tiles;
+  int num_tiles;   // work items = output tiles x ksplit
+  int ksplit, k_per;  // split-K: slice j of an output tile owns k iterations [j*k_per, min(k_iters, (j+1)*k_per))
   float alpha, bias_scale;
   int act;
   float slope;
@@ -37,6 +38,10 @@ struct FpropParams {
 constexpr int kBM = 128;           // MMA M (output pixels per tile)
 constexpr int kChunk = 32;         // channels per K chunk = 128 bytes = one swizzle row
 constexpr int kABytes = kBM * 128; // 16 KB
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <int BN>
 struct FpropCfg {
@@ -94,24 +99,26 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tco = tile % p.tiles_co;
-        int t = tile / p.tiles_co;
+      for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+        const int ks = item % p.ksplit;
+        int t = item / p.ksplit;
+        const int tco = t % p.tiles_co; t /= p.tiles_co;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int tn = t;
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, co0 = tco * BN;
-        for (int tap = 0; tap < p.R * p.S; ++tap) {
+        const int k0 = ks * p.k_per, k1 = min(k_iters, k0 + p.k_per);
+        int tap = k0 / chunks, ch = k0 - tap * chunks;
+        for (int k = k0; k < k1; ++k) {
           const int r = tap / p.S, s = tap - r * p.S;
-          for (int ch = 0; ch < chunks; ++ch) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-            const uint32_t b_dst = a_dst + kABytes;
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_4d(a_dst, &tmA, full_bar(stage), ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
-            tma_load_3d(b_dst, &tmB, full_bar(stage), ch * kChunk, tap, co0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+          const uint32_t b_dst = a_dst + kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_4d(a_dst, &tmA, full_bar(stage), ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma_load_3d(b_dst, &tmB, full_bar(stage), ch * kChunk, tap, co0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++ch == chunks) { ch = 0; ++tap; }
         }
       }
     }
@@ -123,11 +130,13 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
         mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int k = 0; k < k_iters; ++k) {
+        const int ks = item % p.ksplit;
+        const int k_cnt = min(k_iters, (ks + 1) * p.k_per) - ks * p.k_per;
+        for (int k = 0; k < k_cnt; ++k) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = base + stage * Cfg::kStageBytes;
@@ -152,9 +161,9 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rn = row / (p.bw * p.bh);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int tco = tile % p.tiles_co;
-      int t = tile / p.tiles_co;
+    for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+      int t = item / p.ksplit;
+      const int tco = t % p.tiles_co; t /= p.tiles_co;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int tn = t;
@@ -170,17 +179,24 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
         tmem_ld_wait();
         if (valid) {
+          if (p.ksplit > 1) {  // split-K partial: summed into the zeroed output; bias / activation run as a second pass
 #pragma unroll
-          for (int j = 0; j < EC; j += 4) {
-            float4 o;
-            float* oo = reinterpret_cast<float*>(&o);
+            for (int j = 0; j < EC; j += 4)
+              red_add_v4(out + c + j, p.alpha * __uint_as_float(v[j]), p.alpha * __uint_as_float(v[j + 1]),
+                         p.alpha * __uint_as_float(v[j + 2]), p.alpha * __uint_as_float(v[j + 3]));
+          } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = p.alpha * __uint_as_float(v[j + e]);
-              if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
-              oo[e] = act_apply(a, p.act, p.slope);
+            for (int j = 0; j < EC; j += 4) {
+              float4 o;
+              float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = p.alpha * __uint_as_float(v[j + e]);
+                if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
+                oo[e] = act_apply(a, p.act, p.slope);
+              }
+              *reinterpret_cast<float4*>(out + c + j) = o;
             }
-            *reinterpret_cast<float4*>(out + c + j) = o;
           }
         }
       }
@@ -244,15 +260,38 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   p.bw = next_pow2(p.Wo) < 16 ? next_pow2(p.Wo) : 16;
   p.bh = next_pow2(p.Ho) < kBM / p.bw ? next_pow2(p.Ho) : kBM / p.bw;
   p.bn = kBM / (p.bw * p.bh);
-  int BN = Co % 256 == 0 ? 256 : (Co % 128 == 0 ? 128 : Co);
   p.tiles_w = (p.Wo + p.bw - 1) / p.bw;
   p.tiles_h = (p.Ho + p.bh - 1) / p.bh;
   p.tiles_n = (N + p.bn - 1) / p.bn;
-  // few M tiles (low resolutions): narrower N tiles spread the weight stream over more SMs
-  while (BN > 32 && (int64_t)p.tiles_w * p.tiles_h * p.tiles_n * (Co / BN) < kNumSMs / 2) BN >>= 1;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int k_iters = R * S * (Ci / kChunk);
+  int BN = Co % 256 == 0 ? 256 : (Co % 128 == 0 ? 128 : Co);
+  int ksplit = 1;
+  if (m_tiles * (Co / BN) < kNumSMs / 2) {
+    // Low-resolution layers: a handful of output tiles behind a long K loop is latency bound (one CTA streams K at
+    // ~0.3 us per 32-channel step).  Pick the N tile and a split of K over CTAs (partials reduced with red.add) that
+    // minimise a simple cost model: waves x (k steps x 0.3 us + epilogue) .
+    double best = 1e30;
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+      if (Co % bn != 0) continue;
+      const int tiles = m_tiles * (Co / bn);
+      for (int sp = 1; sp <= 16; ++sp) {
+        const int kper = (k_iters + sp - 1) / sp;
+        if (sp > 1 && kper < 8) break;
+        const int items = tiles * ((k_iters + kper - 1) / kper);
+        const int waves = (items + kNumSMs - 1) / kNumSMs;
+        const double cost = waves * (kper * (0.28 + 0.0004 * bn) + (sp > 1 ? 0.06 : 0.012) * bn + 3.0);
+        if (cost < best) { best = cost; BN = bn; ksplit = sp; }
+      }
+    }
+  }
+  p.k_per = (k_iters + ksplit - 1) / ksplit;
+  p.ksplit = (k_iters + p.k_per - 1) / p.k_per;
   p.tiles_co = Co / BN;
-  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+  p.num_tiles = m_tiles * p.tiles_co * p.ksplit;
   p.alpha = alpha; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+  const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
+  if (p.ksplit > 1) GLB_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * p.Ho * p.Wo * Co, st));
 
   CUtensorMap tmA, tmB;
   {
@@ -269,15 +308,18 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
     int rc = make_tmap_f32(&tmB, w, 3, dims, strides, box, "conv weight");
     if (rc) return rc;
   }
+  int rc = GLB_ERR_UNSUPPORTED;
   switch (BN) {
-    case 256: return launch_fprop<256>(tmA, tmB, p, st);
-    case 128: return launch_fprop<128>(tmA, tmB, p, st);
-    case 64: return launch_fprop<64>(tmA, tmB, p, st);
-    case 32: return launch_fprop<32>(tmA, tmB, p, st);
-    case 16: return launch_fprop<16>(tmA, tmB, p, st);
+    case 256: rc = launch_fprop<256>(tmA, tmB, p, st); break;
+    case 128: rc = launch_fprop<128>(tmA, tmB, p, st); break;
+    case 64: rc = launch_fprop<64>(tmA, tmB, p, st); break;
+    case 32: rc = launch_fprop<32>(tmA, tmB, p, st); break;
+    case 16: rc = launch_fprop<16>(tmA, tmB, p, st); break;
+    default: set_error("tcgen05 fprop: no kernel for this N tile");
   }
-  set_error("tcgen05 fprop: no kernel for this N tile");
-  return GLB_ERR_UNSUPPORTED;
+  if (rc == GLB_OK && post_pass)
+    rc = glb_bias_act_fwd(y, bias, y, (int64_t)N * p.Ho * p.Wo, Co, bias_scale, act, slope, (glb_stream_t)st);
+  return rc;
 }
 
 // dgrad = fprop over gy with the flipped / transposed weights wt[Ci][R][S][Co] (glb_conv2d_weight_transpose):
@@ -338,10 +380,6 @@ struct WgradCfg {
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)

@@ -16,10 +16,10 @@ namespace glb {
 namespace {
 
 constexpr int TPB = 256;
-constexpr int CHUNK = 256;  // pixels per block
+constexpr int MAX_CHUNK = 256;  // pixels per block, upper bound
 
 struct SE {
-  int N, HW, C4, chunks;
+  int N, HW, C4, chunks, chunk;  // chunk = pixels per block (runtime: sized so that ~2 blocks land on every SM)
   float slope;
 };
 
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(TPB) se_fwd_stats_kernel(const float4* __restr
   __shared__ float4 red[2 * TPB];
   const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
   const int n = blockIdx.y, chunk = blockIdx.x;
-  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const int p0 = chunk * g.chunk, p1 = min(g.HW, p0 + g.chunk);
   const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TPB) se_fwd_stats_kernel(const float4* __restr
 
 // stats layout: [N][2][C] = (mu plane, rstd plane)
 __global__ void se_fwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int N, int C, int chunks, int HW,
-                                       float eps) {
+                                       int CHUNK, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TPB) se_fwd_apply_kernel(const float4* __restr
                                                            float4* __restrict__ out, SE g) {
   const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
   const int n = blockIdx.y, chunk = blockIdx.x;
-  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const int p0 = chunk * g.chunk, p1 = min(g.HW, p0 + g.chunk);
   const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TPB) se_bwd_stats_kernel(const float4* __restr
   __shared__ float4 red[2 * TPB];
   const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
   const int n = blockIdx.y, chunk = blockIdx.x;
-  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const int p0 = chunk * g.chunk, p1 = min(g.HW, p0 + g.chunk);
   const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TPB) se_bwd_apply_kernel(const float4* __restr
   __shared__ float4 red[2 * TPB];
   const int tid = threadIdx.x, q = tid % g.C4, rl = tid / g.C4, rows = TPB / g.C4;
   const int n = blockIdx.y, chunk = blockIdx.x;
-  const int p0 = chunk * CHUNK, p1 = min(g.HW, p0 + CHUNK);
+  const int p0 = chunk * g.chunk, p1 = min(g.HW, p0 + g.chunk);
   const float4 w4 = nw ? __ldg(nw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
@@ -225,9 +225,20 @@ __global__ void __launch_bounds__(TPB) se_bwd_apply_kernel(const float4* __restr
   }
 }
 
+// pixels per block: aim at ~2 blocks per SM over the whole (N, HW) range, a multiple of the rows a block covers per
+// iteration, at most MAX_CHUNK (low-resolution layers otherwise run on 8 blocks)
+int se_chunk(int N, int HW, int C) {
+  const int rows = TPB / (C / 4) > 0 ? TPB / (C / 4) : 1;
+  int64_t chunk = ((int64_t)N * HW + 2 * kNumSMs - 1) / (2 * kNumSMs);
+  chunk = ((chunk + rows - 1) / rows) * rows;
+  if (chunk > MAX_CHUNK) chunk = MAX_CHUNK;
+  if (chunk < rows) chunk = rows;
+  return (int)chunk;
+}
+
 int se_geom(SE& g, int N, int H, int W, int C, float slope) {
   if (C % 4 != 0 || C / 4 > TPB || TPB % (C / 4) != 0) return shape_fail("style_epilogue: C/4 must divide 256");
-  g.N = N; g.HW = H * W; g.C4 = C / 4; g.chunks = (g.HW + CHUNK - 1) / CHUNK; g.slope = slope;
+  g.N = N; g.HW = H * W; g.C4 = C / 4; g.chunk = se_chunk(N, g.HW, C); g.chunks = (g.HW + g.chunk - 1) / g.chunk; g.slope = slope;
   if (N > 65535) return shape_fail("style_epilogue: N > 65535");
   return GLB_OK;
 }
@@ -238,7 +249,9 @@ int se_geom(SE& g, int N, int H, int W, int C, float slope) {
 using namespace glb;
 
 extern "C" int64_t glb_style_epilogue_work_floats(int N, int H, int W, int C) {
-  const int64_t chunks = ((int64_t)H * W + CHUNK - 1) / CHUNK;
+  if (C < 4) return 0;
+  const int chunk = glb::se_chunk(N, H * W, C);
+  const int64_t chunks = ((int64_t)H * W + chunk - 1) / chunk;
   return (int64_t)N * chunks * 3 * C + (int64_t)N * 2 * C;
 }
 
@@ -251,7 +264,7 @@ extern "C" int glb_style_epilogue_fwd(const float* x, const float* noise, const 
   dim3 grid(g.chunks, N);
   se_fwd_stats_kernel<<<grid, TPB, 0, st>>>((const float4*)x, noise, (const float4*)noise_weight, (const float4*)bias, (float4*)work, g);
   GLB_CHECK_LAUNCH("se_fwd_stats");
-  se_fwd_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(work, stats, N, C, g.chunks, g.HW, eps);
+  se_fwd_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(work, stats, N, C, g.chunks, g.HW, g.chunk, eps);
   GLB_CHECK_LAUNCH("se_fwd_finalize");
   se_fwd_apply_kernel<<<grid, TPB, 0, st>>>((const float4*)x, noise, (const float4*)noise_weight, (const float4*)bias,
                                             (const float4*)style, (const float4*)stats, (float4*)out, g);
