@@ -15,6 +15,8 @@
 //     thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> alpha/bias/act -> HBM).
 //     smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator stages (tmem_full/empty
 //     mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace glb {
@@ -215,6 +217,194 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair fprop
+// Same implicit GEMM with tcgen05 cta_group::2: a cluster of two CTAs (one TPC) computes a 256-pixel x BN tile.  Each CTA
+// stages its own 128-pixel A tile and HALF of the B (weight) tile; one MMA issued by the leader reads A from both CTAs
+// and the two B halves (M = 256, N = BN).  Per SM and K step that is (16 KB + BN*64 B) of TMA fill and the same of operand
+// reads instead of (16 KB + BN*128 B) -- the single-CTA kernel is bound by exactly that shared-memory traffic (ncu: tensor
+// pipe 68-71 % at BN = 256, 46 % at BN = 128, while a bare tcgen05.mma loop reaches 100 %, tools/micro/mma_rate.cu).
+// Barriers: full[] lives in the leader (count 1 = its arrive.expect_tx for BOTH CTAs' bytes; both CTAs' TMA complete_tx on
+// it), empty[] / tmem_full[] exist in both CTAs and are arrived by the leader's multicast tcgen05.commit, tmem_empty[] lives
+// in the leader and collects the 8 epilogue warps of the pair.
+template <int BN>
+struct Fprop2Cfg {
+  static constexpr int kBBytes = (BN / 2) * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 6 : 8;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  using Cfg = Fprop2Cfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  const uint32_t bar0 = base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int chunks = p.Ci / kChunk;
+  const int k_iters = p.R * p.S * chunks;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);  // 4 epilogue warps in each CTA of the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+        const int tco = item % p.tiles_co;
+        int t = (item / p.tiles_co) * 2 + (int)rank;  // this CTA's M tile
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int tn = t;
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        const int co0 = tco * BN + (int)rank * (BN / 2);  // this CTA's half of the weight tile
+        int tap = 0, ch = 0;
+        for (int k = 0; k < k_iters; ++k) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+          const uint32_t b_dst = a_dst + kABytes;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          const uint32_t lfull = mapa(full_bar(stage), 0);
+          tma2_load_4d(a_dst, &tmA, lfull, ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma2_load_3d(b_dst, &tmB, lfull, ch * kChunk, tap, co0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++ch == chunks) { ch = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
+            mma2_tf32(d_tmem, ad, bd, idesc, (k | kk) ? 1u : 0u);
+          }
+          mma2_commit_mc(empty_bar(stage), 3);  // frees this stage in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma2_commit_mc(tfull_bar(as), 3);  // accumulators complete -> both epilogues
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): own 128 rows of the pair's accumulator =====================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rn = row / (p.bw * p.bh);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+      const int tco = item % p.tiles_co;
+      int t = (item / p.tiles_co) * 2 + (int)rank;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int tn = t;
+      const int w = tw * p.bw + rw, h = th * p.bh + rh, n = tn * p.bn + rn, co0 = tco * BN;
+      const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.N);
+      float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = p.alpha * __uint_as_float(v[j + e]);
+              if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
+              oo[e] = act_apply(a, p.act, p.slope);
+            }
+            *reinterpret_cast<float4*>(out + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_fprop2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = Fprop2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+  conv_fprop_tc2_kernel<BN><<<2 * pairs, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GLB_CHECK_LAUNCH("conv_fprop_tc2_kernel");
+  return GLB_OK;
+}
+
 inline int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -293,6 +483,12 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
   if (p.ksplit > 1) GLB_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * p.Ho * p.Wo * Co, st));
 
+  // CTA pairs (cta_group::2) for the layers with at least one wave of pair tiles
+  // (measured: +10 % at BN = 256, no gain at BN = 128, where the loop is bound by L2 -> SM traffic rather than shared memory)
+  bool use_pair = p.ksplit == 1 && BN == 256 && m_tiles % 2 == 0 && (m_tiles / 2) * p.tiles_co >= kNumSMs / 4;
+  if (const char* e = getenv("GLB_FPROP_PAIR")) use_pair = use_pair && atoi(e) != 0;  // tuning experiments only
+  if (use_pair) p.num_tiles = (m_tiles / 2) * p.tiles_co;   // pair items
+
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -304,10 +500,11 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   {
     const uint64_t dims[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
     const uint64_t strides[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
-    const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)BN};
+    const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)(use_pair ? BN / 2 : BN)};
     int rc = make_tmap_f32(&tmB, w, 3, dims, strides, box, "conv weight");
     if (rc) return rc;
   }
+  if (use_pair) return BN == 256 ? launch_fprop2<256>(tmA, tmB, p, st) : launch_fprop2<128>(tmA, tmB, p, st);
   int rc = GLB_ERR_UNSUPPORTED;
   switch (BN) {
     case 256: rc = launch_fprop<256>(tmA, tmB, p, st); break;
@@ -551,6 +748,7 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   int splits = kNumSMs / tiles;
   if (splits > p.num_pb / 4) splits = p.num_pb / 4;         // >= 4 pixel blocks (128 pixels of K) per work item
   if (splits > p.num_pb) splits = p.num_pb;
+  if (const char* e = getenv("GLB_WGRAD_SPLITS")) splits = atoi(e);  // tuning experiments only
   if (splits < 1) splits = 1;
   p.pb_per_split = (p.num_pb + splits - 1) / splits;
   p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;  // every split owns >= 1 pixel block
