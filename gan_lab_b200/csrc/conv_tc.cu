@@ -31,6 +31,8 @@ struct FpropParams {
   int bw, bh, bn;  // M-tile box, bw*bh*bn == 128
   int tiles_w, tiles_h, tiles_n, tiles_co;
   int num_tiles;   // work items = output tiles x ksplit
+  long long* trace;   // tuning experiments only: per-CTA clock64 timeline (8 slots) or NULL
+  int dbg;            // tuning experiments only: 1 = skip the A loads of taps > 0, 2 = skip the B loads of all but the first k step
   int ksplit, k_per;  // split-K: slice j of an output tile owns k iterations [j*k_per, min(k_iters, (j+1)*k_per))
   float alpha, bias_scale;
   int act;
@@ -45,19 +47,26 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN>
+// KC = 32-channel K chunks per pipeline stage.  The single MMA-issuing thread pays ~225 cycles of wait / fence / commit per
+// stage (tools/micro/mma_rate.cu): with 4 MMAs of N <= 128 (<= 64 cycles each) per stage that protocol, not the tensor
+// pipe, sets the pace (measured 576-642 cycles per stage at BN = 128), so narrow tiles use 2 chunks = 8 MMAs per stage.
+template <int BN, int KC>
 struct FpropCfg {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kChunkBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = KC * kChunkBytes;
+  static constexpr int kStages = (192 * 1024 / kStageBytes) > 8 ? 8 : (192 * 1024 / kStageBytes);
   static constexpr int kTmemCols = (2 * BN < 64) ? 64 : 2 * BN;  // power of two >= 32; the epilogue reads 32-column groups
+  static constexpr int kEpiWarps = (BN >= 64) ? 8 : 4;           // 8: two warps per TMEM lane quarter, half the columns each
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+constexpr int kFpropThreads = 384;  // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
-  using Cfg = FpropCfg<BN>;
+  using Cfg = FpropCfg<BN, KC>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -74,6 +83,8 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_iters = p.R * p.S * (p.Ci / kChunk);
   const int chunks = p.Ci / kChunk;
+  long long* tr = p.trace ? p.trace + 8 * blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -86,7 +97,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), Cfg::kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -95,6 +106,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();   // setup done
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -111,16 +123,18 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, co0 = tco * BN;
         const int k0 = ks * p.k_per, k1 = min(k_iters, k0 + p.k_per);
         int tap = k0 / chunks, ch = k0 - tap * chunks;
-        for (int k = k0; k < k1; ++k) {
-          const int r = tap / p.S, s = tap - r * p.S;
+        for (int k = k0; k < k1; k += KC) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-          const uint32_t b_dst = a_dst + kABytes;
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_4d(a_dst, &tmA, full_bar(stage), ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
-          tma_load_3d(b_dst, &tmB, full_bar(stage), ch * kChunk, tap, co0);
+#pragma unroll
+          for (int c = 0; c < KC; ++c) {
+            const int r = tap / p.S, s = tap - r * p.S;
+            const uint32_t a_dst = base + stage * Cfg::kStageBytes + c * Cfg::kChunkBytes;
+            tma_load_4d(a_dst, &tmA, full_bar(stage), ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_3d(a_dst + kABytes, &tmB, full_bar(stage), ch * kChunk, tap, co0);
+            if (++ch == chunks) { ch = 0; ++tap; }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          if (++ch == chunks) { ch = 0; ++tap; }
         }
       }
     }
@@ -138,27 +152,40 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t d_tmem = tmem_base + as * BN;
         const int ks = item % p.ksplit;
         const int k_cnt = min(k_iters, (ks + 1) * p.k_per) - ks * p.k_per;
-        for (int k = 0; k < k_cnt; ++k) {
+        for (int k = 0; k < k_cnt; k += KC) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = base + stage * Cfg::kStageBytes;
-          const uint32_t b_addr = a_addr + kABytes;
+          if (tr && k == 0 && item == (int)blockIdx.x) tr[2] = clock64();   // first operands landed
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
-            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
-            mma_tf32(d_tmem, ad, bd, idesc, (k | kk) ? 1u : 0u);
+          for (int c = 0; c < KC; ++c) {
+            const uint32_t a_addr = base + stage * Cfg::kStageBytes + c * Cfg::kChunkBytes;
+            const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
+              const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
+              mma_tf32(d_tmem, ad, bd, idesc, (k | c | kk) ? 1u : 0u);
+            }
           }
           mma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        if (tr && item == (int)blockIdx.x) tr[3] = clock64();                // first tile: all MMAs issued
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
+      if (tr) tr[4] = clock64();                                            // all tiles: all MMAs issued
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + Cfg::kEpiWarps) {
     // ===================== epilogue: TMEM -> regs -> alpha/bias/act -> global (NHWC) =====================
-    const int q = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
+    // A thread owns one output pixel (TMEM lane) and writes its 32-column fragments with 16-byte stores.  Measured
+    // alternatives (clock64 trace, tools/trace_fprop.py): a shared-memory-staged TMA tile store and a per-warp staged,
+    // fully coalesced store were both SLOWER (16.8k / 21k vs 10.7k cycles per 128x256 tile when all CTAs drain at once):
+    // the burst of 128 KB per CTA from every SM at the same moment is bound by the chip's write path (~3 TB/s), not by
+    // the store instruction pattern.
+    const int q = warp & 3;  // TMEM lane quarter this warp may access (warp id % 4)
+    constexpr int CW = (Cfg::kEpiWarps == 8) ? BN / 2 : BN;   // columns per epilogue warp
+    const int c_begin = ((warp - 4) >> 2) * CW;
     const int row = q * 32 + lane;
     const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rn = row / (p.bw * p.bh);
     int as = 0;
@@ -174,9 +201,10 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (tr && warp == 4 && lane == 0 && item == (int)blockIdx.x) tr[5] = clock64();   // first accumulator complete
       constexpr int EC = (BN < 32) ? BN : 32;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_begin + CW; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
         tmem_ld_wait();
@@ -205,8 +233,10 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (tr && warp == 4 && lane == 0 && item == (int)blockIdx.x) tr[6] = clock64();   // first epilogue done
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (tr && warp == 4 && lane == 0) tr[7] = clock64();                                 // last epilogue done
   }
 
   tc_fence_before();
@@ -236,7 +266,7 @@ struct Fprop2Cfg {
 };
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
 conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
   using Cfg = Fprop2Cfg<BN>;
   constexpr int STAGES = Cfg::kStages;
@@ -270,7 +300,7 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);  // 4 epilogue warps in each CTA of the pair
+      mbar_init(tempty_bar(a), 16);  // 8 epilogue warps in each CTA of the pair
     }
     fence_barrier_init();
   }
@@ -340,7 +370,8 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs): own 128 rows of the pair's accumulator =====================
-    const int q = warp - 4;
+    const int q = warp & 3;
+    const int c_begin = ((warp - 4) >> 2) * (BN / 2);  // two warps per TMEM lane quarter, half the columns each
     const int row = q * 32 + lane;
     const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rn = row / (p.bw * p.bh);
     int as = 0;
@@ -357,7 +388,7 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
         tmem_ld_wait();
@@ -400,7 +431,7 @@ int launch_fprop2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropPar
     configured = true;
   }
   const int pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
-  conv_fprop_tc2_kernel<BN><<<2 * pairs, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  conv_fprop_tc2_kernel<BN><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc2_kernel");
   return GLB_OK;
 }
@@ -411,16 +442,16 @@ inline int next_pow2(int v) {
   return p;
 }
 
-template <int BN>
+template <int BN, int KC>
 int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
-  using Cfg = FpropCfg<BN>;
+  using Cfg = FpropCfg<BN, KC>;
   static bool configured = false;  // per-process, per-instantiation; attribute is sticky for the function
   if (!configured) {
-    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  conv_fprop_tc_kernel<BN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  conv_fprop_tc_kernel<BN, KC><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc_kernel");
   return GLB_OK;
 }
@@ -476,10 +507,15 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
     }
   }
   p.k_per = (k_iters + ksplit - 1) / ksplit;
+  if (ksplit > 1 && (p.k_per & 1)) ++p.k_per;   // whole 2-chunk stages per slice
   p.ksplit = (k_iters + p.k_per - 1) / p.k_per;
   p.tiles_co = Co / BN;
   p.num_tiles = m_tiles * p.tiles_co * p.ksplit;
   p.alpha = alpha; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+  p.dbg = 0;
+  p.trace = nullptr;
+  if (const char* e = getenv("GLB_FPROP_DBG")) p.dbg = atoi(e);
+  if (const char* e = getenv("GLB_FPROP_TRACE")) p.trace = (long long*)strtoull(e, nullptr, 0);
   const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
   if (p.ksplit > 1) GLB_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * p.Ho * p.Wo * Co, st));
 
@@ -506,12 +542,14 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   }
   if (use_pair) return BN == 256 ? launch_fprop2<256>(tmA, tmB, p, st) : launch_fprop2<128>(tmA, tmB, p, st);
   int rc = GLB_ERR_UNSUPPORTED;
+  // two K chunks per stage for the narrow tiles (see FpropCfg); needs whole stages per tap row and per split-K slice
+  const bool kc2 = BN <= 128 && (Ci / kChunk) % 2 == 0 && p.k_per % 2 == 0 && getenv("GLB_FPROP_KC1") == nullptr;
   switch (BN) {
-    case 256: rc = launch_fprop<256>(tmA, tmB, p, st); break;
-    case 128: rc = launch_fprop<128>(tmA, tmB, p, st); break;
-    case 64: rc = launch_fprop<64>(tmA, tmB, p, st); break;
-    case 32: rc = launch_fprop<32>(tmA, tmB, p, st); break;
-    case 16: rc = launch_fprop<16>(tmA, tmB, p, st); break;
+    case 256: rc = launch_fprop<256, 1>(tmA, tmB, p, st); break;
+    case 128: rc = kc2 ? launch_fprop<128, 2>(tmA, tmB, p, st) : launch_fprop<128, 1>(tmA, tmB, p, st); break;
+    case 64: rc = kc2 ? launch_fprop<64, 2>(tmA, tmB, p, st) : launch_fprop<64, 1>(tmA, tmB, p, st); break;
+    case 32: rc = kc2 ? launch_fprop<32, 2>(tmA, tmB, p, st) : launch_fprop<32, 1>(tmA, tmB, p, st); break;
+    case 16: rc = launch_fprop<16, 1>(tmA, tmB, p, st); break;
     default: set_error("tcgen05 fprop: no kernel for this N tile");
   }
   if (rc == GLB_OK && post_pass)
@@ -557,7 +595,7 @@ struct WgradParams {
   float* gw;
   int Co, Ci, RS, S, pad;
   int N, Ho, Wo;
-  int bw, bh, bn;  // K block = 32 pixels = bn x bh x bw box
+  int bw, bh, bn;  // K block = PIX pixels = bn x bh x bw box
   int tiles_w, tiles_h, tiles_n, num_pb;
   int splits, pb_per_split;
   int tiles_co, tiles_ci;
@@ -565,23 +603,25 @@ struct WgradParams {
   int atomic;
 };
 
-constexpr int kWgPix = 32;              // pixels per K block
-constexpr int kWgBlkBytes = kWgPix * 128;  // one (32 ch x 32 px) block = 4 KB
-
-template <int BN>
+// PIX = pixels (K) per pipeline stage: 32 (4 MMAs) for BN = 256, 64 (8 MMAs) for the narrower tiles, whose 64-cycle MMAs would
+// otherwise leave the issuing thread's per-stage wait / commit protocol as the pacing item (see FpropCfg).
+// The tensor maps are 5-D -- (32 ch, W, H, N, C/32) -- so ONE TMA instruction per operand and stage lands all its
+// [channel block][pixel][32 ch] blocks (12 separate 4 KB loads per stage held the main loop at ~35 % tensor-pipe activity).
+template <int BN, int PIX>
 struct WgradCfg {
-  static constexpr int kABytes = 4 * kWgBlkBytes;
-  static constexpr int kBBytes = (BN / 32) * kWgBlkBytes;
+  static constexpr int kBlkBytes = PIX * 128;           // one (32 ch x PIX px) block
+  static constexpr int kABytes = 4 * kBlkBytes;
+  static constexpr int kBBytes = (BN / 32) * kBlkBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = (192 * 1024 / kStageBytes) > 8 ? 8 : (192 * 1024 / kStageBytes);
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int PIX>
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, PIX>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -636,11 +676,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_cons
         const uint32_t a_dst = base + stage * Cfg::kStageBytes;
         const uint32_t b_dst = a_dst + Cfg::kABytes;
         mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) tma_load_4d(a_dst + m * kWgBlkBytes, &tmGy, full_bar(stage), co0 + 32 * m, w0, h0, n0);
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j)
-          tma_load_4d(b_dst + j * kWgBlkBytes, &tmX, full_bar(stage), ci0 + 32 * j, w0 + s - p.pad, h0 + r - p.pad, n0);
+        tma_load_5d(a_dst, &tmGy, full_bar(stage), 0, w0, h0, n0, co0 / 32);
+        tma_load_5d(b_dst, &tmX, full_bar(stage), 0, w0 + s - p.pad, h0 + r - p.pad, n0, ci0 / 32);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -655,9 +692,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_cons
         const uint32_t a_addr = base + stage * Cfg::kStageBytes;
         const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
-        for (int kg = 0; kg < kWgPix / 8; ++kg) {  // K = 8 pixels per MMA = one 1 KB swizzle atom per channel block
-          const uint64_t ad = make_smem_desc(a_addr + kg * 1024, kWgBlkBytes, 512, kLayoutSw128Base32);
-          const uint64_t bd = make_smem_desc(b_addr + kg * 1024, kWgBlkBytes, 512, kLayoutSw128Base32);
+        for (int kg = 0; kg < PIX / 8; ++kg) {  // K = 8 pixels per MMA = two 512 B swizzle atoms per channel block
+          const uint64_t ad = make_smem_desc(a_addr + kg * 1024, Cfg::kBlkBytes, 512, kLayoutSw128Base32);
+          const uint64_t bd = make_smem_desc(b_addr + kg * 1024, Cfg::kBlkBytes, 512, kLayoutSw128Base32);
           mma_tf32(tmem_base, ad, bd, idesc, (pb > pb_begin || kg > 0) ? 1u : 0u);
         }
         mma_commit(empty_bar(stage));
@@ -697,15 +734,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_cons
   }
 }
 
-template <int BN>
+template <int BN, int PIX>
 int launch_wgrad(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, PIX>;
   static bool configured = false;
   if (!configured) {
-    GLB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GLB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  conv_wgrad_tc_kernel<BN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmGy, tmX, p);
+  conv_wgrad_tc_kernel<BN, PIX><<<grid, 256, Cfg::kSmemBytes, st>>>(tmGy, tmX, p);
   GLB_CHECK_LAUNCH("conv_wgrad_tc_kernel");
   return GLB_OK;
 }
@@ -732,21 +769,22 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   WgradParams p;
   p.gw = gw; p.Co = Co; p.Ci = Ci; p.RS = R * S; p.S = S; p.pad = pad;
   p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1;
-  p.bw = next_pow2(p.Wo) < kWgPix ? next_pow2(p.Wo) : kWgPix;
-  p.bh = next_pow2(p.Ho) < kWgPix / p.bw ? next_pow2(p.Ho) : kWgPix / p.bw;
-  p.bn = kWgPix / (p.bw * p.bh);
+  const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
+  const int PIX = BN >= 256 ? 32 : 64;
+  p.bw = next_pow2(p.Wo) < PIX ? next_pow2(p.Wo) : PIX;
+  p.bh = next_pow2(p.Ho) < PIX / p.bw ? next_pow2(p.Ho) : PIX / p.bw;
+  p.bn = PIX / (p.bw * p.bh);
   p.tiles_w = (p.Wo + p.bw - 1) / p.bw;
   p.tiles_h = (p.Ho + p.bh - 1) / p.bh;
   p.tiles_n = (N + p.bn - 1) / p.bn;
   p.num_pb = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
   p.tiles_co = (Co + 127) / 128;
   p.tiles_ci = Ci / BN;
   const int tiles = p.tiles_co * p.tiles_ci * p.RS;
   // one wave: every CTA pays the 128 x BN red.add epilogue once, so fewer, longer work items win (ncu: with ~2.4 waves
   // of short items the atomics epilogue cost more than the MMA main loop)
   int splits = kNumSMs / tiles;
-  if (splits > p.num_pb / 4) splits = p.num_pb / 4;         // >= 4 pixel blocks (128 pixels of K) per work item
+  if (splits > p.num_pb / 4) splits = p.num_pb / 4;         // >= 4 pixel blocks of K per work item
   if (splits > p.num_pb) splits = p.num_pb;
   if (const char* e = getenv("GLB_WGRAD_SPLITS")) splits = atoi(e);  // tuning experiments only
   if (splits < 1) splits = 1;
@@ -757,25 +795,26 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   if (p.atomic) GLB_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Co * R * S * Ci, st));
 
   CUtensorMap tmGy, tmX;
-  const uint32_t box[4] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-  {
-    const uint64_t dims[4] = {(uint64_t)Co, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N};
-    const uint64_t strides[3] = {(uint64_t)Co * 4, (uint64_t)p.Wo * Co * 4, (uint64_t)p.Ho * p.Wo * Co * 4};
-    int rc = make_tmap_f32(&tmGy, gy, 4, dims, strides, box, "wgrad gy", true);
+  {  // (32 ch, Wo, Ho, N, Co/32): box = PIX pixels x 4 channel blocks (blocks beyond Co/32 are zero-filled: M padded to 128)
+    const uint64_t dims[5] = {32u, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N, (uint64_t)(Co / 32)};
+    const uint64_t strides[4] = {(uint64_t)Co * 4, (uint64_t)p.Wo * Co * 4, (uint64_t)p.Ho * p.Wo * Co * 4, 128u};
+    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 4u};
+    int rc = make_tmap_f32(&tmGy, gy, 5, dims, strides, box, "wgrad gy", true);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint64_t strides[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
-    int rc = make_tmap_f32(&tmX, x, 4, dims, strides, box, "wgrad x", true);
+    const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / 32)};
+    const uint64_t strides[4] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4, 128u};
+    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BN / 32)};
+    int rc = make_tmap_f32(&tmX, x, 5, dims, strides, box, "wgrad x", true);
     if (rc) return rc;
   }
   const int grid = tiles * p.splits;
   switch (BN) {
-    case 256: return launch_wgrad<256>(tmGy, tmX, p, grid, st);
-    case 128: return launch_wgrad<128>(tmGy, tmX, p, grid, st);
-    case 64: return launch_wgrad<64>(tmGy, tmX, p, grid, st);
-    case 32: return launch_wgrad<32>(tmGy, tmX, p, grid, st);
+    case 256: return launch_wgrad<256, 32>(tmGy, tmX, p, grid, st);
+    case 128: return launch_wgrad<128, 64>(tmGy, tmX, p, grid, st);
+    case 64: return launch_wgrad<64, 64>(tmGy, tmX, p, grid, st);
+    case 32: return launch_wgrad<32, 64>(tmGy, tmX, p, grid, st);
   }
   return GLB_ERR_UNSUPPORTED;
 }
