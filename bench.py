@@ -312,7 +312,7 @@ def run_ours(args):
 
     log("e2e done")
     # ---- roofline of the dominant kernel family (dense convs), timed live with CUDA events on the launch stream ----
-    roof = conv_roofline(L, pool_dev[0], main_iter_eager, flush) if rank == 0 else None
+    roof, glue = kernel_rooflines(L, pool_dev[0], main_iter_eager, flush) if rank == 0 else (None, None)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -339,6 +339,11 @@ def run_ours(args):
                                    "step); operands are TF32, whose dense peak is half of bf16 -> frac_of_tf32_peak")
             roof["frac_of_tf32_peak"] = roof["achieved"] / (peaks["tf"] / 2)
             line["roofline"] = roof
+        if glue is not None and glue["achieved"] is not None:
+            glue["peak"] = peaks["hbm_gbs"]
+            glue["frac"] = glue["achieved"] / peaks["hbm_gbs"]
+            glue["peak_source"] = peaks["src"] + " HBM copy bandwidth (read+write)"
+            line["roofline_glue"] = glue
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -356,40 +361,71 @@ def run_ours(args):
         os._exit(0)
 
 
-def conv_roofline(L, x, main_iter, flush):
-    """Dominant kernel family = the dense convolutions (fprop / dgrad / wgrad implicit GEMMs).  Every conv launch of one
-    main iteration is recorded (arguments kept alive), then the whole list is re-issued back to back -- GPU bound, in
-    step order, L2 flushed before each repetition -- between one pair of CUDA events per kind.
-    achieved = algorithmic FLOPs of those launches / their device time."""
+GLUE_LAUNCHERS = ("bias_act_fwd", "act_bwd", "axpby", "colsum", "scale_by", "pixelnorm_fwd", "pixelnorm_bwd", "blur3x3",
+                  "upsample2x_fwd", "upsample2x_bwd", "pool_bias_act_fwd", "pool_bias_act_bwd", "style_epilogue_fwd",
+                  "style_epilogue_bwd", "rgb_expand", "rgb_contract", "rgb_wgrad", "fade_up_blend", "fade_up_blend_bwd",
+                  "fade_real", "interp_rows", "batchnorm_fwd", "batchnorm_bwd", "layernorm_fwd", "layernorm_bwd",
+                  "layernorm_bwdbwd", "tanh_fwd", "tanh_bwd", "adam_ewma_multi")
+
+
+def kernel_rooflines(L, x, main_iter, flush):
+    """Both rooflines of BASELINE.json's metric from ONE recorded eager main iteration.
+
+    Every launcher call of the iteration is recorded (arguments kept alive); then, per launcher kind, the recorded
+    calls are re-issued back to back -- GPU bound, in step order, L2 flushed (160 MB write) before each repetition --
+    between one pair of CUDA events on the launch stream.
+      * dense convs (fprop / dgrad / wgrad implicit GEMMs): achieved = algorithmic FLOPs / device time  -> tensor roofline
+      * glue launchers: achieved = compulsory bytes (every tensor argument read once + every output written once,
+        4 B/element; Adam: 28 B/param + 8 B/param for the fused EWMA) / device time                   -> HBM roofline
+    """
     import torch
     from gan_lab_b200 import _kernels as K
     calls = []
     orig = {}
 
-    def wrap(name, flops_fn):
-        f = getattr(K, name)
+    def tensors(obj):
+        if torch.is_tensor(obj):
+            yield obj
+        elif isinstance(obj, (list, tuple)):
+            for o in obj:
+                yield from tensors(o)
+
+    def nbytes(a, k, out):
+        return 4.0 * sum(t.numel() for t in tensors(list(a) + list(k.values()) + [out]))
+
+    def wrap(name, work_fn):
+        f = getattr(K, name, None)
+        if f is None:
+            return
         orig[name] = f
 
         def g(*a, **k):
             out = f(*a, **k)
-            calls.append((name, f, a, k, flops_fn(a, out)))
+            calls.append((name, f, a, k, work_fn(a, k, out)))
             return out
 
         setattr(K, name, g)
 
-    def f_fprop(a, out):
+    def f_fprop(a, k, out):
         w_ = a[1]
         return 2.0 * out.shape[0] * out.shape[2] * out.shape[3] * w_.shape[0] * w_.shape[1] * w_.shape[2] * w_.shape[3]
 
-    def f_dgrad(a, out):
+    def f_dgrad(a, k, out):
         gy_, w_ = a[0], a[1]
         return 2.0 * gy_.shape[0] * gy_.shape[2] * gy_.shape[3] * w_.shape[0] * w_.shape[1] * w_.shape[2] * w_.shape[3]
 
-    def f_wgrad(a, out):
+    def f_wgrad(a, k, out):
         gy_ = a[1]
         return 2.0 * gy_.shape[0] * gy_.shape[2] * gy_.shape[3] * out.numel()
 
+    def f_adam(a, k, out):
+        sizes, ewma_mode = a[1], a[-1]
+        return float(sizes.sum().item()) * (28.0 + (8.0 if ewma_mode else 0.0))
+
+    conv_kinds = ("conv_fprop", "conv_dgrad", "conv_wgrad")
     wrap("conv_fprop", f_fprop); wrap("conv_dgrad", f_dgrad); wrap("conv_wgrad", f_wgrad)
+    for name in GLUE_LAUNCHERS:
+        wrap(name, f_adam if name == "adam_ewma_multi" else nbytes)
     dp, L.dp = L.dp, None          # rank-local pass: no collective may run here (the other ranks are not in it)
     try:
         main_iter(x)
@@ -398,32 +434,58 @@ def conv_roofline(L, x, main_iter, flush):
         L.dp = dp
         for n, f in orig.items():
             setattr(K, n, f)
-    by = {}
-    reps = 3
-    for kind in ("conv_fprop", "conv_dgrad", "conv_wgrad"):
-        sel = [c for c in calls if c[0] == kind]
-        if not sel:
-            continue
+
+    def timed(sel, reps=3):
         times = []
         for _ in range(reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             with torch.no_grad():
-                for _, f, a, k, _fl in sel:
+                for _, f, a, k, _w in sel:
                     f(*a, **k)
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         times.sort()
-        by[kind] = (sum(c[4] for c in sel), times[len(times) // 2], len(sel))
+        return times[len(times) // 2]
+
+    by = {}
+    for kind in conv_kinds:
+        sel = [c for c in calls if c[0] == kind]
+        if sel:
+            by[kind] = (sum(c[4] for c in sel), timed(sel), len(sel))
     tot_f = sum(v[0] for v in by.values())
     tot_ms = sum(v[1] for v in by.values())
     n_launch = sum(v[2] for v in by.values())
-    return {"bound": "tensor", "kernel": "conv2d fprop/dgrad/wgrad family (tcgen05 TF32 implicit GEMM; FFMA for uncovered shapes)",
+    conv = {"bound": "tensor", "kernel": "conv2d fprop/dgrad/wgrad family (tcgen05 TF32 implicit GEMM; FFMA for uncovered shapes)",
             "achieved": tot_f / (tot_ms / 1e3) / 1e12, "unit": "TFLOP/s", "traffic": None, "launches": n_launch,
             "avg_launch_us": 1e3 * tot_ms / max(n_launch, 1), "conv_ms_per_step": tot_ms,
             "by_kind_tflops": {n: v[0] / (v[1] / 1e3) / 1e12 for n, v in by.items()}}
+
+    # glue: launches that move >= 4 MB are HBM-bound and make up the roofline figure; the small ones (latents, 4x4 / 8x8
+    # maps, scalars) are launch-latency bound and reported separately as time only
+    BIG = 4 << 20
+    gby, small_ms, small_n = {}, 0.0, 0
+    for kind in GLUE_LAUNCHERS:
+        sel = [c for c in calls if c[0] == kind]
+        if not sel:
+            continue
+        big = [c for c in sel if c[4] >= BIG]
+        sm = [c for c in sel if c[4] < BIG]
+        if big:
+            gby[kind] = (sum(c[4] for c in big), timed(big), len(big))
+        if sm:
+            small_ms += timed(sm, reps=1); small_n += len(sm)
+    gb = sum(v[0] for v in gby.values())
+    gms = sum(v[1] for v in gby.values())
+    glue = {"bound": "hbm", "kernel": "fused glue launchers moving >= 4 MB (bias/act, blur, up/downsample, style epilogue, RGB, Adam+EWMA)",
+            "achieved": gb / (gms / 1e3) / 1e9 if gms else None, "unit": "GB/s", "traffic": None,
+            "launches": sum(v[2] for v in gby.values()), "glue_ms_per_step": gms, "algorithmic_mb_per_step": gb / 1e6,
+            "small_launches": small_n, "small_launches_ms_per_step": small_ms,
+            "by_kind_gbs": {n: round(v[0] / (v[1] / 1e3) / 1e9, 1) for n, v in gby.items()},
+            "by_kind_ms": {n: round(v[1], 4) for n, v in gby.items()}}
+    return conv, glue
 
 
 def cpu_baseline(args):

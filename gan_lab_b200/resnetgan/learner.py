@@ -134,9 +134,14 @@ class GANLearner(object):
         else:
             raise ValueError(gp)
         xb.requires_grad_(True)
-        outb = self.disc_model(xb)
+        return self.gp_from_forward(self.disc_model(xb), xb)
+
+    def gp_from_forward(self, outb, xb):
+        """Penalty from an existing discriminator forward `outb = D(xb)` (xb requires grad): reference :811-825."""
+        gp = self.gradient_penalty
+        dev = self.config.dev
         with ops.input_grads_only():
-            outb_grads = torch.autograd.grad(outb, xb, grad_outputs=torch.ones(self.batch_size, device=dev),
+            outb_grads = torch.autograd.grad(outb, xb, grad_outputs=torch.ones(outb.shape[0], device=dev),
                                              create_graph=True, retain_graph=True, only_inputs=True)[0]
         n_hw = outb_grads.shape[0] * outb_grads.shape[2] * outb_grads.shape[3]
         if gp == 'wgan-gp':

@@ -265,3 +265,35 @@ def case_learner_train(golden, dev, fname, model):
     assert abs(L.beta - g["beta"]) < 1e-12
     if model == "StyleGAN":
         close(L.gen_model.w_ewma, g["w_ewma"], rtol=1e-3, atol=1e-5)
+
+
+def case_shared_penalty_forward(dev, gp):
+    """disc_step with the R1/R2 penalty riding on the loss's own D forward == the reference's literal order (a separate
+    D forward inside calc_gp), on identical draws; lda inflated so the penalty's gradient is visible in the total."""
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    from gan_lab_b200.optim import FusedAdam
+    grads = {}
+    for share in (False, True):
+        torch.manual_seed(5)
+        cfg = default_config("StyleGAN", res=16, batch_size=4, dev=dev, len_latent=32, len_dlatent=32,
+                             cutoff_trunc_trick=2, lda=1.e4, gradient_penalty=gp, pct_mixing_reg=0., use_ewma_gen=False)
+        L = StyleGANLearner(cfg)
+        gen = torch.Generator().manual_seed(6)
+        with torch.no_grad():
+            for m in (L.gen_model, L.disc_model):
+                for prm in m.parameters():
+                    if float(prm.abs().max()) == 0.0:
+                        prm.copy_((torch.randn(prm.shape, generator=gen) * 0.3).to(dev))
+        L.gen_model.train(); L.disc_model.train()
+        L.share_penalty_forward = share
+        L.opt_disc.step = lambda: None                  # keep the gradients: compare them, not the Adam result
+        x = (torch.rand(4, 3, 16, 16, generator=gen) * 2 - 1).to(dev)
+        torch.manual_seed(7)
+        loss = L.disc_step(x)
+        grads[share] = (float(loss), {n: prm.grad.detach().clone() for n, prm in L.disc_model.named_parameters()
+                                      if prm.grad is not None})
+    (l0, g0), (l1, g1) = grads[False], grads[True]
+    assert abs(l0 - l1) <= 1e-5 * max(1.0, abs(l0)), (l0, l1)
+    assert set(g0) == set(g1) and len(g0) > 10
+    for n in g0:
+        assert relerr(g1[n], g0[n]) < 2e-4, (n, relerr(g1[n], g0[n]))

@@ -315,6 +315,12 @@ def test_cuda_graph_replay_of_train_steps():
         assert torch.isfinite(p).all()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("gp", ["r1", "r2"])
+def test_shared_penalty_forward(gp):
+    PC.case_shared_penalty_forward(DEV, gp)
+
+
 def test_library_was_loaded():
     from gan_lab_b200._lib import LIB
     assert LIB._dll is not None and K.launch_count() > 0

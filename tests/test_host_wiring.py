@@ -62,3 +62,8 @@ def test_pro_nets_modules(golden, fname):
 @pytest.mark.parametrize("fname,model", PC.TRAIN_CASES)
 def test_learner_train(golden, fname, model):
     PC.case_learner_train(golden, DEV, fname, model)
+
+
+@pytest.mark.parametrize("gp", ["r1", "r2"])
+def test_shared_penalty_forward(gp):
+    PC.case_shared_penalty_forward(DEV, gp)
