@@ -386,6 +386,112 @@ def style_epilogue_bwd(gout, x, noise, noise_weight, bias, style, stats, slope):
     return gx, gstyle, g_nw, g_b
 
 
+# --------------------------------------------------------------------------- ResNet-GAN norms (csrc/norm.cu)
+def _hwc(t):
+    """(C,H,W)-shaped affine map -> its (H,W,C)-ordered memory (zero-copy when the parameter is stored that way)."""
+    return None if t is None else t.detach().permute(1, 2, 0).contiguous()
+
+
+def _new_chw_as_hwc(C, H, W, like):
+    return torch.empty((H, W, C), device=like.device, dtype=torch.float32).permute(2, 0, 1)
+
+
+def _ws(n_doubles, like):
+    return torch.empty(int(n_doubles), device=like.device, dtype=torch.float64)
+
+
+def layernorm_fwd(x, gamma, beta, eps, act, slope):
+    """x [N,C,H,W] (NHWC memory), gamma/beta [C,H,W] -> (y, stats[N,2] = mean, rstd)."""
+    _chk(x, gamma, beta)
+    x = nhwc(x)
+    N, C, H, W = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((N, 2), device=x.device, dtype=torch.float32)
+    ws = _ws(LIB.fn("glb_layernorm_ws_doubles")(N), x)
+    g_hwc, b_hwc = _hwc(gamma), _hwc(beta)          # keep the (possibly copied) maps alive across the launch
+    _call("glb_layernorm_fwd", _p(x), _p(g_hwc), _p(b_hwc), _p(y), _p(stats), _p(ws), N, C * H * W, float(eps),
+          int(act), float(slope), _stream())
+    return y, stats
+
+
+def layernorm_bwd(gy, y, x, gamma, stats, act, slope, want_gx=True, want_params=True):
+    """-> (gx, ggamma [C,H,W], gbeta [C,H,W]); entries not asked for are None."""
+    _chk(gy, y, x, gamma, stats)
+    gy, y, x = nhwc(gy), nhwc(y), nhwc(x)
+    N, C, H, W = x.shape
+    gx = torch.empty_like(x) if want_gx else None
+    gg = _new_chw_as_hwc(C, H, W, x) if want_params else None
+    gb = _new_chw_as_hwc(C, H, W, x) if want_params else None
+    ws = _ws(LIB.fn("glb_layernorm_ws_doubles")(N), x)
+    g_hwc = _hwc(gamma)
+    _call("glb_layernorm_bwd", _p(gy), _p(y), _p(x), _p(g_hwc), _p(stats), _p(gx), _p(gg), _p(gb), _p(ws), N, C * H * W,
+          int(act), float(slope), _stream())
+    return gx, gg, gb
+
+
+def layernorm_bwdbwd(u, gy, y, x, gamma, stats, act, slope, want_gy=True, want_x=True, want_gamma=True):
+    """Second order: cotangent u of gx -> (g_gy, g_x, g_gamma [C,H,W])."""
+    _chk(u, gy, y, x, gamma, stats)
+    u, gy, y, x = nhwc(u), nhwc(gy), nhwc(y), nhwc(x)
+    N, C, H, W = x.shape
+    g_gy = torch.empty_like(x) if want_gy else None
+    g_x = torch.empty_like(x) if want_x else None
+    g_gamma = _new_chw_as_hwc(C, H, W, x) if want_gamma else None
+    ws = _ws(LIB.fn("glb_layernorm_ws_doubles")(N), x)
+    g_hwc = _hwc(gamma)
+    _call("glb_layernorm_bwdbwd", _p(u), _p(gy), _p(y), _p(x), _p(g_hwc), _p(stats), _p(g_gy), _p(g_x), _p(g_gamma), _p(ws),
+          N, C * H * W, int(act), float(slope), _stream())
+    return g_gy, g_x, g_gamma
+
+
+def batchnorm_fwd(x, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, slope):
+    """Training-mode BatchNorm2d (+act) on x [N,C,H,W]; updates the running buffers in place -> (y, stats[2,C])."""
+    _chk(x, gamma, beta, running_mean, running_var)
+    x, P, C = _rows(x)
+    y = torch.empty_like(x)
+    stats = torch.empty((2, C), device=x.device, dtype=torch.float32)
+    ws = _ws(LIB.fn("glb_batchnorm_ws_doubles")(C), x)
+    if num_batches_tracked is not None and num_batches_tracked.dtype != torch.int64:
+        raise GlbError("num_batches_tracked must be int64")
+    _call("glb_batchnorm_fwd", _p(x), _p(_flat(gamma)), _p(_flat(beta)), _p(y), _p(stats), _p(running_mean), _p(running_var),
+          _p(num_batches_tracked), _p(ws), P, C, float(eps), float(momentum), int(act), float(slope), _stream())
+    return y, stats
+
+
+def batchnorm_bwd(gy, y, x, gamma, stats, act, slope):
+    """-> (gx, ggamma [C], gbeta [C])."""
+    _chk(gy, y, x, gamma, stats)
+    x, P, C = _rows(x)
+    gy, _, _ = _rows(gy)
+    y, _, _ = _rows(y)
+    gx = torch.empty_like(x)
+    gg = torch.empty(C, device=x.device, dtype=torch.float32)
+    gb = torch.empty(C, device=x.device, dtype=torch.float32)
+    ws = _ws(LIB.fn("glb_batchnorm_ws_doubles")(C), x)
+    _call("glb_batchnorm_bwd", _p(gy), _p(y), _p(x), _p(_flat(gamma)), _p(stats), _p(gx), _p(gg), _p(gb), _p(ws), P, C, int(act),
+          float(slope), _stream())
+    return gx, gg, gb
+
+
+def tanh_fwd(x):
+    _chk(x)
+    x = x if x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)) else x.contiguous()
+    y = torch.empty_like(x)
+    _call("glb_tanh_fwd", _p(x), _p(y), x.numel(), _stream())
+    return y
+
+
+def tanh_bwd(gy, y):
+    _chk(gy, y)
+    if gy.stride() != y.stride():
+        gy = gy.contiguous(memory_format=torch.channels_last) if (y.dim() == 4 and not y.is_contiguous()) else gy.contiguous()
+        if gy.stride() != y.stride():
+            y = y.contiguous(); gy = gy.contiguous()
+    gx = torch.empty_like(y)
+    _call("glb_tanh_bwd", _p(gy), _p(y), _p(gx), y.numel(), _stream())
+    return gx
+
+
 # --------------------------------------------------------------------------- minibatch stddev
 def mbstd_fwd(x, group):
     _chk(x)

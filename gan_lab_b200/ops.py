@@ -405,6 +405,103 @@ def instance_norm(x, eps=1e-8):
     return _StyleEpilogue.apply(x, None, None, None, style, 1.0, float(eps))
 
 
+# ----------------------------------------------------------------------------------------- ResNet-GAN norms
+class _LayerNormAct(Function):
+    """y = act(LayerNorm([C,H,W], elementwise affine)(x)): discriminator ResBlocks, resnetgan/resblocks.py:43-46 through
+    NormalizeLayer (utils/custom_layers.py:103-106) + the shared ReLU.  Twice differentiable (WGAN-GP)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, act, slope):
+        y, stats = K.layernorm_fwd(x, gamma, beta, eps, act, slope)
+        ctx.cfg = (act, slope)
+        ctx.save_for_backward(x, gamma, y, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, y, stats = ctx.saved_tensors
+        act, slope = ctx.cfg
+        want_p = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and _param_grads_wanted()
+        gx, gg, gb = _LayerNormActBwd.apply(gy, y, x, gamma, stats, act, slope, ctx.needs_input_grad[0], want_p)
+        return gx, gg, gb, None, None, None
+
+
+class _LayerNormActBwd(Function):
+    """(gy, x, gamma) -> (gx, ggamma, gbeta); y only provides the activation mask, stats are constants of x's forward
+    that the second-order kernel differentiates through analytically (csrc/norm.cu)."""
+
+    @staticmethod
+    def forward(ctx, gy, y, x, gamma, stats, act, slope, want_gx, want_params):
+        ctx.cfg = (act, slope)
+        ctx.save_for_backward(gy, y, x, gamma, stats)
+        ctx.set_materialize_grads(False)
+        gx, gg, gb = K.layernorm_bwd(gy, y, x, gamma, stats, act, slope, want_gx, want_params)
+        return gx, gg, gb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u, u_gamma, u_beta):
+        if u_gamma is not None or u_beta is not None:
+            raise NotImplementedError("differentiating LayerNorm's parameter gradients is not on any gan-lab path")
+        if u is None:
+            return (None,) * 9
+        gy, y, x, gamma, stats = ctx.saved_tensors
+        act, slope = ctx.cfg
+        g_gy, g_x, g_gamma = K.layernorm_bwdbwd(u, gy, y, x, gamma, stats, act, slope, ctx.needs_input_grad[0],
+                                                ctx.needs_input_grad[2], ctx.needs_input_grad[3] and _param_grads_wanted())
+        return g_gy, None, g_x, g_gamma, None, None, None, None, None
+
+
+def layernorm_act(x, gamma, beta, eps=1e-5, act=ACT_NONE, slope=0.0):
+    return _LayerNormAct.apply(x, gamma, beta, float(eps), int(act), float(slope))
+
+
+class _BatchNormAct(Function):
+    """y = act(BatchNorm2d(x)) with batch statistics + running-buffer update: generator ResBlocks (resblocks.py:43-46 through
+    utils/custom_layers.py:100-102).  Generator side only -> first order."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, eps, momentum, act, slope):
+        y, stats = K.batchnorm_fwd(x, gamma, beta, running_mean, running_var, nbt, eps, momentum, act, slope)
+        ctx.cfg = (act, slope)
+        ctx.save_for_backward(x, gamma, y, stats)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, gamma, y, stats = ctx.saved_tensors
+        act, slope = ctx.cfg
+        gx, gg, gb = K.batchnorm_bwd(gy, y, x, gamma, stats, act, slope)
+        return gx, gg, gb, None, None, None, None, None, None, None
+
+
+def batchnorm_act(x, gamma, beta, running_mean, running_var, num_batches_tracked, eps=1e-5, momentum=0.1, act=ACT_NONE,
+                  slope=0.0):
+    return _BatchNormAct.apply(x, gamma, beta, running_mean, running_var, num_batches_tracked, float(eps), float(momentum),
+                               int(act), float(slope))
+
+
+class _Tanh(Function):
+    """nn.Tanh on the ResNet generator's output (resnetgan/architectures.py:58, 96); first order."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = K.tanh_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return K.tanh_bwd(gy, y)
+
+
+def tanh(x):
+    return _Tanh.apply(x)
+
+
 # ----------------------------------------------------------------------------------------- minibatch stddev
 def mbstd_group(n: int, group_size: int) -> int:
     """Group-size rule of concat_mbstd_layer (utils/custom_layers.py:121-126)."""

@@ -3,8 +3,10 @@
 Keeps the reference's constructor `(config: argparse.Namespace)`, its public attributes (`gen_model`,
 `disc_model`, `opt_gen`, `opt_disc`, `batch_size`, `config`, `loss`, `gradient_penalty`, `optimizer`,
 `lr_sched`) and `calc_gp`; metrics, plotting and checkpoint I/O are outside
-the hot path and not built.  The ResNet-GAN architectures themselves (BatchNorm / LayerNorm blocks) are a
-later row of the scope table; this class is the shared machinery the ProGAN / StyleGAN learners build on.
+the hot path and not built.  With `config.model == 'ResNet GAN'` this class builds the 32 / 64-pixel ResNet generator and
+discriminator (reference :183-232) and `train()` runs the reference's loop (:463-776: generator step(s) FIRST, then
+`num_disc_iters` discriminator steps per main iteration); it is also the shared machinery the ProGAN / StyleGAN
+learners build on.
 """
 import argparse
 import copy
@@ -14,7 +16,7 @@ import torch
 from .. import ops
 from ..optim import FusedAdam
 from ..utils.custom_layers import Upsample2x, AvgPool2x, NearestPool2d, BilinearPool2d, LeakyReLU, ReLU
-from ..utils.latent_utils import RANDOM
+from ..utils.latent_utils import RANDOM, gen_rand_latent_vars
 
 FMAP_SAMPLES = 3
 
@@ -95,6 +97,27 @@ class GANLearner(object):
 
         self.gen_model = None
         self.disc_model = None
+        self.dp = None
+        self.share_penalty_forward = True
+        if self._model == 'ResNet GAN':
+            from .architectures import (Generator32PixResnet, Generator64PixResnet, Discriminator32PixResnet,
+                                        Discriminator64PixResnet, FMAP_G, FMAP_D)
+            c = self.config
+            if c.res_samples == 64:
+                _gen_model, _disc_model, _fmap_g, _fmap_d = Generator64PixResnet, Discriminator64PixResnet, FMAP_G, FMAP_D
+            elif c.res_samples == 32:
+                _gen_model, _disc_model, _fmap_g, _fmap_d = Generator32PixResnet, Discriminator32PixResnet, FMAP_G * 2, FMAP_D * 2
+            else:
+                raise ValueError('GANLearner currently only supports 32 pixel and 64 pixel GAN architectures.\n'
+                                 'If a different generated sample resolution is desired, please use the\n'
+                                 'ProGAN or StyleGAN models featured in this package instead.')
+            self.gen_model = _gen_model(len_latent=c.len_latent, fmap=_fmap_g, upsampler=self.gen_model_upsampler,
+                                        blur_type=c.blur_type, nl=self.nl, num_classes=0, equalized_lr=c.use_equalized_lr)
+            self.disc_model = _disc_model(fmap=_fmap_d, pooler=self.disc_model_downsampler, blur_type=c.blur_type, nl=self.nl,
+                                          num_classes=0, equalized_lr=c.use_equalized_lr)
+            self.gen_model.to(c.dev)
+            self.disc_model.to(c.dev)
+            assert self.gen_model.res == self.disc_model.res
         self._loss = config.loss.casefold()
         self._gradient_penalty = config.gradient_penalty
         self._optimizer = config.optimizer.casefold()
@@ -112,6 +135,120 @@ class GANLearner(object):
         self.curr_img_num = 0
         self.tot_num_epochs = None
         self.not_trained_yet = True
+        if self._model == 'ResNet GAN':
+            self._set_loss()
+            self._set_optimizer()
+
+    # ------------------------------------------------------------------ one step each (reference :544-592, 626-692)
+    def gen_step(self):
+        """One generator step; the discriminator's parameters must already be frozen.  Returns the loss tensor."""
+        c = self.config
+        self.gen_model.zero_grad()
+        zb = gen_rand_latent_vars(num_samples=self.batch_size * c.gen_bs_mult, length=c.len_latent,
+                                  distribution=c.latent_distribution, device=c.dev)
+        zb.requires_grad_(True)
+        loss_train_gen = ops.g_logit_loss(self.disc_model(self.gen_model(zb)), self.loss)
+        loss_train_gen.backward()
+        if self.dp is not None:
+            self.dp.allreduce_grads(self.gen_model)
+        self.opt_gen.step()
+        return loss_train_gen.detach()
+
+    def disc_step(self, xb):
+        """One discriminator step on the real batch `xb`.  Returns the loss tensor."""
+        c = self.config
+        self.disc_model.zero_grad()
+        zb = gen_rand_latent_vars(num_samples=self.batch_size, length=c.len_latent, distribution=c.latent_distribution,
+                                  device=c.dev)
+        # the reference builds (and drops) the generator's graph here (:640-641); its BatchNorm running statistics are
+        # updated by this forward too, which no_grad keeps
+        with torch.no_grad():
+            _xgenb = self.gen_model(zb).detach()
+        xb = xb.to(c.dev, non_blocking=True)
+        gp = self.gradient_penalty
+        share = self.share_penalty_forward and gp in ('r1', 'r2')
+        if share and gp == 'r1':
+            xb = xb.detach().requires_grad_(True)
+        elif share:
+            _xgenb = _xgenb.detach().requires_grad_(True)
+        discriminative_gen = self.disc_model(_xgenb)
+        discriminative_real = self.disc_model(xb)
+        loss_train_disc = ops.d_logit_loss(discriminative_gen, discriminative_real, self.loss, 0.)
+        if share:
+            loss_train_disc = loss_train_disc + (self.gp_from_forward(discriminative_real, xb) if gp == 'r1' else
+                                                 self.gp_from_forward(discriminative_gen, _xgenb))
+            torch.autograd.backward(loss_train_disc, inputs=[p for p in self.disc_model.parameters() if p.requires_grad])
+        else:
+            if gp is not None:
+                loss_train_disc = loss_train_disc + self.calc_gp(_xgenb, xb)
+            loss_train_disc.backward()
+        if self.dp is not None:
+            self.dp.allreduce_grads(self.disc_model)
+        self.opt_disc.step()
+        return loss_train_disc.detach()
+
+    def _set_scheduler(self):
+        """reference resnetgan/learner.py:849-864."""
+        if self._lr_sched == 'linear decay':
+            self.scheduler_fn = lambda main_iter: 1. - (main_iter + self.sched_stop_step) * (1. / self.num_main_iters)
+        elif self._lr_sched == 'custom':
+            self.scheduler_fn = eval(self.config.lr_sched_custom)
+        else:
+            raise ValueError("Currently supported LR Schedulers are: [ 'linear decay', 'custom' ]")
+        self.scheduler_gen = torch.optim.lr_scheduler.LambdaLR(self.opt_gen, self.scheduler_fn, last_epoch=-1)
+        self.scheduler_disc = torch.optim.lr_scheduler.LambdaLR(self.opt_disc, self.scheduler_fn, last_epoch=-1)
+
+    def train(self, train_dl, valid_dl=None, z_valid_dl=None, num_main_iters=None, num_gen_iters=None,
+              num_disc_iters=None, log_every=0, step_callback=None):
+        """reference resnetgan/learner.py:463-776 (signature kept; valid_dl / z_valid_dl accepted and ignored: metrics are
+        outside the hot path).  Per main iteration: `num_gen_iters` generator steps, then `num_disc_iters` discriminator
+        steps, LR schedulers stepped once."""
+        c = self.config
+        num_main_iters = c.num_main_iters if num_main_iters is None else num_main_iters
+        num_gen_iters = c.num_gen_iters if num_gen_iters is None else num_gen_iters
+        num_disc_iters = c.num_disc_iters if num_disc_iters is None else num_disc_iters
+        self.num_main_iters = num_main_iters
+        self.dataset_sz = len(train_dl.dataset) if hasattr(train_dl, 'dataset') else None
+        self.gen_model.to(c.dev); self.gen_model.train()
+        self.disc_model.to(c.dev); self.disc_model.train()
+        if self.sched_bool:
+            if not self.pretrained_model:
+                self.sched_stop_step = 0
+            self._set_scheduler()
+        if self.not_trained_yet or self.pretrained_model:
+            self.train_dataiter = iter(train_dl)
+        self.last_losses = (None, None)
+        loss_d = loss_g = None
+        for itr in range(num_main_iters):
+            # ---- train generator ----
+            for p in self.disc_model.parameters():
+                p.requires_grad_(False)
+            for gen_iter in range(num_gen_iters):
+                loss_g = self.gen_step()
+            # ---- train discriminator ----
+            for p in self.disc_model.parameters():
+                p.requires_grad_(True)
+            for disc_iter in range(num_disc_iters):
+                batch = next(self.train_dataiter, None)
+                if batch is None:
+                    self.curr_epoch_num += 1
+                    self.train_dataiter = iter(train_dl)
+                    batch = next(self.train_dataiter)
+                xb = batch[0] if isinstance(batch, (list, tuple)) else batch
+                loss_d = self.disc_step(xb)
+                self.curr_dataset_batch_num += 1
+                self.curr_img_num += self.batch_size
+            self.last_losses = (loss_d, loss_g)
+            if step_callback is not None:
+                step_callback(itr, loss_d, loss_g)
+            if log_every and (itr % log_every == 0):
+                print(f'itr {itr:7d}  res {c.res_samples:4d}  D {float(loss_d):9.4g}  G {float(loss_g):9.4g}')
+            if self.sched_bool:
+                self.scheduler_gen.step()
+                self.scheduler_disc.step()
+            if self.not_trained_yet:
+                self.not_trained_yet = False
+        return self.last_losses
 
     # ------------------------------------------------------------------ gradient penalties
     def calc_gp(self, gen_data, real_data):

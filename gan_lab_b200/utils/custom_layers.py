@@ -149,8 +149,45 @@ class InstanceNorm2d(nn.Module):
         return ops.instance_norm(x, self.eps)
 
 
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d(ni) of the ResNet generator blocks (reference custom_layers.py:100-102): same parameters / buffers /
+    state_dict keys (weight, bias, running_mean, running_var, num_batches_tracked); training-mode forward (batch
+    statistics, running-buffer momentum update) is one fused kernel family, optionally with the following ReLU."""
+
+    def forward(self, x, act=None, slope=0.0):
+        if not self.training:
+            raise NotImplementedError('BatchNorm2d eval mode (running statistics) is not on the training path; not built')
+        if self.momentum is None or not self.affine or not self.track_running_stats:
+            raise NotImplementedError('only the nn.BatchNorm2d defaults used by gan-lab are built')
+        return ops.batchnorm_act(x, self.weight, self.bias, self.running_mean, self.running_var, self.num_batches_tracked,
+                                 self.eps, self.momentum, ops.ACT_NONE if act is None else act, slope)
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm([ni, res, res]) of the ResNet discriminator blocks (reference custom_layers.py:103-106).  weight / bias
+    keep the reference's (C,H,W) shape and keys but are STORED in (H,W,C) order -- the order of the NHWC activations they
+    multiply -- so the kernels read them in place (load_state_dict / Adam / deepcopy all preserve that layout)."""
+
+    def __init__(self, normalized_shape, eps=1e-5):
+        super(LayerNorm, self).__init__(list(normalized_shape), eps=eps, elementwise_affine=True)
+        assert len(self.normalized_shape) == 3
+        for p in (self.weight, self.bias):
+            p.data = p.data.permute(1, 2, 0).contiguous().permute(2, 0, 1)
+
+    def forward(self, x, act=None, slope=0.0):
+        if tuple(x.shape[1:]) != tuple(self.normalized_shape):
+            raise ValueError(f'LayerNorm{tuple(self.normalized_shape)} got input of shape {tuple(x.shape)}')
+        return ops.layernorm_act(x, self.weight, self.bias, self.eps, ops.ACT_NONE if act is None else act, slope)
+
+
+class Tanh(nn.Tanh):
+    def forward(self, x):
+        return ops.tanh(x)
+
+
 class NormalizeLayer(nn.Module):
-    """All normalization methods in one place (reference custom_layers.py:88-111)."""
+    """All normalization methods in one place (reference custom_layers.py:88-111).  `forward(x, act=...)` lets the blocks fold
+    the nonlinearity that follows a Batch/LayerNorm into the same kernel."""
 
     def __init__(self, norm_type, ni=None, res=None):
         super(NormalizeLayer, self).__init__()
@@ -160,12 +197,20 @@ class NormalizeLayer(nn.Module):
             self.norm = PixelNorm2d()
         elif norm_type in ('instancenorm', 'instance norm'):
             self.norm = InstanceNorm2d(ni, eps=1.e-8)
-        elif norm_type in ('batchnorm', 'batch norm', 'layernorm', 'layer norm'):
-            raise NotImplementedError('BatchNorm/LayerNorm (ResNet GAN path) are not built yet in this round')
+        elif norm_type in ('batchnorm', 'batch norm'):
+            assert isinstance(ni, int)
+            self.norm = BatchNorm2d(ni)
+        elif norm_type in ('layernorm', 'layer norm'):
+            assert isinstance(ni, int); assert isinstance(res, int)
+            self.norm = LayerNorm([ni, res, res])
         else:
             raise Exception(f'`norm_type` == "{norm_type}" not supported.')
+        self.fuses_act = isinstance(self.norm, (BatchNorm2d, LayerNorm))
 
-    def forward(self, x):
+    def forward(self, x, act=None, slope=0.0):
+        if self.fuses_act:
+            return self.norm(x, act=act, slope=slope)
+        assert act is None
         return self.norm(x)
 
 

@@ -195,6 +195,41 @@ int glb_adam_ewma_multi(const void* const* ptrs, const int64_t* sizes, int T, in
                         const float* hyper, float beta1, float beta2, float eps, float wd,
                         float ewma_beta, int ewma_mode, glb_stream_t stream);
 
+/* ---- ResNet-GAN normalisation layers (resnetgan/resblocks.py:43-46 through NormalizeLayer, utils/custom_layers.py:100-106) -- *
+ * Both are fused with the ReLU that always follows them in the blocks (act / slope as everywhere else; y is then the
+ * POST-activation output and doubles as the mask for the backward).  `ws` is a caller-owned scratch of
+ * glb_*_ws_doubles() doubles (block partial sums are combined in fp64).
+ *
+ * LayerNorm([C,H,W]) with elementwise affine on x [N][L], L = H*W*C in NHWC order; gamma/beta [L] in the SAME (H,W,C)
+ * order (the module keeps its (C,H,W)-shaped parameter in that memory order); eps inside the rsqrt, biased variance.
+ *   fwd    : y = act((x-mean_n)*rstd_n*gamma + beta); stats[n] = {mean, rstd}
+ *   bwd    : g = gy*act'(y)*gamma; gx = rstd*(g - mean(g) - xhat*mean(g*xhat)); ggamma = sum_n gy*act'*xhat; gbeta = sum_n gy*act'
+ *            (gx or the parameter pair may be NULL)
+ *   bwdbwd : cotangent u of gx -> gradients w.r.t. gy, x and gamma: the second-order term WGAN-GP sends back through the
+ *            discriminator's LayerNorms (resnetgan/learner.py:811-825; aten native_layer_norm_backward's own backward). */
+int64_t glb_layernorm_ws_doubles(int N);
+int glb_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, void* ws,
+                      int N, int64_t L, float eps, int act, float slope, glb_stream_t stream);
+int glb_layernorm_bwd(const float* gy, const float* y, const float* x, const float* gamma, const float* stats,
+                      float* gx, float* ggamma, float* gbeta, void* ws, int N, int64_t L, int act, float slope,
+                      glb_stream_t stream);
+int glb_layernorm_bwdbwd(const float* u, const float* gy, const float* y, const float* x, const float* gamma,
+                         const float* stats, float* g_gy, float* g_x, float* g_gamma, void* ws, int N, int64_t L,
+                         int act, float slope, glb_stream_t stream);
+/* BatchNorm2d in training mode (batch statistics over the P = N*H*W rows of x [P][C], biased variance for the
+ * normalisation, momentum update of running_mean / running_var with the unbiased variance, num_batches_tracked += 1;
+ * any of the three running pointers may be NULL).  stats = {mean[C], rstd[C]}.  Generator side only -> first order. */
+int64_t glb_batchnorm_ws_doubles(int C);
+int glb_batchnorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked, void* ws,
+                      int64_t P, int C, float eps, float momentum, int act, float slope, glb_stream_t stream);
+int glb_batchnorm_bwd(const float* gy, const float* y, const float* x, const float* gamma, const float* stats,
+                      float* gx, float* ggamma, float* gbeta, void* ws, int64_t P, int C, int act, float slope,
+                      glb_stream_t stream);
+/* nn.Tanh on the generator output (resnetgan/architectures.py:58, 96): y = tanh(x); gx = gy*(1-y^2). */
+int glb_tanh_fwd(const float* x, float* y, int64_t n, glb_stream_t stream);
+int glb_tanh_bwd(const float* gy, const float* y, float* gx, int64_t n, glb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,6 +323,72 @@ def adam_ewma_multi(ptr_table, sizes, T, max_size, hyper, beta1, beta2, eps, wd,
             lag.copy_(p * (1 - ewma_beta) + prev * ewma_beta)
 
 
+# ---- ResNet-GAN norms (csrc/norm.cu); second-order terms come from torch's own autograd on F.layer_norm ------------
+def _ln_core(x, gamma, beta, eps, act, slope):
+    return _act(F.layer_norm(x, tuple(x.shape[1:]), gamma, beta, eps), act, slope)
+
+
+def layernorm_fwd(x, gamma, beta, eps, act, slope):
+    y = _ln_core(x, gamma, beta, eps, act, slope)
+    mean = x.mean(dim=(1, 2, 3))
+    var = x.var(dim=(1, 2, 3), unbiased=False)
+    return _cl(y), torch.stack([mean, (var + eps).rsqrt()], dim=1)
+
+
+def _ln_bwd_graph(gy, y, x, gamma, stats, act, slope):
+    """gx, ggamma, gbeta as differentiable functions of (gy, x, gamma) -- the mask act'(y) is a constant."""
+    n = x.shape[0]
+    mean, rstd = stats[:, 0].view(n, 1, 1, 1), stats[:, 1].view(n, 1, 1, 1)
+    eps_eff = (1.0 / rstd ** 2 - x.var(dim=(1, 2, 3), unbiased=False, keepdim=True)).detach()   # recover eps per sample
+    mu = x.mean(dim=(1, 2, 3), keepdim=True)
+    var = x.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    r = (var + eps_eff).rsqrt()
+    xh = (x - mu) * r
+    gm = gy * _dact(y, act, slope)
+    g = gm * gamma
+    gx = r * (g - g.mean(dim=(1, 2, 3), keepdim=True) - xh * (g * xh).mean(dim=(1, 2, 3), keepdim=True))
+    return gx, (gm * xh).sum(0), gm.sum(0)
+
+
+def layernorm_bwd(gy, y, x, gamma, stats, act, slope, want_gx=True, want_params=True):
+    gx, gg, gb = _ln_bwd_graph(gy, y, x, gamma, stats, act, slope)
+    return (_cl(gx) if want_gx else None), (gg if want_params else None), (gb if want_params else None)
+
+
+def layernorm_bwdbwd(u, gy, y, x, gamma, stats, act, slope, want_gy=True, want_x=True, want_gamma=True):
+    with torch.enable_grad():
+        gy_, x_, gamma_ = (t.detach().clone().requires_grad_(True) for t in (gy, x, gamma))
+        gx, _, _ = _ln_bwd_graph(gy_, y.detach(), x_, gamma_, stats.detach(), act, slope)
+        g_gy, g_x, g_gamma = torch.autograd.grad(gx, (gy_, x_, gamma_), u)
+    return (_cl(g_gy) if want_gy else None), (_cl(g_x) if want_x else None), (g_gamma if want_gamma else None)
+
+
+def batchnorm_fwd(x, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, slope):
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=False)
+    y = F.batch_norm(x, running_mean, running_var, gamma.reshape(-1), beta.reshape(-1), True, momentum, eps)
+    if num_batches_tracked is not None:
+        num_batches_tracked += 1
+    return _cl(_act(y, act, slope)), torch.stack([mean, (var + eps).rsqrt()], dim=0)
+
+
+def batchnorm_bwd(gy, y, x, gamma, stats, act, slope):
+    c = x.shape[1]
+    mean, rstd = stats[0].view(1, c, 1, 1), stats[1].view(1, c, 1, 1)
+    xh = (x - mean) * rstd
+    g = gy * _dact(y, act, slope)
+    gx = gamma.view(1, c, 1, 1) * rstd * (g - g.mean(dim=(0, 2, 3), keepdim=True) - xh * (g * xh).mean(dim=(0, 2, 3), keepdim=True))
+    return _cl(gx), (g * xh).sum(dim=(0, 2, 3)), g.sum(dim=(0, 2, 3))
+
+
+def tanh_fwd(x):
+    return torch.tanh(x)
+
+
+def tanh_bwd(gy, y):
+    return gy * (1 - y * y)
+
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and f.__module__ == __name__
        and n not in ("install",)]
 

@@ -377,6 +377,92 @@ def golden_train_steps(ref, model="StyleGAN", res=16, bs=4, iters=2):
         _unpatch(ref)
 
 
+RESNET_FMAP = 8          # reference constants resnetgan/architectures.py:19-20 (FMAP_G = FMAP_D = 64) patched for small fixtures
+RESNET_LATENT = 16
+
+
+def _resnet_learner(ref, res, bs, **over):
+    cfg = make_config("ResNet GAN", res=res, batch_size=bs, len_latent=RESNET_LATENT, **over)
+    ref.resnet_learner.FMAP_G = ref.resnet_learner.FMAP_D = RESNET_FMAP
+    try:
+        with _quiet():
+            L = ref.resnet_learner.GANLearner(cfg)
+    finally:
+        ref.resnet_learner.FMAP_G = ref.resnet_learner.FMAP_D = 64
+    return L, cfg
+
+
+def perturb_norm_params(module, gen):
+    """BatchNorm / LayerNorm affine maps start at weight = 1, bias = 0: move them so that they matter."""
+    with torch.no_grad():
+        for m in module.modules():
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.LayerNorm)):
+                m.weight.copy_(1.0 + 0.3 * torch.randn(m.weight.shape, generator=gen))
+                m.bias.copy_(0.3 * torch.randn(m.bias.shape, generator=gen))
+
+
+def golden_resnet_nets(ref, res=64, bs=4):
+    """ResNet generator / discriminator forward + backward (+ WGAN-GP through the LayerNorm blocks), reference modules."""
+    torch.manual_seed(41 + res); np.random.seed(41)
+    L, cfg = _resnet_learner(ref, res, bs)
+    G, D = L.gen_model, L.disc_model
+    gen = torch.Generator().manual_seed(43)
+    perturb_zero_params(G, gen); perturb_zero_params(D, gen)
+    perturb_norm_params(G, gen); perturb_norm_params(D, gen)
+    G.train(); D.train()
+    g_sd, d_sd = sd_clone(G), sd_clone(D)
+    z = torch.randn(bs, cfg.len_latent, generator=gen)
+    img = G(z)
+    gimg = torch.randn(img.shape, generator=gen)
+    G.zero_grad(); img.backward(gimg)
+    g_grads = grads_of(G)
+    g_buffers = {k: v.detach().clone() for k, v in G.named_buffers()}       # running statistics after ONE forward
+    x = torch.rand(bs, 3, res, res, generator=gen) * 2 - 1
+    D.zero_grad()
+    logits = D(x); glog = torch.randn(logits.shape, generator=gen); logits.backward(glog)
+    d_grads = grads_of(D)
+    D.zero_grad()
+    with Tape() as tape:
+        gp = L.calc_gp(img.detach(), x)          # wgan-gp: draws eps via torch.rand
+    gp.backward()
+    d_gp_grads = grads_of(D)
+    return dict(res=res, bs=bs, fmap=RESNET_FMAP, len_latent=cfg.len_latent, g_sd=g_sd, d_sd=d_sd, z=z, img=img.detach(),
+                gimg=gimg, g_grads=g_grads, g_buffers=g_buffers, x=x, logits=logits.detach(), glog=glog, d_grads=d_grads,
+                gp=gp.detach(), gp_tape=tape.events, d_gp_grads=d_gp_grads, lda=cfg.lda, gamma=cfg.gamma)
+
+
+def golden_resnet_train(ref, res=64, bs=4, iters=2, num_disc_iters=2):
+    """GANLearner.train() (ResNet GAN: generator step first, then num_disc_iters discriminator steps), unmodified loop."""
+    torch.manual_seed(51); np.random.seed(51)
+    # lr 1e-5: with Adam(beta1=0) every step moves each parameter by ~+-lr whatever the gradient's size; at larger lr the sign
+    # flips of noise-level gradients make the trajectory chaotic (the reference run twice with 1 vs 8 threads disagrees on
+    # 37 % of the discriminator's parameters after 2 iterations at lr 1e-4, on 1.3 % at 1e-5)
+    L, cfg = _resnet_learner(ref, res, bs, num_disc_iters=num_disc_iters, lr_base=1e-5)
+    gen = torch.Generator().manual_seed(53)
+    perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+    perturb_norm_params(L.gen_model, gen); perturb_norm_params(L.disc_model, gen)
+    g0, d0 = sd_clone(L.gen_model), sd_clone(L.disc_model)
+    data = torch.rand(iters * num_disc_iters * bs, 3, res, res, generator=gen) * 2 - 1
+    ds = TensorDataset(data)
+    dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+    losses = []
+    orig_backward = torch.Tensor.backward
+
+    def rec_backward(self, *a, **k):
+        losses.append(float(self.detach()))
+        return orig_backward(self, *a, **k)
+
+    torch.Tensor.backward = rec_backward
+    try:
+        with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+            L.train(dl, num_main_iters=iters)
+    finally:
+        torch.Tensor.backward = orig_backward
+    return dict(model="ResNet GAN", res=res, bs=bs, iters=iters, num_disc_iters=num_disc_iters, fmap=RESNET_FMAP,
+                len_latent=cfg.len_latent, g_sd0=g0, d_sd0=d0, data=data, tape=tape.events, losses=losses,
+                g_sd1=sd_clone(L.gen_model), d_sd1=sd_clone(L.disc_model), lr=cfg.lr_base)
+
+
 def main():
     ref = load_reference()
     GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
@@ -388,6 +474,9 @@ def main():
         "pro_nets_res8_fade.pt": lambda: golden_pro_nets(ref, 8, 4, True),
         "style_train_res16.pt": lambda: golden_train_steps(ref, "StyleGAN", 16, 4, 2),
         "pro_train_res8.pt": lambda: golden_train_steps(ref, "ProGAN", 8, 4, 2),
+        "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
+        "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
+        "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),
     }
     only = sys.argv[1:]
     for name, fn in jobs.items():

@@ -149,6 +149,38 @@ def test_glue_kernels_vs_contract(N, C, H, W):
         both("pixelnorm_bwd", gy, x, 1e-8)
 
 
+@pytest.mark.parametrize("N,C,H,W", [(4, 8, 64, 64), (3, 64, 8, 8), (64, 64, 16, 16), (2, 512, 4, 4), (5, 16, 6, 10)])
+def test_norm_kernels_vs_contract(N, C, H, W):
+    """LayerNorm([C,H,W]) + ReLU with its first- and second-order backward, BatchNorm2d (batch statistics, running-buffer
+    update) + ReLU with its backward, Tanh -- each launcher against its fp64 contract on the same inputs.  The mask of the
+    backward kernels is the saved forward OUTPUT, passed in identically on both sides, so no bit can flip here."""
+    x, gy, u = cl(rn(N, C, H, W) * 1.5 + 0.7), cl(rn(N, C, H, W, seed=1)), cl(rn(N, C, H, W, seed=2))
+    gam, bet = 1.0 + 0.3 * rn(C, H, W, seed=3), 0.3 * rn(C, H, W, seed=4)
+    for act, slope in ((K.ACT_LRELU, 0.0), (K.ACT_NONE, 0.0), (K.ACT_LRELU, 0.2)):
+        y, stats = both("layernorm_fwd", x, gam, bet, 1e-5, act, slope)
+        yc = y.cpu()
+        both("layernorm_bwd", gy, yc, x, gam, stats.cpu(), act, slope, tol=2e-4)
+        both("layernorm_bwd", gy, yc, x, gam, stats.cpu(), act, slope, want_gx=False, tol=2e-4)
+        both("layernorm_bwdbwd", u, gy, yc, x, gam, stats.cpu(), act, slope, tol=5e-4)
+    # parameters stored the way the LayerNorm module stores them: (H,W,C) memory behind the (C,H,W) shape
+    gam_p = gam.permute(1, 2, 0).contiguous().permute(2, 0, 1)
+    y2, _ = K.layernorm_fwd(x.to(DEV), gam_p.to(DEV), bet.to(DEV), 1e-5, K.ACT_LRELU, 0.0)
+    yc, _ = KC.layernorm_fwd(x.double(), gam.double(), bet.double(), 1e-5, K.ACT_LRELU, 0.0)
+    assert rel(y2, yc) < TOL
+    g1, b1 = 1.0 + 0.3 * rn(C, seed=5), 0.3 * rn(C, seed=6)
+    for act, slope in ((K.ACT_LRELU, 0.0), (K.ACT_NONE, 0.0)):
+        rm, rv, nbt = rn(C, seed=7) * 0.1, rn(C, seed=8).abs() + 0.5, torch.tensor(3, dtype=torch.int64)
+        rm_g, rv_g, nbt_g = rm.to(DEV), rv.to(DEV), nbt.to(DEV)
+        y, stats = K.batchnorm_fwd(x.to(DEV), g1.to(DEV), b1.to(DEV), rm_g, rv_g, nbt_g, 1e-5, 0.1, act, slope)
+        rm_c, rv_c, nbt_c = rm.double(), rv.double(), nbt.clone()
+        y_c, stats_c = KC.batchnorm_fwd(x.double(), g1.double(), b1.double(), rm_c, rv_c, nbt_c, 1e-5, 0.1, act, slope)
+        assert rel(y, y_c) < TOL and rel(stats, stats_c) < TOL
+        assert rel(rm_g, rm_c) < TOL and rel(rv_g, rv_c) < TOL and int(nbt_g) == int(nbt_c) == 4
+        both("batchnorm_bwd", gy, y.cpu(), x, g1, stats.cpu(), act, slope, tol=5e-4)
+    both("tanh_fwd", x)
+    both("tanh_bwd", gy, torch.tanh(x))
+
+
 def test_pixelnorm_latents():
     x, gy = rn(8, 512), rn(8, 512, seed=1)
     both("pixelnorm_fwd", x, 1e-8)
@@ -319,6 +351,15 @@ def test_cuda_graph_replay_of_train_steps():
 @pytest.mark.parametrize("gp", ["r1", "r2"])
 def test_shared_penalty_forward(gp):
     PC.case_shared_penalty_forward(DEV, gp)
+
+
+@pytest.mark.parametrize("fname", PC.RESNET_NETS)
+def test_resnet_nets_modules(golden, fname):
+    PC.case_resnet_nets_modules(golden, DEV, fname)
+
+
+def test_resnet_train(golden):
+    PC.case_resnet_train(golden, DEV)
 
 
 def test_library_was_loaded():

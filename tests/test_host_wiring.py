@@ -67,3 +67,22 @@ def test_learner_train(golden, fname, model):
 @pytest.mark.parametrize("gp", ["r1", "r2"])
 def test_shared_penalty_forward(gp):
     PC.case_shared_penalty_forward(DEV, gp)
+
+
+@pytest.mark.parametrize("fname", PC.RESNET_NETS)
+def test_resnet_nets_modules(golden, fname):
+    PC.case_resnet_nets_modules(golden, DEV, fname)
+
+
+@pytest.mark.parametrize("fname", PC.RESNET_NETS)
+def test_resnet_nets_modules_fp64(golden, fname, monkeypatch):
+    """Same case with the CPU doubles in fp64: no ReLU mask bit can flip, so every gradient must agree with the reference
+    down to the fixture's own fp32 noise (this is what pins the host wiring of the ResNet path exactly)."""
+    import torch
+    import gan_lab_b200._kernels as K
+    monkeypatch.setattr(K, "_chk", lambda *ts: None)
+    PC.case_resnet_nets_modules(golden, DEV, fname, dtype=torch.float64, grad_tol=2e-5)
+
+
+def test_resnet_train(golden):
+    PC.case_resnet_train(golden, DEV)
