@@ -369,6 +369,106 @@ def pro_discriminator_forward(p: Params, x, *, res: int, alpha: float = 1.0, fad
 
 
 # --------------------------------------------------------------------------- #
+# ResNet GAN: resnetgan/resblocks.py:15-120, resnetgan/architectures.py:29-182
+# --------------------------------------------------------------------------- #
+def _conv(p: Params, key: str, x, padding: int):
+    """Conv2dEx without equalized LR (ResNet GAN default, config.py:213): plain nn.Conv2d, custom_layers.py:202-211."""
+    return F.conv2d(x, p[key + ".conv2d.weight"], p.get(key + ".conv2d.bias"), 1, padding)
+
+
+def _batchnorm_train(p: Params, key: str, x, buffers: Optional[Params] = None, momentum: float = 0.1, eps: float = 1e-5):
+    """nn.BatchNorm2d in training mode (custom_layers.py:100-102): batch statistics, biased variance for the
+    normalisation; running buffers (if given) updated with the unbiased variance and momentum 0.1."""
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=False)
+    if buffers is not None:
+        n = x.numel() // x.shape[1]
+        with torch.no_grad():
+            buffers[key + ".norm.running_mean"].mul_(1 - momentum).add_(momentum * mean)
+            buffers[key + ".norm.running_var"].mul_(1 - momentum).add_(momentum * var * n / (n - 1))
+            buffers[key + ".norm.num_batches_tracked"] += 1
+    xh = (x - mean.view(1, -1, 1, 1)) * (var.view(1, -1, 1, 1) + eps).rsqrt()
+    return xh * p[key + ".norm.weight"].view(1, -1, 1, 1) + p[key + ".norm.bias"].view(1, -1, 1, 1)
+
+
+def _layernorm(p: Params, key: str, x, eps: float = 1e-5):
+    """nn.LayerNorm([C,H,W]) with elementwise affine (custom_layers.py:103-106)."""
+    mean = x.mean(dim=(1, 2, 3), keepdim=True)
+    var = x.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    return (x - mean) * (var + eps).rsqrt() * p[key + ".norm.weight"] + p[key + ".norm.bias"]
+
+
+def resblock2d(p: Params, key: str, x, *, norm: str, up: bool = False, pool: bool = False, ni: int, nf: int,
+               pix32: bool = False, buffers: Optional[Params] = None):
+    """ResBlock2d / ResBlock2d32Pix.forward (resblocks.py:15-79): skip(x) + conv_layer_2(conv_layer_1(x)) with the module
+    indices the reference's Sequentials give the convs (blur_type = None)."""
+    nrm = (lambda k, t: _batchnorm_train(p, k, t, buffers)) if norm == "BatchNorm" else (lambda k, t: _layernorm(p, k, t))
+    h = torch.relu(nrm(key + ".conv_layer_1.0", x))
+    if up:
+        h = _conv(p, key + ".conv_layer_1.3", upsample2x(h), 1)
+    else:
+        h = _conv(p, key + ".conv_layer_1.2", h, 1)
+    h = torch.relu(nrm(key + ".conv_layer_2.0", h))
+    h = _conv(p, key + ".conv_layer_2.2", h, 1)
+    if pool:
+        h = avgpool2(h)
+    if up:
+        s = _conv(p, key + ".skip_connection.1", upsample2x(x), 0)
+    elif pool and pix32:
+        s = avgpool2(_conv(p, key + ".skip_connection.0", x, 0))                      # resblocks.py:75-76
+    elif pool:
+        s = _conv(p, key + ".skip_connection.1", avgpool2(x), 0)
+    elif ni != nf:
+        s = _conv(p, key + ".skip_connection.0", x, 0)
+    else:
+        s = x
+    return s + h
+
+
+def resnet_generator_forward(p: Params, z, *, res: int, fmap: int = 64, buffers: Optional[Params] = None):
+    """Generator64PixResnet / Generator32PixResnet.forward (architectures.py:63-99 / 29-61), training mode."""
+    len_latent = z.shape[1]
+    if res == 64:
+        c0, plan, blocks = len_latent * 4, [8 * fmap, 4 * fmap, 2 * fmap, fmap], (3, 4, 5, 6)
+    elif res == 32:
+        c0, plan, blocks = len_latent, [fmap, fmap, fmap], (3, 4, 5)
+    else:
+        raise ValueError(res)
+    x = F.linear(z, p["generator_model.1.linear.weight"], p["generator_model.1.linear.bias"]).view(-1, c0, RES_INIT, RES_INIT)
+    ni = c0
+    for idx, nf in zip(blocks, plan):
+        x = resblock2d(p, f"generator_model.{idx}", x, norm="BatchNorm", up=True, ni=ni, nf=nf, buffers=buffers)
+        ni = nf
+    n = blocks[-1] + 1
+    x = torch.relu(_batchnorm_train(p, f"generator_model.{n}", x, buffers))
+    return torch.tanh(_conv(p, f"generator_model.{n + 2}", x, 1))
+
+
+def resnet_discriminator_forward(p: Params, x, *, res: int, fmap: int = 64):
+    """Discriminator64PixResnet / Discriminator32PixResnet.forward (architectures.py:150-182 / 105-133)."""
+    x = x.view(-1, FMAP_SAMPLES, res, res)
+    if res == 64:
+        x = _conv(p, "conv1", x, 1)
+        ni = fmap
+        for b, nf in enumerate([2 * fmap, 4 * fmap, 8 * fmap, 8 * fmap]):
+            x = resblock2d(p, f"resblocks.{b}", x, norm="LayerNorm", pool=True, ni=ni, nf=nf)
+            ni = nf
+        x = x.reshape(-1, 16 * 8 * fmap)
+    elif res == 32:
+        # FastResBlock2dDownsample (resblocks.py:82-120): conv-relu-conv-pool + pool-conv1x1 skip
+        h = torch.relu(_conv(p, "conv1.conv_layer_1.0", x, 1))
+        h = avgpool2(_conv(p, "conv1.conv_layer_2.0", h, 1))
+        x = _conv(p, "conv1.skip_connection.1", avgpool2(x), 0) + h
+        x = resblock2d(p, "resblocks.0", x, norm="LayerNorm", pool=True, ni=fmap, nf=fmap, pix32=True)
+        x = resblock2d(p, "resblocks.1", x, norm="LayerNorm", ni=fmap, nf=fmap, pix32=True)
+        x = resblock2d(p, "resblocks.2", x, norm="LayerNorm", ni=fmap, nf=fmap, pix32=True)
+        x = F.avg_pool2d(torch.relu(x), res // 4).view(-1, fmap)
+    else:
+        raise ValueError(res)
+    return F.linear(x, p["linear1.linear.weight"], p["linear1.linear.bias"]).view(-1)
+
+
+# --------------------------------------------------------------------------- #
 # losses / penalties: progan/learner.py:791-812, 883-896; resnetgan/learner.py:780-827
 # --------------------------------------------------------------------------- #
 def gradient_penalty(d_fn: Callable, gp_type: str, real, fake, lda: float = 10.0, gamma: float = 1.0,

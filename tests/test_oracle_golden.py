@@ -188,6 +188,48 @@ def test_pro_nets(golden, fname):
     _check_grads(names, grads, g["d_gp_grads"], rtol=5e-4)
 
 
+@pytest.mark.parametrize("fname", ["resnet_nets_res64.pt", "resnet_nets_res32.pt"])
+def test_resnet_nets(golden, fname):
+    """ResNet generator (BatchNorm batch statistics + running buffers, Tanh) and discriminator (LayerNorm) restatements vs
+    the reference modules, in fp64 so that no ReLU mask bit flips: forward, parameter gradients, WGAN-GP and its gradients."""
+    g = golden(fname)
+    res, fmap = g["res"], (g["fmap"] if g["res"] == 64 else 2 * g["fmap"])     # 32-pixel nets use FMAP*2 (learner.py:192)
+    dbl = lambda d: {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in d.items()}
+    gp = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in dbl(g["g_sd"]).items()}
+    buffers = {k: v for k, v in gp.items() if "running" in k or "num_batches" in k}
+    img = O.resnet_generator_forward(gp, g["z"].double(), res=res, fmap=fmap, buffers=buffers)
+    close(img, g["img"].double(), rtol=2e-5, atol=2e-6)
+    for k, v in g["g_buffers"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(buffers[k]) == int(v)
+        else:
+            close(buffers[k], v.double(), rtol=1e-5, atol=1e-6)
+    names = [k for k in gp if gp[k].requires_grad]
+    grads = torch.autograd.grad(img, [gp[k] for k in names], g["gimg"].double(), allow_unused=True)
+    big = max(float(v.abs().max()) for v in g["g_grads"].values() if v is not None)
+    for k, gr in zip(names, grads):
+        ref = g["g_grads"][k].double()
+        assert float((gr - ref).abs().max()) <= 2e-5 * max(float(ref.abs().max()), 5e-2 * big), k
+    dp = {k: v.requires_grad_(True) for k, v in dbl(g["d_sd"]).items()}
+    d_fn = lambda t: O.resnet_discriminator_forward(dp, t, res=res, fmap=fmap)
+    logits = d_fn(g["x"].double())
+    close(logits, g["logits"].double(), rtol=2e-5, atol=2e-6)
+    names = list(dp)
+    grads = torch.autograd.grad(logits, [dp[k] for k in names], g["glog"].double(), allow_unused=True)
+    for k, gr in zip(names, grads):
+        assert relerr(gr, g["d_grads"][k].double()) < 2e-5, k
+    (kind, eps), = g["gp_tape"]
+    pen = O.gradient_penalty(d_fn, "wgan-gp", g["x"].double(), g["img"].double(), g["lda"], g["gamma"], eps=eps.double())
+    assert relerr(pen, g["gp"].double()) < 2e-5
+    grads = torch.autograd.grad(pen, [dp[k] for k in names], allow_unused=True)
+    for k, gr in zip(names, grads):
+        ref = g["d_gp_grads"][k]
+        if gr is None or ref is None:         # parameters the penalty does not depend on (last biases)
+            assert (gr is None or float(gr.abs().max()) == 0.0) and (ref is None or float(ref.abs().max()) == 0.0), k
+        else:
+            assert relerr(gr, ref.double()) < 1e-4, (k, relerr(gr, ref.double()))
+
+
 @pytest.mark.parametrize("fname,model,gp,loss", [("style_train_res16.pt", "StyleGAN", "r1", "nonsaturating"),
                                                 ("pro_train_res8.pt", "ProGAN", "wgan-gp", "wgan")])
 def test_train_steps(golden, fname, model, gp, loss):
