@@ -7,8 +7,14 @@ rank, so averaging the per-rank gradients reproduces the single-GPU gradient of 
 (all losses are batch means).  The only exchange step is therefore the gradient all-reduce before each
 optimiser step; parameters, Adam state and the EWMA generator are replicated.
 
-Gradients are reduced in place, bucketed (default 32 MiB) so that NCCL launches overlap each other and the tail
-of the backward pass; buckets are flat views over the gradients' dense storage (channels-last weights included).
+Overlap with backward: every parameter carries a post-accumulate-grad hook; as soon as the gradients that have become
+ready fill a bucket (default 32 MiB, in autograd order: last layers first) the bucket is packed (one `torch.cat` into a
+persistent flat buffer), pre-scaled by 1/world and all-reduced asynchronously -- NCCL runs on the process group's own
+stream while the compute stream keeps executing the rest of backward (including the R1 double-backward tail).
+`allreduce_grads()` after backward only flushes the last partial bucket, makes the compute stream wait for the
+collectives and re-points each `p.grad` at its slice of the reduced bucket (no copy back; the fused Adam reads the
+gradients through pointers).  All of this is stream-ordered, so it is captured into the step's CUDA graph as parallel
+branches.  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
 """
 import torch
 import torch.distributed as dist
@@ -20,44 +26,76 @@ def _flat_view(t):
 
 
 class DataParallel(object):
-    def __init__(self, world_size=None, bucket_bytes=32 * 1024 * 1024):
+    def __init__(self, world_size=None, bucket_bytes=32 * 1024 * 1024, overlap=True):
         self.world = world_size if world_size is not None else dist.get_world_size()
         self.bucket_bytes = bucket_bytes
+        self.overlap = overlap
+        self._hooked = set()        # ids of parameters that carry our hook
+        self._pending = []          # parameters whose gradient is ready but not yet in a bucket
+        self._pending_bytes = 0
+        self._inflight = []         # (work, flat bucket, parameters)
+        self._bufs = {}             # (bucket index, size, device) -> persistent flat buffer (stable addresses across replays)
 
     def broadcast_params(self, module, src=0):
         with torch.no_grad():
             for p in module.parameters():
                 dist.broadcast(_flat_view(p.data), src=src)
+            for b in module.buffers():
+                if b.is_floating_point():
+                    dist.broadcast(_flat_view(b.data), src=src)
+
+    # ------------------------------------------------------------------ overlap machinery
+    def attach(self, *modules):
+        """Hook every parameter of `modules` (idempotent; call again after the networks have grown)."""
+        if self.world == 1 or not self.overlap:
+            return
+        for m in modules:
+            for p in m.parameters():
+                if id(p) not in self._hooked:
+                    p.register_post_accumulate_grad_hook(self._on_grad)
+                    self._hooked.add(id(p))
+
+    def _on_grad(self, p):
+        if p.grad is None:
+            return
+        self._pending.append(p)
+        self._pending_bytes += p.numel() * 4
+        if self._pending_bytes >= self.bucket_bytes:
+            self._launch()
+
+    @torch.no_grad()
+    def _launch(self):
+        ps, self._pending, self._pending_bytes = self._pending, [], 0
+        if not ps:
+            return
+        n = sum(p.numel() for p in ps)
+        key = (len(self._inflight), n, ps[0].device)
+        flat = self._bufs.get(key)
+        if flat is None:
+            flat = self._bufs[key] = torch.empty(n, dtype=ps[0].dtype, device=ps[0].device)
+        torch.cat([_flat_view(p.grad) for p in ps], out=flat)
+        flat.mul_(1.0 / self.world)
+        self._inflight.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, ps))
 
     def allreduce_grads(self, module):
-        """Average gradients across ranks (sum all-reduce of pre-scaled buckets)."""
+        """Average the gradients of `module` across ranks; returns once the compute stream is ordered after the
+        collectives (sum all-reduce of pre-scaled buckets)."""
         if self.world == 1:
             return
-        grads = [p.grad for p in module.parameters() if p.grad is not None]
-        bucket, size, works = [], 0, []
-
-        def flush():
-            nonlocal bucket, size
-            if not bucket:
-                return
-            flat = torch.cat([_flat_view(g) for g in bucket])
-            flat.mul_(1.0 / self.world)
-            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, bucket))
-            bucket, size = [], 0
-
-        for g in reversed(grads):            # reverse-autograd order: last layers' grads are ready first
-            bucket.append(g)
-            size += g.numel() * 4
-            if size >= self.bucket_bytes:
-                flush()
-        flush()
-        for work, flat, bk in works:
-            work.wait()
-            off = 0
-            for g in bk:
-                n = g.numel()
-                _flat_view(g).copy_(flat[off:off + n])
-                off += n
+        done = {id(p) for _, _, ps in self._inflight for p in ps} | {id(p) for p in self._pending}
+        for p in reversed(list(module.parameters())):       # reverse-autograd order: last layers' grads are ready first
+            if p.grad is not None and id(p) not in done:
+                self._on_grad(p)
+        self._launch()
+        with torch.no_grad():
+            for work, flat, ps in self._inflight:
+                work.wait()
+                off = 0
+                for p in ps:
+                    p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
+                    off += p.numel()
+        self._inflight = []
+        self.attach(module)                                  # from the next backward on, buckets launch from the hooks
 
     def allreduce_mean_(self, t):
         if self.world > 1:

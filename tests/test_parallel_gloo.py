@@ -39,9 +39,16 @@ def _worker(rank, world, port, ret):
         local = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
         dp.allreduce_grads(net)
         avg = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
+        # second backward: the hooks attached by the first allreduce_grads() now launch the buckets DURING backward
+        assert len(dp._hooked) == len(list(net.parameters()))
+        net.zero_grad(set_to_none=True)
+        net(x).pow(2).mean().backward()
+        launched_in_backward = len(dp._inflight)
+        dp.allreduce_grads(net)
+        avg2 = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
         t = torch.full((3,), float(rank + 1))
         dp.allreduce_mean_(t)
-        ret[rank] = dict(bcast=w_after_bcast, local=local, avg=avg, mean=t)
+        ret[rank] = dict(bcast=w_after_bcast, local=local, avg=avg, avg2=avg2, mean=t, launched=launched_in_backward)
     finally:
         dist.destroy_process_group()
 
@@ -62,5 +69,9 @@ def test_dataparallel_world2_gloo():
         want = (l0 + l1) / 2
         torch.testing.assert_close(a0, want, rtol=1e-6, atol=1e-7)
         assert torch.equal(a0, a1)
-        assert a0.stride() == l0.stride()                   # layout of the gradient (channels_last) preserved
+        sig = lambda t: [st for st, sz in zip(t.stride(), t.shape) if sz > 1]
+        assert sig(a0) == sig(l0)                           # layout of the gradient (channels_last) preserved
+    assert r0["launched"] >= 2 and r0["launched"] == r1["launched"]     # buckets went out from the hooks, during backward
+    for a, b in zip(r0["avg"], r0["avg2"]):                               # same data, same weights -> same averaged gradient
+        assert (a is None and b is None) or torch.equal(a, b)
     assert torch.allclose(r0["mean"], torch.full((3,), 1.5)) and torch.equal(r0["mean"], r1["mean"])
