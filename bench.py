@@ -375,8 +375,8 @@ def kernel_rooflines(L, x, main_iter, flush):
     """Both rooflines of BASELINE.json's metric from ONE recorded eager main iteration.
 
     Every launcher call of the iteration is recorded (arguments kept alive); then, per launcher kind, the recorded
-    calls are re-issued back to back -- GPU bound, in step order, L2 flushed (160 MB write) before each repetition --
-    between one pair of CUDA events on the launch stream.
+    calls are re-issued back to back as one CUDA graph -- GPU bound, in step order, L2 flushed (160 MB write) before each
+    replay -- between one pair of CUDA events on the launch stream.
       * dense convs (fprop / dgrad / wgrad implicit GEMMs): achieved = algorithmic FLOPs / device time  -> tensor roofline
       * glue launchers: achieved = compulsory bytes (every tensor argument read once + every output written once,
         4 B/element; Adam: 28 B/param + 8 B/param for the fused EWMA) / device time                   -> HBM roofline
@@ -438,15 +438,30 @@ def kernel_rooflines(L, x, main_iter, flush):
         for n, f in orig.items():
             setattr(K, n, f)
 
-    def timed(sel, reps=3):
+    def timed(sel, reps=5):
+        """Median device time of the recorded launches of one kind, re-issued as ONE CUDA graph (as in the real step: no
+        Python between launches), L2 flushed before every replay; eager re-issue if the capture is refused."""
+        graph = None
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                for _, f, a, k, _w in sel:
+                    f(*a, **k)
+        except Exception:
+            graph = None
+            torch.cuda.synchronize()
         times = []
         for _ in range(reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            with torch.no_grad():
-                for _, f, a, k, _w in sel:
-                    f(*a, **k)
+            if graph is not None:
+                graph.replay()
+            else:
+                with torch.no_grad():
+                    for _, f, a, k, _w in sel:
+                        f(*a, **k)
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
@@ -479,7 +494,7 @@ def kernel_rooflines(L, x, main_iter, flush):
         if big:
             gby[kind] = (sum(c[4] for c in big), timed(big), len(big))
         if sm:
-            small_ms += timed(sm, reps=1); small_n += len(sm)
+            small_ms += timed(sm, reps=3); small_n += len(sm)
     gb = sum(v[0] for v in gby.values())
     gms = sum(v[1] for v in gby.values())
     glue = {"bound": "hbm", "kernel": "fused glue launchers moving >= 4 MB (bias/act, blur, up/downsample, style epilogue, RGB, Adam+EWMA)",

@@ -1,12 +1,24 @@
 // Bandwidth-bound "glue" kernels of the G/D training step: fused, 128-bit vectorised, coalesced (NHWC: the
 // channel axis is the contiguous one), warp-shuffle / shared-memory reductions.  Each kernel names the ATen
 // call sites of the reference it replaces; roofline = HBM bandwidth.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace glb {
 namespace {
 
 constexpr int TPB = 256;
+
+// A/B switch for kernel variants (tools/glue_bw.py): GLB_GLUE_OLD is a bit mask that selects the PREVIOUS implementation of
+// bit 0 blur3x3 (9 taps per thread), bit 1 act_bwd (one row per loop iteration).  Unset = current kernels.
+inline int glue_variant() {
+  static const int v = [] {
+    const char* e = getenv("GLB_GLUE_OLD");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // bias + activation (Conv2dBias + LeakyReLU: reference utils/custom_layers.py:222-226 + shared nn.LeakyReLU)
@@ -86,6 +98,57 @@ __global__ void act_bwd_kernel(const float4* __restrict__ gy, const float4* __re
         atomicAdd(gbias + 4 * q + 0, bias_scale * s.x); atomicAdd(gbias + 4 * q + 1, bias_scale * s.y);
         atomicAdd(gbias + 4 * q + 2, bias_scale * s.z); atomicAdd(gbias + 4 * q + 3, bias_scale * s.w);
       }
+    }
+  }
+}
+
+// Same contract for C4 <= blockDim, four rows per loop iteration: the eight 128-bit loads of an iteration are issued before
+// any of them is used, so a thread keeps 128 B in flight instead of 32 B (a streaming kernel with two inputs needs that
+// memory-level parallelism to approach the HBM roofline).
+__global__ void __launch_bounds__(TPB) act_bwd_u4_kernel(const float4* __restrict__ gy, const float4* __restrict__ y,
+                                                         float4* __restrict__ gx, float* __restrict__ gbias, int64_t P, int C4,
+                                                         float bias_scale, int act, float slope) {
+  extern __shared__ float4 red[];
+  constexpr int U = 4;
+  const int tid = threadIdx.x;
+  const int q = tid % C4, rl = tid / C4, rows_per_it = blockDim.x / C4;
+  const int64_t step = (int64_t)gridDim.x * rows_per_it;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t p0 = (int64_t)blockIdx.x * rows_per_it + rl; p0 < P; p0 += U * step) {
+    float4 g[U], yy[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * step;
+      if (p < P) {
+        g[u] = ldg_stream(gy + p * C4 + q);
+        if (y != nullptr) yy[u] = ldg_stream(y + p * C4 + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * step;
+      if (p < P) {
+        float4 o = g[u];
+        if (y != nullptr) {
+          o.x *= act_grad(yy[u].x, act, slope); o.y *= act_grad(yy[u].y, act, slope);
+          o.z *= act_grad(yy[u].z, act, slope); o.w *= act_grad(yy[u].w, act, slope);
+        }
+        if (gx != nullptr) stg_stream(gx + p * C4 + q, o);
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+    }
+  }
+  if (gbias != nullptr) {
+    red[tid] = s;
+    __syncthreads();
+    if (tid < C4) {
+      float4 t = red[tid];
+      for (int r = 1; r < rows_per_it; ++r) {
+        const float4 v = red[r * C4 + tid];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      atomicAdd(gbias + 4 * tid + 0, bias_scale * t.x); atomicAdd(gbias + 4 * tid + 1, bias_scale * t.y);
+      atomicAdd(gbias + 4 * tid + 2, bias_scale * t.z); atomicAdd(gbias + 4 * tid + 3, bias_scale * t.w);
     }
   }
 }
@@ -207,7 +270,7 @@ __global__ void pixelnorm_bwd_kernel(const float4* __restrict__ gy, const float4
 // Each thread produces one channel-quad of one pixel from its 3x3 neighbourhood; neighbouring threads
 // share rows through L1 (the 9 taps of adjacent pixels overlap 6/9), so DRAM traffic stays ~8 B/elem.
 // ------------------------------------------------------------------------------------------------
-__global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4) {
+__global__ void blur3x3_tap9_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4) {
   const int64_t total = (int64_t)N * H * W * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(i % C4);
@@ -230,6 +293,61 @@ __global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict_
       }
     }
     stg_stream(y + i, acc);
+  }
+}
+
+// Sliding-window version (default): a thread owns one channel quad of PW adjacent pixels and walks down TH rows keeping the
+// horizontal [1 2 1] sums of the previous two rows in registers, so every output costs (PW+2)/PW * (TH+2)/TH loads
+// (2.5 at PW=2, TH=8) instead of 9; the shared taps of neighbouring threads hit L1, halo rows of neighbouring tiles hit L2.
+template <int PW>
+__global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4, int TH) {
+  const int WG = (W + PW - 1) / PW, HT = (H + TH - 1) / TH;
+  const int64_t total = (int64_t)N * HT * WG * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4);
+    int64_t t = i / C4;
+    const int w0 = (int)(t % WG) * PW; t /= WG;
+    const int h0 = (int)(t % HT) * TH;
+    const int n = (int)(t / HT);
+    const int h1 = min(H, h0 + TH);
+    const float4* xn = x + (int64_t)n * H * W * C4 + q;
+    float4* yn = y + (int64_t)n * H * W * C4 + q;
+    float4 rm[PW], rc[PW], rn[PW];
+    auto hrow = [&](int hh, float4* r) {
+      if (hh < 0 || hh >= H) {
+#pragma unroll
+        for (int j = 0; j < PW; ++j) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+      }
+      const float4* row = xn + (int64_t)hh * W * C4;
+      float4 v[PW + 2];
+#pragma unroll
+      for (int k = 0; k < PW + 2; ++k) {
+        const int ww = w0 - 1 + k;
+        v[k] = (ww >= 0 && ww < W) ? __ldg(row + (int64_t)ww * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        r[j].x = v[j].x + 2.f * v[j + 1].x + v[j + 2].x; r[j].y = v[j].y + 2.f * v[j + 1].y + v[j + 2].y;
+        r[j].z = v[j].z + 2.f * v[j + 1].z + v[j + 2].z; r[j].w = v[j].w + 2.f * v[j + 1].w + v[j + 2].w;
+      }
+    };
+    hrow(h0 - 1, rm);
+    hrow(h0, rc);
+    for (int h = h0; h < h1; ++h) {
+      hrow(h + 1, rn);
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        if (w0 + j < W) {
+          float4 o;
+          o.x = 0.0625f * (rm[j].x + 2.f * rc[j].x + rn[j].x); o.y = 0.0625f * (rm[j].y + 2.f * rc[j].y + rn[j].y);
+          o.z = 0.0625f * (rm[j].z + 2.f * rc[j].z + rn[j].z); o.w = 0.0625f * (rm[j].w + 2.f * rc[j].w + rn[j].w);
+          stg_stream(yn + ((int64_t)h * W + w0 + j) * C4, o);
+        }
+        rm[j] = rc[j];
+        rc[j] = rn[j];
+      }
+    }
   }
 }
 
@@ -583,6 +701,17 @@ extern "C" int glb_act_bwd(const float* gy, const float* y, float* gx, float* gb
   REQ(C4 > TPB || TPB % C4 == 0, "act_bwd: C/4 must divide 256 or exceed it");
   const int rows_per_it = C4 <= TPB ? TPB / C4 : 1;
   int blocks = (int)((P + rows_per_it - 1) / rows_per_it);
+  if (C4 <= TPB && !(glue_variant() & 2)) {
+    blocks = (blocks + 3) / 4;                       // four rows per thread and iteration
+    // with a bias gradient every block ends in C atomics on the same C addresses: 2 blocks per SM keep that tail short
+    // (1184 blocks x 512 channels = 0.6 M serialised atomics took longer than the streaming pass itself)
+    const int cap = gbias != nullptr ? kNumSMs * 2 : kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    act_bwd_u4_kernel<<<blocks, TPB, TPB * sizeof(float4), (cudaStream_t)stream>>>(
+        (const float4*)gy, (const float4*)y, (float4*)gx, gbias, P, C4, bias_scale, act, slope);
+    GLB_CHECK_LAUNCH("act_bwd_u4");
+    return GLB_OK;
+  }
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   act_bwd_kernel<<<blocks, TPB, TPB * sizeof(float4), (cudaStream_t)stream>>>(
       (const float4*)gy, (const float4*)y, (float4*)gx, gbias, P, C4, bias_scale, act, slope);
@@ -649,8 +778,18 @@ extern "C" int glb_pixelnorm_bwd(const float* gy, const float* x, float* gx, int
 
 extern "C" int glb_blur3x3(const float* x, float* y, int N, int H, int W, int C, glb_stream_t stream) {
   REQ(C % 4 == 0, "blur3x3: C % 4 != 0");
-  const int64_t total = (int64_t)N * H * W * (C / 4);
-  blur3x3_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4);
+  const int C4 = C / 4;
+  if (glue_variant() & 1) {
+    const int64_t total = (int64_t)N * H * W * C4;
+    blur3x3_tap9_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C4);
+    GLB_CHECK_LAUNCH("blur3x3");
+    return GLB_OK;
+  }
+  constexpr int PW = 2;
+  int TH = 8;   // rows per thread: fewer for small maps so that the grid still fills the machine
+  while (TH > 1 && (int64_t)N * ((H + TH - 1) / TH) * ((W + PW - 1) / PW) * C4 < (int64_t)kNumSMs * 4 * TPB) TH >>= 1;
+  const int64_t threads = (int64_t)N * ((H + TH - 1) / TH) * ((W + PW - 1) / PW) * C4;
+  blur3x3_kernel<PW><<<grid_for(threads, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C4, TH);
   GLB_CHECK_LAUNCH("blur3x3");
   return GLB_OK;
 }

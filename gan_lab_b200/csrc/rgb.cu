@@ -14,44 +14,47 @@ constexpr int TPB = 256;
 __global__ void rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, int ws_j, int ws_c,
                                   const float* __restrict__ bias, float4* __restrict__ y, int N, int H, int W, int C4, int pool,
                                   float alpha, float bias_scale, int act, float slope) {
-  const int64_t total = (int64_t)N * H * W * C4;
-  const int IH = pool ? 2 * H : H, IW = pool ? 2 * W : W;
-  const int64_t plane = (int64_t)IH * IW;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % C4);
-    int64_t t = i / C4;
-    const int ww = (int)(t % W); t /= W;
-    const int hh = (int)(t % H);
-    const int64_t n = t / H;
-    float v[3];
+  // blockDim is a multiple of C4 (host), so a thread's channel quad is loop invariant: its 12 weights (alpha folded in) and 4
+  // biases live in registers; per output quad the loop then costs 3 broadcast image loads + 12 FMAs + one 128-bit store.
+  const int q = threadIdx.x % C4;
+  float wr[3][4], br[4];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float* p = img + (n * 3 + j) * plane;
-      if (pool) {
-        const int64_t o = (int64_t)(2 * hh) * IW + 2 * ww;
-        v[j] = 0.25f * (__ldg(p + o) + __ldg(p + o + 1) + __ldg(p + o + IW) + __ldg(p + o + IW + 1));
-      } else {
-        v[j] = __ldg(p + (int64_t)hh * IW + ww);
+  for (int k = 0; k < 4; ++k) {
+    const int c = 4 * q + k;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wr[j][k] = alpha * __ldg(w + j * ws_j + c * ws_c);
+    br[k] = bias != nullptr ? bias_scale * __ldg(bias + c) : 0.f;
+  }
+  const int ppb = blockDim.x / C4;                 // pixels per block and iteration
+  const int64_t P = (int64_t)N * H * W;
+  const int IH = pool ? 2 * H : H, IW = pool ? 2 * W : W;
+  const int64_t plane = (int64_t)IH * IW, HW = (int64_t)H * W;
+  for (int64_t p = (int64_t)blockIdx.x * ppb + threadIdx.x / C4; p < P; p += (int64_t)gridDim.x * ppb) {
+    const int64_t n = p / HW, r = p - n * HW;
+    float v[3];
+    if (pool) {
+      const int hh = (int)(r / W), ww = (int)(r - (int64_t)hh * W);
+      const int64_t o = (int64_t)(2 * hh) * IW + 2 * ww;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float* ip = img + (n * 3 + j) * plane;
+        v[j] = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[j] = __ldg(img + (n * 3 + j) * plane + r);
     }
     float o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = 4 * q + k;
-      float a = 0.f;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) a = fmaf(v[j], __ldg(w + j * ws_j + c * ws_c), a);
-      a *= alpha;
-      if (bias != nullptr) a += bias_scale * __ldg(bias + c);
-      o[k] = act_apply(a, act, slope);
-    }
-    stg_stream(y + i, make_float4(o[0], o[1], o[2], o[3]));
+    for (int k = 0; k < 4; ++k)
+      o[k] = act_apply(fmaf(v[0], wr[0][k], fmaf(v[1], wr[1][k], fmaf(v[2], wr[2][k], br[k]))), act, slope);
+    stg_stream(y + p * C4 + q, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
 
 // img[n,j,h,w] = alpha * sum_c x[n,h,w,c] * w(j,c) + bias_scale*bias[j]; GS lanes cooperate on one pixel.
 // pool: scatter 0.25*value into the 2x2 window of an image of twice the size (adjoint of the avg-pool).
-template <int GS>
+template <int GS, int QPL>   // QPL = quads per lane held in registers (0: read the weights through L1 every time)
 __global__ void rgb_contract_kernel(const float4* __restrict__ x, const float* __restrict__ w, int ws_j, int ws_c,
                                     const float* __restrict__ bias, float* __restrict__ img, int N, int H, int W, int C4, int pool,
                                     float alpha, float bias_scale) {
@@ -60,18 +63,46 @@ __global__ void rgb_contract_kernel(const float4* __restrict__ x, const float* _
   const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS, ngrp = ((int64_t)gridDim.x * blockDim.x) / GS;
   // P is padded up so every lane of a warp takes part in the shuffles
   const int64_t Ppad = ((P + (32 / GS) - 1) / (32 / GS)) * (32 / GS);
+  float wr[QPL > 0 ? QPL : 1][3][4];
+  if (QPL > 0) {
+#pragma unroll
+    for (int i = 0; i < QPL; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = 4 * (lane + i * GS) + k;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) wr[i][j][k] = (lane + i * GS < C4) ? __ldg(w + j * ws_j + c * ws_c) : 0.f;
+      }
+  }
   for (int64_t p = grp; p < Ppad; p += ngrp) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (p < P) {
-      for (int q = lane; q < C4; q += GS) {
-        const float4 v = ldg_stream(x + p * C4 + q);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+      if (QPL > 0) {
+        float4 v[QPL > 0 ? QPL : 1];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = 4 * q + k;
-          a0 = fmaf(vv[k], __ldg(w + 0 * ws_j + c * ws_c), a0);
-          a1 = fmaf(vv[k], __ldg(w + 1 * ws_j + c * ws_c), a1);
-          a2 = fmaf(vv[k], __ldg(w + 2 * ws_j + c * ws_c), a2);
+        for (int i = 0; i < QPL; ++i)
+          v[i] = (lane + i * GS < C4) ? ldg_stream(x + p * C4 + lane + i * GS) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < QPL; ++i) {
+          const float vv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            a0 = fmaf(vv[k], wr[i][0][k], a0);
+            a1 = fmaf(vv[k], wr[i][1][k], a1);
+            a2 = fmaf(vv[k], wr[i][2][k], a2);
+          }
+        }
+      } else {
+        for (int q = lane; q < C4; q += GS) {
+          const float4 v = ldg_stream(x + p * C4 + q);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = 4 * q + k;
+            a0 = fmaf(vv[k], __ldg(w + 0 * ws_j + c * ws_c), a0);
+            a1 = fmaf(vv[k], __ldg(w + 1 * ws_j + c * ws_c), a1);
+            a2 = fmaf(vv[k], __ldg(w + 2 * ws_j + c * ws_c), a2);
+          }
         }
       }
     }
@@ -187,9 +218,13 @@ using namespace glb;
 extern "C" int glb_rgb_expand(const float* img, const float* w, int ws_j, int ws_c, const float* bias, float* y, int N, int H,
                               int W, int C, int pool, float alpha, float bias_scale, int act, float slope, glb_stream_t stream) {
   REQ(C % 4 == 0, "rgb_expand: C % 4 != 0");
-  const int64_t total = (int64_t)N * H * W * (C / 4);
-  rgb_expand_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(img, w, ws_j, ws_c, bias, (float4*)y, N, H, W, C / 4,
-                                                                           pool, alpha, bias_scale, act, slope);
+  const int C4 = C / 4;
+  REQ(C4 <= 1024, "rgb_expand: C > 4096");
+  const int threads = C4 <= TPB ? (TPB / C4) * C4 : C4;            // a multiple of C4: the channel quad of a thread is fixed
+  const int64_t P = (int64_t)N * H * W;
+  const int ppb = threads / C4;
+  rgb_expand_kernel<<<grid_for((P + ppb - 1) / ppb, 1), threads, 0, (cudaStream_t)stream>>>(img, w, ws_j, ws_c, bias, (float4*)y, N, H, W,
+                                                                                          C4, pool, alpha, bias_scale, act, slope);
   GLB_CHECK_LAUNCH("rgb_expand");
   return GLB_OK;
 }
@@ -200,13 +235,19 @@ extern "C" int glb_rgb_contract(const float* x, const float* w, int ws_j, int ws
   const int C4 = C / 4;
   const int64_t P = (int64_t)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(GS)                                                                                                     \
-  rgb_contract_kernel<GS><<<grid_for(P * GS, TPB), TPB, 0, st>>>((const float4*)x, w, ws_j, ws_c, bias, img, N, H, W, C4, pool, \
-                                                                 alpha, bias_scale)
-  if (C4 >= 32) LAUNCH(32);
-  else if (C4 >= 16) LAUNCH(16);
-  else if (C4 >= 8) LAUNCH(8);
-  else LAUNCH(4);
+#define LAUNCH(GS, QPL)                                                                                                 \
+  rgb_contract_kernel<GS, QPL><<<grid_for(P * GS, TPB), TPB, 0, st>>>((const float4*)x, w, ws_j, ws_c, bias, img, N, H, W, C4,  \
+                                                                      pool, alpha, bias_scale)
+  if (C4 == 32) LAUNCH(32, 1);
+  else if (C4 == 64) LAUNCH(32, 2);
+  else if (C4 == 128) LAUNCH(32, 4);
+  else if (C4 > 32) LAUNCH(32, 0);
+  else if (C4 == 16) LAUNCH(16, 1);
+  else if (C4 >= 16) LAUNCH(16, 0);
+  else if (C4 == 8) LAUNCH(8, 1);
+  else if (C4 >= 8) LAUNCH(8, 0);
+  else if (C4 == 4) LAUNCH(4, 1);
+  else LAUNCH(4, 0);
 #undef LAUNCH
   GLB_CHECK_LAUNCH("rgb_contract");
   return GLB_OK;
@@ -220,7 +261,7 @@ extern "C" int glb_rgb_wgrad(const float* img, const float* g, float* gw, int ws
   const int lanes = C4 < TPB ? C4 : TPB, rows = TPB / lanes;
   const int64_t P = (int64_t)N * H * W;
   int blocks = (int)((P + rows - 1) / rows);
-  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;      // every block ends in 3*C atomics on the same addresses: keep them few
   rgb_wgrad_kernel<<<blocks, TPB, 3 * TPB * sizeof(float4), (cudaStream_t)stream>>>(img, (const float4*)g, gw, ws_j, ws_c, N, H, W, C4,
                                                                                    pool, alpha);
   GLB_CHECK_LAUNCH("rgb_wgrad");

@@ -17,6 +17,7 @@ namespace {
 
 constexpr int TPB = 256;
 constexpr int MAX_CHUNK = 256;  // pixels per block, upper bound
+constexpr int UNR = 4;          // rows a thread keeps in flight per loop iteration (memory-level parallelism)
 
 struct SE {
   int N, HW, C4, chunks, chunk;  // chunk = pixels per block (runtime: sized so that ~2 blocks land on every SM)
@@ -65,13 +66,27 @@ __global__ void __launch_bounds__(TPB) se_fwd_stats_kernel(const float4* __restr
     const int64_t px = (int64_t)n * g.HW + p0;
     k4 = lrelu4(pre_act(__ldg(x + px * g.C4 + q), noise ? __ldg(noise + px) : 0.f, w4, b4), g.slope);
   }
-  for (int p = p0 + rl; p < p1; p += rows) {
-    const int64_t px = (int64_t)n * g.HW + p;
-    const float nz = noise ? __ldg(noise + px) : 0.f;
-    float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
-    t.x -= k4.x; t.y -= k4.y; t.z -= k4.z; t.w -= k4.w;
-    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-    ss.x += t.x * t.x; ss.y += t.y * t.y; ss.z += t.z * t.z; ss.w += t.w * t.w;
+  for (int pb = p0 + rl; pb < p1; pb += UNR * rows) {      // UNR rows in flight per thread
+    float4 xv[UNR];
+    float nz[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = pb + u * rows;
+      if (p < p1) {
+        const int64_t px = (int64_t)n * g.HW + p;
+        xv[u] = __ldg(x + px * g.C4 + q);
+        nz[u] = noise ? __ldg(noise + px) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (pb + u * rows < p1) {
+        float4 t = lrelu4(pre_act(xv[u], nz[u], w4, b4), g.slope);
+        t.x -= k4.x; t.y -= k4.y; t.z -= k4.z; t.w -= k4.w;
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        ss.x += t.x * t.x; ss.y += t.y * t.y; ss.z += t.z * t.z; ss.w += t.w * t.w;
+      }
+    }
   }
   block_rows_reduce(s, ss, red, g.C4, rows);
   if (tid < g.C4) {
@@ -136,12 +151,28 @@ __global__ void __launch_bounds__(TPB) se_fwd_apply_kernel(const float4* __restr
   const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
   const float4 ys = __ldg(style + (int64_t)n * 2 * g.C4 + q), yb = __ldg(style + ((int64_t)n * 2 + 1) * g.C4 + q);
   const float4 sc = make_float4(rs.x * (ys.x + 1.f), rs.y * (ys.y + 1.f), rs.z * (ys.z + 1.f), rs.w * (ys.w + 1.f));
-  for (int p = p0 + rl; p < p1; p += rows) {
-    const int64_t px = (int64_t)n * g.HW + p;
-    const float nz = noise ? __ldg(noise + px) : 0.f;
-    const float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
-    stg_stream(out + px * g.C4 + q, make_float4((t.x - mu.x) * sc.x + yb.x, (t.y - mu.y) * sc.y + yb.y,
-                                                (t.z - mu.z) * sc.z + yb.z, (t.w - mu.w) * sc.w + yb.w));
+  for (int pb = p0 + rl; pb < p1; pb += UNR * rows) {
+    float4 xv[UNR];
+    float nz[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = pb + u * rows;
+      if (p < p1) {
+        const int64_t px = (int64_t)n * g.HW + p;
+        xv[u] = ldg_stream(x + px * g.C4 + q);
+        nz[u] = noise ? __ldg(noise + px) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = pb + u * rows;
+      if (p < p1) {
+        const int64_t px = (int64_t)n * g.HW + p;
+        const float4 t = lrelu4(pre_act(xv[u], nz[u], w4, b4), g.slope);
+        stg_stream(out + px * g.C4 + q, make_float4((t.x - mu.x) * sc.x + yb.x, (t.y - mu.y) * sc.y + yb.y,
+                                                    (t.z - mu.z) * sc.z + yb.z, (t.w - mu.w) * sc.w + yb.w));
+      }
+    }
   }
 }
 
@@ -158,14 +189,29 @@ __global__ void __launch_bounds__(TPB) se_bwd_stats_kernel(const float4* __restr
   const float4 b4 = bias ? __ldg(bias + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 mu = __ldg(stats + (int64_t)n * 2 * g.C4 + q), rs = __ldg(stats + ((int64_t)n * 2 + 1) * g.C4 + q);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  for (int p = p0 + rl; p < p1; p += rows) {
-    const int64_t px = (int64_t)n * g.HW + p;
-    const float nz = noise ? __ldg(noise + px) : 0.f;
-    const float4 t = lrelu4(pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4), g.slope);
-    const float4 go = __ldg(gout + px * g.C4 + q);
-    s1.x += go.x; s1.y += go.y; s1.z += go.z; s1.w += go.w;
-    s2.x += go.x * (t.x - mu.x) * rs.x; s2.y += go.y * (t.y - mu.y) * rs.y;
-    s2.z += go.z * (t.z - mu.z) * rs.z; s2.w += go.w * (t.w - mu.w) * rs.w;
+  for (int pb = p0 + rl; pb < p1; pb += UNR * rows) {
+    float4 xv[UNR], gv[UNR];
+    float nz[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = pb + u * rows;
+      if (p < p1) {
+        const int64_t px = (int64_t)n * g.HW + p;
+        xv[u] = __ldg(x + px * g.C4 + q);
+        gv[u] = __ldg(gout + px * g.C4 + q);
+        nz[u] = noise ? __ldg(noise + px) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (pb + u * rows < p1) {
+        const float4 t = lrelu4(pre_act(xv[u], nz[u], w4, b4), g.slope);
+        const float4 go = gv[u];
+        s1.x += go.x; s1.y += go.y; s1.z += go.z; s1.w += go.w;
+        s2.x += go.x * (t.x - mu.x) * rs.x; s2.y += go.y * (t.y - mu.y) * rs.y;
+        s2.z += go.z * (t.z - mu.z) * rs.z; s2.w += go.w * (t.w - mu.w) * rs.w;
+      }
+    }
   }
   block_rows_reduce(s1, s2, red, g.C4, rows);
   if (tid < g.C4) {
@@ -220,20 +266,38 @@ __global__ void __launch_bounds__(TPB) se_bwd_apply_kernel(const float4* __restr
   const float4 m1 = __ldg(means + (int64_t)n * 2 * g.C4 + q), m2 = __ldg(means + ((int64_t)n * 2 + 1) * g.C4 + q);
   const float4 sc = make_float4(ys.x + 1.f, ys.y + 1.f, ys.z + 1.f, ys.w + 1.f);
   float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sn = sb;
-  for (int p = p0 + rl; p < p1; p += rows) {
-    const int64_t px = (int64_t)n * g.HW + p;
-    const float nz = noise ? __ldg(noise + px) : 0.f;
-    const float4 u = pre_act(__ldg(x + px * g.C4 + q), nz, w4, b4);
-    const float4 t = lrelu4(u, g.slope);
-    const float4 go = ldg_stream(gout + px * g.C4 + q);
-    float4 gu;
-    gu.x = rs.x * (sc.x * go.x - m1.x - (t.x - mu.x) * rs.x * m2.x) * (u.x > 0.f ? 1.f : g.slope);
-    gu.y = rs.y * (sc.y * go.y - m1.y - (t.y - mu.y) * rs.y * m2.y) * (u.y > 0.f ? 1.f : g.slope);
-    gu.z = rs.z * (sc.z * go.z - m1.z - (t.z - mu.z) * rs.z * m2.z) * (u.z > 0.f ? 1.f : g.slope);
-    gu.w = rs.w * (sc.w * go.w - m1.w - (t.w - mu.w) * rs.w * m2.w) * (u.w > 0.f ? 1.f : g.slope);
-    stg_stream(gx + px * g.C4 + q, gu);
-    sb.x += gu.x; sb.y += gu.y; sb.z += gu.z; sb.w += gu.w;
-    sn.x += gu.x * nz; sn.y += gu.y * nz; sn.z += gu.z * nz; sn.w += gu.w * nz;
+  for (int pb = p0 + rl; pb < p1; pb += UNR * rows) {
+    float4 xv[UNR], gv[UNR];
+    float nzv[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int p = pb + k * rows;
+      if (p < p1) {
+        const int64_t px = (int64_t)n * g.HW + p;
+        xv[k] = ldg_stream(x + px * g.C4 + q);
+        gv[k] = ldg_stream(gout + px * g.C4 + q);
+        nzv[k] = noise ? __ldg(noise + px) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int p = pb + k * rows;
+      if (p < p1) {
+        const int64_t px = (int64_t)n * g.HW + p;
+        const float nz = nzv[k];
+        const float4 u = pre_act(xv[k], nz, w4, b4);
+        const float4 t = lrelu4(u, g.slope);
+        const float4 go = gv[k];
+        float4 gu;
+        gu.x = rs.x * (sc.x * go.x - m1.x - (t.x - mu.x) * rs.x * m2.x) * (u.x > 0.f ? 1.f : g.slope);
+        gu.y = rs.y * (sc.y * go.y - m1.y - (t.y - mu.y) * rs.y * m2.y) * (u.y > 0.f ? 1.f : g.slope);
+        gu.z = rs.z * (sc.z * go.z - m1.z - (t.z - mu.z) * rs.z * m2.z) * (u.z > 0.f ? 1.f : g.slope);
+        gu.w = rs.w * (sc.w * go.w - m1.w - (t.w - mu.w) * rs.w * m2.w) * (u.w > 0.f ? 1.f : g.slope);
+        stg_stream(gx + px * g.C4 + q, gu);
+        sb.x += gu.x; sb.y += gu.y; sb.z += gu.z; sb.w += gu.w;
+        sn.x += gu.x * nz; sn.y += gu.y * nz; sn.z += gu.z * nz; sn.w += gu.w * nz;
+      }
+    }
   }
   block_rows_reduce(sb, sn, red, g.C4, rows);
   if (tid < g.C4) {
@@ -248,11 +312,12 @@ __global__ void __launch_bounds__(TPB) se_bwd_apply_kernel(const float4* __restr
   }
 }
 
-// pixels per block: aim at ~2 blocks per SM over the whole (N, HW) range, a multiple of the rows a block covers per
-// iteration, at most MAX_CHUNK (low-resolution layers otherwise run on 8 blocks)
+// pixels per block: aim at ~8 blocks of 256 threads per SM over the whole (N, HW) range (full occupancy; with UNR rows in
+// flight per thread that is what a two-input streaming pass needs to approach the HBM roofline), a multiple of the rows a
+// block covers per iteration, at most MAX_CHUNK (low-resolution layers otherwise run on 8 blocks)
 int se_chunk(int N, int HW, int C) {
   const int rows = TPB / (C / 4) > 0 ? TPB / (C / 4) : 1;
-  int64_t chunk = ((int64_t)N * HW + 2 * kNumSMs - 1) / (2 * kNumSMs);
+  int64_t chunk = ((int64_t)N * HW + 8 * kNumSMs - 1) / (8 * kNumSMs);
   chunk = ((chunk + rows - 1) / rows) * rows;
   if (chunk > MAX_CHUNK) chunk = MAX_CHUNK;
   if (chunk < rows) chunk = rows;

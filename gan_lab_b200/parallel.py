@@ -8,13 +8,12 @@ rank, so averaging the per-rank gradients reproduces the single-GPU gradient of 
 optimiser step; parameters, Adam state and the EWMA generator are replicated.
 
 Overlap with backward: every parameter carries a post-accumulate-grad hook; as soon as the gradients that have become
-ready fill a bucket (default 32 MiB, in autograd order: last layers first) the bucket is packed (one `torch.cat` into a
-persistent flat buffer), pre-scaled by 1/world and all-reduced asynchronously -- NCCL runs on the process group's own
-stream while the compute stream keeps executing the rest of backward (including the R1 double-backward tail).
-`allreduce_grads()` after backward only flushes the last partial bucket, makes the compute stream wait for the
-collectives and re-points each `p.grad` at its slice of the reduced bucket (no copy back; the fused Adam reads the
-gradients through pointers).  All of this is stream-ordered, so it is captured into the step's CUDA graph as parallel
-branches.  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
+ready fill a bucket (default 32 MiB, in autograd order: last layers first) the bucket is packed (one `torch.cat`),
+pre-scaled by 1/world and all-reduced asynchronously -- NCCL runs on the process group's own stream while the compute
+stream keeps executing the rest of backward (including the R1 double-backward tail).  `allreduce_grads()` after backward
+only flushes the last partial bucket, makes the compute stream wait for the collectives and scatters the reduced buckets
+back into the gradients (one multi-tensor copy per bucket).  All of this is stream-ordered, so it is captured into the
+step's CUDA graph as parallel branches.  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
 """
 import torch
 import torch.distributed as dist
@@ -34,7 +33,6 @@ class DataParallel(object):
         self._pending = []          # parameters whose gradient is ready but not yet in a bucket
         self._pending_bytes = 0
         self._inflight = []         # (work, flat bucket, parameters)
-        self._bufs = {}             # (bucket index, size, device) -> persistent flat buffer (stable addresses across replays)
 
     def broadcast_params(self, module, src=0):
         with torch.no_grad():
@@ -68,12 +66,7 @@ class DataParallel(object):
         ps, self._pending, self._pending_bytes = self._pending, [], 0
         if not ps:
             return
-        n = sum(p.numel() for p in ps)
-        key = (len(self._inflight), n, ps[0].device)
-        flat = self._bufs.get(key)
-        if flat is None:
-            flat = self._bufs[key] = torch.empty(n, dtype=ps[0].dtype, device=ps[0].device)
-        torch.cat([_flat_view(p.grad) for p in ps], out=flat)
+        flat = torch.cat([_flat_view(p.grad) for p in ps])
         flat.mul_(1.0 / self.world)
         self._inflight.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, ps))
 
@@ -90,10 +83,7 @@ class DataParallel(object):
         with torch.no_grad():
             for work, flat, ps in self._inflight:
                 work.wait()
-                off = 0
-                for p in ps:
-                    p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
-                    off += p.numel()
+                torch._foreach_copy_([_flat_view(p.grad) for p in ps], list(flat.split([p.numel() for p in ps])))
         self._inflight = []
         self.attach(module)                                  # from the next backward on, buckets launch from the hooks
 

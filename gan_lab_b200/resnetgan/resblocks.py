@@ -8,7 +8,7 @@ a Batch/LayerNorm (or a convolution) into the producing kernel; the residual sum
 from torch import nn
 
 from .. import ops
-from ..utils.custom_layers import (Lambda, get_blur_op, NormalizeLayer, Conv2dEx, LeakyReLU, as_native_nl,
+from ..utils.custom_layers import (Lambda, get_blur_op, NormalizeLayer, Conv2dEx, LeakyReLU, AvgPool2x, as_native_nl,
                                    as_native_upsampler, as_native_pooler)
 
 
@@ -20,7 +20,13 @@ def run_fused(seq, x):
         m = mods[i]
         nxt = mods[i + 1] if i + 1 < len(mods) else None
         fuse = isinstance(nxt, LeakyReLU) and ((isinstance(m, NormalizeLayer) and m.fuses_act) or isinstance(m, Conv2dEx))
-        if fuse:
+        if (isinstance(m, AvgPool2x) and isinstance(nxt, Conv2dEx) and nxt.ks == 1 and nxt.ni == 3 and nxt.nf % 4 == 0
+                and x.shape[1] == 3):
+            # avg-pool of the 3-channel image + 1x1 conv (FastResBlock2dDownsample's skip branch): one fromRGB kernel
+            x = ops.fromrgb(x, nxt.conv2d.weight, nxt.conv2d.bias, nxt.alpha, nxt.lrmul if nxt.use_lrmul else 1.,
+                            ops.ACT_NONE, 0.0, pool=True)
+            i += 2
+        elif fuse:
             x = m(x, act=ops.ACT_LRELU, slope=nxt.negative_slope)
             i += 2
         else:
