@@ -106,6 +106,29 @@ def test_conv_family_tf32_vs_contract(shape):
         K.set_conv_impl("fp32")
 
 
+@pytest.mark.parametrize("shape", [(8, 4, 4, 513, 512, 3, 1), (4, 4, 4, 257, 128, 3, 1)])
+def test_conv_ragged_channels_take_the_tensor_core_path(shape):
+    """Ci = 513 (behind the minibatch-stddev concat) is zero-padded to a multiple of 128 by the launchers and runs on the
+    tcgen05 kernels; results (incl. the sliced dgrad / wgrad) must equal the contract of the UNPADDED convolution."""
+    N, H, W, Ci, Co, R, pad = shape
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, R, R, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, H, W, seed=3))
+    K.set_conv_impl("tf32")
+    try:
+        assert not K.tc_covers("fprop", N, H, W, Ci, Co, R, R, pad)
+        assert K._pad_ci("fprop", N, H, W, Ci, Co, R, R, pad) == (Ci + 127) // 128 * 128
+        y, = both("conv_fprop", x, w, b, pad, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_TF32)
+        gx, = both("conv_dgrad", gy, w, (H, W), pad, 0.37, tol=TOL_TF32)
+        gw, = both("conv_wgrad", x, gy, (R, R), pad, 0.37, tol=TOL_TF32)
+        assert gx.shape[1] == Ci and gw.shape[1] == Ci and gw.is_contiguous(memory_format=torch.channels_last)
+        wd = w.to(DEV)
+        a = K.conv_fprop(x.to(DEV), wd, None, pad, 1.0, 1.0, K.ACT_NONE, 0.0)
+        wd.mul_(2.0)                                   # the cached padded copy must follow in-place weight updates
+        assert rel(K.conv_fprop(x.to(DEV), wd, None, pad, 1.0, 1.0, K.ACT_NONE, 0.0), a * 2) < 1e-6
+    finally:
+        K.set_conv_impl("fp32")
+
+
 def test_tf32_dgrad_sees_weight_updates():
     """The tensor-core dgrad multiplies by a cached re-layout of the weight: an in-place update must invalidate it."""
     K.set_conv_impl("tf32")
