@@ -129,8 +129,8 @@ def _pad_ci(kind, N, H, W, Ci, Co, R, S, pad):
 
 def _pad_channels(t, cip):
     """[N,C,H,W] channels-last -> [N,cip,H,W] channels-last, zero filled beyond C."""
-    out = torch.zeros((t.shape[0], cip, t.shape[2], t.shape[3]), device=t.device, dtype=t.dtype,
-                      memory_format=torch.channels_last)
+    out = torch.empty((t.shape[0], cip, t.shape[2], t.shape[3]), device=t.device, dtype=t.dtype,
+                      memory_format=torch.channels_last).zero_()
     out[:, :t.shape[1]].copy_(t)
     return out
 

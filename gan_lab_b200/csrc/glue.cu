@@ -1,9 +1,12 @@
 // Bandwidth-bound "glue" kernels of the G/D training step: fused, 128-bit vectorised, coalesced (NHWC: the
 // channel axis is the contiguous one), warp-shuffle / shared-memory reductions.  Each kernel names the ATen
 // call sites of the reference it replaces; roofline = HBM bandwidth.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace glb {
 namespace {
@@ -562,10 +565,13 @@ __global__ void w_ewma_kernel(const float* __restrict__ w, float* __restrict__ e
 }
 
 // ------------------------------------------------------------------------------------------------
-// minibatch stddev (reference utils/custom_layers.py:117-140); one block per group of `G` samples.
-// location index l runs over D = H*W*C positions of one sample (NHWC order).
+// minibatch stddev (reference utils/custom_layers.py:117-140).  One thread-block CLUSTER of MB_CL CTAs per group of `G`
+// samples: each CTA owns a slice of the D = H*W*C positions (NHWC order) of the group, the group-wide scalars (the stddev
+// average, the second-order term T) are folded across the cluster through distributed shared memory, then every CTA
+// writes its slice of the output.  (One CTA per group -- two CTAs for the whole cfg2 batch -- took 30-45 us per launch.)
 // ------------------------------------------------------------------------------------------------
 constexpr int MB_MAXG = 32;
+constexpr int MB_CL = 8;          // portable cluster size
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -580,14 +586,27 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__global__ void mbstd_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C, int G) {
+// sum of this CTA's value over the cluster (every CTA gets the total); `slot` is a shared-memory float of the caller
+__device__ __forceinline__ float cluster_sum(float v, float* slot) {
+  cg::cluster_group cluster = cg::this_cluster();
+  if (threadIdx.x == 0) *slot = v;
+  cluster.sync();
+  float tot = 0.f;
+  for (unsigned r = 0; r < cluster.num_blocks(); ++r) tot += *cluster.map_shared_rank(slot, r);
+  cluster.sync();                      // nobody leaves (or overwrites its slot) while a peer may still read it
+  return tot;
+}
+
+__global__ void __cluster_dims__(MB_CL, 1, 1) mbstd_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C,
+                                                               int G) {
   __shared__ float red[32];
-  const int g = blockIdx.x;
+  __shared__ float slot;
+  const int g = blockIdx.x / MB_CL, rank = blockIdx.x % MB_CL;
   const int64_t D = (int64_t)HW * C;
   const float* xg = x + (int64_t)g * G * D;
   float s = 0.f;
   if (G > 1) {
-    for (int64_t l = threadIdx.x; l < D; l += blockDim.x) {
+    for (int64_t l = (int64_t)rank * blockDim.x + threadIdx.x; l < D; l += (int64_t)MB_CL * blockDim.x) {
       float mu = 0.f;
       for (int j = 0; j < G; ++j) mu += xg[j * D + l];
       mu /= (float)G;
@@ -595,21 +614,23 @@ __global__ void mbstd_fwd_kernel(const float* __restrict__ x, float* __restrict_
       for (int j = 0; j < G; ++j) { const float d = xg[j * D + l] - mu; ss += d * d; }
       s += sqrtf(ss / (float)(G - 1) + 1e-8f);
     }
-    s = block_sum(s, red) / (float)D;
+    s = block_sum(s, red);
   }
+  s = cluster_sum(s, &slot) / (float)D;
   float* yg = y + (int64_t)g * G * HW * (C + 1);
   const int64_t tot = (int64_t)G * HW * (C + 1);
-  for (int64_t i = threadIdx.x; i < tot; i += blockDim.x) {
+  for (int64_t i = (int64_t)rank * blockDim.x + threadIdx.x; i < tot; i += (int64_t)MB_CL * blockDim.x) {
     const int c = (int)(i % (C + 1));
     const int64_t px = i / (C + 1);
     yg[i] = (c < C) ? xg[px * C + c] : s;
   }
 }
 
+// no group-wide reduction beyond gsd = sum of the G*HW stddev-channel cotangents, which every CTA recomputes: plain grid
 __global__ void mbstd_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, float* __restrict__ gx, int HW, int C,
                                  int G) {
   __shared__ float red[32];
-  const int g = blockIdx.x;
+  const int g = blockIdx.x / MB_CL, rank = blockIdx.x % MB_CL;
   const int64_t D = (int64_t)HW * C;
   const float* xg = x + (int64_t)g * G * D;
   const float* gyg = gy + (int64_t)g * G * HW * (C + 1);
@@ -620,7 +641,7 @@ __global__ void mbstd_bwd_kernel(const float* __restrict__ gy, const float* __re
     gsd = block_sum(gsd, red);
   }
   const float a = (G > 1) ? gsd / ((float)(G - 1) * (float)D) : 0.f;
-  for (int64_t l = threadIdx.x; l < D; l += blockDim.x) {
+  for (int64_t l = (int64_t)rank * blockDim.x + threadIdx.x; l < D; l += (int64_t)MB_CL * blockDim.x) {
     const int64_t px = l / C;
     const int c = (int)(l % C);
     float xv[MB_MAXG];
@@ -636,10 +657,12 @@ __global__ void mbstd_bwd_kernel(const float* __restrict__ gy, const float* __re
 }
 
 // double backward: inputs v (cotangent of gx), gy, x  ->  ggx (wrt x), ggy (wrt gy)
-__global__ void mbstd_bwdbwd_kernel(const float* __restrict__ v, const float* __restrict__ gy, const float* __restrict__ x,
-                                    float* __restrict__ ggx, float* __restrict__ ggy, int HW, int C, int G) {
+__global__ void __cluster_dims__(MB_CL, 1, 1) mbstd_bwdbwd_kernel(const float* __restrict__ v, const float* __restrict__ gy,
+                                                                  const float* __restrict__ x, float* __restrict__ ggx,
+                                                                  float* __restrict__ ggy, int HW, int C, int G) {
   __shared__ float red[32];
-  const int g = blockIdx.x;
+  __shared__ float slot;
+  const int g = blockIdx.x / MB_CL, rank = blockIdx.x % MB_CL;
   const int64_t D = (int64_t)HW * C;
   const float* xg = x + (int64_t)g * G * D;
   const float* vg = v + (int64_t)g * G * D;
@@ -652,7 +675,7 @@ __global__ void mbstd_bwdbwd_kernel(const float* __restrict__ v, const float* __
     for (int64_t px = threadIdx.x; px < (int64_t)G * HW; px += blockDim.x) gsd += gyg[px * (C + 1) + C];
     gsd = block_sum(gsd, red);
   }
-  for (int64_t l = threadIdx.x; l < D; l += blockDim.x) {
+  for (int64_t l = (int64_t)rank * blockDim.x + threadIdx.x; l < D; l += (int64_t)MB_CL * blockDim.x) {
     float d[MB_MAXG], vv[MB_MAXG];
     float mu = 0.f, vbar = 0.f;
     for (int j = 0; j < G; ++j) { d[j] = xg[j * D + l]; vv[j] = vg[j * D + l]; mu += d[j]; vbar += vv[j]; }
@@ -668,9 +691,9 @@ __global__ void mbstd_bwdbwd_kernel(const float* __restrict__ v, const float* __
       for (int j = 0; j < G; ++j) ggxg[j * D + l] = 0.f;
     }
   }
-  T = block_sum(T, red);
+  T = cluster_sum(block_sum(T, red), &slot);
   const int64_t tot = (int64_t)G * HW * (C + 1);
-  for (int64_t i = threadIdx.x; i < tot; i += blockDim.x) {
+  for (int64_t i = (int64_t)rank * blockDim.x + threadIdx.x; i < tot; i += (int64_t)MB_CL * blockDim.x) {
     const int c = (int)(i % (C + 1));
     const int64_t px = i / (C + 1);
     ggyg[i] = (c < C) ? vg[px * C + c] : T;
@@ -887,14 +910,14 @@ extern "C" int glb_w_ewma(const float* w, float* ewma, int M, int K, float beta,
 
 extern "C" int glb_mbstd_fwd(const float* x, float* y, int N, int H, int W, int C, int group, glb_stream_t stream) {
   REQ(group >= 1 && group <= MB_MAXG && N % group == 0, "mbstd: group must divide N and be <= 32");
-  mbstd_fwd_kernel<<<N / group, 512, 0, (cudaStream_t)stream>>>(x, y, H * W, C, group);
+  mbstd_fwd_kernel<<<(N / group) * MB_CL, 256, 0, (cudaStream_t)stream>>>(x, y, H * W, C, group);
   GLB_CHECK_LAUNCH("mbstd_fwd");
   return GLB_OK;
 }
 
 extern "C" int glb_mbstd_bwd(const float* gy, const float* x, float* gx, int N, int H, int W, int C, int group, glb_stream_t stream) {
   REQ(group >= 1 && group <= MB_MAXG && N % group == 0, "mbstd: group must divide N and be <= 32");
-  mbstd_bwd_kernel<<<N / group, 512, 0, (cudaStream_t)stream>>>(gy, x, gx, H * W, C, group);
+  mbstd_bwd_kernel<<<(N / group) * MB_CL, 256, 0, (cudaStream_t)stream>>>(gy, x, gx, H * W, C, group);
   GLB_CHECK_LAUNCH("mbstd_bwd");
   return GLB_OK;
 }
@@ -902,7 +925,7 @@ extern "C" int glb_mbstd_bwd(const float* gy, const float* x, float* gx, int N, 
 extern "C" int glb_mbstd_bwdbwd(const float* v, const float* gy, const float* x, float* ggx, float* ggy, int N, int H, int W, int C,
                                 int group, glb_stream_t stream) {
   REQ(group >= 1 && group <= MB_MAXG && N % group == 0, "mbstd: group must divide N and be <= 32");
-  mbstd_bwdbwd_kernel<<<N / group, 512, 0, (cudaStream_t)stream>>>(v, gy, x, ggx, ggy, H * W, C, group);
+  mbstd_bwdbwd_kernel<<<(N / group) * MB_CL, 256, 0, (cudaStream_t)stream>>>(v, gy, x, ggx, ggy, H * W, C, group);
   GLB_CHECK_LAUNCH("mbstd_bwdbwd");
   return GLB_OK;
 }

@@ -34,13 +34,22 @@ __global__ void __launch_bounds__(256) linear_fwd_small_kernel(const float* __re
 #pragma unroll
   for (int m = 0; m < MB; ++m) acc[m] = 0.f;
   const float* wr = w + (int64_t)n * K;
-  for (int k = lane * 4; k < K; k += 128) {
-    const float4 wv = ldg_stream(reinterpret_cast<const float4*>(wr + k));
+  for (int k0 = lane * 4; k0 < K; k0 += 4 * 128) {       // four weight quads in flight per lane
+    float4 wv[4];
 #pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      if (m < M) {
-        const float4 xv = *reinterpret_cast<const float4*>(xs + m * K + k);
-        acc[m] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[m]))));
+    for (int u = 0; u < 4; ++u)
+      if (k0 + u * 128 < K) wv[u] = ldg_stream(reinterpret_cast<const float4*>(wr + k0 + u * 128));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * 128;
+      if (k < K) {
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+          if (m < M) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + m * K + k);
+            acc[m] = fmaf(xv.x, wv[u].x, fmaf(xv.y, wv[u].y, fmaf(xv.z, wv[u].z, fmaf(xv.w, wv[u].w, acc[m]))));
+          }
+        }
       }
     }
   }
@@ -71,14 +80,22 @@ __global__ void __launch_bounds__(128) linear_dgrad_small_kernel(const float* __
   float4 acc[MB];
 #pragma unroll
   for (int m = 0; m < MB; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = 0; j < nn; ++j) {
-    const float4 wv = ldg_stream(reinterpret_cast<const float4*>(w + (int64_t)(n0 + j) * K + k));
+  for (int j0 = 0; j0 < nn; j0 += 8) {                    // eight weight rows in flight per thread
+    float4 wv[8];
 #pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      if (m < M) {
-        const float g = gs[j * M + m];
-        acc[m].x = fmaf(g, wv.x, acc[m].x); acc[m].y = fmaf(g, wv.y, acc[m].y);
-        acc[m].z = fmaf(g, wv.z, acc[m].z); acc[m].w = fmaf(g, wv.w, acc[m].w);
+    for (int u = 0; u < 8; ++u)
+      if (j0 + u < nn) wv[u] = ldg_stream(reinterpret_cast<const float4*>(w + (int64_t)(n0 + j0 + u) * K + k));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (j0 + u < nn) {
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+          if (m < M) {
+            const float g = gs[(j0 + u) * M + m];
+            acc[m].x = fmaf(g, wv[u].x, acc[m].x); acc[m].y = fmaf(g, wv[u].y, acc[m].y);
+            acc[m].z = fmaf(g, wv[u].z, acc[m].z); acc[m].w = fmaf(g, wv[u].w, acc[m].w);
+          }
+        }
       }
     }
   }
@@ -136,7 +153,7 @@ extern "C" int glb_linear_fwd(const float* x, const float* w, const float* bias,
   if (M <= 0 || K <= 0 || Nout <= 0) return shape_fail("linear_fwd");
   cudaStream_t st = (cudaStream_t)stream;
   if (!small_ok(M, K)) return conv_fprop_simt(x, w, bias, y, M, 1, 1, K, Nout, 1, 1, 0, alpha, bias_scale, act, slope, st);
-  const int warps = 8;
+  const int warps = Nout >= 4096 ? 8 : 4;           // >= 128 blocks for the 512-wide layers (mapping net, style affines)
   const dim3 grid((Nout + warps - 1) / warps);
   const size_t smem = sizeof(float) * (size_t)M * K;
   if (M <= 8)

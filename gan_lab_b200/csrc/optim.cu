@@ -29,17 +29,41 @@ __global__ void adam_ewma_kernel(const void* const* __restrict__ ptrs, const int
       }
     return;
   }
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    float gi = g[i];
-    float pi = p[i];
+  auto upd = [&](float gi, float& pi, float& mi, float& vi) {
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    float mi = m[i], vi = v[i];
     mi = (1.f - b1 >= 0.5f) ? gi - (gi - mi) * b1 : mi + (gi - mi) * (1.f - b1);   // torch lerp_ formula
     vi = vi * b2 + (1.f - b2) * gi * gi;
     const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
     pi = pi - step_size * (mi / denom);
+  };
+  const bool with_lag = ewma_mode != 0 && lag != nullptr;
+  // 128-bit path when every stream of this tensor is 16-byte aligned (always the case for torch allocations)
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)lag)) & 15) == 0;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    float4* p4 = (float4*)p; const float4* g4 = (const float4*)g; float4* m4 = (float4*)m; float4* v4 = (float4*)v;
+    float4* l4 = (float4*)lag;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 gv = ldg_stream(g4 + i);
+      float4 pv = p4[i], mv = m4[i], vv = v4[i];
+      float4 lv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (with_lag && ewma_mode != 2) lv = l4[i];
+      upd(gv.x, pv.x, mv.x, vv.x); upd(gv.y, pv.y, mv.y, vv.y); upd(gv.z, pv.z, mv.z, vv.z); upd(gv.w, pv.w, mv.w, vv.w);
+      p4[i] = pv; m4[i] = mv; v4[i] = vv;
+      if (with_lag) {
+        if (ewma_mode == 2) lv = pv;
+        l4[i] = make_float4(pv.x * (1.f - eb) + lv.x * eb, pv.y * (1.f - eb) + lv.y * eb, pv.z * (1.f - eb) + lv.z * eb,
+                            pv.w * (1.f - eb) + lv.w * eb);
+      }
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(g[i], pi, mi, vi);
     p[i] = pi; m[i] = mi; v[i] = vi;
-    if (ewma_mode != 0 && lag != nullptr) {
+    if (with_lag) {
       const float prev = (ewma_mode == 2) ? pi : lag[i];
       lag[i] = pi * (1.f - eb) + prev * eb;
     }
@@ -71,9 +95,9 @@ extern "C" int glb_adam_ewma_multi(const void* const* ptrs, const int64_t* sizes
                                    glb_stream_t stream) {
   if (T <= 0) return GLB_OK;
   if (T > 65535) return glb::shape_fail("adam: more than 65535 tensors");
-  int bx = (int)((max_size + 256 * 4 - 1) / (256 * 4));
+  int bx = (int)((max_size + 256 * 16 - 1) / (256 * 16));   // >= 4 float4 per thread for the largest tensor
   if (bx < 1) bx = 1;
-  if (bx > 64) bx = 64;
+  if (bx > 96) bx = 96;
   dim3 grid(bx, T);
   glb::adam_ewma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ptrs, sizes, hyper, beta1, beta2, eps, wd, ewma_beta, ewma_mode);
   GLB_CHECK_LAUNCH("adam_ewma_kernel");

@@ -138,30 +138,37 @@ __global__ void rgb_wgrad_kernel(const float* __restrict__ img, const float4* __
   extern __shared__ float4 red[];  // 3 * blockDim
   const int tid = threadIdx.x;
   const int lanes = min(C4, (int)blockDim.x), rows = blockDim.x / lanes, rl = tid / lanes;
-  const int64_t P = (int64_t)N * H * W;
   const int IH = pool ? 2 * H : H, IW = pool ? 2 * W : W;
   const int64_t plane = (int64_t)IH * IW;
+  const int HW = H * W;
   for (int q = tid % lanes; q < C4; q += lanes) {
     float4 s[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t p = (int64_t)blockIdx.x * rows + rl; p < P; p += (int64_t)gridDim.x * rows) {
-      const int ww = (int)(p % W);
-      int64_t t = p / W;
-      const int hh = (int)(t % H);
-      const int64_t n = t / H;
-      const float4 gv = ldg_stream(g + p * C4 + q);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float* ip = img + (n * 3 + j) * plane;
-        float v;
+    // blockIdx.y = sample, blockIdx.x strides the pixels of its plane: 32-bit index math only in the inner loop
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+      const float4* gn = g + (int64_t)n * HW * C4 + q;
+      const float* in = img + (int64_t)n * 3 * plane;
+      for (int r = blockIdx.x * rows + rl; r < HW; r += gridDim.x * rows) {
+        const float4 gv = ldg_stream(gn + (int64_t)r * C4);
+        float v[3];
         if (pool) {
-          const int64_t o = (int64_t)(2 * hh) * IW + 2 * ww;
-          v = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
+          const int hh = r / W, ww = r - hh * W;
+          const int o = (2 * hh) * IW + 2 * ww;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float* ip = in + j * plane;
+            v[j] = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
+          }
         } else {
-          v = __ldg(ip + (int64_t)hh * IW + ww);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) v[j] = __ldg(in + j * plane + r);
         }
-        s[j].x = fmaf(v, gv.x, s[j].x); s[j].y = fmaf(v, gv.y, s[j].y); s[j].z = fmaf(v, gv.z, s[j].z); s[j].w = fmaf(v, gv.w, s[j].w);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          s[j].x = fmaf(v[j], gv.x, s[j].x); s[j].y = fmaf(v[j], gv.y, s[j].y);
+          s[j].z = fmaf(v[j], gv.z, s[j].z); s[j].w = fmaf(v[j], gv.w, s[j].w);
+        }
       }
     }
     if (C4 > lanes) {  // wide: direct atomics
@@ -259,11 +266,14 @@ extern "C" int glb_rgb_wgrad(const float* img, const float* g, float* gw, int ws
   const int C4 = C / 4;
   REQ(C4 > TPB || TPB % C4 == 0, "rgb_wgrad: C/4 must divide 256 or exceed it");
   const int lanes = C4 < TPB ? C4 : TPB, rows = TPB / lanes;
-  const int64_t P = (int64_t)N * H * W;
-  int blocks = (int)((P + rows - 1) / rows);
-  if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;      // every block ends in 3*C atomics on the same addresses: keep them few
-  rgb_wgrad_kernel<<<blocks, TPB, 3 * TPB * sizeof(float4), (cudaStream_t)stream>>>(img, (const float4*)g, gw, ws_j, ws_c, N, H, W, C4,
-                                                                                   pool, alpha);
+  REQ((int64_t)H * W * 4 < (1ll << 31), "rgb_wgrad: plane too large");
+  // every block ends in 3*C atomics on the same addresses: ~2 blocks per SM in total, spread as (plane chunks) x (samples)
+  int by = N < 16 ? N : 16;
+  int bx = (2 * kNumSMs + by - 1) / by;
+  const int max_bx = (H * W + rows - 1) / rows;
+  if (bx > max_bx) bx = max_bx;
+  rgb_wgrad_kernel<<<dim3(bx, by), TPB, 3 * TPB * sizeof(float4), (cudaStream_t)stream>>>(img, (const float4*)g, gw, ws_j, ws_c, N, H, W,
+                                                                                         C4, pool, alpha);
   GLB_CHECK_LAUNCH("rgb_wgrad");
   return GLB_OK;
 }

@@ -98,42 +98,40 @@ __global__ void __launch_bounds__(TPB) se_fwd_stats_kernel(const float4* __restr
 }
 
 // stats layout: [N][2][C] = (mu plane, rstd plane)
-// block = 32 channels x 8 chunk lanes: lane ky folds chunks ky, ky+8, ... with Chan's (count, mean, M2) update in fp64, the
-// 8 partial triples of a channel are folded through shared memory (a serial loop over all chunks took 30 us per call).
-constexpr int FIN_CH = 32, FIN_KY = 8;
-
-__device__ __forceinline__ void chan_merge(double& cnt, double& mu, double& m2, double nk, double mk, double m2k) {
-  if (nk <= 0.0) return;
-  const double d = mk - mu, tot = cnt + nk;
-  mu += d * nk / tot;
-  m2 += m2k + d * d * cnt * nk / tot;
-  cnt = tot;
-}
+// block = 32 channels x 32 chunk lanes.  Every partial (sum, sum of squares about its own shift k_j) is re-based in fp64 to
+// the shift of chunk 0 -- sum(t-K) = s_j + n_j d, sum((t-K)^2) = ss_j + 2 d s_j + n_j d^2 with d = k_j - K -- so the lanes
+// only ADD (no divisions in the loop), then fold through shared memory.  K is a sample of the plane itself, so the final
+// E[(t-K)^2] - E[t-K]^2 does not cancel (same argument as for the per-chunk shifts).
+constexpr int FIN_CH = 32, FIN_KY = 32;
 
 __global__ void __launch_bounds__(FIN_CH * FIN_KY) se_fwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats,
                                                                           int N, int C, int chunks, int HW, int CHUNK, float eps) {
-  __shared__ double sh[3][FIN_KY][FIN_CH];
+  __shared__ double sh[2][FIN_KY][FIN_CH + 1];
   const int cx = threadIdx.x % FIN_CH, ky = threadIdx.x / FIN_CH;
   const int c = blockIdx.x * FIN_CH + cx, n = blockIdx.y;
-  double cnt = 0.0, mu = 0.0, m2 = 0.0;
+  double S = 0.0, SS = 0.0, K0 = 0.0;
   if (c < C) {
+    K0 = (double)part[((int64_t)(n * chunks) * 3 + 2) * C + c];
     for (int k = ky; k < chunks; k += FIN_KY) {
       const float* p = part + ((int64_t)(n * chunks + k) * 3) * C;
       const int rem = HW - k * CHUNK;
       const double nk = rem < CHUNK ? rem : CHUNK;
-      const double sk = (double)p[c], ssk = (double)p[C + c];
-      const double mk = (double)p[2 * C + c] + sk / nk;
-      double m2k = ssk - sk * sk / nk;
-      if (m2k < 0.0) m2k = 0.0;
-      chan_merge(cnt, mu, m2, nk, mk, m2k);
+      const double sk = (double)p[c], ssk = (double)p[C + c], d = (double)p[2 * C + c] - K0;
+      S += sk + nk * d;
+      SS += ssk + 2.0 * d * sk + nk * d * d;
     }
   }
-  sh[0][ky][cx] = cnt; sh[1][ky][cx] = mu; sh[2][ky][cx] = m2;
+  sh[0][ky][cx] = S; sh[1][ky][cx] = SS;
   __syncthreads();
+  for (int o = FIN_KY / 2; o > 0; o >>= 1) {
+    if (ky < o) { sh[0][ky][cx] += sh[0][ky + o][cx]; sh[1][ky][cx] += sh[1][ky + o][cx]; }
+    __syncthreads();
+  }
   if (ky == 0 && c < C) {
-    for (int j = 1; j < FIN_KY; ++j) chan_merge(cnt, mu, m2, sh[0][j][cx], sh[1][j][cx], sh[2][j][cx]);
-    const double var = m2 / HW;
-    stats[((int64_t)n * 2) * C + c] = (float)mu;
+    const double m1 = sh[0][0][cx] / HW;
+    double var = sh[1][0][cx] / HW - m1 * m1;
+    if (var < 0.0) var = 0.0;
+    stats[((int64_t)n * 2) * C + c] = (float)(K0 + m1);
     stats[((int64_t)n * 2 + 1) * C + c] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
@@ -225,7 +223,7 @@ __global__ void __launch_bounds__(TPB) se_bwd_stats_kernel(const float4* __restr
 __global__ void __launch_bounds__(FIN_CH * FIN_KY) se_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ style,
                                                                           float* __restrict__ gstyle, float* __restrict__ means, int N,
                                                                           int C, int chunks, int HW) {
-  __shared__ double sh[2][FIN_KY][FIN_CH];
+  __shared__ double sh[2][FIN_KY][FIN_CH + 1];
   const int cx = threadIdx.x % FIN_CH, ky = threadIdx.x / FIN_CH;
   const int c = blockIdx.x * FIN_CH + cx, n = blockIdx.y;
   double s1 = 0.0, s2 = 0.0;
@@ -238,8 +236,12 @@ __global__ void __launch_bounds__(FIN_CH * FIN_KY) se_bwd_finalize_kernel(const 
   }
   sh[0][ky][cx] = s1; sh[1][ky][cx] = s2;
   __syncthreads();
+  for (int o = FIN_KY / 2; o > 0; o >>= 1) {
+    if (ky < o) { sh[0][ky][cx] += sh[0][ky + o][cx]; sh[1][ky][cx] += sh[1][ky + o][cx]; }
+    __syncthreads();
+  }
   if (ky == 0 && c < C) {
-    for (int j = 1; j < FIN_KY; ++j) { s1 += sh[0][j][cx]; s2 += sh[1][j][cx]; }
+    s1 = sh[0][0][cx]; s2 = sh[1][0][cx];
     gstyle[(int64_t)n * 2 * C + c] = (float)s2;
     gstyle[(int64_t)n * 2 * C + C + c] = (float)s1;
     const double sc = (double)style[(int64_t)n * 2 * C + c] + 1.0;
