@@ -430,11 +430,15 @@ def kernel_rooflines(L, x, main_iter, flush):
     for name in GLUE_LAUNCHERS:
         wrap(name, f_adam if name == "adam_ewma_multi" else nbytes)
     dp, L.dp = L.dp, None          # rank-local pass: no collective may run here (the other ranks are not in it)
+    if dp is not None:
+        dp.enabled = False         # ... including the ones the gradient hooks would launch
     try:
         main_iter(x)
         torch.cuda.synchronize()
     finally:
         L.dp = dp
+        if dp is not None:
+            dp.enabled = True
         for n, f in orig.items():
             setattr(K, n, f)
 
@@ -530,6 +534,9 @@ def cpu_baseline(args):
 
 
 def main():
+    if os.environ.get("GLB_BENCH_FAULT"):          # debugging aid: dump every thread's Python stack if the run hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["GLB_BENCH_FAULT"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -29,6 +29,7 @@ class DataParallel(object):
         self.world = world_size if world_size is not None else dist.get_world_size()
         self.bucket_bytes = bucket_bytes
         self.overlap = overlap
+        self.enabled = True         # False: the hooks stay silent (rank-local passes such as bench.py's roofline replay)
         self._hooked = set()        # ids of parameters that carry our hook
         self._pending = []          # parameters whose gradient is ready but not yet in a bucket
         self._pending_bytes = 0
@@ -54,7 +55,7 @@ class DataParallel(object):
                     self._hooked.add(id(p))
 
     def _on_grad(self, p):
-        if p.grad is None:
+        if p.grad is None or not self.enabled:
             return
         self._pending.append(p)
         self._pending_bytes += p.numel() * 4
