@@ -109,14 +109,16 @@ def measured_peaks():
 
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
-    """The reference's own algorithm on the box's host cores: the CPU oracle port (oracle/train_oracle.py, plain
-    PyTorch fp32 = the ATen kernels the reference itself dispatches to), all host threads.  kind = "port"."""
+    """The reference's own CPU implementation of the path on the box's host cores, all host threads.
+
+    kind = "reference": the UNMODIFIED reference (pip-installed into baseline/_ref) -- its own
+    StyleGANLearner / ProGANLearner built from its own config Namespace, `Learner.train(dl, num_main_iters=...)` on a
+    synthetic TensorDataset, dev = cpu.  Only stubs for the absent, off-path matplotlib / indexed / lmdb modules are
+    installed (oracle/reference_loader.py).  If baseline/_ref is absent: kind = "port", the CPU oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle.train_oracle import OracleTrainer, IterDraws, sample_gen_draws
-    from oracle import gan_oracle as O
     model, res, init_res, bs, alpha = CONFIGS[args.config]
     if args.config == "cfg4":
         bs = bs // 4
@@ -126,17 +128,12 @@ def run_reference(args):
     sample_bs = bs
     if total_steps > 8 and bs >= 8:
         sample_bs = 4            # bounded sample: half batch (keeps one full minibatch-stddev group of 4)
-    gen = torch.Generator().manual_seed(0)
-    g_sd, d_sd = synth_params(model, res, gen)
-    T = OracleTrainer(g_sd, d_sd, model=model, res=res, lr=0.0015, loss="nonsaturating" if model == "StyleGAN" else "wgan",
-                      gp_type="r1" if model == "StyleGAN" else "wgan-gp", ewma_beta=O.ewma_beta(sample_bs),
-                      g_kwargs={} if model == "StyleGAN" else dict(use_pixelnorm=True))
-
-    def one():
-        real = torch.rand(sample_bs, 3, res, res, generator=gen) * 2 - 1
-        eps = torch.rand(sample_bs, 1, 1, 1, generator=gen) if model != "StyleGAN" else None
-        T.main_iter(real, IterDraws(sample_gen_draws(model, res, sample_bs, 512, gen), sample_gen_draws(model, res, sample_bs, 512, gen), eps))
-
+    from oracle.reference_loader import reference_available
+    kind = "reference" if (reference_available() and alpha is None) else "port"
+    if kind == "reference":
+        one, note = _reference_stepper(model, res, sample_bs, args.steps, args.warmup)
+    else:
+        one, note = _port_stepper(model, res, sample_bs)
     for _ in range(args.warmup):
         one()
     t0 = time.perf_counter()
@@ -148,10 +145,53 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "StyleGAN G+D train img/s", "value": val, "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME[args.config], "note": "CPU oracle port of the reference algorithm on host cores"},
-            "cpu_baseline": {"value": val, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD_NAME[args.config], "note": note},
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def _reference_stepper(model, res, bs, steps, warmup):
+    """-> (callable running ONE main iteration of the unmodified reference's Learner.train on CPU, note)."""
+    import contextlib
+    import io
+    import torch
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    from oracle.reference_loader import load_reference, make_config, REFERENCE_ROOT
+    ref = load_reference()
+    torch.manual_seed(0)
+    cfg = make_config(model, res=res, init_res=res, batch_size=bs, dev="cpu")
+    quiet = lambda: contextlib.redirect_stdout(io.StringIO())
+    with quiet():
+        L = (ref.stylegan_learner.StyleGANLearner if model == "StyleGAN" else ref.progan_learner.ProGANLearner)(cfg)
+    gen = torch.Generator().manual_seed(0)
+    data = torch.rand((steps + warmup + 1) * bs, 3, res, res, generator=gen) * 2 - 1
+    ds = TensorDataset(data)
+    dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+
+    def one():
+        with quiet(), contextlib.redirect_stderr(io.StringIO()):
+            L.train(dl, num_main_iters=1)
+
+    return one, f"UNMODIFIED reference (gan_lab {REFERENCE_ROOT}) Learner.train on host cores, dev=cpu"
+
+
+def _port_stepper(model, res, bs):
+    import torch
+    from oracle.train_oracle import OracleTrainer, IterDraws, sample_gen_draws
+    from oracle import gan_oracle as O
+    gen = torch.Generator().manual_seed(0)
+    g_sd, d_sd = synth_params(model, res, gen)
+    T = OracleTrainer(g_sd, d_sd, model=model, res=res, lr=0.0015, loss="nonsaturating" if model == "StyleGAN" else "wgan",
+                      gp_type="r1" if model == "StyleGAN" else "wgan-gp", ewma_beta=O.ewma_beta(bs),
+                      g_kwargs={} if model == "StyleGAN" else dict(use_pixelnorm=True))
+
+    def one():
+        real = torch.rand(bs, 3, res, res, generator=gen) * 2 - 1
+        eps = torch.rand(bs, 1, 1, 1, generator=gen) if model != "StyleGAN" else None
+        T.main_iter(real, IterDraws(sample_gen_draws(model, res, bs, 512, gen), sample_gen_draws(model, res, bs, 512, gen), eps))
+
+    return one, "CPU oracle port of the reference algorithm on host cores"
 
 
 def synth_params(model, res, gen):
@@ -198,8 +238,12 @@ def run_ours(args):
     L = (StyleGANLearner if model == "StyleGAN" else ProGANLearner)(cfg)
     if alpha is not None:
         L.gen_model.increase_scale(); L.disc_model.increase_scale()
+        L.gen_model.to(cfg.dev); L.disc_model.to(cfg.dev)
         L.gen_model.alpha = alpha
         L.batch_size = cfg.bs_dict[res]
+        if cfg.use_ewma_gen:
+            L.beta = L.get_smoothing_ewma_beta(10.)
+            L._sync_lagged_structure()             # the EWMA generator grows with the live one (progan/learner.py:660-686)
         L._set_optimizer()
     bs = L.batch_size
     if world > 1:
@@ -511,26 +555,21 @@ def kernel_rooflines(L, x, main_iter, flush):
 
 
 def cpu_baseline(args):
-    """The CPU oracle port timed on this box's host cores on a bounded sample (1 main iteration of the workload)."""
+    """The reference's CPU path timed on this box's host cores on a bounded sample (1 main iteration of the workload at
+    batch 4): the unmodified reference from baseline/_ref when present (kind "reference"), else the oracle port."""
     import torch
-    from oracle.train_oracle import OracleTrainer, IterDraws, sample_gen_draws
-    from oracle import gan_oracle as O
+    from oracle.reference_loader import reference_available
     model, res, init_res, bs, alpha = CONFIGS[args.config]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    gen = torch.Generator().manual_seed(0)
     sbs = 4
-    g_sd, d_sd = synth_params(model, res, gen)
-    T = OracleTrainer(g_sd, d_sd, model=model, res=res, lr=0.0015, loss="nonsaturating" if model == "StyleGAN" else "wgan",
-                      gp_type="r1" if model == "StyleGAN" else "wgan-gp", ewma_beta=O.ewma_beta(sbs),
-                      g_kwargs={} if model == "StyleGAN" else dict(use_pixelnorm=True))
-    real = torch.rand(sbs, 3, res, res, generator=gen) * 2 - 1
-    eps = torch.rand(sbs, 1, 1, 1, generator=gen) if model != "StyleGAN" else None
+    kind = "reference" if (reference_available() and alpha is None) else "port"
+    one, note = _reference_stepper(model, res, sbs, 1, 0) if kind == "reference" else _port_stepper(model, res, sbs)
     t0 = time.perf_counter()
-    T.main_iter(real, IterDraws(sample_gen_draws(model, res, sbs, 512, gen), sample_gen_draws(model, res, sbs, 512, gen), eps))
+    one()
     dt = time.perf_counter() - t0
-    return {"value": sbs / dt, "unit": "img/s", "cores": threads, "kind": "port",
-            "sample": f"1 main iteration (D step + G step) at batch {sbs} of the same workload, no warm-up, {threads} torch threads"}
+    return {"value": sbs / dt, "unit": "img/s", "cores": threads, "kind": kind,
+            "sample": f"1 main iteration (D step + G step) at batch {sbs} of the same workload, no warm-up, {threads} torch threads; {note}"}
 
 
 def main():

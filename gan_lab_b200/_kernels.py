@@ -94,6 +94,7 @@ def weights_updated():
     """Called by the optimiser after it has rewritten parameters through raw pointers (no torch version bump)."""
     _wt_cache.clear()
     _wp_cache.clear()
+    _pk_cache.clear()
 
 
 def transposed_weight(w):
@@ -148,6 +149,68 @@ def padded_weight(w, cip):
     return wp
 
 
+# ---- pixel-pair packing for the narrow layers (16 / 32 channels at 512^2 / 1024^2, SURVEY.md section 8d "low-intensity layers")
+# The tcgen05 kernels move 32-channel (128-byte) rows; a 16-channel NHWC map [N][H][W][16] IS a 32-channel map [N][H][W/2][32]
+# in memory (two neighbouring pixels per row).  A stride-1 "same" convolution on the original map equals a convolution of
+# the packed map with an expanded weight W'[(po,co)][r][s'][(pi,ci)] = W[co][r][s][ci] where 2*s' + pi = po + s - pad (zero
+# elsewhere): same taps count, twice the channels on both sides -- twice the MMA work, which these HBM-bound layers have
+# to spare -- and NO copy of any activation.  fprop / dgrad run on the packed views with W'; wgrad produces gW' and folds
+# it back.  (Without it these layers ran on the FFMA kernels: 5 ms per wgrad launch at 1024^2.)
+_pk_cache = {}
+
+
+def _pack_ok(kind, N, H, W, Ci, Co, R, S, pad):
+    if _state["conv_impl"] != "tf32" or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+        return False
+    if W % 2 != 0 or R != S or S not in (1, 3) or pad != (S - 1) // 2 or Ci % 4 != 0 or Co % 4 != 0:
+        return False
+    return tc_covers(kind, N, H, W // 2, 2 * Ci, 2 * Co, R, S, pad)
+
+
+def _pack_view(t):
+    """[N,C,H,W] channels-last -> the same memory as [N,2C,H,W/2] channels-last."""
+    n, c, h, w = t.shape
+    return t.permute(0, 2, 3, 1).reshape(n, h, w // 2, 2 * c).permute(0, 3, 1, 2)
+
+
+def _unpack_view(t, c):
+    n, c2, h, w2 = t.shape
+    return t.permute(0, 2, 3, 1).reshape(n, h, 2 * w2, c).permute(0, 3, 1, 2)
+
+
+def _pair_taps(S, pad):
+    """(po, s) -> (s', pi): tap s of output pixel po of a pair reads pixel pi of the pair at offset s' (in pairs)."""
+    out = []
+    for po in (0, 1):
+        for s_ in range(S):
+            t = po + s_ - pad
+            out.append((po, s_, t // 2 + pad, t % 2))       # python floor division / modulo: t = -1 -> (-1, 1)
+    return out
+
+
+def packed_weight(w, pad):
+    """Expanded weight of the pixel-pair packed convolution, cached per weight version."""
+    key = (w.data_ptr(), tuple(w.shape), pad)
+    hit = _pk_cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    Co, Ci, R, S = w.shape
+    wp = torch.empty((2 * Co, 2 * Ci, R, S), device=w.device, dtype=w.dtype, memory_format=torch.channels_last).zero_()
+    for po, s_, sp, pi in _pair_taps(S, pad):
+        wp[po * Co:(po + 1) * Co, pi * Ci:(pi + 1) * Ci, :, sp].copy_(w[:, :, :, s_])
+    if len(_pk_cache) >= 64:
+        _pk_cache.clear()
+    _pk_cache[key] = (w._version, wp, w)
+    return wp
+
+
+def _fold_packed_wgrad(gwp, Co, Ci, S, pad):
+    gw = torch.empty((Co, Ci, gwp.shape[2], S), device=gwp.device, dtype=gwp.dtype, memory_format=torch.channels_last).zero_()
+    for po, s_, sp, pi in _pair_taps(S, pad):
+        gw[:, :, :, s_].add_(gwp[po * Co:(po + 1) * Co, pi * Ci:(pi + 1) * Ci, :, sp])
+    return gw
+
+
 def conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope):
     _chk(x, w, bias)
     x, w = nhwc(x), nhwc(w)
@@ -155,6 +218,10 @@ def conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope):
     Co, Ci2, R, S = w.shape
     if Ci != Ci2:
         raise GlbError(f"conv_fprop: channel mismatch {Ci} vs {Ci2}")
+    if _pack_ok("fprop", N, H, W, Ci, Co, R, S, pad):
+        b2 = None if bias is None else _flat(bias).repeat(2)
+        yp = conv_fprop(_pack_view(x), packed_weight(w, pad), b2, pad, alpha, bias_scale, act, slope)
+        return _unpack_view(yp, Co)
     cip = _pad_ci("fprop", N, H, W, Ci, Co, R, S, pad)
     if cip is not None:
         x, w, Ci = _pad_channels(x, cip), padded_weight(w, cip), cip
@@ -174,6 +241,9 @@ def conv_dgrad(gy, w, x_hw, pad, alpha):
     H, W = x_hw
     if Co != Co2 or Ho != H + 2 * pad - R + 1 or Wo != W + 2 * pad - S + 1:
         raise GlbError("conv_dgrad: shape mismatch")
+    if _pack_ok("dgrad", N, H, W, Ci, Co, R, S, pad):
+        gxp = conv_dgrad(_pack_view(gy), packed_weight(w, pad), (H, W // 2), pad, alpha)
+        return _unpack_view(gxp, Ci)
     cip = _pad_ci("dgrad", N, H, W, Ci, Co, R, S, pad)
     ci_out = Ci
     if cip is not None:
@@ -193,6 +263,9 @@ def conv_wgrad(x, gy, rs, pad, alpha):
     R, S = rs
     if N != N2 or Ho != H + 2 * pad - R + 1 or Wo != W + 2 * pad - S + 1:
         raise GlbError("conv_wgrad: shape mismatch")
+    if _pack_ok("wgrad", N, H, W, Ci, Co, R, S, pad):
+        gwp = conv_wgrad(_pack_view(x), _pack_view(gy), (R, S), pad, alpha)
+        return _fold_packed_wgrad(gwp, Co, Ci, S, pad)
     cip = _pad_ci("wgrad", N, H, W, Ci, Co, R, S, pad)
     ci_out = Ci
     if cip is not None:

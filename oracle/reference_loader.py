@@ -19,7 +19,19 @@ import types
 from collections import OrderedDict
 from pathlib import Path
 
-REFERENCE_ROOT = Path(os.environ.get("GANLAB_REFERENCE_ROOT", "/root/reference"))
+def _find_reference_root() -> Path:
+    """$GANLAB_REFERENCE_ROOT, else /root/reference (build container), else <repo>/baseline/_ref (the unmodified reference
+    pip-installed there with `pip install --no-index --no-deps --target baseline/_ref /root/reference`; git-ignored, it
+    travels to the GPU box with the snapshot and is what `bench.py --impl reference` times)."""
+    cands = [os.environ.get("GANLAB_REFERENCE_ROOT"), "/root/reference",
+             str(Path(__file__).resolve().parent.parent / "baseline" / "_ref")]
+    for c in cands:
+        if c and (Path(c) / "gan_lab" / "utils" / "custom_layers.py").exists():
+            return Path(c)
+    return Path(cands[1])
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -129,6 +129,27 @@ def test_conv_ragged_channels_take_the_tensor_core_path(shape):
         K.set_conv_impl("fp32")
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32, 16, 16, 3), (1, 64, 64, 32, 16, 3), (2, 16, 32, 16, 32, 3), (2, 32, 32, 16, 16, 1),
+                                   (1, 128, 128, 16, 16, 3)])
+def test_conv_narrow_layers_pixel_pair_packing(shape):
+    """16-channel layers (512^2 / 1024^2 blocks of the FFHQ-shape nets) run on the tcgen05 kernels through the pixel-pair
+    packed view (two pixels = one 32-channel row, expanded weight); all three of fprop / dgrad / wgrad must equal the
+    contract of the ORIGINAL convolution."""
+    N, H, W, Ci, Co, R = shape
+    pad = (R - 1) // 2
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, R, R, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, H, W, seed=3))
+    K.set_conv_impl("tf32")
+    try:
+        kinds = [k for k in ("fprop", "dgrad", "wgrad") if K._pack_ok(k, N, H, W, Ci, Co, R, R, pad)]
+        assert kinds, "no kind of this shape takes the packed path"
+        both("conv_fprop", x, w, b, pad, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_TF32)
+        both("conv_dgrad", gy, w, (H, W), pad, 0.37, tol=TOL_TF32)
+        both("conv_wgrad", x, gy, (R, R), pad, 0.37, tol=TOL_TF32)
+    finally:
+        K.set_conv_impl("fp32")
+
+
 def test_tf32_dgrad_sees_weight_updates():
     """The tensor-core dgrad multiplies by a cached re-layout of the weight: an in-place update must invalidate it."""
     K.set_conv_impl("tf32")

@@ -27,8 +27,12 @@ def main():
     L = (StyleGANLearner if model == "StyleGAN" else ProGANLearner)(cfg)
     if alpha is not None:
         L.gen_model.increase_scale(); L.disc_model.increase_scale()
+        L.gen_model.to(cfg.dev); L.disc_model.to(cfg.dev)
         L.gen_model.alpha = alpha
         L.batch_size = cfg.bs_dict[res]
+        if cfg.use_ewma_gen:
+            L.beta = L.get_smoothing_ewma_beta(10.)
+            L._sync_lagged_structure()             # the EWMA generator grows with the live one (progan/learner.py:660-686)
         L._set_optimizer()
     bs = L.batch_size
     L.gen_model.train(); L.disc_model.train()
