@@ -247,6 +247,183 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------ two M tiles per item
+// Same implicit GEMM with TWO 128-pixel M tiles per work item sharing one B tile (for N tiles of 128 channels).  With a
+// single 128 x 128 tile every 32-channel K step reads 16 KB of A and 16 KB of B from shared memory for 64 "MMA cycles" of
+// work -- the SS-mode MMA is then bound by shared-memory operand bandwidth and by L2 -> SM traffic (measured 445-525
+// TFLOP/s against 630-745 for the 256-wide tiles).  Two accumulators per B tile bring bytes per flop down to what the
+// BN = 256 configuration has (48 KB per 2 x 64 cycles): stage = [A0 | A1 | B], 8 MMAs per stage, TMEM = 2 stages x 2 tiles x
+// BN columns.  Used only without split-K and with an even number of M tiles (mt1 = mt0 + 1 in (n, h, w) tile order).
+template <int BN>
+struct FpropM2Cfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = 2 * kABytes + kBBytes;
+  static constexpr int kStages = (192 * 1024 / kStageBytes) > 8 ? 8 : (192 * 1024 / kStageBytes);
+  static constexpr int kTmemCols = 4 * BN;   // 2 accumulator stages x 2 tiles
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kFpropThreads, 1)
+conv_fprop_tc_m2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  using Cfg = FpropM2Cfg<BN>;
+  static_assert(Cfg::kTmemCols <= 512, "TMEM has 512 columns");
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  const uint32_t bar0 = base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = p.Ci / kChunk;
+  const int k_iters = p.R * p.S * chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), Cfg::kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (pair of M tiles, N tile); M tile index mt = (tn * tiles_h + th) * tiles_w + tw
+  auto tile_origin = [&](int mt, int& w0, int& h0, int& n0) {
+    const int tw = mt % p.tiles_w;
+    int t = mt / p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int tn = t / p.tiles_h;
+    w0 = tw * p.bw; h0 = th * p.bh; n0 = tn * p.bn;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+        const int tco = item % p.tiles_co, mt0 = 2 * (item / p.tiles_co);
+        int w0[2], h0[2], n0[2];
+        tile_origin(mt0, w0[0], h0[0], n0[0]);
+        tile_origin(mt0 + 1, w0[1], h0[1], n0[1]);
+        const int co0 = tco * BN;
+        int tap = 0, ch = 0;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const int r = tap / p.S, s = tap - r * p.S;
+          const uint32_t dst = base + stage * Cfg::kStageBytes;
+          tma_load_4d(dst, &tmA, full_bar(stage), ch * kChunk, w0[0] + s - p.pad, h0[0] + r - p.pad, n0[0]);
+          tma_load_4d(dst + kABytes, &tmA, full_bar(stage), ch * kChunk, w0[1] + s - p.pad, h0[1] + r - p.pad, n0[1]);
+          tma_load_3d(dst + 2 * kABytes, &tmB, full_bar(stage), ch * kChunk, tap, co0);
+          if (++ch == chunks) { ch = 0; ++tap; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + as * (2 * BN), d1 = d0 + BN;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a0 = base + stage * Cfg::kStageBytes, a1 = a0 + kABytes, b = a0 + 2 * kABytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bd = make_smem_desc(b + kk * 32, 16, 1024);
+            mma_tf32(d0, make_smem_desc(a0 + kk * 32, 16, 1024), bd, idesc, (k | kk) ? 1u : 0u);
+            mma_tf32(d1, make_smem_desc(a1 + kk * 32, 16, 1024), bd, idesc, (k | kk) ? 1u : 0u);
+          }
+          mma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + Cfg::kEpiWarps) {
+    const int q = warp & 3;
+    constexpr int CW = BN / 2;                         // columns per epilogue warp (two warps per TMEM lane quarter)
+    const int c_begin = ((warp - 4) >> 2) * CW;
+    const int row = q * 32 + lane;
+    const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rn = row / (p.bw * p.bh);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+      const int tco = item % p.tiles_co, mt0 = 2 * (item / p.tiles_co);
+      const int co0 = tco * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        int w0, h0, n0;
+        tile_origin(mt0 + mt, w0, h0, n0);
+        const int w = w0 + rw, h = h0 + rh, n = n0 + rn;
+        const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.N);
+        float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+#pragma unroll 1
+        for (int c = c_begin; c < c_begin + CW; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (2 * BN) + mt * BN + c, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = p.alpha * __uint_as_float(v[j + e]);
+                if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
+                oo[e] = act_apply(a, p.act, p.slope);
+              }
+              *reinterpret_cast<float4*>(out + c + j) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ CTA-pair fprop
 // Same implicit GEMM with tcgen05 cta_group::2: a cluster of two CTAs (one TPC) computes a 256-pixel x BN tile.  Each CTA
 // stages its own 128-pixel A tile and HALF of the B (weight) tile; one MMA issued by the leader reads A from both CTAs
@@ -442,6 +619,20 @@ inline int next_pow2(int v) {
   return p;
 }
 
+template <int BN>
+int launch_fprop_m2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = FpropM2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_m2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  conv_fprop_tc_m2_kernel<BN><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GLB_CHECK_LAUNCH("conv_fprop_tc_m2_kernel");
+  return GLB_OK;
+}
+
 template <int BN, int KC>
 int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = FpropCfg<BN, KC>;
@@ -541,6 +732,13 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
     if (rc) return rc;
   }
   if (use_pair) return BN == 256 ? launch_fprop2<256>(tmA, tmB, p, st) : launch_fprop2<128>(tmA, tmB, p, st);
+  // two M tiles per item for the 128-wide N tiles of the high-resolution layers (>= one wave of pair items)
+  bool use_m2 = BN == 128 && p.ksplit == 1 && m_tiles % 2 == 0 && (m_tiles / 2) * p.tiles_co >= kNumSMs;
+  if (const char* e = getenv("GLB_FPROP_M2")) use_m2 = use_m2 && atoi(e) != 0;   // tuning experiments only
+  if (use_m2) {
+    p.num_tiles = (m_tiles / 2) * p.tiles_co;
+    return launch_fprop_m2<128>(tmA, tmB, p, st);
+  }
   int rc = GLB_ERR_UNSUPPORTED;
   // two K chunks per stage for the narrow tiles (see FpropCfg); needs whole stages per tap row and per split-K slice
   const bool kc2 = BN <= 128 && (Ci / kChunk) % 2 == 0 && p.k_per % 2 == 0 && getenv("GLB_FPROP_KC1") == nullptr;

@@ -87,6 +87,7 @@ TC_SHAPES = [  # N, H, W, Ci, Co, R, pad
     (8, 4, 4, 512, 512, 3, 1), (8, 16, 16, 512, 512, 3, 1), (2, 32, 32, 256, 128, 3, 1), (2, 64, 64, 128, 256, 3, 1),
     (4, 8, 8, 96, 128, 3, 1), (3, 5, 7, 32, 64, 3, 1), (2, 16, 16, 64, 32, 3, 1), (2, 32, 32, 128, 128, 1, 0),
     (1, 128, 128, 128, 128, 3, 1),
+    (3, 128, 128, 128, 128, 3, 1),      # >= one wave of M-tile pairs: the two-accumulator (BN = 128) kernel
 ]
 
 
