@@ -61,6 +61,7 @@ struct FpropCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+constexpr int kHaloDefault = 12;  // tap-reuse kernels used by default: bits 0/1 = single CTA at BN 128/256, bits 2/3 = CTA pair at BN 128/256
 constexpr int kFpropThreads = 384;  // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
 
 template <int BN, int KC>
@@ -424,6 +425,201 @@ conv_fprop_tc_m2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tap reuse ("halo") fprop
+// The kernels above re-read the input window once per filter tap: R*S = 9 TMA loads of 16 KB per 32-channel chunk and tile.
+// Measured (ncu, clock64 traces): every large layer then moves ~16 KB of A per ~660 cycles and SM whatever the N tile
+// (128 wide, 256 wide as a CTA pair, two M tiles per B tile) -- the L2 -> SM path for the per-SM-unique A data is the
+// bound (~7 TB/s chip wide), not the tensor pipe (256 / 512 MMA cycles per chunk step) and not shared memory.
+// Here the M tile is 16 rows x 8 columns of one image, so that one image row of the tile is exactly one 1024-byte
+// swizzle atom (8 pixels x 128 B).  Per chunk S boxes are loaded, one per COLUMN shift s: (32 ch, 8 wide, 16+R-1 tall) =
+// 18 KB each; the ROW shift r of a tap is then just a start-address offset of r atoms (r * 1024 B) into box s -- every
+// descriptor stays canonical (SBO = 1024 B, 1024-byte aligned starts).  A traffic per chunk and tile: S * 18 KB = 54 KB
+// instead of 144 KB.  Two rings: A (one stage = the S boxes of a chunk, released after its R*S taps) and B (one stage
+// = one tap of one chunk).
+template <int BN, int R_, int S_>
+struct FpropHaloCfg {
+  static constexpr int kBoxRows = 16 + R_ - 1;
+  static constexpr int kBoxBytes = kBoxRows * 1024;
+  static constexpr int kAStageBytes = S_ * kBoxBytes;
+  // taps per B stage: the MMA-issuing thread pays a fixed wait / fence / commit cost per stage, so the 64-cycle MMAs of a
+  // 128-wide N tile get 8 per stage (cf. FpropCfg's KC)
+  static constexpr int kTPS = 1;                 // must divide R*S (stages never straddle a chunk; everything unrolls)
+  static constexpr int kTapBytes = BN * 128;
+  static constexpr int kBStageBytes = kTPS * kTapBytes;
+  static constexpr int kAStages = 2;
+  static constexpr int kBStages = (222 * 1024 - kAStages * kAStageBytes) / kBStageBytes > 8
+                                      ? 8 : (222 * 1024 - kAStages * kAStageBytes) / kBStageBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 256;
+};
+
+template <int BN, int R_, int S_>
+__global__ void __launch_bounds__(kFpropThreads, 1)
+conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  using Cfg = FpropHaloCfg<BN, R_, S_>;
+  static_assert(Cfg::kBStages >= 3 || Cfg::kTPS > 1, "B ring too shallow");
+  constexpr int NA = Cfg::kAStages, NB = Cfg::kBStages, TAPS = R_ * S_, TPS = Cfg::kTPS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base, b_base = base + NA * Cfg::kAStageBytes;
+  const uint32_t bar0 = b_base + NB * Cfg::kBStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NA * Cfg::kAStageBytes + NB * Cfg::kBStageBytes);
+  auto afull = [&](int s) { return bar0 + 8u * s; };
+  auto aempty = [&](int s) { return bar0 + 8u * (NA + s); };
+  auto bfull = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+  auto bempty = [&](int s) { return bar0 + 8u * (2 * NA + NB + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA + 2 * NB + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = p.Ci / kChunk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+        int t = item;
+        const int tco = t % p.tiles_co; t /= p.tiles_co;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int n0 = t;
+        const int w0 = tw * 8, h0 = th * 16, co0 = tco * BN;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(aempty(sa), pa ^ 1);
+          mbar_expect_tx(afull(sa), Cfg::kAStageBytes);
+#pragma unroll
+          for (int s = 0; s < S_; ++s)
+            tma_load_4d(a_base + sa * Cfg::kAStageBytes + s * Cfg::kBoxBytes, &tmA, afull(sa), ch * kChunk, w0 + s - p.pad,
+                        h0 - p.pad, n0);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+#pragma unroll
+          for (int g = 0; g < TAPS / TPS; ++g) {              // one B stage = TPS taps of this chunk
+            mbar_wait(bempty(sb), pb ^ 1);
+            mbar_expect_tx(bfull(sb), Cfg::kBStageBytes);
+#pragma unroll
+            for (int u = 0; u < TPS; ++u)
+              tma_load_3d(b_base + sb * Cfg::kBStageBytes + u * Cfg::kTapBytes, &tmB, bfull(sb), ch * kChunk, g * TPS + u, co0);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        // The issuing thread is the pacing item for 64-cycle MMAs: taps are unrolled, so every descriptor is the stage's base
+        // descriptor plus a compile-time constant in its 14-bit address field ((offset) >> 4; shared memory < 256 KB: no carry).
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(afull(sa), pa);
+          tc_fence_after();
+          const uint64_t ad0 = make_smem_desc(a_base + sa * Cfg::kAStageBytes, 16, 1024);
+#pragma unroll
+          for (int g = 0; g < TAPS / TPS; ++g) {
+            mbar_wait(bfull(sb), pb);
+            tc_fence_after();
+            const uint64_t bd0 = make_smem_desc(b_base + sb * Cfg::kBStageBytes, 16, 1024);
+#pragma unroll
+            for (int u = 0; u < TPS; ++u) {
+              const int tap = g * TPS + u, r = tap / S_, s = tap - r * S_;     // row shift = whole swizzle atoms
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                mma_tf32(d_tmem, ad0 + (uint64_t)((s * Cfg::kBoxBytes + r * 1024 + kk * 32) >> 4),
+                         bd0 + (uint64_t)((u * Cfg::kTapBytes + kk * 32) >> 4), idesc, (ch | tap | kk) ? 1u : 0u);
+            }
+            mma_commit(bempty(sb));
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+          mma_commit(aempty(sa));      // the boxes of this chunk are free once all R*S taps have read them
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        mma_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + Cfg::kEpiWarps) {
+    // ===================== epilogue (TMEM lane = pixel (row / 8, row % 8) of the 16 x 8 tile) =====================
+    const int q = warp & 3;
+    constexpr int CW = BN / 2;
+    const int c_begin = ((warp - 4) >> 2) * CW;
+    const int row = q * 32 + lane;
+    const int rw = row & 7, rh = row >> 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+      int t = item;
+      const int tco = t % p.tiles_co; t /= p.tiles_co;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int n = t;
+      const int w = tw * 8 + rw, h = th * 16 + rh, co0 = tco * BN;
+      const bool valid = (w < p.Wo) && (h < p.Ho);
+      float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c_begin; c < c_begin + CW; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = p.alpha * __uint_as_float(v[j + e]);
+              if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
+              oo[e] = act_apply(a, p.act, p.slope);
+            }
+            *reinterpret_cast<float4*>(out + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ CTA-pair fprop
 // Same implicit GEMM with tcgen05 cta_group::2: a cluster of two CTAs (one TPC) computes a 256-pixel x BN tile.  Each CTA
 // stages its own 128-pixel A tile and HALF of the B (weight) tile; one MMA issued by the leader reads A from both CTAs
@@ -599,6 +795,208 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair + tap reuse
+// The two ideas combined: a CTA pair (cta_group::2, M = 256 = two 16 x 8 pixel tiles, each CTA stages its own tile and HALF
+// of the weight tile) with the tap-reuse A staging of conv_fprop_tc_halo_kernel.  Per SM and tap step: 6 KB of A
+// (54 KB per chunk / 9 taps) + BN*64 B of B instead of 16 KB + BN*64 B (pair) or 16 KB + BN*128 B (single CTA).
+// Rings / barriers: A ring (stage = the S boxes of one chunk) and B ring (stage = one tap of one chunk) in both CTAs;
+// afull[] / bfull[] live in the leader and count BOTH CTAs' bytes; aempty[] / bempty[] / tmem_full[] exist in both CTAs and
+// are arrived by the leader's multicast tcgen05.commit; tmem_empty[] lives in the leader (16 epilogue warps of the pair).
+template <int BN>
+struct Fprop2HaloCfg {
+  static constexpr int kBoxBytes = 18 * 1024;
+  static constexpr int kAStageBytes = 3 * kBoxBytes;
+  static constexpr int kTPS = (BN <= 128) ? 3 : 1;          // taps per B stage (12 x 64-cycle MMAs per commit at BN = 128)
+  static constexpr int kTapBytes = (BN / 2) * 128;
+  static constexpr int kBStageBytes = kTPS * kTapBytes;
+  static constexpr int kAStages = 2;
+  static constexpr int kBStages = (BN >= 256) ? 6 : 4;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
+conv_fprop_tc2_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  using Cfg = Fprop2HaloCfg<BN>;
+  constexpr int NA = Cfg::kAStages, NB = Cfg::kBStages, S_ = 3, TAPS = 9, TPS = Cfg::kTPS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base, b_base = base + NA * Cfg::kAStageBytes;
+  const uint32_t bar0 = b_base + NB * Cfg::kBStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NA * Cfg::kAStageBytes + NB * Cfg::kBStageBytes);
+  auto afull = [&](int s) { return bar0 + 8u * s; };
+  auto aempty = [&](int s) { return bar0 + 8u * (NA + s); };
+  auto bfull = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+  auto bempty = [&](int s) { return bar0 + 8u * (2 * NA + NB + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA + 2 * NB + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int chunks = p.Ci / kChunk;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's M tile of pair item `item`: tiles ordered (n, th, tw), tw fastest; 16 x 8 pixels each
+  auto my_tile = [&](int item, int& w0, int& h0, int& n0) {
+    int t = (item / p.tiles_co) * 2 + (int)rank;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    w0 = tw * 8; h0 = th * 16; n0 = t;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+        int w0, h0, n0;
+        my_tile(item, w0, h0, n0);
+        const int co0 = (item % p.tiles_co) * BN + (int)rank * (BN / 2);   // this CTA's half of the weight tile
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(aempty(sa), pa ^ 1);
+          if (leader) mbar_expect_tx(afull(sa), 2 * Cfg::kAStageBytes);
+          const uint32_t lafull = mapa(afull(sa), 0);
+#pragma unroll
+          for (int s = 0; s < S_; ++s)
+            tma2_load_4d(a_base + sa * Cfg::kAStageBytes + s * Cfg::kBoxBytes, &tmA, lafull, ch * kChunk, w0 + s - p.pad, h0 - p.pad, n0);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+#pragma unroll
+          for (int g = 0; g < TAPS / TPS; ++g) {
+            mbar_wait(bempty(sb), pb ^ 1);
+            if (leader) mbar_expect_tx(bfull(sb), 2 * Cfg::kBStageBytes);
+            const uint32_t lbfull = mapa(bfull(sb), 0);
+#pragma unroll
+            for (int u = 0; u < TPS; ++u)
+              tma2_load_3d(b_base + sb * Cfg::kBStageBytes + u * Cfg::kTapBytes, &tmB, lbfull, ch * kChunk, g * TPS + u, co0);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, BN, 0, 0);
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(afull(sa), pa);
+          tc_fence_after();
+          const uint64_t ad0 = make_smem_desc(a_base + sa * Cfg::kAStageBytes, 16, 1024);
+#pragma unroll
+          for (int g = 0; g < TAPS / TPS; ++g) {
+            mbar_wait(bfull(sb), pb);
+            tc_fence_after();
+            const uint64_t bd0 = make_smem_desc(b_base + sb * Cfg::kBStageBytes, 16, 1024);
+#pragma unroll
+            for (int u = 0; u < TPS; ++u) {
+              const int tap = g * TPS + u, r = tap / S_, s = tap - r * S_;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                mma2_tf32(d_tmem, ad0 + (uint64_t)((s * Cfg::kBoxBytes + r * 1024 + kk * 32) >> 4),
+                          bd0 + (uint64_t)((u * Cfg::kTapBytes + kk * 32) >> 4), idesc, (ch | tap | kk) ? 1u : 0u);
+            }
+            mma2_commit_mc(bempty(sb), 3);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+          mma2_commit_mc(aempty(sa), 3);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        mma2_commit_mc(tfull_bar(as), 3);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): own 128 rows of the pair's accumulator =====================
+    const int q = warp & 3;
+    const int c_begin = ((warp - 4) >> 2) * (BN / 2);
+    const int row = q * 32 + lane;
+    const int rw = row & 7, rh = row >> 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+      int w0, h0, n;
+      my_tile(item, w0, h0, n);
+      const int w = w0 + rw, h = h0 + rh, co0 = (item % p.tiles_co) * BN;
+      const bool valid = (w < p.Wo) && (h < p.Ho);
+      float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = p.alpha * __uint_as_float(v[j + e]);
+              if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
+              oo[e] = act_apply(a, p.act, p.slope);
+            }
+            *reinterpret_cast<float4*>(out + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_fprop2_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = Fprop2HaloCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+  conv_fprop_tc2_halo_kernel<BN><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GLB_CHECK_LAUNCH("conv_fprop_tc2_halo_kernel");
+  return GLB_OK;
+}
+
 template <int BN>
 int launch_fprop2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = Fprop2Cfg<BN>;
@@ -617,6 +1015,20 @@ inline int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
   return p;
+}
+
+template <int BN>
+int launch_fprop_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = FpropHaloCfg<BN, 3, 3>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_halo_kernel<BN, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  conv_fprop_tc_halo_kernel<BN, 3, 3><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GLB_CHECK_LAUNCH("conv_fprop_tc_halo_kernel");
+  return GLB_OK;
 }
 
 template <int BN>
@@ -709,6 +1121,54 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   if (const char* e = getenv("GLB_FPROP_TRACE")) p.trace = (long long*)strtoull(e, nullptr, 0);
   const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
   if (p.ksplit > 1) GLB_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * p.Ho * p.Wo * Co, st));
+
+  // tap-reuse kernel: 3x3 "same" convolutions on maps that tile exactly into 16 x 8 pixel tiles, >= one wave of tiles
+  {
+    int halo = 0;   // GLB_FPROP_HALO: bit 0 = use for BN 128, bit 1 = use for BN 256 (default: see below)
+    if (const char* e = getenv("GLB_FPROP_HALO")) halo = atoi(e); else halo = kHaloDefault;
+    const bool shape_ok = p.ksplit == 1 && R == 3 && S == 3 && pad == 1 && p.Ho % 16 == 0 && p.Wo % 8 == 0 &&
+                          (BN == 128 || BN == 256);
+    const int h_tiles = (p.Ho / 16) * (p.Wo / 8) * N * (Co / BN);
+    if (shape_ok && h_tiles >= kNumSMs && ((BN == 128 && (halo & 1)) || (BN == 256 && (halo & 2)))) {
+      FpropParams q = p;
+      q.bw = 8; q.bh = 16; q.bn = 1;
+      q.tiles_w = p.Wo / 8; q.tiles_h = p.Ho / 16; q.tiles_n = N; q.tiles_co = Co / BN;
+      q.num_tiles = h_tiles;
+      CUtensorMap hA, hB;
+      const uint64_t dimsA[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+      const uint64_t stridesA[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+      const uint32_t boxA[4] = {(uint32_t)kChunk, 8u, 18u, 1u};
+      int rc = make_tmap_f32(&hA, x, 4, dimsA, stridesA, boxA, "conv input (halo boxes)");
+      if (rc) return rc;
+      const uint64_t dimsB[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
+      const uint64_t stridesB[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+      const uint32_t boxB[3] = {(uint32_t)kChunk, 1u, (uint32_t)BN};
+      rc = make_tmap_f32(&hB, w, 3, dimsB, stridesB, boxB, "conv weight");
+      if (rc) return rc;
+      return BN == 128 ? launch_fprop_halo<128>(hA, hB, q, st) : launch_fprop_halo<256>(hA, hB, q, st);
+    }
+    // bits 2 / 3: CTA pair + tap reuse for BN 128 / 256 (M = 256 per pair: needs an even number of 16 x 8 tiles)
+    const int m_h = (p.Ho / 16) * (p.Wo / 8) * N;
+    if (shape_ok && m_h % 2 == 0 && (m_h / 2) * (Co / BN) >= 56 &&
+        ((BN == 128 && (halo & 4)) || (BN == 256 && (halo & 8)))) {
+      FpropParams q = p;
+      q.bw = 8; q.bh = 16; q.bn = 1;
+      q.tiles_w = p.Wo / 8; q.tiles_h = p.Ho / 16; q.tiles_n = N; q.tiles_co = Co / BN;
+      q.num_tiles = (m_h / 2) * q.tiles_co;          // pair items
+      CUtensorMap hA, hB;
+      const uint64_t dimsA[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+      const uint64_t stridesA[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+      const uint32_t boxA[4] = {(uint32_t)kChunk, 8u, 18u, 1u};
+      int rc = make_tmap_f32(&hA, x, 4, dimsA, stridesA, boxA, "conv input (halo boxes)");
+      if (rc) return rc;
+      const uint64_t dimsB[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
+      const uint64_t stridesB[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+      const uint32_t boxB[3] = {(uint32_t)kChunk, 1u, (uint32_t)(BN / 2)};
+      rc = make_tmap_f32(&hB, w, 3, dimsB, stridesB, boxB, "conv weight (half tile)");
+      if (rc) return rc;
+      return BN == 128 ? launch_fprop2_halo<128>(hA, hB, q, st) : launch_fprop2_halo<256>(hA, hB, q, st);
+    }
+  }
 
   // CTA pairs (cta_group::2) for the layers with at least one wave of pair tiles
   // (measured: +10 % at BN = 256, no gain at BN = 128, where the loop is bound by L2 -> SM traffic rather than shared memory)
