@@ -1149,7 +1149,7 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
     }
     // bits 2 / 3: CTA pair + tap reuse for BN 128 / 256 (M = 256 per pair: needs an even number of 16 x 8 tiles)
     const int m_h = (p.Ho / 16) * (p.Wo / 8) * N;
-    if (shape_ok && m_h % 2 == 0 && (m_h / 2) * (Co / BN) >= 56 &&
+    if (shape_ok && m_h % 2 == 0 && (m_h / 2) * (Co / BN) >= kNumSMs / 2 &&
         ((BN == 128 && (halo & 4)) || (BN == 256 && (halo & 8)))) {
       FpropParams q = p;
       q.bw = 8; q.bh = 16; q.bn = 1;
@@ -1392,6 +1392,158 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad with tap reuse
+// One CTA per (filter COLUMN s, 128 co, BN ci, split) computes the three taps (r = 0..2, s) at once: per K block (4 rows x 8
+// columns = 32 output pixels of one image) it loads the gy block once and ONE x box of (4 + 2) rows x 8 columns shifted by
+// s; the row shift r of a tap is an offset of r*8 pixels = r*1024 B into that box (MN-major operands: K = pixels advances
+// in whole 1024-byte steps anyway).  Three accumulators (3 x BN TMEM columns).  Per MMA that is 2.4x less TMA / L2 traffic
+// than one tap per CTA (40 KB per 12 MMAs instead of 64 KB per 8 at BN = 128).
+template <int BN>
+struct Wgrad3Cfg {
+  static constexpr int kPix = 32, kBoxPix = 48;              // 4 x 8 output pixels; (4 + 2) x 8 input pixels
+  static constexpr int kABlk = kPix * 128, kBBlk = kBoxPix * 128;
+  static constexpr int kABytes = 4 * kABlk;
+  static constexpr int kBBytes = (BN / 32) * kBBlk;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kTmemCols = (3 * BN <= 128) ? 128 : ((3 * BN <= 256) ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  using Cfg = Wgrad3Cfg<BN>;
+  static_assert(3 * BN <= 512, "three accumulators must fit TMEM");
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  const uint32_t bar0 = base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int split = t % p.splits; t /= p.splits;
+  const int tci = t % p.tiles_ci; t /= p.tiles_ci;
+  const int tco = t % p.tiles_co; t /= p.tiles_co;
+  const int s = t;                                   // filter column of this CTA; rows r = 0..2 are its three accumulators
+  const int co0 = tco * 128, ci0 = tci * BN;
+  const int pb_begin = split * p.pb_per_split;
+  const int pb_end = min(p.num_pb, pb_begin + p.pb_per_split);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmGy);
+    prefetch_tmap(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        int u = pb;
+        const int tw = u % p.tiles_w; u /= p.tiles_w;
+        const int th = u % p.tiles_h; u /= p.tiles_h;
+        const int w0 = tw * 8, h0 = th * 4, n0 = u;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        tma_load_5d(a_dst, &tmGy, full_bar(stage), 0, w0, h0, n0, co0 / 32);
+        tma_load_5d(a_dst + Cfg::kABytes, &tmX, full_bar(stage), 0, w0 + s - p.pad, h0 - p.pad, n0, ci0 / 32);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+        const uint64_t ad0 = make_smem_desc(a_addr, Cfg::kABlk, 512, kLayoutSw128Base32);
+        const uint64_t bd0 = make_smem_desc(a_addr + Cfg::kABytes, Cfg::kBBlk, 512, kLayoutSw128Base32);
+        const uint32_t acc = (pb > pb_begin) ? 1u : 0u;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int kg = 0; kg < Cfg::kPix / 8; ++kg)   // K = 8 pixels per MMA = 1024 B; tap row r = +8 pixels in the x box
+            mma_tf32(tmem_base + r * BN, ad0 + (uint64_t)((kg * 1024) >> 4), bd0 + (uint64_t)(((r + kg) * 1024) >> 4), idesc,
+                     kg > 0 ? 1u : acc);
+        }
+        mma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int co = co0 + q * 32 + lane;
+    const bool valid = co < p.Co;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      float* out = p.gw + ((int64_t)co * p.RS + (r * p.S + s)) * p.Ci + ci0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + r * BN + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float a0 = p.alpha * __uint_as_float(v[j]), a1 = p.alpha * __uint_as_float(v[j + 1]);
+            const float a2 = p.alpha * __uint_as_float(v[j + 2]), a3 = p.alpha * __uint_as_float(v[j + 3]);
+            if (p.atomic) red_add_v4(out + c + j, a0, a1, a2, a3);
+            else *reinterpret_cast<float4*>(out + c + j) = make_float4(a0, a1, a2, a3);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_wgrad3(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
+  using Cfg = Wgrad3Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  conv_wgrad_tc3_kernel<BN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmGy, tmX, p);
+  GLB_CHECK_LAUNCH("conv_wgrad_tc3_kernel");
+  return GLB_OK;
+}
+
 template <int BN, int PIX>
 int launch_wgrad(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
   using Cfg = WgradCfg<BN, PIX>;
@@ -1427,6 +1579,47 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   WgradParams p;
   p.gw = gw; p.Co = Co; p.Ci = Ci; p.RS = R * S; p.S = S; p.pad = pad;
   p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1;
+  {
+    // tap-reuse kernel: 3x3 "same" convolutions whose maps tile into 4 x 8 pixel K blocks, enough of them for one wave
+    bool tap3 = R == 3 && S == 3 && pad == 1 && p.Wo % 8 == 0 && p.Ho % 4 == 0 && (Ci % 128 == 0 || Ci == 64 || Ci == 32);
+    if (const char* e = getenv("GLB_WGRAD_TAP3")) tap3 = tap3 && atoi(e) != 0;   // tuning experiments only
+    const int bn3 = Ci % 128 == 0 ? 128 : Ci;
+    p.tiles_w = p.Wo / 8; p.tiles_h = p.Ho / 4; p.tiles_n = N;
+    p.num_pb = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.tiles_co = (Co + 127) / 128;
+    p.tiles_ci = Ci / bn3;
+    const int tiles3 = p.tiles_co * p.tiles_ci * 3;
+    // measured (tools/check_tc.py): +5..18 % on the 128x128 layers, -7 % at 32x32 / 64x64 where the one-tap kernel needs
+    // no or little split-K (three accumulators per CTA triple the red.add epilogue) -> high-resolution layers only
+    if (tap3 && p.num_pb >= 2048 && tiles3 <= kNumSMs) {
+      int splits = kNumSMs / tiles3;
+      if (splits > p.num_pb / 8) splits = p.num_pb / 8;
+      if (splits < 1) splits = 1;
+      p.pb_per_split = (p.num_pb + splits - 1) / splits;
+      p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;
+      p.alpha = alpha;
+      p.atomic = p.splits > 1 ? 1 : 0;
+      p.bw = 8; p.bh = 4; p.bn = 1;
+      if (p.atomic) GLB_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Co * R * S * Ci, st));
+      CUtensorMap tmGy, tmX;
+      const uint64_t dg[5] = {32u, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N, (uint64_t)(Co / 32)};
+      const uint64_t sg[4] = {(uint64_t)Co * 4, (uint64_t)p.Wo * Co * 4, (uint64_t)p.Ho * p.Wo * Co * 4, 128u};
+      const uint32_t bg[5] = {32u, 8u, 4u, 1u, 4u};
+      int rc = make_tmap_f32(&tmGy, gy, 5, dg, sg, bg, "wgrad gy (4x8 blocks)", true);
+      if (rc) return rc;
+      const uint64_t dx[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / 32)};
+      const uint64_t sx[4] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4, 128u};
+      const uint32_t bx[5] = {32u, 8u, 6u, 1u, (uint32_t)(bn3 / 32)};
+      rc = make_tmap_f32(&tmX, x, 5, dx, sx, bx, "wgrad x (6x8 boxes)", true);
+      if (rc) return rc;
+      const int grid = tiles3 * p.splits;
+      switch (bn3) {
+        case 128: return launch_wgrad3<128>(tmGy, tmX, p, grid, st);
+        case 64: return launch_wgrad3<64>(tmGy, tmX, p, grid, st);
+        case 32: return launch_wgrad3<32>(tmGy, tmX, p, grid, st);
+      }
+    }
+  }
   const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
   const int PIX = BN >= 256 ? 32 : 64;
   p.bw = next_pow2(p.Wo) < PIX ? next_pow2(p.Wo) : PIX;
