@@ -97,21 +97,40 @@ def weights_updated():
     _pk_cache.clear()
 
 
+def _cache_put(cache, key, version, tensor, w):
+    """Cache entries remember the stream that produced them and an event recorded behind the producing kernels: a hit from
+    ANOTHER stream (the learners run independent discriminator passes on two streams) waits for that event first."""
+    ev = None
+    if tensor.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record()
+    cache[key] = (version, tensor, w, ev, torch.cuda.current_stream().cuda_stream if tensor.is_cuda else None)
+    return tensor
+
+
+def _cache_get(cache, key, version):
+    hit = cache.get(key)
+    if hit is None or hit[0] != version:
+        return None
+    if hit[3] is not None and hit[4] != torch.cuda.current_stream().cuda_stream:
+        torch.cuda.current_stream().wait_event(hit[3])
+    return hit[1]
+
+
 def transposed_weight(w):
     """wt[Ci][R][S][Co] with flipped taps (what the tensor-core dgrad multiplies by).  Cached per weight tensor and
     version so the re-layout runs once per optimiser step however many backward passes reuse the weight; the entry
     keeps `w` alive, so its address cannot be recycled for another tensor while the entry exists."""
     key = (w.data_ptr(), tuple(w.shape))
-    hit = _wt_cache.get(key)
-    if hit is not None and hit[0] == w._version:
-        return hit[1]
+    hit = _cache_get(_wt_cache, key, w._version)
+    if hit is not None:
+        return hit
     Co, Ci, R, S = w.shape
     wt = torch.empty((Ci, Co, R, S), device=w.device, dtype=torch.float32, memory_format=torch.channels_last)
     _call("glb_conv2d_weight_transpose", _p(w), _p(wt), Co, R, S, Ci, _stream())
     if len(_wt_cache) >= 96:
         _wt_cache.clear()
-    _wt_cache[key] = (w._version, wt, w)
-    return wt
+    return _cache_put(_wt_cache, key, w._version, wt, w)
 
 
 _wp_cache = {}
@@ -139,14 +158,13 @@ def _pad_channels(t, cip):
 def padded_weight(w, cip):
     """w [Co,Ci,R,S] zero-padded along Ci; cached per weight version like transposed_weight()."""
     key = (w.data_ptr(), tuple(w.shape), cip)
-    hit = _wp_cache.get(key)
-    if hit is not None and hit[0] == w._version:
-        return hit[1]
+    hit = _cache_get(_wp_cache, key, w._version)
+    if hit is not None:
+        return hit
     wp = _pad_channels(w, cip)
     if len(_wp_cache) >= 16:
         _wp_cache.clear()
-    _wp_cache[key] = (w._version, wp, w)
-    return wp
+    return _cache_put(_wp_cache, key, w._version, wp, w)
 
 
 # ---- pixel-pair packing for the narrow layers (16 / 32 channels at 512^2 / 1024^2, SURVEY.md section 8d "low-intensity layers")
@@ -191,17 +209,16 @@ def _pair_taps(S, pad):
 def packed_weight(w, pad):
     """Expanded weight of the pixel-pair packed convolution, cached per weight version."""
     key = (w.data_ptr(), tuple(w.shape), pad)
-    hit = _pk_cache.get(key)
-    if hit is not None and hit[0] == w._version:
-        return hit[1]
+    hit = _cache_get(_pk_cache, key, w._version)
+    if hit is not None:
+        return hit
     Co, Ci, R, S = w.shape
     wp = torch.empty((2 * Co, 2 * Ci, R, S), device=w.device, dtype=w.dtype, memory_format=torch.channels_last).zero_()
     for po, s_, sp, pi in _pair_taps(S, pad):
         wp[po * Co:(po + 1) * Co, pi * Ci:(pi + 1) * Ci, :, sp].copy_(w[:, :, :, s_])
     if len(_pk_cache) >= 64:
         _pk_cache.clear()
-    _pk_cache[key] = (w._version, wp, w)
-    return wp
+    return _cache_put(_pk_cache, key, w._version, wp, w)
 
 
 def _fold_packed_wgrad(gwp, Co, Ci, S, pad):

@@ -46,6 +46,8 @@ class ProGANLearner(GANLearner):
         self._progressively_grow = True
         self.dp = None
         self.share_penalty_forward = True
+        self.parallel_d_passes = True
+        self._side_stream = None
         if self.model == self._model_name:
             self.config = LearnerConfigCopy(config, self.__class__.__name__, self._nonredefinable(),
                                             REDEFINABLE_FROM_LEARNER_ATTRS)
@@ -194,11 +196,35 @@ class ProGANLearner(GANLearner):
             xb = xb.detach().requires_grad_(True)
         elif share:
             _xgenb = _xgenb.detach().requires_grad_(True)
-        discriminative_gen = self.disc_model(_xgenb)
-        discriminative_real = self.disc_model(xb)
+        # The fake and the real pass are independent until the loss: run D(fake) on a second stream.  Autograd runs each
+        # backward node on its forward's stream, so the two passes stay on two streams through backward as well, and in the
+        # captured CUDA graph they are parallel branches: the HBM-bound glue kernels of one pass fill in under the
+        # tensor-bound convolutions of the other, and the low-resolution layers (a few CTAs each) overlap.
+        two_streams = self.parallel_d_passes and xb.is_cuda
+        if two_streams:
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(main)
+            _xgenb.record_stream(side)
+            with torch.cuda.stream(side):
+                discriminative_gen = self.disc_model(_xgenb)
+            discriminative_real = self.disc_model(xb)
+            if share:     # the penalty's create_graph gradient rides on the real pass (main stream) while D(fake) is still running
+                gp_term = self.gp_from_forward(discriminative_real, xb) if gp == 'r1' else None
+            main.wait_stream(side)
+            discriminative_gen.record_stream(main)
+        else:
+            discriminative_gen = self.disc_model(_xgenb)
+            discriminative_real = self.disc_model(xb)
+            gp_term = None
         loss_train_disc = ops.d_logit_loss(discriminative_gen, discriminative_real, self.loss,
                                            c.eps_drift if self.eps else 0.)
-        if share:
+        if share and two_streams and gp == 'r1':
+            loss_train_disc = loss_train_disc + gp_term
+            torch.autograd.backward(loss_train_disc, inputs=[p for p in self.disc_model.parameters() if p.requires_grad])
+        elif share:
             loss_train_disc = loss_train_disc + (self.gp_from_forward(discriminative_real, xb) if gp == 'r1' else
                                                  self.gp_from_forward(discriminative_gen, _xgenb))
             torch.autograd.backward(loss_train_disc, inputs=[p for p in self.disc_model.parameters() if p.requires_grad])
