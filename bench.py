@@ -26,12 +26,14 @@ CONFIGS = {
     "cfg3": ("StyleGAN", 256, 128, 16, 0.5),
     "cfg4": ("StyleGAN", 1024, 1024, 16, None),     # bs_dict[1024] = 16 // 4 = 4 per GPU
     "cfg1": ("ProGAN", 32, 32, 8, None),
+    "cfg5": ("ResNet GAN", 64, 64, 64, None),
 }
 WORKLOAD_NAME = {
     "cfg2": "StyleGAN 128x128 nonsaturating loss + R1, batch 8 per GPU, fp32 storage (BASELINE.json configs[1])",
     "cfg3": "StyleGAN 256x256 mid-fade-in (alpha=0.5), batch 16 per GPU",
     "cfg4": "StyleGAN 1024x1024, batch 4 per GPU",
     "cfg1": "ProGAN 32x32 fixed resolution, batch 8 (BASELINE.json configs[0])",
+    "cfg5": "ResNet GAN 64x64 (WGAN + WGAN-GP, 5 D steps + 1 G step per iteration), batch 64 per GPU",
 }
 
 
@@ -235,6 +237,8 @@ def run_ours(args):
     import numpy as np
     np.random.seed(0)                                  # mixing cut-off stream shared by all ranks (SURVEY 8e caveat)
     cfg = default_config(model, res=res, init_res=init_res, batch_size=bs_cfg, dev=str(dev))
+    if model == "ResNet GAN":
+        return run_resnet(args, cfg, rank, world, dev)
     L = (StyleGANLearner if model == "StyleGAN" else ProGANLearner)(cfg)
     if alpha is not None:
         L.gen_model.increase_scale(); L.disc_model.increase_scale()
@@ -405,6 +409,95 @@ def run_ours(args):
         t = threading.Thread(target=dist.destroy_process_group, daemon=True)
         t.start()
         t.join(timeout=20)
+        os._exit(0)
+
+
+def run_resnet(args, cfg, rank, world, dev):
+    """cfg5: the ResNet GAN loop (reference resnetgan/learner.py:463-776): per main iteration 1 generator step, then 5
+    discriminator steps; eager launches (this path is not CUDA-graph captured yet).  Same JSON contract; the algorithmic
+    conv FLOPs are the ones the recorded conv launches execute (nothing is shared or skipped on this path)."""
+    import torch
+    import torch.distributed as dist
+    from gan_lab_b200 import _kernels as K
+    from gan_lab_b200.resnetgan.learner import GANLearner
+    L = GANLearner(cfg)
+    bs = L.batch_size
+    if world > 1:
+        from gan_lab_b200.parallel import DataParallel
+        L.dp = DataParallel(world)
+        L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
+    L.gen_model.train(); L.disc_model.train()
+    nd = cfg.num_disc_iters
+    res = cfg.res_samples
+    pool_dev = [(torch.rand(bs, 3, res, res, device=dev) * 2 - 1) for _ in range(nd)]
+    pool_host = [(torch.rand(bs, 3, res, res) * 2 - 1).pin_memory() for _ in range(nd)]
+    flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)
+
+    def main_iter(pool):
+        for p in L.disc_model.parameters():
+            p.requires_grad_(False)
+        lg = L.gen_step()
+        for p in L.disc_model.parameters():
+            p.requires_grad_(True)
+        for x in pool:
+            ld = L.disc_step(x)
+        return ld, lg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_iter = 0
+    for _ in range(max(args.warmup, 3)):
+        l0 = K.launch_count()
+        main_iter(pool_dev)
+        launches_per_iter = K.launch_count() - l0
+    barrier()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    for _ in range(args.steps):
+        main_iter(pool_dev)
+    ev[1].record()
+    barrier()
+    if sampler:
+        sampler.stop_flag.set(); sampler.join(timeout=2)
+    ev[2].record()
+    for _ in range(args.steps):                         # e2e: host batches, H2D per D step, losses read back per iteration
+        ld, lg = main_iter(pool_host)
+        _ = (ld.item(), lg.item())
+    ev[3].record()
+    barrier()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    roof, glue = kernel_rooflines(L, pool_dev, lambda pool: main_iter(pool), flush) if rank == 0 else (None, None)
+    if rank == 0:
+        peaks = measured_peaks()
+        imgs = bs * nd * args.steps * world
+        line = {"metric": "ResNet GAN G+D train img/s", "value": imgs / (ms / 1e3), "unit": "img/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.conv_impl == "tf32" else "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAME[args.config], "global_batch": bs * world, "parallelism": f"dp{world}",
+                           "conv_impl": args.conv_impl, "cuda_graphs": False,
+                           "l2": "activations per step (> 1 GB) exceed the 126 MB L2"},
+                "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": nd * bs * 3 * res * res * 4,
+                        "d2h_bytes_per_step": 8},
+                "gpu_launches": launches_per_iter * args.steps, "clocks": sampler.summary() if sampler else None}
+        if roof is not None:
+            roof["peak"] = peaks["tf"]; roof["frac"] = roof["achieved"] / peaks["tf"]
+            roof["frac_of_tf32_peak"] = roof["achieved"] / (peaks["tf"] / 2)
+            line["roofline"] = roof
+        if glue is not None and glue["achieved"] is not None:
+            glue["peak"] = peaks["hbm_gbs"]; glue["frac"] = glue["achieved"] / peaks["hbm_gbs"]
+            line["roofline_glue"] = glue
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        sys.stdout.flush(); sys.stderr.flush()
         os._exit(0)
 
 
