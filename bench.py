@@ -609,6 +609,22 @@ def kernel_rooflines(L, x, main_iter, flush):
         times.sort()
         return times[len(times) // 2]
 
+    if os.environ.get("GLB_BENCH_DUMP"):          # debugging aid: per-call device time of every recorded conv launch
+        rows = []
+        for name, f, a, k, work in [c for c in calls if c[0] in conv_kinds]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.no_grad():
+                f(*a, **k); torch.cuda.synchronize()
+                e0.record(); f(*a, **k); e1.record()
+            torch.cuda.synchronize()
+            shp = [tuple(t.shape) for t in a if torch.is_tensor(t)]
+            rows.append((e0.elapsed_time(e1) * 1e3, name, shp, work))
+        agg = {}
+        for us, name, shp, work in rows:
+            key = (name, str(shp))
+            agg.setdefault(key, [0, 0.0, work]); agg[key][0] += 1; agg[key][1] += us
+        for key, (n, us, work) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+            print(f"[dump] {us:9.1f} us total  x{n:3d}  {work / (us / n) / 1e6:7.1f} TF/s  {key[0]} {key[1]}", file=sys.stderr)
     by = {}
     for kind in conv_kinds:
         sel = [c for c in calls if c[0] == kind]

@@ -141,10 +141,40 @@ def _pad_ci(kind, N, H, W, Ci, Co, R, S, pad):
     miss the tensor-core kernels' Ci % 32 (fprop / wgrad) or Ci % 128 (dgrad output tile) rule and would drop to the FFMA
     implicit GEMM (58 us per launch at cfg2).  Zero-padding Ci up to a multiple of 128 is exact -- the extra input channels
     are zeros, the extra weight columns / gradient columns are dropped -- and ~4x faster.  Returns the padded Ci or None."""
-    if _state["conv_impl"] != "tf32" or Ci < 128 or Ci % 128 == 0 or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+    if _state["conv_impl"] != "tf32" or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
         return None
-    cip = (Ci + 127) // 128 * 128
+    if Ci < 32:
+        cip = 32            # 3-channel image convolutions of the ResNet nets (FFMA kernel: 2.7 ms per wgrad launch at cfg5)
+    elif Ci >= 128 and Ci % 128 != 0:
+        cip = (Ci + 127) // 128 * 128
+    else:
+        return None
     return cip if tc_covers(kind, N, H, W, cip, Co, R, S, pad) else None
+
+
+def _pad_co(kind, N, H, W, Ci, Co, R, S, pad):
+    """Same for a narrow OUTPUT side (the 64 -> 3 convolution in front of the ResNet generator's Tanh): Co < 32 is
+    zero-padded to 32 (zero weight rows / zero gy channels; the extra output channels are dropped).  Returns 32 or None."""
+    if _state["conv_impl"] != "tf32" or Co >= 32 or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+        return None
+    return 32 if tc_covers(kind, N, H, W, Ci, 32, R, S, pad) else None
+
+
+def _pad_dim0(t, n):
+    out = torch.empty((n,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype,
+                      memory_format=torch.channels_last if t.dim() == 4 else torch.contiguous_format).zero_()
+    out[:t.shape[0]].copy_(t)
+    return out
+
+
+def padded_weight_co(w, cop):
+    key = (w.data_ptr(), tuple(w.shape), -cop)
+    hit = _cache_get(_wp_cache, key, w._version)
+    if hit is not None:
+        return hit
+    if len(_wp_cache) >= 16:
+        _wp_cache.clear()
+    return _cache_put(_wp_cache, key, w._version, _pad_dim0(w, cop), w)
 
 
 def _pad_channels(t, cip):
@@ -242,12 +272,17 @@ def conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope):
     cip = _pad_ci("fprop", N, H, W, Ci, Co, R, S, pad)
     if cip is not None:
         x, w, Ci = _pad_channels(x, cip), padded_weight(w, cip), cip
+    cop = _pad_co("fprop", N, H, W, Ci, Co, R, S, pad) if cip is None else None
+    co_out = Co
+    b = _flat(bias)
+    if cop is not None:
+        w, Co = padded_weight_co(w, cop), cop
+        b = None if b is None else _pad_dim0(b, cop)
     Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
     y = _new_nhwc(N, Co, Ho, Wo, x)
-    b = _flat(bias)
     _call("glb_conv2d_fprop", _p(x), _p(w), _p(b), _p(y), N, H, W, Ci, Co, R, S, pad, float(alpha), float(bias_scale),
           int(act), float(slope), _impl_for("fprop", N, H, W, Ci, Co, R, S, pad), _stream())
-    return y
+    return y if cop is None else y[:, :co_out].contiguous(memory_format=torch.channels_last)
 
 
 def conv_dgrad(gy, w, x_hw, pad, alpha):
@@ -265,6 +300,9 @@ def conv_dgrad(gy, w, x_hw, pad, alpha):
     ci_out = Ci
     if cip is not None:
         w, Ci = padded_weight(w, cip), cip
+    elif _pad_co("dgrad", N, H, W, Ci, Co, R, S, pad) is not None:
+        cop = _pad_co("dgrad", N, H, W, Ci, Co, R, S, pad)
+        gy, w, Co = _pad_channels(gy, cop), padded_weight_co(w, cop), cop
     gx = _new_nhwc(N, Ci, H, W, gy)
     impl = _impl_for("dgrad", N, H, W, Ci, Co, R, S, pad)
     wt = transposed_weight(w) if impl == IMPL_TF32 else None
@@ -284,13 +322,22 @@ def conv_wgrad(x, gy, rs, pad, alpha):
         gwp = conv_wgrad(_pack_view(x), _pack_view(gy), (R, S), pad, alpha)
         return _fold_packed_wgrad(gwp, Co, Ci, S, pad)
     cip = _pad_ci("wgrad", N, H, W, Ci, Co, R, S, pad)
-    ci_out = Ci
+    ci_out, co_out = Ci, Co
+    cop = None
     if cip is not None:
         x, Ci = _pad_channels(x, cip), cip
+    else:
+        cop = _pad_co("wgrad", N, H, W, Ci, Co, R, S, pad)
+        if cop is not None:
+            gy, Co = _pad_channels(gy, cop), cop
     gw = _new_nhwc(Co, Ci, R, S, x)
     _call("glb_conv2d_wgrad", _p(x), _p(gy), _p(gw), N, H, W, Ci, Co, R, S, pad, float(alpha),
           _impl_for("wgrad", N, H, W, Ci, Co, R, S, pad), _stream())
-    return gw if cip is None else gw[:, :ci_out].contiguous(memory_format=torch.channels_last)
+    if cip is not None:
+        return gw[:, :ci_out].contiguous(memory_format=torch.channels_last)
+    if cop is not None:
+        return gw[:co_out].contiguous(memory_format=torch.channels_last)
+    return gw
 
 
 # --------------------------------------------------------------------------- linear

@@ -107,6 +107,25 @@ def test_conv_family_tf32_vs_contract(shape):
         K.set_conv_impl("fp32")
 
 
+@pytest.mark.parametrize("shape", [(4, 32, 32, 3, 64, 3, 1), (4, 32, 32, 64, 3, 3, 1), (2, 16, 16, 3, 128, 3, 1)])
+def test_conv_three_channel_sides_take_the_tensor_core_path(shape):
+    """The 3 -> C and C -> 3 3x3 convolutions of the ResNet nets: the narrow side is zero-padded to 32 channels by the
+    launchers; fprop / dgrad / wgrad must equal the contract of the unpadded convolution."""
+    N, H, W, Ci, Co, R, pad = shape
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, R, R, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, H, W, seed=3))
+    K.set_conv_impl("tf32")
+    try:
+        assert not K.tc_covers("fprop", N, H, W, Ci, Co, R, R, pad)
+        assert (K._pad_ci("fprop", N, H, W, Ci, Co, R, R, pad) or K._pad_co("fprop", N, H, W, Ci, Co, R, R, pad)) == 32
+        y, = both("conv_fprop", x, w, b, pad, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_TF32)
+        gx, = both("conv_dgrad", gy, w, (H, W), pad, 0.37, tol=TOL_TF32)
+        gw, = both("conv_wgrad", x, gy, (R, R), pad, 0.37, tol=TOL_TF32)
+        assert y.shape[1] == Co and gx.shape[1] == Ci and tuple(gw.shape) == (Co, Ci, R, R)
+    finally:
+        K.set_conv_impl("fp32")
+
+
 @pytest.mark.parametrize("shape", [(8, 4, 4, 513, 512, 3, 1), (4, 4, 4, 257, 128, 3, 1)])
 def test_conv_ragged_channels_take_the_tensor_core_path(shape):
     """Ci = 513 (behind the minibatch-stddev concat) is zero-padded to a multiple of 128 by the launchers and runs on the
