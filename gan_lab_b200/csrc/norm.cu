@@ -29,6 +29,10 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {   // sh: >= 32 
   return sh[0];
 }
 
+__device__ __forceinline__ void red_add4(float* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float4 f4_mask(const float4& g, const float4& y, int act, float slope) {
   return make_float4(g.x * act_grad(y.x, act, slope), g.y * act_grad(y.y, act, slope), g.z * act_grad(y.z, act, slope),
                      g.w * act_grad(y.w, act, slope));
@@ -154,7 +158,9 @@ __global__ void ln_param_grad_kernel(const float4* __restrict__ gy, const float4
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= L4) return;
   float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = sg;
-  for (int n = 0; n < N; ++n) {
+  // blockIdx.y owns a slice of the samples (the outputs are zeroed by the host and combined with red.add when sliced)
+  const int per = (N + gridDim.y - 1) / gridDim.y, n_begin = blockIdx.y * per, n_end = min(N, n_begin + per);
+  for (int n = n_begin; n < n_end; ++n) {
     const int64_t j = (int64_t)n * L4 + i;
     float4 g = ldg_stream(gy + j);
     if (y != nullptr) g = f4_mask(g, ldg_stream(y + j), act, slope);
@@ -164,8 +170,13 @@ __global__ void ln_param_grad_kernel(const float4* __restrict__ gy, const float4
     sg.z += g.z * (v.z - mean) * rstd; sg.w += g.w * (v.w - mean) * rstd;
     sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
   }
-  ggamma[i] = sg;
-  gbeta[i] = sb;
+  if (gridDim.y == 1) {
+    ggamma[i] = sg;
+    gbeta[i] = sb;
+  } else {
+    red_add4(reinterpret_cast<float*>(ggamma + i), sg);
+    red_add4(reinterpret_cast<float*>(gbeta + i), sb);
+  }
 }
 
 // Second order.  With u the cotangent of gx = B(gy; x, gamma), xh = xhat, r = rstd, g = gy*m*gamma,
@@ -217,7 +228,8 @@ __global__ void ln_bwdbwd_gamma_kernel(const float4* __restrict__ u, const float
   if (i >= L4) return;
   const double invL = 1.0 / (double)(L4 * 4);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int n = 0; n < N; ++n) {
+  const int per = (N + gridDim.y - 1) / gridDim.y, n_begin = blockIdx.y * per, n_end = min(N, n_begin + per);
+  for (int n = n_begin; n < n_end; ++n) {
     const int64_t j = (int64_t)n * L4 + i;
     float4 g = ldg_stream(gy + j);
     if (y != nullptr) g = f4_mask(g, ldg_stream(y + j), act, slope);
@@ -230,7 +242,8 @@ __global__ void ln_bwdbwd_gamma_kernel(const float4* __restrict__ u, const float
     s.z += g.z * r * (uu.z - mu - (v.z - mean) * r * mux);
     s.w += g.w * r * (uu.w - mu - (v.w - mean) * r * mux);
   }
-  g_gamma[i] = s;
+  if (gridDim.y == 1) g_gamma[i] = s;
+  else red_add4(reinterpret_cast<float*>(g_gamma + i), s);
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm
@@ -382,6 +395,15 @@ inline dim3 ln_grid(int N, int64_t L4) {
   return dim3(chunks, N);
 }
 
+// sample slices (grid.y) of the LayerNorm parameter-gradient kernels: enough blocks for ~8 per SM, at least 4 samples each
+inline int ln_sample_slices(int N, int64_t L4) {
+  const int64_t bx = (L4 + 127) / 128;
+  int ny = (int)((8 * (int64_t)kNumSMs + bx - 1) / bx);
+  if (ny > N / 4) ny = N / 4;
+  if (ny > 16) ny = 16;
+  return ny < 1 ? 1 : ny;
+}
+
 inline int bn_threads(int C4) { return ((TPB + C4 - 1) / C4) * C4 > 1024 ? C4 : ((TPB + C4 - 1) / C4) * C4; }
 
 }  // namespace
@@ -422,7 +444,12 @@ extern "C" int glb_layernorm_bwd(const float* gy, const float* y, const float* x
     GLB_CHECK_LAUNCH("ln_bwd_apply_kernel");
   }
   if (ggamma != nullptr && gbeta != nullptr) {
-    ln_param_grad_kernel<<<(unsigned)((L / 4 + 127) / 128), 128, 0, st>>>((const float4*)gy, y4, (const float4*)x, stats,
+    const int ny = ln_sample_slices(N, L / 4);
+    if (ny > 1) {
+      GLB_CUDA(cudaMemsetAsync(ggamma, 0, sizeof(float) * L, st));
+      GLB_CUDA(cudaMemsetAsync(gbeta, 0, sizeof(float) * L, st));
+    }
+    ln_param_grad_kernel<<<dim3((unsigned)((L / 4 + 127) / 128), ny), 128, 0, st>>>((const float4*)gy, y4, (const float4*)x, stats,
                                                                          (float4*)ggamma, (float4*)gbeta, N, L / 4, act, slope);
     GLB_CHECK_LAUNCH("ln_param_grad_kernel");
   }
@@ -447,7 +474,9 @@ extern "C" int glb_layernorm_bwdbwd(const float* u, const float* gy, const float
     GLB_CHECK_LAUNCH("ln_bwdbwd_apply_kernel");
   }
   if (g_gamma != nullptr) {
-    ln_bwdbwd_gamma_kernel<<<(unsigned)((L / 4 + 127) / 128), 128, 0, st>>>((const float4*)u, (const float4*)gy, y4,
+    const int ny = ln_sample_slices(N, L / 4);
+    if (ny > 1) GLB_CUDA(cudaMemsetAsync(g_gamma, 0, sizeof(float) * L, st));
+    ln_bwdbwd_gamma_kernel<<<dim3((unsigned)((L / 4 + 127) / 128), ny), 128, 0, st>>>((const float4*)u, (const float4*)gy, y4,
                                                                            (const float4*)x, stats, (const double*)ws,
                                                                            (float4*)g_gamma, N, L / 4, act, slope);
     GLB_CHECK_LAUNCH("ln_bwdbwd_gamma_kernel");
