@@ -170,6 +170,30 @@ def test_conv_narrow_layers_pixel_pair_packing(shape):
         K.set_conv_impl("fp32")
 
 
+@pytest.mark.parametrize("shape", [(8, 64, 64, 128, 128), (8, 64, 64, 256, 256), (8, 128, 128, 128, 128), (8, 128, 128, 128, 256),
+                                   (16, 256, 256, 64, 64)])
+def test_tf32_highres_kernels_vs_exact_fp32_kernels(shape):
+    """The kernels only full-size layers select -- CTA pair + tap reuse fprop/dgrad (>= 74 pair items), three-tap wgrad
+    (>= 2048 K blocks) -- against the exact fp32 FFMA kernels on the same device tensors (the fp32 kernels themselves are
+    pinned to the fp64 contracts at small shapes above).  TF32 bound as for every tensor-core conv."""
+    N, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(H + Ci + Co)
+    x = cl(torch.randn(N, Ci, H, W, generator=g)).to(DEV)
+    w = cl(torch.randn(Co, Ci, 3, 3, generator=g)).to(DEV)
+    b = torch.randn(Co, generator=g).to(DEV)
+    gy = cl(torch.randn(N, Co, H, W, generator=g)).to(DEV)
+    outs = {}
+    for impl in ("fp32", "tf32"):
+        K.set_conv_impl(impl)
+        try:
+            outs[impl] = (K.conv_fprop(x, w, b, 1, 0.37, 0.5, K.ACT_LRELU, 0.2), K.conv_dgrad(gy, w, (H, W), 1, 0.37),
+                          K.conv_wgrad(x, gy, (3, 3), 1, 0.37))
+        finally:
+            K.set_conv_impl("fp32")
+    for name, a, r in zip(("fprop", "dgrad", "wgrad"), outs["tf32"], outs["fp32"]):
+        assert rel(a, r) < TOL_TF32, (name, rel(a, r))
+
+
 def test_tf32_dgrad_sees_weight_updates():
     """The tensor-core dgrad multiplies by a cached re-layout of the weight: an in-place update must invalidate it."""
     K.set_conv_impl("tf32")
