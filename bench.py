@@ -271,6 +271,10 @@ def run_ours(args):
 
     use_graphs = not args.no_graphs
     L.enable_cuda_graphs(use_graphs, warmup_iters=3)
+    if os.environ.get("GLB_SIDE_STYLES"):
+        L.gen_model.side_stream_styles = os.environ["GLB_SIDE_STYLES"] != "0"
+    if os.environ.get("GLB_PARALLEL_D"):
+        L.parallel_d_passes = os.environ["GLB_PARALLEL_D"] != "0"
 
     def main_iter_eager(x):
         for p in L.disc_model.parameters():

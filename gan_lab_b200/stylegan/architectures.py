@@ -257,11 +257,12 @@ class StyleGenerator(StyleGAN):
             out = m(out)
         return out
 
-    def _layer_tail(self, layer, out, w, noise):
+    def _layer_tail(self, layer, out, w, noise, style=None):
         """layer[1] noise -> layer[2] (bias, lrelu, norms) -> layer[3] style affine + AdaIN (reference :500-526):
         one fused kernel pair when the layer has the default composition, the unfused sequence otherwise."""
         tail = layer[2]
-        style = layer[3](w)                                             # [N, 2C] = [ys ; yb]
+        if style is None:
+            style = layer[3](w)                                         # [N, 2C] = [ys ; yb]
         mods = list(tail)
         bias = mods[0] if mods and isinstance(mods[0], Conv2dBias) else None
         fusable = (self.use_instancenorm and not self.use_pixelnorm and bias is not None and bias.bias_scale == 1.
@@ -284,13 +285,12 @@ class StyleGenerator(StyleGAN):
         return self.z_to_w(z2)
 
     # ------------------------------------------------------------------ forward
-    def _device_mixing_ws(self, w1, bs):
+    def _device_mixing_ws(self, w1, w2):
         """Mixing regularisation decided ON THE DEVICE (CUDA-graph replayable; reference :417-422, :505-511 draw the
         decision and the cut-off with host RNGs, which would bake one outcome into a captured graph): the second
         latent is always mapped, `fire ~ U(0,1) < pct` and `cutoff ~ randint(1, hi)` are device scalars, and layer n
         uses w2 iff fire and n >= cutoff.  Same distribution as the reference, different random stream."""
         hi = 2 * self.scale_stage if self.alpha != 0 else 2 * self.scale_stage - 2
-        w2 = self._second_w(bs, w1.device)
         fire = torch.rand((), device=w1.device) < self.pct_mixing_reg
         cut = torch.randint(1, max(hi, 2), (), device=w1.device)
         layers = torch.arange(len(self.gen_layers), device=w1.device)
@@ -308,8 +308,20 @@ class StyleGenerator(StyleGAN):
                 else:
                     cutoff_idx = RANDOM.source.host_randint(1, 2 * self.scale_stage - 2)
 
-        x = self.z_to_w(x)
         bs = x.shape[0]
+        w2 = None
+        if device_mix and 2 * bs <= 16:
+            # both latents through the mapping network as ONE batch of 2N rows: half the (launch-bound) small linear
+            # kernels of the mapping network, forward and backward
+            z2 = gen_rand_latent_vars(num_samples=bs, length=self.len_latent, distribution=self.latent_distribution,
+                                      device=x.device)
+            z2.requires_grad_(True)
+            both = self.z_to_w(torch.cat([x.view(bs, -1), z2], dim=0))
+            x, w2 = both[:bs], both[bs:]
+        else:
+            x = self.z_to_w(x)
+            if device_mix:
+                w2 = self._second_w(bs, x.device)
 
         if self.use_truncation_trick:
             if self.training:
@@ -322,8 +334,26 @@ class StyleGenerator(StyleGAN):
             elif self.trunc_cutoff_stage is not None:
                 x = self.w_ewma.expand_as(x) + self.w_eval_psi * (x - self.w_ewma.expand_as(x))
 
-        ws = self._device_mixing_ws(x, bs) if device_mix else None
+        ws = self._device_mixing_ws(x, w2) if device_mix else None
         out = self.const_input.expand(bs, -1, -1, -1)
+
+        # All style affines depend only on the dlatents: with `side_stream_styles` they run on a second stream (a parallel
+        # branch of the captured graph, forward and -- because autograd replays each node on its forward's stream --
+        # backward), so these launch-bound small kernels overlap the convolution chain instead of sitting in it.
+        styles = None
+        if ws is not None and getattr(self, 'side_stream_styles', False) and x.is_cuda and not self.fade_in_phase:
+            main = torch.cuda.current_stream()
+            if getattr(self, '_style_stream', None) is None:
+                self._style_stream = torch.cuda.Stream()
+            side = self._style_stream
+            side.wait_stream(main)
+            styles = []
+            with torch.cuda.stream(side):
+                for n, layer in enumerate(self.gen_layers):
+                    st = layer[3](ws[n])
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    styles.append((st, ev))
 
         if self.fade_in_phase:
             for n, layer in enumerate(self.gen_layers[:-2]):
@@ -358,7 +388,12 @@ class StyleGenerator(StyleGAN):
             elif self.use_truncation_trick and not self.training and self.trunc_cutoff_stage is not None and \
                     n == 2 * self.trunc_cutoff_stage:
                 x = (x - self.w_ewma.expand_as(x)).div(self.w_eval_psi) + self.w_ewma.expand_as(x)
-            out = self._layer_tail(layer, out, x if ws is None else ws[n], noise[n] if noise is not None else None)
+            st = None
+            if styles is not None:
+                st, ev = styles[n]
+                torch.cuda.current_stream().wait_event(ev)
+                st.record_stream(torch.cuda.current_stream())
+            out = self._layer_tail(layer, out, x if ws is None else ws[n], noise[n] if noise is not None else None, style=st)
         return self.torgb(out)
 
 
