@@ -374,6 +374,72 @@ def linear_wgrad(x, gy, alpha):
     return gw
 
 
+# --------------------------------------------------------------------------- grouped small linears
+class GroupedLinearTable(object):
+    """Device table for glb_glinear_* over a fixed list of (weight [nout,K], bias [nout] or None, alpha, bias_scale) layers.
+    Rebuilt (one small H2D copy, never inside a CUDA-graph capture) only when a parameter's address changes."""
+
+    def __init__(self):
+        self.key = None
+        self.dev = None
+        self.nouts, self.offs, self.G = [], [], 0
+        self.blocks = (0, 0, 0)
+
+    def update(self, layers, device):
+        import struct
+        key = tuple((w.data_ptr(), 0 if b is None else b.data_ptr(), float(a), float(bs)) for w, b, a, bs in layers)
+        if key == self.key and self.dev is not None and self.dev.device == device:
+            return self
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            raise GlbError("GroupedLinearTable must be built before a CUDA-graph capture (run one eager iteration first)")
+        rows = [LIB.fn("glb_glinear_rows")(i) for i in range(3)]
+        buf = bytearray()
+        off = 0
+        blk = [0, 0, 0]
+        self.nouts, self.offs = [], []
+        for w, b, a, bs in layers:
+            nout = w.shape[0]
+            buf += struct.pack("<qqqqqqqff", w.data_ptr(), 0 if b is None else b.data_ptr(), nout, off, blk[0], blk[1], blk[2],
+                               float(a), float(bs))
+            self.nouts.append(nout); self.offs.append(off)
+            off += nout
+            for i in range(3):
+                blk[i] += (nout + rows[i] - 1) // rows[i]
+        self.G = off
+        self.blocks = tuple(blk)
+        self.dev = torch.frombuffer(buf, dtype=torch.int64).clone().to(device)
+        self.key = key
+        return self
+
+
+def glinear_fwd(ws, tab):
+    """ws [L,M,K] -> flat buffer y; layer l's output is y[M*off_l : M*(off_l+nout_l)].view(M, nout_l)."""
+    _chk(ws)
+    ws = ws.contiguous()
+    L, M, K = ws.shape
+    y = torch.empty(M * tab.G, device=ws.device, dtype=torch.float32)
+    _call("glb_glinear_fwd", _p(ws), _p(tab.dev), _p(y), L, M, K, tab.blocks[0], _stream())
+    return y
+
+
+def glinear_dgrad(g_all, tab, L, M, K):
+    _chk(g_all)
+    g_all = g_all.contiguous()
+    g_ws = torch.empty((L, M, K), device=g_all.device, dtype=torch.float32)
+    _call("glb_glinear_dgrad", _p(g_all), tab.G, _p(tab.dev), _p(g_ws), L, M, K, tab.blocks[1], _stream())
+    return g_ws
+
+
+def glinear_wgrad(ws, g_all, tab):
+    _chk(ws, g_all)
+    ws, g_all = ws.contiguous(), g_all.contiguous()
+    L, M, K = ws.shape
+    gw = torch.empty((tab.G, K), device=ws.device, dtype=torch.float32)
+    gb = torch.empty(tab.G, device=ws.device, dtype=torch.float32)
+    _call("glb_glinear_wgrad", _p(ws), _p(g_all), tab.G, _p(tab.dev), _p(gw), _p(gb), L, M, K, tab.blocks[2], _stream())
+    return gw, gb
+
+
 # --------------------------------------------------------------------------- rows helpers
 def _rows(x):
     """-> (tensor in kernel layout, P, C): 4-D channels_last or 2-D row-major, channel axis contiguous."""

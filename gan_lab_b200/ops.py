@@ -266,6 +266,44 @@ def linear(x, w, bias=None, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2):
     return _LinearFwd.apply(x, w, bias, float(alpha), float(bias_scale), int(act), float(slope))
 
 
+class _GroupedLinear(Function):
+    """styles_l = alpha_l * ws[l] . W_l^T + bias_scale_l * b_l for all layers l in one launch per direction (the style affines of
+    a StyleGenerator pass, stylegan/architectures.py:460 / 524).  Generator side only -> first order."""
+
+    @staticmethod
+    def forward(ctx, ws, tab, *params):
+        y = K.glinear_fwd(ws, tab)
+        M = ws.shape[1]
+        ctx.tab = tab
+        ctx.has_bias = [params[2 * i + 1] is not None for i in range(len(tab.nouts))]
+        ctx.save_for_backward(ws)
+        return tuple(y[M * o:M * (o + n)].view(M, n) for o, n in zip(tab.offs, tab.nouts))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gs):
+        (ws,) = ctx.saved_tensors
+        tab = ctx.tab
+        L, M, Kf = ws.shape
+        g_all = torch.cat([g if g is not None else ws.new_zeros((M, n)) for g, n in zip(gs, tab.nouts)], dim=1)
+        g_ws = K.glinear_dgrad(g_all, tab, L, M, Kf) if ctx.needs_input_grad[0] else None
+        gw, gb = K.glinear_wgrad(ws, g_all, tab)
+        out = [g_ws, None]
+        for i, (o, n) in enumerate(zip(tab.offs, tab.nouts)):
+            out.append(gw[o:o + n] if ctx.needs_input_grad[2 + 2 * i] else None)
+            out.append(gb[o:o + n] if (ctx.has_bias[i] and ctx.needs_input_grad[3 + 2 * i]) else None)
+        return tuple(out)
+
+
+def grouped_linear(ws, tab, layers):
+    """layers: list of (weight, bias or None, alpha, bias_scale); ws [L,M,K].  -> tuple of [M, nout_l] tensors."""
+    tab.update(layers, ws.device)
+    flat = []
+    for w, b, _a, _bs in layers:
+        flat += [w, b]
+    return _GroupedLinear.apply(ws, tab, *flat)
+
+
 # ----------------------------------------------------------------------------------------- stencil / resampling
 class _Blur(Function):
     """Self-adjoint 3x3 binomial FIR (get_blur_op, utils/custom_layers.py:36-53): fwd = bwd = double-bwd."""

@@ -138,6 +138,8 @@ class StyleGenerator(StyleGAN):
         self._trunc_cutoff_stage = truncation_trick_params['cutoff_stage']
         self.use_truncation_trick = True if self._trunc_cutoff_stage else False
         self.w_ewma = None
+        self.grouped_styles = True              # device-mixing path: all style affines as one grouped launch
+        self._style_table = K.GroupedLinearTable()
 
         self.gen_layers.append(nn.ModuleList([None, noise[0], nn.Sequential(*bias[0], self.nl, *norms()), w_to_styles[0]]))
         self.gen_layers.append(nn.ModuleList([conv, noise[1], nn.Sequential(*bias[1], self.nl, *norms()), w_to_styles[1]]))
@@ -341,7 +343,14 @@ class StyleGenerator(StyleGAN):
         # branch of the captured graph, forward and -- because autograd replays each node on its forward's stream --
         # backward), so these launch-bound small kernels overlap the convolution chain instead of sitting in it.
         styles = None
-        if ws is not None and getattr(self, 'side_stream_styles', False) and x.is_cuda and not self.fade_in_phase:
+        if ws is not None and self.grouped_styles and bs <= 16 and bs * ws.shape[2] <= 8192 and not self.fade_in_phase:
+            # all style affines of the pass in ONE launch (and one dgrad + one wgrad launch in backward, which also hand
+            # back the gradient of the whole [L,N,K] dlatent stack: no per-layer select / accumulate kernels)
+            lins = [layer[3] for layer in self.gen_layers]
+            sts = ops.grouped_linear(ws, self._style_table,
+                                     [(l.linear.weight, l.linear.bias, l.alpha, l.lrmul if l.use_lrmul else 1.) for l in lins])
+            styles = [(st, None) for st in sts]
+        elif ws is not None and getattr(self, 'side_stream_styles', False) and x.is_cuda and not self.fade_in_phase:
             main = torch.cuda.current_stream()
             if getattr(self, '_style_stream', None) is None:
                 self._style_stream = torch.cuda.Stream()
@@ -391,8 +400,9 @@ class StyleGenerator(StyleGAN):
             st = None
             if styles is not None:
                 st, ev = styles[n]
-                torch.cuda.current_stream().wait_event(ev)
-                st.record_stream(torch.cuda.current_stream())
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                    st.record_stream(torch.cuda.current_stream())
             out = self._layer_tail(layer, out, x if ws is None else ws[n], noise[n] if noise is not None else None, style=st)
         return self.torgb(out)
 

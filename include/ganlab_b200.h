@@ -230,6 +230,19 @@ int glb_batchnorm_bwd(const float* gy, const float* y, const float* x, const flo
 int glb_tanh_fwd(const float* x, float* y, int64_t n, glb_stream_t stream);
 int glb_tanh_bwd(const float* gy, const float* y, float* gx, int64_t n, glb_stream_t stream);
 
+/* grouped small linears: L layers with their own weights, layer l fed by ws[l] ([L][M][K]), one launch per direction (the 12
+ * style affines of a StyleGAN generator pass, stylegan/architectures.py:460 / 524).  `tab` = device array of L rows of
+ * 8 x int64: {weight ptr [nout][K], bias ptr or 0, nout, column offset off, first block fwd, first block dgrad, first block
+ * wgrad, (alpha, bias_scale) as two packed floats}; blocks per layer = ceil(nout / glb_glinear_rows(which)).
+ *   fwd   : y chunk of layer l = [M][nout_l] at y + M*off_l :  alpha_l * ws[l] . W_l^T + bias_scale_l * b_l
+ *   dgrad : g_all [M][G] (layer l at columns off_l..) -> g_ws [L][M][K]
+ *   wgrad : -> gw_all [G][K] (layer l = rows off_l..), gb_all [G] */
+int glb_glinear_rows(int which);
+int glb_glinear_fwd(const float* ws, const void* tab, float* y, int L, int M, int K, int blocks, glb_stream_t stream);
+int glb_glinear_dgrad(const float* g_all, int G, const void* tab, float* g_ws, int L, int M, int K, int blocks, glb_stream_t stream);
+int glb_glinear_wgrad(const float* ws, const float* g_all, int G, const void* tab, float* gw_all, float* gb_all,
+                      int L, int M, int K, int blocks, glb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -389,6 +389,38 @@ def tanh_bwd(gy, y):
     return gy * (1 - y * y)
 
 
+# ---- grouped small linears (csrc/linear.cu glinear_*): the table object carries python-side copies of what the kernels read
+def _gl_layers(tab):
+    return tab._layers_for_contract
+
+
+def glinear_fwd(ws, tab):
+    outs = []
+    for l, (w, b, a, bs) in enumerate(_gl_layers(tab)):
+        y = a * ws[l] @ w.t()
+        if b is not None:
+            y = y + bs * b
+        outs.append(y.reshape(-1))
+    return torch.cat(outs)
+
+
+def glinear_dgrad(g_all, tab, L, M, Kf):
+    out = []
+    for l, (w, b, a, bs) in enumerate(_gl_layers(tab)):
+        g = g_all[:, tab.offs[l]:tab.offs[l] + tab.nouts[l]]
+        out.append(a * g @ w)
+    return torch.stack(out)
+
+
+def glinear_wgrad(ws, g_all, tab):
+    gw, gb = [], []
+    for l, (w, b, a, bs) in enumerate(_gl_layers(tab)):
+        g = g_all[:, tab.offs[l]:tab.offs[l] + tab.nouts[l]]
+        gw.append(a * g.t() @ ws[l])
+        gb.append(bs * g.sum(0))
+    return torch.cat(gw), torch.cat(gb)
+
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and f.__module__ == __name__
        and n not in ("install",)]
 
@@ -399,3 +431,11 @@ def install(monkeypatch):
     for name in ALL:
         if hasattr(K, name):
             monkeypatch.setattr(K, name, globals()[name])
+    # the grouped-linear table normally holds device pointers; the CPU double keeps the layer tensors themselves
+    def update(self, layers, device):
+        self._layers_for_contract = [(w.detach(), None if b is None else b.detach(), a, bs) for w, b, a, bs in layers]
+        self.nouts = [w.shape[0] for w, _b, _a, _bs in layers]
+        self.offs = [sum(self.nouts[:i]) for i in range(len(self.nouts))]
+        self.G = sum(self.nouts)
+        return self
+    monkeypatch.setattr(K.GroupedLinearTable, "update", update)

@@ -269,6 +269,31 @@ def test_norm_kernels_vs_contract(N, C, H, W):
     both("tanh_bwd", gy, torch.tanh(x))
 
 
+@pytest.mark.parametrize("M,Kf,nouts", [(8, 512, (1024, 1024, 512, 256)), (4, 32, (64, 64, 32, 16, 8)), (16, 512, (1024, 256))])
+def test_grouped_linear_matches_per_layer_linears(M, Kf, nouts):
+    """All style affines of a generator pass as ONE grouped launch per direction == the per-layer LinearEx kernels:
+    outputs, the gradient of the whole dlatent stack, every weight and bias gradient."""
+    from gan_lab_b200 import ops
+    L = len(nouts)
+    ws = rn(L, M, Kf).to(DEV).requires_grad_(True)
+    layers = [(rn(n, Kf, seed=10 + i).to(DEV).requires_grad_(True), rn(n, seed=20 + i).to(DEV).requires_grad_(True),
+               0.05 + 0.01 * i, 1.0 if i % 2 else 0.5) for i, n in enumerate(nouts)]
+    gs = [rn(M, n, seed=30 + i).to(DEV) for i, n in enumerate(nouts)]
+    outs = ops.grouped_linear(ws, K.GroupedLinearTable(), layers)
+    torch.autograd.backward(list(outs), gs)
+    got = (ws.grad.clone(), [w.grad.clone() for w, _b, _a, _s in layers], [b.grad.clone() for _w, b, _a, _s in layers])
+    ws.grad = None
+    for w, b, _a, _s in layers:
+        w.grad = None; b.grad = None
+    refs = [ops.linear(ws[l], w, b, a, bs) for l, (w, b, a, bs) in enumerate(layers)]
+    torch.autograd.backward(refs, gs)
+    for o, r in zip(outs, refs):
+        assert rel(o, r) < TOL
+    assert rel(got[0], ws.grad) < TOL
+    for (w, b, _a, _s), gw, gb in zip(layers, got[1], got[2]):
+        assert rel(gw, w.grad) < TOL and rel(gb, b.grad) < TOL
+
+
 def test_pixelnorm_latents():
     x, gy = rn(8, 512), rn(8, 512, seed=1)
     both("pixelnorm_fwd", x, 1e-8)
