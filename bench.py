@@ -252,7 +252,8 @@ def run_ours(args):
     bs = L.batch_size
     if world > 1:
         from gan_lab_b200.parallel import DataParallel
-        L.dp = DataParallel(world, overlap=os.environ.get("GLB_DP_OVERLAP", "1") != "0")
+        L.dp = DataParallel(world, overlap=os.environ.get("GLB_DP_OVERLAP", "1") != "0",
+                            bucket_bytes=int(float(os.environ.get("GLB_DP_BUCKET_MB", "128")) * 1024 * 1024))
         L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
     def log(msg):
         if args.verbose:
@@ -378,8 +379,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD_NAME[args.config], "global_batch": bs * world, "parallelism": f"dp{world}",
                        "conv_impl": args.conv_impl, "cuda_graphs": use_graphs,
                        "r1_shares_real_forward": bool(getattr(L, "share_penalty_forward", False)),
-                       "grad_allreduce": (("bucketed NCCL, launched from grad hooks during backward" if L.dp.overlap else
-                                           "bucketed NCCL after backward") if world > 1 else None), "l2": "8-batch input pool; activations per step (>1 GB) exceed the 126 MB L2",
+                       "grad_allreduce": (f"NCCL all-reduce, {L.dp.bucket_bytes >> 20} MiB buckets launched from grad hooks as they fill"
+                                          if world > 1 else None), "l2": "8-batch input pool; activations per step (>1 GB) exceed the 126 MB L2",
                        "algorithmic_conv_gflop_per_step_per_gpu": flops / 1e9,
                        "achieved_conv_tflops_whole_step": flops / (ms / args.steps / 1e3) / 1e12},
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": bs * 3 * res * res * 4,

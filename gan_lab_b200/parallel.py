@@ -8,12 +8,15 @@ rank, so averaging the per-rank gradients reproduces the single-GPU gradient of 
 optimiser step; parameters, Adam state and the EWMA generator are replicated.
 
 Overlap with backward: every parameter carries a post-accumulate-grad hook; as soon as the gradients that have become
-ready fill a bucket (default 32 MiB, in autograd order: last layers first) the bucket is packed (one `torch.cat`),
+ready fill a bucket (in autograd order: last layers first) the bucket is packed (one `torch.cat`),
 pre-scaled by 1/world and all-reduced asynchronously -- NCCL runs on the process group's own stream while the compute
 stream keeps executing the rest of backward (including the R1 double-backward tail).  `allreduce_grads()` after backward
 only flushes the last partial bucket, makes the compute stream wait for the collectives and scatters the reduced buckets
 back into the gradients (one multi-tensor copy per bucket).  All of this is stream-ordered, so it is captured into the
-step's CUDA graph as parallel branches.  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
+step's CUDA graph as parallel branches.  Default bucket size 128 MiB = ONE all-reduce per network, issued when its backward
+has finished: measured on 8 B200s (cfg2) 4432 img/s against 4389 with 32 MiB buckets launched during backward and 4392
+with 8 MiB buckets -- the persistent tensor-core kernels occupy every SM, so an NCCL kernel that starts mid-backward
+displaces convolution CTAs and the small-message all-reduces are less efficient than one 92-104 MB one.  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
 """
 import torch
 import torch.distributed as dist
@@ -25,7 +28,7 @@ def _flat_view(t):
 
 
 class DataParallel(object):
-    def __init__(self, world_size=None, bucket_bytes=32 * 1024 * 1024, overlap=True):
+    def __init__(self, world_size=None, bucket_bytes=128 * 1024 * 1024, overlap=True):
         self.world = world_size if world_size is not None else dist.get_world_size()
         self.bucket_bytes = bucket_bytes
         self.overlap = overlap
