@@ -394,6 +394,12 @@ def run_ours(args):
             roof["peak_source"] = ("of " + peaks["src"] + " dense bf16 cuBLAS peak (sustained figure: kernels timed inside a long "
                                    "step); operands are TF32, whose dense peak is half of bf16 -> frac_of_tf32_peak")
             roof["frac_of_tf32_peak"] = roof["achieved"] / (peaks["tf"] / 2)
+            if args.config == "cfg2":
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (a 64x64, 512-channel
+                # layer, 101 us) from the committed `ncu --set full` capture: = that layer's input + output, no re-reads
+                roof["traffic"] = 149.55e6
+                roof["traffic_note"] = ("bytes per launch of conv_fprop_tc2_kernel<256> (profiles/r1_ncu_full_tc2.csv: 68.5 MB read + "
+                                        "81.0 MB written; algorithmic 67.1 MB in + 4.7 MB weights + 67.1 MB out)")
             line["roofline"] = roof
         if glue is not None and glue["achieved"] is not None:
             glue["peak"] = peaks["hbm_gbs"]
