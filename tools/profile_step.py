@@ -38,6 +38,8 @@ def main():
     L.gen_model.train(); L.disc_model.train()
     L.beta = L.get_smoothing_ewma_beta(10.)
     L._init_lagged(); L._attach_ewma()
+    if hasattr(L.gen_model, "_use_mixing_reg"):
+        L.gen_model.device_mixing = True           # the path the CUDA-graph replayed bench runs (grouped style affines)
     x = torch.rand(bs, 3, res, res, device="cuda:0") * 2 - 1
 
     def main_iter():
