@@ -565,6 +565,20 @@ def blur3x3(x):
     return y
 
 
+def blur_act_bwd(gz, y, want_bias, bias_scale, act, slope):
+    """g = blur3x3(gz) * act'(y) (+ bias gradient): backward of `blur(act(conv + b))` in one pass -> (g, gbias or None)."""
+    _chk(gz, y)
+    gz, y = nhwc(gz), nhwc(y)
+    N, C, H, W = y.shape
+    if C % 4 != 0 or 256 % (C // 4) != 0:
+        g0 = blur3x3(gz)
+        return act_bwd(g0, y, want_bias, bias_scale, act, slope)
+    g = torch.empty_like(y)
+    gb = torch.zeros(C, device=y.device, dtype=torch.float32) if want_bias else None
+    _call("glb_blur_act_bwd", _p(gz), _p(y), _p(g), _p(gb), N, H, W, C, float(bias_scale), int(act), float(slope), _stream())
+    return g, gb
+
+
 def upsample2x_fwd(x):
     _chk(x)
     x = nhwc(x)

@@ -302,10 +302,17 @@ __global__ void blur3x3_tap9_kernel(const float4* __restrict__ x, float4* __rest
 // Sliding-window version (default): a thread owns one channel quad of PW adjacent pixels and walks down TH rows keeping the
 // horizontal [1 2 1] sums of the previous two rows in registers, so every output costs (PW+2)/PW * (TH+2)/TH loads
 // (2.5 at PW=2, TH=8) instead of 9; the shared taps of neighbouring threads hit L1, halo rows of neighbouring tiles hit L2.
-template <int PW>
-__global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4, int TH) {
+// MASK = true: the backward of "activation then blur" in one pass, g = blur(x) * act'(mask), plus the bias gradient (column
+// sums of g; needs blockDim % C4 == 0 so that a thread's channel quad is loop invariant): saves the separate act_bwd pass
+// (12 B/element) for 4 B/element of extra mask reads.
+template <int PW, bool MASK>
+__global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4, int TH,
+                               const float4* __restrict__ mask = nullptr, float* __restrict__ gbias = nullptr,
+                               float bias_scale = 1.f, int act = 0, float slope = 0.f) {
+  extern __shared__ float4 red[];
   const int WG = (W + PW - 1) / PW, HT = (H + TH - 1) / TH;
   const int64_t total = (int64_t)N * HT * WG * C4;
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(i % C4);
     int64_t t = i / C4;
@@ -345,11 +352,31 @@ __global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict_
           float4 o;
           o.x = 0.0625f * (rm[j].x + 2.f * rc[j].x + rn[j].x); o.y = 0.0625f * (rm[j].y + 2.f * rc[j].y + rn[j].y);
           o.z = 0.0625f * (rm[j].z + 2.f * rc[j].z + rn[j].z); o.w = 0.0625f * (rm[j].w + 2.f * rc[j].w + rn[j].w);
+          if (MASK) {
+            const float4 mk = ldg_stream(mask + (int64_t)n * H * W * C4 + q + ((int64_t)h * W + w0 + j) * C4);
+            o.x *= act_grad(mk.x, act, slope); o.y *= act_grad(mk.y, act, slope);
+            o.z *= act_grad(mk.z, act, slope); o.w *= act_grad(mk.w, act, slope);
+            bsum.x += o.x; bsum.y += o.y; bsum.z += o.z; bsum.w += o.w;
+          }
           stg_stream(yn + ((int64_t)h * W + w0 + j) * C4, o);
         }
         rm[j] = rc[j];
         rc[j] = rn[j];
       }
+    }
+  }
+  if (MASK && gbias != nullptr) {      // threads tid, tid + C4, ... of the block own the same channel quad
+    const int tid = threadIdx.x;
+    red[tid] = bsum;
+    __syncthreads();
+    if (tid < C4) {
+      float4 t = red[tid];
+      for (int r = tid + C4; r < (int)blockDim.x; r += C4) {
+        const float4 v = red[r];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      atomicAdd(gbias + 4 * tid + 0, bias_scale * t.x); atomicAdd(gbias + 4 * tid + 1, bias_scale * t.y);
+      atomicAdd(gbias + 4 * tid + 2, bias_scale * t.z); atomicAdd(gbias + 4 * tid + 3, bias_scale * t.w);
     }
   }
 }
@@ -812,8 +839,24 @@ extern "C" int glb_blur3x3(const float* x, float* y, int N, int H, int W, int C,
   int TH = 8;   // rows per thread: fewer for small maps so that the grid still fills the machine
   while (TH > 1 && (int64_t)N * ((H + TH - 1) / TH) * ((W + PW - 1) / PW) * C4 < (int64_t)kNumSMs * 4 * TPB) TH >>= 1;
   const int64_t threads = (int64_t)N * ((H + TH - 1) / TH) * ((W + PW - 1) / PW) * C4;
-  blur3x3_kernel<PW><<<grid_for(threads, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C4, TH);
+  blur3x3_kernel<PW, false><<<grid_for(threads, TPB), TPB, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C4, TH);
   GLB_CHECK_LAUNCH("blur3x3");
+  return GLB_OK;
+}
+
+extern "C" int glb_blur_act_bwd(const float* gz, const float* ymask, float* g, float* gbias, int N, int H, int W, int C,
+                                float bias_scale, int act, float slope, glb_stream_t stream) {
+  REQ(C % 4 == 0 && TPB % (C / 4) == 0, "blur_act_bwd: C/4 must divide 256");
+  const int C4 = C / 4;
+  constexpr int PW = 2;
+  int TH = 8;
+  while (TH > 1 && (int64_t)N * ((H + TH - 1) / TH) * ((W + PW - 1) / PW) * C4 < (int64_t)kNumSMs * 4 * TPB) TH >>= 1;
+  const int64_t threads = (int64_t)N * ((H + TH - 1) / TH) * ((W + PW - 1) / PW) * C4;
+  // with a bias gradient every block ends in C atomics on the same addresses: <= 4 blocks per SM (grid-stride loop)
+  const int blocks = grid_for(threads, TPB, gbias != nullptr ? kNumSMs * 4 : kNumSMs * 16);
+  blur3x3_kernel<PW, true><<<blocks, TPB, TPB * sizeof(float4), (cudaStream_t)stream>>>(
+      (const float4*)gz, (float4*)g, N, H, W, C4, TH, (const float4*)ymask, gbias, bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("blur_act_bwd");
   return GLB_OK;
 }
 

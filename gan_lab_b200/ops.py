@@ -138,31 +138,59 @@ def bias_act(x, bias, bias_scale=1.0, act=ACT_NONE, slope=0.2):
     return _BiasAct.apply(x, bias, float(bias_scale), int(act), float(slope))
 
 
+class _BlurActBwd(Function):
+    """(gz, y) -> g = blur(gz) * act'(y)  [+ bias gradient]: backward of `blur(act(.))` fused.  Linear in gz; its own
+    backward (only reached by the R1 / WGAN-GP double backward) is the unfused adjoint blur(gg * act'(y))."""
+
+    @staticmethod
+    def forward(ctx, gz, y, want_bias, bias_scale, act, slope):
+        ctx.save_for_backward(y)
+        ctx.cfg = (bias_scale, act, slope)
+        ctx.set_materialize_grads(False)
+        return K.blur_act_bwd(gz, y, want_bias, bias_scale, act, slope)
+
+    @staticmethod
+    def backward(ctx, gg, ggb):
+        (y,) = ctx.saved_tensors
+        bias_scale, act, slope = ctx.cfg
+        if ggb is not None:
+            raise NotImplementedError("differentiating the bias gradient of the fused blur/activation backward")
+        if gg is None:
+            return None, None, None, None, None, None
+        masked, _ = _ActBwd.apply(gg, y, False, 1.0, act, slope)
+        return _Blur.apply(masked), None, None, None, None, None
+
+
 # ----------------------------------------------------------------------------------------- convolution
 class _ConvFprop(Function):
     """y = act(alpha * conv(x, w) + bias_scale * bias)   (Conv2dEx.forward, utils/custom_layers.py:202-211)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, pad, alpha, bias_scale, act, slope):
+    def forward(ctx, x, w, bias, pad, alpha, bias_scale, act, slope, blur=False):
         y = K.conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope)
-        ctx.cfg = (pad, alpha, bias_scale, act, slope, bias is not None, x.shape, w.shape)
+        blur = bool(blur) and act != ACT_NONE
+        ctx.cfg = (pad, alpha, bias_scale, act, slope, bias is not None, x.shape, w.shape, blur)
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
-        return y
+        # blur=True: the binomial FIR that follows the activation in the D blocks rides in this op, so that the backward can
+        # run blur + activation mask + bias gradient as ONE pass over the gradient (glb_blur_act_bwd)
+        return K.blur3x3(y) if blur else y
 
     @staticmethod
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        pad, alpha, bias_scale, act, slope, has_bias, xshape, wshape = ctx.cfg
+        pad, alpha, bias_scale, act, slope, has_bias, xshape, wshape, blur = ctx.cfg
         pg = _param_grads_wanted()
         want_b = has_bias and ctx.needs_input_grad[2] and pg
-        if act != ACT_NONE:
+        if blur:
+            g, gb = _BlurActBwd.apply(gy, y, want_b, bias_scale, act, slope)
+        elif act != ACT_NONE:
             g, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
         else:
             g = gy
             gb = _ColSum.apply(g, bias_scale) if want_b else None
         gx = _ConvDgrad.apply(g, w, xshape[2], xshape[3], pad, alpha) if ctx.needs_input_grad[0] else None
         gw = _ConvWgrad.apply(x, g, wshape[2], wshape[3], pad, alpha) if (ctx.needs_input_grad[1] and pg) else None
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None
 
 
 class _ConvDgrad(Function):
@@ -201,8 +229,8 @@ class _ConvWgrad(Function):
         return g_x, g_gy, None, None, None, None
 
 
-def conv2d(x, w, bias=None, pad=0, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2):
-    return _ConvFprop.apply(x, w, bias, int(pad), float(alpha), float(bias_scale), int(act), float(slope))
+def conv2d(x, w, bias=None, pad=0, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2, blur=False):
+    return _ConvFprop.apply(x, w, bias, int(pad), float(alpha), float(bias_scale), int(act), float(slope), bool(blur))
 
 
 # ----------------------------------------------------------------------------------------- linear

@@ -36,12 +36,15 @@ class ConvLayer(nn.Sequential):
       D:  blur -> conv(no bias) -> avgpool+bias+lrelu                 |  conv+bias+lrelu
     """
 
-    def forward(self, x):
+    def forward(self, x, blur_after=False, skip_pre_blur=False):
+        """blur_after: the binomial FIR of the NEXT layer rides in this layer's conv op (DiscBlock);
+        skip_pre_blur: ... and that next layer then skips its own pre-blur."""
         mods = list(self)
         i = 0
         n = len(mods)
         while i < n and not isinstance(mods[i], Conv2dEx):     # upsampler / pre-blur
-            x = mods[i](x)
+            if not (skip_pre_blur and isinstance(mods[i], Blur3x3)):
+                x = mods[i](x)
             i += 1
         conv = mods[i]
         i += 1
@@ -61,7 +64,7 @@ class ConvLayer(nn.Sequential):
         act = ops.ACT_LRELU if nl is not None else ops.ACT_NONE
         slope = _slope(nl) if nl is not None else 0.2
         if post_blur is None and pool is None and bias is None:
-            x = conv(x, act=act, slope=slope)                                     # conv + bias + lrelu, one kernel
+            x = conv(x, act=act, slope=slope, blur=blur_after)                    # conv + bias + lrelu (+ blur), one op
         else:
             x = conv(x)
             if post_blur is not None:
@@ -75,6 +78,24 @@ class ConvLayer(nn.Sequential):
         for m in rest:                                                            # pixelnorm / non-fusable tail
             x = m(x)
         return x
+
+
+class DiscBlock(nn.Sequential):
+    """One discriminator block (reference progan/architectures.py:236-259): [conv + bias + lrelu] -> [blur -> conv ->
+    avgpool + bias + lrelu].  Same children / state_dict keys as the reference's nn.Sequential of two conv layers; the
+    forward moves the second layer's pre-blur into the first layer's op, whose backward then runs blur + activation mask +
+    bias gradient as one pass (glb_blur_act_bwd) instead of blur3x3 followed by act_bwd."""
+
+    def forward(self, x):
+        first, second = self[0], self[1]
+        fuse = (len(self) == 2 and isinstance(first, ConvLayer) and isinstance(second, ConvLayer) and len(second) > 0 and
+                isinstance(second[0], Blur3x3) and len(first) == 2 and isinstance(first[0], Conv2dEx) and
+                isinstance(first[1], LeakyReLU))
+        if not fuse:
+            for m in self:
+                x = m(x)
+            return x
+        return second(first(x, blur_after=True), skip_pre_blur=True)
 
 
 class FromRGB(nn.Sequential):
@@ -257,7 +278,7 @@ class _DiscriminatorImpl(object):
         self.prev_fromrgb = copy.deepcopy(self.fromrgb)
         self._update_fromrgb(nf=self.fmap)
         blur_op = get_blur_op(blur_type=self.disc_blur_type, num_channels=self.fmap) if self.disc_blur_type is not None else None
-        self.disc_blocks.insert(0, nn.Sequential(
+        self.disc_blocks.insert(0, DiscBlock(
             self.get_conv_layer(nf=self.fmap),
             self.get_conv_layer(nf=self.fmap_prev, downsample=True, blur_op=blur_op)))
         self.to(next(self.disc_blocks[-1].parameters()).device)

@@ -267,9 +267,9 @@ class Conv2dEx(nn.Module):
         a = self.wscale if self.equalized_lr else 1.
         return a * self.lrmul if self.use_lrmul else a
 
-    def forward(self, x, act=None, slope=0.2):
+    def forward(self, x, act=None, slope=0.2, blur=False):
         """`act=None` reproduces the reference module; the fused architectures pass act=ops.ACT_LRELU to fold
-        the following LeakyReLU into the conv epilogue."""
+        the following LeakyReLU into the conv epilogue, and blur=True to let the binomial FIR that follows ride in the op."""
         act = ops.ACT_NONE if act is None else act
         w, b = self.conv2d.weight, self.conv2d.bias
         bscale = self.lrmul if self.use_lrmul else 1.
@@ -278,7 +278,7 @@ class Conv2dEx(nn.Module):
                 return ops.fromrgb(x, w, b, self.alpha, bscale, act, slope)
             if self.nf == 3 and self.ni % 4 == 0 and act == ops.ACT_NONE:
                 return ops.torgb(x, w, b, self.alpha, bscale)
-        return ops.conv2d(x, w, b, self.padding, self.alpha, bscale, act, slope)
+        return ops.conv2d(x, w, b, self.padding, self.alpha, bscale, act, slope, blur=blur)
 
 
 class Conv2dBias(nn.Module):

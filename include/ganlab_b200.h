@@ -243,6 +243,12 @@ int glb_glinear_dgrad(const float* g_all, int G, const void* tab, float* g_ws, i
 int glb_glinear_wgrad(const float* ws, const float* g_all, int G, const void* tab, float* gw_all, float* gb_all,
                       int L, int M, int K, int blocks, glb_stream_t stream);
 
+/* backward of "activation, then blur" (the D block's conv + bias + lrelu followed by the pre-blur of the next conv,
+ * progan/architectures.py:267-284) in one pass: g = blur3x3(gz) * act'(ymask); gbias (zero-initialised by the caller, may
+ * be NULL) += bias_scale * column sums of g.  Replaces glb_blur3x3 + glb_act_bwd. */
+int glb_blur_act_bwd(const float* gz, const float* ymask, float* g, float* gbias, int N, int H, int W, int C,
+                     float bias_scale, int act, float slope, glb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,11 @@ def blur3x3(x):
     return _cl(O.blur3x3(x))
 
 
+def blur_act_bwd(gz, y, want_bias, bias_scale, act, slope):
+    g = blur3x3(gz) * _dact(y, act, slope)
+    return _cl(g), (bias_scale * g.sum(dim=(0, 2, 3)) if want_bias else None)
+
+
 def upsample2x_fwd(x):
     return _cl(O.upsample2x(x))
 

@@ -225,6 +225,8 @@ def test_glue_kernels_vs_contract(N, C, H, W):
     both("axpby", x, y, 0.3, 0.7)
     both("sumsq", x, 0.01)
     both("blur3x3", x)
+    both("blur_act_bwd", gy, y, True, 0.7, K.ACT_LRELU, 0.2)
+    both("blur_act_bwd", gy, y, False, 1.0, K.ACT_LRELU, 0.2)
     both("upsample2x_fwd", x)
     both("pool_bias_act_fwd", x, b, 0.7, K.ACT_LRELU, 0.2)
     both("pool_bias_act_fwd", x, None, 1.0, K.ACT_NONE, 0.2)
