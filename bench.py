@@ -272,6 +272,9 @@ def run_ours(args):
 
     use_graphs = not args.no_graphs
     L.enable_cuda_graphs(use_graphs, warmup_iters=3)
+    if os.environ.get("GLB_DISC_FUSE"):
+        from gan_lab_b200.progan.architectures import DiscBlock
+        DiscBlock.fuse_blur = os.environ["GLB_DISC_FUSE"] != "0"
     if os.environ.get("GLB_SIDE_STYLES"):
         L.gen_model.side_stream_styles = os.environ["GLB_SIDE_STYLES"] != "0"
     if os.environ.get("GLB_PARALLEL_D"):
@@ -512,7 +515,7 @@ def run_resnet(args, cfg, rank, world, dev):
         os._exit(0)
 
 
-GLUE_LAUNCHERS = ("bias_act_fwd", "act_bwd", "axpby", "colsum", "scale_by", "pixelnorm_fwd", "pixelnorm_bwd", "blur3x3",
+GLUE_LAUNCHERS = ("bias_act_fwd", "act_bwd", "blur_act_bwd", "axpby", "colsum", "scale_by", "pixelnorm_fwd", "pixelnorm_bwd", "blur3x3",
                   "upsample2x_fwd", "upsample2x_bwd", "pool_bias_act_fwd", "pool_bias_act_bwd", "style_epilogue_fwd",
                   "style_epilogue_bwd", "rgb_expand", "rgb_contract", "rgb_wgrad", "fade_up_blend", "fade_up_blend_bwd",
                   "fade_real", "interp_rows", "batchnorm_fwd", "batchnorm_bwd", "layernorm_fwd", "layernorm_bwd",

@@ -86,9 +86,11 @@ class DiscBlock(nn.Sequential):
     forward moves the second layer's pre-blur into the first layer's op, whose backward then runs blur + activation mask +
     bias gradient as one pass (glb_blur_act_bwd) instead of blur3x3 followed by act_bwd."""
 
+    fuse_blur = True      # class-wide switch (A/B runs)
+
     def forward(self, x):
         first, second = self[0], self[1]
-        fuse = (len(self) == 2 and isinstance(first, ConvLayer) and isinstance(second, ConvLayer) and len(second) > 0 and
+        fuse = (self.fuse_blur and len(self) == 2 and isinstance(first, ConvLayer) and isinstance(second, ConvLayer) and len(second) > 0 and
                 isinstance(second[0], Blur3x3) and len(first) == 2 and isinstance(first[0], Conv2dEx) and
                 isinstance(first[1], LeakyReLU))
         if not fuse:
