@@ -252,8 +252,9 @@ def run_ours(args):
     bs = L.batch_size
     if world > 1:
         from gan_lab_b200.parallel import DataParallel
+        mb = os.environ.get("GLB_DP_BUCKET_MB")          # tuning experiments only; default = DataParallel's measured choice
         L.dp = DataParallel(world, overlap=os.environ.get("GLB_DP_OVERLAP", "1") != "0",
-                            bucket_bytes=int(float(os.environ.get("GLB_DP_BUCKET_MB", "128")) * 1024 * 1024))
+                            bucket_bytes=int(float(mb) * 1024 * 1024) if mb else None)
         L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
     def log(msg):
         if args.verbose:

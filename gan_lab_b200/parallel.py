@@ -13,10 +13,11 @@ pre-scaled by 1/world and all-reduced asynchronously -- NCCL runs on the process
 stream keeps executing the rest of backward (including the R1 double-backward tail).  `allreduce_grads()` after backward
 only flushes the last partial bucket, makes the compute stream wait for the collectives and scatters the reduced buckets
 back into the gradients (one multi-tensor copy per bucket).  All of this is stream-ordered, so it is captured into the
-step's CUDA graph as parallel branches.  Default bucket size 128 MiB = ONE all-reduce per network, issued when its backward
-has finished: measured on 8 B200s (cfg2) 4432 img/s against 4389 with 32 MiB buckets launched during backward and 4392
-with 8 MiB buckets -- the persistent tensor-core kernels occupy every SM, so an NCCL kernel that starts mid-backward
-displaces convolution CTAs and the small-message all-reduces are less efficient than one 92-104 MB one.  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
+step's CUDA graph as parallel branches.  Default bucket size: 32 MiB on 2 GPUs, 128 MiB (= ONE all-reduce per network,
+issued when its backward has finished) on more: measured on 8 B200s (cfg2) 4432 img/s against 4389 with 32 MiB buckets
+launched during backward and 4392 with 8 MiB buckets -- the persistent tensor-core kernels occupy every SM, so an NCCL
+kernel that starts mid-backward displaces convolution CTAs, and with more ranks the small-message all-reduces are less
+efficient than one 92-104 MB one; on 2 GPUs the overlap still wins (1151 vs 1123).  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
 """
 import torch
 import torch.distributed as dist
@@ -28,8 +29,12 @@ def _flat_view(t):
 
 
 class DataParallel(object):
-    def __init__(self, world_size=None, bucket_bytes=128 * 1024 * 1024, overlap=True):
+    def __init__(self, world_size=None, bucket_bytes=None, overlap=True):
         self.world = world_size if world_size is not None else dist.get_world_size()
+        if bucket_bytes is None:
+            # measured on B200 (cfg2, img/s): 2 GPUs 1151 with 32 MiB buckets launched during backward vs 1123 with one
+            # 128 MiB bucket per network; 4 GPUs 2184 vs 2275; 8 GPUs 4389 vs 4432
+            bucket_bytes = (32 if self.world <= 2 else 128) * 1024 * 1024
         self.bucket_bytes = bucket_bytes
         self.overlap = overlap
         self.enabled = True         # False: the hooks stay silent (rank-local passes such as bench.py's roofline replay)
