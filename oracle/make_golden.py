@@ -243,8 +243,9 @@ def _quiet():
 
 
 def _build_style_learner(ref, res, init_res, bs, **over):
+    over.setdefault("cutoff_trunc_trick", int(np.log2(res)) - 2)
     cfg = make_config("StyleGAN", res=res, init_res=init_res, batch_size=bs, len_latent=SMALL_FMAP_MAX,
-                      len_dlatent=SMALL_FMAP_MAX, cutoff_trunc_trick=int(np.log2(res)) - 2, **over)
+                      len_dlatent=SMALL_FMAP_MAX, **over)
     with _quiet():
         L = ref.stylegan_learner.StyleGANLearner(cfg)
     return L, cfg
@@ -293,6 +294,40 @@ def golden_style_nets(ref, res=16, bs=4, fade_in=False):
                     img=img.detach(), w_ewma=w_ewma, gimg=gimg, g_grads=g_grads, x=x, logits=logits.detach(),
                     glog=glog, d_grads=d_grads, gp=gp.detach(), d_gp_grads=d_gp_grads, d_gx_img=gxi,
                     lda=cfg.lda)
+    finally:
+        _unpatch(ref)
+
+
+def golden_style_eval(ref, res=32, bs=3):
+    """Evaluation-mode StyleGenerator: supplied per-layer noise, truncation trick on w
+    (psi, cut-off stage, de-truncation at the cut-off), style mixing at a given stage -- reference
+    stylegan/architectures.py:438-440, 505-522."""
+    _patch_small(ref)
+    try:
+        torch.manual_seed(61); np.random.seed(61)
+        L, cfg = _build_style_learner(ref, res, res, bs, cutoff_trunc_trick=2, psi_trunc_trick=.6)
+        G = L.gen_model
+        gen = torch.Generator().manual_seed(63)
+        perturb_zero_params(G, gen)
+        G.train()
+        with torch.no_grad():
+            G(torch.randn(bs, cfg.len_latent, generator=gen))          # one training forward creates w_ewma
+        w_ewma = G.w_ewma.detach().clone()
+        G.eval()
+        n_layers = len(G.gen_layers)
+        hw = [4 * 2 ** (n // 2) for n in range(n_layers)]
+        noise = [torch.randn(bs, 1, h, h, generator=gen) for h in hw]
+        z = torch.randn(bs, cfg.len_latent, generator=gen)
+        z_mix = torch.randn(bs, cfg.len_latent, generator=gen)
+        out = {}
+        with torch.no_grad():
+            out["img_trunc"] = G(z, noise=noise).clone()
+            out["img_mix_low"] = G(z, x_mixing=z_mix, style_mixing_stage=2, noise=noise).clone()     # below the cut-off (2*2)
+            out["img_mix_high"] = G(z, x_mixing=z_mix, style_mixing_stage=5, noise=noise).clone()    # above it
+            G.trunc_cutoff_stage = None
+            out["img_notrunc"] = G(z, noise=noise).clone()
+        return dict(res=res, bs=bs, fmap_max=SMALL_FMAP_MAX, len_latent=cfg.len_latent, g_sd=sd_clone(G), w_ewma=w_ewma,
+                    z=z, z_mix=z_mix, noise=noise, psi=.6, cutoff=2, **out)
     finally:
         _unpatch(ref)
 
@@ -470,6 +505,7 @@ def main():
         "layers.pt": lambda: golden_layers(ref),
         "style_nets_res16.pt": lambda: golden_style_nets(ref, 16, 4, False),
         "style_nets_res16_fade.pt": lambda: golden_style_nets(ref, 16, 4, True),
+        "style_eval_res32.pt": lambda: golden_style_eval(ref, 32, 3),
         "pro_nets_res16.pt": lambda: golden_pro_nets(ref, 16, 4, False),
         "pro_nets_res8_fade.pt": lambda: golden_pro_nets(ref, 8, 4, True),
         "style_train_res16.pt": lambda: golden_train_steps(ref, "StyleGAN", 16, 4, 2),

@@ -399,3 +399,24 @@ def case_resnet_train(golden, dev):
 
     adam_close(L.gen_model.state_dict(), g["g_sd1"], "G", iters)
     adam_close(L.disc_model.state_dict(), g["d_sd1"], "D", iters * g["num_disc_iters"])
+
+
+def case_style_eval(golden, dev):
+    """Evaluation-mode StyleGenerator vs the reference's: supplied noise, truncation trick (psi, cut-off stage and the
+    de-truncation above it), style mixing below and above the cut-off, and truncation switched off."""
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    g = _to(golden("style_eval_res32.pt"), dev)
+    cfg = default_config("StyleGAN", res=g["res"], batch_size=g["bs"], dev=dev, len_latent=g["len_latent"],
+                         len_dlatent=g["len_latent"], cutoff_trunc_trick=g["cutoff"], psi_trunc_trick=g["psi"])
+    L = StyleGANLearner(cfg)
+    G = L.gen_model
+    _load(G, g["g_sd"])
+    G.w_ewma = g["w_ewma"].clone()
+    G.eval()
+    with torch.no_grad():
+        assert relerr(G(g["z"], noise=g["noise"]), g["img_trunc"]) < 1e-4
+        assert relerr(G(g["z"], x_mixing=g["z_mix"], style_mixing_stage=2, noise=g["noise"]), g["img_mix_low"]) < 1e-4
+        assert relerr(G(g["z"], x_mixing=g["z_mix"], style_mixing_stage=5, noise=g["noise"]), g["img_mix_high"]) < 1e-4
+        G.trunc_cutoff_stage = None
+        assert relerr(G(g["z"], noise=g["noise"]), g["img_notrunc"]) < 1e-4
+    assert float((g["img_trunc"] - g["img_notrunc"]).abs().max()) > 1e-3        # the truncation trick did something

@@ -477,6 +477,10 @@ def test_resnet_train(golden):
     PC.case_resnet_train(golden, DEV)
 
 
+def test_style_generator_eval_mode(golden):
+    PC.case_style_eval(golden, DEV)
+
+
 def test_library_was_loaded():
     from gan_lab_b200._lib import LIB
     assert LIB._dll is not None and K.launch_count() > 0

@@ -86,3 +86,7 @@ def test_resnet_nets_modules_fp64(golden, fname, monkeypatch):
 
 def test_resnet_train(golden):
     PC.case_resnet_train(golden, DEV)
+
+
+def test_style_generator_eval_mode(golden):
+    PC.case_style_eval(golden, DEV)
