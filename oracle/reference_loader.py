@@ -38,6 +38,18 @@ def reference_available() -> bool:
     return (REFERENCE_ROOT / "gan_lab" / "utils" / "custom_layers.py").exists()
 
 
+class IndexedOrderedDict(OrderedDict):
+    """Stand-in for the absent `indexed` package (progan/learner.py:472; `.values()[i]` is indexed at :228).  It reports
+    itself as `indexed.IndexedOrderedDict`, so a checkpoint the reference pickles here names the same class a real
+    installation would."""
+
+    def values(self):
+        return list(super().values())
+
+
+IndexedOrderedDict.__module__ = "indexed"
+IndexedOrderedDict.__qualname__ = "IndexedOrderedDict"
+
 _loaded = {}
 
 
@@ -52,10 +64,6 @@ def load_reference():
             sys.modules[name] = types.ModuleType(name)
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     sys.modules["matplotlib.pyplot"].rcParams = {}
-
-    class IndexedOrderedDict(OrderedDict):      # progan/learner.py:472; .values()[i] is indexed (:228)
-        def values(self):
-            return list(super().values())
 
     sys.modules["indexed"].IndexedOrderedDict = IndexedOrderedDict
     ref_pkg = str(REFERENCE_ROOT / "gan_lab")
