@@ -412,6 +412,106 @@ def golden_train_steps(ref, model="StyleGAN", res=16, bs=4, iters=2):
         _unpatch(ref)
 
 
+class PILBoxDataset(torch.utils.data.Dataset):
+    """Synthetic stand-in for the torchvision dataset the reference's train() drives while it grows: uint8 images behind
+    the reference's own transform chain Resize(BOX) -> ToTensor -> Normalize(.5, .5) (data_config.py:312-342); train()
+    rewrites `dataset.transforms.transform.transforms` at every resolution increase (progan/learner.py:611-612).  Every
+    sample served is recorded, so the B200 path can be fed exactly the same real images."""
+
+    def __init__(self, images_u8, res):
+        from PIL import Image
+        from torchvision import transforms as T
+        from torchvision.datasets.vision import StandardTransform
+        self.images = [Image.fromarray(a) for a in images_u8]          # (H, W, 3) uint8
+        self.transforms = StandardTransform(T.Compose([T.Resize((res, res), interpolation=Image.BOX), T.ToTensor(),
+                                                       T.Normalize(mean=[.5] * 3, std=[.5] * 3)]))
+        self.served = []
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, i):
+        x = self.transforms.transform(self.images[i])
+        self.served.append((int(i), x.clone()))
+        return (x,)
+
+
+def golden_grow(ref, model="StyleGAN", init_res=4, res=8, bs_dict=None, nimg_transition=16, iters=11, data_res=8,
+                snap_iters=tuple(range(1, 11))):
+    """Learner.train() THROUGH a resolution increase: stabilise at `init_res`, grow, fade the new
+    block in with a moving alpha (incl. the real-image blend, progan/learner.py:770-779), stabilise at `res`, enter the
+    final phase.  Recorded besides the usual train fixture: the parameters right after every increase_scale() (the
+    freshly initialised block does not come from taped draws), every real sample served, and a per-iteration trace of
+    (curr_res, fade_in_phase, alpha, batch size, learning rates, phase number)."""
+    _patch_small(ref)
+    try:
+        torch.manual_seed(77); np.random.seed(77)
+        bs_dict = bs_dict or {4: 4, 8: 4}     # a batch-size change mid-iterator breaks the reference itself under torch 2.11 (BatchSampler caches it)
+        over = dict(bs_dict={**{r: 4 for r in (4, 8, 16, 32, 64, 128, 256, 512, 1024)}, **bs_dict},
+                    nimg_transition=nimg_transition, res_dataset=data_res,
+                    lr_fctr_dict={4: 1., 8: 1.5, 16: 2., 32: 1., 64: 1., 128: 1., 256: 1., 512: 1., 1024: 1.})
+        if model == "StyleGAN":
+            L, cfg = _build_style_learner(ref, res, init_res, bs_dict[init_res], **over)
+        else:
+            cfg = make_config("ProGAN", res=res, init_res=init_res, batch_size=bs_dict[init_res], len_latent=SMALL_FMAP_MAX,
+                              **over)
+            with _quiet():
+                L = ref.progan_learner.ProGANLearner(cfg)
+        gen = torch.Generator().manual_seed(78)
+        perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+        g0, d0 = sd_clone(L.gen_model), sd_clone(L.disc_model)
+        images = torch.randint(0, 256, (24, data_res, data_res, 3), generator=gen, dtype=torch.uint8).numpy()
+        ds = PILBoxDataset(images, init_res)
+        dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=L.batch_size, drop_last=True))
+
+        after_inc = []
+        for net, tag in ((L.gen_model, "g"), (L.disc_model, "d")):
+            orig = net.increase_scale
+
+            def wrapped(orig=orig, net=net, tag=tag):
+                orig()
+                perturb_zero_params(net, gen)          # the new block's zero-initialised biases / noise weights
+                after_inc.append((tag, sd_clone(net)))
+            net.increase_scale = wrapped
+
+        losses, trace, iter_snaps = [], [], {}
+        orig_backward = torch.Tensor.backward
+
+        def rec_backward(self, *a, **k):
+            losses.append(float(self.detach()))
+            if len(losses) % 2 == 1:                     # D-step backward: the iteration's state is settled here
+                if len(trace) in snap_iters:
+                    iter_snaps[len(trace)] = (sd_clone(L.gen_model), sd_clone(L.disc_model))
+                trace.append(dict(res=int(L.gen_model.curr_res), fade=bool(L.gen_model.fade_in_phase),
+                                  alpha=float(L.gen_model.alpha), bs=int(L.batch_size), phase=int(L.curr_phase_num),
+                                  lr_d=float(L.opt_disc.param_groups[0]["lr"]), lr_g=float(L.opt_gen.param_groups[0]["lr"]),
+                                  beta=float(L.beta), img_num=int(L.curr_img_num)))
+            return orig_backward(self, *a, **k)
+
+        torch.Tensor.backward = rec_backward
+        try:
+            with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+                L.train(dl, num_main_iters=iters)
+        finally:
+            torch.Tensor.backward = orig_backward
+        lagged = {k: v.detach().clone() for k, v in L.lagged_params.items()}
+        out = dict(model=model, init_res=init_res, res=res, iters=iters, fmap_max=SMALL_FMAP_MAX, len_latent=cfg.len_latent,
+                   bs_dict=dict(cfg.bs_dict), nimg_transition=nimg_transition, lr_fctr_dict=dict(cfg.lr_fctr_dict),
+                   lr_base=cfg.lr_base, data_res=data_res, images_u8=torch.from_numpy(images),
+                   g_sd0=g0, d_sd0=d0, after_inc=after_inc, served=ds.served, tape=tape.events, losses=losses, trace=trace,
+                   iter_snaps=iter_snaps,      # parameters at the START of those iterations (behind that many updates)
+                   g_sd1=sd_clone(L.gen_model), d_sd1=sd_clone(L.disc_model), lagged=lagged, beta=float(L.beta),
+                   final=dict(res=int(L.gen_model.curr_res), fade=bool(L.gen_model.fade_in_phase),
+                              alpha=float(L.gen_model.alpha), phase=int(L.curr_phase_num), img_num=int(L.curr_img_num),
+                              nimg_transition_lst=[float(v) for v in L.nimg_transition_lst],
+                              progressively_grow=bool(L.progressively_grow), bs=int(L.batch_size)))
+        if model == "StyleGAN":
+            out["w_ewma"] = L.gen_model.w_ewma.detach().clone()
+        return out
+    finally:
+        _unpatch(ref)
+
+
 RESNET_FMAP = 8          # reference constants resnetgan/architectures.py:19-20 (FMAP_G = FMAP_D = 64) patched for small fixtures
 RESNET_LATENT = 16
 
@@ -510,6 +610,8 @@ def main():
         "pro_nets_res8_fade.pt": lambda: golden_pro_nets(ref, 8, 4, True),
         "style_train_res16.pt": lambda: golden_train_steps(ref, "StyleGAN", 16, 4, 2),
         "pro_train_res8.pt": lambda: golden_train_steps(ref, "ProGAN", 8, 4, 2),
+        "style_grow_4to8.pt": lambda: golden_grow(ref, "StyleGAN"),
+        "pro_grow_4to8.pt": lambda: golden_grow(ref, "ProGAN"),
         "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),

@@ -4,6 +4,7 @@ import math
 
 import torch
 
+import gan_lab_b200._kernels as K
 from gan_lab_b200.config import default_config
 from gan_lab_b200.utils import custom_layers as CL
 from gan_lab_b200.utils.latent_utils import TapeSource, set_random_source
@@ -16,6 +17,7 @@ MBSTD_CASES = ["mbstd_n8", "mbstd_n4", "mbstd_n6", "mbstd_n1", "mbstd_n16"]
 STYLE_NETS = ["style_nets_res16.pt", "style_nets_res16_fade.pt"]
 PRO_NETS = ["pro_nets_res16.pt", "pro_nets_res8_fade.pt"]
 TRAIN_CASES = [("style_train_res16.pt", "StyleGAN"), ("pro_train_res8.pt", "ProGAN")]
+GROW_CASES = [("style_grow_4to8.pt", "StyleGAN"), ("pro_grow_4to8.pt", "ProGAN")]
 RESNET_NETS = ["resnet_nets_res64.pt", "resnet_nets_res32.pt"]
 
 
@@ -275,6 +277,139 @@ def case_learner_train(golden, dev, fname, model):
     assert abs(L.beta - g["beta"]) < 1e-12
     if model == "StyleGAN":
         close(L.gen_model.w_ewma, g["w_ewma"], rtol=1e-3, atol=1e-5)
+
+
+class ReplayLoader(object):
+    """Feeds a learner the real samples the reference's own loader served (recorded in the fixture), in order, `bs` at a
+    time; the learner may change `batch_sampler.batch_size` and call `set_resolution` as it grows."""
+
+    def __init__(self, served, bs, dev):
+        self.dataset = [x for _, x in served]
+        self.batch_sampler = type("_BS", (), {"batch_size": bs})()
+        self.cursor, self.dev, self.resolutions = 0, dev, []
+
+    def set_resolution(self, res):
+        self.resolutions.append(res)
+
+    def __iter__(self):
+        while self.cursor < len(self.dataset):
+            n = self.batch_sampler.batch_size
+            xs = self.dataset[self.cursor:self.cursor + n]
+            self.cursor += n
+            yield (torch.stack(xs).to(self.dev),)
+
+
+def _grow_learner(g, dev, model):
+    from gan_lab_b200.progan.learner import ProGANLearner
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    kw = dict(res=g["res"], init_res=g["init_res"], batch_size=g["bs_dict"][g["init_res"]], dev=dev,
+              len_latent=g["len_latent"], bs_dict=dict(g["bs_dict"]), nimg_transition=g["nimg_transition"],
+              lr_fctr_dict=dict(g["lr_fctr_dict"]), res_dataset=g["data_res"])
+    if model == "StyleGAN":
+        return StyleGANLearner(default_config("StyleGAN", len_dlatent=g["len_latent"],
+                                              cutoff_trunc_trick=int(math.log2(g["res"])) - 2, **kw))
+    return ProGANLearner(default_config("ProGAN", **kw))
+
+
+def _adam_close(mine, ref, lr, steps, what, frac=0.03):
+    """Parameters behind `steps` Adam(beta1=0) updates: a rounding-level gradient difference flips a sign-like update by
+    2*lr, so allow scattered flips (never more than `frac` of a network) and bound every element by 2*lr*steps."""
+    bad = tot = 0
+    for k, v in ref.items():
+        d = (mine[k].detach() - v).abs()
+        assert float(d.max()) <= 2.001 * lr * steps + 1e-6, (what, k, float(d.max()))
+        bad += int((d > 2e-5 + 1e-4 * v.abs()).sum()); tot += v.numel()
+    assert bad <= frac * tot, (what, bad, tot)
+
+
+def case_learner_grow(golden, dev, fname, model):
+    """Learner.train() through a resolution increase vs the reference: phase bookkeeping, the
+    optimiser / scheduler / EWMA rebuild at each phase change, the moving alpha incl. the real-image blend, the final
+    phase.  The new block's initial values are taken from the reference (they are not taped draws); everything carried
+    over (old blocks, torgb -> prev_torgb, lagged generator) is the learner's own."""
+    g = _to(golden(fname), dev)
+    L = _grow_learner(g, dev, model)
+    _load(L.gen_model, g["g_sd0"]); _load(L.disc_model, g["d_sd0"]); _load(L.gen_model_lagged, g["g_sd0"])
+    snaps = {"g": [sd for t, sd in g["after_inc"] if t == "g"], "d": [sd for t, sd in g["after_inc"] if t == "d"]}
+    lr_max = g["lr_base"] * max(g["lr_fctr_dict"][r] for r in (g["init_res"], g["res"]))
+    steps_so_far = [0]
+    # one Adam(beta2=.99) step moves an element by at most lr*sqrt((1-.99^t)/.01) <= lr*t, t = steps since the optimiser was
+    # (re)built at the last phase change; phases are nimg_transition/bs iterations long
+    per = g["nimg_transition"] // min(g["bs_dict"][g["init_res"]], g["bs_dict"][g["res"]])
+    for net, tag, fresh_prefix in ((L.gen_model, "g", ("torgb.",)), (L.disc_model, "d", ("fromrgb.",))):
+        orig = net.increase_scale
+
+        def wrapped(orig=orig, net=net, tag=tag, fresh_prefix=fresh_prefix):
+            before = {id(p) for p in net.parameters()}
+            orig()
+            snap = snaps[tag].pop(0)
+            named = dict(net.named_parameters())
+            assert set(named.keys()) == set(snap.keys()), (set(named.keys()) ^ set(snap.keys()))
+            # prev_torgb / prev_fromrgb are new Parameter objects holding the old torgb / fromrgb VALUES: carried, not fresh
+            fresh = [k for k, p in named.items() if id(p) not in before and not k.startswith("prev_")]
+            assert fresh and any(k.startswith(fresh_prefix) for k in fresh), fresh
+            with torch.no_grad():
+                for k in fresh:                                # freshly initialised by increase_scale()
+                    assert named[k].shape == snap[k].shape, k
+                    named[k].copy_(snap[k])
+            # what the learner carried over (old blocks, re-indexed; torgb -> prev_torgb) must be what the reference carried
+            carried = {k: v for k, v in snap.items() if k not in fresh}
+            assert len(carried) == len(before), (len(carried), len(before))
+            _adam_close(named, carried, lr_max, per, "carried-" + tag, frac=0.01)
+        net.increase_scale = wrapped
+
+    dl = ReplayLoader(g["served"], L.batch_size, dev)
+    set_random_source(TapeSource(g["tape"], dev))
+    losses, trace = [], []
+    orig_d, orig_g = L.disc_step, L.gen_step
+
+    def disc_step(xb):
+        # Adam(beta1=0) makes the trajectory chaotic at fp32 rounding level (the reference re-run from parameters perturbed by
+        # 3e-7 drifts from itself faster than this path drifts from it), so every iteration is checked on its own: compare
+        # with the reference's parameters at the start of the iteration, then continue FROM the reference's parameters.
+        snap = g["iter_snaps"].get(len(trace))
+        if snap is not None:
+            _adam_close(L.gen_model.state_dict(), snap[0], lr_max, per, "G@%d" % len(trace), frac=0.01)
+            _adam_close(L.disc_model.state_dict(), snap[1], lr_max, per, "D@%d" % len(trace), frac=0.01)
+            with torch.no_grad():
+                for net, sd in ((L.gen_model, snap[0]), (L.disc_model, snap[1])):
+                    for k, v in net.state_dict().items():
+                        v.copy_(sd[k])
+            K.weights_updated()
+        trace.append(dict(res=int(L.gen_model.curr_res), fade=bool(L.gen_model.fade_in_phase), alpha=float(L.gen_model.alpha),
+                          bs=int(L.batch_size), phase=int(L.curr_phase_num), lr_d=float(L.opt_disc.param_groups[0]["lr"]),
+                          lr_g=float(L.opt_gen.param_groups[0]["lr"]), beta=float(L.beta), img_num=int(L.curr_img_num)))
+        losses.append(float(orig_d(xb)))
+        steps_so_far[0] += 1
+        return torch.tensor(losses[-1])
+
+    L.disc_step = disc_step
+    L.gen_step = lambda: losses.append(float(orig_g())) or torch.tensor(losses[-1])
+    L.train(dl, num_main_iters=g["iters"])
+    case_learner_grow.debug = dict(losses=losses, ref_losses=g["losses"], trace=trace)
+
+    assert len(trace) == len(g["trace"])
+    for mine, ref in zip(trace, g["trace"]):
+        for k, v in ref.items():
+            assert (abs(mine[k] - v) < 1e-12) if isinstance(v, float) else (mine[k] == v), (k, mine, ref)
+    fin = g["final"]
+    G = L.gen_model
+    assert (int(G.curr_res), bool(G.fade_in_phase), float(G.alpha), L.curr_phase_num, L.curr_img_num, L.batch_size) == \
+           (fin["res"], fin["fade"], fin["alpha"], fin["phase"], fin["img_num"], fin["bs"])
+    assert [float(v) for v in L.nimg_transition_lst] == fin["nimg_transition_lst"]
+    assert bool(L._progressively_grow) == fin["progressively_grow"]
+    assert dl.resolutions == [g["res"]]
+    # losses: the first is a pure function of the inputs; later ones sit behind Adam's sign-like updates
+    assert len(losses) == len(g["losses"])
+    for i, (a, b) in enumerate(zip(losses, g["losses"])):
+        assert abs(a - b) < (1e-4 if i == 0 else 5e-4) * max(1.0, abs(b)), (i, a, b)
+    _adam_close(L.gen_model.state_dict(), g["g_sd1"], lr_max, per, "G", frac=0.01)
+    _adam_close(L.disc_model.state_dict(), g["d_sd1"], lr_max, per, "D", frac=0.01)
+    lag = dict(L.gen_model_lagged.named_parameters())
+    assert set(lag.keys()) == set(g["lagged"].keys())
+    _adam_close(lag, g["lagged"], lr_max, g["iters"], "EWMA-G", frac=0.01)
+    if model == "StyleGAN":
+        close(L.gen_model.w_ewma, g["w_ewma"], rtol=1e-3, atol=1e-4)
 
 
 def case_shared_penalty_forward(dev, gp):

@@ -64,6 +64,11 @@ def test_learner_train(golden, fname, model):
     PC.case_learner_train(golden, DEV, fname, model)
 
 
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+def test_learner_grow(golden, fname, model):
+    PC.case_learner_grow(golden, DEV, fname, model)
+
+
 @pytest.mark.parametrize("gp", ["r1", "r2"])
 def test_shared_penalty_forward(gp):
     PC.case_shared_penalty_forward(DEV, gp)
