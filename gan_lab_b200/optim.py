@@ -127,6 +127,62 @@ class FusedAdam(torch.optim.Optimizer):
         self._tab[key] = (flat, devbuf[:5 * n], devbuf[5 * n:6 * n])
         return devbuf[:5 * n], devbuf[5 * n:6 * n]
 
+    # -- torch.optim.Adam-compatible state dicts (checkpoints) -----------------------------
+    _TORCH_ADAM_GROUP_DEFAULTS = dict(amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False,
+                                      fused=None, decoupled_weight_decay=False)
+
+    def _true_step(self, st):
+        """Steps taken by the parameter behind state `st`: the device-side count of its cohort when it exists (under
+        CUDA-graph replay the host-side counter does not move), else the host-side count."""
+        h = self._hyper.get(st.get('cohort'))
+        if h is not None:
+            return int(round(float(h['t'][3])))       # device -> host read; checkpoints are not on the hot path
+        return int(st.get('step', 0))
+
+    def state_dict(self):
+        """The layout torch.optim.Adam writes and reads (reference progan/learner.py:1271-1272, 1396-1397): per parameter
+        `step` (a float32 scalar tensor), `exp_avg`, `exp_avg_sq`; the moments are handed out contiguous (they live in the
+        parameter's channels_last memory here)."""
+        sd = super(FusedAdam, self).state_dict()
+        steps = {id(st): self._true_step(st) for st in self.state.values()}
+        by_index = {}
+        index = 0
+        for group in self.param_groups:
+            for p in group['params']:
+                if p in self.state and self.state[p]:
+                    by_index[index] = steps[id(self.state[p])]
+                index += 1
+        state = {}
+        for idx, st in sd['state'].items():
+            state[idx] = {'step': torch.tensor(float(by_index[idx]), dtype=torch.float32),
+                          'exp_avg': st['exp_avg'].detach().clone(memory_format=torch.contiguous_format),
+                          'exp_avg_sq': st['exp_avg_sq'].detach().clone(memory_format=torch.contiguous_format)}
+        groups = [{**self._TORCH_ADAM_GROUP_DEFAULTS, **g} for g in sd['param_groups']]
+        return {'state': state, 'param_groups': groups}
+
+    def load_state_dict(self, state_dict):
+        """Accepts torch.optim.Adam's state dict (a reference checkpoint) or this class's own."""
+        super(FusedAdam, self).load_state_dict(state_dict)
+        self._hyper, self._tab, self._capture_slots = {}, {}, None
+        steps = [int(round(float(st['step']))) for st in self.state.values() if st]
+        self._nsteps = max(steps) if steps else 0
+        for p, st in self.state.items():
+            if not st:
+                continue
+            t = int(round(float(st['step'])))
+            st['step'] = t
+            st['cohort'] = self._nsteps - t            # parameters that joined later have taken fewer steps
+            for key in ('exp_avg', 'exp_avg_sq'):      # the kernel walks p, g, m, v with one linear index
+                if st[key].stride() != p.stride() or st[key].device != p.device or st[key].dtype != p.dtype:
+                    st[key] = torch.empty_like(p, memory_format=torch.preserve_format).copy_(st[key])
+            if st['cohort'] not in self._hyper:
+                b1, b2 = next(g['betas'] for g in self.param_groups if any(q is p for q in g['params']))
+                self._hyper[st['cohort']] = {
+                    't': torch.tensor([0.0, 1.0 - b1 ** t, 1.0 - b2 ** t, float(t)], dtype=torch.float32, device=p.device),
+                    'lr': None}
+        for st in self.state.values():
+            st.pop('amsgrad', None)
+
     @torch.no_grad()
     def step(self, closure=None):
         assert closure is None

@@ -326,6 +326,105 @@ class ProGANLearner(GANLearner):
         loss_g = self.gen_step()
         return loss_d, loss_g
 
+    # ------------------------------------------------------------------ checkpoints (reference progan/learner.py:1238-1460)
+    @property
+    def progressively_grow(self):
+        return self._progressively_grow
+
+    def _extra_checkpoint_entries(self):
+        return {}
+
+    def save_model(self, save_path):
+        """reference progan/learner.py:1238-1298 (stylegan/learner.py:433-506 adds `_extra_checkpoint_entries`); the file is
+        readable by the reference's own load_model.  Under data parallelism only rank 0 writes (replicas are identical)."""
+        from pathlib import Path
+        from .. import checkpoint as ckpt
+        if self.dp is not None and getattr(self.dp, 'rank', 0) != 0:
+            return
+        common = self._checkpoint_common()
+        gmeta, dmeta = self._model_metadata()
+        lagged = None
+        if self.config.use_ewma_gen and self.lagged_params is not None:
+            lagged = ckpt.IndexedOrderedDict((k, v.detach().clone(memory_format=torch.contiguous_format))
+                                             for k, v in self.lagged_params.items())
+        save_path = Path(save_path)
+        save_path.parents[0].mkdir(parents=True, exist_ok=True)
+        ckpt.save({
+            **common,
+            'curr_res': self.gen_model.curr_res,
+            'alpha': self.gen_model.alpha,
+            **self._extra_checkpoint_entries(),
+            'gen_model_metadata': gmeta,
+            'gen_model_lagged_state_dict': ckpt.plain_state_dict(self.gen_model_lagged) if self.config.use_ewma_gen else None,
+            'disc_model_metadata': dmeta,
+            'nimg_transition_lst': self.nimg_transition_lst,
+            'latent_distribution': self.latent_distribution,
+            'curr_phase_num': self.curr_phase_num,
+            'lagged_params': lagged,
+            'progressively_grow': self.progressively_grow,
+        }, save_path)
+
+    def _restore_extra_checkpoint_entries(self, checkpoint):
+        pass
+
+    def load_model(self, load_path, dev_of_saved_model='cpu', dev=None):
+        """reference progan/learner.py:1300-1460 / stylegan/learner.py:508-682, in the reference's order: config, networks
+        grown to the stored resolution, alpha (which also settles fade_in_phase), EWMA generator, parameters, optimisers
+        (rebuilt for the stored phase by the `optimizer` setter, then their Adam state), bookkeeping.  Reads files written by
+        the reference itself.  `train()` afterwards takes the reference's `pretrained_model` branches."""
+        from ..utils.custom_layers import as_native_upsampler, as_native_pooler
+        checkpoint = self._load_checkpoint_file(load_path, dev_of_saved_model)
+        self._adopt_checkpoint_config(checkpoint, dev)
+        c = self.config
+        self._latent_distribution = checkpoint['latent_distribution']
+        gmeta, dmeta = checkpoint['gen_model_metadata'], checkpoint['disc_model_metadata']
+        self.gen_model_metadata, self.disc_model_metadata = gmeta, dmeta
+        self.gen_model_upsampler = as_native_upsampler(gmeta['gen_model_upsampler'])
+        self.disc_model_downsampler = as_native_pooler(dmeta['disc_model_downsampler'])
+        self.num_classes_gen, self.num_classes_disc = gmeta['num_classes_gen'], dmeta['num_classes_disc']
+        self.state = GrowthState()
+        self._build_models()
+        self._restore_extra_checkpoint_entries(checkpoint)
+        assert c.init_res <= c.res_samples
+        _curr_res = checkpoint['curr_res']
+        if _curr_res > 4:
+            _init_res_log2 = int(np.log2(_curr_res))
+            if float(_curr_res) != 2 ** _init_res_log2:
+                raise ValueError('Only resolutions that are powers of 2 are supported.')
+            for _ in range(_init_res_log2 - 2):
+                self.gen_model.increase_scale()
+                self.disc_model.increase_scale()
+        self.gen_model.alpha = checkpoint['alpha']      # applies to both networks and takes care of fade_in_phase
+        assert self.gen_model.cls_base is self.disc_model.cls_base
+        self.gen_model_lagged = None
+        if c.use_ewma_gen:
+            with torch.no_grad():
+                self.gen_model_lagged = copy.deepcopy(self.gen_model)
+        self.gen_model.to(c.dev)
+        self.gen_model.load_state_dict(checkpoint['gen_model_state_dict'])
+        self.gen_model.zero_grad()
+        if c.use_ewma_gen:
+            self.gen_model_lagged.to(c.dev)
+            self.gen_model_lagged.load_state_dict(checkpoint['gen_model_lagged_state_dict'])
+            self._restore_lagged_extras(checkpoint)
+            self.gen_model_lagged.zero_grad()
+        self.disc_model.to(c.dev)
+        self.disc_model.load_state_dict(checkpoint['disc_model_state_dict'])
+        self.disc_model.zero_grad()
+        self.lagged_params = None          # train() re-aliases it to the live parameters on resume (reference :462-472)
+        self._graph, self._graph_eager_iters = None, 0
+        self._load_checkpoint_common(checkpoint)
+        self.nimg_transition_lst = checkpoint['nimg_transition_lst']
+        self.latent_distribution = checkpoint['latent_distribution']
+        self.curr_phase_num = checkpoint['curr_phase_num']
+        self.eps = c.eps_drift > 0
+        self._progressively_grow = checkpoint['progressively_grow']
+        if hasattr(self, 'delta_alpha'):
+            del self.delta_alpha
+
+    def _restore_lagged_extras(self, checkpoint):
+        pass
+
     # ------------------------------------------------------------------ train loop
     def train(self, train_dl, valid_dl=None, z_valid_dl=None, num_main_iters=None, num_gen_iters=None,
               num_disc_iters=None, log_every=0, step_callback=None):
@@ -352,16 +451,28 @@ class ProGANLearner(GANLearner):
             self.nimg_transition = round_transition()
         if self.not_trained_yet:
             self.nimg_transition_lst = [self.nimg_transition]
+        if self.not_trained_yet or self.pretrained_model:
+            # on a resume the reference re-aliases `lagged_params` to the live parameters as well (:462-472): the EWMA
+            # generator restarts from the live one at the first step after a load_model()
             self.beta = None
             if c.use_ewma_gen:
                 self.beta = self.get_smoothing_ewma_beta(half_life=EWMA_SMOOTHING_HALFLIFE) if COMPUTE_EWMA_VIA_HALFLIFE \
                     else EWMA_SMOOTHING_BETA
                 self._init_lagged()
                 self._attach_ewma()
-            self.train_dataiter = iter(train_dl)
         if self.sched_bool:
+            if not self.pretrained_model:
+                self.sched_stop_step = 0
             self._set_scheduler()
-        if self.gen_model.fade_in_phase and not hasattr(self, 'delta_alpha'):
+        if self.not_trained_yet:
+            self.train_dataiter = iter(train_dl)
+        elif self.pretrained_model:                        # reference :488-494
+            if hasattr(train_dl, 'batch_sampler') and train_dl.batch_sampler is not None:
+                train_dl.batch_sampler.batch_size = self.batch_size
+            if hasattr(train_dl, 'set_resolution'):
+                train_dl.set_resolution(self.gen_model.curr_res)
+            self.train_dataiter = iter(train_dl)
+        if self.gen_model.fade_in_phase and (self.pretrained_model or not hasattr(self, 'delta_alpha')):
             self.delta_alpha = self.batch_size / ((self.nimg_transition / num_disc_iters) - self.batch_size)
 
         self.last_losses = (None, None)
@@ -445,6 +556,25 @@ class ProGANLearner(GANLearner):
             if self.not_trained_yet:
                 self.not_trained_yet = False
 
+            # ---- periodic checkpoint (reference :960-985).  The reference rebuilds the optimisers before every save "for
+            # [the] niche case when training ends right when alpha becomes 1" -- Adam's moments restart there and the LR
+            # schedulers stay attached to the replaced optimisers until the next phase change; kept as is.
+            if (itr + 1) % c.num_iters_save_model == 0:
+                self._set_optimizer()
+                self.gen_model.eval(); self.disc_model.eval()
+                if c.use_ewma_gen:
+                    self.gen_model_lagged.eval()
+                self.save_model(c.save_model_dir / (self.model.casefold().replace(' ', '') + '_model.tar'))
+                self.gen_model.train(); self.disc_model.train()
+                if c.use_ewma_gen:
+                    self.gen_model_lagged.train()
+
         for p in self.disc_model.parameters():
             p.requires_grad_(True)
+        # end of train() (reference :1016-1030): fresh optimisers (every train() call starts Adam from zero moments), the
+        # networks left in eval mode.  The reference also parks them on the CPU; device placement is left alone here.
+        self._set_optimizer()
+        self.gen_model.eval(); self.disc_model.eval()
+        if c.use_ewma_gen:
+            self.gen_model_lagged.eval()
         return self.last_losses

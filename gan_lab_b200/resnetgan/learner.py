@@ -2,8 +2,8 @@
 
 Keeps the reference's constructor `(config: argparse.Namespace)`, its public attributes (`gen_model`,
 `disc_model`, `opt_gen`, `opt_disc`, `batch_size`, `config`, `loss`, `gradient_penalty`, `optimizer`,
-`lr_sched`) and `calc_gp`; metrics, plotting and checkpoint I/O are outside
-the hot path and not built.  With `config.model == 'ResNet GAN'` this class builds the 32 / 64-pixel ResNet generator and
+`lr_sched`), `calc_gp` and `save_model` / `load_model` (files interchangeable with the reference's); metrics and
+plotting are outside the hot path and not built.  With `config.model == 'ResNet GAN'` this class builds the 32 / 64-pixel ResNet generator and
 discriminator (reference :183-232) and `train()` runs the reference's loop (:463-776: generator step(s) FIRST, then
 `num_disc_iters` discriminator steps per main iteration); it is also the shared machinery the ProGAN / StyleGAN
 learners build on.
@@ -32,6 +32,8 @@ class LearnerConfigCopy(object):
     def __init__(self, config, learner_class: str, nonredefinable_attrs: tuple, redefinable_from_learner_attrs: tuple):
         assert isinstance(config, argparse.Namespace) and 'model' in config.__dict__
         object.__setattr__(self, '__dict__', copy.deepcopy(config.__dict__))
+        self.__dict__['model_name'] = {'GANLearner': 'resnetgan', 'ProGANLearner': 'progan',
+                                       'StyleGANLearner': 'stylegan'}.get(learner_class, learner_class)
         self.__dict__['learner_class'] = learner_class
         self.__dict__['_nonredefinable_attrs'] = nonredefinable_attrs
         self.__dict__['_redefinable_from_learner_attrs'] = redefinable_from_learner_attrs
@@ -46,7 +48,7 @@ class LearnerConfigCopy(object):
         object.__setattr__(self, name, value)
 
     def __str__(self):
-        hidden = ('_nonredefinable_attrs', '_redefinable_from_learner_attrs', 'learner_class')
+        hidden = ('_nonredefinable_attrs', '_redefinable_from_learner_attrs', 'model_name', 'learner_class')
         return '\n'.join(f'  {k}: {v}' for k, v in vars(self).items() if k not in hidden)
 
 
@@ -111,6 +113,7 @@ class GANLearner(object):
                 raise ValueError('GANLearner currently only supports 32 pixel and 64 pixel GAN architectures.\n'
                                  'If a different generated sample resolution is desired, please use the\n'
                                  'ProGAN or StyleGAN models featured in this package instead.')
+            self._fmap_g, self._fmap_d = _fmap_g, _fmap_d
             self.gen_model = _gen_model(len_latent=c.len_latent, fmap=_fmap_g, upsampler=self.gen_model_upsampler,
                                         blur_type=c.blur_type, nl=self.nl, num_classes=0, equalized_lr=c.use_equalized_lr)
             self.disc_model = _disc_model(fmap=_fmap_d, pooler=self.disc_model_downsampler, blur_type=c.blur_type, nl=self.nl,
@@ -134,7 +137,14 @@ class GANLearner(object):
             self.sched_stop_step = 0
         self.curr_img_num = 0
         self.tot_num_epochs = None
+        self.dataset_sz = None
         self.not_trained_yet = True
+        # bookkeeping of the reference's metrics code (resnetgan/learner.py:274-290); carried through checkpoints unchanged
+        self.num_classes_gen = self.num_classes_disc = 0
+        self.valid_z = self.valid_label = self.rand_idxs = None
+        self.grid_inputs_constructed = False
+        self.gen_metrics_num = self.disc_metrics_num = 0
+        self.ds_mean = self.ds_std = None
         if self._model == 'ResNet GAN':
             self._set_loss()
             self._set_optimizer()
@@ -248,6 +258,11 @@ class GANLearner(object):
                 self.scheduler_disc.step()
             if self.not_trained_yet:
                 self.not_trained_yet = False
+            if (itr + 1) % c.num_iters_save_model == 0:          # reference :737-749
+                self.gen_model.eval(); self.disc_model.eval()
+                self.save_model(c.save_model_dir / (self.model.casefold().replace(' ', '') + '_model.tar'))
+                self.gen_model.train(); self.disc_model.train()
+        self.gen_model.eval(); self.disc_model.eval()             # reference :771-776 (it also parks them on the CPU)
         return self.last_losses
 
     # ------------------------------------------------------------------ gradient penalties
@@ -288,6 +303,135 @@ class GANLearner(object):
             return ops.gp_norm(outb_grads, 1., self.config.lda / (2. * n_hw))
         return ops.sumsq(outb_grads, self.config.lda / (2. * n_hw))
 
+    # ------------------------------------------------------------------ checkpoints (reference :1076-1250)
+    def _checkpoint_common(self):
+        """Entries every learner writes (reference resnetgan/learner.py:1104-1137) with the reference's value types."""
+        from .. import checkpoint as ckpt
+        if self.not_trained_yet:
+            raise Exception('Please train your model for atleast 1 iteration before saving.')
+        c = self.config
+        valid_z = self.valid_z if self.valid_z is not None else torch.zeros(c.img_grid_sz ** 2, c.len_latent)
+        mean = self.ds_mean if self.ds_mean is not None else torch.full((FMAP_SAMPLES, 1, 1), .5)
+        std = self.ds_std if self.ds_std is not None else torch.full((FMAP_SAMPLES, 1, 1), .5)
+        return {
+            'config': c,
+            'gen_model_state_dict': ckpt.plain_state_dict(self.gen_model),
+            'disc_model_state_dict': ckpt.plain_state_dict(self.disc_model),
+            'nl': ckpt.to_reference_module(self.nl),
+            'sched_stop_step': self.sched_stop_step,
+            'lr_sched': self.lr_sched,
+            'scheduler_gen_state_dict': self.scheduler_gen.state_dict() if self.sched_bool else None,
+            'scheduler_disc_state_dict': self.scheduler_disc.state_dict() if self.sched_bool else None,
+            'optimizer': self.optimizer,
+            'opt_gen_state_dict': self.opt_gen.state_dict(),
+            'opt_disc_state_dict': self.opt_disc.state_dict(),
+            'loss': self.loss,
+            'gradient_penalty': self.gradient_penalty,
+            'batch_size': self.batch_size,
+            'curr_dataset_batch_num': self.curr_dataset_batch_num,
+            'curr_epoch_num': self.curr_epoch_num,
+            'tot_num_epochs': self.tot_num_epochs,
+            'dataset_sz': self.dataset_sz,
+            'ac': self.ac, 'cond_gen': self.cond_gen, 'cond_disc': self.cond_disc,
+            'valid_z': valid_z.to('cpu'),
+            'valid_label': self.valid_label,
+            'grid_inputs_constructed': self.grid_inputs_constructed,
+            'rand_idxs': self.rand_idxs,
+            'gen_metrics_num': self.gen_metrics_num,
+            'disc_metrics_num': self.disc_metrics_num,
+            'curr_img_num': self.curr_img_num,
+            'not_trained_yet': self.not_trained_yet,
+            'ds_mean': mean, 'ds_std': std,
+        }
+
+    def _model_metadata(self):
+        from .. import checkpoint as ckpt
+        return ({'gen_model_upsampler': ckpt.to_reference_module(self.gen_model_upsampler),
+                 'num_classes_gen': self.num_classes_gen},
+                {'disc_model_downsampler': ckpt.to_reference_module(self.disc_model_downsampler),
+                 'num_classes_disc': self.num_classes_disc})
+
+    def save_model(self, save_path):
+        """reference resnetgan/learner.py:1076-1137; the file is readable by the reference's own load_model.  Under data
+        parallelism only rank 0 writes (replicas are identical)."""
+        from pathlib import Path
+        from .. import checkpoint as ckpt
+        if self.dp is not None and getattr(self.dp, 'rank', 0) != 0:
+            return
+        gmeta, dmeta = self._model_metadata()
+        gmeta = {'gen_model': self.gen_model.__class__, 'fmap_g': self._fmap_g, **gmeta}
+        dmeta = {'disc_model': self.disc_model.__class__, 'fmap_d': self._fmap_d, **dmeta}
+        save_path = Path(save_path)
+        save_path.parents[0].mkdir(parents=True, exist_ok=True)
+        ckpt.save({**self._checkpoint_common(), 'gen_model_metadata': gmeta, 'disc_model_metadata': dmeta}, save_path)
+
+    def _load_checkpoint_file(self, load_path, dev_of_saved_model):
+        from .. import checkpoint as ckpt
+        dev_of_saved_model = dev_of_saved_model.casefold()
+        assert dev_of_saved_model in ('cpu', 'cuda')
+        return ckpt.load(load_path, map_location=(lambda storage, loc: storage) if dev_of_saved_model == 'cpu' else None)
+
+    def _adopt_checkpoint_config(self, checkpoint, dev):
+        """`self.config = checkpoint['config']` (reference :1145); `dev` optionally retargets the run (a reference file
+        written on a CPU box resumed on a GPU)."""
+        from ..utils.custom_layers import as_native_nl
+        self.config = checkpoint['config']
+        if dev is not None:
+            self.config.__dict__['dev'] = torch.device(dev)
+        self.nl = as_native_nl(checkpoint['nl'])
+
+    def _load_checkpoint_common(self, checkpoint):
+        """reference :1196-1239, in its order (the `optimizer` / `loss` setters rebuild the optimisers / loss first)."""
+        # NB on a first load `pretrained_model` is still False here, so the `lr_sched` setter resets the step offset the line
+        # before restored (reference :836-847, 1196-1197) -- kept as is
+        self.sched_stop_step = checkpoint['sched_stop_step']
+        self.lr_sched = checkpoint['lr_sched']
+        # the reference keeps the stored scheduler state dicts but overwrites them with a fresh scheduler's before use
+        # (progan/learner.py:1055-1062): LambdaLR restarts, `sched_stop_step` carries the offset -- same here
+        self._scheduler_gen_state_dict = checkpoint['scheduler_gen_state_dict']
+        self._scheduler_disc_state_dict = checkpoint['scheduler_disc_state_dict']
+        self.optimizer = checkpoint['optimizer']
+        self.opt_gen.load_state_dict(checkpoint['opt_gen_state_dict'])
+        self.opt_disc.load_state_dict(checkpoint['opt_disc_state_dict'])
+        self.batch_size = checkpoint['batch_size']
+        self.loss = checkpoint['loss']
+        self.gradient_penalty = checkpoint['gradient_penalty']
+        for key in ('curr_dataset_batch_num', 'curr_epoch_num', 'tot_num_epochs', 'dataset_sz', 'ac', 'cond_gen', 'cond_disc',
+                    'valid_label', 'grid_inputs_constructed', 'rand_idxs', 'gen_metrics_num', 'disc_metrics_num',
+                    'curr_img_num', 'not_trained_yet', 'ds_mean', 'ds_std'):
+            setattr(self, key, checkpoint[key])
+        if self.ac or self.cond_gen or self.cond_disc:
+            raise NotImplementedError('class conditioning / auxiliary classifier are off the benchmarked path; not built')
+        self.valid_z = checkpoint['valid_z'].to(self.config.dev)
+        self.pretrained_model = True
+
+    def load_model(self, load_path, dev_of_saved_model='cpu', dev=None):
+        """reference resnetgan/learner.py:1139-1250: rebuild the networks the file describes, load parameters, optimiser
+        state and bookkeeping; `train()` then continues from there.  Reads files written by the reference itself."""
+        from ..utils.custom_layers import as_native_upsampler, as_native_pooler
+        checkpoint = self._load_checkpoint_file(load_path, dev_of_saved_model)
+        self._adopt_checkpoint_config(checkpoint, dev)
+        c = self.config
+        gmeta, dmeta = checkpoint['gen_model_metadata'], checkpoint['disc_model_metadata']
+        self.gen_model_metadata, self.disc_model_metadata = gmeta, dmeta
+        self.gen_model_upsampler = as_native_upsampler(gmeta['gen_model_upsampler'])
+        self.disc_model_downsampler = as_native_pooler(dmeta['disc_model_downsampler'])
+        self.num_classes_gen, self.num_classes_disc = gmeta['num_classes_gen'], dmeta['num_classes_disc']
+        self.gen_model = gmeta['gen_model'](len_latent=c.len_latent, fmap=gmeta['fmap_g'], upsampler=self.gen_model_upsampler,
+                                            blur_type=c.blur_type, nl=self.nl, num_classes=self.num_classes_gen,
+                                            equalized_lr=c.use_equalized_lr)
+        self.gen_model.to(c.dev)
+        self.gen_model.load_state_dict(checkpoint['gen_model_state_dict'])
+        self.gen_model.zero_grad()
+        self.disc_model = dmeta['disc_model'](fmap=dmeta['fmap_d'], pooler=self.disc_model_downsampler, blur_type=c.blur_type,
+                                              nl=self.nl, num_classes=self.num_classes_disc, equalized_lr=c.use_equalized_lr)
+        self.disc_model.to(c.dev)
+        self.disc_model.load_state_dict(checkpoint['disc_model_state_dict'])
+        self.disc_model.zero_grad()
+        assert self.gen_model.res == self.disc_model.res
+        self._fmap_g, self._fmap_d = gmeta['fmap_g'], dmeta['fmap_d']
+        self._load_checkpoint_common(checkpoint)
+
     # ------------------------------------------------------------------ properties (reference :831-960)
     @property
     def lr_sched(self):
@@ -297,12 +441,15 @@ class GANLearner(object):
     def lr_sched(self, new_lr_sched):
         self._lr_sched = None
         self.sched_bool = False
+        if not self.pretrained_model:
+            self.sched_stop_step = None
         self.scheduler_gen = None
         self.scheduler_disc = None
         if new_lr_sched is not None:
             self._lr_sched = new_lr_sched.casefold()
             self.sched_bool = True
-            self.sched_stop_step = 0
+            if not self.pretrained_model:
+                self.sched_stop_step = 0
 
     @property
     def optimizer(self):

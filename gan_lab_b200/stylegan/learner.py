@@ -1,5 +1,7 @@
 """StyleGANLearner (reference gan_lab/stylegan/learner.py:90-217): StyleGenerator + StyleDiscriminator on the
 train loop inherited unchanged from ProGANLearner (reference stylegan/learner.py:90)."""
+import torch
+
 from ..progan.learner import ProGANLearner, NONREDEFINABLE_ATTRS as _PRO_ATTRS
 from .architectures import StyleGenerator, StyleDiscriminator
 
@@ -28,6 +30,41 @@ class StyleGANLearner(ProGANLearner):
         self.disc_model = StyleDiscriminator(
             final_res=c.res_samples, pooler=self.disc_model_downsampler, blur_type=c.blur_type, nl=self.nl, num_classes=0,
             equalized_lr=c.use_equalized_lr, mbstd_group_size=c.mbstd_group_size, state=self.state)
+
+    # ---- checkpoint entries StyleGAN adds (reference stylegan/learner.py:456-464, 545-553, 604-607)
+    def _extra_checkpoint_entries(self):
+        g = self.gen_model
+        w = g.w_ewma if g.w_ewma is not None else torch.zeros(self.config.len_dlatent)
+        # the reference re-copies the lagged generator from the live one right before it saves (progan/learner.py:968-971), so the
+        # `w_ewma_lagged` it writes is the live average
+        w_lag = w.detach().to('cpu').clone() if self.config.use_ewma_gen else None
+        return {'use_truncation_trick': g.use_truncation_trick, 'trunc_cutoff_stage': g.trunc_cutoff_stage,
+                'w_eval_psi': g.w_eval_psi, 'w_ewma_beta': g.w_ewma_beta, 'w_ewma': w.detach().to('cpu').clone(),
+                'w_ewma_lagged': w_lag, 'trained_with_noise': g._trained_with_noise, 'pct_mixing_reg': g.pct_mixing_reg}
+
+    def _restore_extra_checkpoint_entries(self, checkpoint):
+        g = self.gen_model
+        g.w_ewma_beta = checkpoint['w_ewma_beta']
+        g._w_eval_psi = checkpoint['w_eval_psi']
+        g._trunc_cutoff_stage = checkpoint['trunc_cutoff_stage']
+        g.use_truncation_trick = checkpoint['use_truncation_trick']
+        g.w_ewma = checkpoint['w_ewma'].to(self.config.dev)
+        g._trained_with_noise = checkpoint['trained_with_noise']
+        g._use_noise = checkpoint['trained_with_noise']
+        g.pct_mixing_reg = checkpoint['pct_mixing_reg']
+        g._use_mixing_reg = True if g.pct_mixing_reg else False
+
+    def _update_gen_lagged(self):
+        """The lagged generator's parameters are always current here; what the reference's re-copy (progan/learner.py:235-242)
+        additionally refreshes is its copy of the live generator's `w_ewma` (used by the truncation trick in eval mode)."""
+        lag = super(StyleGANLearner, self)._update_gen_lagged()
+        if lag is not None and self.gen_model.w_ewma is not None:
+            lag.w_ewma = self.gen_model.w_ewma.detach().clone()
+        return lag
+
+    def _restore_lagged_extras(self, checkpoint):
+        # literal: the reference assigns the stored LAGGED average to the live generator here (stylegan/learner.py:607)
+        self.gen_model.w_ewma = checkpoint['w_ewma_lagged'].to(self.config.dev)
 
     @property
     def latent_distribution(self):

@@ -512,6 +512,95 @@ def golden_grow(ref, model="StyleGAN", init_res=4, res=8, bs_dict=None, nimg_tra
         _unpatch(ref)
 
 
+def golden_resume(ref, model="StyleGAN", iters_before=6, iters_after=3, ckpt_name=None):
+    """The reference saves a checkpoint in the MIDDLE of a fade-in (save_model), a fresh reference learner loads it
+    (load_model) and trains on.  The checkpoint file itself -- a real reference `.tar` -- is committed
+    next to the fixture; the fixture holds what the resumed reference run consumed and produced."""
+    _patch_small(ref)
+    try:
+        torch.manual_seed(91); np.random.seed(91)
+        over = dict(bs_dict={r: 4 for r in (4, 8, 16, 32, 64, 128, 256, 512, 1024)}, nimg_transition=16, res_dataset=8,
+                    lr_fctr_dict={4: 1., 8: 1.5, 16: 2., 32: 1., 64: 1., 128: 1., 256: 1., 512: 1., 1024: 1.})
+        learner_mod = ref.stylegan_learner if model == "StyleGAN" else ref.progan_learner
+        learner_cls = learner_mod.StyleGANLearner if model == "StyleGAN" else learner_mod.ProGANLearner
+
+        def build():
+            if model == "StyleGAN":
+                return _build_style_learner(ref, 8, 4, 4, **over)
+            cfg = make_config("ProGAN", res=8, init_res=4, batch_size=4, len_latent=SMALL_FMAP_MAX, **over)
+            with _quiet():
+                return learner_cls(cfg), cfg
+
+        L, cfg = build()
+        gen = torch.Generator().manual_seed(92)
+        perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+        images = torch.randint(0, 256, (24, 8, 8, 3), generator=gen, dtype=torch.uint8).numpy()
+
+        def loader(learner):
+            ds = PILBoxDataset(images, 4)
+            return ds, DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=learner.batch_size,
+                                                                 drop_last=True))
+
+        for net in (L.gen_model, L.disc_model):
+            orig = net.increase_scale
+            net.increase_scale = lambda orig=orig, net=net: (orig(), perturb_zero_params(net, gen))
+        ds, dl = loader(L)
+        with _quiet(), contextlib.redirect_stderr(io.StringIO()):
+            L.train(dl, num_main_iters=iters_before)
+        # save_model() reads valid_z, which only exists once an image grid has been computed (resnetgan/learner.py:388-389)
+        L.valid_z = torch.zeros(cfg.img_grid_sz ** 2, cfg.len_latent)
+        ckpt = GOLDEN_DIR / (ckpt_name or f"{model.lower()}_reference_checkpoint.tar")
+        L.save_model(ckpt)
+        saved = dict(alpha=float(L.gen_model.alpha), res=int(L.gen_model.curr_res), fade=bool(L.gen_model.fade_in_phase),
+                     img_num=int(L.curr_img_num), phase=int(L.curr_phase_num), g_sd=sd_clone(L.gen_model),
+                     d_sd=sd_clone(L.disc_model), lagged={k: v.detach().clone() for k, v in L.lagged_params.items()})
+
+        # ---- a fresh reference learner resumes from the file
+        # torch >= 2.6 defaults torch.load to weights_only=True, under which the unmodified reference cannot read its own
+        # checkpoints (they pickle the config object, nn.Modules and an IndexedOrderedDict); the harness restores the old default
+        L2, _ = build()
+        orig_load = torch.load
+        torch.load = lambda *a, **k: orig_load(*a, **{"weights_only": False, **k})
+        try:
+            with _quiet():
+                L2.load_model(ckpt, dev_of_saved_model="cpu")
+        finally:
+            torch.load = orig_load
+        ds2, dl2 = loader(L2)
+        losses, trace = [], []
+        orig_backward = torch.Tensor.backward
+
+        def rec_backward(self, *a, **k):
+            losses.append(float(self.detach()))
+            if len(losses) % 2 == 1:
+                trace.append(dict(res=int(L2.gen_model.curr_res), fade=bool(L2.gen_model.fade_in_phase),
+                                  alpha=float(L2.gen_model.alpha), bs=int(L2.batch_size), phase=int(L2.curr_phase_num),
+                                  lr_d=float(L2.opt_disc.param_groups[0]["lr"]), lr_g=float(L2.opt_gen.param_groups[0]["lr"]),
+                                  beta=float(L2.beta), img_num=int(L2.curr_img_num)))
+            return orig_backward(self, *a, **k)
+
+        torch.Tensor.backward = rec_backward
+        try:
+            with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+                L2.train(dl2, num_main_iters=iters_after)
+        finally:
+            torch.Tensor.backward = orig_backward
+        out = dict(model=model, checkpoint=ckpt.name, init_res=4, res=8, iters_before=iters_before, iters_after=iters_after,
+                   fmap_max=SMALL_FMAP_MAX, len_latent=cfg.len_latent, bs_dict=dict(cfg.bs_dict), nimg_transition=16,
+                   lr_fctr_dict=dict(cfg.lr_fctr_dict), lr_base=cfg.lr_base, data_res=8, saved=saved, served=ds2.served,
+                   tape=tape.events, losses=losses, trace=trace, g_sd1=sd_clone(L2.gen_model), d_sd1=sd_clone(L2.disc_model),
+                   lagged={k: v.detach().clone() for k, v in L2.lagged_params.items()}, beta=float(L2.beta),
+                   opt_gen_sd=L2.opt_gen.state_dict(), opt_disc_sd=L2.opt_disc.state_dict(),
+                   final=dict(res=int(L2.gen_model.curr_res), fade=bool(L2.gen_model.fade_in_phase),
+                              alpha=float(L2.gen_model.alpha), phase=int(L2.curr_phase_num), img_num=int(L2.curr_img_num),
+                              nimg_transition_lst=[float(v) for v in L2.nimg_transition_lst], bs=int(L2.batch_size)))
+        if model == "StyleGAN":
+            out["w_ewma"] = L2.gen_model.w_ewma.detach().clone()
+        return out
+    finally:
+        _unpatch(ref)
+
+
 RESNET_FMAP = 8          # reference constants resnetgan/architectures.py:19-20 (FMAP_G = FMAP_D = 64) patched for small fixtures
 RESNET_LATENT = 16
 
@@ -612,6 +701,8 @@ def main():
         "pro_train_res8.pt": lambda: golden_train_steps(ref, "ProGAN", 8, 4, 2),
         "style_grow_4to8.pt": lambda: golden_grow(ref, "StyleGAN"),
         "pro_grow_4to8.pt": lambda: golden_grow(ref, "ProGAN"),
+        "style_resume.pt": lambda: golden_resume(ref, "StyleGAN"),
+        "pro_resume.pt": lambda: golden_resume(ref, "ProGAN"),
         "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),

@@ -18,6 +18,7 @@ STYLE_NETS = ["style_nets_res16.pt", "style_nets_res16_fade.pt"]
 PRO_NETS = ["pro_nets_res16.pt", "pro_nets_res8_fade.pt"]
 TRAIN_CASES = [("style_train_res16.pt", "StyleGAN"), ("pro_train_res8.pt", "ProGAN")]
 GROW_CASES = [("style_grow_4to8.pt", "StyleGAN"), ("pro_grow_4to8.pt", "ProGAN")]
+RESUME_CASES = [("style_resume.pt", "StyleGAN"), ("pro_resume.pt", "ProGAN")]
 RESNET_NETS = ["resnet_nets_res64.pt", "resnet_nets_res32.pt"]
 
 
@@ -410,6 +411,94 @@ def case_learner_grow(golden, dev, fname, model):
     _adam_close(lag, g["lagged"], lr_max, g["iters"], "EWMA-G", frac=0.01)
     if model == "StyleGAN":
         close(L.gen_model.w_ewma, g["w_ewma"], rtol=1e-3, atol=1e-4)
+
+
+def case_learner_resume(golden, dev, fname, model, golden_dir):
+    """load_model() of a checkpoint file written by the UNMODIFIED reference in the middle of a fade-in, then train() on:
+    vs the reference resuming from the same file."""
+    g = _to(golden(fname), dev)
+    L = _grow_learner(g, dev, model)                      # any learner of the family; load_model rebuilds everything
+    L.load_model(golden_dir / g["checkpoint"], dev_of_saved_model="cpu", dev=dev)
+    sv = g["saved"]
+    G = L.gen_model
+    assert (int(G.curr_res), bool(G.fade_in_phase), float(G.alpha), L.curr_img_num, L.curr_phase_num) == \
+           (sv["res"], sv["fade"], sv["alpha"], sv["img_num"], sv["phase"])
+    assert L.pretrained_model and not L.not_trained_yet
+    for mine, ref in ((L.gen_model.state_dict(), sv["g_sd"]), (L.disc_model.state_dict(), sv["d_sd"]),
+                      (dict(L.gen_model_lagged.named_parameters()), sv["lagged"])):
+        assert set(mine.keys()) == set(ref.keys())
+        for k, v in ref.items():
+            assert torch.equal(mine[k].detach(), v), k
+    # the reference rebuilds its optimisers before every save (progan/learner.py:963,1018): the stored Adam state is empty, and
+    # the optimisers load_model() builds for the stored phase (mid-fade-in: prev_torgb / prev_fromrgb included) start fresh
+    for opt, net in ((L.opt_gen, L.gen_model), (L.opt_disc, L.disc_model)):
+        assert not opt.state_dict()["state"]
+        assert len(opt.param_groups[0]["params"]) == len(list(net.parameters()))
+    lr_max = g["lr_base"] * max(g["lr_fctr_dict"][r] for r in (g["init_res"], g["res"]))
+    dl = ReplayLoader(g["served"], 1, dev)                # train() must set the loader's batch size itself on a resume
+    set_random_source(TapeSource(g["tape"], dev))
+    losses, trace = [], []
+    orig_d, orig_g = L.disc_step, L.gen_step
+
+    def disc_step(xb):
+        trace.append(dict(res=int(L.gen_model.curr_res), fade=bool(L.gen_model.fade_in_phase), alpha=float(L.gen_model.alpha),
+                          bs=int(L.batch_size), phase=int(L.curr_phase_num), lr_d=float(L.opt_disc.param_groups[0]["lr"]),
+                          lr_g=float(L.opt_gen.param_groups[0]["lr"]), beta=float(L.beta), img_num=int(L.curr_img_num)))
+        losses.append(float(orig_d(xb)))
+        return torch.tensor(losses[-1])
+
+    L.disc_step = disc_step
+    L.gen_step = lambda: losses.append(float(orig_g())) or torch.tensor(losses[-1])
+    L.train(dl, num_main_iters=g["iters_after"])
+    assert dl.resolutions == [g["res"]] and dl.batch_sampler.batch_size == g["bs_dict"][g["res"]]
+    assert len(trace) == len(g["trace"])
+    for mine, ref in zip(trace, g["trace"]):
+        for k, v in ref.items():
+            assert (abs(mine[k] - v) < 1e-12) if isinstance(v, float) else (mine[k] == v), (k, mine, ref)
+    fin = g["final"]
+    assert (int(G.curr_res), bool(G.fade_in_phase), float(G.alpha), L.curr_phase_num, L.curr_img_num, L.batch_size) == \
+           (fin["res"], fin["fade"], fin["alpha"], fin["phase"], fin["img_num"], fin["bs"])
+    assert [float(v) for v in L.nimg_transition_lst] == fin["nimg_transition_lst"]
+    for i, (a, b) in enumerate(zip(losses, g["losses"])):
+        assert abs(a - b) < (1e-4 if i == 0 else 1e-3) * max(1.0, abs(b)), (i, a, b)
+    per = g["nimg_transition"] // g["bs_dict"][g["res"]]
+    _adam_close(L.gen_model.state_dict(), g["g_sd1"], lr_max, per, "G", frac=0.03)
+    _adam_close(L.disc_model.state_dict(), g["d_sd1"], lr_max, per, "D", frac=0.03)
+    # the EWMA generator restarted from the live one (reference progan/learner.py:462-472)
+    _adam_close(dict(L.gen_model_lagged.named_parameters()), g["lagged"], lr_max, per, "EWMA-G", frac=0.03)
+    if model == "StyleGAN":
+        close(L.gen_model.w_ewma, g["w_ewma"], rtol=1e-3, atol=1e-4)
+    return L
+
+
+def case_checkpoint_roundtrip(golden, dev, fname, model, tmp_path):
+    """save_model() -> load_model() of this package's own file: every tensor and every bookkeeping entry survives, and the
+    resumed learner steps exactly like the one that kept running would after the same end-of-train() optimiser rebuild."""
+    g = _to(golden(fname), dev)
+    L = _grow_learner(g, dev, model)
+    _load(L.gen_model, g["g_sd0"]); _load(L.disc_model, g["d_sd0"]); _load(L.gen_model_lagged, g["g_sd0"])
+    dl = ReplayLoader(g["served"], L.batch_size, dev)
+    L.train(dl, num_main_iters=6)                         # 4 stabilising iterations at 4x4, 2 fading 8x8 in
+    path = tmp_path / "model.tar"
+    L.save_model(path)
+    L2 = _grow_learner(g, dev, model)
+    L2.load_model(path, dev_of_saved_model="cpu", dev=dev)
+    for a, b in ((L.gen_model, L2.gen_model), (L.disc_model, L2.disc_model), (L.gen_model_lagged, L2.gen_model_lagged)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]) and sa[k].stride() == sb[k].stride(), k
+    for attr in ("batch_size", "curr_img_num", "curr_phase_num", "curr_epoch_num", "curr_dataset_batch_num", "loss",
+                 "gradient_penalty", "optimizer", "lr_sched", "latent_distribution", "not_trained_yet", "sched_bool"):
+        assert getattr(L, attr) == getattr(L2, attr), attr
+    assert [float(v) for v in L.nimg_transition_lst] == [float(v) for v in L2.nimg_transition_lst]
+    G, G2 = L.gen_model, L2.gen_model
+    assert (G.curr_res, G.fade_in_phase, G.alpha) == (G2.curr_res, G2.fade_in_phase, G2.alpha)
+    assert vars(L.config).keys() == vars(L2.config).keys()
+    for k, v in vars(L.config).items():
+        assert vars(L2.config)[k] == v, k
+    if model == "StyleGAN":
+        assert torch.equal(G.w_ewma, G2.w_ewma) and G.w_ewma_beta == G2.w_ewma_beta
 
 
 def case_shared_penalty_forward(dev, gp):

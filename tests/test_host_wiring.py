@@ -69,6 +69,17 @@ def test_learner_grow(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model)
 
 
+@pytest.mark.parametrize("fname,model", PC.RESUME_CASES)
+def test_learner_resume_from_reference_checkpoint(golden, fname, model):
+    from conftest import GOLDEN
+    PC.case_learner_resume(golden, DEV, fname, model, GOLDEN)
+
+
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+def test_checkpoint_roundtrip(golden, fname, model, tmp_path):
+    PC.case_checkpoint_roundtrip(golden, DEV, fname, model, tmp_path)
+
+
 @pytest.mark.parametrize("gp", ["r1", "r2"])
 def test_shared_penalty_forward(gp):
     PC.case_shared_penalty_forward(DEV, gp)

@@ -25,3 +25,14 @@ def small_fmaps(monkeypatch):
 @pytest.mark.parametrize("fname,model", PC.GROW_CASES)
 def test_learner_grow(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model)
+
+
+@pytest.mark.parametrize("fname,model", PC.RESUME_CASES)
+def test_learner_resume_from_reference_checkpoint(golden, fname, model):
+    from conftest import GOLDEN
+    PC.case_learner_resume(golden, DEV, fname, model, GOLDEN)
+
+
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+def test_checkpoint_roundtrip(golden, fname, model, tmp_path):
+    PC.case_checkpoint_roundtrip(golden, DEV, fname, model, tmp_path)
