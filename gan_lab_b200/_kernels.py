@@ -900,3 +900,61 @@ def adam_hyper_advance(hyper, beta1, beta2):
 def adam_ewma_multi(ptr_table, sizes, T, max_size, hyper, beta1, beta2, eps, wd, ewma_beta, ewma_mode):
     _call("glb_adam_ewma_multi", _p(ptr_table), _p(sizes), T, max_size, _p(hyper), float(beta1), float(beta2), float(eps),
           float(wd), float(ewma_beta), int(ewma_mode), _stream())
+
+
+# --------------------------------------------------------------------------- real-image input pipeline
+_box_tables_cache = {}
+
+
+def box_resize_tables(in_size: int, out_size: int):
+    """Pillow's BOX-filter coefficient tables for one axis, computed by the library's host helper (double arithmetic as in
+    Pillow's Resample.c) -> (bounds int32 [out, 2], kk int32 [out, ksize]) as CPU tensors."""
+    import ctypes
+    ks = LIB.fn("glb_box_resize_ksize")(int(in_size), int(out_size))
+    if ks <= 0:
+        raise GlbError(f"glb_box_resize_ksize({in_size}, {out_size}) failed")
+    bounds = torch.empty((out_size, 2), dtype=torch.int32)
+    kk = torch.empty((out_size, ks), dtype=torch.int32)
+    LIB.call("glb_box_resize_tables", int(in_size), int(out_size), ctypes.c_void_p(bounds.data_ptr()),
+             ctypes.c_void_p(kk.data_ptr()))
+    return bounds, kk
+
+
+def _box_tables_on(device, in_size, out_size):
+    key = (str(device), int(in_size), int(out_size))
+    ent = _box_tables_cache.get(key)
+    if ent is None:
+        b, k = box_resize_tables(in_size, out_size)
+        ent = (b.to(device), k.to(device))
+        _box_tables_cache[key] = ent
+    return ent
+
+
+def u8_box_resize_normalize(src, index, out_hw, mean, std, flip=None):
+    """uint8 images [M, Hs, Ws, 3] (decoded RGB, HWC, on the device) -> normalised fp32 batch [N, 3, Ho, Wo]: Pillow's BOX
+    resize + ToTensor + Normalize in one kernel, bit-exact (csrc/input.cu).  index: int64 [N] sample picks or None (all M
+    in order); flip: uint8/bool [N] or None; mean / std: 3 floats each."""
+    import ctypes
+    if not src.is_cuda:
+        raise GlbError("gan_lab_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if src.dtype != torch.uint8 or src.dim() != 4 or src.shape[3] != 3 or not src.is_contiguous():
+        raise GlbError("u8_box_resize_normalize: src must be a contiguous uint8 [M, H, W, 3] tensor")
+    M, Hs, Ws, _ = src.shape
+    Ho, Wo = int(out_hw[0]), int(out_hw[1])
+    if index is not None:
+        index = index.to(device=src.device, dtype=torch.int64).contiguous()
+        N = index.numel()
+    else:
+        N = M
+    if flip is not None:
+        flip = flip.to(device=src.device, dtype=torch.uint8).contiguous()
+        assert flip.numel() == N
+    xb, xk = _box_tables_on(src.device, Ws, Wo)
+    yb, yk = _box_tables_on(src.device, Hs, Ho)
+    out = torch.empty((N, 3, Ho, Wo), device=src.device, dtype=torch.float32)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _call("glb_u8_box_resize_normalize", src.data_ptr(), M, _p(index), _p(flip), out.data_ptr(), N, Hs, Ws, Ho, Wo,
+          xb.data_ptr(), xk.data_ptr(), xk.shape[1], yb.data_ptr(), yk.data_ptr(), yk.shape[1],
+          ctypes.cast(m3, ctypes.c_void_p), ctypes.cast(s3, ctypes.c_void_p), _stream())
+    return out

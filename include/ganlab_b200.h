@@ -172,6 +172,24 @@ int glb_fade_up_blend(const float* lo, const float* hi, float* out, int N, int C
 int glb_fade_up_blend_bwd(const float* gout, float* glo, float* ghi, int N, int C, int H, int W, float alpha, glb_stream_t stream);
 int glb_fade_real(const float* x, float* out, int N, int C, int H, int W, float alpha, glb_stream_t stream);
 
+/* ---- real-image input pipeline ------------------------------------------------------------- *
+ * Replaces the host-side torchvision chain every real sample goes through in the reference -- Resize(curr_res, PIL BOX)
+ * -> ToTensor -> Normalize(mean, std) (data_config.py:312-342; Resize rewritten per resolution, progan/learner.py:1099-1112)
+ * -- bit-exactly (Pillow 12.2 src/libImaging/Resample.c: two 8-bit passes with 22-bit fixed-point weights, the horizontal
+ * one rounded to uint8 first; then u8 -> float, /255, -mean, /std in fp32).
+ * glb_box_resize_ksize / _tables: HOST helpers, Pillow's precompute_coeffs + normalize_coeffs_8bpc for one axis (BOX filter):
+ *   bounds int32 [out][2] = first source index, count ; kk int32 [out][ksize] fixed-point weights.  The caller uploads them.
+ * glb_u8_box_resize_normalize: src uint8 [src_images][Hs][Ws][3] (decoded RGB, HWC) -> dst fp32 [N][3][Ho][Wo];
+ *   index int64 [N] picks the samples (NULL: the first N), flip uint8 [N] mirrors a sample horizontally after the resize
+ *   (RandomHorizontalFlip, data_config.py:331-332; NULL: none); xb/xk/yb/yk = device copies of the tables of the two axes;
+ *   mean3/std3 are HOST pointers to 3 floats. */
+int glb_box_resize_ksize(int in_size, int out_size);
+int glb_box_resize_tables(int in_size, int out_size, int32_t* bounds, int32_t* kk);
+int glb_u8_box_resize_normalize(const uint8_t* src, int64_t src_images, const int64_t* index, const uint8_t* flip, float* dst,
+                                int N, int Hs, int Ws, int Ho, int Wo, const int32_t* xb, const int32_t* xk, int xks,
+                                const int32_t* yb, const int32_t* yk, int yks, const float* mean3, const float* std3,
+                                glb_stream_t stream);
+
 /* logit losses (progan/learner.py:791-812, 883-896).  kind: 0 = wgan, 1 = nonsaturating, 2 = minimax.
  * d-loss: loss[0] = L(d_gen, d_real) + eps_drift*mean(d_real^2); also writes dL/d d_gen, dL/d d_real.
  * g-loss: loss[0] = L(d_out); writes dL/d d_out. */

@@ -426,6 +426,14 @@ def glinear_wgrad(ws, g_all, tab):
     return torch.cat(gw), torch.cat(gb)
 
 
+# ---- real-image input pipeline ------------------------------------------------------------------------------------------
+def u8_box_resize_normalize(src, index, out_hw, mean, std, flip=None):
+    from oracle import pil_box
+    out = pil_box.input_pipeline(src.cpu().numpy(), None if index is None else index.cpu().numpy(), out_hw, mean, std,
+                                 None if flip is None else flip.cpu().numpy())
+    return out.to(src.device)
+
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and f.__module__ == __name__
        and n not in ("install",)]
 
