@@ -359,6 +359,8 @@ def run_ours(args):
     # the step's result (both losses) is read back on the host every step, as the reference's tqdm line does
     L.train(loader, num_main_iters=args.steps, step_callback=lambda i, ld, lg: host_losses.append((ld.item(), lg.item())))
     ev2[1].record()
+    # train() ends like the reference's (progan/learner.py:1016-1030): optimisers rebuilt, networks in eval mode
+    L.gen_model.train(); L.disc_model.train()
     barrier()
     ms_e2e = ev2[0].elapsed_time(ev2[1])
     t = torch.tensor([ms_e2e], device=dev)

@@ -326,6 +326,14 @@ class ProGANLearner(GANLearner):
         loss_g = self.gen_step()
         return loss_d, loss_g
 
+    # ------------------------------------------------------------------ validation metrics hooks (reference :248-416)
+    def _fade_real_for_metrics(self, xb):
+        """Real validation images are faded like the generated ones (reference :371-378)."""
+        return ops.fade_real(xb, self.gen_model.alpha) if self.gen_model.fade_in_phase else xb
+
+    def _lagged_for_metrics(self):
+        return self._update_gen_lagged() if self.config.use_ewma_gen else None
+
     # ------------------------------------------------------------------ checkpoints (reference progan/learner.py:1238-1460)
     @property
     def progressively_grow(self):
@@ -428,8 +436,9 @@ class ProGANLearner(GANLearner):
     # ------------------------------------------------------------------ train loop
     def train(self, train_dl, valid_dl=None, z_valid_dl=None, num_main_iters=None, num_gen_iters=None,
               num_disc_iters=None, log_every=0, step_callback=None):
-        """reference progan/learner.py:418-1030 (signature kept; valid_dl / z_valid_dl accepted and ignored: metrics
-        are outside the hot path)."""
+        """reference progan/learner.py:418-1030 (signature kept).  With `z_valid_dl` (and `valid_dl` for the discriminator)
+        and non-empty `config.gen_metrics` / `config.disc_metrics`, validation metrics are computed where the reference
+        computes them."""
         c = self.config
         num_main_iters = c.num_main_iters if num_main_iters is None else num_main_iters
         num_gen_iters = c.num_gen_iters if num_gen_iters is None else num_gen_iters
@@ -523,7 +532,12 @@ class ProGANLearner(GANLearner):
                 self.nimg_transition_lst.append(np.inf)
                 self._progressively_grow = False
 
-            if num_disc_iters == 1 and num_gen_iters == 1:
+            # validation metrics are computed on the first and every `num_iters_valid`-th iteration, between the steps
+            # (reference :820-832, 918-930); those iterations take the step-by-step path
+            validate_now = ((itr + 1) % c.num_iters_valid == 0 or itr == 0)
+            validate_d = validate_now and z_valid_dl is not None and valid_dl is not None and bool(c.disc_metrics)
+            validate_g = validate_now and z_valid_dl is not None and bool(c.gen_metrics)
+            if num_disc_iters == 1 and num_gen_iters == 1 and not (validate_d or validate_g):
                 # ---- D step + G step (CUDA-graph replay once warmed up, see main_iteration) ----
                 loss_d, loss_g = self.main_iteration(self._next_real(train_dl))
                 self.curr_dataset_batch_num += 1
@@ -532,6 +546,10 @@ class ProGANLearner(GANLearner):
                 # ---- train discriminator ----
                 for disc_iter in range(num_disc_iters):
                     loss_d = self.disc_step(self._next_real(train_dl))
+                    if validate_d and disc_iter == num_disc_iters - 1:
+                        vals = self.compute_metrics(metrics=c.disc_metrics, metrics_type='Discriminator',
+                                                    z_valid_dl=z_valid_dl, valid_dl=valid_dl)
+                        print('|\n', 'Discriminator Validation Metrics:\n', *vals)
                     self.curr_dataset_batch_num += 1
                     self.curr_img_num += self.batch_size
 
@@ -540,6 +558,10 @@ class ProGANLearner(GANLearner):
                     p.requires_grad_(False)
                 for gen_iter in range(num_gen_iters):
                     loss_g = self.gen_step()
+                    if validate_g and gen_iter == num_gen_iters - 1:
+                        vals = self.compute_metrics(metrics=c.gen_metrics, metrics_type='Generator',
+                                                    z_valid_dl=z_valid_dl, valid_dl=None)
+                        print('|\n', 'Generator Validation Metrics:\n', *vals)
 
             self.last_losses = (loss_d, loss_g)
             if step_callback is not None:

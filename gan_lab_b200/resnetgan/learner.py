@@ -303,6 +303,130 @@ class GANLearner(object):
             return ops.gp_norm(outb_grads, 1., self.config.lda / (2. * n_hw))
         return ops.sumsq(outb_grads, self.config.lda / (2. * n_hw))
 
+    # ------------------------------------------------------------------ validation metrics (reference :318-460 / progan :248-416)
+    def _fade_real_for_metrics(self, xb):
+        return xb
+
+    def _lagged_for_metrics(self):
+        return None
+
+    @torch.no_grad()
+    def compute_metrics(self, metrics, metrics_type, z_valid_dl, valid_dl=None):
+        """Metric evaluation over a latent validation set (and, for the discriminator, a real one), run periodically by
+        train() or by the user: 'fake realness', 'real realness', 'generator loss', 'discriminator loss' (batch means of the
+        logit losses without penalty or drift term, weighted by batch length) and 'image grid'.  Returns the reference's
+        formatted lines; the raw values are kept in `self.last_metrics`."""
+        c = self.config
+        metrics_type = metrics_type.casefold()
+        if metrics_type not in ('generator', 'critic', 'discriminator'):
+            raise Exception('Invalid metrics_type. Only "generator", "critic", or "discriminator" are accepted.')
+        metrics = [metric.casefold() for metric in metrics]
+        self.disc_model.eval()
+        lagged = None
+        if metrics_type == 'generator':
+            self.gen_model.train()
+            lagged = self._lagged_for_metrics()
+            if lagged is not None:
+                lagged.eval()
+        self.gen_model.eval()
+        valid_dataiter = iter(valid_dl) if valid_dl is not None else None
+        z_valid_dataiter = iter(z_valid_dl) if z_valid_dl is not None else None
+        if z_valid_dl is None:
+            raise ValueError('compute_metrics needs a latent validation loader (z_valid_dl)')
+        n_batches, n_samples = len(z_valid_dl), len(z_valid_dl.dataset)
+        if not self.grid_inputs_constructed and 'image grid' in metrics:
+            assert c.img_grid_sz ** 2 <= n_samples
+            self.rand_idxs = torch.multinomial(torch.ones(n_samples, dtype=torch.float32), num_samples=c.img_grid_sz ** 2,
+                                               replacement=False)
+        self._img_grid_constructed = False
+        sums = {metric: torch.zeros((), device=c.dev, dtype=torch.float32) for metric in metrics}
+        _idx = 0
+        for n in range(n_batches):
+            zbatch = next(z_valid_dataiter)
+            zb = zbatch[0].to(c.dev)
+            nb = len(zb)
+            _xgenb = self.gen_model(zb)
+            fake = None
+            if 'fake realness' in metrics:
+                fake = self.disc_model(_xgenb)
+                sums['fake realness'] += fake.sum()
+            if metrics_type == 'generator':
+                if 'generator loss' in metrics:
+                    _ygenb = fake if fake is not None else self.disc_model(_xgenb)
+                    sums['generator loss'] += ops.g_logit_loss(_ygenb, self.loss) * nb
+                if 'image grid' in metrics:
+                    if self.valid_z is None:
+                        self.valid_z = torch.zeros(c.img_grid_sz ** 2, zb.shape[1], device=c.dev)
+                    if not self.grid_inputs_constructed:
+                        picked = set(int(i) for i in self.rand_idxs)
+                        for o in range(nb):
+                            if (n * self.batch_size + o) in picked:
+                                self.valid_z[_idx] = zb[o]
+                                _idx += 1
+                        if _idx == c.img_grid_sz ** 2:
+                            self.grid_inputs_constructed = True
+                    if self.grid_inputs_constructed and not self._img_grid_constructed:
+                        base = c.save_samples_dir / self.model.casefold().replace(' ', '') / 'image_grid'
+                        if lagged is not None:
+                            (base / 'time_averaged').mkdir(parents=True, exist_ok=True)
+                            self.make_image_grid(self.valid_z, time_average=True,
+                                                 save_path=base / 'time_averaged' / (str(self.gen_metrics_num) + '.png'))
+                        (base / 'original').mkdir(parents=True, exist_ok=True)
+                        self.make_image_grid(self.valid_z, time_average=False,
+                                             save_path=base / 'original' / (str(self.gen_metrics_num) + '.png'))
+                        self._img_grid_constructed = True
+                self.gen_metrics_num += 1 if n == n_batches - 1 else 0
+            else:
+                if valid_dl is not None:
+                    xb = next(valid_dataiter)[0].to(c.dev)
+                    xb = self._fade_real_for_metrics(xb)
+                    real = None
+                    if 'real realness' in metrics:
+                        real = self.disc_model(xb)
+                        sums['real realness'] += real.sum()
+                    if 'discriminator loss' in metrics:
+                        _ygenb = fake if fake is not None else self.disc_model(_xgenb)
+                        _yb = real if real is not None else self.disc_model(xb)
+                        sums['discriminator loss'] += ops.d_logit_loss(_ygenb, _yb, self.loss, 0.) * nb
+                self.disc_metrics_num += 1 if n == n_batches - 1 else 0
+        self.last_metrics = {metric: float(v) / n_samples for metric, v in sums.items() if metric != 'image grid'}
+        width = '%-' + str(max(len(m) for m in metrics) + 3) + 's'
+        lines = ['    ' + (width % (metric + ':')) + '%.4g' % self.last_metrics[metric] + '\n'
+                 for metric in metrics if metric != 'image grid']
+        self.gen_model.train()
+        self.disc_model.train()
+        return lines
+
+    @torch.no_grad()
+    def make_image_grid(self, zs, labels=None, time_average=True, save_path=None):
+        """Grid of generated images for the latent codes `zs` (a perfect-square count), de-normalised with the dataset
+        statistics as the reference does before plotting (progan/learner.py:1198-1234).  The reference draws the grid with
+        matplotlib; here it is assembled as one uint8 [rows*res, cols*res, 3] array (returned) and written as a PNG."""
+        import numpy as np
+        if zs.dim() != 2:
+            raise IndexError('Incorrect dimensions of input latent vector. Must be `dim == 2`.')
+        if zs.shape[1] != self.config.len_latent:
+            raise IndexError(f'Input latent vector must be of size {self.config.len_latent}.')
+        sz = int(round(np.sqrt(len(zs))))
+        if sz * sz != len(zs):
+            raise ValueError('Argument `zs` must be a perfect square-length in order to make image grid.')
+        net = self._lagged_for_metrics() if time_average else self.gen_model
+        if net is None:
+            raise ValueError('time_average=True needs the EWMA generator (config.use_ewma_gen)')
+        mean = self.ds_mean if self.ds_mean is not None else torch.full((FMAP_SAMPLES, 1, 1), .5)
+        std = self.ds_std if self.ds_std is not None else torch.full((FMAP_SAMPLES, 1, 1), .5)
+        x = net(zs.to(self.config.dev)).float().cpu()
+        x = (x * std + mean).clamp_(0., 1.)                       # imshow clips to [0, 1] as well
+        n, ch, h, w = x.shape
+        grid = x.view(sz, sz, ch, h, w).permute(0, 3, 1, 4, 2).reshape(sz * h, sz * w, ch)
+        grid = (grid * 255.).round().to(torch.uint8).numpy()
+        if save_path is not None:
+            from pathlib import Path
+            from PIL import Image
+            Path(save_path).parent.mkdir(parents=True, exist_ok=True)
+            Image.fromarray(grid).save(str(save_path))
+        return grid
+
     # ------------------------------------------------------------------ checkpoints (reference :1076-1250)
     def _checkpoint_common(self):
         """Entries every learner writes (reference resnetgan/learner.py:1104-1137) with the reference's value types."""

@@ -601,6 +601,58 @@ def golden_resume(ref, model="StyleGAN", iters_before=6, iters_after=3, ckpt_nam
         _unpatch(ref)
 
 
+def golden_metrics(ref, model="StyleGAN", res=16, bs=4, n_valid=10):
+    """compute_metrics() of the reference (progan/learner.py:248-416) after one training iteration:
+    generator metrics on a latent validation set whose last batch is short, discriminator metrics on latents + real images."""
+    _patch_small(ref)
+    try:
+        torch.manual_seed(41); np.random.seed(41)
+        if model == "StyleGAN":
+            L, cfg = _build_style_learner(ref, res, res, bs)
+        else:
+            cfg = make_config("ProGAN", res=res, init_res=res, batch_size=bs, len_latent=SMALL_FMAP_MAX)
+            with _quiet():
+                L = ref.progan_learner.ProGANLearner(cfg)
+        gen = torch.Generator().manual_seed(43)
+        perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+        data = torch.rand(bs, 3, res, res, generator=gen) * 2 - 1
+        ds = TensorDataset(data)
+        dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+        with Tape() as train_tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+            L.train(dl, num_main_iters=1)
+        g_sd, d_sd = sd_clone(L.gen_model), sd_clone(L.disc_model)
+        z_valid = torch.randn(n_valid, cfg.len_latent, generator=gen)
+        x_valid = torch.rand(n_valid, 3, res, res, generator=gen) * 2 - 1
+        zds, xds = TensorDataset(z_valid), TensorDataset(x_valid)
+        z_dl = DataLoader(zds, batch_sampler=BatchSampler(SequentialSampler(zds), batch_size=bs, drop_last=False))
+        x_dl = DataLoader(xds, batch_sampler=BatchSampler(SequentialSampler(xds), batch_size=bs, drop_last=False))
+        gen_metrics = ["fake realness", "generator loss"]
+        disc_metrics = ["fake realness", "real realness", "discriminator loss"]
+        # the reference returns the values formatted with %.4g; the harness also keeps the raw floats its `.item()` calls produce
+        items = []
+        orig_item = torch.Tensor.item
+        torch.Tensor.item = lambda self: (items.append(orig_item(self)), items[-1])[1]
+        try:
+            with Tape() as tape_g, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+                vals_g = L.compute_metrics(metrics=gen_metrics, metrics_type="Generator", z_valid_dl=z_dl, valid_dl=None)
+            raw_g = [float(v) for v in items[-len(gen_metrics):]]
+            with Tape() as tape_d, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+                vals_d = L.compute_metrics(metrics=disc_metrics, metrics_type="Discriminator", z_valid_dl=z_dl, valid_dl=x_dl)
+            raw_d = [float(v) for v in items[-len(disc_metrics):]]
+        finally:
+            torch.Tensor.item = orig_item
+        out = dict(model=model, res=res, bs=bs, fmap_max=SMALL_FMAP_MAX, len_latent=cfg.len_latent, g_sd=g_sd, d_sd=d_sd,
+                   z_valid=z_valid, x_valid=x_valid, gen_metrics=gen_metrics, disc_metrics=disc_metrics,
+                   tape_g=tape_g.events, tape_d=tape_d.events, vals_g=vals_g, vals_d=vals_d, raw_g=raw_g, raw_d=raw_d,
+                   gen_metrics_num=int(L.gen_metrics_num), disc_metrics_num=int(L.disc_metrics_num),
+                   modes=(bool(L.gen_model.training), bool(L.disc_model.training)))
+        if model == "StyleGAN":
+            out["w_ewma"] = L.gen_model.w_ewma.detach().clone()
+        return out
+    finally:
+        _unpatch(ref)
+
+
 RESNET_FMAP = 8          # reference constants resnetgan/architectures.py:19-20 (FMAP_G = FMAP_D = 64) patched for small fixtures
 RESNET_LATENT = 16
 
@@ -703,6 +755,8 @@ def main():
         "pro_grow_4to8.pt": lambda: golden_grow(ref, "ProGAN"),
         "style_resume.pt": lambda: golden_resume(ref, "StyleGAN"),
         "pro_resume.pt": lambda: golden_resume(ref, "ProGAN"),
+        "style_metrics.pt": lambda: golden_metrics(ref, "StyleGAN"),
+        "pro_metrics.pt": lambda: golden_metrics(ref, "ProGAN"),
         "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),

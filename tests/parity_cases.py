@@ -19,6 +19,7 @@ PRO_NETS = ["pro_nets_res16.pt", "pro_nets_res8_fade.pt"]
 TRAIN_CASES = [("style_train_res16.pt", "StyleGAN"), ("pro_train_res8.pt", "ProGAN")]
 GROW_CASES = [("style_grow_4to8.pt", "StyleGAN"), ("pro_grow_4to8.pt", "ProGAN")]
 RESUME_CASES = [("style_resume.pt", "StyleGAN"), ("pro_resume.pt", "ProGAN")]
+METRICS_CASES = [("style_metrics.pt", "StyleGAN"), ("pro_metrics.pt", "ProGAN")]
 RESNET_NETS = ["resnet_nets_res64.pt", "resnet_nets_res32.pt"]
 
 
@@ -499,6 +500,54 @@ def case_checkpoint_roundtrip(golden, dev, fname, model, tmp_path):
         assert vars(L2.config)[k] == v, k
     if model == "StyleGAN":
         assert torch.equal(G.w_ewma, G2.w_ewma) and G.w_ewma_beta == G2.w_ewma_beta
+
+
+def case_compute_metrics(golden, dev, fname, model, tmp_path):
+    """Learner.compute_metrics() vs the reference's (progan/learner.py:248-416): generator metrics on a latent validation set
+    with a short last batch, discriminator metrics on latents + reals; eval-mode generator (truncation trick, fresh noise)."""
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    from gan_lab_b200.progan.learner import ProGANLearner
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    g = _to(golden(fname), dev)
+    res, bs = g["res"], g["bs"]
+    kw = dict(res=res, batch_size=bs, dev=dev, len_latent=g["len_latent"], save_samples_dir=tmp_path, img_grid_sz=2)
+    if model == "StyleGAN":
+        L = StyleGANLearner(default_config("StyleGAN", len_dlatent=g["len_latent"], cutoff_trunc_trick=int(math.log2(res)) - 2, **kw))
+        L.gen_model.w_ewma = g["w_ewma"].clone()
+    else:
+        L = ProGANLearner(default_config("ProGAN", **kw))
+    _load(L.gen_model, g["g_sd"]); _load(L.disc_model, g["d_sd"]); _load(L.gen_model_lagged, g["g_sd"])
+    L.gen_model.train(); L.disc_model.train()
+    zds, xds = TensorDataset(g["z_valid"]), TensorDataset(g["x_valid"])
+    z_dl = DataLoader(zds, batch_sampler=BatchSampler(SequentialSampler(zds), batch_size=bs, drop_last=False))
+    x_dl = DataLoader(xds, batch_sampler=BatchSampler(SequentialSampler(xds), batch_size=bs, drop_last=False))
+
+    def check(lines, ref_lines, raw, names):
+        assert len(lines) == len(ref_lines)
+        for name, want in zip(names, raw):
+            got = L.last_metrics[name]
+            assert abs(got - want) < 2e-4 * max(1.0, abs(want)), (name, got, want)
+        for a, b in zip(lines, ref_lines):            # same layout; the %.4g figure may differ in its last digit
+            assert a.split(":")[0] == b.split(":")[0] and a.endswith("\n")
+            assert abs(float(a.split(":")[1]) - float(b.split(":")[1])) <= 2e-3 * max(1.0, abs(float(b.split(":")[1])))
+
+    set_random_source(TapeSource(g["tape_g"], dev))
+    lines = L.compute_metrics(metrics=g["gen_metrics"], metrics_type="Generator", z_valid_dl=z_dl, valid_dl=None)
+    check(lines, g["vals_g"], g["raw_g"], g["gen_metrics"])
+    set_random_source(TapeSource(g["tape_d"], dev))
+    lines = L.compute_metrics(metrics=g["disc_metrics"], metrics_type="Discriminator", z_valid_dl=z_dl, valid_dl=x_dl)
+    check(lines, g["vals_d"], g["raw_d"], g["disc_metrics"])
+    assert (L.gen_metrics_num, L.disc_metrics_num) == (g["gen_metrics_num"], g["disc_metrics_num"])
+    assert (L.gen_model.training, L.disc_model.training) == g["modes"]
+    # image grid: 2x2 samples from both generators, written as PNGs where the reference writes them
+    set_random_source(None)
+    L.compute_metrics(metrics=["image grid"], metrics_type="Generator", z_valid_dl=z_dl)
+    assert L.grid_inputs_constructed and L.valid_z.shape == (4, g["len_latent"])
+    base = tmp_path / model.casefold() / "image_grid"
+    from PIL import Image
+    for sub in ("original", "time_averaged"):
+        im = Image.open(base / sub / (str(g["gen_metrics_num"]) + ".png"))
+        assert im.size == (2 * res, 2 * res) and im.mode == "RGB"
 
 
 def case_shared_penalty_forward(dev, gp):

@@ -80,6 +80,11 @@ def test_checkpoint_roundtrip(golden, fname, model, tmp_path):
     PC.case_checkpoint_roundtrip(golden, DEV, fname, model, tmp_path)
 
 
+@pytest.mark.parametrize("fname,model", PC.METRICS_CASES)
+def test_compute_metrics(golden, fname, model, tmp_path):
+    PC.case_compute_metrics(golden, DEV, fname, model, tmp_path)
+
+
 @pytest.mark.parametrize("gp", ["r1", "r2"])
 def test_shared_penalty_forward(gp):
     PC.case_shared_penalty_forward(DEV, gp)
@@ -106,3 +111,30 @@ def test_resnet_train(golden):
 
 def test_style_generator_eval_mode(golden):
     PC.case_style_eval(golden, DEV)
+
+
+def test_train_runs_validation_metrics_where_the_reference_does(capsys):
+    """train() with validation loaders: discriminator metrics after the D step and generator metrics after the G step of the
+    first and every num_iters_valid-th iteration (reference progan/learner.py:820-832, 918-930)."""
+    import torch
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    torch.manual_seed(0)
+    cfg = default_config("StyleGAN", res=8, batch_size=4, dev=DEV, len_latent=32, len_dlatent=32, cutoff_trunc_trick=1,
+                         gen_metrics=["generator loss", "fake realness"], disc_metrics=["discriminator loss"], num_iters_valid=3)
+    L = StyleGANLearner(cfg)
+
+    def loader(t):
+        ds = TensorDataset(t)
+        return DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=4, drop_last=True))
+
+    calls = []
+    orig = L.compute_metrics
+    L.compute_metrics = lambda **kw: calls.append((kw["metrics_type"], L.curr_img_num)) or orig(**kw)
+    L.train(loader(torch.rand(16, 3, 8, 8) * 2 - 1), valid_dl=loader(torch.rand(8, 3, 8, 8) * 2 - 1),
+            z_valid_dl=loader(torch.randn(8, 32)), num_main_iters=4)
+    assert calls == [("Discriminator", 0), ("Generator", 4), ("Discriminator", 8), ("Generator", 12)]
+    out = capsys.readouterr().out
+    assert out.count("Discriminator Validation Metrics:") == 2 and out.count("generator loss:") == 2
+    assert (L.gen_metrics_num, L.disc_metrics_num) == (2, 2)

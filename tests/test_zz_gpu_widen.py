@@ -36,3 +36,8 @@ def test_learner_resume_from_reference_checkpoint(golden, fname, model):
 @pytest.mark.parametrize("fname,model", PC.GROW_CASES)
 def test_checkpoint_roundtrip(golden, fname, model, tmp_path):
     PC.case_checkpoint_roundtrip(golden, DEV, fname, model, tmp_path)
+
+
+@pytest.mark.parametrize("fname,model", PC.METRICS_CASES)
+def test_compute_metrics(golden, fname, model, tmp_path):
+    PC.case_compute_metrics(golden, DEV, fname, model, tmp_path)
