@@ -75,3 +75,58 @@ def test_dataparallel_world2_gloo():
     for a, b in zip(r0["avg"], r0["avg2"]):                               # same data, same weights -> same averaged gradient
         assert (a is None and b is None) or torch.equal(a, b)
     assert torch.allclose(r0["mean"], torch.full((3,), 1.5)) and torch.equal(r0["mean"], r1["mean"])
+
+
+class _Patch(object):
+    """monkeypatch stand-in for a spawned worker process (nothing to undo: the process ends)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def _learner_worker(rank, world, port, ret, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from pathlib import Path
+        import gan_lab_b200._growth as growth
+        from gan_lab_b200.config import default_config
+        from gan_lab_b200.data import DeviceImageLoader
+        from gan_lab_b200.parallel import DataParallel
+        from gan_lab_b200.stylegan.learner import StyleGANLearner
+        from oracle import kernel_contracts
+        kernel_contracts.install(_Patch)                     # CPU doubles of the kernels: host logic only
+        growth.FMAP_MAX = 32
+        torch.manual_seed(100 + rank); np.random.seed(5)     # different weights / z / noise per rank, shared mixing stream
+        cfg = default_config("StyleGAN", res=8, batch_size=4, dev="cpu", len_latent=32, len_dlatent=32, cutoff_trunc_trick=1)
+        L = StyleGANLearner(cfg)
+        L.dp = DataParallel(world, bucket_bytes=4096)
+        L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
+        images = torch.randint(0, 256, (16, 16, 16, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+        dl = DeviceImageLoader(images, batch_size=4, res=8, shuffle=True, device="cpu", seed=3, rank=rank, world_size=world)
+        seen = []
+        orig = dl.batch
+        dl.batch = lambda idx, flip=None: seen.extend(int(i) for i in idx) or orig(idx, flip)
+        L.train(dl, num_main_iters=2)
+        path = Path(tmp) / f"rank{rank}" / "model.tar"
+        L.save_model(path)
+        ret[rank] = dict(g=[p.detach().clone() for p in L.gen_model.parameters()],
+                         d=[p.detach().clone() for p in L.disc_model.parameters()], seen=seen, saved=path.exists())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_learner_loader_checkpoint_world2_gloo(tmp_path):
+    """The N>1 path of the rows around the step: per-rank shards of the real-image loader, gradient averaging inside the
+    learner's steps (replicas stay identical although every rank draws its own latents and noise), rank 0 alone writes the
+    checkpoint."""
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_learner_worker, args=(world, port, ret, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = ret[0], ret[1]
+    assert len(r0["seen"]) == len(r1["seen"]) == 8 and not set(r0["seen"]) & set(r1["seen"])
+    for a, b in zip(r0["g"] + r0["d"], r1["g"] + r1["d"]):
+        assert torch.equal(a, b)
+    assert r0["saved"] and not r1["saved"]
