@@ -334,6 +334,10 @@ class ProGANLearner(GANLearner):
     def _lagged_for_metrics(self):
         return self._update_gen_lagged() if self.config.use_ewma_gen else None
 
+    def compute_metrics(self, metrics, metrics_type, z_valid_dl, valid_dl=None):
+        self._sync_replicas()
+        return super(ProGANLearner, self).compute_metrics(metrics, metrics_type, z_valid_dl, valid_dl)
+
     # ------------------------------------------------------------------ checkpoints (reference progan/learner.py:1238-1460)
     @property
     def progressively_grow(self):
@@ -342,11 +346,16 @@ class ProGANLearner(GANLearner):
     def _extra_checkpoint_entries(self):
         return {}
 
+    def _sync_replicas(self):
+        """Bring rank-local running statistics to their global-batch value (collective: every rank calls it).  Nothing to do
+        for ProGAN; StyleGAN averages `w_ewma`."""
+
     def save_model(self, save_path):
         """reference progan/learner.py:1238-1298 (stylegan/learner.py:433-506 adds `_extra_checkpoint_entries`); the file is
         readable by the reference's own load_model.  Under data parallelism only rank 0 writes (replicas are identical)."""
         from pathlib import Path
         from .. import checkpoint as ckpt
+        self._sync_replicas()
         if self.dp is not None and getattr(self.dp, 'rank', 0) != 0:
             return
         common = self._checkpoint_common()
@@ -596,6 +605,7 @@ class ProGANLearner(GANLearner):
         # end of train() (reference :1016-1030): fresh optimisers (every train() call starts Adam from zero moments), the
         # networks left in eval mode.  The reference also parks them on the CPU; device placement is left alone here.
         self._set_optimizer()
+        self._sync_replicas()
         self.gen_model.eval(); self.disc_model.eval()
         if c.use_ewma_gen:
             self.gen_model_lagged.eval()

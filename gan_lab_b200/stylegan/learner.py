@@ -62,6 +62,15 @@ class StyleGANLearner(ProGANLearner):
             lag.w_ewma = self.gen_model.w_ewma.detach().clone()
         return lag
 
+    def _sync_replicas(self):
+        """Under data parallelism every rank's generator averages the w of ITS latents into `w_ewma`
+        (stylegan/architectures.py:427-437).  The update is linear, so the mean over ranks of the rank-local averages IS the
+        average the reference would hold at the global batch -- at any time; it is therefore taken lazily, where `w_ewma` is
+        observed (end of train(), checkpoints, validation metrics), not in every step."""
+        dp, w = self.dp, self.gen_model.w_ewma
+        if dp is not None and dp.world > 1 and w is not None:
+            dp.allreduce_mean_(w)
+
     def _restore_lagged_extras(self, checkpoint):
         # literal: the reference assigns the stored LAGGED average to the live generator here (stylegan/learner.py:607)
         self.gen_model.w_ewma = checkpoint['w_ewma_lagged'].to(self.config.dev)

@@ -109,11 +109,15 @@ def _learner_worker(rank, world, port, ret, tmp):
         seen = []
         orig = dl.batch
         dl.batch = lambda idx, flip=None: seen.extend(int(i) for i in idx) or orig(idx, flip)
+        local_w = []
+        orig_sync = L._sync_replicas
+        L._sync_replicas = lambda: local_w.append(L.gen_model.w_ewma.clone()) or orig_sync()
         L.train(dl, num_main_iters=2)
         path = Path(tmp) / f"rank{rank}" / "model.tar"
         L.save_model(path)
         ret[rank] = dict(g=[p.detach().clone() for p in L.gen_model.parameters()],
-                         d=[p.detach().clone() for p in L.disc_model.parameters()], seen=seen, saved=path.exists())
+                         d=[p.detach().clone() for p in L.disc_model.parameters()], seen=seen, saved=path.exists(),
+                         w_local=local_w[0], w=L.gen_model.w_ewma.clone())
     finally:
         dist.destroy_process_group()
 
@@ -130,3 +134,7 @@ def test_learner_loader_checkpoint_world2_gloo(tmp_path):
     for a, b in zip(r0["g"] + r0["d"], r1["g"] + r1["d"]):
         assert torch.equal(a, b)
     assert r0["saved"] and not r1["saved"]
+    # w_ewma: rank-local averages differ (different latents), the synchronised one is their mean on both ranks
+    assert not torch.equal(r0["w_local"], r1["w_local"])
+    torch.testing.assert_close(r0["w"], (r0["w_local"] + r1["w_local"]) / 2, rtol=1e-6, atol=1e-7)
+    assert torch.equal(r0["w"], r1["w"])
