@@ -19,6 +19,7 @@ class GrowthState(object):
         self.fmap_base = FMAP_BASE if fmap_base is None else fmap_base
         self.fmap_max = FMAP_MAX if fmap_max is None else fmap_max
         self.final_res = None
+        self.alpha_dev = None          # _kernels.DeviceAlpha once a learner asks for CUDA-graph replay of fade-in phases
         self.reset()
 
     def get_fmap(self, scale_stage):
@@ -39,6 +40,18 @@ class GrowthState(object):
 
     def as_dict(self):
         return dict(self.__dict__)
+
+    def enable_device_alpha(self, device):
+        from . import _kernels as K
+        if self.alpha_dev is None or self.alpha_dev.coef.device != device:
+            self.alpha_dev = K.DeviceAlpha(device)
+        self.alpha_dev.set(self.alpha)
+
+    def blend_coefs(self):
+        """(alpha, 1 - alpha) for the fade-in blends: floats, or handles of the device-side vector when that is enabled."""
+        if self.alpha_dev is not None:
+            return self.alpha_dev.alpha, self.alpha_dev.one_minus
+        return self.alpha, 1. - self.alpha
 
 
 def _state_property(name):

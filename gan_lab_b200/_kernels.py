@@ -480,6 +480,40 @@ def colsum(x, scale):
     return out
 
 
+class DeviceAlpha(object):
+    """The fade-in alpha kept ON THE DEVICE as `coef` = [alpha, 1 - alpha] (fp32), so that the blends of a fade-in phase -- whose
+    alpha moves every iteration (reference progan/learner.py:951-952) -- can live in a captured CUDA graph.  `set()` is called
+    by the learner before every iteration (outside any capture); `.alpha` / `.one_minus` are the handles the launchers accept
+    wherever they accept a float coefficient."""
+
+    def __init__(self, device):
+        self.coef = torch.zeros(2, device=device, dtype=torch.float32)
+        self.value = None
+        self.alpha, self.one_minus = Coef(self, 0), Coef(self, 1)
+
+    def set(self, alpha):
+        alpha = float(alpha)
+        if alpha != self.value:
+            self.coef[0:1].fill_(alpha)
+            self.coef[1:2].fill_(1. - alpha)
+            self.value = alpha
+
+
+class Coef(object):
+    """One entry of a DeviceAlpha vector; float(c) is the host-side value last set."""
+
+    def __init__(self, ref, idx):
+        self.ref, self.idx = ref, idx
+
+    def __float__(self):
+        v = self.ref.value
+        return v if self.idx == 0 else 1. - v
+
+
+def coef_or_float(v):
+    return v if isinstance(v, Coef) else float(v)
+
+
 def axpby(a, b, alpha, beta):
     _chk(a, b)
     if a.dim() == 4 and a.shape[1] > 3:
@@ -489,6 +523,14 @@ def axpby(a, b, alpha, beta):
         a = a.contiguous()
         b = b.contiguous() if b is not None else None
     y = torch.empty_like(a)
+    if isinstance(alpha, Coef):
+        ib = alpha.idx
+        if b is not None:
+            if not (isinstance(beta, Coef) and beta.ref is alpha.ref):
+                raise GlbError("axpby: both coefficients must come from the same DeviceAlpha")
+            ib = beta.idx
+        _call("glb_axpby_dev", _p(a), _p(b), _p(y), a.numel(), alpha.ref.coef.data_ptr(), alpha.idx, ib, _stream())
+        return y
     _call("glb_axpby", _p(a), _p(b), _p(y), a.numel(), float(alpha), float(beta), _stream())
     return y
 
@@ -839,6 +881,10 @@ def fade_up_blend(lo, hi, alpha):
     lo, hi = lo.contiguous(), hi.contiguous()
     N, C, H, W = hi.shape
     out = torch.empty_like(hi)
+    if isinstance(alpha, Coef):
+        assert alpha.idx == 0
+        _call("glb_fade_up_blend_dev", _p(lo), _p(hi), _p(out), N, C, H, W, alpha.ref.coef.data_ptr(), _stream())
+        return out
     _call("glb_fade_up_blend", _p(lo), _p(hi), _p(out), N, C, H, W, float(alpha), _stream())
     return out
 
@@ -849,6 +895,10 @@ def fade_up_blend_bwd(gout, alpha):
     N, C, H, W = gout.shape
     glo = torch.empty((N, C, H // 2, W // 2), device=gout.device, dtype=torch.float32)
     ghi = torch.empty_like(gout)
+    if isinstance(alpha, Coef):
+        assert alpha.idx == 0
+        _call("glb_fade_up_blend_bwd_dev", _p(gout), _p(glo), _p(ghi), N, C, H, W, alpha.ref.coef.data_ptr(), _stream())
+        return glo, ghi
     _call("glb_fade_up_blend_bwd", _p(gout), _p(glo), _p(ghi), N, C, H, W, float(alpha), _stream())
     return glo, ghi
 
@@ -858,6 +908,10 @@ def fade_real(x, alpha):
     x = x.contiguous()
     N, C, H, W = x.shape
     out = torch.empty_like(x)
+    if isinstance(alpha, Coef):
+        assert alpha.idx == 0
+        _call("glb_fade_real_dev", _p(x), _p(out), N, C, H, W, alpha.ref.coef.data_ptr(), _stream())
+        return out
     _call("glb_fade_real", _p(x), _p(out), N, C, H, W, float(alpha), _stream())
     return out
 

@@ -166,8 +166,11 @@ __global__ void colsum_scalar_kernel(const float* __restrict__ x, float* __restr
   }
 }
 
+// coef != nullptr: alpha = coef[ia], beta = coef[ib] are read on the device (a fade-in alpha that moves every iteration
+// must not be baked into a captured CUDA graph)
 __global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n,
-                             float alpha, float beta) {
+                             float alpha, float beta, const float* __restrict__ coef = nullptr, int ia = 0, int ib = 0) {
+  if (coef != nullptr) { alpha = __ldg(coef + ia); beta = __ldg(coef + ib); }
   const int64_t n4 = n >> 2;
   const float4* a4 = reinterpret_cast<const float4*>(a);
   const float4* b4 = reinterpret_cast<const float4*>(b);
@@ -485,7 +488,8 @@ __global__ void pool_bias_act_bwd_kernel(const float4* __restrict__ gy, const fl
 // image-space fade-in helpers (NCHW)
 // ------------------------------------------------------------------------------------------------
 __global__ void fade_up_blend_kernel(const float* __restrict__ lo, const float* __restrict__ hi, float* __restrict__ out,
-                                     int64_t planes, int H, int W, float alpha) {
+                                     int64_t planes, int H, int W, float alpha, const float* __restrict__ coef = nullptr) {
+  if (coef != nullptr) alpha = __ldg(coef);
   const int64_t total = planes * H * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
@@ -498,7 +502,8 @@ __global__ void fade_up_blend_kernel(const float* __restrict__ lo, const float* 
 }
 
 __global__ void fade_up_blend_bwd_kernel(const float* __restrict__ gout, float* __restrict__ glo, float* __restrict__ ghi,
-                                         int64_t planes, int H, int W, float alpha) {
+                                         int64_t planes, int H, int W, float alpha, const float* __restrict__ coef = nullptr) {
+  if (coef != nullptr) alpha = __ldg(coef);
   // one thread per LOW-res pixel
   const int LH = H / 2, LW = W / 2;
   const int64_t total = planes * LH * LW;
@@ -514,7 +519,9 @@ __global__ void fade_up_blend_bwd_kernel(const float* __restrict__ gout, float* 
   }
 }
 
-__global__ void fade_real_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t planes, int H, int W, float alpha) {
+__global__ void fade_real_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t planes, int H, int W, float alpha,
+                                 const float* __restrict__ coef = nullptr) {
+  if (coef != nullptr) alpha = __ldg(coef);
   const int LH = H / 2, LW = W / 2;
   const int64_t total = planes * LH * LW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -926,6 +933,41 @@ extern "C" int glb_fade_real(const float* x, float* out, int N, int C, int H, in
   const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
   fade_real_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(x, out, (int64_t)N * C, H, W, alpha);
   GLB_CHECK_LAUNCH("fade_real");
+  return GLB_OK;
+}
+
+// ---- the same four with alpha / beta read from a device vector `coef` = [alpha, 1 - alpha] (CUDA-graph replayable fade-in)
+extern "C" int glb_axpby_dev(const float* a, const float* b, float* y, int64_t n, const float* coef, int ia, int ib,
+                             glb_stream_t stream) {
+  REQ(n > 0 && coef != nullptr && ia >= 0 && ib >= 0, "axpby_dev");
+  axpby_kernel<<<grid_for((n + 3) / 4, TPB), TPB, 0, (cudaStream_t)stream>>>(a, b, y, n, 0.f, 0.f, coef, ia, ib);
+  GLB_CHECK_LAUNCH("axpby_dev");
+  return GLB_OK;
+}
+
+extern "C" int glb_fade_up_blend_dev(const float* lo, const float* hi, float* out, int N, int C, int H, int W, const float* coef,
+                                     glb_stream_t stream) {
+  REQ(H % 2 == 0 && W % 2 == 0 && coef != nullptr, "fade_up_blend_dev");
+  const int64_t total = (int64_t)N * C * H * W;
+  fade_up_blend_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(lo, hi, out, (int64_t)N * C, H, W, 0.f, coef);
+  GLB_CHECK_LAUNCH("fade_up_blend_dev");
+  return GLB_OK;
+}
+
+extern "C" int glb_fade_up_blend_bwd_dev(const float* gout, float* glo, float* ghi, int N, int C, int H, int W, const float* coef,
+                                         glb_stream_t stream) {
+  REQ(H % 2 == 0 && W % 2 == 0 && coef != nullptr, "fade_up_blend_bwd_dev");
+  const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
+  fade_up_blend_bwd_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(gout, glo, ghi, (int64_t)N * C, H, W, 0.f, coef);
+  GLB_CHECK_LAUNCH("fade_up_blend_bwd_dev");
+  return GLB_OK;
+}
+
+extern "C" int glb_fade_real_dev(const float* x, float* out, int N, int C, int H, int W, const float* coef, glb_stream_t stream) {
+  REQ(H % 2 == 0 && W % 2 == 0 && coef != nullptr, "fade_real_dev");
+  const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
+  fade_real_kernel<<<grid_for(total, TPB), TPB, 0, (cudaStream_t)stream>>>(x, out, (int64_t)N * C, H, W, 0.f, coef);
+  GLB_CHECK_LAUNCH("fade_real_dev");
   return GLB_OK;
 }
 

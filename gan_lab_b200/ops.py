@@ -68,7 +68,7 @@ class _Axpby(Function):
 
 
 def axpby(a, b, alpha, beta):
-    return _Axpby.apply(a, b, float(alpha), float(beta))
+    return _Axpby.apply(a, b, K.coef_or_float(alpha), K.coef_or_float(beta))
 
 
 class _ActBwd(Function):
@@ -705,12 +705,12 @@ class _FadeUpBlend(Function):
 
 
 def fade_up_blend(lo, hi, alpha):
-    return _FadeUpBlend.apply(lo, hi, float(alpha))
+    return _FadeUpBlend.apply(lo, hi, K.coef_or_float(alpha))
 
 
 def fade_real(x, alpha):
     """Real-image fade-in (progan/learner.py:770-779) on the device; no gradient."""
-    return K.fade_real(x.detach(), float(alpha))
+    return K.fade_real(x.detach(), K.coef_or_float(alpha))
 
 
 # ----------------------------------------------------------------------------------------- losses

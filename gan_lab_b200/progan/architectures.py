@@ -233,7 +233,7 @@ class ProGenerator(ProGAN):
         for gen_block in self.gen_blocks[:-1]:
             x = gen_block(x)
         if self.fade_in_phase:
-            return ops.fade_up_blend(self.prev_torgb(x), self.torgb(self.gen_blocks[-1](x)), self.alpha)
+            return ops.fade_up_blend(self.prev_torgb(x), self.torgb(self.gen_blocks[-1](x)), self._state.blend_coefs()[0])
         return self.torgb(self.gen_blocks[-1](x))
 
 
@@ -317,8 +317,8 @@ class _DiscriminatorImpl(object):
         x = self.preprocess_x(x)
         if self.fade_in_phase:
             # prev_fromrgb(avg_pool2d(x))*(1-alpha) + disc_blocks[0](fromrgb(x))*alpha
-            x = ops.axpby(self.prev_fromrgb(x, pool=True), self.disc_blocks[0](self.fromrgb(x)),
-                          1. - self.alpha, self.alpha)
+            alpha, one_minus_alpha = self._state.blend_coefs()
+            x = ops.axpby(self.prev_fromrgb(x, pool=True), self.disc_blocks[0](self.fromrgb(x)), one_minus_alpha, alpha)
         else:
             x = self.disc_blocks[0](self.fromrgb(x))
         for disc_block in self.disc_blocks[1:]:

@@ -185,7 +185,7 @@ class ProGANLearner(GANLearner):
             _xgenb = self.gen_model(zb).detach()
         xb = xb.to(c.dev, non_blocking=True)
         if self.gen_model.fade_in_phase:
-            xb = ops.fade_real(xb, self.gen_model.alpha)
+            xb = ops.fade_real(xb, self.state.blend_coefs()[0])
         # R1 / R2 differentiate D at exactly the batch one of the two loss forwards already ran on (reference
         # resnetgan/learner.py:799-802 re-runs D on the same tensor): share that forward, so the penalty's create_graph
         # gradient and its double backward ride on the loss's own graph -- same values, one D forward and one
@@ -258,7 +258,14 @@ class ProGANLearner(GANLearner):
     # launch bound.  With `enable_cuda_graphs()` the D step and the G step (forward, double
     # backward, fused Adam/EWMA, RNG) are captured once per (resolution, phase, batch size) after a few eager
     # iterations and replayed; the real batch is copied into a static input buffer, the losses are static tensors.
-    def enable_cuda_graphs(self, enabled=True, warmup_iters=3):
+    def enable_cuda_graphs(self, enabled=True, warmup_iters=3, device_alpha=False):
+        """device_alpha: keep the fade-in alpha in a device vector read by the blend kernels (`_kernels.DeviceAlpha`), so that
+        fade-in phases -- whose alpha moves every iteration -- are captured and replayed as well (otherwise they run eagerly).
+        Opt-in until it has been measured on the GPU."""
+        if device_alpha:
+            self.state.enable_device_alpha(torch.device(self.config.dev))
+        else:
+            self.state.alpha_dev = None
         self._graph_on = bool(enabled)
         self._graph_warmup = int(warmup_iters)
         self._graph = None
@@ -266,15 +273,24 @@ class ProGANLearner(GANLearner):
         if hasattr(self.gen_model, '_use_mixing_reg'):
             self.gen_model.device_mixing = bool(enabled)   # mixing decision on the device (graph replayable)
 
+    def _push_alpha(self):
+        """Write the current alpha to its device-side copy (no-op without one); never inside a capture."""
+        if self.state.alpha_dev is not None:
+            self.state.alpha_dev.set(self.gen_model.alpha)
+
     def _graph_key(self):
         g = self.gen_model
-        return (g.curr_res, bool(g.fade_in_phase), float(g.alpha) if g.fade_in_phase else None, self.batch_size,
+        if g.fade_in_phase:      # with a device-side alpha only its being zero matters (host-side control flow depends on it)
+            alpha_key = ('dev', g.alpha != 0) if self.state.alpha_dev is not None else float(g.alpha)
+        else:
+            alpha_key = None
+        return (g.curr_res, bool(g.fade_in_phase), alpha_key, self.batch_size,
                 id(self.opt_disc), id(self.opt_gen), self.loss, self.gradient_penalty)
 
     def _graphs_allowed(self):
         if not self._graph_on or self.config.num_disc_iters != 1 or self.config.num_gen_iters != 1:
             return False
-        if self.gen_model.fade_in_phase and getattr(self, 'delta_alpha', 0.0) != 0.0:
+        if self.gen_model.fade_in_phase and getattr(self, 'delta_alpha', 0.0) != 0.0 and self.state.alpha_dev is None:
             return False                      # alpha is a kernel argument that changes every iteration while fading in
         return str(self.config.dev).startswith('cuda')
 
@@ -305,6 +321,7 @@ class ProGANLearner(GANLearner):
     def main_iteration(self, xb):
         """One D step on real batch `xb` + one G step (the num_disc_iters = num_gen_iters = 1 case); eager for the
         first `warmup_iters` iterations of a phase, CUDA-graph replay afterwards.  Returns (loss_d, loss_g) tensors."""
+        self._push_alpha()
         if self._graphs_allowed():
             if self._graph is not None and self._graph['key'] != self._graph_key():
                 self._graph, self._graph_eager_iters = None, 0
@@ -329,7 +346,7 @@ class ProGANLearner(GANLearner):
     # ------------------------------------------------------------------ validation metrics hooks (reference :248-416)
     def _fade_real_for_metrics(self, xb):
         """Real validation images are faded like the generated ones (reference :371-378)."""
-        return ops.fade_real(xb, self.gen_model.alpha) if self.gen_model.fade_in_phase else xb
+        return ops.fade_real(xb, self.gen_model.alpha) if self.gen_model.fade_in_phase else xb      # (host-side alpha: eval path)
 
     def _lagged_for_metrics(self):
         return self._update_gen_lagged() if self.config.use_ewma_gen else None
@@ -553,6 +570,7 @@ class ProGANLearner(GANLearner):
                 self.curr_img_num += self.batch_size
             else:
                 # ---- train discriminator ----
+                self._push_alpha()
                 for disc_iter in range(num_disc_iters):
                     loss_d = self.disc_step(self._next_real(train_dl))
                     if validate_d and disc_iter == num_disc_iters - 1:

@@ -382,7 +382,7 @@ class StyleGenerator(StyleGAN):
                 x = self._second_w(bs, x.device)
             out = self._layer_conv(self.gen_layers[-1], out)
             out = self._layer_tail(self.gen_layers[-1], out, x if ws is None else ws[n], noise[-1] if noise is not None else None)
-            return ops.fade_up_blend(skip, self.torgb(out), self.alpha)
+            return ops.fade_up_blend(skip, self.torgb(out), self._state.blend_coefs()[0])
 
         for n, layer in enumerate(self.gen_layers):
             if n:

@@ -171,6 +171,13 @@ int glb_mbstd_bwdbwd(const float* v, const float* gy, const float* x, float* ggx
 int glb_fade_up_blend(const float* lo, const float* hi, float* out, int N, int C, int H, int W, float alpha, glb_stream_t stream);
 int glb_fade_up_blend_bwd(const float* gout, float* glo, float* ghi, int N, int C, int H, int W, float alpha, glb_stream_t stream);
 int glb_fade_real(const float* x, float* out, int N, int C, int H, int W, float alpha, glb_stream_t stream);
+/* The same blends with the coefficients read ON THE DEVICE from `coef` = float[2] {alpha, 1 - alpha}: alpha moves every
+ * iteration of a fade-in phase (progan/learner.py:951-952), and a value baked into a captured CUDA graph could not.
+ * glb_axpby_dev: y = a*coef[ia] + b*coef[ib] (b may be NULL: y = a*coef[ia]). */
+int glb_axpby_dev(const float* a, const float* b, float* y, int64_t n, const float* coef, int ia, int ib, glb_stream_t stream);
+int glb_fade_up_blend_dev(const float* lo, const float* hi, float* out, int N, int C, int H, int W, const float* coef, glb_stream_t stream);
+int glb_fade_up_blend_bwd_dev(const float* gout, float* glo, float* ghi, int N, int C, int H, int W, const float* coef, glb_stream_t stream);
+int glb_fade_real_dev(const float* x, float* out, int N, int C, int H, int W, const float* coef, glb_stream_t stream);
 
 /* ---- real-image input pipeline ------------------------------------------------------------- *
  * Replaces the host-side torchvision chain every real sample goes through in the reference -- Resize(curr_res, PIL BOX)

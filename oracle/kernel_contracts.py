@@ -88,7 +88,16 @@ def colsum(x, scale):
     return scale * x.sum((0, 2, 3) if x.dim() == 4 else (0,))
 
 
+def _coef(v):
+    """A coefficient handed over as a device-side handle (gan_lab_b200._kernels.Coef) is read from the tensor the kernel would
+    read -- not from the host-side mirror -- so that a missing DeviceAlpha.set() shows up in the host-wiring tests."""
+    if hasattr(v, "ref") and hasattr(v, "idx"):
+        return float(v.ref.coef[v.idx])
+    return v
+
+
 def axpby(a, b, alpha, beta):
+    alpha, beta = _coef(alpha), _coef(beta)
     return _cl(alpha * a + (beta * b if b is not None else 0))
 
 
@@ -259,15 +268,17 @@ def plane_sum(img, scale):
 
 # ---- fade-in / losses / misc ---------------------------------------------------------------------------------------
 def fade_up_blend(lo, hi, alpha):
+    alpha = _coef(alpha)
     return (1 - alpha) * O.upsample2x(lo) + alpha * hi
 
 
 def fade_up_blend_bwd(gout, alpha):
+    alpha = _coef(alpha)
     return (1 - alpha) * F.avg_pool2d(gout, 2, 2) * 4, alpha * gout
 
 
 def fade_real(x, alpha):
-    return O.fade_real_images(x, alpha)
+    return O.fade_real_images(x, _coef(alpha))
 
 
 def d_logit_loss(d_gen, d_real, kind, eps_drift):

@@ -324,13 +324,16 @@ def _adam_close(mine, ref, lr, steps, what, frac=0.03):
     assert bad <= frac * tot, (what, bad, tot)
 
 
-def case_learner_grow(golden, dev, fname, model):
+def case_learner_grow(golden, dev, fname, model, device_alpha=False):
     """Learner.train() through a resolution increase vs the reference: phase bookkeeping, the
     optimiser / scheduler / EWMA rebuild at each phase change, the moving alpha incl. the real-image blend, the final
     phase.  The new block's initial values are taken from the reference (they are not taped draws); everything carried
     over (old blocks, torgb -> prev_torgb, lagged generator) is the learner's own."""
     g = _to(golden(fname), dev)
     L = _grow_learner(g, dev, model)
+    if device_alpha:         # the blends read alpha from a device vector (what lets fade-in phases replay as CUDA graphs)
+        L.enable_cuda_graphs(False, device_alpha=True)
+        assert L.state.alpha_dev is not None
     _load(L.gen_model, g["g_sd0"]); _load(L.disc_model, g["d_sd0"]); _load(L.gen_model_lagged, g["g_sd0"])
     snaps = {"g": [sd for t, sd in g["after_inc"] if t == "g"], "d": [sd for t, sd in g["after_inc"] if t == "d"]}
     lr_max = g["lr_base"] * max(g["lr_fctr_dict"][r] for r in (g["init_res"], g["res"]))

@@ -69,6 +69,11 @@ def test_learner_grow(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model)
 
 
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+def test_learner_grow_device_alpha(golden, fname, model):
+    PC.case_learner_grow(golden, DEV, fname, model, device_alpha=True)
+
+
 @pytest.mark.parametrize("fname,model", PC.RESUME_CASES)
 def test_learner_resume_from_reference_checkpoint(golden, fname, model):
     from conftest import GOLDEN

@@ -27,6 +27,11 @@ def test_learner_grow(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model)
 
 
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+def test_learner_grow_device_alpha(golden, fname, model):
+    PC.case_learner_grow(golden, DEV, fname, model, device_alpha=True)
+
+
 @pytest.mark.parametrize("fname,model", PC.RESUME_CASES)
 def test_learner_resume_from_reference_checkpoint(golden, fname, model):
     from conftest import GOLDEN
@@ -41,3 +46,43 @@ def test_checkpoint_roundtrip(golden, fname, model, tmp_path):
 @pytest.mark.parametrize("fname,model", PC.METRICS_CASES)
 def test_compute_metrics(golden, fname, model, tmp_path):
     PC.case_compute_metrics(golden, DEV, fname, model, tmp_path)
+
+
+def test_fade_in_phase_replays_as_cuda_graph_with_device_alpha():
+    """A fade-in phase with a MOVING alpha captured once (alpha lives in a device vector the blend kernels read): the graph
+    key does not change with alpha, and the replayed graph really reads it -- with the vector forced to alpha = 1 the branch
+    being faded out gets exactly zero gradient, with alpha = 0 the new branch does, whatever latents the replay draws."""
+    import math
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    torch.manual_seed(0)
+    cfg = default_config("StyleGAN", res=16, init_res=8, batch_size=4, dev=DEV, len_latent=32, len_dlatent=32,
+                         cutoff_trunc_trick=2)
+    L = StyleGANLearner(cfg)
+    L.gen_model.increase_scale(); L.disc_model.increase_scale()
+    L.gen_model.to(cfg.dev); L.disc_model.to(cfg.dev)
+    L.gen_model.alpha = 0.2
+    L.beta = L.get_smoothing_ewma_beta(10.)
+    L._sync_lagged_structure()
+    L._set_optimizer()
+    L.gen_model.train(); L.disc_model.train()
+    L._init_lagged(); L._attach_ewma()
+    L.delta_alpha = 0.05
+    L.enable_cuda_graphs(True, warmup_iters=2, device_alpha=True)
+    x = torch.rand(4, 3, 16, 16, device=DEV) * 2 - 1
+    keys = []
+    for i in range(5):
+        ld, lg = L.main_iteration(x)
+        keys.append(L._graph_key())
+        L.gen_model.alpha += L.delta_alpha
+    torch.cuda.synchronize()
+    assert L._graph is not None and len(set(keys)) == 1                 # captured once, replayed while alpha moved
+    assert abs(float(L.state.alpha_dev.coef[0]) - 0.4) < 1e-6          # the value pushed before the last replay
+    assert math.isfinite(float(ld)) and math.isfinite(float(lg))
+    G = L.gen_model
+    for alpha, dead, alive in ((1.0, G.prev_torgb, G.torgb), (0.0, G.torgb, G.prev_torgb)):
+        L.state.alpha_dev.coef.copy_(torch.tensor([alpha, 1.0 - alpha]))
+        L._graph["gd"].replay(); L._graph["gg"].replay()
+        torch.cuda.synchronize()
+        assert float(dead.conv2d.weight.grad.abs().max()) == 0.0, alpha
+        assert float(alive.conv2d.weight.grad.abs().max()) > 0.0, alpha
