@@ -258,10 +258,12 @@ class ProGANLearner(GANLearner):
     # launch bound.  With `enable_cuda_graphs()` the D step and the G step (forward, double
     # backward, fused Adam/EWMA, RNG) are captured once per (resolution, phase, batch size) after a few eager
     # iterations and replayed; the real batch is copied into a static input buffer, the losses are static tensors.
-    def enable_cuda_graphs(self, enabled=True, warmup_iters=3, device_alpha=False):
-        """device_alpha: keep the fade-in alpha in a device vector read by the blend kernels (`_kernels.DeviceAlpha`), so that
-        fade-in phases -- whose alpha moves every iteration -- are captured and replayed as well (otherwise they run eagerly).
-        Opt-in until it has been measured on the GPU."""
+    def enable_cuda_graphs(self, enabled=True, warmup_iters=3, device_alpha=None):
+        """device_alpha (default: on with graphs): keep the fade-in alpha in a device vector read by the blend kernels
+        (`_kernels.DeviceAlpha`), so that fade-in phases -- whose alpha moves every iteration -- are captured once and replayed
+        as well; without it they run eagerly (alpha is then a kernel argument)."""
+        if device_alpha is None:
+            device_alpha = bool(enabled)
         if device_alpha:
             self.state.enable_device_alpha(torch.device(self.config.dev))
         else:
