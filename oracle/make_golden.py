@@ -653,6 +653,78 @@ def golden_metrics(ref, model="StyleGAN", res=16, bs=4, n_valid=10):
         _unpatch(ref)
 
 
+# Configuration switches of the train step that the headline fixtures do not exercise (each is an attribute the reference's loop
+# or networks read, SURVEY.md section 8b "Learner surface to keep"); two main iterations each at 8x8 with 16 feature maps.
+TRAIN_VARIANTS = {
+    "style_minimax_r2": ("StyleGAN", dict(loss="minimax", gradient_penalty="r2")),
+    "style_wgan_wgangp_gamma": ("StyleGAN", dict(loss="wgan", gradient_penalty="wgan-gp", gamma=750., lda=5.)),
+    # (gen_bs_mult > 1 only works with the wgan loss in the reference: its BCE targets keep the discriminator's batch size)
+    "style_two_d_iters_gen_bs_mult": ("StyleGAN", dict(num_disc_iters=2, gen_bs_mult=2, loss="wgan")),
+    "style_no_noise_no_in_pixelnorm": ("StyleGAN", dict(use_noise=False, use_instancenorm=False, use_pixelnorm=True)),
+    "style_no_mixing_no_ewma_uniform": ("StyleGAN", dict(pct_mixing_reg=0., use_ewma_gen=False, latent_distribution="uniform",
+                                                          normalize_z=False)),
+    # (gradient_penalty=None is a documented choice, config.py:108, but the reference's property crashes on it, :908)
+    "style_linear_decay_no_drift": ("StyleGAN", dict(lr_sched="linear decay", eps_drift=0.)),
+    "style_nearest_pool_no_blur": ("StyleGAN", dict(model_downsample_type="nearest", blur_type=None, mbstd_group_size=2)),
+    "style_not_equalized_relu": ("StyleGAN", dict(use_equalized_lr=False, nonlinearity="relu", mapping_lrmul=1.)),
+    "pro_nonsaturating_r1_no_pixelnorm": ("ProGAN", dict(loss="nonsaturating", gradient_penalty="r1", use_pixelnorm=False)),
+    "pro_two_gen_iters_no_sched": ("ProGAN", dict(num_gen_iters=2, lr_sched=None, beta1=.5, wd=1e-3)),
+}
+VARIANT_FMAP = 16
+
+
+def golden_train_variants(ref, res=8, bs=4, iters=2):
+    out = {}
+    _patch_small(ref, VARIANT_FMAP)
+    try:
+        for name, (model, over) in TRAIN_VARIANTS.items():
+            torch.manual_seed(300 + len(out)); np.random.seed(300 + len(out))
+            if model == "StyleGAN":
+                over_ = dict(over)
+                over_.setdefault("cutoff_trunc_trick", int(np.log2(res)) - 2)
+                cfg = make_config("StyleGAN", res=res, init_res=res, batch_size=bs, len_latent=VARIANT_FMAP,
+                                  len_dlatent=VARIANT_FMAP, **over_)
+                with _quiet():
+                    L = ref.stylegan_learner.StyleGANLearner(cfg)
+            else:
+                cfg = make_config("ProGAN", res=res, init_res=res, batch_size=bs, len_latent=VARIANT_FMAP, **over)
+                with _quiet():
+                    L = ref.progan_learner.ProGANLearner(cfg)
+            gen = torch.Generator().manual_seed(400 + len(out))
+            perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+            g0, d0 = sd_clone(L.gen_model), sd_clone(L.disc_model)
+            n_d = cfg.num_disc_iters
+            data = torch.rand(iters * n_d * bs, 3, res, res, generator=gen) * 2 - 1
+            ds = TensorDataset(data)
+            dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+            losses, lrs, iter_snaps = [], [], {}
+            orig_backward = torch.Tensor.backward
+            per_iter = cfg.num_disc_iters + cfg.num_gen_iters
+
+            def rec_backward(self, *a, **k):
+                if len(losses) and len(losses) % per_iter == 0:      # first backward of a later main iteration
+                    iter_snaps[len(losses) // per_iter] = (sd_clone(L.gen_model), sd_clone(L.disc_model))
+                losses.append(float(self.detach()))
+                lrs.append((float(L.opt_disc.param_groups[0]["lr"]), float(L.opt_gen.param_groups[0]["lr"])))
+                return orig_backward(self, *a, **k)
+
+            torch.Tensor.backward = rec_backward
+            try:
+                with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+                    L.train(dl, num_main_iters=iters)
+            finally:
+                torch.Tensor.backward = orig_backward
+            lagged = {k: v.detach().clone() for k, v in L.lagged_params.items()} if cfg.use_ewma_gen else None
+            out[name] = dict(model=model, over=over, res=res, bs=bs, iters=iters, fmap_max=VARIANT_FMAP,
+                             len_latent=cfg.len_latent, g_sd0=g0, d_sd0=d0, data=data, tape=tape.events, losses=losses, lrs=lrs,
+                             iter_snaps=iter_snaps,      # parameters at the start of main iteration 1, 2, ...
+                             g_sd1=sd_clone(L.gen_model), d_sd1=sd_clone(L.disc_model), lagged=lagged,
+                             lr=cfg.lr_base * (cfg.lr_fctr_dict[res] if cfg.lr_sched == "resolution dependent" else 1.))
+        return out
+    finally:
+        _unpatch(ref)
+
+
 RESNET_FMAP = 8          # reference constants resnetgan/architectures.py:19-20 (FMAP_G = FMAP_D = 64) patched for small fixtures
 RESNET_LATENT = 16
 
@@ -757,6 +829,7 @@ def main():
         "pro_resume.pt": lambda: golden_resume(ref, "ProGAN"),
         "style_metrics.pt": lambda: golden_metrics(ref, "StyleGAN"),
         "pro_metrics.pt": lambda: golden_metrics(ref, "ProGAN"),
+        "train_variants.pt": lambda: golden_train_variants(ref),
         "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),

@@ -90,6 +90,11 @@ def test_compute_metrics(golden, fname, model, tmp_path):
     PC.case_compute_metrics(golden, DEV, fname, model, tmp_path)
 
 
+@pytest.mark.parametrize("name", PC.TRAIN_VARIANTS)
+def test_train_variant(golden, name, monkeypatch):
+    PC.case_train_variant(golden, DEV, name, monkeypatch)
+
+
 @pytest.mark.parametrize("gp", ["r1", "r2"])
 def test_shared_penalty_forward(gp):
     PC.case_shared_penalty_forward(DEV, gp)

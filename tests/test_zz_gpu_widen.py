@@ -86,3 +86,13 @@ def test_fade_in_phase_replays_as_cuda_graph_with_device_alpha():
         torch.cuda.synchronize()
         assert float(dead.conv2d.weight.grad.abs().max()) == 0.0, alpha
         assert float(alive.conv2d.weight.grad.abs().max()) > 0.0, alpha
+
+
+# Written after the round's GPU budget was spent: the host wiring of these switches is pinned on the CPU doubles
+# (tests/test_host_wiring.py::test_train_variant) and every kernel involved has its own GPU parity test, but this combination
+# has not been run on hardware yet -- non-strict xfail, so that the first hardware run records the outcome without turning an
+# otherwise verified suite red.  To be made plain tests once seen green.
+@pytest.mark.xfail(strict=False, reason="first hardware run of the configuration variants pending")
+@pytest.mark.parametrize("name", PC.TRAIN_VARIANTS)
+def test_train_variant(golden, name, monkeypatch):
+    PC.case_train_variant(golden, DEV, name, monkeypatch)
