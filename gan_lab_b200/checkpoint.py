@@ -59,6 +59,10 @@ class _Pickler(pickle._Pickler):
     """Pure-Python pickler (the C one cannot be told to write a global under another name).  Only the object skeleton goes
     through it; tensor payloads are written by torch as zip records."""
 
+    def __init__(self, *args, **kwargs):
+        super(_Pickler, self).__init__(*args, **kwargs)
+        self._renames = {cls: key for key, cls in _class_map().items()}
+
     def save_global(self, obj, name=None):
         ref_name = self._renames.get(obj)
         if ref_name is None:
@@ -71,8 +75,6 @@ class _Pickler(pickle._Pickler):
         else:
             self.write(pickle.GLOBAL + module.encode('utf-8') + b'\n' + qualname.encode('utf-8') + b'\n')
         self.memoize(obj)
-
-    _renames = {}
 
 
 class _PickleModule(object):
@@ -97,7 +99,6 @@ def load(path, map_location=None):
 
 def save(obj, path):
     """Write `obj` so that both `load()` and the reference's `torch.load` can read it."""
-    _Pickler._renames = {cls: key for key, cls in _class_map().items()}
     torch.save(obj, path, pickle_module=_PickleModule)
 
 
