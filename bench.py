@@ -412,6 +412,8 @@ def run_ours(args):
             glue["frac"] = glue["achieved"] / peaks["hbm_gbs"]
             glue["peak_source"] = peaks["src"] + " HBM copy bandwidth (read+write)"
             line["roofline_glue"] = glue
+        if world == 1:
+            line["roofline_input"] = input_pipeline_roofline(peaks)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -523,6 +525,37 @@ GLUE_LAUNCHERS = ("bias_act_fwd", "act_bwd", "blur_act_bwd", "axpby", "colsum", 
                   "style_epilogue_bwd", "rgb_expand", "rgb_contract", "rgb_wgrad", "fade_up_blend", "fade_up_blend_bwd",
                   "fade_real", "interp_rows", "batchnorm_fwd", "batchnorm_bwd", "layernorm_fwd", "layernorm_bwd",
                   "layernorm_bwdbwd", "tanh_fwd", "tanh_bwd", "adam_ewma_multi")
+
+
+def input_pipeline_roofline(peaks):
+    """HBM roofline of the real-image input kernel (csrc/input.cu), outside the timed step: 96 uint8
+    1024x1024 sources (302 MB > L2) -> the 128x128 fp32 batch the cfg2 step consumes; algorithmic bytes = 3 B per source pixel +
+    12 B per output pixel; CUDA events on the launch stream.  Never allowed to take the bench line down with it."""
+    try:
+        import torch
+        from gan_lab_b200 import _kernels as K
+        n, hs, ho = 96, 1024, 128
+        src = torch.randint(0, 256, (n, hs, hs, 3), dtype=torch.uint8, device="cuda")
+        idx = torch.randperm(n)
+        for _ in range(3):
+            out = K.u8_box_resize_normalize(src, idx, (ho, ho), (.5,) * 3, (.5,) * 3)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = K.u8_box_resize_normalize(src, idx, (ho, ho), (.5,) * 3, (.5,) * 3)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        gbs = (n * hs * hs * 3 + out.numel() * 4) / ms / 1e6
+        del src, out
+        return {"bound": "hbm", "kernel": "box_resize_normalize_kernel (Pillow BOX resize + ToTensor + Normalize, uint8 1024x1024 -> "
+                "fp32 128x128, 96 images per launch)", "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                "frac": gbs / peaks["hbm_gbs"], "traffic": None, "images_per_s": n / ms * 1e3, "launch_us": ms * 1e3}
+    except Exception as e:       # noqa: BLE001 -- an auxiliary figure
+        return {"error": repr(e)[:300]}
 
 
 def kernel_rooflines(L, x, main_iter, flush):
