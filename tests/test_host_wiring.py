@@ -148,3 +148,30 @@ def test_train_runs_validation_metrics_where_the_reference_does(capsys):
     out = capsys.readouterr().out
     assert out.count("Discriminator Validation Metrics:") == 2 and out.count("generator loss:") == 2
     assert (L.gen_metrics_num, L.disc_metrics_num) == (2, 2)
+
+
+def test_batch_size_changes_with_resolution_through_the_device_loader():
+    """bs_dict gives 8 samples per batch at 4x4 and 4 at 8x8: at the resolution increase train() re-sizes the loader's batches,
+    asks it for the new resolution, recomputes the EWMA beta and the transition length, and counts images accordingly.  (The
+    reference itself cannot run this under torch 2.11 -- BatchSampler caches its size -- so there is no fixture)"""
+    import torch
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.data import DeviceImageLoader
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    torch.manual_seed(0)
+    bs_dict = {r: 4 for r in (16, 32, 64, 128, 256, 512, 1024)}
+    bs_dict.update({4: 8, 8: 4})
+    cfg = default_config("StyleGAN", res=8, init_res=4, batch_size=8, dev=DEV, len_latent=32, len_dlatent=32, cutoff_trunc_trick=1,
+                         bs_dict=bs_dict, nimg_transition=12)          # not a multiple of 8 -> rounded up to 16 at 4x4, 12 at 8x8
+    L = StyleGANLearner(cfg)
+    images = torch.randint(0, 256, (32, 8, 8, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(1))
+    dl = DeviceImageLoader(images, batch_size=L.batch_size, res=4, shuffle=False, device=DEV)
+    seen = []
+    L.train(dl, num_main_iters=7, step_callback=lambda i, ld, lg: seen.append(
+        (L.gen_model.curr_res, L.batch_size, dl.res, dl.batch_sampler.batch_size, L.curr_img_num, round(float(L.gen_model.alpha), 6))))
+    assert seen[0][:4] == (4, 8, 4, 8) and seen[1][:4] == (4, 8, 4, 8)
+    assert [s[4] for s in seen] == [8, 16, 20, 24, 28, 32, 36]            # 2 x 8 images, then 4 per iteration
+    assert all(s[:4] == (8, 4, 8, 4) for s in seen[2:])
+    assert [s[5] for s in seen[2:5]] == [0.0, 0.5, 1.0]                  # delta_alpha = 4 / (12 - 4)
+    assert L.nimg_transition_lst[:3] == [16, 12, float("inf")] or L.nimg_transition_lst[:2] == [16, 12]
+    assert abs(L.beta - 0.5 ** (4 / 10000.)) < 1e-15
