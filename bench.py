@@ -278,6 +278,8 @@ def run_ours(args):
         DiscBlock.fuse_blur = os.environ["GLB_DISC_FUSE"] != "0"
     if os.environ.get("GLB_SIDE_STYLES"):
         L.gen_model.side_stream_styles = os.environ["GLB_SIDE_STYLES"] != "0"
+    if os.environ.get("GLB_BATCH_D"):          # A/B switch: D(fake) and D(real) as one pass over the concatenated batch
+        L.batch_d_passes = os.environ["GLB_BATCH_D"] != "0"
     if os.environ.get("GLB_PARALLEL_D"):
         L.parallel_d_passes = os.environ["GLB_PARALLEL_D"] != "0"
 
@@ -385,6 +387,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD_NAME[args.config], "global_batch": bs * world, "parallelism": f"dp{world}",
                        "conv_impl": args.conv_impl, "cuda_graphs": use_graphs,
                        "r1_shares_real_forward": bool(getattr(L, "share_penalty_forward", False)),
+                       "d_fake_real_one_pass": bool(getattr(L, "batch_d_passes", False)),
                        "grad_allreduce": (f"NCCL all-reduce, {L.dp.bucket_bytes >> 20} MiB buckets launched from grad hooks as they fill"
                                           if world > 1 else None), "l2": "8-batch input pool; activations per step (>1 GB) exceed the 126 MB L2",
                        "algorithmic_conv_gflop_per_step_per_gpu": flops / 1e9,

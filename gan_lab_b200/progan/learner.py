@@ -46,6 +46,11 @@ class ProGANLearner(GANLearner):
         self._progressively_grow = True
         self.dp = None
         self.share_penalty_forward = True
+        # D(fake) and D(real) as ONE pass over the concatenated batch: identical values (samples are independent in D except
+        # minibatch-stddev, whose groups of `mbstd_group_size` consecutive samples stay inside one half when the batch size is a
+        # multiple of it), half the discriminator launches, twice the work per launch in the latency-bound low-resolution layers,
+        # no gradient accumulation between the two passes.  Opt-in until measured on the GPU (bench: GLB_BATCH_D=1).
+        self.batch_d_passes = False
         self.parallel_d_passes = False     # two-stream D passes: measured neutral on B200 (598 vs 596 img/s at cfg2), kept as an option
         self._side_stream = None
         if self.model == self._model_name:
@@ -215,6 +220,10 @@ class ProGANLearner(GANLearner):
                 gp_term = self.gp_from_forward(discriminative_real, xb) if gp == 'r1' else None
             main.wait_stream(side)
             discriminative_gen.record_stream(main)
+        elif self._can_batch_d_passes(_xgenb, xb):
+            both = self.disc_model(torch.cat((_xgenb, xb), dim=0))
+            discriminative_gen, discriminative_real = both[:_xgenb.shape[0]], both[_xgenb.shape[0]:]
+            gp_term = None
         else:
             discriminative_gen = self.disc_model(_xgenb)
             discriminative_real = self.disc_model(xb)
@@ -236,6 +245,12 @@ class ProGANLearner(GANLearner):
             self.dp.allreduce_grads(self.disc_model)
         self.opt_disc.step()
         return loss_train_disc.detach()
+
+    def _can_batch_d_passes(self, fake, real):
+        if not self.batch_d_passes or fake.shape != real.shape:
+            return False
+        group = self.config.mbstd_group_size
+        return group is None or group <= 1 or fake.shape[0] % min(group, fake.shape[0]) == 0 and fake.shape[0] >= group
 
     def gen_step(self):
         """One generator step (reference progan/learner.py:854-916).  Returns the loss tensor."""

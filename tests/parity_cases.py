@@ -651,6 +651,43 @@ def case_shared_penalty_forward(dev, gp):
         assert relerr(g1[n], g0[n]) < 2e-4, (n, relerr(g1[n], g0[n]))
 
 
+def case_batched_d_passes(dev, gp, bs=4):
+    """disc_step with D(fake) and D(real) evaluated as one pass over the concatenated batch == two separate passes (loss and every
+    discriminator gradient), with the R1 / R2 penalty riding on its half of the batch; lda inflated so the penalty is visible.
+    With a batch smaller than the minibatch-stddev group the learner must fall back to separate passes by itself."""
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    grads = {}
+    for batched in (False, True):
+        torch.manual_seed(5)
+        cfg = default_config("StyleGAN", res=16, batch_size=bs, dev=dev, len_latent=32, len_dlatent=32,
+                             cutoff_trunc_trick=2, lda=1.e3, gradient_penalty=gp, pct_mixing_reg=0., use_ewma_gen=False)
+        L = StyleGANLearner(cfg)
+        gen = torch.Generator().manual_seed(6)
+        with torch.no_grad():
+            for m in (L.gen_model, L.disc_model):
+                for prm in m.parameters():
+                    if float(prm.abs().max()) == 0.0:
+                        prm.copy_((torch.randn(prm.shape, generator=gen) * 0.3).to(dev))
+        L.gen_model.train(); L.disc_model.train()
+        L.batch_d_passes = batched
+        calls = []
+        orig_forward = L.disc_model.forward
+        L.disc_model.forward = lambda x: calls.append(x.shape[0]) or orig_forward(x)
+        L.opt_disc.step = lambda: None
+        x = (torch.rand(bs, 3, 16, 16, generator=gen) * 2 - 1).to(dev)
+        torch.manual_seed(7)
+        loss = L.disc_step(x)
+        want_batched = batched and bs % 4 == 0
+        assert calls == ([2 * bs] if want_batched else [bs, bs]), calls
+        grads[batched] = (float(loss), {n: prm.grad.detach().clone() for n, prm in L.disc_model.named_parameters()
+                                        if prm.grad is not None})
+    (l0, g0), (l1, g1) = grads[False], grads[True]
+    assert abs(l0 - l1) <= 1e-5 * max(1.0, abs(l0)), (l0, l1)
+    assert g0.keys() == g1.keys()
+    for n in g0:
+        assert relerr(g1[n], g0[n]) < 2e-4, (n, relerr(g1[n], g0[n]))
+
+
 def _resnet_learner(g, dev, **over):
     """GANLearner for the small ResNet fixtures: the reference's FMAP_G / FMAP_D constants (resnetgan/architectures.py:19-20)
     were patched to g['fmap'] when the fixture was made; do the same to our mirror of them."""

@@ -175,3 +175,8 @@ def test_batch_size_changes_with_resolution_through_the_device_loader():
     assert [s[5] for s in seen[2:5]] == [0.0, 0.5, 1.0]                  # delta_alpha = 4 / (12 - 4)
     assert L.nimg_transition_lst[:3] == [16, 12, float("inf")] or L.nimg_transition_lst[:2] == [16, 12]
     assert abs(L.beta - 0.5 ** (4 / 10000.)) < 1e-15
+
+
+@pytest.mark.parametrize("gp,bs", [("r1", 4), ("r2", 8), ("r1", 2)])
+def test_batched_d_passes(gp, bs):
+    PC.case_batched_d_passes(DEV, gp, bs)

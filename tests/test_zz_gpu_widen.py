@@ -96,3 +96,9 @@ def test_fade_in_phase_replays_as_cuda_graph_with_device_alpha():
 @pytest.mark.parametrize("name", PC.TRAIN_VARIANTS)
 def test_train_variant(golden, name, monkeypatch):
     PC.case_train_variant(golden, DEV, name, monkeypatch)
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
+@pytest.mark.parametrize("gp,bs", [("r1", 4), ("r2", 8), ("r1", 2)])
+def test_batched_d_passes(gp, bs):
+    PC.case_batched_d_passes(DEV, gp, bs)
