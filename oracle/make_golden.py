@@ -811,6 +811,59 @@ def golden_resnet_train(ref, res=64, bs=4, iters=2, num_disc_iters=2):
                 g_sd1=sd_clone(L.gen_model), d_sd1=sd_clone(L.disc_model), lr=cfg.lr_base)
 
 
+def golden_resnet_resume(ref, res=32, bs=4, num_disc_iters=2):
+    """ResNet GAN: the reference trains one main iteration, saves (resnetgan/learner.py:1076-1137 -- with its Adam state: this
+    learner does not rebuild its optimisers before a save), a fresh reference learner loads the file and trains one more."""
+    torch.manual_seed(71); np.random.seed(71)
+    L, cfg = _resnet_learner(ref, res, bs, num_disc_iters=num_disc_iters, lr_base=1e-5)
+    gen = torch.Generator().manual_seed(73)
+    perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+    perturb_norm_params(L.gen_model, gen); perturb_norm_params(L.disc_model, gen)
+    data = torch.rand(2 * num_disc_iters * bs, 3, res, res, generator=gen) * 2 - 1
+
+    def loader():
+        ds = TensorDataset(data)
+        return DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+
+    with _quiet(), contextlib.redirect_stderr(io.StringIO()):
+        L.train(loader(), num_main_iters=1)
+    L.valid_z = torch.zeros(cfg.img_grid_sz ** 2, cfg.len_latent)          # see golden_resume
+    ckpt = GOLDEN_DIR / "resnetgan_reference_checkpoint.tar"
+    # save_model() writes the module constants FMAP_G / FMAP_D (resnetgan/learner.py:1082-1085): keep them at the small fixtures' value
+    ref.resnet_learner.FMAP_G = ref.resnet_learner.FMAP_D = RESNET_FMAP
+    try:
+        L.save_model(ckpt)
+    finally:
+        ref.resnet_learner.FMAP_G = ref.resnet_learner.FMAP_D = 64
+    saved = dict(g_sd=sd_clone(L.gen_model), d_sd=sd_clone(L.disc_model), img_num=int(L.curr_img_num),
+                 opt_disc_steps=sorted({float(st["step"]) for st in L.opt_disc.state_dict()["state"].values()}))
+    L2, _ = _resnet_learner(ref, res, bs, num_disc_iters=num_disc_iters, lr_base=1e-5)
+    orig_load = torch.load
+    torch.load = lambda *a, **k: orig_load(*a, **{"weights_only": False, **k})
+    try:
+        with _quiet():
+            L2.load_model(ckpt, dev_of_saved_model="cpu")
+    finally:
+        torch.load = orig_load
+    losses = []
+    orig_backward = torch.Tensor.backward
+
+    def rec_backward(self, *a, **k):
+        losses.append(float(self.detach()))
+        return orig_backward(self, *a, **k)
+
+    torch.Tensor.backward = rec_backward
+    try:
+        with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+            L2.train(loader(), num_main_iters=1)
+    finally:
+        torch.Tensor.backward = orig_backward
+    return dict(model="ResNet GAN", checkpoint=ckpt.name, res=res, bs=bs, num_disc_iters=num_disc_iters, fmap=RESNET_FMAP,
+                len_latent=cfg.len_latent, data=data, saved=saved, tape=tape.events, losses=losses, lr=cfg.lr_base,
+                g_sd1=sd_clone(L2.gen_model), d_sd1=sd_clone(L2.disc_model), img_num=int(L2.curr_img_num),
+                opt_disc_steps=sorted({float(st["step"]) for st in L2.opt_disc.state_dict()["state"].values()}))
+
+
 def main():
     ref = load_reference()
     GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
@@ -833,6 +886,7 @@ def main():
         "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),
+        "resnet_resume_res32.pt": lambda: golden_resnet_resume(ref),
     }
     only = sys.argv[1:]
     for name, fn in jobs.items():

@@ -780,6 +780,47 @@ def case_resnet_train(golden, dev):
     adam_close(L.disc_model.state_dict(), g["d_sd1"], "D", iters * g["num_disc_iters"])
 
 
+def case_resnet_resume(golden, dev, golden_dir):
+    """GANLearner.load_model() of a checkpoint the UNMODIFIED reference wrote after one ResNet-GAN iteration -- networks, BatchNorm
+    buffers and torch.optim.Adam state (step 2, both moments) -- then one more iteration vs the reference resuming from the file."""
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    g = _to(golden("resnet_resume_res32.pt"), dev)
+    L, _ = _resnet_learner(g, dev)
+    L.load_model(golden_dir / g["checkpoint"], dev_of_saved_model="cpu", dev=dev)
+    assert (L.config.num_disc_iters, L.config.lr_base, L.curr_img_num, L.batch_size) == (g["num_disc_iters"], g["lr"],
+                                                                                          g["saved"]["img_num"], g["bs"])
+    for mine, ref in ((L.gen_model.state_dict(), g["saved"]["g_sd"]), (L.disc_model.state_dict(), g["saved"]["d_sd"])):
+        assert list(mine.keys()) == list(ref.keys())
+        for k, v in ref.items():
+            assert torch.equal(mine[k], v), k
+    assert sorted({float(st["step"]) for st in L.opt_disc.state_dict()["state"].values()}) == g["saved"]["opt_disc_steps"]
+    for p in L.opt_disc.param_groups[0]["params"]:
+        st = L.opt_disc.state[p]
+        assert st["exp_avg_sq"].stride() == p.stride() and st["exp_avg_sq"].device == p.device
+    ds = TensorDataset(g["data"])
+    dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=g["bs"], drop_last=True))
+    set_random_source(TapeSource(g["tape"], dev))
+    losses = []
+    orig_d, orig_g = L.disc_step, L.gen_step
+    L.disc_step = lambda xb: losses.append(float(orig_d(xb))) or torch.tensor(losses[-1])
+    L.gen_step = lambda: losses.append(float(orig_g())) or torch.tensor(losses[-1])
+    L.train(dl, num_main_iters=1)
+    assert L.curr_img_num == g["img_num"]
+    assert sorted({float(st["step"]) for st in L.opt_disc.state_dict()["state"].values()}) == g["opt_disc_steps"]
+    for i, (a, b) in enumerate(zip(losses, g["losses"])):
+        assert abs(a - b) < (1e-4 if i == 0 else 1e-3) * max(1.0, abs(b)), (losses, g["losses"])
+    # steps 3 and 4 of the loaded Adam state: a wrong step count or lost moments would move every element by a different amount
+    for mine, ref, steps in ((L.gen_model.state_dict(), g["g_sd1"], 1), (L.disc_model.state_dict(), g["d_sd1"], g["num_disc_iters"])):
+        bad = tot = 0
+        for k, v in ref.items():
+            if not v.is_floating_point() or "running_" in k:
+                continue
+            d = (mine[k].detach() - v).abs()
+            assert float(d.max()) <= 4.0 * g["lr"] * steps + 1e-7, (k, float(d.max()))
+            bad += int((d > 0.02 * g["lr"] + 2e-7 * v.abs()).sum()); tot += v.numel()
+        assert bad <= 0.05 * tot, (bad, tot)
+
+
 def case_style_eval(golden, dev):
     """Evaluation-mode StyleGenerator vs the reference's: supplied noise, truncation trick (psi, cut-off stage and the
     de-truncation above it), style mixing below and above the cut-off, and truncation switched off."""

@@ -180,3 +180,8 @@ def test_batch_size_changes_with_resolution_through_the_device_loader():
 @pytest.mark.parametrize("gp,bs", [("r1", 4), ("r2", 8), ("r1", 2)])
 def test_batched_d_passes(gp, bs):
     PC.case_batched_d_passes(DEV, gp, bs)
+
+
+def test_resnet_resume_from_reference_checkpoint(golden):
+    from conftest import GOLDEN
+    PC.case_resnet_resume(golden, DEV, GOLDEN)

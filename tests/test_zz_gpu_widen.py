@@ -102,3 +102,9 @@ def test_train_variant(golden, name, monkeypatch):
 @pytest.mark.parametrize("gp,bs", [("r1", 4), ("r2", 8), ("r1", 2)])
 def test_batched_d_passes(gp, bs):
     PC.case_batched_d_passes(DEV, gp, bs)
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
+def test_resnet_resume_from_reference_checkpoint(golden):
+    from conftest import GOLDEN
+    PC.case_resnet_resume(golden, DEV, GOLDEN)
