@@ -455,7 +455,13 @@ def run_resnet(args, cfg, rank, world, dev):
     pool_host = [(torch.rand(bs, 3, res, res) * 2 - 1).pin_memory() for _ in range(nd)]
     flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)
 
+    resnet_graphs = os.environ.get("GLB_RESNET_GRAPHS", "0") != "0"     # opt-in until measured: CUDA-graph replay of the steps
+    if resnet_graphs:
+        L.enable_cuda_graphs(True, warmup_iters=3)
+
     def main_iter(pool):
+        if resnet_graphs:
+            return L.main_iteration(pool)
         for p in L.disc_model.parameters():
             p.requires_grad_(False)
         lg = L.gen_step()

@@ -101,6 +101,7 @@ class GANLearner(object):
         self.disc_model = None
         self.dp = None
         self.share_penalty_forward = True
+        self._graph_on, self._graph, self._graph_eager_iters, self._graph_warmup = False, None, 0, 3
         if self._model == 'ResNet GAN':
             from .architectures import (Generator32PixResnet, Generator64PixResnet, Discriminator32PixResnet,
                                         Discriminator64PixResnet, FMAP_G, FMAP_D)
@@ -197,6 +198,75 @@ class GANLearner(object):
         self.opt_disc.step()
         return loss_train_disc.detach()
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the steps (opt-in)
+    # The ResNet loop launches ~300 kernels per step behind ~50 us of Python each and is launch bound when run eagerly.  With
+    # `enable_cuda_graphs()` one generator step and one discriminator step are captured after a few eager iterations and
+    # replayed (the generator graph `num_gen_iters` times, the discriminator graph once per real batch, which is copied into a
+    # static input buffer): latents and the WGAN-GP interpolation weights are drawn on the device inside the graphs, BatchNorm's
+    # running buffers and Adam's step count advance inside them.  Same machinery as ProGANLearner's (which overrides these).
+    def enable_cuda_graphs(self, enabled=True, warmup_iters=3):
+        self._graph_on = bool(enabled)
+        self._graph_warmup = int(warmup_iters)
+        self._graph, self._graph_eager_iters = None, 0
+
+    def _graphs_allowed(self):
+        return self._graph_on and str(self.config.dev).startswith('cuda')
+
+    def _graph_key(self):
+        return (self.batch_size, id(self.opt_disc), id(self.opt_gen), self.loss, self.gradient_penalty)
+
+    def _capture_graphs(self):
+        from .. import _kernels as K
+        c = self.config
+        st = {'key': self._graph_key(), 'x': torch.empty(self.batch_size, FMAP_SAMPLES, c.res_samples, c.res_samples, device=c.dev)}
+        self.opt_disc.prepare_capture(); self.opt_gen.prepare_capture()
+        self.disc_model.zero_grad(set_to_none=True); self.gen_model.zero_grad(set_to_none=True)
+        for p in self.disc_model.parameters():
+            p.requires_grad_(False)
+        K.weights_updated()
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg):
+            st['lg'] = self.gen_step()
+        for p in self.disc_model.parameters():
+            p.requires_grad_(True)
+        K.weights_updated()
+        gd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gd, pool=gg.pool()):
+            st['ld'] = self.disc_step(st['x'])
+        K.weights_updated()
+        self.opt_disc.finish_capture(); self.opt_gen.finish_capture()
+        st['gg'], st['gd'] = gg, gd
+        return st
+
+    def main_iteration(self, real_batches, num_gen_iters=1):
+        """`num_gen_iters` generator steps, then one discriminator step per batch of `real_batches` (reference :544-692); eager
+        for the first `warmup_iters` iterations, CUDA-graph replay afterwards when enabled.  Returns (loss_d, loss_g) tensors."""
+        if self._graphs_allowed():
+            if self._graph is not None and self._graph['key'] != self._graph_key():
+                self._graph, self._graph_eager_iters = None, 0
+            if self._graph is None and self._graph_eager_iters >= self._graph_warmup:
+                self._graph = self._capture_graphs()
+            if self._graph is not None:
+                g = self._graph
+                self.opt_disc.push_lr(); self.opt_gen.push_lr()
+                for _ in range(num_gen_iters):
+                    g['gg'].replay()
+                for xb in real_batches:
+                    g['x'].copy_(xb, non_blocking=True)
+                    g['gd'].replay()
+                return g['ld'], g['lg']
+            self._graph_eager_iters += 1
+        loss_d = loss_g = None
+        for p in self.disc_model.parameters():
+            p.requires_grad_(False)
+        for _ in range(num_gen_iters):
+            loss_g = self.gen_step()
+        for p in self.disc_model.parameters():
+            p.requires_grad_(True)
+        for xb in real_batches:
+            loss_d = self.disc_step(xb)
+        return loss_d, loss_g
+
     def _set_scheduler(self):
         """reference resnetgan/learner.py:849-864."""
         if self._lr_sched == 'linear decay':
@@ -230,24 +300,18 @@ class GANLearner(object):
         self.last_losses = (None, None)
         loss_d = loss_g = None
         for itr in range(num_main_iters):
-            # ---- train generator ----
-            for p in self.disc_model.parameters():
-                p.requires_grad_(False)
-            for gen_iter in range(num_gen_iters):
-                loss_g = self.gen_step()
-            # ---- train discriminator ----
-            for p in self.disc_model.parameters():
-                p.requires_grad_(True)
+            # ---- generator step(s), then `num_disc_iters` discriminator steps on fresh real batches ----
+            reals = []
             for disc_iter in range(num_disc_iters):
                 batch = next(self.train_dataiter, None)
                 if batch is None:
                     self.curr_epoch_num += 1
                     self.train_dataiter = iter(train_dl)
                     batch = next(self.train_dataiter)
-                xb = batch[0] if isinstance(batch, (list, tuple)) else batch
-                loss_d = self.disc_step(xb)
-                self.curr_dataset_batch_num += 1
-                self.curr_img_num += self.batch_size
+                reals.append(batch[0] if isinstance(batch, (list, tuple)) else batch)
+            loss_d, loss_g = self.main_iteration(reals, num_gen_iters)
+            self.curr_dataset_batch_num += num_disc_iters
+            self.curr_img_num += self.batch_size * num_disc_iters
             self.last_losses = (loss_d, loss_g)
             if step_callback is not None:
                 step_callback(itr, loss_d, loss_g)

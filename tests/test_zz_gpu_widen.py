@@ -108,3 +108,34 @@ def test_batched_d_passes(gp, bs):
 def test_resnet_resume_from_reference_checkpoint(golden):
     from conftest import GOLDEN
     PC.case_resnet_resume(golden, DEV, GOLDEN)
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
+def test_resnet_steps_replay_as_cuda_graphs(golden):
+    """ResNet GAN: one generator step and one discriminator step captured and replayed (opt-in): Adam's device-side step count,
+    BatchNorm's num_batches_tracked and the parameters advance per replay, fresh latents per replay, everything finite."""
+    import math
+    g = golden("resnet_train_res64.pt")
+    L, _ = PC._resnet_learner(g, DEV, num_disc_iters=2)
+    L.gen_model.train(); L.disc_model.train()
+    L.enable_cuda_graphs(True, warmup_iters=2)
+    xs = [torch.rand(g["bs"], 3, g["res"], g["res"], device=DEV) * 2 - 1 for _ in range(2)]
+    for _ in range(2):
+        L.main_iteration(xs)
+    assert L._graph is None
+    ld, lg = L.main_iteration(xs)                       # capture + first replay
+    assert L._graph is not None
+    torch.cuda.synchronize()
+    nbt = next(b for n, b in L.gen_model.named_buffers() if n.endswith("num_batches_tracked"))
+    n0, t0 = int(nbt), float(next(iter(L.opt_disc._hyper.values()))["t"][3])
+    w0 = next(L.disc_model.parameters()).detach().clone()
+    l1 = (float(ld), float(lg))
+    ld, lg = L.main_iteration(xs)
+    torch.cuda.synchronize()
+    l2 = (float(ld), float(lg))
+    assert int(nbt) == n0 + 3                           # 1 generator step + 2 discriminator steps run the generator forward
+    assert float(next(iter(L.opt_disc._hyper.values()))["t"][3]) == t0 + 2
+    assert not torch.equal(w0, next(L.disc_model.parameters()).detach())
+    assert all(math.isfinite(v) for v in l1 + l2) and l1 != l2
+    for p in list(L.gen_model.parameters()) + list(L.disc_model.parameters()):
+        assert torch.isfinite(p).all()
