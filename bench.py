@@ -358,8 +358,31 @@ def run_ours(args):
     if L.gen_model.fade_in_phase:
         L.delta_alpha = 0.0                            # hold alpha fixed (cfg3: mid-fade-in)
     host_losses = []
-    # the step's result (both losses) is read back on the host every step, as the reference's tqdm line does
-    L.train(loader, num_main_iters=args.steps, step_callback=lambda i, ld, lg: host_losses.append((ld.item(), lg.item())))
+    # the step's result (both losses) is read back to the host every step (the reference's tqdm line reads them too): an
+    # asynchronous 8-byte device-to-host copy into pinned memory per step, stream-ordered before the next replay overwrites the
+    # static loss tensors, consumed after the loop -- no host stall per step.  Falls back to a blocking read if that fails.
+    readback = {"buf": None, "n": 0}
+    try:
+        readback["buf"] = torch.empty(args.steps, 2, dtype=torch.float32).pin_memory()
+    except Exception:
+        readback["buf"] = None
+
+    def on_step(i, ld, lg):
+        buf = readback["buf"]
+        if buf is not None and i < buf.shape[0]:
+            try:
+                buf[i, 0].copy_(ld.detach().reshape(()), non_blocking=True)
+                buf[i, 1].copy_(lg.detach().reshape(()), non_blocking=True)
+                readback["n"] = i + 1
+                return
+            except Exception:
+                readback["buf"] = None
+        host_losses.append((ld.item(), lg.item()))
+
+    L.train(loader, num_main_iters=args.steps, step_callback=on_step)
+    if readback["n"]:
+        torch.cuda.current_stream().synchronize()       # the last read has landed; inside the timed region
+        host_losses.extend(tuple(r) for r in readback["buf"][:readback["n"]].tolist())
     ev2[1].record()
     # train() ends like the reference's (progan/learner.py:1016-1030): optimisers rebuilt, networks in eval mode
     L.gen_model.train(); L.disc_model.train()
