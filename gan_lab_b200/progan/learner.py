@@ -77,6 +77,11 @@ class ProGANLearner(GANLearner):
     def _finish_init(self, config):
         c = self.config
         assert c.init_res <= c.res_samples
+        if getattr(c, 'bit_exact_resampling', False):
+            # reference :770-776: the real images' fade-in skip connection through PIL (de-normalise -> uint8 -> BOX down ->
+            # NEAREST up -> normalise).  Only the default torch-resampling variant (:777-779) has a kernel (`ops.fade_real`).
+            raise NotImplementedError("bit_exact_resampling=True (PIL resampling of the real images' skip connection) is not "
+                                      "built; the default (False) is")
         if c.init_res > 4:
             _init_res_log2 = int(np.log2(c.init_res))
             if float(c.init_res) != 2 ** _init_res_log2:
