@@ -438,7 +438,10 @@ class ProGANLearner(GANLearner):
         self.gen_model_upsampler = as_native_upsampler(gmeta['gen_model_upsampler'])
         self.disc_model_downsampler = as_native_pooler(dmeta['disc_model_downsampler'])
         self.num_classes_gen, self.num_classes_disc = gmeta['num_classes_gen'], dmeta['num_classes_disc']
+        had_device_alpha = getattr(self, 'state', None) is not None and self.state.alpha_dev is not None
         self.state = GrowthState()
+        if had_device_alpha:
+            self.state.enable_device_alpha(torch.device(c.dev))
         self._build_models()
         self._restore_extra_checkpoint_entries(checkpoint)
         assert c.init_res <= c.res_samples
