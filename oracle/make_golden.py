@@ -228,14 +228,22 @@ def golden_layers(ref):
 
 
 # --------------------------------------------------------------------------- #
-def _patch_small(ref, fmap_max=SMALL_FMAP_MAX):
-    ref.stylegan_base.FMAP_MAX = fmap_max
-    ref.progan_base.FMAP_MAX = fmap_max
+def _patch_small(ref, fmap_max=SMALL_FMAP_MAX, fmap_base=8192):
+    """fmap(stage) = min(FMAP_BASE / 2^stage, FMAP_MAX) (stylegan/base.py:16-17, 76-77).  With the default base every stage of a
+    small fixture sits at FMAP_MAX; TAPER_FMAP_BASE makes the channel count halve from 16x16 on, like 512 -> 256 -> 128 ... in the
+    full-size networks (blocks with ni != nf, prev_torgb / torgb of different widths)."""
+    for mod in (ref.stylegan_base, ref.progan_base):
+        mod.FMAP_MAX = fmap_max
+        mod.FMAP_BASE = fmap_base
+
+
+TAPER_FMAP_BASE = 128      # 32, 32, 16, 8 feature maps at 4, 8, 16, 32 pixels
 
 
 def _unpatch(ref):
-    ref.stylegan_base.FMAP_MAX = 512
-    ref.progan_base.FMAP_MAX = 512
+    for mod in (ref.stylegan_base, ref.progan_base):
+        mod.FMAP_MAX = 512
+        mod.FMAP_BASE = 8192
 
 
 def _quiet():
@@ -251,9 +259,9 @@ def _build_style_learner(ref, res, init_res, bs, **over):
     return L, cfg
 
 
-def golden_style_nets(ref, res=16, bs=4, fade_in=False):
+def golden_style_nets(ref, res=16, bs=4, fade_in=False, fmap_base=8192):
     """StyleGenerator / StyleDiscriminator forward+backward(+R1) on the reference modules."""
-    _patch_small(ref)
+    _patch_small(ref, fmap_base=fmap_base)
     try:
         torch.manual_seed(7 + int(fade_in)); np.random.seed(7)
         L, cfg = _build_style_learner(ref, res, res // 2 if fade_in else res, bs)
@@ -289,7 +297,7 @@ def golden_style_nets(ref, res=16, bs=4, fade_in=False):
         # grad of D output wrt image (the G-step path)
         xi = img.detach().clone().requires_grad_(True)
         gxi, = torch.autograd.grad(D(xi), xi, glog)
-        return dict(res=res, bs=bs, fade_in=fade_in, alpha=alpha, fmap_max=SMALL_FMAP_MAX,
+        return dict(res=res, bs=bs, fade_in=fade_in, alpha=alpha, fmap_max=SMALL_FMAP_MAX, fmap_base=fmap_base,
                     len_latent=cfg.len_latent, g_sd=sd_clone(G), d_sd=sd_clone(D), z=z, tape=tape.events,
                     img=img.detach(), w_ewma=w_ewma, gimg=gimg, g_grads=g_grads, x=x, logits=logits.detach(),
                     glog=glog, d_grads=d_grads, gp=gp.detach(), d_gp_grads=d_gp_grads, d_gx_img=gxi,
@@ -332,8 +340,8 @@ def golden_style_eval(ref, res=32, bs=3):
         _unpatch(ref)
 
 
-def golden_pro_nets(ref, res=16, bs=4, fade_in=False):
-    _patch_small(ref)
+def golden_pro_nets(ref, res=16, bs=4, fade_in=False, fmap_base=8192):
+    _patch_small(ref, fmap_base=fmap_base)
     try:
         torch.manual_seed(11 + int(fade_in)); np.random.seed(11)
         cfg = make_config("ProGAN", res=res, init_res=res // 2 if fade_in else res, batch_size=bs,
@@ -362,7 +370,7 @@ def golden_pro_nets(ref, res=16, bs=4, fade_in=False):
             gp = L.calc_gp(img.detach(), x)          # wgan-gp: draws eps via torch.rand
         gp.backward()
         d_gp_grads = grads_of(D)
-        return dict(res=res, bs=bs, fade_in=fade_in, alpha=alpha, fmap_max=SMALL_FMAP_MAX,
+        return dict(res=res, bs=bs, fade_in=fade_in, alpha=alpha, fmap_max=SMALL_FMAP_MAX, fmap_base=fmap_base,
                     len_latent=cfg.len_latent, g_sd=sd_clone(G), d_sd=sd_clone(D), z=z, img=img.detach(),
                     gimg=gimg, g_grads=g_grads, x=x, logits=logits.detach(), glog=glog, d_grads=d_grads,
                     gp=gp.detach(), gp_tape=tape.events, d_gp_grads=d_gp_grads, lda=cfg.lda, gamma=cfg.gamma)
@@ -437,16 +445,16 @@ class PILBoxDataset(torch.utils.data.Dataset):
 
 
 def golden_grow(ref, model="StyleGAN", init_res=4, res=8, bs_dict=None, nimg_transition=16, iters=11, data_res=8,
-                snap_iters=tuple(range(1, 11))):
+                snap_iters=tuple(range(1, 11)), fmap_base=8192):
     """Learner.train() THROUGH a resolution increase: stabilise at `init_res`, grow, fade the new
     block in with a moving alpha (incl. the real-image blend, progan/learner.py:770-779), stabilise at `res`, enter the
     final phase.  Recorded besides the usual train fixture: the parameters right after every increase_scale() (the
     freshly initialised block does not come from taped draws), every real sample served, and a per-iteration trace of
     (curr_res, fade_in_phase, alpha, batch size, learning rates, phase number)."""
-    _patch_small(ref)
+    _patch_small(ref, fmap_base=fmap_base)
     try:
         torch.manual_seed(77); np.random.seed(77)
-        bs_dict = bs_dict or {4: 4, 8: 4}     # a batch-size change mid-iterator breaks the reference itself under torch 2.11 (BatchSampler caches it)
+        bs_dict = bs_dict or {r: 4 for r in (4, 8, 16, 32)}     # a batch-size change mid-iterator breaks the reference itself under torch 2.11 (BatchSampler caches it)
         over = dict(bs_dict={**{r: 4 for r in (4, 8, 16, 32, 64, 128, 256, 512, 1024)}, **bs_dict},
                     nimg_transition=nimg_transition, res_dataset=data_res,
                     lr_fctr_dict={4: 1., 8: 1.5, 16: 2., 32: 1., 64: 1., 128: 1., 256: 1., 512: 1., 1024: 1.})
@@ -495,8 +503,8 @@ def golden_grow(ref, model="StyleGAN", init_res=4, res=8, bs_dict=None, nimg_tra
         finally:
             torch.Tensor.backward = orig_backward
         lagged = {k: v.detach().clone() for k, v in L.lagged_params.items()}
-        out = dict(model=model, init_res=init_res, res=res, iters=iters, fmap_max=SMALL_FMAP_MAX, len_latent=cfg.len_latent,
-                   bs_dict=dict(cfg.bs_dict), nimg_transition=nimg_transition, lr_fctr_dict=dict(cfg.lr_fctr_dict),
+        out = dict(model=model, init_res=init_res, res=res, iters=iters, fmap_max=SMALL_FMAP_MAX, fmap_base=fmap_base,
+                   len_latent=cfg.len_latent, bs_dict=dict(cfg.bs_dict), nimg_transition=nimg_transition, lr_fctr_dict=dict(cfg.lr_fctr_dict),
                    lr_base=cfg.lr_base, data_res=data_res, images_u8=torch.from_numpy(images),
                    g_sd0=g0, d_sd0=d0, after_inc=after_inc, served=ds.served, tape=tape.events, losses=losses, trace=trace,
                    iter_snaps=iter_snaps,      # parameters at the START of those iterations (behind that many updates)
@@ -876,6 +884,12 @@ def main():
         "pro_nets_res8_fade.pt": lambda: golden_pro_nets(ref, 8, 4, True),
         "style_train_res16.pt": lambda: golden_train_steps(ref, "StyleGAN", 16, 4, 2),
         "pro_train_res8.pt": lambda: golden_train_steps(ref, "ProGAN", 8, 4, 2),
+        "style_nets_res32_taper_fade.pt": lambda: golden_style_nets(ref, 32, 4, True, fmap_base=TAPER_FMAP_BASE),
+        "pro_nets_res32_taper_fade.pt": lambda: golden_pro_nets(ref, 32, 4, True, fmap_base=TAPER_FMAP_BASE),
+        "style_grow_8to16_taper.pt": lambda: golden_grow(ref, "StyleGAN", init_res=8, res=16, data_res=16, iters=10,
+                                                         snap_iters=(2, 4, 5, 6, 8), fmap_base=TAPER_FMAP_BASE),
+        "pro_grow_8to16_taper.pt": lambda: golden_grow(ref, "ProGAN", init_res=8, res=16, data_res=16, iters=10,
+                                                       snap_iters=(2, 4, 5, 6, 8), fmap_base=TAPER_FMAP_BASE),
         "style_grow_4to8.pt": lambda: golden_grow(ref, "StyleGAN"),
         "pro_grow_4to8.pt": lambda: golden_grow(ref, "ProGAN"),
         "style_resume.pt": lambda: golden_resume(ref, "StyleGAN"),

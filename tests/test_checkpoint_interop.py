@@ -75,7 +75,7 @@ def test_fused_adam_state_dict_is_torch_adams():
 
 
 @pytest.mark.skipif(not reference_available(), reason="needs the reference tree (build container only)")
-@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES + PC.GROW_TAPER_CASES)
 def test_reference_loads_our_checkpoint(golden, fname, model, tmp_path):
     """This package trains through a resolution increase and saves mid-fade-in; the unmodified reference's load_model()
     rebuilds its own networks from the file: same parameters, same phase, and its train() runs on from there."""
@@ -90,7 +90,7 @@ def test_reference_loads_our_checkpoint(golden, fname, model, tmp_path):
     L.save_model(path)
 
     ref = load_reference()
-    MG._patch_small(ref)
+    MG._patch_small(ref, fmap_base=g.get("fmap_base", 8192))
     orig_load = torch.load
     torch.load = lambda *a, **k: orig_load(*a, **{"weights_only": False, **k})     # torch >= 2.6 default; see make_golden
     try:

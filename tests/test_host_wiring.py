@@ -49,12 +49,12 @@ def test_style_epilogue_op(golden):
     PC.case_style_epilogue_op(golden, DEV)
 
 
-@pytest.mark.parametrize("fname", PC.STYLE_NETS)
+@pytest.mark.parametrize("fname", PC.STYLE_NETS + PC.STYLE_NETS_TAPER)
 def test_style_nets_modules(golden, fname):
     PC.case_style_nets_modules(golden, DEV, fname)
 
 
-@pytest.mark.parametrize("fname", PC.PRO_NETS)
+@pytest.mark.parametrize("fname", PC.PRO_NETS + PC.PRO_NETS_TAPER)
 def test_pro_nets_modules(golden, fname):
     PC.case_pro_nets_modules(golden, DEV, fname)
 
@@ -64,12 +64,12 @@ def test_learner_train(golden, fname, model):
     PC.case_learner_train(golden, DEV, fname, model)
 
 
-@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES + PC.GROW_TAPER_CASES)
 def test_learner_grow(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model)
 
 
-@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES + PC.GROW_TAPER_CASES)
 def test_learner_grow_device_alpha(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model, device_alpha=True)
 
@@ -80,7 +80,7 @@ def test_learner_resume_from_reference_checkpoint(golden, fname, model):
     PC.case_learner_resume(golden, DEV, fname, model, GOLDEN)
 
 
-@pytest.mark.parametrize("fname,model", PC.GROW_CASES)
+@pytest.mark.parametrize("fname,model", PC.GROW_CASES + PC.GROW_TAPER_CASES)
 def test_checkpoint_roundtrip(golden, fname, model, tmp_path):
     PC.case_checkpoint_roundtrip(golden, DEV, fname, model, tmp_path)
 

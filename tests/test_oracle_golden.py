@@ -130,7 +130,7 @@ def _check_grads(names, grads, ref, rtol=2e-4):
         assert relerr(gr, r) < rtol, (k, relerr(gr, r))
 
 
-@pytest.mark.parametrize("fname", ["style_nets_res16.pt", "style_nets_res16_fade.pt"])
+@pytest.mark.parametrize("fname", ["style_nets_res16.pt", "style_nets_res16_fade.pt", "style_nets_res32_taper_fade.pt"])
 def test_style_nets(golden, fname):
     g = golden(fname)
     res = g["res"]
@@ -163,7 +163,7 @@ def test_style_nets(golden, fname):
     assert relerr(gxi, g["d_gx_img"]) < 2e-4
 
 
-@pytest.mark.parametrize("fname", ["pro_nets_res16.pt", "pro_nets_res8_fade.pt"])
+@pytest.mark.parametrize("fname", ["pro_nets_res16.pt", "pro_nets_res8_fade.pt", "pro_nets_res32_taper_fade.pt"])
 def test_pro_nets(golden, fname):
     g = golden(fname)
     res = g["res"]

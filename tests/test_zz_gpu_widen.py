@@ -139,3 +139,25 @@ def test_resnet_steps_replay_as_cuda_graphs(golden):
     assert all(math.isfinite(v) for v in l1 + l2) and l1 != l2
     for p in list(L.gen_model.parameters()) + list(L.disc_model.parameters()):
         assert torch.isfinite(p).all()
+
+
+# ---- tapering channel counts (32, 32, 16, 8): pinned on the CPU doubles, first hardware run pending
+_PENDING = pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
+
+
+@_PENDING
+@pytest.mark.parametrize("fname", PC.STYLE_NETS_TAPER)
+def test_style_nets_modules_taper(golden, fname):
+    PC.case_style_nets_modules(golden, DEV, fname)
+
+
+@_PENDING
+@pytest.mark.parametrize("fname", PC.PRO_NETS_TAPER)
+def test_pro_nets_modules_taper(golden, fname):
+    PC.case_pro_nets_modules(golden, DEV, fname)
+
+
+@_PENDING
+@pytest.mark.parametrize("fname,model", PC.GROW_TAPER_CASES)
+def test_learner_grow_taper(golden, fname, model):
+    PC.case_learner_grow(golden, DEV, fname, model, device_alpha=True)
