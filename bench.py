@@ -124,6 +124,8 @@ def run_reference(args):
     model, res, init_res, bs, alpha = CONFIGS[args.config]
     if args.config == "cfg4":
         bs = bs // 4
+    if getattr(args, "ref_dev", "cpu") == "cuda":
+        return run_reference_on_gpu(args, model, res, bs, alpha)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     total_steps = args.steps + args.warmup
@@ -150,6 +152,49 @@ def run_reference(args):
             "config": {"workload": WORKLOAD_NAME[args.config], "note": note},
             "cpu_baseline": {"value": val, "unit": "img/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_on_gpu(args, model, res, bs, alpha):
+    """`--impl reference --ref-dev cuda` (not the contract's reference arm, which is the CPU path): the UNMODIFIED reference
+    with dev=cuda, i.e. stock PyTorch eager (cuDNN / cuBLAS / ATen kernels) on the same B200 -- the number SURVEY.md 8d calls
+    'the real bar to beat'.  Full per-GPU batch, one train() call for the warm-up and one for the timed steps (the reference
+    parks its networks on the CPU at the end of every train() call), wall clock around a device synchronise."""
+    import contextlib
+    import io
+    import torch
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    from oracle.reference_loader import load_reference, make_config, reference_available, REFERENCE_ROOT
+    if not reference_available() or alpha is not None or model == "ResNet GAN" or not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "reference-on-GPU needs baseline/_ref, a CUDA device and a "
+                          "fixed-resolution StyleGAN / ProGAN config"}), flush=True)
+        return
+    ref = load_reference()
+    torch.manual_seed(0)
+    cfg = make_config(model, res=res, init_res=res, batch_size=bs, dev="cuda", metrics_dev=torch.device("cuda"))
+    quiet = lambda: contextlib.redirect_stdout(io.StringIO())
+    with quiet():
+        L = (ref.stylegan_learner.StyleGANLearner if model == "StyleGAN" else ref.progan_learner.ProGANLearner)(cfg)
+    gen = torch.Generator().manual_seed(0)
+    data = torch.rand(8 * bs, 3, res, res, generator=gen) * 2 - 1
+    ds = TensorDataset(data)
+    dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True), pin_memory=True)
+    with quiet(), contextlib.redirect_stderr(io.StringIO()):
+        L.train(dl, num_main_iters=max(args.warmup, 3))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.train(dl, num_main_iters=args.steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    val = bs * args.steps / dt
+    line = {"impl": "reference", "metric": "StyleGAN G+D train img/s", "value": val, "unit": "img/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (stock PyTorch defaults: cuDNN TF32 allowed, matmul fp32)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME[args.config],
+                       "note": f"UNMODIFIED reference (gan_lab {REFERENCE_ROOT}) Learner.train with dev=cuda: stock PyTorch eager on "
+                               f"the B200, torch {torch.__version__}"},
+            "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": bs * 3 * res * res * 4, "d2h_bytes_per_step": 8}}
     print(json.dumps(line), flush=True)
 
 
@@ -772,6 +817,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-dev", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cpu = the contract's reference arm (host cores); cuda = the unmodified "
+                         "reference through stock PyTorch on the GPU (an extra comparison, never the default)")
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
     ap.add_argument("--conv-impl", default=os.environ.get("GLB_CONV_IMPL", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
