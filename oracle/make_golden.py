@@ -872,6 +872,30 @@ def golden_resnet_resume(ref, res=32, bs=4, num_disc_iters=2):
                 opt_disc_steps=sorted({float(st["step"]) for st in L2.opt_disc.state_dict()["state"].values()}))
 
 
+def golden_state_dict_shapes(ref):
+    """Parameter / buffer names and shapes of the reference's FULL-SIZE networks (no patched constants): the contract that lets
+    its checkpoints load into the drop-in modules (SURVEY.md 8b 'Parameter names/shapes')."""
+    out = {}
+    shapes = lambda m: [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    for model in ("StyleGAN", "ProGAN"):
+        for res, init_res in ((4, 4), (128, 128), (256, 128), (1024, 1024)):
+            torch.manual_seed(0)
+            cfg = make_config(model, res=res, init_res=init_res, batch_size=8,
+                              cutoff_trunc_trick=(min(4, int(np.log2(res)) - 2) or None))
+            with _quiet():
+                L = (ref.stylegan_learner.StyleGANLearner if model == "StyleGAN" else ref.progan_learner.ProGANLearner)(cfg)
+            if init_res != res:                     # cfg3: grown once more, mid-fade-in (prev_torgb / prev_fromrgb present)
+                L.gen_model.increase_scale(); L.disc_model.increase_scale()
+            out[(model, res, init_res)] = dict(g=shapes(L.gen_model), d=shapes(L.disc_model))
+            del L
+    for res in (32, 64):
+        cfg = make_config("ResNet GAN", res=res, batch_size=8)
+        with _quiet():
+            L = ref.resnet_learner.GANLearner(cfg)
+        out[("ResNet GAN", res, res)] = dict(g=shapes(L.gen_model), d=shapes(L.disc_model))
+    return out
+
+
 def main():
     ref = load_reference()
     GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
@@ -897,6 +921,7 @@ def main():
         "style_metrics.pt": lambda: golden_metrics(ref, "StyleGAN"),
         "pro_metrics.pt": lambda: golden_metrics(ref, "ProGAN"),
         "train_variants.pt": lambda: golden_train_variants(ref),
+        "state_dict_shapes.pt": lambda: golden_state_dict_shapes(ref),
         "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),

@@ -185,3 +185,29 @@ def test_batched_d_passes(gp, bs):
 def test_resnet_resume_from_reference_checkpoint(golden):
     from conftest import GOLDEN
     PC.case_resnet_resume(golden, DEV, GOLDEN)
+
+
+def test_full_size_state_dict_names_and_shapes(golden, monkeypatch):
+    """The drop-in networks at their REAL sizes (512-channel plan, 4x4 ... 1024x1024, cfg3's mid-fade-in 256x256, both ResNets)
+    carry exactly the reference's parameter / buffer names, order and logical shapes -- what lets its checkpoints load."""
+    import math
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.progan.learner import ProGANLearner
+    from gan_lab_b200.resnetgan.learner import GANLearner
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    monkeypatch.setattr(growth, "FMAP_MAX", 512)
+    shapes = lambda m: [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    table = golden("state_dict_shapes.pt")
+    assert len(table) == 10
+    for (model, res, init_res), want in table.items():
+        if model == "ResNet GAN":
+            L = GANLearner(default_config("ResNet GAN", res=res, batch_size=8, dev=DEV))
+        else:
+            cls = StyleGANLearner if model == "StyleGAN" else ProGANLearner
+            L = cls(default_config(model, res=res, init_res=init_res, batch_size=8, dev=DEV, use_ewma_gen=False,
+                                   cutoff_trunc_trick=(min(4, int(math.log2(res)) - 2) or None)))
+            if init_res != res:
+                L.gen_model.increase_scale(); L.disc_model.increase_scale()
+        assert shapes(L.gen_model) == want["g"], (model, res)
+        assert shapes(L.disc_model) == want["d"], (model, res)
+        del L
