@@ -896,6 +896,41 @@ def golden_state_dict_shapes(ref):
     return out
 
 
+def _digest(t):
+    import hashlib
+    return hashlib.sha256(t.detach().contiguous().cpu().numpy().tobytes()).hexdigest()
+
+
+def golden_init_digests(ref):
+    """sha256 of every freshly initialised parameter / buffer of the reference's networks under a fixed seed (tapering small
+    networks, grown once after construction; both ResNets at full size): the drop-in modules draw the same numbers in the same
+    order, so `Learner(config)` under the same seed starts from bit-identical weights."""
+    out = {}
+    _patch_small(ref, SMALL_FMAP_MAX, TAPER_FMAP_BASE)
+    try:
+        for model in ("StyleGAN", "ProGAN"):
+            torch.manual_seed(5); np.random.seed(5)
+            kw = dict(res=32, init_res=16, batch_size=4, len_latent=SMALL_FMAP_MAX)
+            if model == "StyleGAN":
+                kw.update(len_dlatent=SMALL_FMAP_MAX, cutoff_trunc_trick=2)
+            with _quiet():
+                L = (ref.stylegan_learner.StyleGANLearner if model == "StyleGAN" else ref.progan_learner.ProGANLearner)(
+                    make_config(model, **kw))
+            L.gen_model.increase_scale(); L.disc_model.increase_scale()
+            out[model] = dict(seed=5, kw=kw, fmap_max=SMALL_FMAP_MAX, fmap_base=TAPER_FMAP_BASE,
+                              g={k: _digest(v) for k, v in L.gen_model.state_dict().items()},
+                              d={k: _digest(v) for k, v in L.disc_model.state_dict().items()})
+    finally:
+        _unpatch(ref)
+    for res in (32, 64):
+        torch.manual_seed(7)
+        with _quiet():
+            L = ref.resnet_learner.GANLearner(make_config("ResNet GAN", res=res, batch_size=4))
+        out[f"ResNet GAN {res}"] = dict(seed=7, res=res, g={k: _digest(v) for k, v in L.gen_model.state_dict().items()},
+                                        d={k: _digest(v) for k, v in L.disc_model.state_dict().items()})
+    return out
+
+
 def main():
     ref = load_reference()
     GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
@@ -922,6 +957,7 @@ def main():
         "pro_metrics.pt": lambda: golden_metrics(ref, "ProGAN"),
         "train_variants.pt": lambda: golden_train_variants(ref),
         "state_dict_shapes.pt": lambda: golden_state_dict_shapes(ref),
+        "init_digests.pt": lambda: golden_init_digests(ref),
         "resnet_nets_res64.pt": lambda: golden_resnet_nets(ref, 64, 4),
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),

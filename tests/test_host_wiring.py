@@ -211,3 +211,31 @@ def test_full_size_state_dict_names_and_shapes(golden, monkeypatch):
         assert shapes(L.gen_model) == want["g"], (model, res)
         assert shapes(L.disc_model) == want["d"], (model, res)
         del L
+
+
+def test_fresh_networks_under_a_seed_equal_the_references(golden, monkeypatch):
+    """Learner(config) under torch.manual_seed(s) starts from the reference's initial weights bit for bit (same initialisers drawing
+    in the same order, incl. the blocks increase_scale() adds): sha256 of every parameter / buffer vs the reference's."""
+    import hashlib
+    import numpy as np
+    import torch
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.progan.learner import ProGANLearner
+    from gan_lab_b200.resnetgan.learner import GANLearner
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    dig = lambda t: hashlib.sha256(t.detach().contiguous().cpu().numpy().tobytes()).hexdigest()
+    table = golden("init_digests.pt")
+    for name, want in table.items():
+        if name.startswith("ResNet"):
+            torch.manual_seed(want["seed"])
+            L = GANLearner(default_config("ResNet GAN", res=want["res"], batch_size=4, dev=DEV))
+        else:
+            monkeypatch.setattr(growth, "FMAP_MAX", want["fmap_max"]); monkeypatch.setattr(growth, "FMAP_BASE", want["fmap_base"])
+            torch.manual_seed(want["seed"]); np.random.seed(want["seed"])
+            L = (StyleGANLearner if name == "StyleGAN" else ProGANLearner)(default_config(name, dev=DEV, **want["kw"]))
+            L.gen_model.increase_scale(); L.disc_model.increase_scale()
+        for net, ref in ((L.gen_model, want["g"]), (L.disc_model, want["d"])):
+            sd = net.state_dict()
+            assert list(sd.keys()) == list(ref.keys()), name
+            for k, v in sd.items():
+                assert dig(v) == ref[k], (name, k)
