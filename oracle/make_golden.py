@@ -788,13 +788,13 @@ def golden_resnet_nets(ref, res=64, bs=4):
                 gp=gp.detach(), gp_tape=tape.events, d_gp_grads=d_gp_grads, lda=cfg.lda, gamma=cfg.gamma)
 
 
-def golden_resnet_train(ref, res=64, bs=4, iters=2, num_disc_iters=2):
+def golden_resnet_train(ref, res=64, bs=4, iters=2, num_disc_iters=2, **over):
     """GANLearner.train() (ResNet GAN: generator step first, then num_disc_iters discriminator steps), unmodified loop."""
     torch.manual_seed(51); np.random.seed(51)
     # lr 1e-5: with Adam(beta1=0) every step moves each parameter by ~+-lr whatever the gradient's size; at larger lr the sign
     # flips of noise-level gradients make the trajectory chaotic (the reference run twice with 1 vs 8 threads disagrees on
     # 37 % of the discriminator's parameters after 2 iterations at lr 1e-4, on 1.3 % at 1e-5)
-    L, cfg = _resnet_learner(ref, res, bs, num_disc_iters=num_disc_iters, lr_base=1e-5)
+    L, cfg = _resnet_learner(ref, res, bs, num_disc_iters=num_disc_iters, lr_base=1e-5, **over)
     gen = torch.Generator().manual_seed(53)
     perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
     perturb_norm_params(L.gen_model, gen); perturb_norm_params(L.disc_model, gen)
@@ -802,11 +802,12 @@ def golden_resnet_train(ref, res=64, bs=4, iters=2, num_disc_iters=2):
     data = torch.rand(iters * num_disc_iters * bs, 3, res, res, generator=gen) * 2 - 1
     ds = TensorDataset(data)
     dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
-    losses = []
+    losses, lrs = [], []
     orig_backward = torch.Tensor.backward
 
     def rec_backward(self, *a, **k):
         losses.append(float(self.detach()))
+        lrs.append((float(L.opt_disc.param_groups[0]["lr"]), float(L.opt_gen.param_groups[0]["lr"])))
         return orig_backward(self, *a, **k)
 
     torch.Tensor.backward = rec_backward
@@ -815,8 +816,8 @@ def golden_resnet_train(ref, res=64, bs=4, iters=2, num_disc_iters=2):
             L.train(dl, num_main_iters=iters)
     finally:
         torch.Tensor.backward = orig_backward
-    return dict(model="ResNet GAN", res=res, bs=bs, iters=iters, num_disc_iters=num_disc_iters, fmap=RESNET_FMAP,
-                len_latent=cfg.len_latent, g_sd0=g0, d_sd0=d0, data=data, tape=tape.events, losses=losses,
+    return dict(model="ResNet GAN", res=res, bs=bs, iters=iters, num_disc_iters=num_disc_iters, fmap=RESNET_FMAP, over=over,
+                len_latent=cfg.len_latent, g_sd0=g0, d_sd0=d0, data=data, tape=tape.events, losses=losses, lrs=lrs,
                 g_sd1=sd_clone(L.gen_model), d_sd1=sd_clone(L.disc_model), lr=cfg.lr_base)
 
 
@@ -963,6 +964,9 @@ def main():
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),
         "resnet_resume_res32.pt": lambda: golden_resnet_resume(ref),
+        "resnet_train_res32_variant.pt": lambda: golden_resnet_train(
+            ref, 32, 4, 2, 1, loss="nonsaturating", gradient_penalty="r1", num_gen_iters=2,     # (equalized LR crashes in the reference ResNets: wscale None)
+            lr_sched="linear decay", nonlinearity="leaky relu"),
     }
     only = sys.argv[1:]
     for name, fn in jobs.items():

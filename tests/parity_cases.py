@@ -765,23 +765,28 @@ def case_resnet_nets_modules(golden, dev, fname, dtype=torch.float32, grad_tol=5
     pen.backward(); _grads_ok(D, g["d_gp_grads"], max(grad_tol, 5e-4))
 
 
-def case_resnet_train(golden, dev):
-    """GANLearner.train() (ResNet GAN 64x64, WGAN + WGAN-GP, generator step first then 2 discriminator steps) for two
-    main iterations vs the reference's: every loss, post-Adam parameters and BatchNorm buffers."""
+def case_resnet_train(golden, dev, fname="resnet_train_res64.pt"):
+    """GANLearner.train() (ResNet GAN 64x64, WGAN + WGAN-GP, generator step first then 2 discriminator steps; or the 32x32
+    variant: non-saturating loss + R1, two generator steps, LeakyReLU, linear-decay LR) for two main iterations vs the
+    reference's: every loss, the learning rates, post-Adam parameters and BatchNorm buffers."""
     from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
-    g = _to(golden("resnet_train_res64.pt"), dev)
+    g = _to(golden(fname), dev)
     bs, iters = g["bs"], g["iters"]
-    L, cfg = _resnet_learner(g, dev, num_disc_iters=g["num_disc_iters"], lr_base=g["lr"])
+    L, cfg = _resnet_learner(g, dev, num_disc_iters=g["num_disc_iters"], lr_base=g["lr"], **g.get("over", {}))
     _load(L.gen_model, g["g_sd0"]); _load(L.disc_model, g["d_sd0"])
     ds = TensorDataset(g["data"])
     dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
     set_random_source(TapeSource(g["tape"], dev))
     losses = []
     orig_d, orig_g = L.disc_step, L.gen_step
-    L.disc_step = lambda xb: losses.append(float(orig_d(xb))) or torch.tensor(losses[-1])
-    L.gen_step = lambda: losses.append(float(orig_g())) or torch.tensor(losses[-1])
+    lrs = []
+    note_lr = lambda: lrs.append((float(L.opt_disc.param_groups[0]["lr"]), float(L.opt_gen.param_groups[0]["lr"])))
+    L.disc_step = lambda xb: note_lr() or losses.append(float(orig_d(xb))) or torch.tensor(losses[-1])
+    L.gen_step = lambda: note_lr() or losses.append(float(orig_g())) or torch.tensor(losses[-1])
     L.train(dl, num_main_iters=iters)
     assert len(losses) == len(g["losses"])
+    for mine, ref in zip(lrs, g.get("lrs", [])):
+        assert abs(mine[0] - ref[0]) < 1e-15 and abs(mine[1] - ref[1]) < 1e-15, (lrs, g["lrs"])
     # the first G and D losses are pure functions of the inputs; later ones sit behind Adam(beta1=0) sign-like updates of
     # every parameter (+-lr wherever a gradient is rounding noise) and an unbounded WGAN critic -> 1e-2 there
     for i, (a, b) in enumerate(zip(losses, g["losses"])):
@@ -802,7 +807,7 @@ def case_resnet_train(golden, dev):
         # scattered +-2*lr sign flips where a gradient is rounding noise (the reference against itself, 1 vs 8 threads: 1.3 %)
         assert bad <= 0.05 * tot, (what, bad, tot)
 
-    adam_close(L.gen_model.state_dict(), g["g_sd1"], "G", iters)
+    adam_close(L.gen_model.state_dict(), g["g_sd1"], "G", iters * cfg.num_gen_iters)
     adam_close(L.disc_model.state_dict(), g["d_sd1"], "D", iters * g["num_disc_iters"])
 
 

@@ -119,6 +119,10 @@ def test_resnet_train(golden):
     PC.case_resnet_train(golden, DEV)
 
 
+def test_resnet_train_variant(golden):
+    PC.case_resnet_train(golden, DEV, "resnet_train_res32_variant.pt")
+
+
 def test_style_generator_eval_mode(golden):
     PC.case_style_eval(golden, DEV)
 

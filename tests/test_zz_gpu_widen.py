@@ -161,3 +161,8 @@ def test_pro_nets_modules_taper(golden, fname):
 @pytest.mark.parametrize("fname,model", PC.GROW_TAPER_CASES)
 def test_learner_grow_taper(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model, device_alpha=True)
+
+
+@_PENDING
+def test_resnet_train_variant(golden):
+    PC.case_resnet_train(golden, DEV, "resnet_train_res32_variant.pt")
