@@ -62,6 +62,49 @@ class StyleGANLearner(ProGANLearner):
             lag.w_ewma = self.gen_model.w_ewma.detach().clone()
         return lag
 
+    @torch.no_grad()
+    def make_stylemixing_grid(self, zs_sourceb, zs_coarse=(), zs_middle=(), zs_fine=(), labels=None, time_average=True,
+                              save_path=None):
+        """Style-mixed grid in the layout of Figure 3 of Karras et al. 2019 (reference stylegan/learner.py:306-431): first row =
+        the source-B images, first column = the source-A images, cell (a, b) = source A with source B's styles mixed in from
+        stage 1 (coarse rows), 4 (middle rows) or 8 (fine rows) on.  The reference draws it with matplotlib; here the cells are
+        assembled into one uint8 [(1+rows)*res, (1+cols)*res, 3] array (white top-left corner), returned and optionally saved."""
+        from ..resnetgan.learner import FMAP_SAMPLES
+        groups = [(torch.as_tensor(zs), stage) for zs, stage in ((zs_coarse, 1), (zs_middle, 4), (zs_fine, 8)) if len(zs)]
+        assert groups, 'give at least one of zs_coarse / zs_middle / zs_fine'
+        net = self._lagged_for_metrics() if time_average else self.gen_model
+        if net is None:
+            raise ValueError('time_average=True needs the EWMA generator (config.use_ewma_gen)')
+        was_training = net.training
+        net.eval()
+        dev = self.config.dev
+        zb = torch.as_tensor(zs_sourceb).reshape(-1, self.config.len_latent).to(dev)
+        mean = self.ds_mean if self.ds_mean is not None else torch.full((FMAP_SAMPLES, 1, 1), .5)
+        std = self.ds_std if self.ds_std is not None else torch.full((FMAP_SAMPLES, 1, 1), .5)
+
+        def cell(x):                    # [n, 3, H, W] -> uint8 [n, H, W, 3]
+            x = (x.float().cpu() * std + mean).clamp_(0., 1.)
+            return (x * 255.).round().to(torch.uint8).permute(0, 2, 3, 1)
+
+        top = cell(net(zb))
+        res = top.shape[1]
+        rows = [torch.cat([torch.full((res, res, 3), 255, dtype=torch.uint8)] + list(top), dim=1)]
+        for zs, stage in groups:
+            za = zs.reshape(-1, self.config.len_latent).to(dev)
+            left = cell(net(za))
+            for i in range(za.shape[0]):
+                mixed = cell(net(za[i:i + 1].expand(zb.shape[0], -1).contiguous(), x_mixing=zb, style_mixing_stage=stage))
+                rows.append(torch.cat([left[i]] + list(mixed), dim=1))
+        if was_training:            # (not net.train(False): as in the reference, that would switch mixing regularisation on)
+            net.train()
+        grid = torch.cat(rows, dim=0).numpy()
+        if save_path is not None:
+            from pathlib import Path
+            from PIL import Image
+            Path(save_path).parent.mkdir(parents=True, exist_ok=True)
+            Image.fromarray(grid).save(str(save_path))
+        return grid
+
     def _sync_replicas(self):
         """Under data parallelism every rank's generator averages the w of ITS latents into `w_ewma`
         (stylegan/architectures.py:427-437).  The update is linear, so the mean over ranks of the rank-local averages IS the

@@ -243,3 +243,38 @@ def test_fresh_networks_under_a_seed_equal_the_references(golden, monkeypatch):
             assert list(sd.keys()) == list(ref.keys()), name
             for k, v in sd.items():
                 assert dig(v) == ref[k], (name, k)
+
+
+def test_stylemixing_grid(tmp_path):
+    """make_stylemixing_grid: first row = source B, first column = source A, cell (a, b) = A with B's styles from the group's
+    stage on (stylegan/learner.py:306-431 without matplotlib): checked cell by cell against the evaluation-mode generator."""
+    import numpy as np
+    import torch
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    torch.manual_seed(3)
+    cfg = default_config("StyleGAN", res=32, batch_size=4, dev=DEV, len_latent=32, len_dlatent=32, cutoff_trunc_trick=2,
+                         use_noise=False)
+    L = StyleGANLearner(cfg)
+    G = L.gen_model
+    G.train(); G(torch.randn(4, 32)); G.eval()                      # one training forward creates w_ewma
+    zb, zc, zf = torch.randn(3, 32), torch.randn(2, 32), torch.randn(1, 32)
+    grid = L.make_stylemixing_grid(zb, zs_coarse=zc, zs_fine=zf, time_average=False, save_path=tmp_path / "mix.png")
+    assert grid.shape == ((1 + 3) * 32, (1 + 3) * 32, 3) and grid.dtype == np.uint8
+    assert (grid[:32, :32] == 255).all()
+
+    def u8(x):
+        return ((x[0].float() * .5 + .5).clamp(0, 1) * 255).round().to(torch.uint8).permute(1, 2, 0).numpy()
+
+    def same(a, b):         # the grid evaluates whole rows as one batch: fp32 rounding may move a pixel by one uint8 step
+        return int(np.abs(a.astype(int) - b.astype(int)).max()) <= 1
+
+    with torch.no_grad():
+        assert same(grid[:32, 64:96], u8(G(zb[1:2])))                                   # source B, column 2
+        assert same(grid[64:96, :32], u8(G(zc[1:2])))                                   # source A (coarse row 2)
+        assert same(grid[32:64, 96:128], u8(G(zc[0:1], x_mixing=zb[2:3], style_mixing_stage=1)))
+        assert same(grid[96:128, 32:64], u8(G(zf[0:1], x_mixing=zb[0:1], style_mixing_stage=8)))
+        assert not same(grid[32:64, 96:128], u8(G(zc[0:1])))                            # mixing did something
+    from PIL import Image
+    assert Image.open(tmp_path / "mix.png").size == (128, 128)
+    assert not G.training
