@@ -576,10 +576,12 @@ def golden_resume(ref, model="StyleGAN", iters_before=6, iters_after=3, ckpt_nam
         finally:
             torch.load = orig_load
         ds2, dl2 = loader(L2)
-        losses, trace = [], []
+        losses, trace, iter_snaps = [], [], {}
         orig_backward = torch.Tensor.backward
 
         def rec_backward(self, *a, **k):
+            if len(losses) and len(losses) % 2 == 0:           # first backward of a later iteration: parameters at its start
+                iter_snaps[len(losses) // 2] = (sd_clone(L2.gen_model), sd_clone(L2.disc_model))
             losses.append(float(self.detach()))
             if len(losses) % 2 == 1:
                 trace.append(dict(res=int(L2.gen_model.curr_res), fade=bool(L2.gen_model.fade_in_phase),
@@ -597,6 +599,7 @@ def golden_resume(ref, model="StyleGAN", iters_before=6, iters_after=3, ckpt_nam
         out = dict(model=model, checkpoint=ckpt.name, init_res=4, res=8, iters_before=iters_before, iters_after=iters_after,
                    fmap_max=SMALL_FMAP_MAX, len_latent=cfg.len_latent, bs_dict=dict(cfg.bs_dict), nimg_transition=16,
                    lr_fctr_dict=dict(cfg.lr_fctr_dict), lr_base=cfg.lr_base, data_res=8, saved=saved, served=ds2.served,
+                   iter_snaps=iter_snaps,
                    tape=tape.events, losses=losses, trace=trace, g_sd1=sd_clone(L2.gen_model), d_sd1=sd_clone(L2.disc_model),
                    lagged={k: v.detach().clone() for k, v in L2.lagged_params.items()}, beta=float(L2.beta),
                    opt_gen_sd=L2.opt_gen.state_dict(), opt_disc_sd=L2.opt_disc.state_dict(),
