@@ -289,7 +289,7 @@ def case_learner_train(golden, dev, fname, model):
         assert abs(a - b) < (1e-4 if i == 0 else 1e-3) * max(1.0, abs(b)), (losses, g["losses"])
 
     def adam_close(mine, ref, what):         # scattered sign flips, never concentrated; exact per-step Adam bound
-        _adam_close(mine, ref, g["lr"], iters, what, frac=0.03)
+        _adam_close(mine, ref, g["lr"], iters, what, frac=0.05)     # (measured on the doubles: <= 1.5 %; a wiring error gives > 50 %)
 
     adam_close(L.gen_model.state_dict(), g["g_sd1"], "G")
     adam_close(L.disc_model.state_dict(), g["d_sd1"], "D")
