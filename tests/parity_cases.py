@@ -415,7 +415,6 @@ def case_learner_grow(golden, dev, fname, model, device_alpha=False):
     L.disc_step = disc_step
     L.gen_step = lambda: losses.append(float(orig_g())) or torch.tensor(losses[-1])
     L.train(dl, num_main_iters=g["iters"])
-    case_learner_grow.debug = dict(losses=losses, ref_losses=g["losses"], trace=trace)
 
     assert len(trace) == len(g["trace"])
     for mine, ref in zip(trace, g["trace"]):
