@@ -155,12 +155,30 @@ class BatchNorm2d(nn.BatchNorm2d):
     statistics, running-buffer momentum update) is one fused kernel family, optionally with the following ReLU."""
 
     def forward(self, x, act=None, slope=0.0):
-        if not self.training:
-            raise NotImplementedError('BatchNorm2d eval mode (running statistics) is not on the training path; not built')
         if self.momentum is None or not self.affine or not self.track_running_stats:
             raise NotImplementedError('only the nn.BatchNorm2d defaults used by gan-lab are built')
+        if not self.training:
+            return self._forward_eval(x, act, slope)
         return ops.batchnorm_act(x, self.weight, self.bias, self.running_mean, self.running_var, self.num_batches_tracked,
                                  self.eps, self.momentum, ops.ACT_NONE if act is None else act, slope)
+
+
+    def _forward_eval(self, x, act, slope):
+        """Evaluation mode (validation metrics, image grids -- off the training path): running statistics, i.e. a per-channel
+        affine map y = x*s + t, s = weight / sqrt(running_var + eps), t = bias - running_mean*s.  No kernel of its own: it is
+        issued as a 1x1 convolution with the diagonal weight diag(s), bias t and the fused activation on the exact fp32
+        convolution kernel (C <= 512 here, so the C/1 excess of multiplies is immaterial for an inference-only call)."""
+        from .. import _kernels as K
+        with torch.no_grad():
+            s = self.weight.detach() / torch.sqrt(self.running_var + self.eps)
+            t = self.bias.detach() - self.running_mean * s
+            w = torch.diag(s).view(s.numel(), s.numel(), 1, 1).contiguous(memory_format=torch.channels_last)
+        impl = K.get_conv_impl()
+        K.set_conv_impl('fp32')                     # not the TF32 tensor-core path: its operand truncation would show in eval outputs
+        try:
+            return ops.conv2d(x, w, t, 0, 1.0, 1.0, ops.ACT_NONE if act is None else act, slope)
+        finally:
+            K.set_conv_impl(impl)
 
 
 class LayerNorm(nn.LayerNorm):

@@ -278,3 +278,38 @@ def test_stylemixing_grid(tmp_path):
     from PIL import Image
     assert Image.open(tmp_path / "mix.png").size == (128, 128)
     assert not G.training
+
+
+def test_batchnorm_eval_mode_and_resnet_metrics(golden, tmp_path):
+    """BatchNorm2d in evaluation mode (running statistics; issued as a diagonal 1x1 convolution) against nn.BatchNorm2d, and with it
+    the ResNet learner's validation metrics and image grid (the reference's compute_metrics runs its generator in eval mode)."""
+    import torch
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    from gan_lab_b200 import ops
+    from gan_lab_b200.utils import custom_layers as CL
+    torch.manual_seed(0)
+    ref = torch.nn.BatchNorm2d(12)
+    with torch.no_grad():
+        ref.weight.uniform_(.5, 1.5); ref.bias.normal_(); ref.running_mean.normal_(); ref.running_var.uniform_(.5, 2.)
+    mine = CL.BatchNorm2d(12)
+    mine.load_state_dict(ref.state_dict())
+    ref.eval(); mine.eval()
+    x = torch.randn(3, 12, 5, 7)
+    torch.testing.assert_close(mine(x).contiguous(), ref(x), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(mine(x, act=ops.ACT_LRELU, slope=0.0).contiguous(), torch.relu(ref(x)), rtol=1e-5, atol=1e-6)
+    assert int(mine.num_batches_tracked) == 0                                   # eval mode leaves the buffers alone
+
+    g = golden("resnet_nets_res32.pt")
+    L, cfg = PC._resnet_learner(g, DEV, save_samples_dir=tmp_path, img_grid_sz=2)
+    PC._load(L.gen_model, g["g_sd"]); PC._load(L.disc_model, g["d_sd"])
+    zds = TensorDataset(torch.randn(6, cfg.len_latent)); xds = TensorDataset(torch.rand(6, 3, 32, 32) * 2 - 1)
+    z_dl = DataLoader(zds, batch_sampler=BatchSampler(SequentialSampler(zds), batch_size=4, drop_last=False))
+    x_dl = DataLoader(xds, batch_sampler=BatchSampler(SequentialSampler(xds), batch_size=4, drop_last=False))
+    lines = L.compute_metrics(["fake realness", "generator loss", "image grid"], "Generator", z_dl)
+    assert len(lines) == 2 and set(L.last_metrics) == {"fake realness", "generator loss"}
+    assert abs(L.last_metrics["generator loss"] + L.last_metrics["fake realness"]) < 1e-5      # wgan: loss = -mean(D(G(z)))
+    lines = L.compute_metrics(["real realness", "discriminator loss"], "Discriminator", z_dl, x_dl)
+    assert len(lines) == 2 and all(torch.isfinite(torch.tensor(v)) for v in L.last_metrics.values())
+    from PIL import Image
+    assert Image.open(tmp_path / "resnetgan" / "image_grid" / "original" / "0.png").size == (64, 64)
+    assert L.gen_model.training and L.disc_model.training

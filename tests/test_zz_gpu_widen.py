@@ -166,3 +166,24 @@ def test_learner_grow_taper(golden, fname, model):
 @_PENDING
 def test_resnet_train_variant(golden):
     PC.case_resnet_train(golden, DEV, "resnet_train_res32_variant.pt")
+
+
+@_PENDING
+def test_batchnorm_eval_mode_vs_torch():
+    from gan_lab_b200 import ops
+    from gan_lab_b200.utils import custom_layers as CL
+    torch.manual_seed(0)
+    ref = torch.nn.BatchNorm2d(64).to(DEV)
+    with torch.no_grad():
+        ref.weight.uniform_(.5, 1.5); ref.bias.normal_(); ref.running_mean.normal_(); ref.running_var.uniform_(.5, 2.)
+    mine = CL.BatchNorm2d(64).to(DEV)
+    mine.load_state_dict(ref.state_dict())
+    ref.eval(); mine.eval()
+    x = torch.randn(4, 64, 16, 16, device=DEV)
+    K.set_conv_impl("tf32")                 # the eval path must pick the exact kernel by itself
+    try:
+        torch.testing.assert_close(mine(x).contiguous(), ref(x), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(mine(x, act=ops.ACT_LRELU, slope=0.0).contiguous(), torch.relu(ref(x)), rtol=1e-5, atol=1e-5)
+        assert K.get_conv_impl() == "tf32"
+    finally:
+        K.set_conv_impl("fp32")
