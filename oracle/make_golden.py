@@ -936,6 +936,44 @@ def golden_init_digests(ref):
     return out
 
 
+def golden_resnet_metrics(ref, res=32, bs=4, n_valid=10):
+    """compute_metrics() of the reference's ResNet learner (resnetgan/learner.py:318-460) after one training iteration: its
+    generator runs in eval mode, i.e. BatchNorm on the running statistics that iteration left behind."""
+    torch.manual_seed(81); np.random.seed(81)
+    L, cfg = _resnet_learner(ref, res, bs, num_disc_iters=2, lr_base=1e-5)
+    gen = torch.Generator().manual_seed(83)
+    perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+    perturb_norm_params(L.gen_model, gen); perturb_norm_params(L.disc_model, gen)
+    data = torch.rand(2 * bs, 3, res, res, generator=gen) * 2 - 1
+    ds = TensorDataset(data)
+    dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+    with _quiet(), contextlib.redirect_stderr(io.StringIO()):
+        L.train(dl, num_main_iters=1)
+    g_sd, d_sd = sd_clone(L.gen_model), sd_clone(L.disc_model)
+    z_valid = torch.randn(n_valid, cfg.len_latent, generator=gen)
+    x_valid = torch.rand(n_valid, 3, res, res, generator=gen) * 2 - 1
+    zds, xds = TensorDataset(z_valid), TensorDataset(x_valid)
+    z_dl = DataLoader(zds, batch_sampler=BatchSampler(SequentialSampler(zds), batch_size=bs, drop_last=False))
+    x_dl = DataLoader(xds, batch_sampler=BatchSampler(SequentialSampler(xds), batch_size=bs, drop_last=False))
+    gen_metrics = ["fake realness", "generator loss"]
+    disc_metrics = ["fake realness", "real realness", "discriminator loss"]
+    items = []
+    orig_item = torch.Tensor.item
+    torch.Tensor.item = lambda self: (items.append(orig_item(self)), items[-1])[1]
+    try:
+        with _quiet(), contextlib.redirect_stderr(io.StringIO()):
+            vals_g = L.compute_metrics(metrics=gen_metrics, metrics_type="Generator", z_valid_dl=z_dl, valid_dl=None)
+        raw_g = [float(v) for v in items[-len(gen_metrics):]]
+        with _quiet(), contextlib.redirect_stderr(io.StringIO()):
+            vals_d = L.compute_metrics(metrics=disc_metrics, metrics_type="Discriminator", z_valid_dl=z_dl, valid_dl=x_dl)
+        raw_d = [float(v) for v in items[-len(disc_metrics):]]
+    finally:
+        torch.Tensor.item = orig_item
+    return dict(model="ResNet GAN", res=res, bs=bs, fmap=RESNET_FMAP, len_latent=cfg.len_latent, g_sd=g_sd, d_sd=d_sd,
+                z_valid=z_valid, x_valid=x_valid, gen_metrics=gen_metrics, disc_metrics=disc_metrics, vals_g=vals_g, vals_d=vals_d,
+                raw_g=raw_g, raw_d=raw_d)
+
+
 def main():
     ref = load_reference()
     GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
@@ -967,6 +1005,7 @@ def main():
         "resnet_nets_res32.pt": lambda: golden_resnet_nets(ref, 32, 4),
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),
         "resnet_resume_res32.pt": lambda: golden_resnet_resume(ref),
+        "resnet_metrics_res32.pt": lambda: golden_resnet_metrics(ref),
         "resnet_train_res32_variant.pt": lambda: golden_resnet_train(
             ref, 32, 4, 2, 1, loss="nonsaturating", gradient_penalty="r1", num_gen_iters=2,     # (equalized LR crashes in the reference ResNets: wscale None)
             lr_sched="linear decay", nonlinearity="leaky relu"),

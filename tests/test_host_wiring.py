@@ -313,3 +313,24 @@ def test_batchnorm_eval_mode_and_resnet_metrics(golden, tmp_path):
     from PIL import Image
     assert Image.open(tmp_path / "resnetgan" / "image_grid" / "original" / "0.png").size == (64, 64)
     assert L.gen_model.training and L.disc_model.training
+
+
+def test_resnet_compute_metrics_vs_reference(golden):
+    """ResNet learner compute_metrics() vs the reference's raw values: eval-mode generator = BatchNorm on the running statistics."""
+    import torch
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    g = golden("resnet_metrics_res32.pt")
+    L, cfg = PC._resnet_learner(g, DEV, num_disc_iters=2)
+    PC._load(L.gen_model, g["g_sd"]); PC._load(L.disc_model, g["d_sd"])
+    bs = g["bs"]
+    zds, xds = TensorDataset(g["z_valid"]), TensorDataset(g["x_valid"])
+    z_dl = DataLoader(zds, batch_sampler=BatchSampler(SequentialSampler(zds), batch_size=bs, drop_last=False))
+    x_dl = DataLoader(xds, batch_sampler=BatchSampler(SequentialSampler(xds), batch_size=bs, drop_last=False))
+    lines = L.compute_metrics(g["gen_metrics"], "Generator", z_dl)
+    for name, want in zip(g["gen_metrics"], g["raw_g"]):
+        assert abs(L.last_metrics[name] - want) < 2e-4 * max(1.0, abs(want)), (name, L.last_metrics[name], want)
+    assert [l.split(":")[0] for l in lines] == [l.split(":")[0] for l in g["vals_g"]]
+    lines = L.compute_metrics(g["disc_metrics"], "Discriminator", z_dl, x_dl)
+    for name, want in zip(g["disc_metrics"], g["raw_d"]):
+        assert abs(L.last_metrics[name] - want) < 2e-4 * max(1.0, abs(want)), (name, L.last_metrics[name], want)
+    assert [l.split(":")[0] for l in lines] == [l.split(":")[0] for l in g["vals_d"]]

@@ -187,3 +187,20 @@ def test_batchnorm_eval_mode_vs_torch():
         assert K.get_conv_impl() == "tf32"
     finally:
         K.set_conv_impl("fp32")
+
+
+@_PENDING
+def test_resnet_compute_metrics_vs_reference(golden):
+    from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
+    g = golden("resnet_metrics_res32.pt")
+    L, cfg = PC._resnet_learner(g, DEV, num_disc_iters=2)
+    PC._load(L.gen_model, g["g_sd"]); PC._load(L.disc_model, g["d_sd"])
+    zds, xds = TensorDataset(g["z_valid"]), TensorDataset(g["x_valid"])
+    z_dl = DataLoader(zds, batch_sampler=BatchSampler(SequentialSampler(zds), batch_size=g["bs"], drop_last=False))
+    x_dl = DataLoader(xds, batch_sampler=BatchSampler(SequentialSampler(xds), batch_size=g["bs"], drop_last=False))
+    L.compute_metrics(g["gen_metrics"], "Generator", z_dl)
+    for name, want in zip(g["gen_metrics"], g["raw_g"]):
+        assert abs(L.last_metrics[name] - want) < 2e-4 * max(1.0, abs(want)), (name, L.last_metrics[name], want)
+    L.compute_metrics(g["disc_metrics"], "Discriminator", z_dl, x_dl)
+    for name, want in zip(g["disc_metrics"], g["raw_d"]):
+        assert abs(L.last_metrics[name] - want) < 2e-4 * max(1.0, abs(want)), (name, L.last_metrics[name], want)
