@@ -134,3 +134,16 @@ def test_kernel_bit_exact_several_column_tiles(h, w, oh, ow):
     imgs = _images(3, h, w)
     got = K.u8_box_resize_normalize(torch.from_numpy(imgs).cuda(), None, (oh, ow), MEAN, STD).cpu()
     assert torch.equal(got, pil_box.input_pipeline(imgs, None, (oh, ow), MEAN, STD))
+
+
+def test_no_cpu_path():
+    """The product path has no CPU fallback: a host tensor is refused loudly (the CPU restatement lives under oracle/ only)."""
+    from gan_lab_b200._lib import GlbError
+    imgs = torch.from_numpy(_images(2, 8, 8))
+    with pytest.raises(GlbError):
+        K.u8_box_resize_normalize(imgs, None, (4, 4), MEAN, STD)
+    from gan_lab_b200.data import DeviceImageLoader
+    with pytest.raises(GlbError):
+        next(iter(DeviceImageLoader(imgs, batch_size=2, res=4, shuffle=False, device="cpu")))
+    with pytest.raises(ValueError):
+        DeviceImageLoader(imgs.float(), batch_size=2, res=4)
