@@ -26,7 +26,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._ewma = None          # (named lagged tensors aligned with extra params, beta)
         self._ewma_started = False
         self._nsteps = 0
-        self._hyper = {}           # cohort -> {'t': device float[4] = lr, 1-b1^t, 1-b2^t, t ; 'lr': value on the device}
+        self._hyper = {}           # (group index, cohort) -> {'t': device float[4] = lr, 1-b1^t, 1-b2^t, t ; 'lr': value on the device}
         self._tab = {}             # (group index, cohort) -> cached device tables of the eager path
         self._capture_slots = None
 
@@ -34,7 +34,7 @@ class FusedAdam(torch.optim.Optimizer):
         """named_params: iterable of (name, param) whose lagged copies live in `lagged[name]` (same shapes/layout)."""
         self._ewma = (list(named_params), lagged, float(beta))
 
-    def _tables(self, group):
+    def _tables(self, group, gi=0):
         """-> {cohort: (rows, sizes)}; rows = (p, g, m, v, lagged) pointers.  torch.optim.Adam keeps a step count per
         parameter (a parameter first seen later lags behind), so rows are grouped by the step they joined at."""
         by = {}
@@ -50,6 +50,7 @@ class FusedAdam(torch.optim.Optimizer):
             if not st:
                 st['step'] = 0
                 st['cohort'] = self._nsteps
+                st['group'] = gi
                 st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st['step'] += 1
@@ -75,11 +76,16 @@ class FusedAdam(torch.optim.Optimizer):
         return by
 
     # -- device-side state ---------------------------------------------------------------------------------------
-    def _hyper_for(self, cohort, dev, lr):
-        h = self._hyper.get(cohort)
+    def _hyper_for(self, gi, cohort, dev, lr):
+        """One (lr, bias corrections, step count) vector per (param group, cohort): groups may differ in lr / betas and
+        every vector is advanced exactly once per step()."""
+        h = self._hyper.get((gi, cohort))
         if h is None:
+            if _capturing():
+                raise RuntimeError("FusedAdam: a new (group, cohort) appeared inside a CUDA-graph capture; run one eager "
+                                   "step() with these parameters first")
             h = {'t': torch.zeros(4, dtype=torch.float32, device=dev), 'lr': None}
-            self._hyper[cohort] = h
+            self._hyper[(gi, cohort)] = h
         if h['lr'] != lr:
             if _capturing():
                 raise RuntimeError("FusedAdam: the learning rate changed inside a CUDA-graph capture; call push_lr() first")
@@ -90,9 +96,9 @@ class FusedAdam(torch.optim.Optimizer):
     def push_lr(self):
         """Write a changed learning rate (LambdaLR edits param_groups on the host) to the device copies; called by
         the learner before replaying a captured step."""
-        for group in self.param_groups:
-            for h in self._hyper.values():
-                if h['lr'] != group['lr']:
+        for gi, group in enumerate(self.param_groups):
+            for (hg, _cohort), h in self._hyper.items():
+                if hg == gi and h['lr'] != group['lr']:
                     h['t'][0:1].fill_(group['lr'])
                     h['lr'] = group['lr']
 
@@ -102,8 +108,9 @@ class FusedAdam(torch.optim.Optimizer):
         inside a capture would leave capture-mode events in torch's pinned-memory allocator."""
         n = sum(len(g['params']) for g in self.param_groups) + (len(self._ewma[0]) if self._ewma else 0) + 8
         dev = self.param_groups[0]['params'][0].device
-        self._capture_slots = [torch.empty(6 * n, dtype=torch.int64, device=dev)
-                               for _ in range(max(1, len(self.param_groups)) * 2)]
+        cohorts = {st.get('cohort') for st in self.state.values() if st}
+        slots = max(1, len(self.param_groups)) * (max(1, len(cohorts)) + 1)     # one table per (group, cohort) + one spare
+        self._capture_slots = [torch.empty(6 * n, dtype=torch.int64, device=dev) for _ in range(slots)]
         self._pending_uploads = []
 
     def finish_capture(self):
@@ -134,7 +141,7 @@ class FusedAdam(torch.optim.Optimizer):
     def _true_step(self, st):
         """Steps taken by the parameter behind state `st`: the device-side count of its cohort when it exists (under
         CUDA-graph replay the host-side counter does not move), else the host-side count."""
-        h = self._hyper.get(st.get('cohort'))
+        h = self._hyper.get((st.get('group', 0), st.get('cohort')))
         if h is not None:
             return int(round(float(h['t'][3])))       # device -> host read; checkpoints are not on the hot path
         return int(st.get('step', 0))
@@ -175,9 +182,11 @@ class FusedAdam(torch.optim.Optimizer):
             for key in ('exp_avg', 'exp_avg_sq'):      # the kernel walks p, g, m, v with one linear index
                 if st[key].stride() != p.stride() or st[key].device != p.device or st[key].dtype != p.dtype:
                     st[key] = torch.empty_like(p, memory_format=torch.preserve_format).copy_(st[key])
-            if st['cohort'] not in self._hyper:
-                b1, b2 = next(g['betas'] for g in self.param_groups if any(q is p for q in g['params']))
-                self._hyper[st['cohort']] = {
+            gi = next(i for i, g in enumerate(self.param_groups) if any(q is p for q in g['params']))
+            st['group'] = gi
+            if (gi, st['cohort']) not in self._hyper:
+                b1, b2 = self.param_groups[gi]['betas']
+                self._hyper[(gi, st['cohort'])] = {
                     't': torch.tensor([0.0, 1.0 - b1 ** t, 1.0 - b2 ** t, float(t)], dtype=torch.float32, device=p.device),
                     'lr': None}
         for st in self.state.values():
@@ -187,7 +196,7 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         assert closure is None
         for gi, group in enumerate(self.param_groups):
-            by = self._tables(group)
+            by = self._tables(group, gi)
             if not by:
                 continue
             dev = group['params'][0].device
@@ -197,7 +206,7 @@ class FusedAdam(torch.optim.Optimizer):
                 beta = self._ewma[2]
                 mode = 1 if self._ewma_started else 2
             for cohort, (rows, sizes) in by.items():
-                hyper = self._hyper_for(cohort, dev, group['lr'])
+                hyper = self._hyper_for(gi, cohort, dev, group['lr'])
                 K.adam_hyper_advance(hyper, b1, b2)
                 table, szs = self._upload((gi, cohort), rows, sizes, dev)
                 K.adam_ewma_multi(table, szs, len(rows), max(sizes), hyper, b1, b2, group['eps'],

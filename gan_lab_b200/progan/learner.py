@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from .. import _kernels as K
 from .._growth import GrowthState
 from ..resnetgan.learner import GANLearner, LearnerConfigCopy
 from ..utils.latent_utils import gen_rand_latent_vars
@@ -345,8 +346,11 @@ class ProGANLearner(GANLearner):
         first `warmup_iters` iterations of a phase, CUDA-graph replay afterwards.  Returns (loss_d, loss_g) tensors."""
         self._push_alpha()
         if self._graphs_allowed():
-            if self._graph is not None and self._graph['key'] != self._graph_key():
-                self._graph, self._graph_eager_iters = None, 0
+            key = self._graph_key()
+            if key != getattr(self, '_graph_last_key', None):
+                # a new phase: drop the captured graphs AND restart the eager warm-up (the grouped-linear tables and the
+                # optimisers' device-side hyper vectors of the new phase are built by its first eager iterations)
+                self._graph, self._graph_eager_iters, self._graph_last_key = None, 0, key
             if self._graph is None and self._graph_eager_iters >= self._graph_warmup:
                 self._graph = self._capture_graphs()
             if self._graph is not None:
@@ -355,6 +359,9 @@ class ProGANLearner(GANLearner):
                 self.opt_disc.push_lr(); self.opt_gen.push_lr()
                 g['gd'].replay()
                 g['gg'].replay()
+                # the replayed optimiser kernels rewrote the weights through raw pointers: no torch version bump, so the
+                # weight re-layout caches (transposed / padded / packed copies) must not survive into an eager pass
+                K.weights_updated()
                 return g['ld'], g['lg']
             self._graph_eager_iters += 1
         for p in self.disc_model.parameters():
@@ -384,6 +391,19 @@ class ProGANLearner(GANLearner):
 
     def _extra_checkpoint_entries(self):
         return {}
+
+    def _broadcast_replicas(self):
+        """Data parallelism: rank 0's parameters to every rank (collective).  New blocks / torgb / fromrgb are initialised
+        from each rank's own RNG by increase_scale(), and a checkpoint may have been loaded on one rank only; gradients are
+        averaged, so replicas that start different stay different.  Called after every growth and after load_model()."""
+        if self.dp is None or getattr(self.dp, 'world', 1) == 1:
+            return
+        self.dp.broadcast_params(self.gen_model)
+        self.dp.broadcast_params(self.disc_model)
+        if self.gen_model_lagged is not None:
+            self.dp.broadcast_params(self.gen_model_lagged)
+        from .. import _kernels as K
+        K.weights_updated()
 
     def _sync_replicas(self):
         """Bring rank-local running statistics to their global-batch value (collective: every rank calls it).  Nothing to do
@@ -480,6 +500,7 @@ class ProGANLearner(GANLearner):
         self._progressively_grow = checkpoint['progressively_grow']
         if hasattr(self, 'delta_alpha'):
             del self.delta_alpha
+        self._broadcast_replicas()
 
     def _restore_lagged_extras(self, checkpoint):
         pass
@@ -554,6 +575,7 @@ class ProGANLearner(GANLearner):
                             self.beta = self.get_smoothing_ewma_beta(half_life=EWMA_SMOOTHING_HALFLIFE) if \
                                 COMPUTE_EWMA_VIA_HALFLIFE else self.beta
                             self._sync_lagged_structure()
+                        self._broadcast_replicas()
                         self._set_optimizer()
                         if self.sched_bool:
                             self.sched_stop_step += self.scheduler_gen._step_count

@@ -14,6 +14,7 @@ import copy
 import torch
 
 from .. import ops
+from .. import _kernels as K
 from ..optim import FusedAdam
 from ..utils.custom_layers import Upsample2x, AvgPool2x, NearestPool2d, BilinearPool2d, LeakyReLU, ReLU
 from ..utils.latent_utils import RANDOM, gen_rand_latent_vars
@@ -254,6 +255,7 @@ class GANLearner(object):
                 for xb in real_batches:
                     g['x'].copy_(xb, non_blocking=True)
                     g['gd'].replay()
+                K.weights_updated()      # replays rewrite the weights through raw pointers (no torch version bump)
                 return g['ld'], g['lg']
             self._graph_eager_iters += 1
         loss_d = loss_g = None

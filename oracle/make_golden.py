@@ -936,6 +936,130 @@ def golden_init_digests(ref):
     return out
 
 
+def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
+    """ONE main iteration (D step + G step, Adam, EWMA) of the UNMODIFIED reference at cfg2's REAL widths (StyleGAN 128x128,
+    FMAP_MAX 512: 512 -> 256 -> 128 channels, batch 8, nonsaturating + R1 + drift, noise, mixing .9) -- the configuration
+    bench.py times.  49 M parameters and their gradients do not fit a committed fixture, so: the initial weights are NOT
+    stored (the drop-in learner built under the same seed starts from bit-identical weights, see init_digests.pt; their
+    sha256 digests are stored and asserted), the real batch is regenerated from its generator seed, the reference's random
+    draws are taped as usual, and every gradient / post-Adam parameter / EWMA tensor is stored as an oracle.summaries summary
+    (norm, max-norm, strided sample, random projections)."""
+    from oracle import summaries as S
+    torch.manual_seed(seed); np.random.seed(seed)
+    cfg = make_config("StyleGAN", res=res, init_res=res, batch_size=bs)
+    with _quiet():
+        L = ref.stylegan_learner.StyleGANLearner(cfg)
+    gen = torch.Generator().manual_seed(seed + 1)
+    perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+    if ulp_perturb:          # every weight moved by about one unit in the last place (see golden_cfg2_fullwidth_step)
+        pg = torch.Generator().manual_seed(seed + 2)
+        with torch.no_grad():
+            for p in list(L.gen_model.parameters()) + list(L.disc_model.parameters()):
+                p.mul_(1. + 6e-8 * (torch.empty(p.shape).random_(0, 2, generator=pg) * 2 - 1))
+    g_dig = {k: _digest(v) for k, v in L.gen_model.state_dict().items()}
+    d_dig = {k: _digest(v) for k, v in L.disc_model.state_dict().items()}
+    p0 = {"g." + k: S.summarize("p0.g." + k, v) for k, v in L.gen_model.state_dict().items()}
+    p0.update({"d." + k: S.summarize("p0.d." + k, v) for k, v in L.disc_model.state_dict().items()})
+    data = torch.rand(bs, 3, res, res, generator=gen) * 2 - 1
+    ds = TensorDataset(data)
+    dl = DataLoader(ds, batch_sampler=BatchSampler(SequentialSampler(ds), batch_size=bs, drop_last=True))
+    names = {id(p): "g." + n for n, p in L.gen_model.named_parameters()}
+    names.update({id(p): "d." + n for n, p in L.disc_model.named_parameters()})
+    # the R1 penalty on its own at the initial weights (inside the whole loss it is ~1e-8 of it at random init, SURVEY.md 8c):
+    # value and every discriminator gradient of calc_gp's double backward
+    L.disc_model.train(); L.disc_model.zero_grad()
+    gp_alone = L.calc_gp(data.clone(), data.clone())          # R1 only looks at the real batch (resnetgan/learner.py:799-802)
+    gp_alone.backward()
+    gp_grads = {"d." + n: S.summarize("gpgrad.d." + n, p.grad) for n, p in L.disc_model.named_parameters() if p.grad is not None}
+    L.disc_model.zero_grad()
+    # the generator step's forward / backward on the INITIAL weights (inside train() it runs behind the discriminator's first
+    # Adam step, whose sign-like updates amplify rounding noise): G(z) with taped draws -> D -> non-saturating loss
+    # (progan/learner.py:883-896: binary_cross_entropy_with_logits against ones) -> every generator gradient
+    L.gen_model.train(); L.gen_model.zero_grad()
+    z_alone = torch.randn(bs, cfg.len_latent, generator=gen)
+    with Tape() as tape_alone:
+        img_alone = L.gen_model(z_alone)
+    for p in L.disc_model.parameters():
+        p.requires_grad_(False)
+    logits_alone = L.disc_model(img_alone).view(-1)
+    g_alone_loss = torch.nn.functional.binary_cross_entropy_with_logits(logits_alone, torch.ones_like(logits_alone))
+    g_alone_loss.backward()
+    for p in L.disc_model.parameters():
+        p.requires_grad_(True)
+    g_alone = dict(z=z_alone, tape=tape_alone.events, loss=float(g_alone_loss.detach()), img=S.summarize("galone.img", img_alone),
+                   logits=logits_alone.detach().clone(),
+                   grads={"g." + n: S.summarize("galone.g." + n, p.grad) for n, p in L.gen_model.named_parameters()
+                          if p.grad is not None})
+    L.gen_model.zero_grad(); L.disc_model.zero_grad()
+    L.gen_model.w_ewma = None            # the stand-alone forward created it; train() must start like a fresh learner
+    losses, grads, gp_vals = [], {}, []
+    orig_backward, orig_step, orig_gp = torch.Tensor.backward, torch.optim.Adam.step, L.calc_gp
+
+    def rec_backward(self, *a, **k):
+        losses.append(float(self.detach()))
+        return orig_backward(self, *a, **k)
+
+    def rec_step(self, *a, **k):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    grads[names[id(p)]] = S.summarize("grad." + names[id(p)], p.grad)
+        return orig_step(self, *a, **k)
+
+    def rec_gp(*a, **k):
+        v = orig_gp(*a, **k)
+        gp_vals.append(float(v.detach()))
+        return v
+
+    torch.Tensor.backward, torch.optim.Adam.step, L.calc_gp = rec_backward, rec_step, rec_gp
+    try:
+        with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+            L.train(dl, num_main_iters=1)
+    finally:
+        torch.Tensor.backward, torch.optim.Adam.step = orig_backward, orig_step
+    p1 = {"g." + k: S.summarize("p1.g." + k, v) for k, v in L.gen_model.state_dict().items()}
+    p1.update({"d." + k: S.summarize("p1.d." + k, v) for k, v in L.disc_model.state_dict().items()})
+    lagged = {k: S.summarize("lag." + k, v) for k, v in L.lagged_params.items()}
+    return dict(model="StyleGAN", res=res, bs=bs, seed=seed, lr=cfg.lr_base * cfg.lr_fctr_dict[res], lda=cfg.lda,
+                g_digests=g_dig, d_digests=d_dig, data_digest=_digest(data), tape=tape.events, losses=losses, gp=gp_vals,
+                p0=p0, grads=grads, p1=p1, lagged=lagged, beta=float(L.beta), gp_alone=float(gp_alone.detach()), gp_grads=gp_grads, g_alone=g_alone,
+                w_ewma=L.gen_model.w_ewma.detach().clone())
+
+
+
+def golden_cfg2_fullwidth_step(ref, res=128, bs=8, seed=1234):
+    """The fixture proper + the reference's OWN noise floor at this size: the same iteration re-run with every weight moved by
+    about one fp32 unit in the last place (relative 6e-8, random sign); `self_noise` holds, per class, the worst relative L2
+    difference (over tensors) between the two reference runs.  Cancellation-dominated gradients (biases / noise weights in
+    front of InstanceNorm, everything behind leaky-ReLU masks that sit within rounding of zero at random init) amplify a 1-ulp
+    perturbation by 3-4 orders of magnitude; the GPU tests' bounds are stated as multiples of this floor."""
+    from oracle import summaries as S
+    a = _cfg2_fullwidth_run(ref, res, bs, seed, False)
+    b = _cfg2_fullwidth_run(ref, res, bs, seed, True)
+
+    def worst(x, y):
+        out = dict(l2=0.0, smax=0.0)
+        for k, sx in x.items():
+            sy = y[k]
+            scale = max(sx["norm"], 1e-30)
+            out["l2"] = max(out["l2"], float((sx["proj"] - sy["proj"]).abs().max()) / scale)
+            out["smax"] = max(out["smax"], float((sx["sample"] - sy["sample"]).abs().max()) / max(sx["absmax"], 1e-30))
+        return out
+
+    gd = lambda d, tag: {k: v for k, v in d.items() if k.startswith(tag)}
+    a["self_noise"] = dict(
+        perturbation="weights * (1 +- 6e-8)",
+        loss_d=abs(a["losses"][0] - b["losses"][0]) / max(1.0, abs(a["losses"][0])),
+        loss_g=abs(a["losses"][1] - b["losses"][1]) / max(1.0, abs(a["losses"][1])),
+        gp_value=abs(a["gp_alone"] - b["gp_alone"]) / abs(a["gp_alone"]),
+        gp_grads=worst(a["gp_grads"], b["gp_grads"]),
+        g_alone_loss=abs(a["g_alone"]["loss"] - b["g_alone"]["loss"]) / max(1.0, abs(a["g_alone"]["loss"])),
+        g_alone_img=worst({"img": a["g_alone"]["img"]}, {"img": b["g_alone"]["img"]}),
+        g_alone_grads=worst(a["g_alone"]["grads"], b["g_alone"]["grads"]),
+        d_grads=worst(gd(a["grads"], "d."), gd(b["grads"], "d.")),
+        g_grads=worst(gd(a["grads"], "g."), gd(b["grads"], "g.")))
+    return a
+
 def golden_resnet_metrics(ref, res=32, bs=4, n_valid=10):
     """compute_metrics() of the reference's ResNet learner (resnetgan/learner.py:318-460) after one training iteration: its
     generator runs in eval mode, i.e. BatchNorm on the running statistics that iteration left behind."""
@@ -1006,6 +1130,7 @@ def main():
         "resnet_train_res64.pt": lambda: golden_resnet_train(ref, 64, 4, 2, 2),
         "resnet_resume_res32.pt": lambda: golden_resnet_resume(ref),
         "resnet_metrics_res32.pt": lambda: golden_resnet_metrics(ref),
+        "style_cfg2_fullwidth_step.pt": lambda: golden_cfg2_fullwidth_step(ref),
         "resnet_train_res32_variant.pt": lambda: golden_resnet_train(
             ref, 32, 4, 2, 1, loss="nonsaturating", gradient_penalty="r1", num_gen_iters=2,     # (equalized LR crashes in the reference ResNets: wscale None)
             lr_sched="linear decay", nonlinearity="leaky relu"),

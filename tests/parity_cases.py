@@ -6,6 +6,7 @@ import math
 import torch
 
 import gan_lab_b200._kernels as K
+from gan_lab_b200 import ops
 from gan_lab_b200.config import default_config
 from gan_lab_b200.utils import custom_layers as CL
 from gan_lab_b200.utils.latent_utils import TapeSource, set_random_source
@@ -339,11 +340,16 @@ def _adam_close(mine, ref, lr, steps, what, frac=0.03):
     noise, e.g. a bias in front of an InstanceNorm), and two trajectories can move apart by twice that."""
     bound = 2.001 * lr * sum(math.sqrt((1. - .99 ** t) / .01) for t in range(1, steps + 1)) + 1e-6
     bad = tot = 0
+    per_key = {}
     for k, v in ref.items():
         d = (mine[k].detach() - v).abs()
         assert float(d.max()) <= bound, (what, k, float(d.max()), bound)
-        bad += int((d > 2e-5 + 1e-4 * v.abs()).sum()); tot += v.numel()
-    assert bad <= frac * tot, (what, bad, tot)
+        nb = int((d > 2e-5 + 1e-4 * v.abs()).sum())
+        if nb:
+            per_key[k] = (nb, v.numel(), float(d.max()))
+        bad += nb; tot += v.numel()
+    worst = sorted(per_key.items(), key=lambda kv: -kv[1][0])[:8]
+    assert bad <= frac * tot, (what, bad, tot, worst)
 
 
 def case_learner_grow(golden, dev, fname, model, device_alpha=False):
@@ -879,3 +885,183 @@ def case_style_eval(golden, dev):
         G.trunc_cutoff_stage = None
         assert relerr(G(g["z"], noise=g["noise"]), g["img_notrunc"]) < 1e-4
     assert float((g["img_trunc"] - g["img_notrunc"]).abs().max()) > 1e-3        # the truncation trick did something
+
+
+# ------------------------------------------------------------------------------------------------ cfg2 at its real widths
+def _perturb_zero_params(module, gen):
+    """Same rule as oracle.make_golden.perturb_zero_params (zero-initialised parameters get 0.3 * N(0,1) from `gen`)."""
+    with torch.no_grad():
+        for _name, p in module.named_parameters():
+            if float(p.abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+
+
+def cfg2_fullwidth_learner(g, dev):
+    """The drop-in StyleGANLearner at cfg2's real size rebuilt from the fixture's seeds: bit-identical initial weights and real
+    batch (sha256 digests asserted), without the fixture having to carry 49 M parameters."""
+    import hashlib
+    import numpy as np
+    from gan_lab_b200.stylegan.learner import StyleGANLearner
+    dig = lambda t: hashlib.sha256(t.detach().contiguous().cpu().numpy().tobytes()).hexdigest()
+    torch.manual_seed(g["seed"]); np.random.seed(g["seed"])
+    L = StyleGANLearner(default_config("StyleGAN", res=g["res"], init_res=g["res"], batch_size=g["bs"], dev=dev))
+    gen = torch.Generator().manual_seed(g["seed"] + 1)
+    _perturb_zero_params(L.gen_model, gen); _perturb_zero_params(L.disc_model, gen)
+    for net, want in ((L.gen_model, g["g_digests"]), (L.disc_model, g["d_digests"])):
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(want.keys())
+        for k, v in sd.items():
+            assert dig(v) == want[k], k
+    data = torch.rand(g["bs"], 3, g["res"], g["res"], generator=gen) * 2 - 1
+    assert dig(data) == g["data_digest"]
+    return L, data
+
+
+def case_cfg2_fullwidth_step(golden, dev, impl, graph):
+    """ONE main iteration of cfg2 (StyleGAN 128x128, 512/256/128 channels, batch 8, nonsaturating + R1 + drift, noise, mixing)
+    -- the configuration bench.py times -- against the UNMODIFIED reference's (tests/golden/style_cfg2_fullwidth_step.pt):
+    D loss, G loss, the R1 penalty on its own (value + every D gradient of its double backward, through the shared-forward
+    path the step uses), every parameter gradient of the D step and of the G step, the post-Adam parameters, the EWMA generator
+    and w_ewma.  impl: 'fp32' | 'tf32' (the benchmarked conv path); graph: run the step as a captured-and-replayed CUDA graph
+    pair, as bench.py does.  Returns the worst error per class (the callers assert their bounds on it)."""
+    from oracle import summaries as S
+    g = golden("style_cfg2_fullwidth_step.pt")
+    L, data = cfg2_fullwidth_learner(g, dev)
+    G, D = L.gen_model, L.disc_model
+    x = data.to(dev)
+    tape = [(k, v.to(dev) if torch.is_tensor(v) else v) for k, v in g["tape"]]
+    K.set_conv_impl(impl)
+    out = {}
+    try:
+        G.train(); D.train()
+        L.beta = L.get_smoothing_ewma_beta(10.)
+        assert abs(L.beta - g["beta"]) < 1e-12
+        L._init_lagged(); L._attach_ewma()
+        if L.sched_bool:                 # train() attaches the resolution-dependent LR schedule (lr = lr_base * 1.5 at 128x128)
+            L.sched_stop_step = 0
+            L._set_scheduler()
+        assert abs(L.opt_disc.param_groups[0]["lr"] - g["lr"]) < 1e-12
+        # ---- the R1 penalty on its own, through the path the step uses (penalty rides on the loss's own D(real) forward)
+        xr = x.detach().clone().requires_grad_(True)
+        pen = L.gp_from_forward(D(xr), xr)
+        D.zero_grad()
+        pen.backward()
+        out["gp_value"] = abs(float(pen.detach()) - g["gp_alone"]) / abs(g["gp_alone"])
+        cmp = {k: S.compare("gpgrad." + k, dict(D.named_parameters())[k[2:]].grad, v) for k, v in g["gp_grads"].items()}
+        out["gp_grads_l2"] = max(c["l2"] for c in cmp.values())
+        out["gp_grads_smax"] = max(c["smax"] for c in cmp.values())
+        out["gp_grads_worst"] = max(cmp.items(), key=lambda kv: kv[1]["l2"])[0]
+        out["gp_per_tensor"] = cmp
+        D.zero_grad(set_to_none=True)
+        # ---- the generator step's forward / backward on the initial weights (no Adam step in front of it)
+        ga = g["g_alone"]
+        set_random_source(TapeSource([(k, v.to(dev) if torch.is_tensor(v) else v) for k, v in ga["tape"]], dev))
+        for p in D.parameters():
+            p.requires_grad_(False)
+        img = G(ga["z"].to(dev))
+        logits = D(img)
+        loss_alone = ops.g_logit_loss(logits, L.loss)
+        G.zero_grad()
+        loss_alone.backward()
+        set_random_source(None)
+        for p in D.parameters():
+            p.requires_grad_(True)
+        ci = S.compare("galone.img", img, ga["img"])
+        out["g_alone_img_l2"], out["g_alone_img_smax"] = ci["l2"], ci["smax"]
+        out["g_alone_logits"] = float((logits.detach().view(-1).cpu() - ga["logits"]).abs().max() / ga["logits"].abs().max())
+        out["g_alone_loss"] = abs(float(loss_alone.detach()) - ga["loss"]) / max(1.0, abs(ga["loss"]))
+        cmp = {k: S.compare("galone." + k, dict(G.named_parameters())[k[2:]].grad, v) for k, v in ga["grads"].items()}
+        out["g_alone_grads_l2"] = max(c["l2"] for c in cmp.values())
+        out["g_alone_grads_smax"] = max(c["smax"] for c in cmp.values())
+        out["g_alone_grads_worst"] = max(cmp.items(), key=lambda kv: kv[1]["l2"])[0]
+        out["g_alone_per_tensor"] = cmp
+        G.zero_grad(set_to_none=True)
+        G.w_ewma = None
+        del img, logits, loss_alone
+        p0 = {id(p): p.detach().clone() for p in list(G.parameters()) + list(D.parameters())}
+
+        if graph:
+            # one eager iteration builds the optimisers' device-side state and the grouped-linear tables (a capture cannot);
+            # then every piece of training state is put back to its initial value and the step is captured WITH the taped
+            # draws (host-side mixing decision, taped latents / noise as device tensors) and replayed
+            L.enable_cuda_graphs(True, warmup_iters=1)
+            G.device_mixing = False
+            L.main_iteration(torch.rand_like(x) * 2 - 1)
+            assert L._graph is None
+            with torch.no_grad():
+                for p in list(G.parameters()) + list(D.parameters()):
+                    p.copy_(p0[id(p)])
+                for opt in (L.opt_disc, L.opt_gen):
+                    for st in opt.state.values():
+                        st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+                    for h in opt._hyper.values():
+                        h["t"][1:].zero_()
+                for n, p in L.gen_model_lagged.named_parameters():
+                    p.copy_(dict(G.named_parameters())[n])
+            G.w_ewma = None
+            K.weights_updated()
+            set_random_source(TapeSource(tape, dev))
+            ld, lg = L.main_iteration(x)                   # capture + first replay
+            assert L._graph is not None
+            torch.cuda.synchronize()
+            lag_mode_first = False                         # the captured step's EWMA update is the steady-state one
+        else:
+            set_random_source(TapeSource(tape, dev))
+            for p in D.parameters():
+                p.requires_grad_(True)
+            ld = L.disc_step(x)
+            d_grads = {n: p.grad.detach().clone() for n, p in D.named_parameters() if p.grad is not None}
+            for p in D.parameters():
+                p.requires_grad_(False)
+            lg = L.gen_step()
+            lag_mode_first = True
+        set_random_source(None)
+        if graph:
+            d_grads = {n: p.grad.detach() for n, p in D.named_parameters() if p.grad is not None}
+        g_grads = {n: p.grad.detach() for n, p in G.named_parameters() if p.grad is not None}
+        out["loss_d"] = abs(float(ld) - g["losses"][0]) / max(1.0, abs(g["losses"][0]))
+        out["loss_g"] = abs(float(lg) - g["losses"][1]) / max(1.0, abs(g["losses"][1]))
+
+        def worst(cmp):
+            k = max(cmp, key=lambda n: cmp[n]["l2"])
+            return max(c["l2"] for c in cmp.values()), max(c["smax"] for c in cmp.values()), max(c["norm"] for c in cmp.values()), k
+
+        want_d = {k[2:]: v for k, v in g["grads"].items() if k.startswith("d.")}
+        want_g = {k[2:]: v for k, v in g["grads"].items() if k.startswith("g.")}
+        assert set(d_grads) == set(want_d) and set(g_grads) == set(want_g), (set(d_grads) ^ set(want_d), set(g_grads) ^ set(want_g))
+        per_d = {n: S.compare("grad.d." + n, t, want_d[n]) for n, t in d_grads.items()}
+        per_g = {n: S.compare("grad.g." + n, t, want_g[n]) for n, t in g_grads.items()}
+        out["d_grads_l2"], out["d_grads_smax"], out["d_grads_norm"], out["d_grads_worst"] = worst(per_d)
+        out["g_grads_l2"], out["g_grads_smax"], out["g_grads_norm"], out["g_grads_worst"] = worst(per_g)
+        out["per_tensor"] = {"d." + n: c for n, c in per_d.items()}
+        out["per_tensor"].update({"g." + n: c for n, c in per_g.items()})
+
+        # ---- post-Adam parameters: step 1 of Adam(beta1 = 0) moves every element by lr * g / (|g| + eps), i.e. by +-lr unless the
+        # gradient is tiny: hard bound 2*lr per element, and only a small fraction of the sampled elements may differ at all
+        lr = g["lr"]
+        bad = tot = 0
+        hard = 0.0
+        for net, tag in ((G, "g."), (D, "d.")):
+            for n, p in net.named_parameters():
+                ref = g["p1"][tag + n]
+                f = p.detach().reshape(-1)
+                mine = f[S.sample_index(f.numel()).to(f.device)].cpu()
+                d = (mine - ref["sample"]).abs()
+                hard = max(hard, float(d.max()))
+                bad += int((d > 0.02 * lr).sum()); tot += d.numel()
+        out["p1_max_abs_diff_over_lr"] = hard / lr
+        out["p1_flip_fraction"] = bad / tot
+        # ---- EWMA generator: first-step semantics in the eager run (lagged = post-Adam parameter, progan/learner.py:472 aliasing);
+        # the replayed graph holds the steady-state update lagged = p1*(1-beta) + lagged0*beta with lagged0 = p0
+        lag_err = 0.0
+        for n, p in G.named_parameters():
+            lag = dict(L.gen_model_lagged.named_parameters())[n].detach()
+            prev = p.detach() if lag_mode_first else p0[id(p)]
+            want = p.detach() * (1. - L.beta) + prev * L.beta
+            lag_err = max(lag_err, float(((lag - want).abs() / want.abs().clamp_min(1.0)).max()))
+        out["lagged_rel_err"] = lag_err
+        out["w_ewma"] = float((G.w_ewma.cpu() - g["w_ewma"]).abs().max() / g["w_ewma"].abs().max())
+        return out
+    finally:
+        K.set_conv_impl("fp32")
+        set_random_source(None)

@@ -1,0 +1,67 @@
+"""Whole-step parity of the path bench.py times: cfg2 (StyleGAN 128x128, batch 8) at its REAL widths (512 / 256 / 128
+channels), tensor-core (TF32) convolutions, run eagerly and as the captured-and-replayed CUDA graph pair, against one main
+iteration of the UNMODIFIED reference (tests/golden/style_cfg2_fullwidth_step.pt, made by oracle/make_golden.py from
+progan/learner.py:734-916 + stylegan/architectures.py:411-528 on CPU fp32).
+
+Bounds (per tensor: estimated relative L2 error of the WHOLE tensor from random projections, and max-norm error on a strided
+sample, see oracle/summaries.py):
+  fp32 path (exact FFMA convolutions)         losses 1e-4, gradients 1e-3 (the reference's own fp32 reassociation noise is 6e-5)
+  TF32 path (tcgen05 kind::tf32, benchmarked)  losses 2e-3, gradients 2e-2 (L2) -- operands rounded to 10 mantissa bits per conv,
+                                               ~20 convolutions deep, R1 double backward twice as deep
+"""
+import json
+import os
+
+import pytest
+import torch
+
+import parity_cases as PC
+
+DEV = "cuda"
+
+
+def _dump(tag, out):
+    d = os.environ.get("GLB_DUMP_PARITY")
+    if d:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, f"cfg2_fullwidth_{tag}.json"), "w") as f:
+            json.dump(out, f, indent=1)
+
+
+# Bounds = multiples of the reference's OWN noise floor at this size (fixture key `self_noise`: the unmodified reference re-run
+# with every weight moved by one fp32 ulp; worst tensor per class), never below a base value.  (loss base, gradient multiple)
+BOUNDS = {"fp32": (1e-4, 4.0), "tf32": (3e-3, 12.0)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl,graph", [("fp32", False), ("tf32", False), ("tf32", True)])
+def test_cfg2_fullwidth_step_vs_reference(golden, impl, graph):
+    out = PC.case_cfg2_fullwidth_step(golden, DEV, impl, graph)
+    _dump(f"{impl}_{'graph' if graph else 'eager'}", out)
+    floor = golden("style_cfg2_fullwidth_step.pt")["self_noise"]
+    b_loss, mult = BOUNDS[impl]
+    msg = {k: v for k, v in out.items() if not k.endswith("per_tensor")}
+    assert out["loss_d"] < b_loss and out["g_alone_loss"] < b_loss, msg
+    assert out["loss_g"] < max(b_loss, mult * floor["loss_g"]), msg          # behind the discriminator's first Adam step
+    assert out["gp_value"] < max(10 * b_loss, mult * floor["gp_value"]), msg
+    assert out["g_alone_img_l2"] < 10 * b_loss and out["g_alone_logits"] < 10 * b_loss, msg
+    for key, fl in (("gp_grads", floor["gp_grads"]), ("g_alone_grads", floor["g_alone_grads"]), ("d_grads", floor["d_grads"]),
+                    ("g_grads", floor["g_grads"])):
+        assert out[key + "_l2"] < mult * fl["l2"], (key, out[key + "_l2"], fl, msg)
+        assert out[key + "_smax"] < mult * fl["smax"], (key, out[key + "_smax"], fl, msg)
+    assert out["p1_max_abs_diff_over_lr"] <= 2.001, msg
+    assert out["p1_flip_fraction"] < (0.03 if impl == "fp32" else 0.10), msg
+    assert out["lagged_rel_err"] < 5e-7, msg
+    assert out["w_ewma"] < 10 * b_loss, msg
+
+
+def test_cfg2_fullwidth_fixture_is_reproducible_from_its_seeds(golden):
+    """No GPU needed: the drop-in learner built on the CPU under the fixture's seed has the reference's initial weights bit for
+    bit at full width (sha256 per tensor) and regenerates the same real batch; the summaries carry every parameter."""
+    g = golden("style_cfg2_fullwidth_step.pt")
+    L, data = PC.cfg2_fullwidth_learner(g, "cpu")
+    names = {"g." + n for n, _ in L.gen_model.named_parameters()} | {"d." + n for n, _ in L.disc_model.named_parameters()}
+    assert set(g["p1"].keys()) == names
+    trained = {n for n in names if not n.startswith(("g.prev_torgb", "d.prev_fromrgb"))}
+    assert set(g["grads"].keys()) == trained
+    assert len(g["losses"]) == 2 and g["gp_alone"] > 0

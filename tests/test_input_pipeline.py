@@ -128,7 +128,6 @@ def test_kernel_unaligned_views_and_pinned_loader():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (outputs wider than one 128-column tile; index logic checked by emulation)")
 @pytest.mark.parametrize("h,w,oh,ow", [(40, 300, 20, 150), (24, 520, 24, 260), (16, 257, 16, 257), (512, 512, 256, 256)])
 def test_kernel_bit_exact_several_column_tiles(h, w, oh, ow):
     imgs = _images(3, h, w)

@@ -1,6 +1,5 @@
 """GPU parity of the rows SURVEY.md 8f adds around the train step (progressive-growing schedule, checkpoints, input
-pipeline).  Kept in a file that sorts last: these cases were written after the round's GPU budget was spent, so a surprise
-here must not hide the results of tests/test_gpu_parity.py under `pytest -x`."""
+pipeline).  Kept in a file that sorts last so that the kernel / nets / train parity of tests/test_gpu_parity.py reports first under `pytest -x`."""
 import pytest
 import torch
 
@@ -88,29 +87,23 @@ def test_fade_in_phase_replays_as_cuda_graph_with_device_alpha():
         assert float(alive.conv2d.weight.grad.abs().max()) > 0.0, alpha
 
 
-# Written after the round's GPU budget was spent: the host wiring of these switches is pinned on the CPU doubles
-# (tests/test_host_wiring.py::test_train_variant) and every kernel involved has its own GPU parity test, but this combination
-# has not been run on hardware yet -- non-strict xfail, so that the first hardware run records the outcome without turning an
-# otherwise verified suite red.  To be made plain tests once seen green.
-@pytest.mark.xfail(strict=False, reason="first hardware run of the configuration variants pending")
+# Configuration switches the headline fixtures leave at their defaults (host wiring also pinned on the CPU doubles,
+# tests/test_host_wiring.py::test_train_variant).
 @pytest.mark.parametrize("name", PC.TRAIN_VARIANTS)
 def test_train_variant(golden, name, monkeypatch):
     PC.case_train_variant(golden, DEV, name, monkeypatch)
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
 @pytest.mark.parametrize("gp,bs", [("r1", 4), ("r2", 8), ("r1", 2)])
 def test_batched_d_passes(gp, bs):
     PC.case_batched_d_passes(DEV, gp, bs)
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
 def test_resnet_resume_from_reference_checkpoint(golden):
     from conftest import GOLDEN
     PC.case_resnet_resume(golden, DEV, GOLDEN)
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
 def test_resnet_steps_replay_as_cuda_graphs(golden):
     """ResNet GAN: one generator step and one discriminator step captured and replayed (opt-in): Adam's device-side step count,
     BatchNorm's num_batches_tracked and the parameters advance per replay, fresh latents per replay, everything finite."""
@@ -141,34 +134,28 @@ def test_resnet_steps_replay_as_cuda_graphs(golden):
         assert torch.isfinite(p).all()
 
 
-# ---- tapering channel counts (32, 32, 16, 8): pinned on the CPU doubles, first hardware run pending
-_PENDING = pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
+# ---- tapering channel counts (32, 32, 16, 8)
 
 
-@_PENDING
 @pytest.mark.parametrize("fname", PC.STYLE_NETS_TAPER)
 def test_style_nets_modules_taper(golden, fname):
     PC.case_style_nets_modules(golden, DEV, fname)
 
 
-@_PENDING
 @pytest.mark.parametrize("fname", PC.PRO_NETS_TAPER)
 def test_pro_nets_modules_taper(golden, fname):
     PC.case_pro_nets_modules(golden, DEV, fname)
 
 
-@_PENDING
 @pytest.mark.parametrize("fname,model", PC.GROW_TAPER_CASES)
 def test_learner_grow_taper(golden, fname, model):
     PC.case_learner_grow(golden, DEV, fname, model, device_alpha=True)
 
 
-@_PENDING
 def test_resnet_train_variant(golden):
     PC.case_resnet_train(golden, DEV, "resnet_train_res32_variant.pt")
 
 
-@_PENDING
 def test_batchnorm_eval_mode_vs_torch():
     from gan_lab_b200 import ops
     from gan_lab_b200.utils import custom_layers as CL
@@ -189,7 +176,6 @@ def test_batchnorm_eval_mode_vs_torch():
         K.set_conv_impl("fp32")
 
 
-@_PENDING
 def test_resnet_compute_metrics_vs_reference(golden):
     from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
     g = golden("resnet_metrics_res32.pt")
