@@ -39,6 +39,14 @@ struct FpropParams {
   float slope;
 };
 
+// tcgen05 kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits (cuDNN's TF32 kernels round to nearest).  Truncation is
+// biased: for a log-uniform mantissa the expected relative error of an operand is 0.5 * 2^-10 * E[1/m] = 3.52e-4, i.e. every
+// product comes out 7.04e-4 too small on average -- a coherent scale error that accumulates over the ~26 convolutions a
+// discriminator gradient passes through (measured at cfg2's size: R1 penalty value -2.3 % against the reference's CPU run, its
+// own cuDNN-TF32 run -0.08 %).  The kernels fold the reciprocal of the expected shrinkage into the epilogue scale `alpha`
+// (mean-compensated truncation): the bias goes, the zero-mean part (same variance as round-to-nearest) stays.
+constexpr float kTf32TruncComp = 1.0f / (1.0f - 7.04e-4f);
+
 constexpr int kBM = 128;           // MMA M (output pixels per tile)
 constexpr int kChunk = 32;         // channels per K chunk = 128 bytes = one swizzle row
 constexpr int kABytes = kBM * 128; // 16 KB
@@ -61,6 +69,7 @@ struct FpropCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+constexpr int kH1Default = 0;     // conv_fprop_tc2_h1_kernel: off until verified on hardware (GLB_FPROP_H1=1 / 2)
 constexpr int kHaloDefault = 12;  // tap-reuse kernels used by default: bits 0/1 = single CTA at BN 128/256, bits 2/3 = CTA pair at BN 128/256
 constexpr int kFpropThreads = 384;  // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
 
@@ -436,11 +445,19 @@ conv_fprop_tc_m2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 // descriptor stays canonical (SBO = 1024 B, 1024-byte aligned starts).  A traffic per chunk and tile: S * 18 KB = 54 KB
 // instead of 144 KB.  Two rings: A (one stage = the S boxes of a chunk, released after its R*S taps) and B (one stage
 // = one tap of one chunk).
-template <int BN, int R_, int S_>
+// ONEBOX: ONE box per chunk, (32 ch, 8 + S - 1 wide, 16 + R - 1 tall), covering every tap: the column shift s becomes a start-address
+// offset of s pixels (s * 128 B) as well, with SBO = (8 + S - 1) * 128 B between the 8-pixel row groups of the MMA tile.  The
+// start is then no longer 1024-byte aligned; the 128B swizzle is a function of the shared-memory ADDRESS bits (chunk ^= addr[7:9],
+// what TMA applies on the way in), so a 128-byte-aligned start inside the pattern addresses the same bytes.  A traffic per chunk
+// and tile: 22.5 KB instead of 54 KB (the loop is bound by L2 -> SM bytes: ncu lts2xbar at 82 % of its peak).
+template <int BN, int R_, int S_, bool ONEBOX = false>
 struct FpropHaloCfg {
   static constexpr int kBoxRows = 16 + R_ - 1;
-  static constexpr int kBoxBytes = kBoxRows * 1024;
-  static constexpr int kAStageBytes = S_ * kBoxBytes;
+  static constexpr int kBoxCols = ONEBOX ? 8 + S_ - 1 : 8;
+  static constexpr int kBoxBytes = ONEBOX ? ((kBoxRows * kBoxCols * 128 + 1023) / 1024) * 1024 : kBoxRows * 1024;
+  static constexpr int kAStageBytes = (ONEBOX ? 1 : S_) * kBoxBytes;
+  static constexpr int kTxBytes = ONEBOX ? kBoxRows * kBoxCols * 128 : kAStageBytes;   // bytes TMA actually writes per A stage
+  static constexpr int kRowPitch = kBoxCols * 128;                                     // SBO: one image row of the box
   // taps per B stage: the MMA-issuing thread pays a fixed wait / fence / commit cost per stage, so the 64-cycle MMAs of a
   // 128-wide N tile get 8 per stage (cf. FpropCfg's KC)
   static constexpr int kTPS = 1;                 // must divide R*S (stages never straddle a chunk; everything unrolls)
@@ -454,10 +471,10 @@ struct FpropHaloCfg {
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 256;
 };
 
-template <int BN, int R_, int S_>
+template <int BN, int R_, int S_, bool ONEBOX>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
-  using Cfg = FpropHaloCfg<BN, R_, S_>;
+  using Cfg = FpropHaloCfg<BN, R_, S_, ONEBOX>;
   static_assert(Cfg::kBStages >= 3 || Cfg::kTPS > 1, "B ring too shallow");
   constexpr int NA = Cfg::kAStages, NB = Cfg::kBStages, TAPS = R_ * S_, TPS = Cfg::kTPS;
   extern __shared__ uint8_t smem_raw[];
@@ -508,11 +525,15 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         const int w0 = tw * 8, h0 = th * 16, co0 = tco * BN;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(aempty(sa), pa ^ 1);
-          mbar_expect_tx(afull(sa), Cfg::kAStageBytes);
+          mbar_expect_tx(afull(sa), Cfg::kTxBytes);
+          if (ONEBOX) {
+            tma_load_4d(a_base + sa * Cfg::kAStageBytes, &tmA, afull(sa), ch * kChunk, w0 - p.pad, h0 - p.pad, n0);
+          } else {
 #pragma unroll
-          for (int s = 0; s < S_; ++s)
-            tma_load_4d(a_base + sa * Cfg::kAStageBytes + s * Cfg::kBoxBytes, &tmA, afull(sa), ch * kChunk, w0 + s - p.pad,
-                        h0 - p.pad, n0);
+            for (int s = 0; s < S_; ++s)
+              tma_load_4d(a_base + sa * Cfg::kAStageBytes + s * Cfg::kBoxBytes, &tmA, afull(sa), ch * kChunk, w0 + s - p.pad,
+                          h0 - p.pad, n0);
+          }
           if (++sa == NA) { sa = 0; pa ^= 1; }
 #pragma unroll
           for (int g = 0; g < TAPS / TPS; ++g) {              // one B stage = TPS taps of this chunk
@@ -541,7 +562,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(afull(sa), pa);
           tc_fence_after();
-          const uint64_t ad0 = make_smem_desc(a_base + sa * Cfg::kAStageBytes, 16, 1024);
+          const uint64_t ad0 = make_smem_desc(a_base + sa * Cfg::kAStageBytes, 16, Cfg::kRowPitch);
 #pragma unroll
           for (int g = 0; g < TAPS / TPS; ++g) {
             mbar_wait(bfull(sb), pb);
@@ -549,10 +570,11 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const uint64_t bd0 = make_smem_desc(b_base + sb * Cfg::kBStageBytes, 16, 1024);
 #pragma unroll
             for (int u = 0; u < TPS; ++u) {
-              const int tap = g * TPS + u, r = tap / S_, s = tap - r * S_;     // row shift = whole swizzle atoms
+              const int tap = g * TPS + u, r = tap / S_, s = tap - r * S_;     // row shift = whole box rows
+              const int a_off = ONEBOX ? (r * Cfg::kBoxCols + s) * 128 : s * Cfg::kBoxBytes + r * 1024;
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                mma_tf32(d_tmem, ad0 + (uint64_t)((s * Cfg::kBoxBytes + r * 1024 + kk * 32) >> 4),
+                mma_tf32(d_tmem, ad0 + (uint64_t)((a_off + kk * 32) >> 4),
                          bd0 + (uint64_t)((u * Cfg::kTapBytes + kk * 32) >> 4), idesc, (ch | tap | kk) ? 1u : 0u);
             }
             mma_commit(bempty(sb));
@@ -983,6 +1005,251 @@ conv_fprop_tc2_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA pair, one-box tap reuse, MT tiles per B tile
+// What bounds the kernels above on the large layers is the L2 -> SM path (ncu: lts2xbar at 82 % of its peak while the tensor
+// pipe is 76 % active): per 32-channel chunk a CTA of conv_fprop_tc2_halo_kernel<256> pulls 54 KB of A (three column-shifted
+// boxes) + 147 KB of B for 4608 MMA cycles = 44 B / cycle / SM against a chip-wide ~42 B / cycle / SM L2 output cap.  Here
+//   * ONE box per M tile and chunk -- (32 ch, 10 wide, 18 tall) = 22.5 KB -- serves all nine taps: tap (r, s) is the start-address
+//     offset (r * 10 + s) * 128 B into it, with SBO = 10 * 128 B between the 8-pixel row groups (see FpropHaloCfg ONEBOX);
+//   * every B (weight) tile is used for MT = 2 M tiles per CTA (four per pair): two accumulators per TMEM stage (MT * BN * 2
+//     stages = 512 columns at BN = 128), B bytes per flop halved.
+// 2 * 22.5 + 72 = 117 KB per chunk and CTA for the same 4608 MMA cycles = 26 B / cycle / SM.
+// Work is cut into UNITS = (one 16 x 8 pixel tile per CTA of the pair, one 128-channel N tile), N tile slowest; every pair owns a
+// contiguous range of units (sizes differ by at most one: no wave quantisation) and processes them two at a time where the
+// two share the N tile.
+template <int BN, int MT>
+struct Fprop2H1Cfg {
+  static constexpr int kBoxCols = 10, kBoxRows = 18;
+  static constexpr int kTileTx = kBoxRows * kBoxCols * 128;                  // bytes TMA writes per tile and chunk
+  static constexpr int kTileBytes = ((kTileTx + 1023) / 1024) * 1024;       // swizzle pattern restarts on 1024-byte boundaries
+  static constexpr int kAStageBytes = MT * kTileBytes;
+  static constexpr int kRowPitch = kBoxCols * 128;
+  static constexpr int kTPS = 3;                                              // taps per B stage
+  static constexpr int kTapBytes = (BN / 2) * 128;
+  static constexpr int kBStageBytes = kTPS * kTapBytes;
+  static constexpr int kAStages = 2;
+  static constexpr int kBStages = (BN >= 256) ? 3 : 4;
+  static constexpr int kTmemCols = 2 * MT * BN;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 256;
+};
+
+struct H1Range { int begin, end; };
+__device__ __forceinline__ H1Range h1_range(int units, int pair_id, int num_pairs) {
+  H1Range r;
+  r.begin = (int)(((long long)units * pair_id) / num_pairs);
+  r.end = (int)(((long long)units * (pair_id + 1)) / num_pairs);
+  return r;
+}
+
+template <int BN, int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
+conv_fprop_tc2_h1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  using Cfg = Fprop2H1Cfg<BN, MT>;
+  static_assert(Cfg::kTmemCols <= 512, "TMEM has 512 columns");
+  constexpr int NA = Cfg::kAStages, NB = Cfg::kBStages, S_ = 3, TAPS = 9, TPS = Cfg::kTPS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base, b_base = base + NA * Cfg::kAStageBytes;
+  const uint32_t bar0 = b_base + NB * Cfg::kBStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NA * Cfg::kAStageBytes + NB * Cfg::kBStageBytes);
+  auto afull = [&](int s) { return bar0 + 8u * s; };
+  auto aempty = [&](int s) { return bar0 + 8u * (NA + s); };
+  auto bfull = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+  auto bempty = [&](int s) { return bar0 + 8u * (2 * NA + NB + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA + 2 * NB + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int chunks = p.Ci / kChunk;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  // p.num_tiles = units; p.tiles_n = M-tile pairs per N tile (units = tiles_co * m_pairs, N tile slowest)
+  const int m_pairs = p.num_tiles / p.tiles_co;
+  const H1Range rg = h1_range(p.num_tiles, pair_id, num_pairs);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's tile of unit u: M tiles ordered (n, th, tw), tw fastest; 16 x 8 pixels each
+  auto unit_tile = [&](int u, int& w0, int& h0, int& n0) {
+    int t = (u % m_pairs) * 2 + (int)rank;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    w0 = tw * 8; h0 = th * 16; n0 = t;
+  };
+  // units of the item that starts at u: MT when the next unit exists in this pair's range and shares the N tile
+  auto item_units = [&](int u) { return (MT > 1 && u + 1 < rg.end && (u + 1) / m_pairs == u / m_pairs) ? 2 : 1; };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int u = rg.begin; u < rg.end;) {
+        const int mt = item_units(u);
+        int w0[MT], h0[MT], n0[MT];
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+          if (j < mt) unit_tile(u + j, w0[j], h0[j], n0[j]);
+        const int co0 = (u / m_pairs) * BN + (int)rank * (BN / 2);   // this CTA's half of the weight tile
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(aempty(sa), pa ^ 1);
+          if (leader) mbar_expect_tx(afull(sa), 2 * mt * Cfg::kTileTx);
+          const uint32_t lafull = mapa(afull(sa), 0);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            if (j < mt)
+              tma2_load_4d(a_base + sa * Cfg::kAStageBytes + j * Cfg::kTileBytes, &tmA, lafull, ch * kChunk, w0[j] - p.pad,
+                           h0[j] - p.pad, n0[j]);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+#pragma unroll
+          for (int g = 0; g < TAPS / TPS; ++g) {
+            mbar_wait(bempty(sb), pb ^ 1);
+            if (leader) mbar_expect_tx(bfull(sb), 2 * Cfg::kBStageBytes);
+            const uint32_t lbfull = mapa(bfull(sb), 0);
+#pragma unroll
+            for (int t = 0; t < TPS; ++t)
+              tma2_load_3d(b_base + sb * Cfg::kBStageBytes + t * Cfg::kTapBytes, &tmB, lbfull, ch * kChunk, g * TPS + t, co0);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+        }
+        u += mt;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, BN, 0, 0);
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      for (int u = rg.begin; u < rg.end;) {
+        const int mt = item_units(u);
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * (MT * BN);
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(afull(sa), pa);
+          tc_fence_after();
+          const uint64_t ad0 = make_smem_desc(a_base + sa * Cfg::kAStageBytes, 16, Cfg::kRowPitch);
+#pragma unroll
+          for (int g = 0; g < TAPS / TPS; ++g) {
+            mbar_wait(bfull(sb), pb);
+            tc_fence_after();
+            const uint64_t bd0 = make_smem_desc(b_base + sb * Cfg::kBStageBytes, 16, 1024);
+#pragma unroll
+            for (int t = 0; t < TPS; ++t) {
+              const int tap = g * TPS + t, r = tap / S_, s = tap - r * S_;
+              const int a_off = (r * Cfg::kBoxCols + s) * 128;
+#pragma unroll
+              for (int j = 0; j < MT; ++j) {
+                if (j < mt) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    mma2_tf32(d_tmem + j * BN, ad0 + (uint64_t)((j * Cfg::kTileBytes + a_off + kk * 32) >> 4),
+                              bd0 + (uint64_t)((t * Cfg::kTapBytes + kk * 32) >> 4), idesc, (ch | tap | kk) ? 1u : 0u);
+                }
+              }
+            }
+            mma2_commit_mc(bempty(sb), 3);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+          mma2_commit_mc(aempty(sa), 3);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        mma2_commit_mc(tfull_bar(as), 3);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        u += mt;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): own 128 rows of each of the pair's accumulators =====================
+    const int q = warp & 3;
+    const int c_begin = ((warp - 4) >> 2) * (BN / 2);
+    const int row = q * 32 + lane;
+    const int rw = row & 7, rh = row >> 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int u = rg.begin; u < rg.end;) {
+      const int mt = item_units(u);
+      const int co0 = (u / m_pairs) * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < mt; ++j) {
+        int w0, h0, n;
+        unit_tile(u + j, w0, h0, n);
+        const int w = w0 + rw, h = h0 + rh;
+        const bool valid = (w < p.Wo) && (h < p.Ho);
+        float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+#pragma unroll 1
+        for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (MT * BN) + j * BN + c, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int e4 = 0; e4 < 32; e4 += 4) {
+              float4 o;
+              float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = p.alpha * __uint_as_float(v[e4 + e]);
+                if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + e4 + e);
+                oo[e] = act_apply(a, p.act, p.slope);
+              }
+              *reinterpret_cast<float4*>(out + c + e4) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+      u += mt;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int MT>
+int launch_fprop2_h1(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = Fprop2H1Cfg<BN, MT>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_h1_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int items = (p.num_tiles + MT - 1) / MT;
+  const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
+  conv_fprop_tc2_h1_kernel<BN, MT><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GLB_CHECK_LAUNCH("conv_fprop_tc2_h1_kernel");
+  return GLB_OK;
+}
+
 template <int BN>
 int launch_fprop2_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = Fprop2HaloCfg<BN>;
@@ -1017,16 +1284,16 @@ inline int next_pow2(int v) {
   return p;
 }
 
-template <int BN>
+template <int BN, bool ONEBOX>
 int launch_fprop_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
-  using Cfg = FpropHaloCfg<BN, 3, 3>;
+  using Cfg = FpropHaloCfg<BN, 3, 3, ONEBOX>;
   static bool configured = false;
   if (!configured) {
-    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_halo_kernel<BN, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_halo_kernel<BN, 3, 3, ONEBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  conv_fprop_tc_halo_kernel<BN, 3, 3><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  conv_fprop_tc_halo_kernel<BN, 3, 3, ONEBOX><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc_halo_kernel");
   return GLB_OK;
 }
@@ -1114,13 +1381,42 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   p.ksplit = (k_iters + p.k_per - 1) / p.k_per;
   p.tiles_co = Co / BN;
   p.num_tiles = m_tiles * p.tiles_co * p.ksplit;
-  p.alpha = alpha; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+  p.alpha = alpha * kTf32TruncComp; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
   p.dbg = 0;
   p.trace = nullptr;
   if (const char* e = getenv("GLB_FPROP_DBG")) p.dbg = atoi(e);
   if (const char* e = getenv("GLB_FPROP_TRACE")) p.trace = (long long*)strtoull(e, nullptr, 0);
   const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
   if (p.ksplit > 1) GLB_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * p.Ho * p.Wo * Co, st));
+
+  // CTA pair + one-box tap reuse + two M tiles per B tile (conv_fprop_tc2_h1_kernel): 3x3 "same" convolutions on maps that tile
+  // into 16 x 8 pixel tiles, an even number of them, Co a multiple of 128, at least one unit pair per CTA pair
+  {
+    int h1 = 0;                                   // GLB_FPROP_H1: 0 = off, 1 = <128, 2> (default once measured), 2 = <256, 1>
+    if (const char* e = getenv("GLB_FPROP_H1")) h1 = atoi(e); else h1 = kH1Default;
+    const int bnh = (h1 == 2) ? 256 : 128;
+    const int m_h = (p.Ho / 16) * (p.Wo / 8) * N;
+    const bool ok = h1 != 0 && p.ksplit == 1 && R == 3 && S == 3 && pad == 1 && p.Ho % 16 == 0 && p.Wo % 8 == 0 && Co % bnh == 0 &&
+                    m_h % 2 == 0 && (m_h / 2) * (Co / bnh) >= kNumSMs;
+    if (ok) {
+      FpropParams q = p;
+      q.bw = 8; q.bh = 16; q.bn = 1;
+      q.tiles_w = p.Wo / 8; q.tiles_h = p.Ho / 16; q.tiles_n = N; q.tiles_co = Co / bnh;
+      q.num_tiles = (m_h / 2) * q.tiles_co;          // units
+      CUtensorMap hA, hB;
+      const uint64_t dimsA[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+      const uint64_t stridesA[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+      const uint32_t boxA[4] = {(uint32_t)kChunk, 10u, 18u, 1u};
+      int rc = make_tmap_f32(&hA, x, 4, dimsA, stridesA, boxA, "conv input (10 x 18 box)");
+      if (rc) return rc;
+      const uint64_t dimsB[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
+      const uint64_t stridesB[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+      const uint32_t boxB[3] = {(uint32_t)kChunk, 1u, (uint32_t)(bnh / 2)};
+      rc = make_tmap_f32(&hB, w, 3, dimsB, stridesB, boxB, "conv weight (half tile)");
+      if (rc) return rc;
+      return bnh == 128 ? launch_fprop2_h1<128, 2>(hA, hB, q, st) : launch_fprop2_h1<256, 1>(hA, hB, q, st);
+    }
+  }
 
   // tap-reuse kernel: 3x3 "same" convolutions on maps that tile exactly into 16 x 8 pixel tiles, >= one wave of tiles
   {
@@ -1137,7 +1433,8 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
       CUtensorMap hA, hB;
       const uint64_t dimsA[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
       const uint64_t stridesA[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
-      const uint32_t boxA[4] = {(uint32_t)kChunk, 8u, 18u, 1u};
+      const bool onebox = getenv("GLB_FPROP_ONEBOX") != nullptr && atoi(getenv("GLB_FPROP_ONEBOX")) != 0;   // A/B experiment
+      const uint32_t boxA[4] = {(uint32_t)kChunk, onebox ? 10u : 8u, 18u, 1u};
       int rc = make_tmap_f32(&hA, x, 4, dimsA, stridesA, boxA, "conv input (halo boxes)");
       if (rc) return rc;
       const uint64_t dimsB[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
@@ -1145,7 +1442,8 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
       const uint32_t boxB[3] = {(uint32_t)kChunk, 1u, (uint32_t)BN};
       rc = make_tmap_f32(&hB, w, 3, dimsB, stridesB, boxB, "conv weight");
       if (rc) return rc;
-      return BN == 128 ? launch_fprop_halo<128>(hA, hB, q, st) : launch_fprop_halo<256>(hA, hB, q, st);
+      if (onebox) return BN == 128 ? launch_fprop_halo<128, true>(hA, hB, q, st) : launch_fprop_halo<256, true>(hA, hB, q, st);
+      return BN == 128 ? launch_fprop_halo<128, false>(hA, hB, q, st) : launch_fprop_halo<256, false>(hA, hB, q, st);
     }
     // bits 2 / 3: CTA pair + tap reuse for BN 128 / 256 (M = 256 per pair: needs an even number of 16 x 8 tiles)
     const int m_h = (p.Ho / 16) * (p.Wo / 8) * N;
@@ -1597,7 +1895,7 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
       if (splits < 1) splits = 1;
       p.pb_per_split = (p.num_pb + splits - 1) / splits;
       p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;
-      p.alpha = alpha;
+      p.alpha = alpha * kTf32TruncComp;
       p.atomic = p.splits > 1 ? 1 : 0;
       p.bw = 8; p.bh = 4; p.bn = 1;
       if (p.atomic) GLB_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Co * R * S * Ci, st));
@@ -1641,7 +1939,7 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   if (splits < 1) splits = 1;
   p.pb_per_split = (p.num_pb + splits - 1) / splits;
   p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;  // every split owns >= 1 pixel block
-  p.alpha = alpha;
+  p.alpha = alpha * kTf32TruncComp;
   p.atomic = p.splits > 1 ? 1 : 0;
   if (p.atomic) GLB_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Co * R * S * Ci, st));
 

@@ -29,26 +29,40 @@ __global__ void rgb_expand_kernel(const float* __restrict__ img, const float* __
   const int64_t P = (int64_t)N * H * W;
   const int IH = pool ? 2 * H : H, IW = pool ? 2 * W : W;
   const int64_t plane = (int64_t)IH * IW, HW = (int64_t)H * W;
-  for (int64_t p = (int64_t)blockIdx.x * ppb + threadIdx.x / C4; p < P; p += (int64_t)gridDim.x * ppb) {
-    const int64_t n = p / HW, r = p - n * HW;
-    float v[3];
-    if (pool) {
-      const int hh = (int)(r / W), ww = (int)(r - (int64_t)hh * W);
-      const int64_t o = (int64_t)(2 * hh) * IW + 2 * ww;
+  constexpr int EU = 4;                                 // pixels per thread and iteration: their image loads are independent
+  const int64_t stride = (int64_t)gridDim.x * ppb;
+  for (int64_t p0 = (int64_t)blockIdx.x * ppb + threadIdx.x / C4; p0 < P; p0 += EU * stride) {
+    float v[EU][3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float* ip = img + (n * 3 + j) * plane;
-        v[j] = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
+    for (int u = 0; u < EU; ++u) {
+      const int64_t p = p0 + u * stride;
+      if (p < P) {
+        const int64_t n = p / HW, r = p - n * HW;
+        if (pool) {
+          const int hh = (int)(r / W), ww = (int)(r - (int64_t)hh * W);
+          const int64_t o = (int64_t)(2 * hh) * IW + 2 * ww;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float* ip = img + (n * 3 + j) * plane;
+            v[u][j] = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) v[u][j] = __ldg(img + (n * 3 + j) * plane + r);
+        }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) v[j] = __ldg(img + (n * 3 + j) * plane + r);
     }
-    float o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      o[k] = act_apply(fmaf(v[0], wr[0][k], fmaf(v[1], wr[1][k], fmaf(v[2], wr[2][k], br[k]))), act, slope);
-    stg_stream(y + p * C4 + q, make_float4(o[0], o[1], o[2], o[3]));
+    for (int u = 0; u < EU; ++u) {
+      const int64_t p = p0 + u * stride;
+      if (p < P) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          o[k] = act_apply(fmaf(v[u][0], wr[0][k], fmaf(v[u][1], wr[1][k], fmaf(v[u][2], wr[2][k], br[k]))), act, slope);
+        stg_stream(y + p * C4 + q, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
   }
 }
 
@@ -58,11 +72,15 @@ template <int GS, int QPL>   // QPL = quads per lane held in registers (0: read 
 __global__ void rgb_contract_kernel(const float4* __restrict__ x, const float* __restrict__ w, int ws_j, int ws_c,
                                     const float* __restrict__ bias, float* __restrict__ img, int N, int H, int W, int C4, int pool,
                                     float alpha, float bias_scale) {
+  // PX pixels per group and iteration: PX * QPL independent 16-byte loads in flight per lane (one pixel per iteration left the
+  // kernel latency bound at ~2 TB/s)
+  constexpr int PX = (QPL > 0 && QPL <= 2) ? 4 : (QPL == 4 ? 2 : 1);
   const int64_t P = (int64_t)N * H * W;
   const int lane = threadIdx.x % GS;
   const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS, ngrp = ((int64_t)gridDim.x * blockDim.x) / GS;
-  // P is padded up so every lane of a warp takes part in the shuffles
-  const int64_t Ppad = ((P + (32 / GS) - 1) / (32 / GS)) * (32 / GS);
+  // the pixel range is padded up so every lane of a warp takes part in the shuffles
+  const int64_t per = (32 / GS) * PX;
+  const int64_t Ppad = ((P + per - 1) / per) * per;
   float wr[QPL > 0 ? QPL : 1][3][4];
   if (QPL > 0) {
 #pragma unroll
@@ -74,59 +92,67 @@ __global__ void rgb_contract_kernel(const float4* __restrict__ x, const float* _
         for (int j = 0; j < 3; ++j) wr[i][j][k] = (lane + i * GS < C4) ? __ldg(w + j * ws_j + c * ws_c) : 0.f;
       }
   }
-  for (int64_t p = grp; p < Ppad; p += ngrp) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (p < P) {
-      if (QPL > 0) {
-        float4 v[QPL > 0 ? QPL : 1];
+  for (int64_t pbase = grp * PX; pbase < Ppad; pbase += ngrp * PX) {
+    float acc[PX][3];
+#pragma unroll
+    for (int u = 0; u < PX; ++u) acc[u][0] = acc[u][1] = acc[u][2] = 0.f;
+    if (QPL > 0) {
+      float4 v[PX][QPL > 0 ? QPL : 1];
+#pragma unroll
+      for (int u = 0; u < PX; ++u)
 #pragma unroll
         for (int i = 0; i < QPL; ++i)
-          v[i] = (lane + i * GS < C4) ? ldg_stream(x + p * C4 + lane + i * GS) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u][i] = (pbase + u < P && lane + i * GS < C4) ? ldg_stream(x + (pbase + u) * C4 + lane + i * GS) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < PX; ++u)
 #pragma unroll
         for (int i = 0; i < QPL; ++i) {
-          const float vv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          const float vv[4] = {v[u][i].x, v[u][i].y, v[u][i].z, v[u][i].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            a0 = fmaf(vv[k], wr[i][0][k], a0);
-            a1 = fmaf(vv[k], wr[i][1][k], a1);
-            a2 = fmaf(vv[k], wr[i][2][k], a2);
+            acc[u][0] = fmaf(vv[k], wr[i][0][k], acc[u][0]);
+            acc[u][1] = fmaf(vv[k], wr[i][1][k], acc[u][1]);
+            acc[u][2] = fmaf(vv[k], wr[i][2][k], acc[u][2]);
           }
         }
-      } else {
-        for (int q = lane; q < C4; q += GS) {
-          const float4 v = ldg_stream(x + p * C4 + q);
-          const float vv[4] = {v.x, v.y, v.z, v.w};
+    } else if (pbase < P) {
+      for (int q = lane; q < C4; q += GS) {
+        const float4 v = ldg_stream(x + pbase * C4 + q);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = 4 * q + k;
-            a0 = fmaf(vv[k], __ldg(w + 0 * ws_j + c * ws_c), a0);
-            a1 = fmaf(vv[k], __ldg(w + 1 * ws_j + c * ws_c), a1);
-            a2 = fmaf(vv[k], __ldg(w + 2 * ws_j + c * ws_c), a2);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * q + k;
+          acc[0][0] = fmaf(vv[k], __ldg(w + 0 * ws_j + c * ws_c), acc[0][0]);
+          acc[0][1] = fmaf(vv[k], __ldg(w + 1 * ws_j + c * ws_c), acc[0][1]);
+          acc[0][2] = fmaf(vv[k], __ldg(w + 2 * ws_j + c * ws_c), acc[0][2]);
         }
       }
     }
 #pragma unroll
-    for (int o = GS / 2; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (p < P && lane < 3) {
-      float a = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
-      a *= alpha;
-      if (bias != nullptr) a += bias_scale * __ldg(bias + lane);
-      const int ww = (int)(p % W);
-      int64_t t = p / W;
-      const int hh = (int)(t % H);
-      const int64_t n = t / H;
-      if (pool) {
-        const int OW = 2 * W;
-        float* o = img + ((n * 3 + lane) * (2 * H) + 2 * hh) * (int64_t)OW + 2 * ww;
-        a *= 0.25f;
-        o[0] = a; o[1] = a; o[OW] = a; o[OW + 1] = a;
-      } else {
-        img[((n * 3 + lane) * H + hh) * (int64_t)W + ww] = a;
+    for (int u = 0; u < PX; ++u) {
+#pragma unroll
+      for (int o = GS / 2; o > 0; o >>= 1) {
+        acc[u][0] += __shfl_xor_sync(0xffffffffu, acc[u][0], o);
+        acc[u][1] += __shfl_xor_sync(0xffffffffu, acc[u][1], o);
+        acc[u][2] += __shfl_xor_sync(0xffffffffu, acc[u][2], o);
+      }
+      const int64_t p = pbase + u;
+      if (p < P && lane < 3) {
+        float a = lane == 0 ? acc[u][0] : (lane == 1 ? acc[u][1] : acc[u][2]);
+        a *= alpha;
+        if (bias != nullptr) a += bias_scale * __ldg(bias + lane);
+        const int ww = (int)(p % W);
+        int64_t t = p / W;
+        const int hh = (int)(t % H);
+        const int64_t n = t / H;
+        if (pool) {
+          const int OW = 2 * W;
+          float* o = img + ((n * 3 + lane) * (2 * H) + 2 * hh) * (int64_t)OW + 2 * ww;
+          a *= 0.25f;
+          o[0] = a; o[1] = a; o[OW] = a; o[OW + 1] = a;
+        } else {
+          img[((n * 3 + lane) * H + hh) * (int64_t)W + ww] = a;
+        }
       }
     }
   }
@@ -149,26 +175,40 @@ __global__ void rgb_wgrad_kernel(const float* __restrict__ img, const float4* __
     for (int n = blockIdx.y; n < N; n += gridDim.y) {
       const float4* gn = g + (int64_t)n * HW * C4 + q;
       const float* in = img + (int64_t)n * 3 * plane;
-      for (int r = blockIdx.x * rows + rl; r < HW; r += gridDim.x * rows) {
-        const float4 gv = ldg_stream(gn + (int64_t)r * C4);
-        float v[3];
-        if (pool) {
-          const int hh = r / W, ww = r - hh * W;
-          const int o = (2 * hh) * IW + 2 * ww;
+      constexpr int WU = 4;                             // rows in flight per thread (one row per iteration: 1.3 TB/s, latency bound)
+      const int stride = gridDim.x * rows;
+      for (int r0 = blockIdx.x * rows + rl; r0 < HW; r0 += WU * stride) {
+        float4 gv[WU];
+        float v[WU][3];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          const int r = r0 + u * stride;
+          if (r < HW) {
+            gv[u] = ldg_stream(gn + (int64_t)r * C4);
+            if (pool) {
+              const int hh = r / W, ww = r - hh * W;
+              const int o = (2 * hh) * IW + 2 * ww;
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const float* ip = in + j * plane;
+                v[u][j] = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) v[u][j] = __ldg(in + j * plane + r);
+            }
+          } else {
+            gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u][0] = v[u][1] = v[u][2] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < WU; ++u)
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            const float* ip = in + j * plane;
-            v[j] = 0.25f * (__ldg(ip + o) + __ldg(ip + o + 1) + __ldg(ip + o + IW) + __ldg(ip + o + IW + 1));
+            s[j].x = fmaf(v[u][j], gv[u].x, s[j].x); s[j].y = fmaf(v[u][j], gv[u].y, s[j].y);
+            s[j].z = fmaf(v[u][j], gv[u].z, s[j].z); s[j].w = fmaf(v[u][j], gv[u].w, s[j].w);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) v[j] = __ldg(in + j * plane + r);
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          s[j].x = fmaf(v[j], gv.x, s[j].x); s[j].y = fmaf(v[j], gv.y, s[j].y);
-          s[j].z = fmaf(v[j], gv.z, s[j].z); s[j].w = fmaf(v[j], gv.w, s[j].w);
-        }
       }
     }
     if (C4 > lanes) {  // wide: direct atomics
@@ -267,9 +307,13 @@ extern "C" int glb_rgb_wgrad(const float* img, const float* g, float* gw, int ws
   REQ(C4 > TPB || TPB % C4 == 0, "rgb_wgrad: C/4 must divide 256 or exceed it");
   const int lanes = C4 < TPB ? C4 : TPB, rows = TPB / lanes;
   REQ((int64_t)H * W * 4 < (1ll << 31), "rgb_wgrad: plane too large");
-  // every block ends in 3*C atomics on the same addresses: ~2 blocks per SM in total, spread as (plane chunks) x (samples)
+  // every block ends in 3*C atomics on the same 3*C addresses (80 us of pure contention with 6 blocks per SM at C = 512): at most
+  // ~2 blocks per SM, fewer when there is little to read (>= 8 rows of 4 per thread), spread as (plane chunks) x (samples)
   int by = N < 16 ? N : 16;
-  int bx = (2 * kNumSMs + by - 1) / by;
+  int64_t want = ((int64_t)N * H * W * C4 + (int64_t)TPB * 32 - 1) / ((int64_t)TPB * 32);
+  if (want > 2 * kNumSMs) want = 2 * kNumSMs;
+  if (want < by) want = by;
+  int bx = (int)((want + by - 1) / by);
   const int max_bx = (H * W + rows - 1) / rows;
   if (bx > max_bx) bx = max_bx;
   rgb_wgrad_kernel<<<dim3(bx, by), TPB, 3 * TPB * sizeof(float4), (cudaStream_t)stream>>>(img, (const float4*)g, gw, ws_j, ws_c, N, H, W,

@@ -67,6 +67,39 @@ class Tape:
         return False
 
 
+class ReplayTape:
+    """The inverse of Tape: while active, torch.randn / rand / randint / np.random.rand hand out recorded draws in order
+    (moved to `dev`), so that a second run of the reference -- on another device -- sees exactly the first run's random numbers."""
+
+    def __init__(self, events, dev):
+        self.events, self.dev, self._orig = list(events), dev, {}
+
+    def _pop(self, kind):
+        k, v = self.events.pop(0)
+        assert k == kind, (k, kind)
+        return v
+
+    def __enter__(self):
+        self._orig = dict(randn=torch.randn, rand=torch.rand, randint=torch.randint, nprand=np.random.rand)
+        tape = self
+
+        def tensor_draw(kind):
+            def f(*a, **k):
+                t = tape._pop(kind)
+                want = k.get("device", None)
+                return t.to(want) if want is not None else t.clone()
+            return f
+
+        torch.randn, torch.rand, torch.randint = tensor_draw("randn"), tensor_draw("rand"), tensor_draw("randint")
+        np.random.rand = lambda *a: tape._pop("np_rand")
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.rand, torch.randint = self._orig["randn"], self._orig["rand"], self._orig["randint"]
+        np.random.rand = self._orig["nprand"]
+        return False
+
+
 def perturb_zero_params(module, gen):
     """Zero-initialised params (biases, noise_weight) hide whole code paths; perturb them
     (SURVEY.md section 8c 'Determinism hooks')."""
@@ -936,7 +969,7 @@ def golden_init_digests(ref):
     return out
 
 
-def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
+def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False, dev="cpu", replay=None):
     """ONE main iteration (D step + G step, Adam, EWMA) of the UNMODIFIED reference at cfg2's REAL widths (StyleGAN 128x128,
     FMAP_MAX 512: 512 -> 256 -> 128 channels, batch 8, nonsaturating + R1 + drift, noise, mixing .9) -- the configuration
     bench.py times.  49 M parameters and their gradients do not fit a committed fixture, so: the initial weights are NOT
@@ -946,11 +979,14 @@ def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
     (norm, max-norm, strided sample, random projections)."""
     from oracle import summaries as S
     torch.manual_seed(seed); np.random.seed(seed)
-    cfg = make_config("StyleGAN", res=res, init_res=res, batch_size=bs)
+    # dev / replay: the same run on another device with the CPU run's taped draws replayed (tests/calibrate_tf32_bounds.py:
+    # the unmodified reference through stock PyTorch on the B200); the fixture itself is dev = "cpu", replay = None
+    cfg = make_config("StyleGAN", res=res, init_res=res, batch_size=bs, dev=dev, metrics_dev=torch.device(dev))
     with _quiet():
         L = ref.stylegan_learner.StyleGANLearner(cfg)
     gen = torch.Generator().manual_seed(seed + 1)
     perturb_zero_params(L.gen_model, gen); perturb_zero_params(L.disc_model, gen)
+    taping = (lambda key: Tape()) if replay is None else (lambda key: ReplayTape(replay[key], dev))
     if ulp_perturb:          # every weight moved by about one unit in the last place (see golden_cfg2_fullwidth_step)
         pg = torch.Generator().manual_seed(seed + 2)
         with torch.no_grad():
@@ -968,7 +1004,8 @@ def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
     # the R1 penalty on its own at the initial weights (inside the whole loss it is ~1e-8 of it at random init):
     # value and every discriminator gradient of calc_gp's double backward
     L.disc_model.train(); L.disc_model.zero_grad()
-    gp_alone = L.calc_gp(data.clone(), data.clone())          # R1 only looks at the real batch (resnetgan/learner.py:799-802)
+    L.disc_model.to(dev); L.gen_model.to(dev)
+    gp_alone = L.calc_gp(data.clone().to(dev), data.clone().to(dev))          # R1 only looks at the real batch (resnetgan/learner.py:799-802)
     gp_alone.backward()
     gp_grads = {"d." + n: S.summarize("gpgrad.d." + n, p.grad) for n, p in L.disc_model.named_parameters() if p.grad is not None}
     L.disc_model.zero_grad()
@@ -977,8 +1014,8 @@ def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
     # (progan/learner.py:883-896: binary_cross_entropy_with_logits against ones) -> every generator gradient
     L.gen_model.train(); L.gen_model.zero_grad()
     z_alone = torch.randn(bs, cfg.len_latent, generator=gen)
-    with Tape() as tape_alone:
-        img_alone = L.gen_model(z_alone)
+    with taping("g_alone") as tape_alone:
+        img_alone = L.gen_model(z_alone.to(dev))
     for p in L.disc_model.parameters():
         p.requires_grad_(False)
     logits_alone = L.disc_model(img_alone).view(-1)
@@ -987,7 +1024,7 @@ def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
     for p in L.disc_model.parameters():
         p.requires_grad_(True)
     g_alone = dict(z=z_alone, tape=tape_alone.events, loss=float(g_alone_loss.detach()), img=S.summarize("galone.img", img_alone),
-                   logits=logits_alone.detach().clone(),
+                   logits=logits_alone.detach().cpu().clone(),
                    grads={"g." + n: S.summarize("galone.g." + n, p.grad) for n, p in L.gen_model.named_parameters()
                           if p.grad is not None})
     L.gen_model.zero_grad(); L.disc_model.zero_grad()
@@ -1013,7 +1050,7 @@ def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
 
     torch.Tensor.backward, torch.optim.Adam.step, L.calc_gp = rec_backward, rec_step, rec_gp
     try:
-        with Tape() as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
+        with taping("train") as tape, _quiet(), contextlib.redirect_stderr(io.StringIO()):
             L.train(dl, num_main_iters=1)
     finally:
         torch.Tensor.backward, torch.optim.Adam.step = orig_backward, orig_step
@@ -1023,8 +1060,17 @@ def _cfg2_fullwidth_run(ref, res, bs, seed, ulp_perturb=False):
     return dict(model="StyleGAN", res=res, bs=bs, seed=seed, lr=cfg.lr_base * cfg.lr_fctr_dict[res], lda=cfg.lda,
                 g_digests=g_dig, d_digests=d_dig, data_digest=_digest(data), tape=tape.events, losses=losses, gp=gp_vals,
                 p0=p0, grads=grads, p1=p1, lagged=lagged, beta=float(L.beta), gp_alone=float(gp_alone.detach()), gp_grads=gp_grads, g_alone=g_alone,
-                w_ewma=L.gen_model.w_ewma.detach().clone())
+                w_ewma=L.gen_model.w_ewma.detach().cpu().clone())
 
+
+
+def _flip_fraction(p1a, p1b, lr):
+    """Fraction of the sampled post-Adam parameter elements that differ by more than 2 % of the learning rate."""
+    bad = tot = 0
+    for k, sa in p1a.items():
+        d = (sa["sample"] - p1b[k]["sample"]).abs()
+        bad += int((d > 0.02 * lr).sum()); tot += d.numel()
+    return bad / tot
 
 
 def golden_cfg2_fullwidth_step(ref, res=128, bs=8, seed=1234):
@@ -1057,7 +1103,8 @@ def golden_cfg2_fullwidth_step(ref, res=128, bs=8, seed=1234):
         g_alone_img=worst({"img": a["g_alone"]["img"]}, {"img": b["g_alone"]["img"]}),
         g_alone_grads=worst(a["g_alone"]["grads"], b["g_alone"]["grads"]),
         d_grads=worst(gd(a["grads"], "d."), gd(b["grads"], "d.")),
-        g_grads=worst(gd(a["grads"], "g."), gd(b["grads"], "g.")))
+        g_grads=worst(gd(a["grads"], "g."), gd(b["grads"], "g.")),
+        p1_flip_fraction=_flip_fraction(a["p1"], b["p1"], a["lr"]))
     return a
 
 def golden_resnet_metrics(ref, res=32, bs=4, n_valid=10):

@@ -45,3 +45,20 @@ def compare(name: str, t: torch.Tensor, ref: dict) -> dict:
     return dict(l2=float((mine["proj"] - ref["proj"]).abs().max()) / scale,
                 smax=float((mine["sample"] - ref["sample"]).abs().max()) / max(ref["absmax"], 1e-30),
                 norm=abs(mine["norm"] - ref["norm"]) / scale)
+
+
+def compare_summaries(mine: dict, ref: dict) -> dict:
+    """Both sides already summarised (same tensor names): -> dict(l2, smax, norm) as `compare`."""
+    scale = max(ref["norm"], 1e-30)
+    return dict(l2=float((mine["proj"] - ref["proj"]).abs().max()) / scale,
+                smax=float((mine["sample"] - ref["sample"]).abs().max()) / max(ref["absmax"], 1e-30),
+                norm=abs(mine["norm"] - ref["norm"]) / scale)
+
+
+def class_stats(per_tensor: dict) -> dict:
+    """worst / median of the per-tensor errors of one class of tensors."""
+    import statistics
+    l2 = [c["l2"] for c in per_tensor.values()]
+    sm = [c["smax"] for c in per_tensor.values()]
+    return dict(l2=max(l2), smax=max(sm), l2_median=statistics.median(l2), smax_median=statistics.median(sm),
+                worst=max(per_tensor, key=lambda k: per_tensor[k]["l2"]))

@@ -333,7 +333,7 @@ def _grow_learner(g, dev, model):
         return ProGANLearner(default_config("ProGAN", **kw))
 
 
-def _adam_close(mine, ref, lr, steps, what, frac=0.03):
+def _adam_close(mine, ref, lr, steps, what, frac=0.03, big=None):
     """Parameters behind `steps` Adam(beta1=0) updates: a rounding-level gradient difference flips a sign-like update, so allow
     scattered flips (never more than `frac` of a network).  Hard bound per element: step t of Adam(beta2=.99) moves a parameter by
     at most lr*sqrt((1-.99^t)/.01) (a gradient much larger than its own history; typical for gradients that are pure rounding
@@ -344,7 +344,9 @@ def _adam_close(mine, ref, lr, steps, what, frac=0.03):
     for k, v in ref.items():
         d = (mine[k].detach() - v).abs()
         assert float(d.max()) <= bound, (what, k, float(d.max()), bound)
-        nb = int((d > 2e-5 + 1e-4 * v.abs()).sum())
+        # big: count only elements that moved apart by more than `big` (a fraction of a step): where the gradient itself carries
+        # per-cent noise (generator gradients behind the discriminator's fresh Adam step) every element differs a little
+        nb = int((d > (2e-5 + 1e-4 * v.abs() if big is None else big)).sum())
         if nb:
             per_key[k] = (nb, v.numel(), float(d.max()))
         bad += nb; tot += v.numel()
@@ -404,8 +406,21 @@ def case_learner_grow(golden, dev, fname, model, device_alpha=False):
         # with the reference's parameters at the start of the iteration, then continue FROM the reference's parameters.
         snap = g["iter_snaps"].get(len(trace))
         if snap is not None:
-            _adam_close(L.gen_model.state_dict(), snap[0], lr_max, per, "G@%d" % len(trace), frac=0.01)
-            _adam_close(L.disc_model.state_dict(), snap[1], lr_max, per, "D@%d" % len(trace), frac=0.01)
+            # The generator step of the FIRST iteration after an optimiser rebuild is a pure sign step (Adam, t = 1) on gradients
+            # taken behind the discriminator's own sign step of the same iteration: the unmodified reference re-run with its
+            # weights moved by one ulp differs from itself by ~5 % (L2) in exactly these gradients at cfg2's size
+            # (tests/golden/style_cfg2_fullwidth_step.pt, `self_noise`), i.e. a few per cent of sign flips.  Elsewhere 1 %.
+            # From the second step on the update lr * g2 / sqrt((g1^2 + g2^2) / 2) is smooth in the gradient, so that per-cent
+            # gradient noise moves EVERY element by a few per cent of a step: only elements a quarter of a step apart count.
+            # Iterations run since the last re-synchronisation with the reference's parameters widen the gap further -- for the
+            # discriminator as well, whose step then sits behind a generator that has already drifted.
+            prev = max([k for k in g["iter_snaps"] if k < len(trace)], default=0)
+            gap = max(1, len(trace) - prev)
+            _adam_close(L.gen_model.state_dict(), snap[0], lr_max, per, "G@%d" % len(trace), frac=0.05 * gap, big=0.25 * lr_max)
+            if gap == 1:
+                _adam_close(L.disc_model.state_dict(), snap[1], lr_max, per, "D@%d" % len(trace), frac=0.01)
+            else:
+                _adam_close(L.disc_model.state_dict(), snap[1], lr_max, per, "D@%d" % len(trace), frac=0.05 * gap, big=0.25 * lr_max)
             with torch.no_grad():
                 for net, sd in ((L.gen_model, snap[0]), (L.disc_model, snap[1])):
                     for k, v in net.state_dict().items():
@@ -438,9 +453,12 @@ def case_learner_grow(golden, dev, fname, model, device_alpha=False):
     for i, (a, b) in enumerate(zip(losses, g["losses"])):
         assert abs(a - b) < (1e-4 if i == 0 else 5e-4) * max(1.0, abs(b)), (i, a, b)
     free = g["iters"] - max(g["iter_snaps"])           # iterations run since the last re-synchronisation with the reference
-    frac = 0.01 if free <= 1 else 0.05
-    _adam_close(L.gen_model.state_dict(), g["g_sd1"], lr_max, per, "G", frac=frac)
-    _adam_close(L.disc_model.state_dict(), g["d_sd1"], lr_max, per, "D", frac=frac)
+    if free <= 1:
+        _adam_close(L.gen_model.state_dict(), g["g_sd1"], lr_max, per, "G", frac=0.05, big=0.25 * lr_max)
+        _adam_close(L.disc_model.state_dict(), g["d_sd1"], lr_max, per, "D", frac=0.01)
+    else:       # free-running iterations: see the per-iteration checks above
+        _adam_close(L.gen_model.state_dict(), g["g_sd1"], lr_max, per, "G", frac=0.05 * free, big=0.25 * lr_max)
+        _adam_close(L.disc_model.state_dict(), g["d_sd1"], lr_max, per, "D", frac=0.05 * free, big=0.25 * lr_max)
     lag = dict(L.gen_model_lagged.named_parameters())
     assert set(lag.keys()) == set(g["lagged"].keys())
     _adam_close(lag, g["lagged"], lr_max, g["iters"], "EWMA-G", frac=0.01)
@@ -896,6 +914,17 @@ def _perturb_zero_params(module, gen):
                 p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
 
 
+class _CapturableTape(TapeSource):
+    """Taped draws handed out as CLONES made on the current (capturing) stream: a leaf tensor that was created on the legacy
+    default stream would make autograd synchronise that stream with the capture."""
+
+    def randn(self, shape, device):
+        return TapeSource.randn(self, shape, device).clone()
+
+    def rand(self, shape, device):
+        return TapeSource.rand(self, shape, device).clone()
+
+
 def cfg2_fullwidth_learner(g, dev):
     """The drop-in StyleGANLearner at cfg2's real size rebuilt from the fixture's seeds: bit-identical initial weights and real
     batch (sha256 digests asserted), without the fixture having to carry 49 M parameters."""
@@ -929,7 +958,8 @@ def case_cfg2_fullwidth_step(golden, dev, impl, graph):
     L, data = cfg2_fullwidth_learner(g, dev)
     G, D = L.gen_model, L.disc_model
     x = data.to(dev)
-    tape = [(k, v.to(dev) if torch.is_tensor(v) else v) for k, v in g["tape"]]
+    on_dev = lambda events: [(k, v.to(dev) if (torch.is_tensor(v) and k != "randint") else v) for k, v in events]   # the mixing cut-off is a host draw
+    tape = on_dev(g["tape"])
     K.set_conv_impl(impl)
     out = {}
     try:
@@ -953,9 +983,10 @@ def case_cfg2_fullwidth_step(golden, dev, impl, graph):
         out["gp_grads_worst"] = max(cmp.items(), key=lambda kv: kv[1]["l2"])[0]
         out["gp_per_tensor"] = cmp
         D.zero_grad(set_to_none=True)
+        del pen, xr         # (a live autograd graph would keep the parameters' AccumulateGrad nodes bound to this stream: no capture later)
         # ---- the generator step's forward / backward on the initial weights (no Adam step in front of it)
         ga = g["g_alone"]
-        set_random_source(TapeSource([(k, v.to(dev) if torch.is_tensor(v) else v) for k, v in ga["tape"]], dev))
+        set_random_source(TapeSource(on_dev(ga["tape"]), dev))
         for p in D.parameters():
             p.requires_grad_(False)
         img = G(ga["z"].to(dev))
@@ -1000,7 +1031,7 @@ def case_cfg2_fullwidth_step(golden, dev, impl, graph):
                     p.copy_(dict(G.named_parameters())[n])
             G.w_ewma = None
             K.weights_updated()
-            set_random_source(TapeSource(tape, dev))
+            set_random_source(_CapturableTape(tape, dev))
             ld, lg = L.main_iteration(x)                   # capture + first replay
             assert L._graph is not None
             torch.cuda.synchronize()

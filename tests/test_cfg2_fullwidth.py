@@ -28,9 +28,19 @@ def _dump(tag, out):
             json.dump(out, f, indent=1)
 
 
-# Bounds = multiples of the reference's OWN noise floor at this size (fixture key `self_noise`: the unmodified reference re-run
-# with every weight moved by one fp32 ulp; worst tensor per class), never below a base value.  (loss base, gradient multiple)
-BOUNDS = {"fp32": (1e-4, 4.0), "tf32": (3e-3, 12.0)}
+# Bounds.  fp32 path: multiples of the reference's OWN noise floor at this size (fixture key `self_noise`: the unmodified
+# reference re-run on the CPU with every weight moved by one fp32 ulp; worst tensor per class).  TF32 path: multiples of what the
+# unmodified reference ITSELF deviates by when it runs on the B200 through stock PyTorch with its default cuDNN-TF32 convolutions
+# (tests/golden/cfg2_reference_on_b200_deviation.json, measured by tests/calibrate_tf32_bounds.py on the same fixture): at random
+# initialisation leaky-ReLU masks within rounding of zero and mean-removing InstanceNorms amplify a 5e-4 operand rounding to
+# 2-8 % (median over tensors) / up to 80 % (cancellation-dominated bias gradients of the R1 penalty) in ANY TF32 implementation.
+FP32_LOSS, FP32_MULT = 1e-4, 4.0
+TF32_MULT = 1.6
+
+
+def _tf32_yardstick():
+    with open(os.path.join(os.path.dirname(__file__), "golden", "cfg2_reference_on_b200_deviation.json")) as f:
+        return json.load(f)["reference_cudnn_tf32"]
 
 
 @pytest.mark.gpu
@@ -38,21 +48,34 @@ BOUNDS = {"fp32": (1e-4, 4.0), "tf32": (3e-3, 12.0)}
 def test_cfg2_fullwidth_step_vs_reference(golden, impl, graph):
     out = PC.case_cfg2_fullwidth_step(golden, DEV, impl, graph)
     _dump(f"{impl}_{'graph' if graph else 'eager'}", out)
-    floor = golden("style_cfg2_fullwidth_step.pt")["self_noise"]
-    b_loss, mult = BOUNDS[impl]
     msg = {k: v for k, v in out.items() if not k.endswith("per_tensor")}
-    assert out["loss_d"] < b_loss and out["g_alone_loss"] < b_loss, msg
-    assert out["loss_g"] < max(b_loss, mult * floor["loss_g"]), msg          # behind the discriminator's first Adam step
-    assert out["gp_value"] < max(10 * b_loss, mult * floor["gp_value"]), msg
-    assert out["g_alone_img_l2"] < 10 * b_loss and out["g_alone_logits"] < 10 * b_loss, msg
-    for key, fl in (("gp_grads", floor["gp_grads"]), ("g_alone_grads", floor["g_alone_grads"]), ("d_grads", floor["d_grads"]),
-                    ("g_grads", floor["g_grads"])):
+    if impl == "fp32":
+        floor = golden("style_cfg2_fullwidth_step.pt")["self_noise"]
+        mult = FP32_MULT
+        assert out["loss_d"] < FP32_LOSS and out["g_alone_loss"] < FP32_LOSS, msg
+        assert out["loss_g"] < max(FP32_LOSS, mult * floor["loss_g"]), msg          # behind the discriminator's first Adam step
+        assert out["gp_value"] < max(10 * FP32_LOSS, mult * floor["gp_value"]), msg
+        assert out["g_alone_img_l2"] < 10 * FP32_LOSS and out["g_alone_logits"] < 10 * FP32_LOSS, msg
+        assert out["w_ewma"] < 10 * FP32_LOSS, msg
+        flips = 0.03
+    else:
+        floor = _tf32_yardstick()
+        mult = TF32_MULT
+        base = 1e-3          # never tighter than this: the yardstick's own small entries are single draws
+        assert out["loss_d"] < max(base, mult * floor["loss_d"]) and out["g_alone_loss"] < max(base, mult * floor["g_alone_loss"]), msg
+        assert out["loss_g"] < max(3 * base, 4 * floor["loss_g"]), msg              # behind the discriminator's first Adam step
+        assert out["gp_value"] < max(5 * base, 4 * floor["gp_value"]), msg
+        assert out["g_alone_img_l2"] < mult * floor["g_alone_img"]["l2"], msg
+        assert out["g_alone_logits"] < mult * floor["g_alone_logits"], msg
+        assert out["w_ewma"] < 2e-3, msg
+        flips = max(0.03, mult * floor["p1_flip_fraction"])
+    for key in ("gp_grads", "g_alone_grads", "d_grads", "g_grads"):
+        fl = floor[key]
         assert out[key + "_l2"] < mult * fl["l2"], (key, out[key + "_l2"], fl, msg)
         assert out[key + "_smax"] < mult * fl["smax"], (key, out[key + "_smax"], fl, msg)
     assert out["p1_max_abs_diff_over_lr"] <= 2.001, msg
-    assert out["p1_flip_fraction"] < (0.03 if impl == "fp32" else 0.10), msg
+    assert out["p1_flip_fraction"] < flips, msg
     assert out["lagged_rel_err"] < 5e-7, msg
-    assert out["w_ewma"] < 10 * b_loss, msg
 
 
 def test_cfg2_fullwidth_fixture_is_reproducible_from_its_seeds(golden):

@@ -302,8 +302,11 @@ def test_pixelnorm_latents():
     both("pixelnorm_bwd", gy, x, 1e-8)
 
 
-@pytest.mark.parametrize("N,C,H,W", [(4, 32, 8, 8), (8, 512, 4, 4), (2, 128, 64, 64), (2, 16, 128, 128), (3, 64, 16, 16)])
-def test_style_epilogue_vs_contract(N, C, H, W):
+@pytest.mark.parametrize("mode", ["0", "1", "2"])       # three kernels / one sample-ordered kernel (default) / cluster kernels
+@pytest.mark.parametrize("N,C,H,W", [(4, 32, 8, 8), (8, 512, 4, 4), (2, 128, 64, 64), (2, 16, 128, 128), (3, 64, 16, 16),
+                                     (8, 128, 128, 128), (5, 8, 32, 32)])
+def test_style_epilogue_vs_contract(N, C, H, W, mode, monkeypatch):
+    monkeypatch.setenv("GLB_SE_MODE", mode)
     x, noise, nw, b = cl(rn(N, C, H, W)), rn(N, 1, H, W, seed=1), rn(C, seed=2) * .3, rn(C, seed=3) * .3
     style, gout = rn(N, 2 * C, seed=4), cl(rn(N, C, H, W, seed=5))
     out_g, stats = K.style_epilogue_fwd(x.to(DEV), noise.to(DEV), nw.to(DEV), b.to(DEV), style.to(DEV), 0.2, 1e-8)
