@@ -38,6 +38,11 @@ WORKLOAD_NAME = {
 
 
 # ----------------------------------------------------------------------------------------------- helpers
+def workload_config(name, per_gpu_batch, world):
+    """The `config` object of BOTH arms (ours and --impl reference): what is computed, nothing about how."""
+    return {"workload": WORKLOAD_NAME[name], "global_batch": per_gpu_batch * world, "parallelism": f"dp{world}"}
+
+
 def conv_flops_per_iter(model, res, bs):
     """Algorithmic conv/linear FLOPs of one main iteration = 4 F_G + 14 F_D."""
     import math
@@ -109,6 +114,44 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tf": 1400.0, "src": "fallback"}
 
 
+def measured_mma_peaks():
+    """tcgen05 issue peaks measured on this pool's B200 by tools/micro/mma_peak.cu (every SM issuing back-to-back M128 N256 MMAs
+    from shared memory; CUDA events): the committed run in profiles/."""
+    p = ROOT / "profiles" / "r2_mma_peak_tcgen05.txt"
+    out = {"tf32": 1115.0, "bf16": 2234.0}
+    try:
+        d = json.loads([ln for ln in p.read_text().splitlines() if ln.startswith("{")][-1])
+        out = {"tf32": d["tf32_tflops_sustained"], "bf16": d["bf16_mma_tflops_sustained"]}
+    except Exception:
+        pass
+    return out
+
+
+def ncu_traffic():
+    """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant convolution kernel, read from
+    the committed `ncu --set full` capture (profiles/r2_ncu_full_conv_dominant.csv, raw page, one row per launch)."""
+    import csv
+    p = ROOT / "profiles" / "r2_ncu_full_conv_dominant.csv"
+    if not p.exists():
+        return {"traffic": None, "traffic_note": "no committed ncu capture"}
+    try:
+        rows = list(csv.reader(p.open()))
+        hdr = rows[0]
+        body = [r for r in rows[1:] if len(r) == len(hdr) and r[hdr.index("ID")].strip().isdigit()]
+        rd, wr, nm = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        unit = rows[1] if rows[1][hdr.index("ID")].strip() == "" else None          # units row of the raw page
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        def val(r, i):
+            u = unit[i] if unit else "byte"
+            return float(r[i].replace(",", "")) * scale.get(u, 1.0)
+        tr = [val(r, rd) + val(r, wr) for r in body]
+        return {"traffic": sum(tr) / len(tr),
+                "traffic_note": f"mean over {len(tr)} launches of {body[0][nm][:60]} in profiles/r2_ncu_full_conv_dominant.csv "
+                                "(dram__bytes_read.sum + dram__bytes_write.sum)"}
+    except Exception as e:          # noqa: BLE001
+        return {"traffic": None, "traffic_note": "ncu csv unreadable: " + repr(e)[:120]}
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path on the box's host cores, all host threads.
@@ -128,10 +171,7 @@ def run_reference(args):
         return run_reference_on_gpu(args, model, res, bs, alpha)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    total_steps = args.steps + args.warmup
-    sample_bs = bs
-    if total_steps > 8 and bs >= 8:
-        sample_bs = 4            # bounded sample: half batch (keeps one full minibatch-stddev group of 4)
+    sample_bs = bs               # the full per-GPU batch of the workload: same configuration as our arm (~5 s per step on 16 cores)
     from oracle.reference_loader import reference_available
     kind = "reference" if (reference_available() and alpha is None) else "port"
     if kind == "reference":
@@ -145,11 +185,12 @@ def run_reference(args):
         one()
     dt = time.perf_counter() - t0
     val = sample_bs * args.steps / dt
-    sample = f"{args.steps} main iterations (1 D step + 1 G step) at batch {sample_bs} of the {bs}-per-GPU workload, after {args.warmup} warm-up"
+    sample = (f"{args.steps} main iterations (1 D step + 1 G step) at the workload's full batch {sample_bs}, after {args.warmup} warm-up, "
+              f"{threads} torch threads")
     line = {"impl": "reference", "metric": "StyleGAN G+D train img/s", "value": val, "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME[args.config], "note": note},
+            "config": workload_config(args.config, bs, 1), "details": {"note": note},
             "cpu_baseline": {"value": val, "unit": "img/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -166,9 +207,10 @@ def run_reference_on_gpu(args, model, res, bs, alpha):
     from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, TensorDataset
     from oracle.reference_loader import load_reference, make_config, reference_available, REFERENCE_ROOT
     if not reference_available() or alpha is not None or model == "ResNet GAN" or not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable": "reference-on-GPU needs baseline/_ref, a CUDA device and a "
-                          "fixed-resolution StyleGAN / ProGAN config"}), flush=True)
-        return
+        if not getattr(args, "_embed", False):
+            print(json.dumps({"impl": "reference", "unavailable": "reference-on-GPU needs baseline/_ref, a CUDA device and a "
+                              "fixed-resolution StyleGAN / ProGAN config"}), flush=True)
+        return None
     ref = load_reference()
     torch.manual_seed(0)
     cfg = make_config(model, res=res, init_res=res, batch_size=bs, dev="cuda", metrics_dev=torch.device("cuda"))
@@ -191,11 +233,13 @@ def run_reference_on_gpu(args, model, res, bs, alpha):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (stock PyTorch defaults: cuDNN TF32 allowed, matmul fp32)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME[args.config],
-                       "note": f"UNMODIFIED reference (gan_lab {REFERENCE_ROOT}) Learner.train with dev=cuda: stock PyTorch eager on "
-                               f"the B200, torch {torch.__version__}"},
+            "config": workload_config(args.config, bs, 1),
+            "details": {"note": f"UNMODIFIED reference (gan_lab {REFERENCE_ROOT}) Learner.train with dev=cuda: stock PyTorch eager on "
+                                f"the B200, torch {torch.__version__}"},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": bs * 3 * res * res * 4, "d2h_bytes_per_step": 8}}
-    print(json.dumps(line), flush=True)
+    if not getattr(args, "_embed", False):
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def _reference_stepper(model, res, bs, steps, warmup):
@@ -366,13 +410,18 @@ def run_ours(args):
     if sampler:
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     ev[0].record()
+    step_ev[0].record()
     for i in range(args.steps):
         main_iter(pool_dev[i % n_pool])
+        step_ev[i + 1].record()
     ev[1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[1])
+    per_step = sorted(step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps))
+    ms_median = per_step[len(per_step) // 2]
     log(f"timed region done: {ms / args.steps:.2f} ms/step")
     launches = launches_per_iter * args.steps   # kernels of this repo per main iteration (counted on an eager iteration) x steps
     if sampler:
@@ -452,8 +501,9 @@ def run_ours(args):
             "metric": "StyleGAN G+D train img/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32" if args.conv_impl == "tf32" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME[args.config], "global_batch": bs * world, "parallelism": f"dp{world}",
-                       "conv_impl": args.conv_impl, "cuda_graphs": use_graphs,
+            "config": workload_config(args.config, bs, world),
+            "ms_per_step_median": ms_median, "value_from_median_step": bs * cfg.num_disc_iters * world / (ms_median / 1e3),
+            "details": {"conv_impl": args.conv_impl, "cuda_graphs": use_graphs,
                        "r1_shares_real_forward": bool(getattr(L, "share_penalty_forward", False)),
                        "d_fake_real_one_pass": bool(getattr(L, "batch_d_passes", False)),
                        "grad_allreduce": (f"NCCL all-reduce, {L.dp.bucket_bytes >> 20} MiB buckets launched from grad hooks as they fill"
@@ -468,15 +518,14 @@ def run_ours(args):
         if roof is not None:
             roof["peak"] = peaks["tf"]
             roof["frac"] = roof["achieved"] / peaks["tf"]
+            mma = measured_mma_peaks()
             roof["peak_source"] = ("of " + peaks["src"] + " dense bf16 cuBLAS peak (sustained figure: kernels timed inside a long "
-                                   "step); operands are TF32, whose dense peak is half of bf16 -> frac_of_tf32_peak")
-            roof["frac_of_tf32_peak"] = roof["achieved"] / (peaks["tf"] / 2)
+                                   "step); operands are TF32 -> frac_of_tf32_mma_peak is against the MEASURED tcgen05 kind::tf32 issue "
+                                   "peak of this chip (tools/micro/mma_peak.cu, profiles/r2_mma_peak_tcgen05.txt)")
+            roof["tf32_mma_peak"] = mma["tf32"]
+            roof["frac_of_tf32_mma_peak"] = roof["achieved"] / mma["tf32"]
             if args.config == "cfg2":
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (a 64x64, 512-channel
-                # layer, 101 us) from the committed `ncu --set full` capture: = that layer's input + output, no re-reads
-                roof["traffic"] = 149.55e6
-                roof["traffic_note"] = ("bytes per launch of conv_fprop_tc2_kernel<256> (profiles/r1_ncu_full_tc2.csv: 68.5 MB read + "
-                                        "81.0 MB written; algorithmic 67.1 MB in + 4.7 MB weights + 67.1 MB out)")
+                roof.update(ncu_traffic())
             line["roofline"] = roof
         if glue is not None and glue["achieved"] is not None:
             glue["peak"] = peaks["hbm_gbs"]
@@ -487,6 +536,21 @@ def run_ours(args):
             line["roofline_input"] = input_pipeline_roofline(peaks)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+            # SURVEY.md 8d "the real bar to beat": the UNMODIFIED reference through stock PyTorch (cuDNN / cuBLAS / ATen) on this
+            # same B200, same workload, 3 iterations after 3 warm-up (~1.5 s each)
+            try:
+                L._graph = None
+                del L
+                import gc
+                gc.collect(); torch.cuda.empty_cache()
+                sub = argparse.Namespace(**vars(args)); sub.steps, sub.warmup, sub._embed, sub.ref_dev = 3, 3, True, "cuda"
+                ref_line = run_reference_on_gpu(sub, model, res, bs, alpha)
+                if ref_line is not None:
+                    line["torch_eager_b200"] = {"value": ref_line["value"], "unit": "img/s", "ms_per_step": ref_line["ms_per_step"],
+                                                "steps": 3, "note": ref_line["details"]["note"],
+                                                "speedup_of_this_repo": line["e2e"]["value"] / ref_line["value"]}
+            except Exception as e:          # noqa: BLE001 -- an auxiliary figure must not take the bench line down
+                line["torch_eager_b200"] = {"error": repr(e)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured NCCL work keeps the communicator busy: drop the graphs first, then tear down; never let a stuck
@@ -504,7 +568,7 @@ def run_ours(args):
 
 def run_resnet(args, cfg, rank, world, dev):
     """cfg5: the ResNet GAN loop (reference resnetgan/learner.py:463-776): per main iteration 1 generator step, then 5
-    discriminator steps; eager launches (this path is not CUDA-graph captured yet).  Same JSON contract; the algorithmic
+    discriminator steps, each step replayed as a CUDA graph.  Same JSON contract; the algorithmic
     conv FLOPs are the ones the recorded conv launches execute (nothing is shared or skipped on this path)."""
     import torch
     import torch.distributed as dist
@@ -523,7 +587,7 @@ def run_resnet(args, cfg, rank, world, dev):
     pool_host = [(torch.rand(bs, 3, res, res) * 2 - 1).pin_memory() for _ in range(nd)]
     flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)
 
-    resnet_graphs = os.environ.get("GLB_RESNET_GRAPHS", "0") != "0"     # opt-in until measured: CUDA-graph replay of the steps
+    resnet_graphs = os.environ.get("GLB_RESNET_GRAPHS", "1") != "0" and not args.no_graphs   # measured on B200: 3081 vs 2603 img/s
     if resnet_graphs:
         L.enable_cuda_graphs(True, warmup_iters=3)
 
@@ -571,16 +635,26 @@ def run_resnet(args, cfg, rank, world, dev):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    roof, glue = kernel_rooflines(L, pool_dev, lambda pool: main_iter(pool), flush) if rank == 0 else (None, None)
+    def eager_iter(pool):
+        for p in L.disc_model.parameters():
+            p.requires_grad_(False)
+        lg = L.gen_step()
+        for p in L.disc_model.parameters():
+            p.requires_grad_(True)
+        for x in pool:
+            ld = L.disc_step(x)
+        return ld, lg
+
+    roof, glue = kernel_rooflines(L, pool_dev, eager_iter, flush) if rank == 0 else (None, None)
     if rank == 0:
         peaks = measured_peaks()
         imgs = bs * nd * args.steps * world
         line = {"metric": "ResNet GAN G+D train img/s", "value": imgs / (ms / 1e3), "unit": "img/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.conv_impl == "tf32" else "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD_NAME[args.config], "global_batch": bs * world, "parallelism": f"dp{world}",
-                           "conv_impl": args.conv_impl, "cuda_graphs": False,
-                           "l2": "activations per step (> 1 GB) exceed the 126 MB L2"},
+                "config": workload_config(args.config, bs, world),
+                "details": {"conv_impl": args.conv_impl, "cuda_graphs": resnet_graphs,
+                            "l2": "activations per step (> 1 GB) exceed the 126 MB L2"},
                 "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": nd * bs * 3 * res * res * 4,
                         "d2h_bytes_per_step": 8},
                 "gpu_launches": launches_per_iter * args.steps, "clocks": sampler.summary() if sampler else None}
@@ -791,21 +865,23 @@ def kernel_rooflines(L, x, main_iter, flush):
 
 
 def cpu_baseline(args):
-    """The reference's CPU path timed on this box's host cores on a bounded sample (1 main iteration of the workload at
-    batch 4): the unmodified reference from baseline/_ref when present (kind "reference"), else the oracle port."""
+    """The reference's CPU path timed on this box's host cores on a bounded sample (2 main iterations of the workload at its
+    full batch after 1 warm-up, ~15 s): the unmodified reference from baseline/_ref when present (kind "reference"), else the
+    oracle port."""
     import torch
     from oracle.reference_loader import reference_available
     model, res, init_res, bs, alpha = CONFIGS[args.config]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sbs = 4
+    sbs = bs // 4 if args.config == "cfg4" else bs
     kind = "reference" if (reference_available() and alpha is None) else "port"
-    one, note = _reference_stepper(model, res, sbs, 1, 0) if kind == "reference" else _port_stepper(model, res, sbs)
-    t0 = time.perf_counter()
+    one, note = _reference_stepper(model, res, sbs, 2, 1) if kind == "reference" else _port_stepper(model, res, sbs)
     one()
-    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    one(); one()
+    dt = (time.perf_counter() - t0) / 2
     return {"value": sbs / dt, "unit": "img/s", "cores": threads, "kind": kind,
-            "sample": f"1 main iteration (D step + G step) at batch {sbs} of the same workload, no warm-up, {threads} torch threads; {note}"}
+            "sample": f"2 main iterations (D step + G step) at the workload's full batch {sbs} after 1 warm-up, {threads} torch threads; {note}"}
 
 
 def main():
@@ -814,8 +890,8 @@ def main():
         faulthandler.dump_traceback_later(int(os.environ["GLB_BENCH_FAULT"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-dev", default="cpu", choices=["cpu", "cuda"],
                     help="with --impl reference: cpu = the contract's reference arm (host cores); cuda = the unmodified "

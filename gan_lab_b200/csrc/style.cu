@@ -709,7 +709,9 @@ __global__ void __launch_bounds__(CTPB) se_bwd_cluster_kernel(const float4* __re
 // cluster size for an H*W plane: the smallest power of two <= 8 that brings a CTA's part of a 16-channel slab to <= 64 KB
 // (two CTAs per SM), else 8 with up to 200 KB; 0 = the plane does not fit (three-kernel path)
 int sec_cluster(int HW) {
-  for (int cl = 1; cl <= 8; cl <<= 1)
+  int max_cl = 8;
+  if (const char* e = getenv("GLB_SE_CL16")) if (atoi(e) != 0) max_cl = 16;   // non-portable cluster size (A/B experiment)
+  for (int cl = 1; cl <= max_cl; cl <<= 1)
     if (HW % cl == 0 && (int64_t)(HW / cl) * CS * 4 <= 64 * 1024) return cl;
   if (HW % 8 == 0 && (int64_t)(HW / 8) * CS * 4 <= 200 * 1024) return 8;
   return 0;
@@ -721,6 +723,7 @@ int sec_launch(Kern kern, const char* name, int N, int HW, int C, int CL, cudaSt
   static size_t configured = 0;                        // per kernel instantiation (Kern differs)
   if (smem > configured) {
     GLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = 200 * 1024;
   }
   cudaLaunchConfig_t cfg = {};
@@ -750,14 +753,20 @@ int se_chunk(int N, int HW, int C) {
   return (int)chunk;
 }
 
-// GLB_SE_MODE: 0 = three kernels, 1 = one sample-ordered kernel (default), 2 = cluster kernels where the plane fits
-// (A/B measurements; the parity tests run all three).  GLB_SE_3PASS=1 is the older spelling of mode 0.
+// GLB_SE_MODE: 0 = three kernels, 1 = one sample-ordered kernel, 2 = cluster kernels wherever the plane fits, 3 (default) = per
+// size, whichever measured faster on B200 (tools/glue_bw.py, N = 8): cluster kernels for planes up to 32 x 32 forward / 64 x 64
+// backward, three kernels above.  The parity tests run modes 0-2 on every shape.
 int se_mode() {
-  if (const char* e = getenv("GLB_SE_3PASS")) if (atoi(e) != 0) return 0;
   if (const char* e = getenv("GLB_SE_MODE")) return atoi(e);
-  return 1;
+  return 3;
 }
-bool se_force_3pass() { return se_mode() != 2; }
+bool se_use_cluster(int HW, bool backward) {
+  const int m = se_mode();
+  if (m == 2) return true;
+  if (m != 3) return false;
+  if (const char* e = getenv("GLB_SE_CL16")) if (atoi(e) != 0) return true;     // A/B: 16-CTA clusters make every cfg2 plane fit 64 KB
+  return HW <= (backward ? 4096 : 1024);
+}
 
 int se_geom(SE& g, int N, int H, int W, int C, float slope) {
   if (C % 4 != 0 || C / 4 > TPB || TPB % (C / 4) != 0) return shape_fail("style_epilogue: C/4 must divide 256");
@@ -797,7 +806,7 @@ extern "C" int glb_style_epilogue_fwd(const float* x, const float* noise, const 
                                       const float* style, float* out, float* stats, float* work, int N, int H, int W, int C,
                                       float slope, float eps, glb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (const int CL = (C % CS == 0 && N <= 65535 && !se_force_3pass()) ? sec_cluster(H * W) : 0) {
+  if (const int CL = (C % CS == 0 && N <= 65535 && se_use_cluster(H * W, false)) ? sec_cluster(H * W) : 0) {
     SEC c{N, H * W, C, H * W / CL, slope, eps};
     return sec_launch(se_fwd_cluster_kernel, "se_fwd_cluster_kernel", N, H * W, C, CL, st, (const float4*)x, noise,
                       (const float4*)noise_weight, (const float4*)bias, style, (float4*)out, stats, c);
@@ -829,7 +838,7 @@ extern "C" int glb_style_epilogue_bwd(const float* gout, const float* x, const f
                                       float* g_noise_weight, float* g_bias, float* work, int N, int H, int W, int C, float slope,
                                       glb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (const int CL = (C % CS == 0 && N <= 65535 && !se_force_3pass()) ? sec_cluster(H * W) : 0) {
+  if (const int CL = (C % CS == 0 && N <= 65535 && se_use_cluster(H * W, true)) ? sec_cluster(H * W) : 0) {
     SEC c{N, H * W, C, H * W / CL, slope, 0.f};
     return sec_launch(se_bwd_cluster_kernel, "se_bwd_cluster_kernel", N, H * W, C, CL, st, (const float4*)gout, (const float4*)x,
                       noise, (const float4*)noise_weight, (const float4*)bias, style, stats, (float4*)gx, gstyle, g_noise_weight,
