@@ -129,16 +129,18 @@ def measured_mma_peaks():
 
 def ncu_traffic():
     """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant convolution kernel, read from
-    the committed `ncu --set full` capture (profiles/r2_ncu_full_conv_dominant.csv, raw page, one row per launch)."""
+    the committed `ncu --set full` capture (profiles/r2_ncu_full_conv_family.csv, raw page, one row per launch; the rows of
+    conv_fprop_tc2_halo_kernel<256>, the kernel with the largest share of the step)."""
     import csv
-    p = ROOT / "profiles" / "r2_ncu_full_conv_dominant.csv"
+    p = ROOT / "profiles" / "r2_ncu_full_conv_family.csv"
     if not p.exists():
         return {"traffic": None, "traffic_note": "no committed ncu capture"}
     try:
         rows = list(csv.reader(p.open()))
         hdr = rows[0]
-        body = [r for r in rows[1:] if len(r) == len(hdr) and r[hdr.index("ID")].strip().isdigit()]
         rd, wr, nm = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        body = [r for r in rows[1:] if len(r) == len(hdr) and r[hdr.index("ID")].strip().isdigit()
+                and "conv_fprop_tc2_halo_kernel<256>" in r[nm]]
         unit = rows[1] if rows[1][hdr.index("ID")].strip() == "" else None          # units row of the raw page
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         def val(r, i):
@@ -146,7 +148,7 @@ def ncu_traffic():
             return float(r[i].replace(",", "")) * scale.get(u, 1.0)
         tr = [val(r, rd) + val(r, wr) for r in body]
         return {"traffic": sum(tr) / len(tr),
-                "traffic_note": f"mean over {len(tr)} launches of {body[0][nm][:60]} in profiles/r2_ncu_full_conv_dominant.csv "
+                "traffic_note": f"mean over {len(tr)} launches of conv_fprop_tc2_halo_kernel<256> in profiles/r2_ncu_full_conv_family.csv "
                                 "(dram__bytes_read.sum + dram__bytes_write.sum)"}
     except Exception as e:          # noqa: BLE001
         return {"traffic": None, "traffic_note": "ncu csv unreadable: " + repr(e)[:120]}
@@ -500,7 +502,7 @@ def run_ours(args):
         line = {
             "metric": "StyleGAN G+D train img/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if args.conv_impl == "tf32" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.conv_impl], "data": "synthetic",
             "config": workload_config(args.config, bs, world),
             "ms_per_step_median": ms_median, "value_from_median_step": bs * cfg.num_disc_iters * world / (ms_median / 1e3),
             "details": {"conv_impl": args.conv_impl, "cuda_graphs": use_graphs,
@@ -671,7 +673,7 @@ def run_resnet(args, cfg, rank, world, dev):
         os._exit(0)
 
 
-GLUE_LAUNCHERS = ("bias_act_fwd", "act_bwd", "blur_act_bwd", "axpby", "colsum", "scale_by", "pixelnorm_fwd", "pixelnorm_bwd", "blur3x3",
+GLUE_LAUNCHERS = ("cvt_bf16", "bias_act_fwd", "act_bwd", "blur_act_bwd", "axpby", "colsum", "scale_by", "pixelnorm_fwd", "pixelnorm_bwd", "blur3x3",
                   "upsample2x_fwd", "upsample2x_bwd", "pool_bias_act_fwd", "pool_bias_act_bwd", "style_epilogue_fwd",
                   "style_epilogue_bwd", "rgb_expand", "rgb_contract", "rgb_wgrad", "fade_up_blend", "fade_up_blend_bwd",
                   "fade_real", "interp_rows", "batchnorm_fwd", "batchnorm_bwd", "layernorm_fwd", "layernorm_bwd",
@@ -763,10 +765,13 @@ def kernel_rooflines(L, x, main_iter, flush):
         sizes, ewma_mode = a[1], a[-1]
         return float(sizes.sum().item()) * (28.0 + (8.0 if ewma_mode else 0.0))
 
+    def f_cvt(a, k, out):
+        return 6.0 * out.numel()
+
     conv_kinds = ("conv_fprop", "conv_dgrad", "conv_wgrad")
     wrap("conv_fprop", f_fprop); wrap("conv_dgrad", f_dgrad); wrap("conv_wgrad", f_wgrad)
     for name in GLUE_LAUNCHERS:
-        wrap(name, f_adam if name == "adam_ewma_multi" else nbytes)
+        wrap(name, f_adam if name == "adam_ewma_multi" else (f_cvt if name == "cvt_bf16" else nbytes))
     dp, L.dp = L.dp, None          # rank-local pass: no collective may run here (the other ranks are not in it)
     if dp is not None:
         dp.enabled = False         # ... including the ones the gradient hooks would launch
@@ -834,7 +839,8 @@ def kernel_rooflines(L, x, main_iter, flush):
     tot_f = sum(v[0] for v in by.values())
     tot_ms = sum(v[1] for v in by.values())
     n_launch = sum(v[2] for v in by.values())
-    conv = {"bound": "tensor", "kernel": "conv2d fprop/dgrad/wgrad family (tcgen05 TF32 implicit GEMM; FFMA for uncovered shapes)",
+    conv = {"bound": "tensor", "kernel": "conv2d fprop/dgrad/wgrad family (tcgen05 implicit GEMM, operands " + K.get_conv_impl() +
+                                       "; FFMA for uncovered shapes; bf16 mode: the operand conversion passes are counted under glue)",
             "achieved": tot_f / (tot_ms / 1e3) / 1e12, "unit": "TFLOP/s", "traffic": None, "launches": n_launch,
             "avg_launch_us": 1e3 * tot_ms / max(n_launch, 1), "conv_ms_per_step": tot_ms,
             "by_kind_tflops": {n: v[0] / (v[1] / 1e3) / 1e12 for n, v in by.items()}}
@@ -897,7 +903,8 @@ def main():
                     help="with --impl reference: cpu = the contract's reference arm (host cores); cuda = the unmodified "
                          "reference through stock PyTorch on the GPU (an extra comparison, never the default)")
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
-    ap.add_argument("--conv-impl", default=os.environ.get("GLB_CONV_IMPL", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--conv-impl", default=os.environ.get("GLB_CONV_IMPL", "tf32"), choices=["fp32", "tf32", "bf16"],
+                    help="tf32 (default; the precision BASELINE.json names) | bf16 (opt-in: bf16 GEMM operands, fp32 everything else) | fp32 (exact FFMA)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress lines on stderr")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay of the D/G steps")

@@ -20,9 +20,12 @@ _state = {"conv_impl": "fp32", "launches": 0}
 
 def set_conv_impl(mode: str):
     """'fp32' = exact FFMA implicit GEMM everywhere; 'tf32' = tcgen05 tensor-core kernels wherever the
-    shape is covered (TF32 operands, fp32 accumulation), FFMA kernels for the rest."""
-    assert mode in ("fp32", "tf32")
+    shape is covered (TF32 operands, fp32 accumulation), FFMA kernels for the rest; 'bf16' = tcgen05 kind::f16 on bf16
+    copies of the two GEMM operands (round to nearest; fp32 accumulation, bias, activation and storage) wherever THAT is
+    covered (channel counts multiples of 64), the 'tf32' choice elsewhere."""
+    assert mode in ("fp32", "tf32", "bf16")
     _state["conv_impl"] = mode
+    weights_updated()
 
 
 def get_conv_impl() -> str:
@@ -81,10 +84,22 @@ def tc_covers(kind: str, N, H, W, Ci, Co, R, S, pad) -> bool:
     return bool(LIB.fn("glb_conv2d_tc_covers")(_KIND[kind], N, H, W, Ci, Co, R, S, pad))
 
 
+def _tc_mode() -> bool:
+    return _state["conv_impl"] in ("tf32", "bf16")
+
+
 def _impl_for(kind, N, H, W, Ci, Co, R, S, pad):
-    if _state["conv_impl"] == "tf32" and tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+    if _tc_mode() and tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
         return IMPL_TF32
     return IMPL_FP32
+
+
+def bf16_covers(kind: str, N, H, W, Ci, Co, R, S, pad) -> bool:
+    return bool(LIB.fn("glb_conv2d_bf16_covers")(_KIND[kind], N, H, W, Ci, Co, R, S, pad))
+
+
+def _use_bf16(kind, N, H, W, Ci, Co, R, S, pad) -> bool:
+    return _state["conv_impl"] == "bf16" and bf16_covers(kind, N, H, W, Ci, Co, R, S, pad)
 
 
 _wt_cache = {}
@@ -95,6 +110,46 @@ def weights_updated():
     _wt_cache.clear()
     _wp_cache.clear()
     _pk_cache.clear()
+    _b16_cache.clear()
+
+
+# ---- bf16 operand copies (conv_impl "bf16") -----------------------------------------------------------------------------
+# One conversion pass per tensor and use site group: an activation is converted when its forward convolution runs and found
+# again by the weight-gradient kernel of the backward pass, an incoming gradient is shared by dgrad and wgrad; weights (and their
+# flipped / transposed copies) are converted once per optimiser step.  Entries keep their source tensor alive, so its address
+# cannot be recycled while the entry exists; everything is dropped at every optimiser step (weights_updated).
+_b16_cache = {}
+
+
+def cvt_bf16(t):
+    """fp32 -> bf16 (round to nearest even), same logical shape and memory format; one streaming pass (6 bytes per element)."""
+    _chk(t)
+    if not (t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))):
+        raise GlbError("cvt_bf16: the source must be dense in channels_last or contiguous layout")
+    out = torch.empty_strided(t.shape, t.stride(), device=t.device, dtype=torch.bfloat16)    # same element order as the source
+    _call("glb_cvt_f32_bf16", _p(t), _p(out), t.numel(), _stream())
+    return out
+
+
+def _to_bf16(t, tag=""):
+    key = (t.data_ptr(), tuple(t.shape), tag)
+    hit = _cache_get(_b16_cache, key, t._version)
+    if hit is not None:
+        return hit
+    out = cvt_bf16(t)
+    if len(_b16_cache) >= 512:
+        _b16_cache.clear()
+    return _cache_put(_b16_cache, key, t._version, out, t)
+
+
+def bf16_operand(t):
+    """bf16 copy of an NHWC activation / gradient (cached per tensor version)."""
+    return _to_bf16(nhwc(t))
+
+
+def bf16_weight(w, transposed=False):
+    """bf16 copy of the KRSC weights, or of their flipped / transposed copy (what dgrad multiplies by)."""
+    return _to_bf16(transposed_weight(w), "wt") if transposed else _to_bf16(nhwc(w), "w")
 
 
 def _cache_put(cache, key, version, tensor, w):
@@ -141,7 +196,7 @@ def _pad_ci(kind, N, H, W, Ci, Co, R, S, pad):
     miss the tensor-core kernels' Ci % 32 (fprop / wgrad) or Ci % 128 (dgrad output tile) rule and would drop to the FFMA
     implicit GEMM (58 us per launch at cfg2).  Zero-padding Ci up to a multiple of 128 is exact -- the extra input channels
     are zeros, the extra weight columns / gradient columns are dropped -- and ~4x faster.  Returns the padded Ci or None."""
-    if _state["conv_impl"] != "tf32" or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+    if not _tc_mode() or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
         return None
     if Ci < 32:
         cip = 32            # 3-channel image convolutions of the ResNet nets (FFMA kernel: 2.7 ms per wgrad launch at cfg5)
@@ -155,7 +210,7 @@ def _pad_ci(kind, N, H, W, Ci, Co, R, S, pad):
 def _pad_co(kind, N, H, W, Ci, Co, R, S, pad):
     """Same for a narrow OUTPUT side (the 64 -> 3 convolution in front of the ResNet generator's Tanh): Co < 32 is
     zero-padded to 32 (zero weight rows / zero gy channels; the extra output channels are dropped).  Returns 32 or None."""
-    if _state["conv_impl"] != "tf32" or Co >= 32 or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+    if not _tc_mode() or Co >= 32 or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
         return None
     return 32 if tc_covers(kind, N, H, W, Ci, 32, R, S, pad) else None
 
@@ -208,7 +263,7 @@ _pk_cache = {}
 
 
 def _pack_ok(kind, N, H, W, Ci, Co, R, S, pad):
-    if _state["conv_impl"] != "tf32" or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
+    if not _tc_mode() or tc_covers(kind, N, H, W, Ci, Co, R, S, pad):
         return False
     if W % 2 != 0 or R != S or S not in (1, 3) or pad != (S - 1) // 2 or Ci % 4 != 0 or Co % 4 != 0:
         return False
@@ -265,6 +320,11 @@ def conv_fprop(x, w, bias, pad, alpha, bias_scale, act, slope):
     Co, Ci2, R, S = w.shape
     if Ci != Ci2:
         raise GlbError(f"conv_fprop: channel mismatch {Ci} vs {Ci2}")
+    if _use_bf16("fprop", N, H, W, Ci, Co, R, S, pad):
+        y = _new_nhwc(N, Co, H + 2 * pad - R + 1, W + 2 * pad - S + 1, x)
+        _call("glb_conv2d_fprop_bf16", _p(bf16_operand(x)), _p(bf16_weight(w)), _p(_flat(bias)), _p(y), N, H, W, Ci, Co, R, S, pad,
+              float(alpha), float(bias_scale), int(act), float(slope), _stream())
+        return y
     if _pack_ok("fprop", N, H, W, Ci, Co, R, S, pad):
         b2 = None if bias is None else _flat(bias).repeat(2)
         yp = conv_fprop(_pack_view(x), packed_weight(w, pad), b2, pad, alpha, bias_scale, act, slope)
@@ -293,6 +353,11 @@ def conv_dgrad(gy, w, x_hw, pad, alpha):
     H, W = x_hw
     if Co != Co2 or Ho != H + 2 * pad - R + 1 or Wo != W + 2 * pad - S + 1:
         raise GlbError("conv_dgrad: shape mismatch")
+    if _use_bf16("dgrad", N, H, W, Ci, Co, R, S, pad):
+        gx = _new_nhwc(N, Ci, H, W, gy)
+        _call("glb_conv2d_dgrad_bf16", _p(bf16_operand(gy)), _p(bf16_weight(w, transposed=True)), _p(gx), N, H, W, Ci, Co, R, S, pad,
+              float(alpha), _stream())
+        return gx
     if _pack_ok("dgrad", N, H, W, Ci, Co, R, S, pad):
         gxp = conv_dgrad(_pack_view(gy), packed_weight(w, pad), (H, W // 2), pad, alpha)
         return _unpack_view(gxp, Ci)
@@ -318,6 +383,11 @@ def conv_wgrad(x, gy, rs, pad, alpha):
     R, S = rs
     if N != N2 or Ho != H + 2 * pad - R + 1 or Wo != W + 2 * pad - S + 1:
         raise GlbError("conv_wgrad: shape mismatch")
+    if _use_bf16("wgrad", N, H, W, Ci, Co, R, S, pad):
+        gw = _new_nhwc(Co, Ci, R, S, x)
+        _call("glb_conv2d_wgrad_bf16", _p(bf16_operand(x)), _p(bf16_operand(gy)), _p(gw), N, H, W, Ci, Co, R, S, pad, float(alpha),
+              _stream())
+        return gw
     if _pack_ok("wgrad", N, H, W, Ci, Co, R, S, pad):
         gwp = conv_wgrad(_pack_view(x), _pack_view(gy), (R, S), pad, alpha)
         return _fold_packed_wgrad(gwp, Co, Ci, S, pad)

@@ -61,3 +61,45 @@ extern "C" int glb_conv2d_wgrad(const float* x, const float* gy, float* gw, int 
   if (impl == GLB_IMPL_TF32) return glb::conv_wgrad_tc(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
   return glb::conv_wgrad_simt(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
 }
+
+// ---- bf16 operand path (GLB_IMPL_BF16): tcgen05 kind::f16, bf16 x bf16 -> fp32 ------------------------------------------
+namespace glb {
+bool conv_fprop_bf16_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad);
+bool conv_dgrad_bf16_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad);
+bool conv_wgrad_bf16_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad);
+int conv_fprop_bf16(const void* x, const void* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int R, int S,
+                    int pad, float alpha, float bias_scale, int act, float slope, cudaStream_t st);
+int conv_dgrad_bf16(const void* gy, const void* wt, float* gx, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                    float alpha, cudaStream_t st);
+int conv_wgrad_bf16(const void* x, const void* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                    float alpha, cudaStream_t st);
+}  // namespace glb
+
+extern "C" int glb_conv2d_bf16_covers(int kind, int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return 0;
+  switch (kind) {
+    case 0: return glb::conv_fprop_bf16_covers(N, H, W, Ci, Co, R, S, pad) ? 1 : 0;
+    case 1: return glb::conv_dgrad_bf16_covers(N, H, W, Ci, Co, R, S, pad) ? 1 : 0;
+    case 2: return glb::conv_wgrad_bf16_covers(N, H, W, Ci, Co, R, S, pad) ? 1 : 0;
+  }
+  return 0;
+}
+
+extern "C" int glb_conv2d_fprop_bf16(const void* x, const void* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
+                                     int R, int S, int pad, float alpha, float bias_scale, int act, float slope,
+                                     glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_fprop_bf16");
+  return glb::conv_fprop_bf16(x, w, bias, y, N, H, W, Ci, Co, R, S, pad, alpha, bias_scale, act, slope, (cudaStream_t)stream);
+}
+
+extern "C" int glb_conv2d_dgrad_bf16(const void* gy, const void* wt, float* gx, int N, int H, int W, int Ci, int Co, int R, int S,
+                                     int pad, float alpha, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_dgrad_bf16");
+  return glb::conv_dgrad_bf16(gy, wt, gx, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
+}
+
+extern "C" int glb_conv2d_wgrad_bf16(const void* x, const void* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S,
+                                     int pad, float alpha, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_wgrad_bf16");
+  return glb::conv_wgrad_bf16(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
+}

@@ -73,11 +73,12 @@ constexpr int kH1Default = 0;     // conv_fprop_tc2_h1_kernel: off until verifie
 constexpr int kHaloDefault = 12;  // tap-reuse kernels used by default: bits 0/1 = single CTA at BN 128/256, bits 2/3 = CTA pair at BN 128/256
 constexpr int kFpropThreads = 384;  // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
 
-template <int BN, int KC>
+template <int BN, int KC, bool BF>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
   using Cfg = FpropCfg<BN, KC>;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int kChunk = BF ? 64 : 32;              // channels per 128-byte operand row (shadows the fp32 constant)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
@@ -151,7 +152,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc<BF>(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -174,7 +175,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
               const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
               const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
-              mma_tf32(d_tmem, ad, bd, idesc, (k | c | kk) ? 1u : 0u);
+              mma_ss<BF>(d_tmem, ad, bd, idesc, (k | c | kk) ? 1u : 0u);
             }
           }
           mma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
@@ -660,11 +661,12 @@ struct Fprop2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
 conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
   using Cfg = Fprop2Cfg<BN>;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int kChunk = BF ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -701,6 +703,7 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), Cfg::kTmemCols);
   tc_fence_before();
+  __syncthreads();          // (the cluster barrier below orders the CTA as well; compute-sanitizer racecheck only models this one)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -736,7 +739,7 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc<BF>(2 * kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -754,7 +757,7 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
             const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
-            mma2_tf32(d_tmem, ad, bd, idesc, (k | kk) ? 1u : 0u);
+            mma2_ss<BF>(d_tmem, ad, bd, idesc, (k | kk) ? 1u : 0u);
           }
           mma2_commit_mc(empty_bar(stage), 3);  // frees this stage in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -837,11 +840,12 @@ struct Fprop2HaloCfg {
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
 conv_fprop_tc2_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
   using Cfg = Fprop2HaloCfg<BN>;
   constexpr int NA = Cfg::kAStages, NB = Cfg::kBStages, S_ = 3, TAPS = 9, TPS = Cfg::kTPS;
+  constexpr int kChunk = BF ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -875,6 +879,7 @@ conv_fprop_tc2_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
   if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), Cfg::kTmemCols);
   tc_fence_before();
+  __syncthreads();          // (the cluster barrier below orders the CTA as well; compute-sanitizer racecheck only models this one)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -920,7 +925,7 @@ conv_fprop_tc2_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc<BF>(2 * kBM, BN, 0, 0);
       int sa = 0, sb = 0, as = 0;
       uint32_t pa = 0, pb = 0, aphase = 0;
       for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
@@ -941,8 +946,8 @@ conv_fprop_tc2_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
               const int tap = g * TPS + u, r = tap / S_, s = tap - r * S_;
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                mma2_tf32(d_tmem, ad0 + (uint64_t)((s * Cfg::kBoxBytes + r * 1024 + kk * 32) >> 4),
-                          bd0 + (uint64_t)((u * Cfg::kTapBytes + kk * 32) >> 4), idesc, (ch | tap | kk) ? 1u : 0u);
+                mma2_ss<BF>(d_tmem, ad0 + (uint64_t)((s * Cfg::kBoxBytes + r * 1024 + kk * 32) >> 4),
+                            bd0 + (uint64_t)((u * Cfg::kTapBytes + kk * 32) >> 4), idesc, (ch | tap | kk) ? 1u : 0u);
             }
             mma2_commit_mc(bempty(sb), 3);
             if (++sb == NB) { sb = 0; pb ^= 1; }
@@ -1083,6 +1088,7 @@ conv_fprop_tc2_h1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
   if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), Cfg::kTmemCols);
   tc_fence_before();
+  __syncthreads();          // (the cluster barrier below orders the CTA as well; compute-sanitizer racecheck only models this one)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -1250,30 +1256,30 @@ int launch_fprop2_h1(const CUtensorMap& tmA, const CUtensorMap& tmB, const Fprop
   return GLB_OK;
 }
 
-template <int BN>
+template <int BN, bool BF = false>
 int launch_fprop2_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = Fprop2HaloCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_halo_kernel<BN, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
-  conv_fprop_tc2_halo_kernel<BN><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  conv_fprop_tc2_halo_kernel<BN, BF><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc2_halo_kernel");
   return GLB_OK;
 }
 
-template <int BN>
+template <int BN, bool BF = false>
 int launch_fprop2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = Fprop2Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_kernel<BN, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
-  conv_fprop_tc2_kernel<BN><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  conv_fprop_tc2_kernel<BN, BF><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc2_kernel");
   return GLB_OK;
 }
@@ -1312,16 +1318,16 @@ int launch_fprop_m2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropP
   return GLB_OK;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, bool BF = false>
 int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = FpropCfg<BN, KC>;
   static bool configured = false;  // per-process, per-instantiation; attribute is sticky for the function
   if (!configured) {
-    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BN, KC, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  conv_fprop_tc_kernel<BN, KC><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  conv_fprop_tc_kernel<BN, KC, BF><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc_kernel");
   return GLB_OK;
 }
@@ -1329,19 +1335,30 @@ int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropPara
 }  // namespace
 
 // Shapes the tensor-core fprop covers: stride-1 RxS with `pad`, Ci % 32 == 0, Co in {16, 32, 64} or a multiple of 128.
-bool conv_fprop_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
-  if (Ci % kChunk != 0 || Ci < kChunk) return false;
+// (bf16 operands: 64 channels per 128-byte row -> Ci % 64 == 0)
+static bool fprop_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad, int chunk) {
+  if (Ci % chunk != 0 || Ci < chunk) return false;
   if (!(Co == 16 || Co == 32 || Co == 64 || Co % 128 == 0)) return false;
   const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
   if (Ho <= 0 || Wo <= 0) return false;
   if (R * S > 25) return false;
   return true;
 }
+bool conv_fprop_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  return fprop_covers(N, H, W, Ci, Co, R, S, pad, 32);
+}
+bool conv_fprop_bf16_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  return fprop_covers(N, H, W, Ci, Co, R, S, pad, 64);
+}
 
-int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int R, int S,
-                  int pad, float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
-  if (!conv_fprop_tc_covers(N, H, W, Ci, Co, R, S, pad)) {
-    set_error("tcgen05 fprop: shape not covered (need Ci % 32 == 0 and Co in {16,32,64} or Co % 128 == 0)");
+// BF = false: x, w are fp32 (kind::tf32 truncates them); BF = true: x, w are bf16 copies (round-to-nearest, glb_cvt_f32_bf16)
+template <bool BF>
+static int conv_fprop_tc_impl(const void* x, const void* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int R,
+                              int S, int pad, float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
+  constexpr int kChunk = BF ? 64 : 32;             // channels per 128-byte operand row
+  constexpr uint64_t ES = BF ? 2 : 4;              // operand element size
+  if (!fprop_covers(N, H, W, Ci, Co, R, S, pad, kChunk)) {
+    set_error("tcgen05 fprop: shape not covered (need Ci % 32 == 0 (bf16: 64) and Co in {16,32,64} or Co % 128 == 0)");
     return GLB_ERR_UNSUPPORTED;
   }
   FpropParams p;
@@ -1381,7 +1398,7 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   p.ksplit = (k_iters + p.k_per - 1) / p.k_per;
   p.tiles_co = Co / BN;
   p.num_tiles = m_tiles * p.tiles_co * p.ksplit;
-  p.alpha = alpha * kTf32TruncComp; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+  p.alpha = BF ? alpha : alpha * kTf32TruncComp; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
   p.dbg = 0;
   p.trace = nullptr;
   if (const char* e = getenv("GLB_FPROP_DBG")) p.dbg = atoi(e);
@@ -1394,6 +1411,7 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   {
     int h1 = 0;                                   // GLB_FPROP_H1: 0 = off, 1 = <128, 2> (default once measured), 2 = <256, 1>
     if (const char* e = getenv("GLB_FPROP_H1")) h1 = atoi(e); else h1 = kH1Default;
+    if (BF) h1 = 0;
     const int bnh = (h1 == 2) ? 256 : 128;
     const int m_h = (p.Ho / 16) * (p.Wo / 8) * N;
     const bool ok = h1 != 0 && p.ksplit == 1 && R == 3 && S == 3 && pad == 1 && p.Ho % 16 == 0 && p.Wo % 8 == 0 && Co % bnh == 0 &&
@@ -1405,16 +1423,16 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
       q.num_tiles = (m_h / 2) * q.tiles_co;          // units
       CUtensorMap hA, hB;
       const uint64_t dimsA[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-      const uint64_t stridesA[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+      const uint64_t stridesA[3] = {(uint64_t)Ci * ES, (uint64_t)W * Ci * ES, (uint64_t)H * W * Ci * ES};
       const uint32_t boxA[4] = {(uint32_t)kChunk, 10u, 18u, 1u};
-      int rc = make_tmap_f32(&hA, x, 4, dimsA, stridesA, boxA, "conv input (10 x 18 box)");
+      int rc = make_tmap(&hA, x, 4, dimsA, stridesA, boxA, "conv input (10 x 18 box)", false, BF);
       if (rc) return rc;
       const uint64_t dimsB[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
-      const uint64_t stridesB[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+      const uint64_t stridesB[2] = {(uint64_t)Ci * ES, (uint64_t)R * S * Ci * ES};
       const uint32_t boxB[3] = {(uint32_t)kChunk, 1u, (uint32_t)(bnh / 2)};
-      rc = make_tmap_f32(&hB, w, 3, dimsB, stridesB, boxB, "conv weight (half tile)");
+      rc = make_tmap(&hB, w, 3, dimsB, stridesB, boxB, "conv weight (half tile)", false, BF);
       if (rc) return rc;
-      return bnh == 128 ? launch_fprop2_h1<128, 2>(hA, hB, q, st) : launch_fprop2_h1<256, 1>(hA, hB, q, st);
+      if (!BF) return bnh == 128 ? launch_fprop2_h1<128, 2>(hA, hB, q, st) : launch_fprop2_h1<256, 1>(hA, hB, q, st);
     }
   }
 
@@ -1425,22 +1443,22 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
     const bool shape_ok = p.ksplit == 1 && R == 3 && S == 3 && pad == 1 && p.Ho % 16 == 0 && p.Wo % 8 == 0 &&
                           (BN == 128 || BN == 256);
     const int h_tiles = (p.Ho / 16) * (p.Wo / 8) * N * (Co / BN);
-    if (shape_ok && h_tiles >= kNumSMs && ((BN == 128 && (halo & 1)) || (BN == 256 && (halo & 2)))) {
+    if (!BF && shape_ok && h_tiles >= kNumSMs && ((BN == 128 && (halo & 1)) || (BN == 256 && (halo & 2)))) {
       FpropParams q = p;
       q.bw = 8; q.bh = 16; q.bn = 1;
       q.tiles_w = p.Wo / 8; q.tiles_h = p.Ho / 16; q.tiles_n = N; q.tiles_co = Co / BN;
       q.num_tiles = h_tiles;
       CUtensorMap hA, hB;
       const uint64_t dimsA[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-      const uint64_t stridesA[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+      const uint64_t stridesA[3] = {(uint64_t)Ci * ES, (uint64_t)W * Ci * ES, (uint64_t)H * W * Ci * ES};
       const bool onebox = getenv("GLB_FPROP_ONEBOX") != nullptr && atoi(getenv("GLB_FPROP_ONEBOX")) != 0;   // A/B experiment
       const uint32_t boxA[4] = {(uint32_t)kChunk, onebox ? 10u : 8u, 18u, 1u};
-      int rc = make_tmap_f32(&hA, x, 4, dimsA, stridesA, boxA, "conv input (halo boxes)");
+      int rc = make_tmap(&hA, x, 4, dimsA, stridesA, boxA, "conv input (halo boxes)", false, BF);
       if (rc) return rc;
       const uint64_t dimsB[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
-      const uint64_t stridesB[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+      const uint64_t stridesB[2] = {(uint64_t)Ci * ES, (uint64_t)R * S * Ci * ES};
       const uint32_t boxB[3] = {(uint32_t)kChunk, 1u, (uint32_t)BN};
-      rc = make_tmap_f32(&hB, w, 3, dimsB, stridesB, boxB, "conv weight");
+      rc = make_tmap(&hB, w, 3, dimsB, stridesB, boxB, "conv weight", false, BF);
       if (rc) return rc;
       if (onebox) return BN == 128 ? launch_fprop_halo<128, true>(hA, hB, q, st) : launch_fprop_halo<256, true>(hA, hB, q, st);
       return BN == 128 ? launch_fprop_halo<128, false>(hA, hB, q, st) : launch_fprop_halo<256, false>(hA, hB, q, st);
@@ -1455,16 +1473,16 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
       q.num_tiles = (m_h / 2) * q.tiles_co;          // pair items
       CUtensorMap hA, hB;
       const uint64_t dimsA[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-      const uint64_t stridesA[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+      const uint64_t stridesA[3] = {(uint64_t)Ci * ES, (uint64_t)W * Ci * ES, (uint64_t)H * W * Ci * ES};
       const uint32_t boxA[4] = {(uint32_t)kChunk, 8u, 18u, 1u};
-      int rc = make_tmap_f32(&hA, x, 4, dimsA, stridesA, boxA, "conv input (halo boxes)");
+      int rc = make_tmap(&hA, x, 4, dimsA, stridesA, boxA, "conv input (halo boxes)", false, BF);
       if (rc) return rc;
       const uint64_t dimsB[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
-      const uint64_t stridesB[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+      const uint64_t stridesB[2] = {(uint64_t)Ci * ES, (uint64_t)R * S * Ci * ES};
       const uint32_t boxB[3] = {(uint32_t)kChunk, 1u, (uint32_t)(BN / 2)};
-      rc = make_tmap_f32(&hB, w, 3, dimsB, stridesB, boxB, "conv weight (half tile)");
+      rc = make_tmap(&hB, w, 3, dimsB, stridesB, boxB, "conv weight (half tile)", false, BF);
       if (rc) return rc;
-      return BN == 128 ? launch_fprop2_halo<128>(hA, hB, q, st) : launch_fprop2_halo<256>(hA, hB, q, st);
+      return BN == 128 ? launch_fprop2_halo<128, BF>(hA, hB, q, st) : launch_fprop2_halo<256, BF>(hA, hB, q, st);
     }
   }
 
@@ -1477,21 +1495,21 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint64_t strides[3] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4};
+    const uint64_t strides[3] = {(uint64_t)Ci * ES, (uint64_t)W * Ci * ES, (uint64_t)H * W * Ci * ES};
     const uint32_t box[4] = {(uint32_t)kChunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    int rc = make_tmap_f32(&tmA, x, 4, dims, strides, box, "conv input");
+    int rc = make_tmap(&tmA, x, 4, dims, strides, box, "conv input", false, BF);
     if (rc) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
-    const uint64_t strides[2] = {(uint64_t)Ci * 4, (uint64_t)R * S * Ci * 4};
+    const uint64_t strides[2] = {(uint64_t)Ci * ES, (uint64_t)R * S * Ci * ES};
     const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)(use_pair ? BN / 2 : BN)};
-    int rc = make_tmap_f32(&tmB, w, 3, dims, strides, box, "conv weight");
+    int rc = make_tmap(&tmB, w, 3, dims, strides, box, "conv weight", false, BF);
     if (rc) return rc;
   }
-  if (use_pair) return BN == 256 ? launch_fprop2<256>(tmA, tmB, p, st) : launch_fprop2<128>(tmA, tmB, p, st);
+  if (use_pair) return BN == 256 ? launch_fprop2<256, BF>(tmA, tmB, p, st) : launch_fprop2<128, BF>(tmA, tmB, p, st);
   // two M tiles per item for the 128-wide N tiles of the high-resolution layers (>= one wave of pair items)
-  bool use_m2 = BN == 128 && p.ksplit == 1 && m_tiles % 2 == 0 && (m_tiles / 2) * p.tiles_co >= kNumSMs;
+  bool use_m2 = !BF && BN == 128 && p.ksplit == 1 && m_tiles % 2 == 0 && (m_tiles / 2) * p.tiles_co >= kNumSMs;
   if (const char* e = getenv("GLB_FPROP_M2")) use_m2 = use_m2 && atoi(e) != 0;   // tuning experiments only
   if (use_m2) {
     p.num_tiles = (m_tiles / 2) * p.tiles_co;
@@ -1501,16 +1519,43 @@ int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, i
   // two K chunks per stage for the narrow tiles (see FpropCfg); needs whole stages per tap row and per split-K slice
   const bool kc2 = BN <= 128 && (Ci / kChunk) % 2 == 0 && p.k_per % 2 == 0 && getenv("GLB_FPROP_KC1") == nullptr;
   switch (BN) {
-    case 256: rc = launch_fprop<256, 1>(tmA, tmB, p, st); break;
-    case 128: rc = kc2 ? launch_fprop<128, 2>(tmA, tmB, p, st) : launch_fprop<128, 1>(tmA, tmB, p, st); break;
-    case 64: rc = kc2 ? launch_fprop<64, 2>(tmA, tmB, p, st) : launch_fprop<64, 1>(tmA, tmB, p, st); break;
-    case 32: rc = kc2 ? launch_fprop<32, 2>(tmA, tmB, p, st) : launch_fprop<32, 1>(tmA, tmB, p, st); break;
-    case 16: rc = launch_fprop<16, 1>(tmA, tmB, p, st); break;
+    case 256: rc = launch_fprop<256, 1, BF>(tmA, tmB, p, st); break;
+    case 128: rc = kc2 ? launch_fprop<128, 2, BF>(tmA, tmB, p, st) : launch_fprop<128, 1, BF>(tmA, tmB, p, st); break;
+    case 64: rc = kc2 ? launch_fprop<64, 2, BF>(tmA, tmB, p, st) : launch_fprop<64, 1, BF>(tmA, tmB, p, st); break;
+    case 32: rc = kc2 ? launch_fprop<32, 2, BF>(tmA, tmB, p, st) : launch_fprop<32, 1, BF>(tmA, tmB, p, st); break;
+    case 16: rc = launch_fprop<16, 1, BF>(tmA, tmB, p, st); break;
     default: set_error("tcgen05 fprop: no kernel for this N tile");
   }
   if (rc == GLB_OK && post_pass)
     rc = glb_bias_act_fwd(y, bias, y, (int64_t)N * p.Ho * p.Wo, Co, bias_scale, act, slope, (glb_stream_t)st);
   return rc;
+}
+
+int conv_fprop_tc(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int R, int S,
+                  int pad, float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
+  return conv_fprop_tc_impl<false>(x, w, bias, y, N, H, W, Ci, Co, R, S, pad, alpha, bias_scale, act, slope, st);
+}
+
+// bf16 operands (x [N,H,W,Ci] and w [Co,R,S,Ci] as bf16), fp32 accumulate / bias / activation / output
+int conv_fprop_bf16(const void* x, const void* w, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int R, int S,
+                    int pad, float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
+  return conv_fprop_tc_impl<true>(x, w, bias, y, N, H, W, Ci, Co, R, S, pad, alpha, bias_scale, act, slope, st);
+}
+
+int conv_dgrad_bf16(const void* gy, const void* wt, float* gx, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                    float alpha, cudaStream_t st) {
+  if (wt == nullptr || R != S) {
+    set_error("bf16 dgrad needs the transposed bf16 weights and a square filter");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  return conv_fprop_tc_impl<true>(gy, wt, nullptr, gx, N, Ho, Wo, Co, Ci, R, S, R - 1 - pad, alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+}
+
+bool conv_dgrad_bf16_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  if (R != S || R - 1 - pad < 0) return false;
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  return conv_fprop_bf16_covers(N, Ho, Wo, Co, Ci, R, S, R - 1 - pad);
 }
 
 // dgrad = fprop over gy with the flipped / transposed weights wt[Ci][R][S][Co] (glb_conv2d_weight_transpose):
@@ -1563,21 +1608,24 @@ struct WgradParams {
 // otherwise leave the issuing thread's per-stage wait / commit protocol as the pacing item (see FpropCfg).
 // The tensor maps are 5-D -- (32 ch, W, H, N, C/32) -- so ONE TMA instruction per operand and stage lands all its
 // [channel block][pixel][32 ch] blocks (12 separate 4 KB loads per stage held the main loop at ~35 % tensor-pipe activity).
-template <int BN, int PIX>
+template <int BN, int PIX, bool BF = false>
 struct WgradCfg {
-  static constexpr int kBlkBytes = PIX * 128;           // one (32 ch x PIX px) block
-  static constexpr int kABytes = 4 * kBlkBytes;
-  static constexpr int kBBytes = (BN / 32) * kBlkBytes;
+  static constexpr int kCH = BF ? 64 : 32;              // channels per 128-byte row
+  static constexpr int kBlkBytes = PIX * 128;           // one (kCH ch x PIX px) block
+  static constexpr int kABytes = (128 / kCH) * kBlkBytes;
+  static constexpr int kBBytes = (BN / kCH) * kBlkBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (192 * 1024 / kStageBytes) > 8 ? 8 : (192 * 1024 / kStageBytes);
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BN, int PIX>
+// BF: bf16 operands.  16-bit MN-major operands use the PLAIN 128-byte swizzle: one atom = 8 pixels x 64 channels (1024 B),
+// SBO = 1024 B between 8-pixel groups, LBO = one (64 ch x PIX px) block between 64-channel blocks, K = 16 pixels per MMA.
+template <int BN, int PIX, bool BF>
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
-  using Cfg = WgradCfg<BN, PIX>;
+  using Cfg = WgradCfg<BN, PIX, BF>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -1632,14 +1680,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_cons
         const uint32_t a_dst = base + stage * Cfg::kStageBytes;
         const uint32_t b_dst = a_dst + Cfg::kABytes;
         mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        tma_load_5d(a_dst, &tmGy, full_bar(stage), 0, w0, h0, n0, co0 / 32);
-        tma_load_5d(b_dst, &tmX, full_bar(stage), 0, w0 + s - p.pad, h0 + r - p.pad, n0, ci0 / 32);
+        tma_load_5d(a_dst, &tmGy, full_bar(stage), 0, w0, h0, n0, co0 / Cfg::kCH);
+        tma_load_5d(b_dst, &tmX, full_bar(stage), 0, w0 + s - p.pad, h0 + r - p.pad, n0, ci0 / Cfg::kCH);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+      constexpr uint32_t idesc = make_idesc<BF>(128, BN, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int pb = pb_begin; pb < pb_end; ++pb) {
@@ -1647,11 +1695,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_cons
         tc_fence_after();
         const uint32_t a_addr = base + stage * Cfg::kStageBytes;
         const uint32_t b_addr = a_addr + Cfg::kABytes;
+        if (BF) {
 #pragma unroll
-        for (int kg = 0; kg < PIX / 8; ++kg) {  // K = 8 pixels per MMA = two 512 B swizzle atoms per channel block
-          const uint64_t ad = make_smem_desc(a_addr + kg * 1024, Cfg::kBlkBytes, 512, kLayoutSw128Base32);
-          const uint64_t bd = make_smem_desc(b_addr + kg * 1024, Cfg::kBlkBytes, 512, kLayoutSw128Base32);
-          mma_tf32(tmem_base, ad, bd, idesc, (pb > pb_begin || kg > 0) ? 1u : 0u);
+          for (int kg = 0; kg < PIX / 16; ++kg) {  // K = 16 pixels per MMA = two 1024 B swizzle atoms per 64-channel block
+            const uint64_t ad = make_smem_desc(a_addr + kg * 2048, Cfg::kBlkBytes, 1024, kLayoutSw128);
+            const uint64_t bd = make_smem_desc(b_addr + kg * 2048, Cfg::kBlkBytes, 1024, kLayoutSw128);
+            mma_bf16(tmem_base, ad, bd, idesc, (pb > pb_begin || kg > 0) ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int kg = 0; kg < PIX / 8; ++kg) {  // K = 8 pixels per MMA = two 512 B swizzle atoms per channel block
+            const uint64_t ad = make_smem_desc(a_addr + kg * 1024, Cfg::kBlkBytes, 512, kLayoutSw128Base32);
+            const uint64_t bd = make_smem_desc(b_addr + kg * 1024, Cfg::kBlkBytes, 512, kLayoutSw128Base32);
+            mma_tf32(tmem_base, ad, bd, idesc, (pb > pb_begin || kg > 0) ? 1u : 0u);
+          }
         }
         mma_commit(empty_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1842,21 +1899,21 @@ int launch_wgrad3(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradPa
   return GLB_OK;
 }
 
-template <int BN, int PIX>
+template <int BN, int PIX, bool BF = false>
 int launch_wgrad(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
-  using Cfg = WgradCfg<BN, PIX>;
+  using Cfg = WgradCfg<BN, PIX, BF>;
   static bool configured = false;
   if (!configured) {
-    GLB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GLB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, PIX, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  conv_wgrad_tc_kernel<BN, PIX><<<grid, 256, Cfg::kSmemBytes, st>>>(tmGy, tmX, p);
+  conv_wgrad_tc_kernel<BN, PIX, BF><<<grid, 256, Cfg::kSmemBytes, st>>>(tmGy, tmX, p);
   GLB_CHECK_LAUNCH("conv_wgrad_tc_kernel");
   return GLB_OK;
 }
 
-bool conv_wgrad_tc_covers_impl(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
-  if (Ci % 32 != 0 || Co % 32 != 0) return false;
+bool conv_wgrad_tc_covers_impl(int N, int H, int W, int Ci, int Co, int R, int S, int pad, int chunk = 32) {
+  if (Ci % chunk != 0 || Co % chunk != 0) return false;
   const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
   if (Ho <= 0 || Wo <= 0 || R * S > 25) return false;
   return true;
@@ -1868,10 +1925,17 @@ bool conv_wgrad_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int
   return conv_wgrad_tc_covers_impl(N, H, W, Ci, Co, R, S, pad);
 }
 
-int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
-                  float alpha, cudaStream_t st) {
-  if (!conv_wgrad_tc_covers_impl(N, H, W, Ci, Co, R, S, pad)) {
-    set_error("tcgen05 wgrad: shape not covered (need Ci % 32 == 0 and Co % 32 == 0)");
+bool conv_wgrad_bf16_covers(int N, int H, int W, int Ci, int Co, int R, int S, int pad) {
+  return conv_wgrad_tc_covers_impl(N, H, W, Ci, Co, R, S, pad, 64);
+}
+
+template <bool BF>
+static int conv_wgrad_tc_impl(const void* x, const void* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                              float alpha, cudaStream_t st) {
+  constexpr int CH = BF ? 64 : 32;
+  constexpr uint64_t ES = BF ? 2 : 4;
+  if (!conv_wgrad_tc_covers_impl(N, H, W, Ci, Co, R, S, pad, CH)) {
+    set_error("tcgen05 wgrad: shape not covered (need Ci and Co multiples of 32; bf16: of 64)");
     return GLB_ERR_UNSUPPORTED;
   }
   WgradParams p;
@@ -1879,7 +1943,7 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1;
   {
     // tap-reuse kernel: 3x3 "same" convolutions whose maps tile into 4 x 8 pixel K blocks, enough of them for one wave
-    bool tap3 = R == 3 && S == 3 && pad == 1 && p.Wo % 8 == 0 && p.Ho % 4 == 0 && (Ci % 128 == 0 || Ci == 64 || Ci == 32);
+    bool tap3 = !BF && R == 3 && S == 3 && pad == 1 && p.Wo % 8 == 0 && p.Ho % 4 == 0 && (Ci % 128 == 0 || Ci == 64 || Ci == 32);
     if (const char* e = getenv("GLB_WGRAD_TAP3")) tap3 = tap3 && atoi(e) != 0;   // tuning experiments only
     const int bn3 = Ci % 128 == 0 ? 128 : Ci;
     p.tiles_w = p.Wo / 8; p.tiles_h = p.Ho / 4; p.tiles_n = N;
@@ -1919,7 +1983,7 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
     }
   }
   const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
-  const int PIX = BN >= 256 ? 32 : 64;
+  const int PIX = (BN >= 256 ? 32 : 64) * (BF ? 2 : 1);      // same bytes and MMAs per stage for either operand type
   p.bw = next_pow2(p.Wo) < PIX ? next_pow2(p.Wo) : PIX;
   p.bh = next_pow2(p.Ho) < PIX / p.bw ? next_pow2(p.Ho) : PIX / p.bw;
   p.bn = PIX / (p.bw * p.bh);
@@ -1939,26 +2003,34 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
   if (splits < 1) splits = 1;
   p.pb_per_split = (p.num_pb + splits - 1) / splits;
   p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;  // every split owns >= 1 pixel block
-  p.alpha = alpha * kTf32TruncComp;
+  p.alpha = BF ? alpha : alpha * kTf32TruncComp;
   p.atomic = p.splits > 1 ? 1 : 0;
   if (p.atomic) GLB_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Co * R * S * Ci, st));
 
   CUtensorMap tmGy, tmX;
   {  // (32 ch, Wo, Ho, N, Co/32): box = PIX pixels x 4 channel blocks (blocks beyond Co/32 are zero-filled: M padded to 128)
-    const uint64_t dims[5] = {32u, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N, (uint64_t)(Co / 32)};
-    const uint64_t strides[4] = {(uint64_t)Co * 4, (uint64_t)p.Wo * Co * 4, (uint64_t)p.Ho * p.Wo * Co * 4, 128u};
-    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 4u};
-    int rc = make_tmap_f32(&tmGy, gy, 5, dims, strides, box, "wgrad gy", true);
+    const uint64_t dims[5] = {(uint64_t)CH, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N, (uint64_t)(Co / CH)};
+    const uint64_t strides[4] = {(uint64_t)Co * ES, (uint64_t)p.Wo * Co * ES, (uint64_t)p.Ho * p.Wo * Co * ES, 128u};
+    const uint32_t box[5] = {(uint32_t)CH, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(128 / CH)};
+    int rc = make_tmap(&tmGy, gy, 5, dims, strides, box, "wgrad gy", !BF, BF);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / 32)};
-    const uint64_t strides[4] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4, 128u};
-    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BN / 32)};
-    int rc = make_tmap_f32(&tmX, x, 5, dims, strides, box, "wgrad x", true);
+    const uint64_t dims[5] = {(uint64_t)CH, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / CH)};
+    const uint64_t strides[4] = {(uint64_t)Ci * ES, (uint64_t)W * Ci * ES, (uint64_t)H * W * Ci * ES, 128u};
+    const uint32_t box[5] = {(uint32_t)CH, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BN / CH)};
+    int rc = make_tmap(&tmX, x, 5, dims, strides, box, "wgrad x", !BF, BF);
     if (rc) return rc;
   }
   const int grid = tiles * p.splits;
+  if (BF) {
+    switch (BN) {
+      case 256: return launch_wgrad<256, 64, true>(tmGy, tmX, p, grid, st);
+      case 128: return launch_wgrad<128, 128, true>(tmGy, tmX, p, grid, st);
+      case 64: return launch_wgrad<64, 128, true>(tmGy, tmX, p, grid, st);
+    }
+    return GLB_ERR_UNSUPPORTED;
+  }
   switch (BN) {
     case 256: return launch_wgrad<256, 32>(tmGy, tmX, p, grid, st);
     case 128: return launch_wgrad<128, 64>(tmGy, tmX, p, grid, st);
@@ -1966,6 +2038,16 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
     case 32: return launch_wgrad<32, 64>(tmGy, tmX, p, grid, st);
   }
   return GLB_ERR_UNSUPPORTED;
+}
+
+int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                  float alpha, cudaStream_t st) {
+  return conv_wgrad_tc_impl<false>(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, st);
+}
+
+int conv_wgrad_bf16(const void* x, const void* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                    float alpha, cudaStream_t st) {
+  return conv_wgrad_tc_impl<true>(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, st);
 }
 
 }  // namespace glb

@@ -1097,3 +1097,35 @@ extern "C" int glb_interp_rows(const float* a, const float* b, const float* eps,
   GLB_CHECK_LAUNCH("interp_rows");
   return GLB_OK;
 }
+
+// ---- fp32 -> bf16 (round to nearest even): operand copies for the bf16 tensor-core path ---------------------------------
+#include <cuda_bf16.h>
+namespace glb {
+namespace {
+__global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float4* __restrict__ x, uint4* __restrict__ y, int64_t n8,
+                                                           const float* __restrict__ xt, __nv_bfloat16* __restrict__ yt, int tail) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = ldg_stream(x + 2 * i), b = ldg_stream(x + 2 * i + 1);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    y[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < tail) yt[threadIdx.x] = __float2bfloat16_rn(xt[threadIdx.x]);
+}
+}  // namespace
+}  // namespace glb
+
+extern "C" int glb_cvt_f32_bf16(const float* x, void* y, int64_t n, glb_stream_t stream) {
+  if (n <= 0) return GLB_OK;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return glb::shape_fail("cvt_f32_bf16: 16-byte alignment");
+  const int64_t n8 = n / 8;
+  const int tail = (int)(n - 8 * n8);
+  glb::cvt_f32_bf16_kernel<<<glb::grid_for(n8 > 0 ? n8 : 1, 256, glb::kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (uint4*)y, n8, x + 8 * n8, reinterpret_cast<__nv_bfloat16*>(y) + 8 * n8, tail);
+  GLB_CHECK_LAUNCH("cvt_f32_bf16_kernel");
+  return GLB_OK;
+}

@@ -31,8 +31,8 @@ inline EncodeTiledFn encode_tiled_fn() {
 // dims/box in elements, strides in BYTES for dims 1..rank-1.
 // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands) instead of
 // the plain 128B swizzle.
-inline int make_tmap_f32(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                         const uint32_t* box, const char* what, bool atom32 = false) {
+inline int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, const char* what, bool atom32, bool bf16) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -47,7 +47,7 @@ inline int make_tmap_f32(CUtensorMap* tm, const void* ptr, int rank, const uint6
     es[i] = 1;
     if (i > 0) gs[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -56,6 +56,11 @@ inline int make_tmap_f32(CUtensorMap* tm, const void* ptr, int rank, const uint6
     return GLB_ERR_CUDA;
   }
   return GLB_OK;
+}
+
+inline int make_tmap_f32(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, const char* what, bool atom32 = false) {
+  return make_tmap(tm, ptr, rank, dims, strides_bytes, box, what, atom32, false);
 }
 
 // ------------------------------------------------------------------------------------------------ device: PTX wrappers
@@ -136,6 +141,22 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with bf16 operands (kind::f16; K = 16 per instruction = the same 32 bytes per operand row)
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool BF>
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (BF) mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 // mbarrier arrives once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -175,6 +196,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with bf16 A and B, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+template <bool BF>
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return BF ? make_idesc_bf16(M, N, a_mn, b_mn) : make_idesc_tf32(M, N, a_mn, b_mn);
 }
 
 }  // namespace tc
@@ -234,6 +265,21 @@ __device__ __forceinline__ void mma2_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void mma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool BF>
+__device__ __forceinline__ void mma2_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (BF) mma2_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else mma2_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 // arrive on the mbarrier at the same shared-memory offset in every CTA of `mask` once the pair's MMAs so far are done
 __device__ __forceinline__ void mma2_commit_mc(uint32_t bar, uint16_t mask) {

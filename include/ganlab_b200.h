@@ -36,6 +36,7 @@ extern "C" {
 
 #define GLB_IMPL_FP32 0
 #define GLB_IMPL_TF32 1
+#define GLB_IMPL_BF16 2   /* the *_bf16 entry points below; not a value of the `impl` argument of the fp32-pointer calls */
 
 #define GLB_ACT_NONE 0
 #define GLB_ACT_LRELU 1   /* leaky ReLU with `slope` (slope 0 = ReLU) */
@@ -71,6 +72,22 @@ int glb_conv2d_wgrad(const float* x, const float* gy, float* gw,
 int glb_conv2d_tc_covers(int kind, int N, int H, int W, int Ci, int Co, int R, int S, int pad);
 /* workspace-free weight re-layout used by the tensor-core dgrad: wt[Ci][R][S][Co] (taps flipped). */
 int glb_conv2d_weight_transpose(const float* w, float* wt, int Co, int R, int S, int Ci, glb_stream_t stream);
+
+/* ---- bf16-operand variant of the convolution family (opt-in: set_conv_impl("bf16")) ---------------------------- *
+ * Same contract as above with the two GEMM operands given as bf16 copies (round to nearest even, made by
+ * glb_cvt_f32_bf16 from the fp32 tensors; the weight copies once per optimiser step), fp32 accumulation, bias,
+ * activation and output: tcgen05 kind::f16 runs at twice the kind::tf32 rate.  Replaces the same ATen call sites as
+ * glb_conv2d_fprop / _dgrad / _wgrad (utils/custom_layers.py:202-211) under a looser stated tolerance.
+ * dgrad takes the bf16 copy of the flipped / transposed weights (glb_conv2d_weight_transpose, then glb_cvt_f32_bf16). */
+int glb_cvt_f32_bf16(const float* x, void* y_bf16, int64_t n, glb_stream_t stream);
+int glb_conv2d_bf16_covers(int kind, int N, int H, int W, int Ci, int Co, int R, int S, int pad);
+int glb_conv2d_fprop_bf16(const void* x_bf16, const void* w_bf16, const float* bias, float* y,
+                          int N, int H, int W, int Ci, int Co, int R, int S, int pad,
+                          float alpha, float bias_scale, int act, float slope, glb_stream_t stream);
+int glb_conv2d_dgrad_bf16(const void* gy_bf16, const void* wt_bf16, float* gx,
+                          int N, int H, int W, int Ci, int Co, int R, int S, int pad, float alpha, glb_stream_t stream);
+int glb_conv2d_wgrad_bf16(const void* x_bf16, const void* gy_bf16, float* gw,
+                          int N, int H, int W, int Ci, int Co, int R, int S, int pad, float alpha, glb_stream_t stream);
 
 /* ---- RGB 1x1 convolutions (3 <-> C channels; pure bandwidth) ---------------------------------- *
  * fromRGB (progan/architectures.py:286-292) and toRGB (stylegan/architectures.py:338-341).

@@ -107,6 +107,44 @@ def test_conv_family_tf32_vs_contract(shape):
         K.set_conv_impl("fp32")
 
 
+# bf16 operand path (tcgen05 kind::f16 on round-to-nearest bf16 copies of x / gy / w, fp32 accumulation): 8 mantissa bits per
+# operand -> stated bound 1e-2 of the tensor's max-norm (expected ~3e-3 over K = 576..4608); channel counts multiples of 64.
+TOL_BF16 = 1e-2
+BF16_SHAPES = [  # N, H, W, Ci, Co, R, pad
+    (8, 4, 4, 512, 512, 3, 1), (8, 16, 16, 512, 512, 3, 1), (2, 32, 32, 256, 128, 3, 1), (2, 64, 64, 128, 256, 3, 1),
+    (2, 16, 16, 64, 64, 3, 1), (2, 32, 32, 128, 128, 1, 0), (8, 32, 32, 512, 512, 3, 1), (8, 64, 64, 256, 256, 3, 1),
+    (3, 128, 128, 128, 128, 3, 1), (8, 4, 4, 512, 512, 4, 0),
+]
+
+
+@pytest.mark.parametrize("shape", BF16_SHAPES)
+def test_conv_family_bf16_vs_contract(shape):
+    N, H, W, Ci, Co, R, pad = shape
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, R, R, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, H + 2 * pad - R + 1, W + 2 * pad - R + 1, seed=3))
+    K.set_conv_impl("bf16")
+    try:
+        for kind in ("fprop", "dgrad", "wgrad"):
+            assert K.bf16_covers(kind, N, H, W, Ci, Co, R, R, pad), kind
+        n0 = K.launch_count()
+        both("conv_fprop", x, w, b, pad, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_BF16)
+        both("conv_fprop", x, w, None, pad, 1.0, 1.0, K.ACT_NONE, 0.2, tol=TOL_BF16)
+        both("conv_dgrad", gy, w, (H, W), pad, 0.37, tol=TOL_BF16)
+        both("conv_wgrad", x, gy, (R, R), pad, 0.37, tol=TOL_BF16)
+        assert K.launch_count() > n0
+    finally:
+        K.set_conv_impl("fp32")
+
+
+def test_bf16_conversion_is_round_to_nearest_even():
+    x = torch.randn(3, 7, 5, 11, device=DEV) * 3
+    x.view(-1)[:4] = torch.tensor([1.0, 1.00390625, 1.01171875, -65504.0], device=DEV)     # exact, tie -> even, tie -> even
+    got = K.cvt_bf16(x.contiguous())
+    assert got.dtype == torch.bfloat16 and torch.equal(got, x.to(torch.bfloat16))
+    xc = cl(torch.randn(2, 64, 9, 9, device=DEV))
+    assert torch.equal(K.cvt_bf16(xc), xc.to(torch.bfloat16)) and K.cvt_bf16(xc).is_contiguous(memory_format=torch.channels_last)
+
+
 @pytest.mark.parametrize("shape", [(4, 32, 32, 3, 64, 3, 1), (4, 32, 32, 64, 3, 3, 1), (2, 16, 16, 3, 128, 3, 1)])
 def test_conv_three_channel_sides_take_the_tensor_core_path(shape):
     """The 3 -> C and C -> 3 3x3 convolutions of the ResNet nets: the narrow side is zero-padded to 32 channels by the
