@@ -345,7 +345,8 @@ def run_ours(args):
         from gan_lab_b200.parallel import DataParallel
         mb = os.environ.get("GLB_DP_BUCKET_MB")          # tuning experiments only; default = DataParallel's measured choice
         L.dp = DataParallel(world, overlap=os.environ.get("GLB_DP_OVERLAP", "1") != "0",
-                            bucket_bytes=int(float(mb) * 1024 * 1024) if mb else None)
+                            bucket_bytes=int(float(mb) * 1024 * 1024) if mb else None,
+                            inplace=(os.environ["GLB_DP_INPLACE"] != "0") if "GLB_DP_INPLACE" in os.environ else None)
         L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
     def log(msg):
         if args.verbose:
@@ -508,7 +509,8 @@ def run_ours(args):
             "details": {"conv_impl": args.conv_impl, "cuda_graphs": use_graphs,
                        "r1_shares_real_forward": bool(getattr(L, "share_penalty_forward", False)),
                        "d_fake_real_one_pass": bool(getattr(L, "batch_d_passes", False)),
-                       "grad_allreduce": (f"NCCL all-reduce, {L.dp.bucket_bytes >> 20} MiB buckets launched from grad hooks as they fill"
+                       "grad_allreduce": (f"NCCL all-reduce ({'in place, grouped, ncclAvg' if L.dp.inplace else 'packed buckets'}), "
+                                          f"{L.dp.bucket_bytes >> 20} MiB buckets launched from grad hooks as they fill"
                                           if world > 1 else None), "l2": "8-batch input pool; activations per step (>1 GB) exceed the 126 MB L2",
                        "algorithmic_conv_gflop_per_step_per_gpu": flops / 1e9,
                        "achieved_conv_tflops_whole_step": flops / (ms / args.steps / 1e3) / 1e12},
@@ -538,6 +540,22 @@ def run_ours(args):
             line["roofline_input"] = input_pipeline_roofline(peaks)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+            # the opt-in bf16-operand mode on the same workload, as its own process (same harness)
+            if args.conv_impl == "tf32" and os.environ.get("GLB_BENCH_NO_BF16") is None:
+                try:
+                    sub = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--config", args.config, "--conv-impl", "bf16",
+                                          "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline"],
+                                         capture_output=True, text=True, timeout=600)
+                    b = json.loads([ln for ln in sub.stdout.splitlines() if ln.startswith("{")][-1])
+                    line["opt_in_bf16_operands"] = {
+                        "value": b["value"], "unit": "img/s", "ms_per_step": b["ms_per_step"], "e2e": b["e2e"]["value"],
+                        "conv_tflops": b["roofline"]["achieved"], "conv_frac_of_bf16_peak": b["roofline"]["frac"],
+                        "glue_gbs": b["roofline_glue"]["achieved"],
+                        "note": "python bench.py --conv-impl bf16: bf16 copies of the GEMM operands (round to nearest), fp32 accumulation / "
+                                "storage; NOT the default -- BASELINE.json names fp32/TF32 for this workload and the whole-step deviation "
+                                "is 4-10x the TF32 one (tests/test_cfg2_fullwidth.py)"}
+                except Exception as e:          # noqa: BLE001
+                    line["opt_in_bf16_operands"] = {"error": repr(e)[:300]}
             # SURVEY.md 8d "the real bar to beat": the UNMODIFIED reference through stock PyTorch (cuDNN / cuBLAS / ATen) on this
             # same B200, same workload, 3 iterations after 3 warm-up (~1.5 s each)
             try:

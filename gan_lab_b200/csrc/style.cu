@@ -374,11 +374,13 @@ __device__ __forceinline__ void se_wait(int* counter, int target) {
   __syncthreads();
 }
 
+constexpr int SEK = 8;   // accumulator copies per sample: ~150 blocks hitting ONE address serialise (~90 ns per atomic at L2)
+
 __device__ __forceinline__ void atomic_add4(double* p, const float4& v) {
   atomicAdd(p + 0, (double)v.x); atomicAdd(p + 1, (double)v.y); atomicAdd(p + 2, (double)v.z); atomicAdd(p + 3, (double)v.w);
 }
 
-// acc: [N][2][C] doubles, zeroed before the launch; counter: [N] ints, zeroed
+// acc: [N][SEK][2][C] doubles, zeroed before the launch; counter: [N] ints, zeroed
 __global__ void __launch_bounds__(TPB) se_fwd_fused_kernel(const float4* __restrict__ x, const float* __restrict__ noise,
                                                            const float4* __restrict__ nw, const float4* __restrict__ bias,
                                                            const float4* __restrict__ style, double* acc, float* __restrict__ stats,
@@ -387,13 +389,14 @@ __global__ void __launch_bounds__(TPB) se_fwd_fused_kernel(const float4* __restr
   const int per = 2 * g.chunks;
   const int n = blockIdx.x / per, r = blockIdx.x - n * per;
   const int C = 4 * g.C4, q = threadIdx.x % g.C4;
-  double* an = acc + (int64_t)n * 2 * C;
+  double* an = acc + (int64_t)n * SEK * 2 * C;
   if (r < g.chunks) {
     float4 s, ss, k4;
     se_fwd_stats_sums(x, noise, nw, bias, g, red, n, r, 0, s, ss, k4);
     if (threadIdx.x < g.C4) {
-      atomic_add4(an + 4 * q, s);
-      atomic_add4(an + C + 4 * q, ss);
+      double* ak = an + (int64_t)(r % SEK) * 2 * C;
+      atomic_add4(ak + 4 * q, s);
+      atomic_add4(ak + C + 4 * q, ss);
     }
     se_signal(counter + n);
   } else {
@@ -407,8 +410,14 @@ __global__ void __launch_bounds__(TPB) se_fwd_fused_kernel(const float4* __restr
     float mu[4], rs[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const double m1 = __ldcg(an + 4 * q + e) / g.HW;
-      double var = __ldcg(an + C + 4 * q + e) / g.HW - m1 * m1;
+      double S = 0.0, SS = 0.0;
+#pragma unroll
+      for (int k = 0; k < SEK; ++k) {
+        S += __ldcg(an + (int64_t)k * 2 * C + 4 * q + e);
+        SS += __ldcg(an + (int64_t)k * 2 * C + C + 4 * q + e);
+      }
+      const double m1 = S / g.HW;
+      double var = SS / g.HW - m1 * m1;
       if (var < 0.0) var = 0.0;
       mu[e] = (float)(kk[e] + m1);
       rs[e] = (float)(1.0 / sqrt(var + (double)eps));
@@ -432,13 +441,14 @@ __global__ void __launch_bounds__(TPB) se_bwd_fused_kernel(const float4* __restr
   const int per = 2 * g.chunks;
   const int n = blockIdx.x / per, r = blockIdx.x - n * per;
   const int C = 4 * g.C4, q = threadIdx.x % g.C4;
-  double* an = acc + (int64_t)n * 2 * C;
+  double* an = acc + (int64_t)n * SEK * 2 * C;
   if (r < g.chunks) {
     float4 s1, s2;
     se_bwd_stats_sums(gout, x, noise, nw, bias, stats, g, red, n, r, s1, s2);
     if (threadIdx.x < g.C4) {
-      atomic_add4(an + 4 * q, s1);
-      atomic_add4(an + C + 4 * q, s2);
+      double* ak = an + (int64_t)(r % SEK) * 2 * C;
+      atomic_add4(ak + 4 * q, s1);
+      atomic_add4(ak + C + 4 * q, s2);
     }
     se_signal(counter + n);
   } else {
@@ -448,7 +458,12 @@ __global__ void __launch_bounds__(TPB) se_bwd_fused_kernel(const float4* __restr
     float m1[4], m2[4], S1[4], S2[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const double a1 = __ldcg(an + 4 * q + e), a2 = __ldcg(an + C + 4 * q + e);
+      double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < SEK; ++k) {
+        a1 += __ldcg(an + (int64_t)k * 2 * C + 4 * q + e);
+        a2 += __ldcg(an + (int64_t)k * 2 * C + C + 4 * q + e);
+      }
       S1[e] = (float)a1; S2[e] = (float)a2;
       m1[e] = (float)(sc[e] * a1 / g.HW);
       m2[e] = (float)(sc[e] * a2 / g.HW);
@@ -797,7 +812,7 @@ double* se_fused_acc(float* work) {
 
 extern "C" int64_t glb_style_epilogue_work_floats(int N, int H, int W, int C) {
   if (C < 4) return 0;
-  const int64_t fused = 4 * (int64_t)N * C + (int64_t)N + 16;      // [N][2][C] doubles + [N] ints (+ alignment slack), in floats
+  const int64_t fused = 4 * (int64_t)N * C * 8 + (int64_t)N + 16;  // [N][SEK = 8][2][C] doubles + [N] ints (+ alignment slack), in floats
   const int64_t three = glb::se_part_floats(N, H, W, C);
   return three > fused ? three : fused;
 }
@@ -815,8 +830,8 @@ extern "C" int glb_style_epilogue_fwd(const float* x, const float* noise, const 
   if (int rc = se_geom(g, N, H, W, C, slope)) return rc;
   if (se_mode() == 1) {
     double* acc = se_fused_acc(work);
-    int* counter = reinterpret_cast<int*>(acc + (int64_t)N * 2 * C);
-    GLB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * N * 2 * C + sizeof(int) * N, st));
+    int* counter = reinterpret_cast<int*>(acc + (int64_t)N * SEK * 2 * C);
+    GLB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * N * SEK * 2 * C + sizeof(int) * N, st));
     se_fwd_fused_kernel<<<N * 2 * g.chunks, TPB, 0, st>>>((const float4*)x, noise, (const float4*)noise_weight, (const float4*)bias,
                                                          (const float4*)style, acc, stats, (float4*)out, counter, g, eps);
     GLB_CHECK_LAUNCH("se_fwd_fused");
@@ -850,8 +865,8 @@ extern "C" int glb_style_epilogue_bwd(const float* gout, const float* x, const f
   float* means = work + (int64_t)N * g.chunks * 2 * C;
   if (se_mode() == 1) {
     double* acc = se_fused_acc(work);
-    int* counter = reinterpret_cast<int*>(acc + (int64_t)N * 2 * C);
-    GLB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * N * 2 * C + sizeof(int) * N, st));
+    int* counter = reinterpret_cast<int*>(acc + (int64_t)N * SEK * 2 * C);
+    GLB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * N * SEK * 2 * C + sizeof(int) * N, st));
     se_bwd_fused_kernel<<<N * 2 * g.chunks, TPB, 0, st>>>((const float4*)gout, (const float4*)x, noise, (const float4*)noise_weight,
                                                          (const float4*)bias, style, (const float4*)stats, acc, (float4*)gx, gstyle,
                                                          g_noise_weight, g_bias, counter, g);

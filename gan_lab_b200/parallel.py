@@ -29,7 +29,7 @@ def _flat_view(t):
 
 
 class DataParallel(object):
-    def __init__(self, world_size=None, bucket_bytes=None, overlap=True):
+    def __init__(self, world_size=None, bucket_bytes=None, overlap=True, inplace=None):
         self.world = world_size if world_size is not None else dist.get_world_size()
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0   # rank 0 writes checkpoints
         if bucket_bytes is None:
@@ -38,6 +38,12 @@ class DataParallel(object):
             bucket_bytes = (32 if self.world <= 2 else 128) * 1024 * 1024
         self.bucket_bytes = bucket_bytes
         self.overlap = overlap
+        # inplace (NCCL only; default on): the gradients of a bucket are all-reduced WHERE THEY ARE, as one grouped NCCL call
+        # (ncclGroupStart / one ncclAllReduce per tensor / ncclGroupEnd, averaging in the collective: ncclAvg) -- no pack
+        # (`torch.cat`), no pre-scale and no scatter-back pass, i.e. ~6 bytes of HBM traffic per gradient byte less per step.
+        if inplace is None:
+            inplace = dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+        self.inplace = bool(inplace)
         self.enabled = True         # False: the hooks stay silent (rank-local passes such as bench.py's roofline replay)
         self._hooked = set()        # ids of parameters that carry our hook
         self._pending = []          # parameters whose gradient is ready but not yet in a bucket
@@ -76,6 +82,13 @@ class DataParallel(object):
         ps, self._pending, self._pending_bytes = self._pending, [], 0
         if not ps:
             return
+        if self.inplace:
+            grads = [_flat_view(p.grad) for p in ps]
+            with dist._coalescing_manager(device=grads[0].device, async_ops=True) as cm:
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG)
+            self._inflight.append((cm, None, ps))
+            return
         flat = torch.cat([_flat_view(p.grad) for p in ps])
         flat.mul_(1.0 / self.world)
         self._inflight.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, ps))
@@ -93,7 +106,8 @@ class DataParallel(object):
         with torch.no_grad():
             for work, flat, ps in self._inflight:
                 work.wait()
-                torch._foreach_copy_([_flat_view(p.grad) for p in ps], list(flat.split([p.numel() for p in ps])))
+                if flat is not None:
+                    torch._foreach_copy_([_flat_view(p.grad) for p in ps], list(flat.split([p.numel() for p in ps])))
         self._inflight = []
         self.attach(module)                                  # from the next backward on, buckets launch from the hooks
 

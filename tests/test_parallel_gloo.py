@@ -138,3 +138,47 @@ def test_learner_loader_checkpoint_world2_gloo(tmp_path):
     assert not torch.equal(r0["w_local"], r1["w_local"])
     torch.testing.assert_close(r0["w"], (r0["w_local"] + r1["w_local"]) / 2, rtol=1e-6, atol=1e-7)
     assert torch.equal(r0["w"], r1["w"])
+
+
+def _growth_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        import gan_lab_b200._growth as growth
+        from gan_lab_b200.config import default_config
+        from gan_lab_b200.data import DeviceImageLoader
+        from gan_lab_b200.parallel import DataParallel
+        from gan_lab_b200.stylegan.learner import StyleGANLearner
+        from oracle import kernel_contracts
+        kernel_contracts.install(_Patch)
+        growth.FMAP_MAX = 32
+        torch.manual_seed(200 + rank); np.random.seed(5)     # every rank's own RNG: increase_scale() draws the new blocks from it
+        cfg = default_config("StyleGAN", res=8, init_res=4, batch_size=4, dev="cpu", len_latent=32, len_dlatent=32,
+                             cutoff_trunc_trick=1, nimg_transition=8)
+        L = StyleGANLearner(cfg)
+        L.dp = DataParallel(world, bucket_bytes=4096)
+        L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model); L.dp.broadcast_params(L.gen_model_lagged)
+        images = torch.randint(0, 256, (32, 16, 16, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+        dl = DeviceImageLoader(images, batch_size=4, res=4, shuffle=True, device="cpu", seed=3, rank=rank, world_size=world)
+        L.train(dl, num_main_iters=3)                       # 2 iterations at 4x4, growth, 1 iteration of the 8x8 fade-in
+        ret[rank] = dict(res=int(L.gen_model.curr_res), fade=bool(L.gen_model.fade_in_phase),
+                         g=[p.detach().clone() for p in L.gen_model.parameters()],
+                         d=[p.detach().clone() for p in L.disc_model.parameters()],
+                         lag=[p.detach().clone() for p in L.gen_model_lagged.parameters()])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_growth_keeps_replicas_identical_world2_gloo():
+    """increase_scale() initialises the new blocks / torgb / fromrgb from each rank's own RNG: train() must re-broadcast rank 0's
+    parameters (and the EWMA generator) after a growth, or the replicas differ from then on although gradients are averaged."""
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_growth_worker, args=(world, port, ret), nprocs=world, join=True)
+    r0, r1 = ret[0], ret[1]
+    assert r0["res"] == r1["res"] == 8
+    for key in ("g", "d", "lag"):
+        assert len(r0[key]) == len(r1[key])
+        for a, b in zip(r0[key], r1[key]):
+            assert torch.equal(a, b), key
