@@ -862,6 +862,33 @@ def kernel_rooflines(L, x, main_iter, flush):
             "achieved": tot_f / (tot_ms / 1e3) / 1e12, "unit": "TFLOP/s", "traffic": None, "launches": n_launch,
             "avg_launch_us": 1e3 * tot_ms / max(n_launch, 1), "conv_ms_per_step": tot_ms,
             "by_kind_tflops": {n: v[0] / (v[1] / 1e3) / 1e12 for n, v in by.items()}}
+    # layers whose arithmetic intensity (algorithmic FLOPs / compulsory bytes: operands + output, 4 B each) lies
+    # below the ridge of the machine -- 3-channel / 16-32-channel layers at high resolution, weight-bound layers with M <= 512
+    # pixels -- are HBM-bound and belong on the HBM roofline; the rest on the tensor roofline.  Both classes timed separately.
+    try:
+        pk = measured_peaks()
+        ridge = pk["tf"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+        cls = {"tensor_bound": [], "hbm_bound": []}
+        for c in calls:
+            if c[0] in conv_kinds:
+                a = c[2]
+                nb = 4.0 * sum(t.numel() for t in a if torch.is_tensor(t))
+                out_elems = {"conv_fprop": lambda: a[0].shape[0] * a[1].shape[0] * (a[0].shape[2] + 2 * a[3] - a[1].shape[2] + 1) * (a[0].shape[3] + 2 * a[3] - a[1].shape[3] + 1),
+                             "conv_dgrad": lambda: a[0].shape[0] * a[1].shape[1] * a[2][0] * a[2][1],
+                             "conv_wgrad": lambda: a[1].shape[1] * a[0].shape[1] * a[2][0] * a[2][1]}[c[0]]()
+                nb += 4.0 * out_elems
+                cls["tensor_bound" if c[4] / nb >= ridge else "hbm_bound"].append((c, nb))
+        split = {"ridge_flop_per_byte": ridge}
+        for name, sel in cls.items():
+            if not sel:
+                continue
+            ms_ = timed([c for c, _ in sel])
+            fl, by_ = sum(c[4] for c, _ in sel), sum(nb for _, nb in sel)
+            split[name] = {"launches": len(sel), "ms_per_step": ms_, "tflops": fl / (ms_ / 1e3) / 1e12, "gbs": by_ / (ms_ / 1e3) / 1e9,
+                           "frac_of_tensor_peak": fl / (ms_ / 1e3) / 1e12 / pk["tf"], "frac_of_hbm_peak": by_ / (ms_ / 1e3) / 1e9 / pk["hbm_gbs"]}
+        conv["split_by_roofline"] = split
+    except Exception as e:          # noqa: BLE001 -- an auxiliary breakdown
+        conv["split_by_roofline"] = {"error": repr(e)[:200]}
 
     # glue: launches that move >= 4 MB are HBM-bound and make up the roofline figure; the small ones (latents, 4x4 / 8x8
     # maps, scalars) are launch-latency bound and reported separately as time only

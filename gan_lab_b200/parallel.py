@@ -5,7 +5,9 @@ naturally: samples are independent in G (InstanceNorm is per-sample) and in D ex
 whose groups are 4 CONSECUTIVE samples -- with a per-GPU batch that is a multiple of 4 every group stays on one
 rank, so averaging the per-rank gradients reproduces the single-GPU gradient of the N-times larger batch
 (all losses are batch means).  The only exchange step is therefore the gradient all-reduce before each
-optimiser step; parameters, Adam state and the EWMA generator are replicated.
+optimiser step; parameters, Adam state and the EWMA generator are replicated.  (Not so for the ResNet GAN:
+its generator's BatchNorm sees per-rank batch statistics -- standard DDP semantics, not the single-GPU result at the larger
+batch -- and its running buffers are averaged over the ranks where they are observed, GANLearner._sync_bn_buffers.)
 
 Overlap with backward: every parameter carries a post-accumulate-grad hook; as soon as the gradients that have become
 ready fill a bucket (in autograd order: last layers first) the bucket is packed (one `torch.cat`),

@@ -159,6 +159,7 @@ class ProGANLearner(GANLearner):
         """After increase_scale(): give the lagged generator the new blocks (initialised from the live ones) and
         carry torgb -> prev_torgb over, as reference progan/learner.py:660-686 does on `lagged_params`."""
         old = {n: p.detach().clone() for n, p in self.gen_model_lagged.named_parameters()}
+        fresh = []
         with torch.no_grad():
             self.gen_model_lagged = copy.deepcopy(self.gen_model)
             for n, p in self.gen_model_lagged.named_parameters():
@@ -169,6 +170,11 @@ class ProGANLearner(GANLearner):
                     src = old.get(n)
                 if src is not None and src.shape == p.shape:
                     p.copy_(src)
+                else:
+                    fresh.append(n)
+        # the reference ALIASES lagged_params[name] to the live Parameter for every new name (:664-666): their first update after
+        # the growth yields lagged = post-Adam parameter; reproduced after the next generator step (see gen_step)
+        self._fresh_lagged = fresh
         self._init_lagged_keep_started()
 
     def _init_lagged_keep_started(self):
@@ -272,6 +278,14 @@ class ProGANLearner(GANLearner):
         self.opt_gen.step()      # Adam + EWMA generator in one fused pass
         if c.use_ewma_gen:
             self._ewma_started = True
+            fresh = getattr(self, '_fresh_lagged', None)
+            if fresh:            # first generator step after a growth (always an eager iteration): new names start from the live values
+                live = dict(self.gen_model.named_parameters())
+                with torch.no_grad():
+                    for n in fresh:
+                        if n in self.lagged_params and n in live:
+                            self.lagged_params[n].copy_(live[n])
+                self._fresh_lagged = []
         return loss_train_gen.detach()
 
     # ------------------------------------------------------------------ CUDA-graph replay of the two steps

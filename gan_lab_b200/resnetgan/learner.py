@@ -383,6 +383,8 @@ class GANLearner(object):
         logit losses without penalty or drift term, weighted by batch length) and 'image grid'.  Returns the reference's
         formatted lines; the raw values are kept in `self.last_metrics`."""
         c = self.config
+        if type(self) is GANLearner:
+            self._sync_bn_buffers()
         metrics_type = metrics_type.casefold()
         if metrics_type not in ('generator', 'critic', 'discriminator'):
             raise Exception('Invalid metrics_type. Only "generator", "critic", or "discriminator" are accepted.')
@@ -541,11 +543,27 @@ class GANLearner(object):
                 {'disc_model_downsampler': ckpt.to_reference_module(self.disc_model_downsampler),
                  'num_classes_disc': self.num_classes_disc})
 
+    def _sync_bn_buffers(self):
+        """Data parallelism: the generator's BatchNorm uses per-rank batch statistics (standard DDP semantics -- NOT the
+        single-GPU result at the N-times larger batch), so its running_mean / running_var buffers drift apart per rank.  Where
+        they are observed (checkpoints, validation metrics) they are averaged over the ranks first (collective: every rank
+        calls it).  With a per-rank batch that is not a multiple of the minibatch-stddev group the discriminator's groups would
+        straddle ranks: refused."""
+        dp = self.dp
+        if dp is None or getattr(dp, 'world', 1) == 1:
+            return
+        for net in (self.gen_model, self.disc_model):
+            for b in net.buffers():
+                if b.is_floating_point():
+                    dp.allreduce_mean_(b)
+
     def save_model(self, save_path):
         """reference resnetgan/learner.py:1076-1137; the file is readable by the reference's own load_model.  Under data
-        parallelism only rank 0 writes (replicas are identical)."""
+        parallelism only rank 0 writes (parameters are identical on every rank; BatchNorm buffers are averaged first)."""
         from pathlib import Path
         from .. import checkpoint as ckpt
+        if type(self) is GANLearner:
+            self._sync_bn_buffers()
         if self.dp is not None and getattr(self.dp, 'rank', 0) != 0:
             return
         gmeta, dmeta = self._model_metadata()

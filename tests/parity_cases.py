@@ -167,7 +167,7 @@ def case_style_epilogue_op(golden, dev):
     close(nw.grad, g["g_noise_weight"], rtol=1e-3); close(b.grad, g["g_bias"], rtol=1e-3)
 
 
-def _grads_ok(module, ref, rtol, skip_cancelled=False):
+def _grads_ok(module, ref, rtol, skip_cancelled=False, report=None, tag=""):
     """Per-tensor max-norm relative error.  skip_cancelled: gradients that are analytically zero (a conv bias feeding a
     BatchNorm) hold only rounding noise in the fixture; they are compared against 5e-2 of the largest gradient instead."""
     floor = 0.0
@@ -183,6 +183,8 @@ def _grads_ok(module, ref, rtol, skip_cancelled=False):
                 continue
             r = r.to(p.grad.dtype)
             err = float((p.grad.detach() - r).abs().max() / r.abs().max().clamp_min(max(floor, 1e-30)))
+            if report is not None and err > report.get(tag, (0.0, None))[0]:
+                report[tag] = (err, k)
             assert err < rtol, (k, err)
 
 
@@ -757,7 +759,7 @@ def _resnet_learner(g, dev, **over):
         RA.FMAP_G, RA.FMAP_D = old
 
 
-def case_resnet_nets_modules(golden, dev, fname, dtype=torch.float32, grad_tol=5e-2):
+def case_resnet_nets_modules(golden, dev, fname, dtype=torch.float32, grad_tol=5e-2, report=None, d_grad_tol=None):
     """ResNet generator (BatchNorm blocks, Tanh) / discriminator (LayerNorm blocks) forward, backward and the WGAN-GP
     double backward vs the reference's modules; also the BatchNorm running buffers after one forward.
 
@@ -765,7 +767,11 @@ def case_resnet_nets_modules(golden, dev, fname, dtype=torch.float32, grad_tol=5
     within fp32 rounding of zero; an implementation that rounds differently flips such a mask bit, which moves every
     gradient behind it by ~1e-3..1e-2 of its max-norm (measured: the reference's own fp32 vs fp64).  fp32 runs therefore
     use grad_tol = 5e-2 (forward values stay at 1e-4); the CPU host-wiring test runs the same case in fp64, where no bit
-    flips, at 2e-5 -- i.e. down to the fp32 noise of the fixture itself."""
+    flips, at 2e-5 -- i.e. down to the fp32 noise of the fixture itself.  Measured on B200 (fp32 kernels): only the GENERATOR
+    (BatchNorm + ReLU) shows such flips (3.7e-2 on one skip-connection weight of the 64x64 net, 8e-6 at 32x32); the
+    discriminator's gradients, including the WGAN-GP double backward through its LayerNorm blocks, agree to 2e-6 -- the GPU test
+    therefore holds them to d_grad_tol = 2e-4."""
+    d_grad_tol = grad_tol if d_grad_tol is None else d_grad_tol
     g = _to(golden(fname), dev)
     L, cfg = _resnet_learner(g, dev)
     G, D = L.gen_model, L.disc_model
@@ -780,7 +786,7 @@ def case_resnet_nets_modules(golden, dev, fname, dtype=torch.float32, grad_tol=5
     # max-norm relative error (Tanh output, |img| <= 1): an element-wise bound near the zero crossings depends on the CPU's
     # summation order, i.e. on the thread count the doubles happen to run with
     assert relerr(img, c(g["img"])) < ftol
-    G.zero_grad(); img.backward(c(g["gimg"])); _grads_ok(G, g["g_grads"], grad_tol, skip_cancelled=True)
+    G.zero_grad(); img.backward(c(g["gimg"])); _grads_ok(G, g["g_grads"], grad_tol, skip_cancelled=True, report=report, tag="g_grads")
     for k, v in G.named_buffers():
         if k.endswith("num_batches_tracked"):
             assert int(v) == int(g["g_buffers"][k])
@@ -788,12 +794,12 @@ def case_resnet_nets_modules(golden, dev, fname, dtype=torch.float32, grad_tol=5
             close(v, c(g["g_buffers"][k]), rtol=1e-4, atol=1e-6)
     D.zero_grad()
     logits = D(c(g["x"])); close(logits, c(g["logits"]), rtol=ftol, atol=ftol / 10)
-    logits.backward(c(g["glog"])); _grads_ok(D, g["d_grads"], grad_tol)
+    logits.backward(c(g["glog"])); _grads_ok(D, g["d_grads"], d_grad_tol, report=report, tag="d_grads")
     D.zero_grad()
     set_random_source(TapeSource(g["gp_tape"], dev))
     pen = L.calc_gp(c(g["img"]), c(g["x"]))
     assert relerr(pen, c(g["gp"])) < ftol
-    pen.backward(); _grads_ok(D, g["d_gp_grads"], max(grad_tol, 5e-4))
+    pen.backward(); _grads_ok(D, g["d_gp_grads"], max(d_grad_tol, 2e-4), report=report, tag="d_gp_grads")
 
 
 def case_resnet_train(golden, dev, fname="resnet_train_res64.pt"):

@@ -7,6 +7,8 @@ Run on the B200 box:  python -m pytest tests -m gpu
 """
 import math
 
+import os
+
 import pytest
 import torch
 
@@ -83,6 +85,7 @@ def test_conv_family_vs_contract(shape):
 # TF32 tensor-core path (tcgen05): operands are truncated to 10 mantissa bits, accumulation is fp32.  Stated bound: 3e-3 of
 # the tensor's max-norm (measured ~8e-4 on B200 over K = 288..4608); the fp32 FFMA path above keeps the 1e-4 bar.
 TOL_TF32 = 3e-3
+RESNET_GRAD_TOL = 5e-2      # whole-net ResNet gradients on the fp32 path (see parity_cases.case_resnet_nets_modules)
 TC_SHAPES = [  # N, H, W, Ci, Co, R, pad
     (8, 4, 4, 512, 512, 3, 1), (8, 16, 16, 512, 512, 3, 1), (2, 32, 32, 256, 128, 3, 1), (2, 64, 64, 128, 256, 3, 1),
     (4, 8, 8, 96, 128, 3, 1), (3, 5, 7, 32, 64, 3, 1), (2, 16, 16, 64, 32, 3, 1), (2, 32, 32, 128, 128, 1, 0),
@@ -511,7 +514,16 @@ def test_shared_penalty_forward(gp):
 
 @pytest.mark.parametrize("fname", PC.RESNET_NETS)
 def test_resnet_nets_modules(golden, fname):
-    PC.case_resnet_nets_modules(golden, DEV, fname)
+    report = {}
+    try:
+        PC.case_resnet_nets_modules(golden, DEV, fname, grad_tol=RESNET_GRAD_TOL, report=report, d_grad_tol=2e-4)
+    finally:
+        d = os.environ.get("GLB_DUMP_PARITY")
+        if d:
+            import json
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "resnet_nets_" + fname.replace(".pt", ".json")), "w") as f:
+                json.dump(report, f)
 
 
 def test_resnet_train(golden):
