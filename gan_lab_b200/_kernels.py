@@ -75,6 +75,72 @@ def _flat(t):
     return None if t is None else t.detach().reshape(-1).contiguous()
 
 
+# --------------------------------------------------------------------------- zeroed accumulators
+# Per-channel gradient accumulators (bias / noise-weight / RGB-weight gradients, penalty sums) are filled by atomics and need a
+# zeroed buffer: ~80 of them per StyleGAN iteration, each a `torch.zeros` = one fill kernel.  Inside a learner step they are
+# carved from ONE arena per step kind that is cleared by a single memset when the next step of that kind begins (a captured
+# step replays that memset); outside a step (tests, metrics) `_zeros` is plain `torch.zeros`.
+class _ZeroArena(object):
+    CAP = 1 << 19                     # floats (2 MB): a cfg2 step uses ~60 K; cleared as a whole (~1 us), whatever was used
+
+    def __init__(self):
+        self.buf, self.off = None, 0
+
+    def begin(self, device):
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device(device.type, torch.cuda.current_device())
+        if self.buf is None or self.buf.device != device:
+            if torch.cuda.is_current_stream_capturing():
+                self.buf = None       # never allocate the arena inside a capture (it must outlive the graph's pool)
+                return
+            self.buf = torch.zeros(self.CAP, device=device, dtype=torch.float32)
+        else:
+            self.buf.zero_()
+        self.off = 0
+
+    def take(self, n):
+        m = (n + 3) & ~3              # 16-byte aligned slices
+        if self.buf is None or self.off + m > self.CAP:
+            return None
+        out = self.buf[self.off:self.off + n]
+        self.off += m
+        return out
+
+
+_arenas = {}
+_active_arena = [None]
+_ARENA_OFF = bool(__import__("os").environ.get("GLB_NO_ARENA"))       # A/B measurements
+
+
+def begin_step(tag, device):
+    """Called by the learners at the start of a discriminator / generator step (one arena per `tag`: the gradients of one
+    step kind stay valid until the next step of the SAME kind begins)."""
+    if _ARENA_OFF:
+        return
+    a = _arenas.get(tag)
+    if a is None:
+        a = _arenas[tag] = _ZeroArena()
+    a.begin(device)
+    _active_arena[0] = a
+
+
+def end_step():
+    _active_arena[0] = None
+
+
+def _zeros(shape, like):
+    n = 1
+    for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
+        n *= int(d)
+    a = _active_arena[0]
+    if a is not None and a.buf is not None and a.buf.device == like.device:
+        t = a.take(n)
+        if t is not None:
+            return t.view(shape)
+    return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+
 # --------------------------------------------------------------------------- conv family
 _KIND = {"fprop": 0, "dgrad": 1, "wgrad": 2}
 
@@ -534,7 +600,7 @@ def act_bwd(gy, y, want_bias, bias_scale, act, slope):
     _chk(gy, y)
     y, P, C = _rows(y)
     gy, _, _ = _rows(gy)
-    gb = torch.zeros(C, device=gy.device, dtype=torch.float32) if want_bias else None
+    gb = _zeros(C, gy) if want_bias else None
     if C % 4 == 0 and ((C // 4) > 256 or 256 % (C // 4) == 0):
         gx = torch.empty_like(gy)
         _call("glb_act_bwd", _p(gy), _p(y), _p(gx), _p(gb), P, C, float(bias_scale), int(act), float(slope), _stream())
@@ -545,7 +611,7 @@ def act_bwd(gy, y, want_bias, bias_scale, act, slope):
 def colsum(x, scale):
     _chk(x)
     x, P, C = _rows(x)
-    out = torch.zeros(C, device=x.device, dtype=torch.float32)
+    out = _zeros(C, x)
     _call("glb_colsum", _p(x), _p(out), P, C, float(scale), _stream())
     return out
 
@@ -619,7 +685,7 @@ def sumsq(x, scale):
     _chk(x)
     if not (x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))):
         x = x.contiguous()
-    out = torch.zeros((), device=x.device, dtype=torch.float32)
+    out = _zeros((), x)
     _call("glb_sumsq", _p(x), _p(out), x.numel(), float(scale), _stream())
     return out
 
@@ -628,7 +694,7 @@ def gp_norm_fwd(g, gamma, scale):
     _chk(g)
     g = g.contiguous()
     N, C = g.shape[0], g.shape[1]
-    out = torch.zeros((), device=g.device, dtype=torch.float32)
+    out = _zeros((), g)
     _call("glb_gp_norm_fwd", _p(g), _p(out), N, C, g.numel() // (N * C), float(gamma), float(scale), _stream())
     return out
 
@@ -686,7 +752,7 @@ def blur_act_bwd(gz, y, want_bias, bias_scale, act, slope):
         g0 = blur3x3(gz)
         return act_bwd(g0, y, want_bias, bias_scale, act, slope)
     g = torch.empty_like(y)
-    gb = torch.zeros(C, device=y.device, dtype=torch.float32) if want_bias else None
+    gb = _zeros(C, y) if want_bias else None
     _call("glb_blur_act_bwd", _p(gz), _p(y), _p(g), _p(gb), N, H, W, C, float(bias_scale), int(act), float(slope), _stream())
     return g, gb
 
@@ -725,7 +791,7 @@ def pool_bias_act_bwd(gy, y, want_bias, bias_scale, act, slope):
     y = nhwc(y) if y is not None else None
     N, C, Hh, Wh = gy.shape
     gx = _new_nhwc(N, C, 2 * Hh, 2 * Wh, gy)
-    gb = torch.zeros(C, device=gy.device, dtype=torch.float32) if want_bias else None
+    gb = _zeros(C, gy) if want_bias else None
     _call("glb_pool_bias_act_bwd", _p(gy), _p(y), _p(gx), _p(gb), N, 2 * Hh, 2 * Wh, C, float(bias_scale), int(act), float(slope),
           _stream())
     return gx, gb
@@ -754,8 +820,8 @@ def style_epilogue_bwd(gout, x, noise, noise_weight, bias, style, stats, slope):
     style = style.contiguous()
     gx = torch.empty_like(x)
     gstyle = torch.empty_like(style)
-    g_nw = torch.zeros(C, device=x.device, dtype=torch.float32) if noise_weight is not None else None
-    g_b = torch.zeros(C, device=x.device, dtype=torch.float32) if bias is not None else None
+    g_nw = _zeros(C, x) if noise_weight is not None else None
+    g_b = _zeros(C, x) if bias is not None else None
     work = torch.empty(LIB.fn("glb_style_epilogue_work_floats")(N, H, W, C), device=x.device, dtype=torch.float32)
     _call("glb_style_epilogue_bwd", _p(gout), _p(x), _p(noise_c), _p(_flat(noise_weight)), _p(_flat(bias)), _p(style), _p(stats),
           _p(gx), _p(gstyle), _p(g_nw), _p(g_b), _p(work), N, H, W, C, float(slope), _stream())
@@ -931,7 +997,7 @@ def rgb_wgrad(img, g, w_shape, ws_j, ws_c, pool, alpha):
     img = img.contiguous()
     g = nhwc(g)
     N, C, H, W = g.shape
-    gw = torch.zeros(w_shape, device=g.device, dtype=torch.float32)
+    gw = _zeros(tuple(w_shape), g)
     _call("glb_rgb_wgrad", _p(img), _p(g), _p(gw), ws_j, ws_c, N, H, W, C, int(pool), float(alpha), _stream())
     return gw
 
@@ -940,7 +1006,7 @@ def plane_sum(img, scale):
     _chk(img)
     img = img.contiguous()
     N, C = img.shape[0], img.shape[1]
-    out = torch.zeros(C, device=img.device, dtype=torch.float32)
+    out = _zeros(C, img)
     _call("glb_plane_sum", _p(img), _p(out), N, C, img.numel() // (N * C), float(scale), _stream())
     return out
 

@@ -195,6 +195,15 @@ class ProGANLearner(GANLearner):
     def disc_step(self, xb):
         """One discriminator step on real batch `xb` (reference progan/learner.py:734-816).  Returns the loss tensor."""
         c = self.config
+        if str(c.dev).startswith('cuda'):
+            K.begin_step('disc', c.dev)
+        try:
+            return self._disc_step(xb)
+        finally:
+            K.end_step()
+
+    def _disc_step(self, xb):
+        c = self.config
         self.disc_model.zero_grad()
         zb = gen_rand_latent_vars(num_samples=self.batch_size, length=c.len_latent, distribution=self.latent_distribution,
                                   device=c.dev)
@@ -254,6 +263,10 @@ class ProGANLearner(GANLearner):
                 loss_train_disc = loss_train_disc + self.calc_gp(_xgenb, xb)
             loss_train_disc.backward()
         if self.dp is not None:
+            group = c.mbstd_group_size
+            if group and group > 1 and self.batch_size % min(group, self.batch_size) != 0:
+                raise ValueError("data parallelism needs a per-GPU batch that is a multiple of the minibatch-stddev group "
+                                 f"({self.batch_size} vs {group}): a group must not straddle ranks (SURVEY.md 8e)")
             self.dp.allreduce_grads(self.disc_model)
         self.opt_disc.step()
         return loss_train_disc.detach()
@@ -266,6 +279,15 @@ class ProGANLearner(GANLearner):
 
     def gen_step(self):
         """One generator step (reference progan/learner.py:854-916).  Returns the loss tensor."""
+        c = self.config
+        if str(c.dev).startswith('cuda'):
+            K.begin_step('gen', c.dev)
+        try:
+            return self._gen_step()
+        finally:
+            K.end_step()
+
+    def _gen_step(self):
         c = self.config
         self.gen_model.zero_grad()
         zb = gen_rand_latent_vars(num_samples=self.batch_size * c.gen_bs_mult, length=c.len_latent,
