@@ -348,6 +348,8 @@ def run_ours(args):
                             bucket_bytes=int(float(mb) * 1024 * 1024) if mb else None,
                             inplace=(os.environ["GLB_DP_INPLACE"] != "0") if "GLB_DP_INPLACE" in os.environ else None)
         L.dp.broadcast_params(L.gen_model); L.dp.broadcast_params(L.disc_model)
+        if os.environ.get("GLB_DP_OVERLAP_D"):           # A/B: D's all-reduce + Adam beside the generator forward of the G step
+            L.overlap_d_update = os.environ["GLB_DP_OVERLAP_D"] != "0"
     def log(msg):
         if args.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
@@ -511,6 +513,7 @@ def run_ours(args):
                        "d_fake_real_one_pass": bool(getattr(L, "batch_d_passes", False)),
                        "grad_allreduce": (f"NCCL all-reduce ({'in place, grouped, ncclAvg' if L.dp.inplace else 'packed buckets'}), "
                                           f"{L.dp.bucket_bytes >> 20} MiB buckets launched from grad hooks as they fill"
+                                          + ("; D's all-reduce + Adam overlapped with the generator forward of the G step" if getattr(L, "overlap_d_update", False) else "")
                                           if world > 1 else None), "l2": "8-batch input pool; activations per step (>1 GB) exceed the 126 MB L2",
                        "algorithmic_conv_gflop_per_step_per_gpu": flops / 1e9,
                        "achieved_conv_tflops_whole_step": flops / (ms / args.steps / 1e3) / 1e12},

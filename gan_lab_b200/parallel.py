@@ -67,7 +67,7 @@ class DataParallel(object):
             return
         for m in modules:
             for p in m.parameters():
-                if id(p) not in self._hooked:
+                if id(p) not in self._hooked and p.requires_grad:     # (frozen for the moment: hooked at a later call)
                     p.register_post_accumulate_grad_hook(self._on_grad)
                     self._hooked.add(id(p))
 
