@@ -34,8 +34,8 @@ def _dump(tag, out):
 # (tests/golden/cfg2_reference_on_b200_deviation.json, measured by tests/calibrate_tf32_bounds.py on the same fixture): at random
 # initialisation leaky-ReLU masks within rounding of zero and mean-removing InstanceNorms amplify a 5e-4 operand rounding to
 # 2-8 % (median over tensors) / up to 80 % (cancellation-dominated bias gradients of the R1 penalty) in ANY TF32 implementation.
-FP32_LOSS, FP32_MULT = 1e-4, 4.0
-TF32_MULT = 1.6
+FP32_LOSS, FP32_MULT = 1e-4, 6.0     # measured: <= 3.6x the floor (split-K / atomics order varies run to run)
+TF32_MULT = 2.0                       # measured: 0.9-1.3x the yardstick
 BF16_MULT = 12.0         # bf16 operands carry 8 mantissa bits: 4x the TF32 rounding step; measured 2-10x the yardstick (opt-in mode,
                          # not the default: image 2 %, logits 3 %, gradients 9-19 % (median over tensors) at random initialisation)
 
