@@ -3,11 +3,9 @@ channels), tensor-core (TF32) convolutions, run eagerly and as the captured-and-
 iteration of the UNMODIFIED reference (tests/golden/style_cfg2_fullwidth_step.pt, made by oracle/make_golden.py from
 progan/learner.py:734-916 + stylegan/architectures.py:411-528 on CPU fp32).
 
-Bounds (per tensor: estimated relative L2 error of the WHOLE tensor from random projections, and max-norm error on a strided
-sample, see oracle/summaries.py):
-  fp32 path (exact FFMA convolutions)         losses 1e-4, gradients 1e-3 (the reference's own fp32 reassociation noise is 6e-5)
-  TF32 path (tcgen05 kind::tf32, benchmarked)  losses 2e-3, gradients 2e-2 (L2) -- operands rounded to 10 mantissa bits per conv,
-                                               ~20 convolutions deep, R1 double backward twice as deep
+Errors are per tensor: the estimated relative L2 error of the WHOLE tensor (random projections) and the max-norm error on a
+strided sample (oracle/summaries.py).  Bounds are multiples of two measured yardsticks, see the comment above FP32_MULT and
+DESIGN.md section 2 ("The benchmarked path, pinned") for the measured values.
 """
 import json
 import os
