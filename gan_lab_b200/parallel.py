@@ -10,16 +10,17 @@ its generator's BatchNorm sees per-rank batch statistics -- standard DDP semanti
 batch -- and its running buffers are averaged over the ranks where they are observed, GANLearner._sync_bn_buffers.)
 
 Overlap with backward: every parameter carries a post-accumulate-grad hook; as soon as the gradients that have become
-ready fill a bucket (in autograd order: last layers first) the bucket is packed (one `torch.cat`),
-pre-scaled by 1/world and all-reduced asynchronously -- NCCL runs on the process group's own stream while the compute
-stream keeps executing the rest of backward (including the R1 double-backward tail).  `allreduce_grads()` after backward
-only flushes the last partial bucket, makes the compute stream wait for the collectives and scatters the reduced buckets
-back into the gradients (one multi-tensor copy per bucket).  All of this is stream-ordered, so it is captured into the
-step's CUDA graph as parallel branches.  Default bucket size: 32 MiB on 2 GPUs, 128 MiB (= ONE all-reduce per network,
-issued when its backward has finished) on more: measured on 8 B200s (cfg2) 4432 img/s against 4389 with 32 MiB buckets
-launched during backward and 4392 with 8 MiB buckets -- the persistent tensor-core kernels occupy every SM, so an NCCL
-kernel that starts mid-backward displaces convolution CTAs, and with more ranks the small-message all-reduces are less
-efficient than one 92-104 MB one; on 2 GPUs the overlap still wins (1151 vs 1123).  Bucket composition follows the autograd order, which is identical on every rank (same graph on every rank).
+ready fill a bucket (in autograd order: last layers first) the bucket is all-reduced asynchronously -- NCCL runs on the process
+group's own stream while the compute stream keeps executing the rest of backward (including the R1 double-backward tail).  With
+NCCL the gradients of a bucket are reduced IN PLACE as one grouped call (ncclGroupStart / ncclAllReduce(ncclAvg) per tensor /
+ncclGroupEnd): no pack, pre-scale or scatter-back pass; other backends (the gloo CPU tests) pack the bucket with `torch.cat`,
+pre-scale by 1/world and copy back.  `allreduce_grads()` after backward only flushes the last partial bucket and makes the compute
+stream wait for the collectives.  All of this is stream-ordered, so it is captured into the step's CUDA graph as parallel branches.
+Default bucket size: 32 MiB on 2 GPUs, 128 MiB (= ONE group per network, issued when its backward has finished) on more: measured
+on 8 B200s (cfg2, round 1) 4432 img/s against 4389 with 32 MiB buckets launched during backward -- the persistent tensor-core
+kernels occupy every SM, so an NCCL kernel that starts mid-backward displaces convolution CTAs; on 2 GPUs the overlap wins (1151 vs
+1123).  Round 2, in place: 1171 / 2302 / 4502 img/s on 2 / 4 / 8 GPUs.  Bucket composition follows the autograd order, which is
+identical on every rank (same graph on every rank).
 """
 import torch
 import torch.distributed as dist

@@ -50,7 +50,8 @@ class ProGANLearner(GANLearner):
         # D(fake) and D(real) as ONE pass over the concatenated batch: identical values (samples are independent in D except
         # minibatch-stddev, whose groups of `mbstd_group_size` consecutive samples stay inside one half when the batch size is a
         # multiple of it), half the discriminator launches, twice the work per launch in the latency-bound low-resolution layers,
-        # no gradient accumulation between the two passes.  Opt-in until measured on the GPU (bench: GLB_BATCH_D=1).
+        # no gradient accumulation between the two passes.  Measured on B200 (cfg2): SLOWER, 568 vs 617 img/s (the R1 double
+        # backward then runs over the whole 2N-sample graph) -- kept as an option (bench: GLB_BATCH_D=1), off.
         self.batch_d_passes = False
         self.parallel_d_passes = False     # two-stream D passes: measured neutral on B200 (598 vs 596 img/s at cfg2), kept as an option
         self._side_stream = None
