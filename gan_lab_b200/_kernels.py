@@ -8,6 +8,8 @@ No CPU path: a non-CUDA tensor raises.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ._lib import LIB, GlbError
@@ -177,6 +179,7 @@ def weights_updated():
     _wp_cache.clear()
     _pk_cache.clear()
     _b16_cache.clear()
+    _up_cache.clear()
 
 
 # ---- bf16 operand copies (conv_impl "bf16") -----------------------------------------------------------------------------
@@ -222,10 +225,11 @@ def _cache_put(cache, key, version, tensor, w):
     """Cache entries remember the stream that produced them and an event recorded behind the producing kernels: a hit from
     ANOTHER stream (the learners run independent discriminator passes on two streams) waits for that event first."""
     ev = None
-    if tensor.is_cuda:
+    on_gpu = (tensor[0] if isinstance(tensor, tuple) else tensor).is_cuda
+    if on_gpu:
         ev = torch.cuda.Event()
         ev.record()
-    cache[key] = (version, tensor, w, ev, torch.cuda.current_stream().cuda_stream if tensor.is_cuda else None)
+    cache[key] = (version, tensor, w, ev, torch.cuda.current_stream().cuda_stream if on_gpu else None)
     return tensor
 
 
@@ -473,6 +477,74 @@ def conv_wgrad(x, gy, rs, pad, alpha):
         return gw[:, :ci_out].contiguous(memory_format=torch.channels_last)
     if cop is not None:
         return gw[:co_out].contiguous(memory_format=torch.channels_last)
+    return gw
+
+
+# ---- nearest-neighbour 2x upsample folded into the 3x3 convolution behind it (glb_upconv_*, TF32 tensor-core path) ---------
+# conv3x3(upsample2x(x)) as four 2x2 convolutions of the LOW-resolution x with pre-summed taps: 4/9 of the multiply-adds, no
+# upsampled copy.  GLB_UPCONV=0 switches back to the two-kernel sequence (A/B runs).
+_up_cache = {}
+
+
+def upconv_covers(kind: str, N, H, W, Ci, Co) -> bool:
+    """H, W: LOW-resolution map.  Only in "tf32" mode (the exact FFMA and the bf16-operand modes keep the two-kernel sequence)."""
+    if _state["conv_impl"] != "tf32" or os.environ.get("GLB_UPCONV", "1") == "0":
+        return False
+    return bool(LIB.fn("glb_upconv_covers")(_KIND[kind], N, H, W, Ci, Co))
+
+
+def upconv_weights(w):
+    """(wp [4*Co,2,2,Ci] for the forward, wt [Ci,16,Co] for the data gradient) of w [Co,Ci,3,3]; cached per weight version."""
+    key = (w.data_ptr(), tuple(w.shape))
+    hit = _cache_get(_up_cache, key, w._version)
+    if hit is not None:
+        return hit
+    Co, Ci, R, S = w.shape
+    wp = torch.empty((4 * Co, 2, 2, Ci), device=w.device, dtype=torch.float32)
+    wt = torch.empty((Ci, 16, Co), device=w.device, dtype=torch.float32)
+    _call("glb_upconv_weights", _p(w), _p(wp), _p(wt), Co, Ci, _stream())
+    if len(_up_cache) >= 32:
+        _up_cache.clear()
+    return _cache_put(_up_cache, key, w._version, (wp, wt), w)
+
+
+def upconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
+    _chk(x, w, bias)
+    x, w = nhwc(x), nhwc(w)
+    N, Ci, H, W = x.shape
+    Co, Ci2, R, S = w.shape
+    if Ci != Ci2 or R != 3 or S != 3:
+        raise GlbError("upconv_fprop: needs a 3x3 weight with matching channels")
+    wp, _ = upconv_weights(w)
+    y = _new_nhwc(N, Co, 2 * H, 2 * W, x)
+    _call("glb_upconv_fprop", _p(x), _p(wp), _p(_flat(bias)), _p(y), N, H, W, Ci, Co, float(alpha), float(bias_scale), int(act),
+          float(slope), _stream())
+    return y
+
+
+def upconv_dgrad(gy, w, alpha):
+    _chk(gy, w)
+    gy, w = nhwc(gy), nhwc(w)
+    N, Co, H2, W2 = gy.shape
+    Co2, Ci, R, S = w.shape
+    if Co != Co2 or H2 % 2 or W2 % 2:
+        raise GlbError("upconv_dgrad: shape mismatch")
+    _, wt = upconv_weights(w)
+    gx = _new_nhwc(N, Ci, H2 // 2, W2 // 2, gy)
+    _call("glb_upconv_dgrad", _p(gy), _p(wt), _p(gx), N, H2 // 2, W2 // 2, Ci, Co, float(alpha), _stream())
+    return gx
+
+
+def upconv_wgrad(x, gy, alpha):
+    _chk(x, gy)
+    x, gy = nhwc(x), nhwc(gy)
+    N, Ci, H, W = x.shape
+    N2, Co, H2, W2 = gy.shape
+    if N != N2 or H2 != 2 * H or W2 != 2 * W:
+        raise GlbError("upconv_wgrad: shape mismatch")
+    gwp = torch.empty((Co, 16, Ci), device=x.device, dtype=torch.float32)
+    gw = _new_nhwc(Co, Ci, 3, 3, x)
+    _call("glb_upconv_wgrad", _p(x), _p(gy), _p(gwp), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
     return gw
 
 

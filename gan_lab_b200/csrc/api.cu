@@ -103,3 +103,38 @@ extern "C" int glb_conv2d_wgrad_bf16(const void* x, const void* gy, float* gw, i
   if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0 || R <= 0 || S <= 0 || pad < 0) return glb::shape_fail("conv2d_wgrad_bf16");
   return glb::conv_wgrad_bf16(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, (cudaStream_t)stream);
 }
+
+// ---- nearest-neighbour 2x upsample folded into the following 3x3 convolution (csrc/conv_tc.cu) -----------------------------
+namespace glb {
+bool conv_upconv_covers(int kind, int N, int H, int W, int Ci, int Co);
+int conv_upconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, cudaStream_t st);
+int conv_upconv_fprop_tc(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
+                         float bias_scale, int act, float slope, cudaStream_t st);
+int conv_upconv_dgrad_tc(const float* gy, const float* wt, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st);
+int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                         cudaStream_t st);
+}  // namespace glb
+
+extern "C" int glb_upconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return 0;
+  return glb::conv_upconv_covers(kind, N, H, W, Ci, Co) ? 1 : 0;
+}
+extern "C" int glb_upconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, glb_stream_t stream) {
+  if (Co <= 0 || Ci <= 0) return glb::shape_fail("upconv_weights");
+  return glb::conv_upconv_weights(w, wp, wt, Co, Ci, (cudaStream_t)stream);
+}
+extern "C" int glb_upconv_fprop(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
+                                float alpha, float bias_scale, int act, float slope, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("upconv_fprop");
+  return glb::conv_upconv_fprop_tc(x, wp, bias, y, N, H, W, Ci, Co, alpha, bias_scale, act, slope, (cudaStream_t)stream);
+}
+extern "C" int glb_upconv_dgrad(const float* gy, const float* wt, float* gx, int N, int H, int W, int Ci, int Co, float alpha,
+                                glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("upconv_dgrad");
+  return glb::conv_upconv_dgrad_tc(gy, wt, gx, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
+}
+extern "C" int glb_upconv_wgrad(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
+                                float alpha, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("upconv_wgrad");
+  return glb::conv_upconv_wgrad_tc(x, gy, gwp, gw, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
+}

@@ -37,7 +37,17 @@ struct FpropParams {
   float alpha, bias_scale;
   int act;
   float slope;
+  // nearest-neighbour 2x upsample folded into a 3x3 "same" convolution (conv_fprop_tc_kernel / conv_fprop_tc2_kernel only):
+  //   up = 1: forward -- output phase (dy, dx) of pixel (2i+dy, 2j+dx) is a 2x2 convolution of the LOW-resolution input with
+  //           pre-summed taps (4/9 of the MMA work, no upsampled copy): the phase is part of the M index, pad = 1 - d per axis,
+  //           weights [4*Co][2][2][Ci] phase-major, (Ho, Wo) = the low-resolution grid, (OH, OW) = 2x that
+  //   up = 2: its data gradient -- K runs over (phase, tap, Co chunk): A comes from four strided views of the high-resolution
+  //           gradient (one tensor map per phase), weights [Ci][16][Co]
+  int up;
+  int OH, OW;         // dims of the output tensor (address computation); = (Ho, Wo) unless up == 1
 };
+
+struct alignas(64) TMapSet { CUtensorMap m[4]; };   // A-operand maps: m[0] only, or one per output phase (up == 2)
 
 // tcgen05 kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits (cuDNN's TF32 kernels round to nearest).  Truncation is
 // biased: for a log-uniform mantissa the expected relative error of an operand is 0.5 * 2^-10 * E[1/m] = 3.52e-4, i.e. every
@@ -75,7 +85,7 @@ constexpr int kFpropThreads = 384;  // warps 0-3: TMA producer, MMA issuer, TMEM
 
 template <int BN, int KC, bool BF>
 __global__ void __launch_bounds__(kFpropThreads, 1)
-conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+conv_fprop_tc_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
   using Cfg = FpropCfg<BN, KC>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int kChunk = BF ? 64 : 32;              // channels per 128-byte operand row (shadows the fp32 constant)
@@ -98,7 +108,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmAs.m[0]);
     prefetch_tmap(&tmB);
   }
   if (warp == 1 && lane == 0) {
@@ -128,10 +138,13 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int ks = item % p.ksplit;
         int t = item / p.ksplit;
         const int tco = t % p.tiles_co; t /= p.tiles_co;
+        int ph = 0;
+        if (p.up == 1) { ph = t & 3; t >>= 2; }
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int tn = t;
-        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, co0 = tco * BN;
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, co0 = tco * BN + ph * p.Co;
+        const int pad_h = p.up == 1 ? 1 - (ph >> 1) : p.pad, pad_w = p.up == 1 ? 1 - (ph & 1) : p.pad;
         const int k0 = ks * p.k_per, k1 = min(k_iters, k0 + p.k_per);
         int tap = k0 / chunks, ch = k0 - tap * chunks;
         for (int k = k0; k < k1; k += KC) {
@@ -139,9 +152,15 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
 #pragma unroll
           for (int c = 0; c < KC; ++c) {
-            const int r = tap / p.S, s = tap - r * p.S;
+            int mi = 0, dh, dw;
+            if (p.up == 2) {                              // tap = phase * 4 + a * 2 + b (taps already flipped in the weights)
+              mi = tap >> 2; dh = ((tap >> 1) & 1) - (mi >> 1); dw = (tap & 1) - (mi & 1);
+            } else {
+              const int r = tap / p.S, s = tap - r * p.S;
+              dh = r - pad_h; dw = s - pad_w;
+            }
             const uint32_t a_dst = base + stage * Cfg::kStageBytes + c * Cfg::kChunkBytes;
-            tma_load_4d(a_dst, &tmA, full_bar(stage), ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_4d(a_dst, &tmAs.m[mi], full_bar(stage), ch * kChunk, w0 + dw, h0 + dh, n0);
             tma_load_3d(a_dst + kABytes, &tmB, full_bar(stage), ch * kChunk, tap, co0);
             if (++ch == chunks) { ch = 0; ++tap; }
           }
@@ -204,12 +223,15 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
       int t = item / p.ksplit;
       const int tco = t % p.tiles_co; t /= p.tiles_co;
+      int ph = 0;
+      if (p.up == 1) { ph = t & 3; t >>= 2; }
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int tn = t;
       const int w = tw * p.bw + rw, h = th * p.bh + rh, n = tn * p.bn + rn, co0 = tco * BN;
       const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.N);
-      float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+      const int oh = p.up == 1 ? 2 * h + (ph >> 1) : h, ow = p.up == 1 ? 2 * w + (ph & 1) : w;
+      float* out = p.y + (((int64_t)n * p.OH + oh) * p.OW + ow) * p.Co + co0;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       if (tr && warp == 4 && lane == 0 && item == (int)blockIdx.x) tr[5] = clock64();   // first accumulator complete
@@ -663,7 +685,7 @@ struct Fprop2Cfg {
 
 template <int BN, bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
-conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+conv_fprop_tc2_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
   using Cfg = Fprop2Cfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int kChunk = BF ? 64 : 32;
@@ -687,7 +709,7 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmAs.m[0]);
     prefetch_tmap(&tmB);
   }
   if (warp == 1 && lane == 0) {
@@ -715,21 +737,30 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
         const int tco = item % p.tiles_co;
-        int t = (item / p.tiles_co) * 2 + (int)rank;  // this CTA's M tile
+        int u = item / p.tiles_co, ph = 0;
+        if (p.up == 1) { ph = u & 3; u >>= 2; }       // both M tiles of a pair belong to one output phase (they share B)
+        int t = u * 2 + (int)rank;                    // this CTA's M tile
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int tn = t;
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-        const int co0 = tco * BN + (int)rank * (BN / 2);  // this CTA's half of the weight tile
+        const int co0 = tco * BN + (int)rank * (BN / 2) + ph * p.Co;  // this CTA's half of the weight tile
+        const int pad_h = p.up == 1 ? 1 - (ph >> 1) : p.pad, pad_w = p.up == 1 ? 1 - (ph & 1) : p.pad;
         int tap = 0, ch = 0;
         for (int k = 0; k < k_iters; ++k) {
-          const int r = tap / p.S, s = tap - r * p.S;
+          int mi = 0, dh, dw;
+          if (p.up == 2) {
+            mi = tap >> 2; dh = ((tap >> 1) & 1) - (mi >> 1); dw = (tap & 1) - (mi & 1);
+          } else {
+            const int r = tap / p.S, s = tap - r * p.S;
+            dh = r - pad_h; dw = s - pad_w;
+          }
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + kABytes;
           if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
           const uint32_t lfull = mapa(full_bar(stage), 0);
-          tma2_load_4d(a_dst, &tmA, lfull, ch * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma2_load_4d(a_dst, &tmAs.m[mi], lfull, ch * kChunk, w0 + dw, h0 + dh, n0);
           tma2_load_3d(b_dst, &tmB, lfull, ch * kChunk, tap, co0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (++ch == chunks) { ch = 0; ++tap; }
@@ -776,13 +807,16 @@ conv_fprop_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint32_t aphase = 0;
     for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
       const int tco = item % p.tiles_co;
-      int t = (item / p.tiles_co) * 2 + (int)rank;
+      int u = item / p.tiles_co, ph = 0;
+      if (p.up == 1) { ph = u & 3; u >>= 2; }
+      int t = u * 2 + (int)rank;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int tn = t;
       const int w = tw * p.bw + rw, h = th * p.bh + rh, n = tn * p.bn + rn, co0 = tco * BN;
       const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.N);
-      float* out = p.y + (((int64_t)n * p.Ho + h) * p.Wo + w) * p.Co + co0;
+      const int oh = p.up == 1 ? 2 * h + (ph >> 1) : h, ow = p.up == 1 ? 2 * w + (ph & 1) : w;
+      float* out = p.y + (((int64_t)n * p.OH + oh) * p.OW + ow) * p.Co + co0;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -1271,7 +1305,7 @@ int launch_fprop2_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Fpr
 }
 
 template <int BN, bool BF = false>
-int launch_fprop2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+int launch_fprop2(const TMapSet& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = Fprop2Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -1319,7 +1353,7 @@ int launch_fprop_m2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropP
 }
 
 template <int BN, int KC, bool BF = false>
-int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+int launch_fprop(const TMapSet& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
   using Cfg = FpropCfg<BN, KC>;
   static bool configured = false;  // per-process, per-instantiation; attribute is sticky for the function
   if (!configured) {
@@ -1330,6 +1364,26 @@ int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropPara
   conv_fprop_tc_kernel<BN, KC, BF><<<grid, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc_kernel");
   return GLB_OK;
+}
+
+// Low-resolution layers: a handful of output tiles behind a long K loop is latency bound (one CTA streams K at ~0.3 us per
+// 32-channel step).  Pick the N tile and a split of K over CTAs (partials reduced with red.add) that minimise a simple cost
+// model: waves x (k steps x 0.3 us + epilogue).  Leaves (BN, ksplit) alone when the layer has at least half a wave of tiles.
+void pick_tile_and_split(int m_tiles, int Co, int k_iters, int& BN, int& ksplit) {
+  if (m_tiles * (Co / BN) >= kNumSMs / 2) return;
+  double best = 1e30;
+  for (int bn = 256; bn >= 32; bn >>= 1) {
+    if (Co % bn != 0) continue;
+    const int tiles = m_tiles * (Co / bn);
+    for (int sp = 1; sp <= 16; ++sp) {
+      const int kper = (k_iters + sp - 1) / sp;
+      if (sp > 1 && kper < 8) break;
+      const int items = tiles * ((k_iters + kper - 1) / kper);
+      const int waves = (items + kNumSMs - 1) / kNumSMs;
+      const double cost = waves * (kper * (0.28 + 0.0004 * bn) + (sp > 1 ? 0.06 : 0.012) * bn + 3.0);
+      if (cost < best) { best = cost; BN = bn; ksplit = sp; }
+    }
+  }
 }
 
 }  // namespace
@@ -1375,30 +1429,14 @@ static int conv_fprop_tc_impl(const void* x, const void* w, const float* bias, f
   const int k_iters = R * S * (Ci / kChunk);
   int BN = Co % 256 == 0 ? 256 : (Co % 128 == 0 ? 128 : Co);
   int ksplit = 1;
-  if (m_tiles * (Co / BN) < kNumSMs / 2) {
-    // Low-resolution layers: a handful of output tiles behind a long K loop is latency bound (one CTA streams K at
-    // ~0.3 us per 32-channel step).  Pick the N tile and a split of K over CTAs (partials reduced with red.add) that
-    // minimise a simple cost model: waves x (k steps x 0.3 us + epilogue) .
-    double best = 1e30;
-    for (int bn = 256; bn >= 32; bn >>= 1) {
-      if (Co % bn != 0) continue;
-      const int tiles = m_tiles * (Co / bn);
-      for (int sp = 1; sp <= 16; ++sp) {
-        const int kper = (k_iters + sp - 1) / sp;
-        if (sp > 1 && kper < 8) break;
-        const int items = tiles * ((k_iters + kper - 1) / kper);
-        const int waves = (items + kNumSMs - 1) / kNumSMs;
-        const double cost = waves * (kper * (0.28 + 0.0004 * bn) + (sp > 1 ? 0.06 : 0.012) * bn + 3.0);
-        if (cost < best) { best = cost; BN = bn; ksplit = sp; }
-      }
-    }
-  }
+  pick_tile_and_split(m_tiles, Co, k_iters, BN, ksplit);
   p.k_per = (k_iters + ksplit - 1) / ksplit;
   if (ksplit > 1 && (p.k_per & 1)) ++p.k_per;   // whole 2-chunk stages per slice
   p.ksplit = (k_iters + p.k_per - 1) / p.k_per;
   p.tiles_co = Co / BN;
   p.num_tiles = m_tiles * p.tiles_co * p.ksplit;
   p.alpha = BF ? alpha : alpha * kTf32TruncComp; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+  p.up = 0; p.OH = p.Ho; p.OW = p.Wo;
   p.dbg = 0;
   p.trace = nullptr;
   if (const char* e = getenv("GLB_FPROP_DBG")) p.dbg = atoi(e);
@@ -1492,13 +1530,15 @@ static int conv_fprop_tc_impl(const void* x, const void* w, const float* bias, f
   if (const char* e = getenv("GLB_FPROP_PAIR")) use_pair = use_pair && atoi(e) != 0;  // tuning experiments only
   if (use_pair) p.num_tiles = (m_tiles / 2) * p.tiles_co;   // pair items
 
-  CUtensorMap tmA, tmB;
+  TMapSet tmA;
+  CUtensorMap tmB;
   {
     const uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)Ci * ES, (uint64_t)W * Ci * ES, (uint64_t)H * W * Ci * ES};
     const uint32_t box[4] = {(uint32_t)kChunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    int rc = make_tmap(&tmA, x, 4, dims, strides, box, "conv input", false, BF);
+    int rc = make_tmap(&tmA.m[0], x, 4, dims, strides, box, "conv input", false, BF);
     if (rc) return rc;
+    tmA.m[1] = tmA.m[2] = tmA.m[3] = tmA.m[0];
   }
   {
     const uint64_t dims[3] = {(uint64_t)Ci, (uint64_t)(R * S), (uint64_t)Co};
@@ -1513,7 +1553,7 @@ static int conv_fprop_tc_impl(const void* x, const void* w, const float* bias, f
   if (const char* e = getenv("GLB_FPROP_M2")) use_m2 = use_m2 && atoi(e) != 0;   // tuning experiments only
   if (use_m2) {
     p.num_tiles = (m_tiles / 2) * p.tiles_co;
-    return launch_fprop_m2<128>(tmA, tmB, p, st);
+    return launch_fprop_m2<128>(tmA.m[0], tmB, p, st);
   }
   int rc = GLB_ERR_UNSUPPORTED;
   // two K chunks per stage for the narrow tiles (see FpropCfg); needs whole stages per tap row and per split-K slice
@@ -1581,6 +1621,118 @@ bool conv_dgrad_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int
   return conv_fprop_tc_covers(N, Ho, Wo, Co, Ci, R, S, R - 1 - pad);
 }
 
+// ------------------------------------------------------------------------------------------------ upsample folded into the conv
+// y = conv3x3_same(upsample2x_nearest(x), w)  (reference stylegan/architectures.py:155-156 / progan/architectures.py: the
+// `nn.Upsample` in front of a Conv2dEx) WITHOUT the upsampled copy and with 4/9 of the multiply-adds: output phase (dy, dx),
+//   y[n, 2i+dy, 2j+dx, co] = sum_{a,b in {0,1}} sum_ci x[n, i + a - (1-dy), j + b - (1-dx), ci] * wp[dy*2+dx][co][a][b][ci],
+// where along each axis  d = 0: tap a=0 <- w[0], a=1 <- w[1] + w[2];   d = 1: a=0 <- w[0] + w[1], a=1 <- w[2]
+// (rows 2i-1 | 2i, 2i+1 of the upsampled map are rows i-1 | i, i of x, and so on; the zero padding of the upsampled map is
+// exactly the out-of-bounds zero fill on x).  glb_upconv_weights writes wp and, for the data gradient, wt[ci][ph*4+a'*2+b'][co] =
+// wp[ph][co][1-a'][1-b'][ci].
+bool conv_upconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
+  if (N <= 0 || H <= 0 || W <= 0) return false;
+  const bool n_ok_co = (Co == 32 || Co == 64 || Co % 128 == 0), n_ok_ci = (Ci == 32 || Ci == 64 || Ci % 128 == 0);
+  switch (kind) {
+    case 0: return Ci % 32 == 0 && n_ok_co;               // fprop: K = Ci, GEMM N = Co
+    case 1: return Co % 32 == 0 && n_ok_ci;               // dgrad: K = Co, GEMM N = Ci
+    case 2: return Ci % 32 == 0 && Co % 32 == 0;          // wgrad
+  }
+  return false;
+}
+
+// shared by the forward (up = 1) and the data gradient (up = 2): `kc` = channels of the reduction, `nc` = channels of the output
+static int upconv_launch(int up, const float* in, const float* wmat, const float* bias, float* out, int N, int H, int W, int kc, int nc,
+                         float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
+  FpropParams p;
+  p.y = out; p.bias = bias;
+  p.N = N; p.Ho = H; p.Wo = W; p.Co = nc;
+  p.Ci = kc; p.R = up == 1 ? 2 : 4; p.S = p.R; p.pad = 0;
+  p.up = up; p.OH = up == 1 ? 2 * H : H; p.OW = up == 1 ? 2 * W : W;
+  p.bw = next_pow2(W) < 16 ? next_pow2(W) : 16;
+  p.bh = next_pow2(H) < kBM / p.bw ? next_pow2(H) : kBM / p.bw;
+  p.bn = kBM / (p.bw * p.bh);
+  p.tiles_w = (W + p.bw - 1) / p.bw;
+  p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_n = (N + p.bn - 1) / p.bn;
+  const int m_one = p.tiles_w * p.tiles_h * p.tiles_n;         // M tiles of one phase
+  const int m_tiles = up == 1 ? 4 * m_one : m_one;
+  const int k_iters = p.R * p.S * (kc / kChunk);
+  int BN = nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : nc);
+  int ksplit = 1;
+  pick_tile_and_split(m_tiles, nc, k_iters, BN, ksplit);
+  p.k_per = (k_iters + ksplit - 1) / ksplit;
+  if (ksplit > 1 && (p.k_per & 1)) ++p.k_per;
+  p.ksplit = (k_iters + p.k_per - 1) / p.k_per;
+  p.tiles_co = nc / BN;
+  p.num_tiles = m_tiles * p.tiles_co * p.ksplit;
+  p.alpha = alpha * kTf32TruncComp; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+  p.dbg = 0; p.trace = nullptr;
+  const int64_t out_rows = (int64_t)N * p.OH * p.OW;
+  const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
+  if (p.ksplit > 1) GLB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)out_rows * nc, st));
+  const bool use_pair = p.ksplit == 1 && BN == 256 && m_one % 2 == 0 && (m_tiles / 2) * p.tiles_co >= kNumSMs / 4;
+  if (use_pair) p.num_tiles = (m_tiles / 2) * p.tiles_co;
+
+  TMapSet tmA;
+  CUtensorMap tmB;
+  const uint32_t boxA[4] = {(uint32_t)kChunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  if (up == 1) {
+    const uint64_t dims[4] = {(uint64_t)kc, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)kc * 4, (uint64_t)W * kc * 4, (uint64_t)H * W * kc * 4};
+    int rc = make_tmap_f32(&tmA.m[0], in, 4, dims, strides, boxA, "upconv input", false);
+    if (rc) return rc;
+    tmA.m[1] = tmA.m[2] = tmA.m[3] = tmA.m[0];
+  } else {
+    // phase (dy, dx) of the high-resolution gradient [N][2H][2W][kc] as a strided [N][H][W][kc] view
+    const uint64_t dims[4] = {(uint64_t)kc, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)2 * kc * 4, (uint64_t)2 * (2 * W) * kc * 4, (uint64_t)(2 * H) * (2 * W) * kc * 4};
+    for (int ph = 0; ph < 4; ++ph) {
+      const float* base = in + ((int64_t)(ph >> 1) * (2 * W) + (ph & 1)) * kc;
+      int rc = make_tmap_f32(&tmA.m[ph], base, 4, dims, strides, boxA, "upconv gradient (phase view)", false);
+      if (rc) return rc;
+    }
+  }
+  {
+    const int taps = p.R * p.S;
+    const uint64_t rows = up == 1 ? (uint64_t)4 * nc : (uint64_t)nc;
+    const uint64_t dims[3] = {(uint64_t)kc, (uint64_t)taps, rows};
+    const uint64_t strides[2] = {(uint64_t)kc * 4, (uint64_t)taps * kc * 4};
+    const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)(use_pair ? BN / 2 : BN)};
+    int rc = make_tmap_f32(&tmB, wmat, 3, dims, strides, box, "upconv weight", false);
+    if (rc) return rc;
+  }
+  if (use_pair) return launch_fprop2<256, false>(tmA, tmB, p, st);
+  int rc = GLB_ERR_UNSUPPORTED;
+  const bool kc2 = BN <= 128 && (kc / kChunk) % 2 == 0 && p.k_per % 2 == 0;
+  switch (BN) {
+    case 256: rc = launch_fprop<256, 1, false>(tmA, tmB, p, st); break;
+    case 128: rc = kc2 ? launch_fprop<128, 2, false>(tmA, tmB, p, st) : launch_fprop<128, 1, false>(tmA, tmB, p, st); break;
+    case 64: rc = kc2 ? launch_fprop<64, 2, false>(tmA, tmB, p, st) : launch_fprop<64, 1, false>(tmA, tmB, p, st); break;
+    case 32: rc = kc2 ? launch_fprop<32, 2, false>(tmA, tmB, p, st) : launch_fprop<32, 1, false>(tmA, tmB, p, st); break;
+    default: set_error("upconv: no kernel for this N tile");
+  }
+  if (rc == GLB_OK && post_pass) rc = glb_bias_act_fwd(out, bias, out, out_rows, nc, bias_scale, act, slope, (glb_stream_t)st);
+  return rc;
+}
+
+int conv_upconv_fprop_tc(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
+                         float bias_scale, int act, float slope, cudaStream_t st) {
+  if (!conv_upconv_covers(0, N, H, W, Ci, Co)) {
+    set_error("upconv fprop: shape not covered (Ci % 32 == 0, Co in {32, 64} or a multiple of 128)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch(1, x, wp, bias, y, N, H, W, Ci, Co, alpha, bias_scale, act, slope, st);
+}
+
+// gx[n,i,j,ci] = alpha * sum_{ph,a',b',co} gy[n, 2(i + a' - dy) + dy, 2(j + b' - dx) + dx, co] * wt[ci][ph*4 + a'*2 + b'][co]
+int conv_upconv_dgrad_tc(const float* gy, const float* wt, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st) {
+  if (!conv_upconv_covers(1, N, H, W, Ci, Co)) {
+    set_error("upconv dgrad: shape not covered (Co % 32 == 0, Ci in {32, 64} or a multiple of 128)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch(2, gy, wt, nullptr, gx, N, H, W, Co, Ci, alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+}
+
 namespace {
 using namespace tc;
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -1602,6 +1754,8 @@ struct WgradParams {
   int tiles_co, tiles_ci;
   float alpha;
   int atomic;
+  int up;          // 1: weight gradient of the upsample-folded convolution (see FpropParams::up): 16 "taps" = phase*4 + a*2 + b,
+                   //    gy comes from the strided view of its phase, (Ho, Wo) = the low-resolution grid, pad = 1
 };
 
 // PIX = pixels (K) per pipeline stage: 32 (4 MMAs) for BN = 256, 64 (8 MMAs) for the narrower tiles, whose 64-cycle MMAs would
@@ -1624,7 +1778,7 @@ struct WgradCfg {
 // SBO = 1024 B between 8-pixel groups, LBO = one (64 ch x PIX px) block between 64-channel blocks, K = 16 pixels per MMA.
 template <int BN, int PIX, bool BF>
 __global__ void __launch_bounds__(256, 1)
-conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+conv_wgrad_tc_kernel(const __grid_constant__ TMapSet tmGys, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
   using Cfg = WgradCfg<BN, PIX, BF>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1644,7 +1798,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_cons
   const int tci = t % p.tiles_ci; t /= p.tiles_ci;
   const int tco = t % p.tiles_co; t /= p.tiles_co;
   const int tap = t;
-  const int r = tap / p.S, s = tap - r * p.S;
+  int r = tap / p.S, s = tap - r * p.S, mi = 0;
+  if (p.up) { mi = tap >> 2; r = ((tap >> 1) & 1) + (mi >> 1); s = (tap & 1) + (mi & 1); }   // shift a - (1 - dy) = r - pad with pad = 1
+  const CUtensorMap& tmGy = tmGys.m[mi];
   const int co0 = tco * 128, ci0 = tci * BN;
   const int pb_begin = split * p.pb_per_split;
   const int pb_end = min(p.num_pb, pb_begin + p.pb_per_split);
@@ -1900,7 +2056,7 @@ int launch_wgrad3(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradPa
 }
 
 template <int BN, int PIX, bool BF = false>
-int launch_wgrad(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
+int launch_wgrad(const TMapSet& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
   using Cfg = WgradCfg<BN, PIX, BF>;
   static bool configured = false;
   if (!configured) {
@@ -1939,7 +2095,7 @@ static int conv_wgrad_tc_impl(const void* x, const void* gy, float* gw, int N, i
     return GLB_ERR_UNSUPPORTED;
   }
   WgradParams p;
-  p.gw = gw; p.Co = Co; p.Ci = Ci; p.RS = R * S; p.S = S; p.pad = pad;
+  p.gw = gw; p.Co = Co; p.Ci = Ci; p.RS = R * S; p.S = S; p.pad = pad; p.up = 0;
   p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1;
   {
     // tap-reuse kernel: 3x3 "same" convolutions whose maps tile into 4 x 8 pixel K blocks, enough of them for one wave
@@ -2007,13 +2163,15 @@ static int conv_wgrad_tc_impl(const void* x, const void* gy, float* gw, int N, i
   p.atomic = p.splits > 1 ? 1 : 0;
   if (p.atomic) GLB_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Co * R * S * Ci, st));
 
-  CUtensorMap tmGy, tmX;
+  TMapSet tmGy;
+  CUtensorMap tmX;
   {  // (32 ch, Wo, Ho, N, Co/32): box = PIX pixels x 4 channel blocks (blocks beyond Co/32 are zero-filled: M padded to 128)
     const uint64_t dims[5] = {(uint64_t)CH, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N, (uint64_t)(Co / CH)};
     const uint64_t strides[4] = {(uint64_t)Co * ES, (uint64_t)p.Wo * Co * ES, (uint64_t)p.Ho * p.Wo * Co * ES, 128u};
     const uint32_t box[5] = {(uint32_t)CH, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(128 / CH)};
-    int rc = make_tmap(&tmGy, gy, 5, dims, strides, box, "wgrad gy", !BF, BF);
+    int rc = make_tmap(&tmGy.m[0], gy, 5, dims, strides, box, "wgrad gy", !BF, BF);
     if (rc) return rc;
+    tmGy.m[1] = tmGy.m[2] = tmGy.m[3] = tmGy.m[0];
   }
   {
     const uint64_t dims[5] = {(uint64_t)CH, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / CH)};
@@ -2048,6 +2206,165 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gw, int N, int H, int 
 int conv_wgrad_bf16(const void* x, const void* gy, float* gw, int N, int H, int W, int Ci, int Co, int R, int S, int pad,
                     float alpha, cudaStream_t st) {
   return conv_wgrad_tc_impl<true>(x, gy, gw, N, H, W, Ci, Co, R, S, pad, alpha, st);
+}
+
+// ------------------------------------------------------------------------------------------------ upconv: weights and wgrad
+namespace {
+// taps of the 3-tap axis that land on tap `a` of phase `d`:  d=0: a=0 -> {0}, a=1 -> {1,2};  d=1: a=0 -> {0,1}, a=1 -> {2}
+__device__ __forceinline__ void up_taps(int d, int a, int& lo, int& hi) {
+  lo = d == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+  hi = d == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+}
+
+// wp[ph][co][a][b][ci]: one float4 of ci per thread
+__global__ void upconv_weights_fwd_kernel(const float4* __restrict__ w, float4* __restrict__ wp, int Co, int Ci4) {
+  const int64_t total = (int64_t)16 * Co * Ci4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % Ci4);
+    int64_t t = i / Ci4;
+    const int ab = (int)(t & 3); t >>= 2;
+    const int co = (int)(t % Co);
+    const int ph = (int)(t / Co);
+    int r0, r1, s0, s1;
+    up_taps(ph >> 1, ab >> 1, r0, r1);
+    up_taps(ph & 1, ab & 1, s0, s1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r <= r1; ++r)
+      for (int s = s0; s <= s1; ++s) {
+        const float4 v = __ldg(w + ((int64_t)co * 9 + r * 3 + s) * Ci4 + c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    wp[i] = acc;
+  }
+}
+
+// wt[ci][ph*4 + a'*2 + b'][co] = wp[ph][co][1-a'][1-b'][ci]: 32 x 32 tile transpose over (co, ci) per (phase, tap)
+__global__ void upconv_weights_bwd_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci) {
+  __shared__ float tile[32][33];
+  const int t16 = blockIdx.z, ph = t16 >> 2, a = 1 - ((t16 >> 1) & 1), b = 1 - (t16 & 1);
+  int r0, r1, s0, s1;
+  up_taps(ph >> 1, a, r0, r1);
+  up_taps(ph & 1, b, s0, s1);
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int co = co0 + i, ci = ci0 + threadIdx.x;
+    float acc = 0.f;
+    if (co < Co && ci < Ci)
+      for (int r = r0; r <= r1; ++r)
+        for (int s = s0; s <= s1; ++s) acc += w[((int64_t)co * 9 + r * 3 + s) * Ci + ci];
+    tile[i][threadIdx.x] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ci = ci0 + i, co = co0 + threadIdx.x;
+    if (co < Co && ci < Ci) wt[((int64_t)ci * 16 + t16) * Co + co] = tile[threadIdx.x][i];
+  }
+}
+
+// gw[co][r][s][ci] = sum over the (phase, tap) pairs whose pre-summed tap contains (r, s) of gwp[co][ph*4 + a*2 + b][ci]
+__global__ void upconv_wgrad_fold_kernel(const float4* __restrict__ gwp, float4* __restrict__ gw, int Co, int Ci4) {
+  const int64_t total = (int64_t)Co * 9 * Ci4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % Ci4);
+    int64_t t = i / Ci4;
+    const int rs = (int)(t % 9), co = (int)(t / 9);
+    const int r = rs / 3, s = rs % 3;
+    // axis sources (d, a): r=0: (0,0),(1,0)   r=1: (0,1),(1,0)   r=2: (0,1),(1,1)
+    const int ay[2] = {r == 0 ? 0 : 1, r == 2 ? 1 : 0}, ax[2] = {s == 0 ? 0 : 1, s == 2 ? 1 : 0};
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int t16 = (dy * 2 + dx) * 4 + ay[dy] * 2 + ax[dx];
+        const float4 v = __ldg(gwp + ((int64_t)co * 16 + t16) * Ci4 + c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    gw[i] = acc;
+  }
+}
+}  // namespace
+
+int conv_upconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, cudaStream_t st) {
+  if (Ci % 4 != 0) { set_error("upconv weights: Ci % 4 != 0"); return GLB_ERR_SHAPE; }
+  if (wp) {
+    const int64_t total = (int64_t)16 * Co * (Ci / 4);
+    const int grid = (int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs);
+    upconv_weights_fwd_kernel<<<grid, 256, 0, st>>>((const float4*)w, (float4*)wp, Co, Ci / 4);
+    GLB_CHECK_LAUNCH("upconv_weights_fwd_kernel");
+  }
+  if (wt) {
+    dim3 grid((Ci + 31) / 32, (Co + 31) / 32, 16), block(32, 8);
+    upconv_weights_bwd_kernel<<<grid, block, 0, st>>>(w, wt, Co, Ci);
+    GLB_CHECK_LAUNCH("upconv_weights_bwd_kernel");
+  }
+  return GLB_OK;
+}
+
+// gw [Co][3][3][Ci] of conv3x3(upsample2x(x)); gwp = [Co][16][Ci] scratch (phase/tap gradients, folded at the end)
+int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                         cudaStream_t st) {
+  if (!conv_upconv_covers(2, N, H, W, Ci, Co)) {
+    set_error("upconv wgrad: shape not covered (Ci and Co multiples of 32)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  WgradParams p;
+  p.gw = gwp; p.Co = Co; p.Ci = Ci; p.RS = 16; p.S = 4; p.pad = 1; p.up = 1;
+  p.N = N; p.Ho = H; p.Wo = W;
+  const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
+  const int PIX = BN >= 256 ? 32 : 64;
+  p.bw = next_pow2(W) < PIX ? next_pow2(W) : PIX;
+  p.bh = next_pow2(H) < PIX / p.bw ? next_pow2(H) : PIX / p.bw;
+  p.bn = PIX / (p.bw * p.bh);
+  p.tiles_w = (W + p.bw - 1) / p.bw;
+  p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.num_pb = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.tiles_co = (Co + 127) / 128;
+  p.tiles_ci = Ci / BN;
+  const int tiles = p.tiles_co * p.tiles_ci * 16;
+  int splits = kNumSMs / tiles;
+  if (splits > p.num_pb / 4) splits = p.num_pb / 4;
+  if (splits > p.num_pb) splits = p.num_pb;
+  if (splits < 1) splits = 1;
+  p.pb_per_split = (p.num_pb + splits - 1) / splits;
+  p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;
+  p.alpha = alpha * kTf32TruncComp;
+  p.atomic = p.splits > 1 ? 1 : 0;
+  if (p.atomic) GLB_CUDA(cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Co * 16 * Ci, st));
+  TMapSet tmGy;
+  CUtensorMap tmX;
+  {
+    const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Co / 32)};
+    const uint64_t strides[4] = {(uint64_t)2 * Co * 4, (uint64_t)2 * (2 * W) * Co * 4, (uint64_t)(2 * H) * (2 * W) * Co * 4, 128u};
+    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 4u};
+    for (int ph = 0; ph < 4; ++ph) {
+      const float* base = gy + ((int64_t)(ph >> 1) * (2 * W) + (ph & 1)) * Co;
+      int rc = make_tmap_f32(&tmGy.m[ph], base, 5, dims, strides, box, "upconv wgrad gy (phase view)", true);
+      if (rc) return rc;
+    }
+  }
+  {
+    const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / 32)};
+    const uint64_t strides[4] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4, 128u};
+    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BN / 32)};
+    int rc = make_tmap_f32(&tmX, x, 5, dims, strides, box, "upconv wgrad x", true);
+    if (rc) return rc;
+  }
+  const int grid = tiles * p.splits;
+  int rc = GLB_ERR_UNSUPPORTED;
+  switch (BN) {
+    case 256: rc = launch_wgrad<256, 32>(tmGy, tmX, p, grid, st); break;
+    case 128: rc = launch_wgrad<128, 64>(tmGy, tmX, p, grid, st); break;
+    case 64: rc = launch_wgrad<64, 64>(tmGy, tmX, p, grid, st); break;
+    case 32: rc = launch_wgrad<32, 64>(tmGy, tmX, p, grid, st); break;
+  }
+  if (rc != GLB_OK) return rc;
+  const int64_t total = (int64_t)Co * 9 * (Ci / 4);
+  const int fgrid = (int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs);
+  upconv_wgrad_fold_kernel<<<fgrid, 256, 0, st>>>((const float4*)gwp, (float4*)gw, Co, Ci / 4);
+  GLB_CHECK_LAUNCH("upconv_wgrad_fold_kernel");
+  return GLB_OK;
 }
 
 }  // namespace glb

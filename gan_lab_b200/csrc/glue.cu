@@ -4,7 +4,7 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -382,6 +382,141 @@ __global__ void blur3x3_kernel(const float4* __restrict__ x, float4* __restrict_
       atomicAdd(gbias + 4 * tid + 2, bias_scale * t.z); atomicAdd(gbias + 4 * tid + 3, bias_scale * t.w);
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ blur, shared-memory tiles
+// The same filter with the input staged by TMA: a 16 x 16-pixel x 32-channel output tile needs an 18 x 18 x 32 box (40.5 KB, one
+// cp.async.bulk.tensor with zero fill outside the map = the zero padding), double buffered, so the HBM / L2 reads are few large
+// asynchronous transactions instead of 4-5 dependent 16-byte loads per thread and row.  A thread owns one (column, channel quad)
+// of half the tile and slides down 8 rows with the horizontal [1 2 1] sums of two rows in registers: 30 conflict-free LDS.128 per
+// 8 outputs.  Blocks own contiguous tile ranges ordered channel-block-major, so the MASK variant (blur + activation mask + bias
+// gradient, see blur3x3_kernel) flushes its column sums only when the channel block changes.
+constexpr int BT = 16;                                   // tile edge (pixels)
+constexpr int BTB = BT + 2;                              // box edge
+constexpr int BT_TX = BTB * BTB * 128;                   // bytes per box
+constexpr int BT_STAGE = ((BT_TX + 1023) / 1024) * 1024;
+
+template <bool MASK>
+__global__ void __launch_bounds__(256, 2)
+blur_tile_kernel(const __grid_constant__ CUtensorMap tmX, float4* __restrict__ y, int N, int H, int W, int C4, int tiles_w, int tiles_h,
+                 int total, const float4* __restrict__ mask, float* __restrict__ gbias, float bias_scale, int act, float slope) {
+  using namespace tc;
+  extern __shared__ uint8_t bt_raw[];
+  __shared__ uint64_t full[2];
+  __shared__ float4 red[256];
+  const uint32_t raw = smem_u32(bt_raw);
+  const uint32_t base = (raw + 127u) & ~127u;
+  const float4* tile0 = reinterpret_cast<const float4*>(bt_raw + (base - raw));
+  const int tid = threadIdx.x, q = tid & 7, col = (tid >> 3) & 15, half = tid >> 7;
+  const int per_cb = N * tiles_h * tiles_w;
+  const int t_begin = (int)(((long long)total * blockIdx.x) / gridDim.x), t_end = (int)(((long long)total * (blockIdx.x + 1)) / gridDim.x);
+  if (tid == 0) {
+    mbar_init(smem_u32(&full[0]), 1);
+    mbar_init(smem_u32(&full[1]), 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmX);
+  }
+  __syncthreads();
+  auto issue = [&](int t, int stage) {
+    const int cb = t / per_cb;
+    int r = t - cb * per_cb;
+    const int tw = r % tiles_w; r /= tiles_w;
+    const int th = r % tiles_h;
+    const int n = r / tiles_h;
+    mbar_expect_tx(smem_u32(&full[stage]), BT_TX);
+    tma_load_4d(base + stage * BT_STAGE, &tmX, smem_u32(&full[stage]), cb * 32, tw * BT - 1, th * BT - 1, n);
+  };
+  if (tid == 0 && t_begin < t_end) issue(t_begin, 0);
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur_cb = -1;
+  auto flush = [&]() {                                    // column sums of the finished channel block -> gbias
+    red[tid] = bsum;
+    __syncthreads();
+    if (tid < 8) {
+      float4 s = red[tid];
+      for (int r = tid + 8; r < 256; r += 8) { const float4 v = red[r]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+      float* gb = gbias + (cur_cb * 8 + tid) * 4;
+      atomicAdd(gb + 0, bias_scale * s.x); atomicAdd(gb + 1, bias_scale * s.y);
+      atomicAdd(gb + 2, bias_scale * s.z); atomicAdd(gb + 3, bias_scale * s.w);
+    }
+    __syncthreads();
+    bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && t + 1 < t_end) issue(t + 1, stage ^ 1);           // that stage was last read in iteration it - 1
+    const int cb = t / per_cb;
+    int r = t - cb * per_cb;
+    const int tw = r % tiles_w; r /= tiles_w;
+    const int th = r % tiles_h;
+    const int n = r / tiles_h;
+    if (MASK && gbias != nullptr && cb != cur_cb) {
+      if (cur_cb >= 0) flush();
+      cur_cb = cb;
+    }
+    const int r0 = half * 8, w = tw * BT + col;
+    float4 mk[8];
+    if (MASK) {                                           // the eight mask loads of this thread go out before the tile is awaited
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int h = th * BT + r0 + j;
+        mk[j] = (h < H && w < W) ? ldg_stream(mask + (((int64_t)n * H + h) * W + w) * C4 + cb * 8 + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+    }
+    mbar_wait(smem_u32(&full[stage]), (it >> 1) & 1);
+    const float4* tl = tile0 + stage * (BT_STAGE / 16) + q;
+    auto hsum = [&](int br) {
+      const float4 a = tl[(br * BTB + col) * 8], b = tl[(br * BTB + col + 1) * 8], c = tl[(br * BTB + col + 2) * 8];
+      return make_float4(a.x + 2.f * b.x + c.x, a.y + 2.f * b.y + c.y, a.z + 2.f * b.z + c.z, a.w + 2.f * b.w + c.w);
+    };
+    float4 rm = hsum(r0), rc = hsum(r0 + 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 rn = hsum(r0 + j + 2);
+      const int h = th * BT + r0 + j;
+      if (h < H && w < W) {
+        float4 o = make_float4(0.0625f * (rm.x + 2.f * rc.x + rn.x), 0.0625f * (rm.y + 2.f * rc.y + rn.y),
+                               0.0625f * (rm.z + 2.f * rc.z + rn.z), 0.0625f * (rm.w + 2.f * rc.w + rn.w));
+        const int64_t idx = (((int64_t)n * H + h) * W + w) * C4 + cb * 8 + q;
+        if (MASK) {
+          o.x *= act_grad(mk[j].x, act, slope); o.y *= act_grad(mk[j].y, act, slope);
+          o.z *= act_grad(mk[j].z, act, slope); o.w *= act_grad(mk[j].w, act, slope);
+          bsum.x += o.x; bsum.y += o.y; bsum.z += o.z; bsum.w += o.w;
+        }
+        stg_stream(y + idx, o);
+      }
+      rm = rc; rc = rn;
+    }
+    __syncthreads();                                                   // everyone is done with this stage before it is refilled
+  }
+  if (MASK && gbias != nullptr && cur_cb >= 0) flush();
+}
+
+// -> GLB_OK if launched, GLB_ERR_UNSUPPORTED if the shape is left to the register-window kernels
+template <bool MASK>
+int blur_tile_launch(const float* x, float* y, int N, int H, int W, int C, const float* mask, float* gbias, float bias_scale, int act,
+                     float slope, cudaStream_t st) {
+  if (C % 32 != 0 || H < 32 || W < 32 || (glue_variant() & 4)) return GLB_ERR_UNSUPPORTED;
+  CUtensorMap tm;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+  const uint32_t box[4] = {32u, (uint32_t)BTB, (uint32_t)BTB, 1u};
+  if (int rc = tc::make_tmap(&tm, x, 4, dims, strides, box, "blur input", false, false, true)) return rc;
+  const int tiles_w = (W + BT - 1) / BT, tiles_h = (H + BT - 1) / BT;
+  const int64_t total = (int64_t)(C / 32) * N * tiles_h * tiles_w;
+  if (total >= (1ll << 31)) return GLB_ERR_UNSUPPORTED;
+  const int smem = 2 * BT_STAGE + 128;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(blur_tile_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = total < 2 * kNumSMs ? (int)total : 2 * kNumSMs;
+  blur_tile_kernel<MASK><<<grid, 256, smem, st>>>(tm, (float4*)y, N, H, W, C / 4, tiles_w, tiles_h, (int)total, (const float4*)mask, gbias,
+                                                 bias_scale, act, slope);
+  GLB_CHECK_LAUNCH("blur_tile_kernel");
+  return GLB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -842,6 +977,10 @@ extern "C" int glb_blur3x3(const float* x, float* y, int N, int H, int W, int C,
     GLB_CHECK_LAUNCH("blur3x3");
     return GLB_OK;
   }
+  {
+    const int rc = blur_tile_launch<false>(x, y, N, H, W, C, nullptr, nullptr, 1.f, 0, 0.f, (cudaStream_t)stream);
+    if (rc != GLB_ERR_UNSUPPORTED) return rc;
+  }
   constexpr int PW = 2;
   int TH = 8;   // rows per thread: fewer for small maps so that the grid still fills the machine
   while (TH > 1 && (int64_t)N * ((H + TH - 1) / TH) * ((W + PW - 1) / PW) * C4 < (int64_t)kNumSMs * 4 * TPB) TH >>= 1;
@@ -854,6 +993,10 @@ extern "C" int glb_blur3x3(const float* x, float* y, int N, int H, int W, int C,
 extern "C" int glb_blur_act_bwd(const float* gz, const float* ymask, float* g, float* gbias, int N, int H, int W, int C,
                                 float bias_scale, int act, float slope, glb_stream_t stream) {
   REQ(C % 4 == 0 && TPB % (C / 4) == 0, "blur_act_bwd: C/4 must divide 256");
+  {
+    const int rc = blur_tile_launch<true>(gz, g, N, H, W, C, ymask, gbias, bias_scale, act, slope, (cudaStream_t)stream);
+    if (rc != GLB_ERR_UNSUPPORTED) return rc;
+  }
   const int C4 = C / 4;
   constexpr int PW = 2;
   int TH = 8;

@@ -32,7 +32,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands) instead of
 // the plain 128B swizzle.
 inline int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, const char* what, bool atom32, bool bf16) {
+                     const uint32_t* box, const char* what, bool atom32, bool bf16, bool no_swizzle = false) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -48,7 +48,8 @@ inline int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t*
     if (i > 0) gs[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

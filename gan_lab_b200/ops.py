@@ -373,6 +373,55 @@ def upsample2x(x):
     return _Up2.apply(x)
 
 
+class _UpConvFprop(Function):
+    """y = act(alpha * conv3x3_same(upsample2x(x), w) + bias_scale * bias) with the upsample folded into the convolution
+    (glb_upconv_*: four 2x2 phase convolutions on the low-resolution map; reference `nn.Upsample` + `Conv2dEx`,
+    stylegan/architectures.py:155-156).  Backward: fused data / weight gradients on the plain backward pass; when a graph of
+    the backward is asked for (double backward) the differentiable two-kernel composition is used instead."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, alpha, bias_scale, act, slope):
+        y = K.upconv_fprop(x, w, bias, alpha, bias_scale, act, slope)
+        ctx.cfg = (alpha, bias_scale, act, slope, bias is not None, x.shape, w.shape)
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        alpha, bias_scale, act, slope, has_bias, xshape, wshape = ctx.cfg
+        pg = _param_grads_wanted()
+        want_b = has_bias and ctx.needs_input_grad[2] and pg
+        if act != ACT_NONE:
+            g, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
+        else:
+            g = gy
+            gb = _ColSum.apply(g, bias_scale) if want_b else None
+        N, Ci, H, W = xshape
+        Co = wshape[0]
+        fused = not torch.is_grad_enabled()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            if fused and K.upconv_covers("dgrad", N, H, W, Ci, Co):
+                gx = K.upconv_dgrad(g, w, alpha)
+            else:
+                gx = _Up2Bwd.apply(_ConvDgrad.apply(g, w, 2 * H, 2 * W, 1, alpha))
+        if ctx.needs_input_grad[1] and pg:
+            if fused and K.upconv_covers("wgrad", N, H, W, Ci, Co):
+                gw = K.upconv_wgrad(x, g, alpha)
+            else:
+                gw = _ConvWgrad.apply(_Up2.apply(x), g, 3, 3, 1, alpha)
+        return gx, gw, gb, None, None, None, None
+
+
+def upconv2d(x, w, bias=None, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2):
+    """conv2d(upsample2x(x), w, pad=1) for a 3x3 weight; one fused launch where the tensor-core path covers the shape."""
+    N, Ci, H, W = x.shape
+    if w.shape[2] == 3 and w.shape[3] == 3 and x.is_cuda and K.upconv_covers("fprop", N, H, W, Ci, w.shape[0]):
+        return _UpConvFprop.apply(x, w, bias, float(alpha), float(bias_scale), int(act), float(slope))
+    return conv2d(upsample2x(x), w, bias, 1, alpha, bias_scale, act, slope)
+
+
 class _AvgPoolBwd(Function):
     """g [N,C,H/2,W/2] -> 0.25 * nearest-upsample(g): adjoint of the 2x2 average pool."""
 

@@ -8,6 +8,8 @@ bandwidth kernel) instead of one ATen call per child.
 """
 import copy
 
+import functools
+
 import torch
 from torch import nn
 
@@ -42,11 +44,16 @@ class ConvLayer(nn.Sequential):
         mods = list(self)
         i = 0
         n = len(mods)
+        up = False
         while i < n and not isinstance(mods[i], Conv2dEx):     # upsampler / pre-blur
-            if not (skip_pre_blur and isinstance(mods[i], Blur3x3)):
+            if isinstance(mods[i], Upsample2x) and i + 1 < n and isinstance(mods[i + 1], Conv2dEx):
+                up = True                                      # rides in the convolution (ops.upconv2d)
+            elif not (skip_pre_blur and isinstance(mods[i], Blur3x3)):
                 x = mods[i](x)
             i += 1
         conv = mods[i]
+        if up:
+            conv = functools.partial(conv, up=True)
         i += 1
         rest = mods[i:]
         post_blur = rest[0] if rest and isinstance(rest[0], Blur3x3) else None

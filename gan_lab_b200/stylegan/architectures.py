@@ -255,8 +255,14 @@ class StyleGenerator(StyleGAN):
         op = layer[0]
         if isinstance(op, Conv2dEx):
             return op(out)
-        for m in op:
-            out = m(out)
+        mods, i = list(op), 0
+        while i < len(mods):
+            if isinstance(mods[i], Upsample2x) and i + 1 < len(mods) and isinstance(mods[i + 1], Conv2dEx):
+                out = mods[i + 1](out, up=True)             # the upsampler rides in the convolution (ops.upconv2d)
+                i += 2
+            else:
+                out = mods[i](out)
+                i += 1
         return out
 
     def _layer_tail(self, layer, out, w, noise, style=None):

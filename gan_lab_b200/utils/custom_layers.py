@@ -285,12 +285,16 @@ class Conv2dEx(nn.Module):
         a = self.wscale if self.equalized_lr else 1.
         return a * self.lrmul if self.use_lrmul else a
 
-    def forward(self, x, act=None, slope=0.2, blur=False):
+    def forward(self, x, act=None, slope=0.2, blur=False, up=False):
         """`act=None` reproduces the reference module; the fused architectures pass act=ops.ACT_LRELU to fold
         the following LeakyReLU into the conv epilogue, and blur=True to let the binomial FIR that follows ride in the op."""
         act = ops.ACT_NONE if act is None else act
         w, b = self.conv2d.weight, self.conv2d.bias
         bscale = self.lrmul if self.use_lrmul else 1.
+        if up:                                         # the nearest-neighbour 2x upsampler in front of this layer rides in the conv
+            if self.ks == 3 and self.padding == 1 and not blur:
+                return ops.upconv2d(x, w, b, self.alpha, bscale, act, slope)
+            x = ops.upsample2x(x)
         if self.ks == 1 and self.padding == 0 and x.dim() == 4:
             if self.ni == 3 and self.nf % 4 == 0:
                 return ops.fromrgb(x, w, b, self.alpha, bscale, act, slope)

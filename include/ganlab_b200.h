@@ -89,6 +89,24 @@ int glb_conv2d_dgrad_bf16(const void* gy_bf16, const void* wt_bf16, float* gx,
 int glb_conv2d_wgrad_bf16(const void* x_bf16, const void* gy_bf16, float* gw,
                           int N, int H, int W, int Ci, int Co, int R, int S, int pad, float alpha, glb_stream_t stream);
 
+/* ---- nearest-neighbour 2x upsample folded into the 3x3 convolution that follows it (TF32 tensor-core path) ------ *
+ * Replaces `nn.Upsample(scale_factor=2)` + `Conv2dEx(ks=3, padding=1)` of the generator blocks
+ * (stylegan/architectures.py:155-156, 331; progan/architectures.py:209-224; resnetgan/learner.py:154-158) by ONE
+ * launch on the LOW-resolution map: each of the four output phases (dy, dx) of y[2i+dy, 2j+dx] is a 2x2 convolution of
+ * x with pre-summed taps -- 4/9 of the multiply-adds and no upsampled copy in HBM.  Same for the data gradient
+ * (= upsample2x_bwd(dgrad)) and the weight gradient (= wgrad(upsample2x(x), gy)).
+ * x [N,H,W,Ci], y / gy [N,2H,2W,Co], w / gw [Co,3,3,Ci];
+ * wp [4*Co,2,2,Ci] (forward) and wt [Ci,16,Co] (data gradient) are written by glb_upconv_weights (either may be NULL);
+ * gwp [Co,16,Ci] is scratch of glb_upconv_wgrad.  kind: 0 fprop, 1 dgrad, 2 wgrad. */
+int glb_upconv_covers(int kind, int N, int H, int W, int Ci, int Co);
+int glb_upconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, glb_stream_t stream);
+int glb_upconv_fprop(const float* x, const float* wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
+                     float alpha, float bias_scale, int act, float slope, glb_stream_t stream);
+int glb_upconv_dgrad(const float* gy, const float* wt, float* gx, int N, int H, int W, int Ci, int Co,
+                     float alpha, glb_stream_t stream);
+int glb_upconv_wgrad(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
+                     float alpha, glb_stream_t stream);
+
 /* ---- RGB 1x1 convolutions (3 <-> C channels; pure bandwidth) ---------------------------------- *
  * fromRGB (progan/architectures.py:286-292) and toRGB (stylegan/architectures.py:338-341).
  * In all three the weight element (j = rgb channel, c = feature channel) lives at w[j*ws_j + c*ws_c], so the

@@ -57,6 +57,20 @@ def conv_wgrad(x, gy, rs, pad, alpha):
     return _cl(alpha * torch.nn.grad.conv2d_weight(x, (gy.shape[1], x.shape[1], rs[0], rs[1]), gy, 1, pad))
 
 
+# conv3x3_same(upsample2x_nearest(x)) and its two gradients, stated as the literal composition the reference runs
+# (nn.Upsample + Conv2dEx, stylegan/architectures.py:155-156): what glb_upconv_* must reproduce without the upsampled copy
+def upconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
+    return conv_fprop(O.upsample2x(x), w, bias, 1, alpha, bias_scale, act, slope)
+
+
+def upconv_dgrad(gy, w, alpha):
+    return upsample2x_bwd(conv_dgrad(gy, w, (gy.shape[2], gy.shape[3]), 1, alpha))
+
+
+def upconv_wgrad(x, gy, alpha):
+    return conv_wgrad(O.upsample2x(x), gy, (3, 3), 1, alpha)
+
+
 def linear_fwd(x, w, bias, alpha, bias_scale, act, slope):
     y = alpha * (x @ w.t())
     if bias is not None:

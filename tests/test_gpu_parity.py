@@ -110,6 +110,67 @@ def test_conv_family_tf32_vs_contract(shape):
         K.set_conv_impl("fp32")
 
 
+# Upsample folded into the convolution (glb_upconv_*): N, H, W (low resolution), Ci, Co.  Covers the split-K path (4^2, 8^2), the
+# single-CTA kernels at BN 256 / 128 / 64 / 32, the CTA-pair kernel (>= 37 pair items at BN 256), ragged maps (5 x 7) and every
+# cfg2 layer shape at a reduced batch.
+UPCONV_SHAPES = [
+    (8, 4, 4, 512, 512), (8, 8, 8, 512, 512), (2, 16, 16, 512, 512), (8, 16, 16, 512, 512), (2, 32, 32, 512, 256),
+    (2, 64, 64, 256, 128), (3, 5, 7, 32, 64), (2, 16, 16, 64, 32), (4, 8, 8, 96, 128), (1, 32, 32, 128, 64),
+]
+
+
+@pytest.mark.parametrize("shape", UPCONV_SHAPES)
+def test_upconv_family_vs_contract(shape):
+    """conv3x3(upsample2x(x)) as four 2x2 phase convolutions on the low-resolution map vs the literal composition in fp64."""
+    N, H, W, Ci, Co = shape
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, 3, 3, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, 2 * H, 2 * W, seed=3))
+    K.set_conv_impl("tf32")
+    try:
+        assert K.upconv_covers("fprop", N, H, W, Ci, Co) and K.upconv_covers("wgrad", N, H, W, Ci, Co)
+        n0 = K.launch_count()
+        both("upconv_fprop", x, w, b, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_TF32)
+        both("upconv_fprop", x, w, None, 1.0, 1.0, K.ACT_NONE, 0.2, tol=TOL_TF32)
+        if K.upconv_covers("dgrad", N, H, W, Ci, Co):         # GEMM N = Ci: 32, 64 or a multiple of 128 (ops.upconv2d falls back otherwise)
+            both("upconv_dgrad", gy, w, 0.37, tol=TOL_TF32)
+        else:
+            assert Ci == 96
+        both("upconv_wgrad", x, gy, 0.37, tol=TOL_TF32)
+        assert K.launch_count() > n0
+    finally:
+        K.set_conv_impl("fp32")
+
+
+def test_upconv_op_matches_two_kernel_sequence():
+    """ops.upconv2d (fused) against ops.conv2d(ops.upsample2x(x)) on the same TF32 path: outputs and all three gradients;
+    with create_graph the backward falls back to the differentiable composition (second-order derivative exists)."""
+    from gan_lab_b200 import ops
+    N, H, W, Ci, Co = 2, 16, 16, 128, 128
+    x0, w0, b0 = cl(rn(N, Ci, H, W)).to(DEV), cl(rn(Co, Ci, 3, 3, seed=1)).to(DEV), rn(Co, seed=2).to(DEV)
+    K.set_conv_impl("tf32")
+    try:
+        outs = []
+        for fused in (True, False):
+            x, w, b = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            if fused:
+                y = ops.upconv2d(x, w, b, 0.5, 1.0, ops.ACT_LRELU, 0.2)
+            else:
+                y = ops.conv2d(ops.upsample2x(x), w, b, 1, 0.5, 1.0, ops.ACT_LRELU, 0.2)
+            (y * y).sum().backward()
+            outs.append((y.detach(), x.grad, w.grad, b.grad))
+        for a, c in zip(*outs):
+            assert rel(a, c) < TOL_TF32, rel(a, c)
+        x = x0.clone().requires_grad_(True)
+        w = w0.clone().requires_grad_(True)
+        y = ops.upconv2d(x, w, None, 0.5)
+        (gx,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+        assert gx.requires_grad
+        (gx * gx).sum().backward()
+        assert w.grad is not None and torch.isfinite(w.grad).all()
+    finally:
+        K.set_conv_impl("fp32")
+
+
 # bf16 operand path (tcgen05 kind::f16 on round-to-nearest bf16 copies of x / gy / w, fp32 accumulation): 8 mantissa bits per
 # operand -> stated bound 1e-2 of the tensor's max-norm (expected ~3e-3 over K = 576..4608); channel counts multiples of 64.
 TOL_BF16 = 1e-2
@@ -254,6 +315,16 @@ def test_linear_family_vs_contract(M, Kf, Nout):
     both("linear_fwd", x, w, b, 0.01, 0.01, K.ACT_LRELU, 0.2)
     both("linear_dgrad", gy, w, 0.3)
     both("linear_wgrad", x, gy, 0.3)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 64, 40, 52), (2, 32, 33, 47), (8, 128, 128, 128), (3, 256, 64, 64), (1, 512, 32, 32)])
+def test_blur_tile_kernels_vs_contract(N, C, H, W):
+    """The TMA-staged shared-memory blur kernels (maps >= 32 x 32, channel counts multiples of 32), ragged tile edges included:
+    plain blur, and blur + activation mask + bias gradient."""
+    x, y, gy = cl(rn(N, C, H, W)), cl(rn(N, C, H, W, seed=1)), cl(rn(N, C, H, W, seed=2))
+    both("blur3x3", x)
+    both("blur_act_bwd", gy, y, True, 0.7, K.ACT_LRELU, 0.2, tol=3e-4)       # (bias gradient: fp32 atomics over N*H*W terms)
+    both("blur_act_bwd", gy, y, False, 1.0, K.ACT_LRELU, 0.2)
 
 
 @pytest.mark.parametrize("N,C,H,W", [(2, 16, 8, 8), (4, 512, 4, 4), (1, 128, 32, 32), (3, 2048, 2, 2), (2, 32, 6, 10)])
