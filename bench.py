@@ -789,8 +789,23 @@ def kernel_rooflines(L, x, main_iter, flush):
     def f_cvt(a, k, out):
         return 6.0 * out.numel()
 
-    conv_kinds = ("conv_fprop", "conv_dgrad", "conv_wgrad")
+    # upsample / average pool folded into the convolution (glb_upconv_* / glb_downconv_*): EXECUTED FLOPs = 16 pre-summed taps per
+    # low-resolution pixel (4/9 of the literal upsample -> conv / conv -> pool sequence)
+    def f_fold(lo):
+        def f(a, k, out):
+            t = lo(a, out)
+            w_ = a[1] if a[1].dim() == 4 and a[1].shape[2] == 3 else None
+            ci_co = (w_.shape[0] * w_.shape[1]) if w_ is not None else a[0].shape[1] * a[1].shape[1]
+            return 2.0 * t.shape[0] * t.shape[2] * t.shape[3] * 16.0 * ci_co
+        return f
+
+    conv_kinds = ("conv_fprop", "conv_dgrad", "conv_wgrad", "upconv_fprop", "upconv_dgrad", "upconv_wgrad",
+                  "downconv_fprop", "downconv_dgrad", "downconv_wgrad")
     wrap("conv_fprop", f_fprop); wrap("conv_dgrad", f_dgrad); wrap("conv_wgrad", f_wgrad)
+    wrap("upconv_fprop", f_fold(lambda a, out: a[0])); wrap("upconv_dgrad", f_fold(lambda a, out: out))
+    wrap("upconv_wgrad", f_fold(lambda a, out: a[0]))
+    wrap("downconv_fprop", f_fold(lambda a, out: out)); wrap("downconv_dgrad", f_fold(lambda a, out: a[0]))
+    wrap("downconv_wgrad", f_fold(lambda a, out: a[1]))
     for name in GLUE_LAUNCHERS:
         wrap(name, f_adam if name == "adam_ewma_multi" else (f_cvt if name == "cvt_bf16" else nbytes))
     dp, L.dp = L.dp, None          # rank-local pass: no collective may run here (the other ranks are not in it)
@@ -878,7 +893,13 @@ def kernel_rooflines(L, x, main_iter, flush):
                 nb = 4.0 * sum(t.numel() for t in a if torch.is_tensor(t))
                 out_elems = {"conv_fprop": lambda: a[0].shape[0] * a[1].shape[0] * (a[0].shape[2] + 2 * a[3] - a[1].shape[2] + 1) * (a[0].shape[3] + 2 * a[3] - a[1].shape[3] + 1),
                              "conv_dgrad": lambda: a[0].shape[0] * a[1].shape[1] * a[2][0] * a[2][1],
-                             "conv_wgrad": lambda: a[1].shape[1] * a[0].shape[1] * a[2][0] * a[2][1]}[c[0]]()
+                             "conv_wgrad": lambda: a[1].shape[1] * a[0].shape[1] * a[2][0] * a[2][1],
+                             "upconv_fprop": lambda: 4 * a[0].shape[0] * a[1].shape[0] * a[0].shape[2] * a[0].shape[3],
+                             "upconv_dgrad": lambda: a[0].shape[0] * a[1].shape[1] * a[0].shape[2] * a[0].shape[3] // 4,
+                             "upconv_wgrad": lambda: 9 * a[0].shape[1] * a[1].shape[1],
+                             "downconv_fprop": lambda: a[0].shape[0] * a[1].shape[0] * a[0].shape[2] * a[0].shape[3] // 4,
+                             "downconv_dgrad": lambda: 4 * a[0].shape[0] * a[1].shape[1] * a[0].shape[2] * a[0].shape[3],
+                             "downconv_wgrad": lambda: 9 * a[0].shape[1] * a[1].shape[1]}[c[0]]()
                 nb += 4.0 * out_elems
                 cls["tensor_bound" if c[4] / nb >= ridge else "hbm_bound"].append((c, nb))
         split = {"ridge_flop_per_byte": ridge}

@@ -548,6 +548,74 @@ def upconv_wgrad(x, gy, alpha):
     return gw
 
 
+# ---- 2x2 average pool folded into the 3x3 convolution in front of it (glb_downconv_*: the adjoint structure of upconv) ------
+def downconv_covers(N, H, W, Ci, Co) -> bool:
+    """H, W: LOW-resolution (output) map.  All three kernels must cover the pair (the family is closed under differentiation:
+    the R1 double backward runs fprop / dgrad / wgrad of the same layer)."""
+    if _state["conv_impl"] != "tf32" or os.environ.get("GLB_DOWNCONV", "1") == "0":
+        return False
+    f = LIB.fn("glb_downconv_covers")
+    return all(bool(f(k, N, H, W, Ci, Co)) for k in (0, 1, 2))
+
+
+def downconv_weights(w):
+    """(wp [4*Ci,2,2,Co] for the data gradient, wt [Co,16,Ci] for the forward) of w [Co,Ci,3,3]; cached per weight version."""
+    key = (w.data_ptr(), tuple(w.shape), "down")
+    hit = _cache_get(_up_cache, key, w._version)
+    if hit is not None:
+        return hit
+    Co, Ci, R, S = w.shape
+    wtmp = torch.empty((Ci, 3, 3, Co), device=w.device, dtype=torch.float32)
+    wp = torch.empty((4 * Ci, 2, 2, Co), device=w.device, dtype=torch.float32)
+    wt = torch.empty((Co, 16, Ci), device=w.device, dtype=torch.float32)
+    _call("glb_downconv_weights", _p(w), _p(wtmp), _p(wp), _p(wt), Co, Ci, _stream())
+    if len(_up_cache) >= 32:
+        _up_cache.clear()
+    return _cache_put(_up_cache, key, w._version, (wp, wt), w)
+
+
+def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
+    """act(alpha * avgpool2x2(conv3x3_same(x, w)) + bias_scale * bias) -> [N, Co, H/2, W/2]"""
+    _chk(x, w, bias)
+    x, w = nhwc(x), nhwc(w)
+    N, Ci, H2, W2 = x.shape
+    Co, Ci2, R, S = w.shape
+    if Ci != Ci2 or R != 3 or S != 3 or H2 % 2 or W2 % 2:
+        raise GlbError("downconv_fprop: needs a 3x3 weight with matching channels and an even map")
+    _, wt = downconv_weights(w)
+    y = _new_nhwc(N, Co, H2 // 2, W2 // 2, x)
+    _call("glb_downconv_fprop", _p(x), _p(wt), _p(_flat(bias)), _p(y), N, H2 // 2, W2 // 2, Ci, Co, float(alpha), float(bias_scale),
+          int(act), float(slope), _stream())
+    return y
+
+
+def downconv_dgrad(gy, w, alpha):
+    _chk(gy, w)
+    gy, w = nhwc(gy), nhwc(w)
+    N, Co, H, W = gy.shape
+    Co2, Ci, R, S = w.shape
+    if Co != Co2:
+        raise GlbError("downconv_dgrad: shape mismatch")
+    wp, _ = downconv_weights(w)
+    gx = _new_nhwc(N, Ci, 2 * H, 2 * W, gy)
+    _call("glb_downconv_dgrad", _p(gy), _p(wp), _p(gx), N, H, W, Ci, Co, float(alpha), _stream())
+    return gx
+
+
+def downconv_wgrad(x, gy, alpha):
+    _chk(x, gy)
+    x, gy = nhwc(x), nhwc(gy)
+    N, Ci, H2, W2 = x.shape
+    N2, Co, H, W = gy.shape
+    if N != N2 or H2 != 2 * H or W2 != 2 * W:
+        raise GlbError("downconv_wgrad: shape mismatch")
+    gwp = torch.empty((Ci, 16, Co), device=x.device, dtype=torch.float32)
+    gwt = torch.empty((Ci, 3, 3, Co), device=x.device, dtype=torch.float32)
+    gw = _new_nhwc(Co, Ci, 3, 3, x)
+    _call("glb_downconv_wgrad", _p(x), _p(gy), _p(gwp), _p(gwt), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
+    return gw
+
+
 # --------------------------------------------------------------------------- linear
 def linear_fwd(x, w, bias, alpha, bias_scale, act, slope):
     _chk(x, w, bias)

@@ -2367,4 +2367,60 @@ int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw,
   return GLB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ 2x2 average pool folded into the conv
+// y = avgpool2x2(conv3x3_same(x, w))  (reference progan/architectures.py:267-284: Conv2dEx followed by nn.AvgPool2d in the
+// discriminator blocks) = 0.25 * U^T C_w x with U the nearest 2x upsample: the ADJOINT structure of the upsample-folded
+// convolution above.  With w' = the flipped / transposed weights (C_w = C_w'^T):
+//   fprop  y  = 0.25 * upconv_dgrad(x;  w')      (K over (input phase, 2x2 tap, Ci): a stride-2 4x4 convolution, 4/9 of the MMAs,
+//                                                 the full-resolution conv output never exists)
+//   dgrad  gx = 0.25 * upconv_fprop(gy; w')
+//   wgrad  gw = 0.25 * transpose_flip(upconv_wgrad(x_lo := gy, gy_hi := x))
+// so the same three kernels serve it; H, W below are the LOW-resolution (output) dims, x / gx are [N,2H,2W,Ci].
+// glb_downconv_weights: wp [4*Ci][2][2][Co] (dgrad) and wt [Co][16][Ci] (fprop) = glb_upconv_weights of w'.
+extern "C" int glb_conv2d_weight_transpose(const float* w, float* wt, int Co, int R, int S, int Ci, glb_stream_t stream);
+
+bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
+  switch (kind) {
+    case 0: return conv_upconv_covers(1, N, H, W, Co, Ci);
+    case 1: return conv_upconv_covers(0, N, H, W, Co, Ci);
+    case 2: return conv_upconv_covers(2, N, H, W, Co, Ci);
+  }
+  return false;
+}
+
+int conv_downconv_weights(const float* w, float* wtmp, float* wp, float* wt, int Co, int Ci, cudaStream_t st) {
+  int rc = glb_conv2d_weight_transpose(w, wtmp, Co, 3, 3, Ci, (glb_stream_t)st);    // w'[ci][2-r][2-s][co]
+  if (rc) return rc;
+  return conv_upconv_weights(wtmp, wp, wt, /*Co' =*/Ci, /*Ci' =*/Co, st);
+}
+
+int conv_downconv_fprop_tc(const float* x, const float* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
+                           float bias_scale, int act, float slope, cudaStream_t st) {
+  if (!conv_downconv_covers(0, N, H, W, Ci, Co)) {
+    set_error("downconv fprop: shape not covered (Ci % 32 == 0, Co in {32, 64} or a multiple of 128)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch(2, x, wt, bias, y, N, H, W, Ci, Co, 0.25f * alpha, bias_scale, act, slope, st);
+}
+
+int conv_downconv_dgrad_tc(const float* gy, const float* wp, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st) {
+  if (!conv_downconv_covers(1, N, H, W, Ci, Co)) {
+    set_error("downconv dgrad: shape not covered (Co % 32 == 0, Ci in {32, 64} or a multiple of 128)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch(1, gy, wp, nullptr, gx, N, H, W, Co, Ci, 0.25f * alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+}
+
+// gwp [Ci][16][Co] and gwt [Ci][3][3][Co] are scratch
+int conv_downconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gwt, float* gw, int N, int H, int W, int Ci, int Co,
+                           float alpha, cudaStream_t st) {
+  if (!conv_downconv_covers(2, N, H, W, Ci, Co)) {
+    set_error("downconv wgrad: shape not covered (Ci and Co multiples of 32)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  int rc = conv_upconv_wgrad_tc(gy, x, gwp, gwt, N, H, W, /*Ci' =*/Co, /*Co' =*/Ci, 0.25f * alpha, st);
+  if (rc) return rc;
+  return glb_conv2d_weight_transpose(gwt, gw, /*Co' =*/Ci, 3, 3, /*Ci' =*/Co, (glb_stream_t)st);
+}
+
 }  // namespace glb

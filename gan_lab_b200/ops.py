@@ -383,6 +383,7 @@ class _UpConvFprop(Function):
     def forward(ctx, x, w, bias, alpha, bias_scale, act, slope):
         y = K.upconv_fprop(x, w, bias, alpha, bias_scale, act, slope)
         ctx.cfg = (alpha, bias_scale, act, slope, bias is not None, x.shape, w.shape)
+        ctx.bshape = None if bias is None else bias.shape
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
         return y
 
@@ -411,7 +412,7 @@ class _UpConvFprop(Function):
                 gw = K.upconv_wgrad(x, g, alpha)
             else:
                 gw = _ConvWgrad.apply(_Up2.apply(x), g, 3, 3, 1, alpha)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, (gb.view(ctx.bshape) if gb is not None else None), None, None, None, None
 
 
 def upconv2d(x, w, bias=None, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2):
@@ -420,6 +421,80 @@ def upconv2d(x, w, bias=None, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2
     if w.shape[2] == 3 and w.shape[3] == 3 and x.is_cuda and K.upconv_covers("fprop", N, H, W, Ci, w.shape[0]):
         return _UpConvFprop.apply(x, w, bias, float(alpha), float(bias_scale), int(act), float(slope))
     return conv2d(upsample2x(x), w, bias, 1, alpha, bias_scale, act, slope)
+
+
+class _DownConvFprop(Function):
+    """y = act(alpha * avgpool2x2(conv3x3_same(x, w)) + bias_scale * bias): the discriminator's conv -> AvgPool2d -> bias ->
+    LeakyReLU (reference progan/architectures.py:267-284) as one stride-2 4x4 convolution (glb_downconv_*).  {fprop, dgrad,
+    wgrad} of it is closed under differentiation like the plain convolution family, so the R1 / WGAN-GP double backward
+    stays on the fused kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, alpha, bias_scale, act, slope):
+        y = K.downconv_fprop(x, w, bias, alpha, bias_scale, act, slope)
+        ctx.cfg = (alpha, bias_scale, act, slope, bias is not None)
+        ctx.bshape = None if bias is None else bias.shape
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        alpha, bias_scale, act, slope, has_bias = ctx.cfg
+        pg = _param_grads_wanted()
+        want_b = has_bias and ctx.needs_input_grad[2] and pg
+        if act != ACT_NONE:
+            g, gb = act_bwd(gy, y, want_b, bias_scale, act, slope)
+        else:
+            g = gy
+            gb = _ColSum.apply(g, bias_scale) if want_b else None
+        gx = _DownConvDgrad.apply(g, w, alpha) if ctx.needs_input_grad[0] else None
+        gw = _DownConvWgrad.apply(x, g, alpha) if (ctx.needs_input_grad[1] and pg) else None
+        return gx, gw, (gb.view(ctx.bshape) if gb is not None else None), None, None, None, None
+
+
+class _DownConvDgrad(Function):
+    """gx = alpha * conv_transpose(0.25 * upsample2x(gy), w).  Bilinear in (gy, w)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(gy, w)
+        return K.downconv_dgrad(gy, w, alpha)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gy, w = ctx.saved_tensors
+        g_gy = _DownConvFprop.apply(ggx, w, None, ctx.alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[0] else None
+        g_w = _DownConvWgrad.apply(ggx, gy, ctx.alpha) if ctx.needs_input_grad[1] else None
+        return g_gy, g_w, None
+
+
+class _DownConvWgrad(Function):
+    """gw = alpha * sum_pixels (0.25 * upsample2x(gy)) (x) x.  Bilinear in (x, gy)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(x, gy)
+        return K.downconv_wgrad(x, gy, alpha)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        g_x = _DownConvDgrad.apply(gy, ggw, ctx.alpha) if ctx.needs_input_grad[0] else None
+        g_gy = _DownConvFprop.apply(x, ggw, None, ctx.alpha, 1.0, ACT_NONE, 0.0) if ctx.needs_input_grad[1] else None
+        return g_x, g_gy, None
+
+
+def downconv2d(x, w, bias=None, alpha=1.0, bias_scale=1.0, act=ACT_NONE, slope=0.2):
+    """act(alpha * avgpool2x2(conv2d(x, w, pad=1)) + bias_scale * bias) for a 3x3 weight: one fused launch where the
+    tensor-core path covers the layer, conv2d -> pool_bias_act otherwise."""
+    N, Ci, H, W = x.shape
+    if (w.shape[2] == 3 and w.shape[3] == 3 and x.is_cuda and H % 2 == 0 and W % 2 == 0
+            and K.downconv_covers(N, H // 2, W // 2, Ci, w.shape[0])):
+        return _DownConvFprop.apply(x, w, bias, float(alpha), float(bias_scale), int(act), float(slope))
+    return pool_bias_act(conv2d(x, w, None, 1, alpha), bias, bias_scale, act, slope)
 
 
 class _AvgPoolBwd(Function):

@@ -72,6 +72,11 @@ class ConvLayer(nn.Sequential):
         slope = _slope(nl) if nl is not None else 0.2
         if post_blur is None and pool is None and bias is None:
             x = conv(x, act=act, slope=slope, blur=blur_after)                    # conv + bias + lrelu (+ blur), one op
+        elif (pool is not None and post_blur is None and not up and conv.ks == 3 and conv.padding == 1 and conv.conv2d.bias is None
+              and (bias is None or not (bias.bias is None))):
+            # conv -> avgpool -> bias -> lrelu as one stride-2 4x4 convolution (ops.downconv2d; falls back by itself)
+            x = ops.downconv2d(x, conv.conv2d.weight, bias.bias if bias is not None else None, conv.alpha,
+                               bias.bias_scale if bias is not None else 1., act, slope)
         else:
             x = conv(x)
             if post_blur is not None:

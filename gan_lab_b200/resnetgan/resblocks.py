@@ -8,7 +8,7 @@ a Batch/LayerNorm (or a convolution) into the producing kernel; the residual sum
 from torch import nn
 
 from .. import ops
-from ..utils.custom_layers import (Lambda, get_blur_op, NormalizeLayer, Conv2dEx, LeakyReLU, AvgPool2x, as_native_nl,
+from ..utils.custom_layers import (Lambda, get_blur_op, NormalizeLayer, Conv2dEx, LeakyReLU, AvgPool2x, Upsample2x, as_native_nl,
                                    as_native_upsampler, as_native_pooler)
 
 
@@ -25,6 +25,12 @@ def run_fused(seq, x):
             # avg-pool of the 3-channel image + 1x1 conv (FastResBlock2dDownsample's skip branch): one fromRGB kernel
             x = ops.fromrgb(x, nxt.conv2d.weight, nxt.conv2d.bias, nxt.alpha, nxt.lrmul if nxt.use_lrmul else 1.,
                             ops.ACT_NONE, 0.0, pool=True)
+            i += 2
+        elif isinstance(m, Upsample2x) and isinstance(nxt, Conv2dEx) and nxt.ks == 3 and nxt.padding == 1:
+            x = nxt(x, up=True)                         # upsample folded into the 3x3 convolution (ops.upconv2d)
+            i += 2
+        elif isinstance(m, Upsample2x) and isinstance(nxt, Conv2dEx) and nxt.ks == 1 and nxt.padding == 0:
+            x = m(nxt(x))                               # a 1x1 convolution commutes with nearest upsampling: same values, 1/4 of the work
             i += 2
         elif fuse:
             x = m(x, act=ops.ACT_LRELU, slope=nxt.negative_slope)

@@ -107,6 +107,24 @@ int glb_upconv_dgrad(const float* gy, const float* wt, float* gx, int N, int H, 
 int glb_upconv_wgrad(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
                      float alpha, glb_stream_t stream);
 
+/* ---- 2x2 average pool folded into the 3x3 convolution in front of it (TF32 tensor-core path) ---------------------- *
+ * Replaces `Conv2dEx(ks=3, padding=1)` + `nn.AvgPool2d(2, 2)` (+ Conv2dBias + LeakyReLU) of the discriminator blocks
+ * (progan/architectures.py:267-284; resnetgan/learner.py:160-164) by ONE launch that writes the LOW-resolution map:
+ * avgpool(conv3x3(x)) is a stride-2 4x4 convolution = 0.25 * U^T C_w, the adjoint structure of glb_upconv_* -- four
+ * strided input phases x 2x2 pre-summed taps, 4/9 of the multiply-adds, no full-resolution intermediate -- and runs on
+ * the same kernels with the flipped / transposed weights.
+ * x / gx [N,2H,2W,Ci], y / gy [N,H,W,Co] (H, W = output dims), w / gw [Co,3,3,Ci];
+ * y = act(0.25 * alpha * pooled conv + bias_scale * bias);  wt [Co,16,Ci] (forward) and wp [4*Ci,2,2,Co] (data gradient)
+ * come from glb_downconv_weights (wtmp [Ci,3,3,Co] scratch); gwp [Ci,16,Co] and gwt [Ci,3,3,Co] are scratch of the wgrad. */
+int glb_downconv_covers(int kind, int N, int H, int W, int Ci, int Co);
+int glb_downconv_weights(const float* w, float* wtmp, float* wp, float* wt, int Co, int Ci, glb_stream_t stream);
+int glb_downconv_fprop(const float* x, const float* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
+                       float alpha, float bias_scale, int act, float slope, glb_stream_t stream);
+int glb_downconv_dgrad(const float* gy, const float* wp, float* gx, int N, int H, int W, int Ci, int Co,
+                       float alpha, glb_stream_t stream);
+int glb_downconv_wgrad(const float* x, const float* gy, float* gwp, float* gwt, float* gw, int N, int H, int W, int Ci, int Co,
+                       float alpha, glb_stream_t stream);
+
 /* ---- RGB 1x1 convolutions (3 <-> C channels; pure bandwidth) ---------------------------------- *
  * fromRGB (progan/architectures.py:286-292) and toRGB (stylegan/architectures.py:338-341).
  * In all three the weight element (j = rgb channel, c = feature channel) lives at w[j*ws_j + c*ws_c], so the

@@ -71,6 +71,24 @@ def upconv_wgrad(x, gy, alpha):
     return conv_wgrad(O.upsample2x(x), gy, (3, 3), 1, alpha)
 
 
+# avgpool2x2(conv3x3_same(x)) + bias + activation and its gradients, as the literal composition the reference runs
+# (Conv2dEx + nn.AvgPool2d + Conv2dBias + LeakyReLU, progan/architectures.py:267-284): what glb_downconv_* must reproduce
+def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
+    v = F.avg_pool2d(alpha * F.conv2d(x, w, None, 1, 1), 2, 2)
+    if bias is not None:
+        v = v + bias_scale * _b(bias, 4)
+    return _cl(_act(v, act, slope))
+
+
+def downconv_dgrad(gy, w, alpha):
+    g = 0.25 * O.upsample2x(gy)
+    return conv_dgrad(g, w, (g.shape[2], g.shape[3]), 1, alpha)
+
+
+def downconv_wgrad(x, gy, alpha):
+    return conv_wgrad(x, 0.25 * O.upsample2x(gy), (3, 3), 1, alpha)
+
+
 def linear_fwd(x, w, bias, alpha, bias_scale, act, slope):
     y = alpha * (x @ w.t())
     if bias is not None:

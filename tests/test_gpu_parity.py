@@ -141,6 +141,63 @@ def test_upconv_family_vs_contract(shape):
         K.set_conv_impl("fp32")
 
 
+# Average pool folded into the convolution (glb_downconv_*): N, H, W (LOW-resolution output), Ci, Co
+DOWNCONV_SHAPES = [
+    (8, 4, 4, 512, 512), (8, 8, 8, 512, 512), (2, 16, 16, 512, 512), (2, 32, 32, 256, 512), (2, 64, 64, 128, 256),
+    (3, 5, 7, 64, 32), (2, 16, 16, 32, 64), (1, 32, 32, 128, 128),
+]
+
+
+@pytest.mark.parametrize("shape", DOWNCONV_SHAPES)
+def test_downconv_family_vs_contract(shape):
+    """avgpool2x2(conv3x3(x)) (+ bias + lrelu) as one stride-2 4x4 convolution vs the literal composition in fp64."""
+    N, H, W, Ci, Co = shape
+    x, w, b = cl(rn(N, Ci, 2 * H, 2 * W)), cl(rn(Co, Ci, 3, 3, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, H, W, seed=3))
+    K.set_conv_impl("tf32")
+    try:
+        assert K.downconv_covers(N, H, W, Ci, Co)
+        n0 = K.launch_count()
+        both("downconv_fprop", x, w, b, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_TF32)
+        both("downconv_fprop", x, w, None, 1.0, 1.0, K.ACT_NONE, 0.2, tol=TOL_TF32)
+        both("downconv_dgrad", gy, w, 0.37, tol=TOL_TF32)
+        both("downconv_wgrad", x, gy, 0.37, tol=TOL_TF32)
+        assert K.launch_count() > n0
+    finally:
+        K.set_conv_impl("fp32")
+
+
+def test_downconv_op_matches_two_kernel_sequence_incl_double_backward():
+    """ops.downconv2d (fused) against conv2d -> pool_bias_act on the same TF32 path: output with the fused bias + LeakyReLU, and
+    -- without the activation, whose mask would flip on outputs near zero between two differently rounded TF32 paths --
+    first-order gradients and the gradients of an R1-style penalty (double backward through the fused family)."""
+    from gan_lab_b200 import ops
+    N, H, W, Ci, Co = 2, 16, 16, 128, 128
+    x0, w0 = cl(rn(N, Ci, 2 * H, 2 * W)).to(DEV), cl(rn(Co, Ci, 3, 3, seed=1)).to(DEV)
+    b0 = rn(1, Co, 1, 1, seed=2).to(DEV)
+    K.set_conv_impl("tf32")
+    try:
+        ya = ops.downconv2d(x0, w0, b0, 0.05, 1.0, ops.ACT_LRELU, 0.2)
+        yb = ops.pool_bias_act(ops.conv2d(x0, w0, None, 1, 0.05), b0, 1.0, ops.ACT_LRELU, 0.2)
+        assert rel(ya, yb) < TOL_TF32
+        outs = []
+        for fused in (True, False):
+            x, w, b = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            n0 = K.launch_count()
+            if fused:
+                y = ops.downconv2d(x, w, b, 0.05, 1.0, ops.ACT_NONE, 0.2)
+            else:
+                y = ops.pool_bias_act(ops.conv2d(x, w, None, 1, 0.05), b, 1.0, ops.ACT_NONE, 0.2)
+            (gx,) = torch.autograd.grad(y.square().sum(), x, create_graph=True)
+            pen = (gx * gx).sum()
+            (y.square().sum() + 10.0 * pen).backward()
+            outs.append((y.detach(), gx.detach(), x.grad, w.grad, b.grad))
+        for i, (a, c) in enumerate(zip(*outs)):
+            assert rel(a, c) < TOL_TF32, (i, rel(a, c))
+    finally:
+        K.set_conv_impl("fp32")
+
+
 def test_upconv_op_matches_two_kernel_sequence():
     """ops.upconv2d (fused) against ops.conv2d(ops.upsample2x(x)) on the same TF32 path: outputs and all three gradients;
     with create_graph the backward falls back to the differentiable composition (second-order derivative exists)."""

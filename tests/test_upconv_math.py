@@ -69,3 +69,21 @@ def test_phase_forward_dgrad_wgrad_equal_the_composition():
                 for dx in range(2):
                     gw[:, :, r, s] += gwp[:, (dy * 2 + dx) * 4 + ay[dy] * 2 + ax[dx], :]
     torch.testing.assert_close(gw, KC.upconv_wgrad(x, gy, 1.0).contiguous(), rtol=1e-12, atol=1e-12)
+
+
+def test_downconv_is_the_adjoint_structure_of_upconv():
+    """glb_downconv_* runs on the upconv kernels: avgpool(conv(x, w)) = 0.25 * upconv_dgrad(x; w'), its data gradient =
+    0.25 * upconv_fprop(gy; w'), its weight gradient = 0.25 * flip/transpose(upconv_wgrad(gy, x)), w' = flipped, transposed w."""
+    torch.manual_seed(1)
+    N, Ci, Co, H, W = 2, 5, 4, 3, 4
+    x = torch.randn(N, Ci, 2 * H, 2 * W, dtype=torch.float64)
+    w = torch.randn(Co, Ci, 3, 3, dtype=torch.float64)
+    gy = torch.randn(N, Co, H, W, dtype=torch.float64)
+    wprime = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    kw = dict(rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(KC.downconv_fprop(x, w, None, 1.0, 1.0, 0, 0.2).contiguous(),
+                               0.25 * KC.upconv_dgrad(x, wprime, 1.0).contiguous(), **kw)
+    torch.testing.assert_close(KC.downconv_dgrad(gy, w, 1.0).contiguous(),
+                               0.25 * KC.upconv_fprop(gy, wprime, None, 1.0, 1.0, 0, 0.2).contiguous(), **kw)
+    torch.testing.assert_close(KC.downconv_wgrad(x, gy, 1.0).contiguous(),
+                               (0.25 * KC.upconv_wgrad(gy, x, 1.0)).flip(2, 3).permute(1, 0, 2, 3).contiguous(), **kw)
