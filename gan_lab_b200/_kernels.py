@@ -493,19 +493,39 @@ def upconv_covers(kind: str, N, H, W, Ci, Co) -> bool:
     return bool(LIB.fn("glb_upconv_covers")(_KIND[kind], N, H, W, Ci, Co))
 
 
-def upconv_weights(w):
-    """(wp [4*Co,2,2,Ci] for the forward, wt [Ci,16,Co] for the data gradient) of w [Co,Ci,3,3]; cached per weight version."""
-    key = (w.data_ptr(), tuple(w.shape))
+def _folded_weights(w, down, want):
+    """The two operand re-layouts of a folded convolution, cached per weight version: (forward operand, data-gradient operand).
+    One launch writes both when a backward pass can follow (grad mode on), only the forward one under no_grad; a missing one is
+    added on demand."""
+    key = (w.data_ptr(), tuple(w.shape), "down" if down else "up")
     hit = _cache_get(_up_cache, key, w._version)
-    if hit is not None:
-        return hit
+    fwd, bwd = hit if hit is not None else (None, None)
+    need_f = fwd is None and (want == "fwd" or torch.is_grad_enabled())
+    need_b = bwd is None and (want == "bwd" or torch.is_grad_enabled())
+    if (want == "fwd" and fwd is not None) or (want == "bwd" and bwd is not None):
+        return fwd, bwd
     Co, Ci, R, S = w.shape
-    wp = torch.empty((4 * Co, 2, 2, Ci), device=w.device, dtype=torch.float32)
-    wt = torch.empty((Ci, 16, Co), device=w.device, dtype=torch.float32)
-    _call("glb_upconv_weights", _p(w), _p(wp), _p(wt), Co, Ci, _stream())
-    if len(_up_cache) >= 32:
+    if down:        # forward: wt [Co,16,Ci]; data gradient: wp [4*Ci,2,2,Co]
+        if need_f:
+            fwd = torch.empty((Co, 16, Ci), device=w.device, dtype=torch.float32)
+        if need_b:
+            bwd = torch.empty((4 * Ci, 2, 2, Co), device=w.device, dtype=torch.float32)
+        _call("glb_downconv_weights", _p(w), _p(bwd if need_b else None), _p(fwd if need_f else None), Co, Ci, _stream())
+    else:           # forward: wp [4*Co,2,2,Ci]; data gradient: wt [Ci,16,Co]
+        if need_f:
+            fwd = torch.empty((4 * Co, 2, 2, Ci), device=w.device, dtype=torch.float32)
+        if need_b:
+            bwd = torch.empty((Ci, 16, Co), device=w.device, dtype=torch.float32)
+        _call("glb_upconv_weights", _p(w), _p(fwd if need_f else None), _p(bwd if need_b else None), Co, Ci, _stream())
+    if len(_up_cache) >= 64:
         _up_cache.clear()
-    return _cache_put(_up_cache, key, w._version, (wp, wt), w)
+    _cache_put(_up_cache, key, w._version, (fwd, bwd), w)
+    return fwd, bwd
+
+
+def upconv_weights(w, want="fwd"):
+    """(wp [4*Co,2,2,Ci] for the forward, wt [Ci,16,Co] for the data gradient) of w [Co,Ci,3,3]."""
+    return _folded_weights(w, False, want)
 
 
 def upconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
@@ -515,7 +535,7 @@ def upconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
     Co, Ci2, R, S = w.shape
     if Ci != Ci2 or R != 3 or S != 3:
         raise GlbError("upconv_fprop: needs a 3x3 weight with matching channels")
-    wp, _ = upconv_weights(w)
+    wp, _ = upconv_weights(w, "fwd")
     y = _new_nhwc(N, Co, 2 * H, 2 * W, x)
     _call("glb_upconv_fprop", _p(x), _p(wp), _p(_flat(bias)), _p(y), N, H, W, Ci, Co, float(alpha), float(bias_scale), int(act),
           float(slope), _stream())
@@ -529,7 +549,7 @@ def upconv_dgrad(gy, w, alpha):
     Co2, Ci, R, S = w.shape
     if Co != Co2 or H2 % 2 or W2 % 2:
         raise GlbError("upconv_dgrad: shape mismatch")
-    _, wt = upconv_weights(w)
+    _, wt = upconv_weights(w, "bwd")
     gx = _new_nhwc(N, Ci, H2 // 2, W2 // 2, gy)
     _call("glb_upconv_dgrad", _p(gy), _p(wt), _p(gx), N, H2 // 2, W2 // 2, Ci, Co, float(alpha), _stream())
     return gx
@@ -558,20 +578,9 @@ def downconv_covers(N, H, W, Ci, Co) -> bool:
     return all(bool(f(k, N, H, W, Ci, Co)) for k in (0, 1, 2))
 
 
-def downconv_weights(w):
-    """(wp [4*Ci,2,2,Co] for the data gradient, wt [Co,16,Ci] for the forward) of w [Co,Ci,3,3]; cached per weight version."""
-    key = (w.data_ptr(), tuple(w.shape), "down")
-    hit = _cache_get(_up_cache, key, w._version)
-    if hit is not None:
-        return hit
-    Co, Ci, R, S = w.shape
-    wtmp = torch.empty((Ci, 3, 3, Co), device=w.device, dtype=torch.float32)
-    wp = torch.empty((4 * Ci, 2, 2, Co), device=w.device, dtype=torch.float32)
-    wt = torch.empty((Co, 16, Ci), device=w.device, dtype=torch.float32)
-    _call("glb_downconv_weights", _p(w), _p(wtmp), _p(wp), _p(wt), Co, Ci, _stream())
-    if len(_up_cache) >= 32:
-        _up_cache.clear()
-    return _cache_put(_up_cache, key, w._version, (wp, wt), w)
+def downconv_weights(w, want="fwd"):
+    """(wt [Co,16,Ci] for the forward, wp [4*Ci,2,2,Co] for the data gradient) of w [Co,Ci,3,3]."""
+    return _folded_weights(w, True, want)
 
 
 def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
@@ -582,7 +591,7 @@ def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
     Co, Ci2, R, S = w.shape
     if Ci != Ci2 or R != 3 or S != 3 or H2 % 2 or W2 % 2:
         raise GlbError("downconv_fprop: needs a 3x3 weight with matching channels and an even map")
-    _, wt = downconv_weights(w)
+    wt, _ = downconv_weights(w, "fwd")
     y = _new_nhwc(N, Co, H2 // 2, W2 // 2, x)
     _call("glb_downconv_fprop", _p(x), _p(wt), _p(_flat(bias)), _p(y), N, H2 // 2, W2 // 2, Ci, Co, float(alpha), float(bias_scale),
           int(act), float(slope), _stream())
@@ -596,7 +605,7 @@ def downconv_dgrad(gy, w, alpha):
     Co2, Ci, R, S = w.shape
     if Co != Co2:
         raise GlbError("downconv_dgrad: shape mismatch")
-    wp, _ = downconv_weights(w)
+    _, wp = downconv_weights(w, "bwd")
     gx = _new_nhwc(N, Ci, 2 * H, 2 * W, gy)
     _call("glb_downconv_dgrad", _p(gy), _p(wp), _p(gx), N, H, W, Ci, Co, float(alpha), _stream())
     return gx
@@ -610,9 +619,8 @@ def downconv_wgrad(x, gy, alpha):
     if N != N2 or H2 != 2 * H or W2 != 2 * W:
         raise GlbError("downconv_wgrad: shape mismatch")
     gwp = torch.empty((Ci, 16, Co), device=x.device, dtype=torch.float32)
-    gwt = torch.empty((Ci, 3, 3, Co), device=x.device, dtype=torch.float32)
     gw = _new_nhwc(Co, Ci, 3, 3, x)
-    _call("glb_downconv_wgrad", _p(x), _p(gy), _p(gwp), _p(gwt), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
+    _call("glb_downconv_wgrad", _p(x), _p(gy), _p(gwp), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
     return gw
 
 

@@ -142,21 +142,21 @@ extern "C" int glb_upconv_wgrad(const float* x, const float* gy, float* gwp, flo
 // ---- 2x2 average pool folded into the 3x3 convolution in front of it (csrc/conv_tc.cu) ---------------------------------------
 namespace glb {
 bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co);
-int conv_downconv_weights(const float* w, float* wtmp, float* wp, float* wt, int Co, int Ci, cudaStream_t st);
+int conv_downconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, cudaStream_t st);
 int conv_downconv_fprop_tc(const float* x, const float* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
                            float bias_scale, int act, float slope, cudaStream_t st);
 int conv_downconv_dgrad_tc(const float* gy, const float* wp, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st);
-int conv_downconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gwt, float* gw, int N, int H, int W, int Ci, int Co,
-                           float alpha, cudaStream_t st);
+int conv_downconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                           cudaStream_t st);
 }  // namespace glb
 
 extern "C" int glb_downconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
   if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return 0;
   return glb::conv_downconv_covers(kind, N, H, W, Ci, Co) ? 1 : 0;
 }
-extern "C" int glb_downconv_weights(const float* w, float* wtmp, float* wp, float* wt, int Co, int Ci, glb_stream_t stream) {
-  if (Co <= 0 || Ci <= 0 || Co % 4 != 0) return glb::shape_fail("downconv_weights");
-  return glb::conv_downconv_weights(w, wtmp, wp, wt, Co, Ci, (cudaStream_t)stream);
+extern "C" int glb_downconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, glb_stream_t stream) {
+  if (Co <= 0 || Ci <= 0) return glb::shape_fail("downconv_weights");
+  return glb::conv_downconv_weights(w, wp, wt, Co, Ci, (cudaStream_t)stream);
 }
 extern "C" int glb_downconv_fprop(const float* x, const float* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
                                   float alpha, float bias_scale, int act, float slope, glb_stream_t stream) {
@@ -168,8 +168,8 @@ extern "C" int glb_downconv_dgrad(const float* gy, const float* wp, float* gx, i
   if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("downconv_dgrad");
   return glb::conv_downconv_dgrad_tc(gy, wp, gx, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
 }
-extern "C" int glb_downconv_wgrad(const float* x, const float* gy, float* gwp, float* gwt, float* gw, int N, int H, int W, int Ci,
-                                  int Co, float alpha, glb_stream_t stream) {
+extern "C" int glb_downconv_wgrad(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
+                                  float alpha, glb_stream_t stream) {
   if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("downconv_wgrad");
-  return glb::conv_downconv_wgrad_tc(x, gy, gwp, gwt, gw, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
+  return glb::conv_downconv_wgrad_tc(x, gy, gwp, gw, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
 }

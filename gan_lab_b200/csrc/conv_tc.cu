@@ -2216,48 +2216,89 @@ __device__ __forceinline__ void up_taps(int d, int a, int& lo, int& hi) {
   hi = d == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
 }
 
-// wp[ph][co][a][b][ci]: one float4 of ci per thread
-__global__ void upconv_weights_fwd_kernel(const float4* __restrict__ w, float4* __restrict__ wp, int Co, int Ci4) {
-  const int64_t total = (int64_t)16 * Co * Ci4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % Ci4);
-    int64_t t = i / Ci4;
-    const int ab = (int)(t & 3); t >>= 2;
-    const int co = (int)(t % Co);
-    const int ph = (int)(t / Co);
-    int r0, r1, s0, s1;
-    up_taps(ph >> 1, ab >> 1, r0, r1);
-    up_taps(ph & 1, ab & 1, s0, s1);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = r0; r <= r1; ++r)
-      for (int s = s0; s <= s1; ++s) {
-        const float4 v = __ldg(w + ((int64_t)co * 9 + r * 3 + s) * Ci4 + c4);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+// Operand re-layout of the folded convolutions, ONE pass over w [Co][3][3][Ci] per layer and optimiser step.  With
+//   S[ph][a][b][co][ci] = sum_{r in T(dy,a), s in T(dx,b)} wsrc[co][r][s][ci],   wsrc = w (upconv) or w with flipped taps (downconv)
+// the four operands are
+//   upconv   forward  wp [ph][co][a][b][ci]          = S[ph][a][b]        (ci innermost: "A" output)
+//            dgrad    wt [ci][ph*4 + a'*2 + b'][co]  = S[ph][1-a'][1-b']  (co innermost: "B" output, transposed)
+//   downconv forward  wt'[co][ph*4 + a'*2 + b'][ci]  = S[ph][1-a'][1-b']  ("A")
+//            dgrad    wp'[ph][ci][a][b][co]          = S[ph][a][b]        ("B")
+// A block stages the nine 32 x 32 (co, ci) tap tiles in shared memory and writes all 16 slots of both outputs from there;
+// 1024 threads, one (co, ci) element of either orientation per thread (with 256 threads and four rows per thread the
+// serial instruction stream of a block took 22 us whatever the layer size).
+template <bool DOWN>
+__global__ void __launch_bounds__(1024) fold_weights_kernel(const float* __restrict__ w, float* __restrict__ outA, float* __restrict__ outB,
+                                                           int Co, int Ci) {
+  __shared__ float t[9][32][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int src = DOWN ? 8 - tap : tap;
+    const int co = co0 + y, ci = ci0 + x;
+    t[tap][y][x] = (co < Co && ci < Ci) ? __ldg(w + ((int64_t)co * 9 + src) * Ci + ci) : 0.f;
+  }
+  __syncthreads();
+  // per (row i): the nine taps of element (co0+i, ci0+x) ["A" orientation] and of (co0+x, ci0+i) ["B"] go to registers, the 16
+  // slot sums are compile-time tap subsets (everything below unrolls), stores are 128-byte rows of either output
+  {
+    const int i = y;
+    float va[9], vb[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) { va[tap] = t[tap][i][x]; vb[tap] = t[tap][x][i]; }
+    const int coA = co0 + i, ciA = ci0 + x, coB = co0 + x, ciB = ci0 + i;
+    const bool okA = outA != nullptr && coA < Co && ciA < Ci, okB = outB != nullptr && coB < Co && ciB < Ci;
+#pragma unroll
+    for (int slot = 0; slot < 16; ++slot) {
+      const int ph = slot >> 2, a = (slot >> 1) & 1, b = slot & 1;
+      const int flipped = ph * 4 + (1 - a) * 2 + (1 - b);
+      int r0, r1, s0, s1;
+      up_taps(ph >> 1, a, r0, r1);
+      up_taps(ph & 1, b, s0, s1);
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (r >= r0 && r <= r1 && q >= s0 && q <= s1) { sa += va[r * 3 + q]; sb += vb[r * 3 + q]; }
+      if (okA) {
+        if (DOWN) outA[((int64_t)coA * 16 + flipped) * Ci + ciA] = sa;
+        else outA[(((int64_t)ph * Co + coA) * 4 + a * 2 + b) * Ci + ciA] = sa;
       }
-    wp[i] = acc;
+      if (okB) {
+        if (DOWN) outB[(((int64_t)ph * Ci + ciB) * 4 + a * 2 + b) * Co + coB] = sb;
+        else outB[((int64_t)ciB * 16 + flipped) * Co + coB] = sb;
+      }
+    }
   }
 }
 
-// wt[ci][ph*4 + a'*2 + b'][co] = wp[ph][co][1-a'][1-b'][ci]: 32 x 32 tile transpose over (co, ci) per (phase, tap)
-__global__ void upconv_weights_bwd_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci) {
-  __shared__ float tile[32][33];
-  const int t16 = blockIdx.z, ph = t16 >> 2, a = 1 - ((t16 >> 1) & 1), b = 1 - (t16 & 1);
-  int r0, r1, s0, s1;
-  up_taps(ph >> 1, a, r0, r1);
-  up_taps(ph & 1, b, s0, s1);
-  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int co = co0 + i, ci = ci0 + threadIdx.x;
-    float acc = 0.f;
-    if (co < Co && ci < Ci)
-      for (int r = r0; r <= r1; ++r)
-        for (int s = s0; s <= s1; ++s) acc += w[((int64_t)co * 9 + r * 3 + s) * Ci + ci];
-    tile[i][threadIdx.x] = acc;
+// downconv weight gradient: gw[co][r][s][ci] = gw'[ci][2-r][2-s][co] with gw' the 3x3 fold (below) of gwp [ci][16][co]: fold
+// and transpose in one pass (16 ci x 32 co tiles of all 16 slots staged in shared memory)
+__global__ void __launch_bounds__(512) fold_wgrad_transposed_kernel(const float* __restrict__ gwp, float* __restrict__ gw, int Co, int Ci) {
+  __shared__ float t[16][16][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 16;
+#pragma unroll
+  for (int slot = 0; slot < 16; ++slot) {
+    const int ci = ci0 + y, co = co0 + x;                  // 512 threads: y = 0..15
+    t[slot][y][x] = (ci < Ci && co < Co) ? __ldg(gwp + ((int64_t)ci * 16 + slot) * Co + co) : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int ci = ci0 + i, co = co0 + threadIdx.x;
-    if (co < Co && ci < Ci) wt[((int64_t)ci * 16 + t16) * Co + co] = tile[threadIdx.x][i];
+  const int xi = threadIdx.x & 15, j = threadIdx.x >> 4;
+#pragma unroll
+  for (int rs = 0; rs < 9; ++rs) {
+    const int r = 2 - rs / 3, q = 2 - rs % 3;              // tap of gw' behind tap rs of gw
+    const int ay[2] = {r == 0 ? 0 : 1, r == 2 ? 1 : 0}, ax[2] = {q == 0 ? 0 : 1, q == 2 ? 1 : 0};
+    {
+      float acc = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) acc += t[(dy * 2 + dx) * 4 + ay[dy] * 2 + ax[dx]][xi][j];
+      const int co = co0 + j, ci = ci0 + xi;
+      if (co < Co && ci < Ci) gw[((int64_t)co * 9 + rs) * Ci + ci] = acc;
+    }
   }
 }
 
@@ -2286,24 +2327,16 @@ __global__ void upconv_wgrad_fold_kernel(const float4* __restrict__ gwp, float4*
 }  // namespace
 
 int conv_upconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, cudaStream_t st) {
-  if (Ci % 4 != 0) { set_error("upconv weights: Ci % 4 != 0"); return GLB_ERR_SHAPE; }
-  if (wp) {
-    const int64_t total = (int64_t)16 * Co * (Ci / 4);
-    const int grid = (int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs);
-    upconv_weights_fwd_kernel<<<grid, 256, 0, st>>>((const float4*)w, (float4*)wp, Co, Ci / 4);
-    GLB_CHECK_LAUNCH("upconv_weights_fwd_kernel");
-  }
-  if (wt) {
-    dim3 grid((Ci + 31) / 32, (Co + 31) / 32, 16), block(32, 8);
-    upconv_weights_bwd_kernel<<<grid, block, 0, st>>>(w, wt, Co, Ci);
-    GLB_CHECK_LAUNCH("upconv_weights_bwd_kernel");
-  }
+  if (wp == nullptr && wt == nullptr) return GLB_OK;
+  dim3 grid((Ci + 31) / 32, (Co + 31) / 32);
+  fold_weights_kernel<false><<<grid, 1024, 0, st>>>(w, wp, wt, Co, Ci);
+  GLB_CHECK_LAUNCH("fold_weights_kernel");
   return GLB_OK;
 }
 
 // gw [Co][3][3][Ci] of conv3x3(upsample2x(x)); gwp = [Co][16][Ci] scratch (phase/tap gradients, folded at the end)
-int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
-                         cudaStream_t st) {
+static int upconv_wgrad_impl(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                             bool transposed_out, cudaStream_t st) {
   if (!conv_upconv_covers(2, N, H, W, Ci, Co)) {
     set_error("upconv wgrad: shape not covered (Ci and Co multiples of 32)");
     return GLB_ERR_UNSUPPORTED;
@@ -2360,11 +2393,22 @@ int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw,
     case 32: rc = launch_wgrad<32, 64>(tmGy, tmX, p, grid, st); break;
   }
   if (rc != GLB_OK) return rc;
+  if (transposed_out) {     // downconv: this problem's (Co, Ci) are the layer's (Ci, Co); gw is the layer's [Co_layer][3][3][Ci_layer]
+    dim3 tgrid((Co + 15) / 16, (Ci + 31) / 32);
+    fold_wgrad_transposed_kernel<<<tgrid, 512, 0, st>>>(gwp, gw, /*Co_layer =*/Ci, /*Ci_layer =*/Co);
+    GLB_CHECK_LAUNCH("fold_wgrad_transposed_kernel");
+    return GLB_OK;
+  }
   const int64_t total = (int64_t)Co * 9 * (Ci / 4);
   const int fgrid = (int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs);
   upconv_wgrad_fold_kernel<<<fgrid, 256, 0, st>>>((const float4*)gwp, (float4*)gw, Co, Ci / 4);
   GLB_CHECK_LAUNCH("upconv_wgrad_fold_kernel");
   return GLB_OK;
+}
+
+int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                         cudaStream_t st) {
+  return upconv_wgrad_impl(x, gy, gwp, gw, N, H, W, Ci, Co, alpha, false, st);
 }
 
 // ------------------------------------------------------------------------------------------------ 2x2 average pool folded into the conv
@@ -2376,9 +2420,7 @@ int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw,
 //   dgrad  gx = 0.25 * upconv_fprop(gy; w')
 //   wgrad  gw = 0.25 * transpose_flip(upconv_wgrad(x_lo := gy, gy_hi := x))
 // so the same three kernels serve it; H, W below are the LOW-resolution (output) dims, x / gx are [N,2H,2W,Ci].
-// glb_downconv_weights: wp [4*Ci][2][2][Co] (dgrad) and wt [Co][16][Ci] (fprop) = glb_upconv_weights of w'.
-extern "C" int glb_conv2d_weight_transpose(const float* w, float* wt, int Co, int R, int S, int Ci, glb_stream_t stream);
-
+// glb_downconv_weights: wp [4*Ci][2][2][Co] (dgrad) and wt [Co][16][Ci] (fprop) = glb_upconv_weights of w' (fold_weights_kernel<true>).
 bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
   switch (kind) {
     case 0: return conv_upconv_covers(1, N, H, W, Co, Ci);
@@ -2388,10 +2430,12 @@ bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
   return false;
 }
 
-int conv_downconv_weights(const float* w, float* wtmp, float* wp, float* wt, int Co, int Ci, cudaStream_t st) {
-  int rc = glb_conv2d_weight_transpose(w, wtmp, Co, 3, 3, Ci, (glb_stream_t)st);    // w'[ci][2-r][2-s][co]
-  if (rc) return rc;
-  return conv_upconv_weights(wtmp, wp, wt, /*Co' =*/Ci, /*Ci' =*/Co, st);
+int conv_downconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, cudaStream_t st) {
+  if (wp == nullptr && wt == nullptr) return GLB_OK;
+  dim3 grid((Ci + 31) / 32, (Co + 31) / 32);
+  fold_weights_kernel<true><<<grid, 1024, 0, st>>>(w, /*A: forward operand*/ wt, /*B: dgrad operand*/ wp, Co, Ci);
+  GLB_CHECK_LAUNCH("fold_weights_kernel");
+  return GLB_OK;
 }
 
 int conv_downconv_fprop_tc(const float* x, const float* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
@@ -2411,16 +2455,14 @@ int conv_downconv_dgrad_tc(const float* gy, const float* wp, float* gx, int N, i
   return upconv_launch(1, gy, wp, nullptr, gx, N, H, W, Co, Ci, 0.25f * alpha, 0.f, GLB_ACT_NONE, 0.f, st);
 }
 
-// gwp [Ci][16][Co] and gwt [Ci][3][3][Co] are scratch
-int conv_downconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gwt, float* gw, int N, int H, int W, int Ci, int Co,
-                           float alpha, cudaStream_t st) {
+// gwp [Ci][16][Co] is scratch
+int conv_downconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                           cudaStream_t st) {
   if (!conv_downconv_covers(2, N, H, W, Ci, Co)) {
     set_error("downconv wgrad: shape not covered (Ci and Co multiples of 32)");
     return GLB_ERR_UNSUPPORTED;
   }
-  int rc = conv_upconv_wgrad_tc(gy, x, gwp, gwt, N, H, W, /*Ci' =*/Co, /*Co' =*/Ci, 0.25f * alpha, st);
-  if (rc) return rc;
-  return glb_conv2d_weight_transpose(gwt, gw, /*Co' =*/Ci, 3, 3, /*Ci' =*/Co, (glb_stream_t)st);
+  return upconv_wgrad_impl(gy, x, gwp, gw, N, H, W, /*Ci' =*/Co, /*Co' =*/Ci, 0.25f * alpha, true, st);
 }
 
 }  // namespace glb

@@ -115,14 +115,14 @@ int glb_upconv_wgrad(const float* x, const float* gy, float* gwp, float* gw, int
  * the same kernels with the flipped / transposed weights.
  * x / gx [N,2H,2W,Ci], y / gy [N,H,W,Co] (H, W = output dims), w / gw [Co,3,3,Ci];
  * y = act(0.25 * alpha * pooled conv + bias_scale * bias);  wt [Co,16,Ci] (forward) and wp [4*Ci,2,2,Co] (data gradient)
- * come from glb_downconv_weights (wtmp [Ci,3,3,Co] scratch); gwp [Ci,16,Co] and gwt [Ci,3,3,Co] are scratch of the wgrad. */
+ * come from glb_downconv_weights (either may be NULL); gwp [Ci,16,Co] is scratch of the wgrad. */
 int glb_downconv_covers(int kind, int N, int H, int W, int Ci, int Co);
-int glb_downconv_weights(const float* w, float* wtmp, float* wp, float* wt, int Co, int Ci, glb_stream_t stream);
+int glb_downconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, glb_stream_t stream);
 int glb_downconv_fprop(const float* x, const float* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
                        float alpha, float bias_scale, int act, float slope, glb_stream_t stream);
 int glb_downconv_dgrad(const float* gy, const float* wp, float* gx, int N, int H, int W, int Ci, int Co,
                        float alpha, glb_stream_t stream);
-int glb_downconv_wgrad(const float* x, const float* gy, float* gwp, float* gwt, float* gw, int N, int H, int W, int Ci, int Co,
+int glb_downconv_wgrad(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
                        float alpha, glb_stream_t stream);
 
 /* ---- RGB 1x1 convolutions (3 <-> C channels; pure bandwidth) ---------------------------------- *

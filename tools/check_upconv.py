@@ -41,6 +41,11 @@ def main():
             ("dgrad", lambda: K.upconv_dgrad(gy, w, 1.0), lambda: K.upsample2x_bwd(K.conv_dgrad(gy, w, (2 * H, 2 * W), 1, 1.0))),
             ("wgrad", lambda: K.upconv_wgrad(x, gy, 1.0), lambda: K.conv_wgrad(xu, gy, (3, 3), 1, 1.0)),
         ]
+        def prep(down):
+            K._up_cache.clear()
+            K._folded_weights(w, down, "fwd")         # grad mode on: both operands in one launch
+        print(f"    operand re-layout (both operands, one launch): upconv {timed(lambda: prep(False)):6.1f} us   downconv {timed(lambda: prep(True)):6.1f} us"
+              f"   ({(9 + 32) * Ci * Co * 4 / 1e6:.1f} MB)")
         for kind, fused, two in rows:
             tf, tt = timed(fused), timed(two)
             print(f"N{N} {H}x{W}->{2*H}x{2*W} {Ci}->{Co:<6d} {kind:6s} {tf:9.1f} {fl / tf / 1e6:10.1f} {tt:14.1f} {tt / tf:8.2f}")
