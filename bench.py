@@ -127,10 +127,13 @@ def measured_mma_peaks():
     return out
 
 
+DOMINANT_KERNEL = "conv_fprop_tc2_kernel<256"     # CTA-pair implicit GEMM (plain 3x3 layers below one wave of halo tiles + the folded layers)
+
+
 def ncu_traffic():
     """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant convolution kernel, read from
     the committed `ncu --set full` capture (profiles/r2_ncu_full_conv_family.csv, raw page, one row per launch; the rows of
-    conv_fprop_tc2_halo_kernel<256>, the kernel with the largest share of the step)."""
+    DOMINANT_KERNEL, the kernel with the largest share of the step in profiles/r2_launches_cfg2_tf32_summary.txt)."""
     import csv
     p = ROOT / "profiles" / "r2_ncu_full_conv_family.csv"
     if not p.exists():
@@ -140,7 +143,7 @@ def ncu_traffic():
         hdr = rows[0]
         rd, wr, nm = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
         body = [r for r in rows[1:] if len(r) == len(hdr) and r[hdr.index("ID")].strip().isdigit()
-                and "conv_fprop_tc2_halo_kernel<256>" in r[nm]]
+                and DOMINANT_KERNEL in r[nm]]
         unit = rows[1] if rows[1][hdr.index("ID")].strip() == "" else None          # units row of the raw page
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         def val(r, i):
@@ -148,7 +151,7 @@ def ncu_traffic():
             return float(r[i].replace(",", "")) * scale.get(u, 1.0)
         tr = [val(r, rd) + val(r, wr) for r in body]
         return {"traffic": sum(tr) / len(tr),
-                "traffic_note": f"mean over {len(tr)} launches of conv_fprop_tc2_halo_kernel<256> in profiles/r2_ncu_full_conv_family.csv "
+                "traffic_note": f"mean over {len(tr)} launches of {DOMINANT_KERNEL}...> in profiles/r2_ncu_full_conv_family.csv "
                                 "(dram__bytes_read.sum + dram__bytes_write.sum)"}
     except Exception as e:          # noqa: BLE001
         return {"traffic": None, "traffic_note": "ncu csv unreadable: " + repr(e)[:120]}
@@ -875,11 +878,18 @@ def kernel_rooflines(L, x, main_iter, flush):
     tot_f = sum(v[0] for v in by.values())
     tot_ms = sum(v[1] for v in by.values())
     n_launch = sum(v[2] for v in by.values())
-    conv = {"bound": "tensor", "kernel": "conv2d fprop/dgrad/wgrad family (tcgen05 implicit GEMM, operands " + K.get_conv_impl() +
-                                       "; FFMA for uncovered shapes; bf16 mode: the operand conversion passes are counted under glue)",
+    # the folded layers execute 16 taps per low-resolution pixel where the literal upsample -> conv / conv -> pool sequence of the
+    # reference executes 36: `achieved` counts what the kernels EXECUTE; the literal-sequence figure is reported beside it
+    lit_f = sum(v[0] * (2.25 if n.startswith(("upconv", "downconv")) else 1.0) for n, v in by.items())
+    conv = {"bound": "tensor", "kernel": "conv2d fprop/dgrad/wgrad family incl. the upsample- / pool-folded layers (tcgen05 implicit GEMM, "
+                                       "operands " + K.get_conv_impl() + "; FFMA for uncovered shapes; bf16 mode: the operand conversion "
+                                       "passes are counted under glue); FLOPs = executed by the kernels",
             "achieved": tot_f / (tot_ms / 1e3) / 1e12, "unit": "TFLOP/s", "traffic": None, "launches": n_launch,
             "avg_launch_us": 1e3 * tot_ms / max(n_launch, 1), "conv_ms_per_step": tot_ms,
-            "by_kind_tflops": {n: v[0] / (v[1] / 1e3) / 1e12 for n, v in by.items()}}
+            "executed_conv_gflop_per_step": tot_f / 1e9, "literal_sequence_conv_gflop_per_step": lit_f / 1e9,
+            "tflops_on_literal_sequence_flops": lit_f / (tot_ms / 1e3) / 1e12,
+            "by_kind_tflops": {n: v[0] / (v[1] / 1e3) / 1e12 for n, v in by.items()},
+            "by_kind_ms": {n: round(v[1], 4) for n, v in by.items()}}
     # layers whose arithmetic intensity (algorithmic FLOPs / compulsory bytes: operands + output, 4 B each) lies
     # below the ridge of the machine -- 3-channel / 16-32-channel layers at high resolution, weight-bound layers with M <= 512
     # pixels -- are HBM-bound and belong on the HBM roofline; the rest on the tensor roofline.  Both classes timed separately.

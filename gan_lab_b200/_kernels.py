@@ -487,10 +487,17 @@ _up_cache = {}
 
 
 def upconv_covers(kind: str, N, H, W, Ci, Co) -> bool:
-    """H, W: LOW-resolution map.  Only in "tf32" mode (the exact FFMA and the bf16-operand modes keep the two-kernel sequence)."""
-    if _state["conv_impl"] != "tf32" or os.environ.get("GLB_UPCONV", "1") == "0":
+    """H, W: LOW-resolution map.  Tensor-core modes only (the exact FFMA mode keeps the two-kernel sequence); in "bf16" mode a
+    layer the bf16 kernels do not cover (channel counts not multiples of 64) falls back to the two-kernel sequence as well."""
+    if not _tc_mode() or os.environ.get("GLB_UPCONV", "1") == "0":
         return False
-    return bool(LIB.fn("glb_upconv_covers")(_KIND[kind], N, H, W, Ci, Co))
+    name = "glb_upconv_bf16_covers" if _state["conv_impl"] == "bf16" else "glb_upconv_covers"
+    return bool(LIB.fn(name)(_KIND[kind], N, H, W, Ci, Co))
+
+
+def _fold16(t):
+    """bf16 copy of a re-laid-out weight operand (contiguous), cached with the operand itself"""
+    return _to_bf16(t, "fold")
 
 
 def _folded_weights(w, down, want):
@@ -537,6 +544,10 @@ def upconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
         raise GlbError("upconv_fprop: needs a 3x3 weight with matching channels")
     wp, _ = upconv_weights(w, "fwd")
     y = _new_nhwc(N, Co, 2 * H, 2 * W, x)
+    if _state["conv_impl"] == "bf16":
+        _call("glb_upconv_fprop_bf16", _p(bf16_operand(x)), _p(_fold16(wp)), _p(_flat(bias)), _p(y), N, H, W, Ci, Co, float(alpha),
+              float(bias_scale), int(act), float(slope), _stream())
+        return y
     _call("glb_upconv_fprop", _p(x), _p(wp), _p(_flat(bias)), _p(y), N, H, W, Ci, Co, float(alpha), float(bias_scale), int(act),
           float(slope), _stream())
     return y
@@ -551,6 +562,9 @@ def upconv_dgrad(gy, w, alpha):
         raise GlbError("upconv_dgrad: shape mismatch")
     _, wt = upconv_weights(w, "bwd")
     gx = _new_nhwc(N, Ci, H2 // 2, W2 // 2, gy)
+    if _state["conv_impl"] == "bf16":
+        _call("glb_upconv_dgrad_bf16", _p(bf16_operand(gy)), _p(_fold16(wt)), _p(gx), N, H2 // 2, W2 // 2, Ci, Co, float(alpha), _stream())
+        return gx
     _call("glb_upconv_dgrad", _p(gy), _p(wt), _p(gx), N, H2 // 2, W2 // 2, Ci, Co, float(alpha), _stream())
     return gx
 
@@ -564,6 +578,9 @@ def upconv_wgrad(x, gy, alpha):
         raise GlbError("upconv_wgrad: shape mismatch")
     gwp = torch.empty((Co, 16, Ci), device=x.device, dtype=torch.float32)
     gw = _new_nhwc(Co, Ci, 3, 3, x)
+    if _state["conv_impl"] == "bf16":
+        _call("glb_upconv_wgrad_bf16", _p(bf16_operand(x)), _p(bf16_operand(gy)), _p(gwp), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
+        return gw
     _call("glb_upconv_wgrad", _p(x), _p(gy), _p(gwp), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
     return gw
 
@@ -572,9 +589,9 @@ def upconv_wgrad(x, gy, alpha):
 def downconv_covers(N, H, W, Ci, Co) -> bool:
     """H, W: LOW-resolution (output) map.  All three kernels must cover the pair (the family is closed under differentiation:
     the R1 double backward runs fprop / dgrad / wgrad of the same layer)."""
-    if _state["conv_impl"] != "tf32" or os.environ.get("GLB_DOWNCONV", "1") == "0":
+    if not _tc_mode() or os.environ.get("GLB_DOWNCONV", "1") == "0":
         return False
-    f = LIB.fn("glb_downconv_covers")
+    f = LIB.fn("glb_downconv_bf16_covers" if _state["conv_impl"] == "bf16" else "glb_downconv_covers")
     return all(bool(f(k, N, H, W, Ci, Co)) for k in (0, 1, 2))
 
 
@@ -593,6 +610,10 @@ def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
         raise GlbError("downconv_fprop: needs a 3x3 weight with matching channels and an even map")
     wt, _ = downconv_weights(w, "fwd")
     y = _new_nhwc(N, Co, H2 // 2, W2 // 2, x)
+    if _state["conv_impl"] == "bf16":
+        _call("glb_downconv_fprop_bf16", _p(bf16_operand(x)), _p(_fold16(wt)), _p(_flat(bias)), _p(y), N, H2 // 2, W2 // 2, Ci, Co,
+              float(alpha), float(bias_scale), int(act), float(slope), _stream())
+        return y
     _call("glb_downconv_fprop", _p(x), _p(wt), _p(_flat(bias)), _p(y), N, H2 // 2, W2 // 2, Ci, Co, float(alpha), float(bias_scale),
           int(act), float(slope), _stream())
     return y
@@ -607,6 +628,9 @@ def downconv_dgrad(gy, w, alpha):
         raise GlbError("downconv_dgrad: shape mismatch")
     _, wp = downconv_weights(w, "bwd")
     gx = _new_nhwc(N, Ci, 2 * H, 2 * W, gy)
+    if _state["conv_impl"] == "bf16":
+        _call("glb_downconv_dgrad_bf16", _p(bf16_operand(gy)), _p(_fold16(wp)), _p(gx), N, H, W, Ci, Co, float(alpha), _stream())
+        return gx
     _call("glb_downconv_dgrad", _p(gy), _p(wp), _p(gx), N, H, W, Ci, Co, float(alpha), _stream())
     return gx
 
@@ -620,6 +644,9 @@ def downconv_wgrad(x, gy, alpha):
         raise GlbError("downconv_wgrad: shape mismatch")
     gwp = torch.empty((Ci, 16, Co), device=x.device, dtype=torch.float32)
     gw = _new_nhwc(Co, Ci, 3, 3, x)
+    if _state["conv_impl"] == "bf16":
+        _call("glb_downconv_wgrad_bf16", _p(bf16_operand(x)), _p(bf16_operand(gy)), _p(gwp), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
+        return gw
     _call("glb_downconv_wgrad", _p(x), _p(gy), _p(gwp), _p(gw), N, H, W, Ci, Co, float(alpha), _stream())
     return gw
 

@@ -173,3 +173,58 @@ extern "C" int glb_downconv_wgrad(const float* x, const float* gy, float* gwp, f
   if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("downconv_wgrad");
   return glb::conv_downconv_wgrad_tc(x, gy, gwp, gw, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
 }
+
+// ---- bf16-operand variants of the folded convolutions (opt-in: set_conv_impl("bf16")) ------------------------------------------
+namespace glb {
+bool conv_upconv_covers(int kind, int N, int H, int W, int Ci, int Co, int chunk);
+bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co, int chunk);
+int conv_upconv_fprop_bf16(const void* x, const void* wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
+                           float bias_scale, int act, float slope, cudaStream_t st);
+int conv_upconv_dgrad_bf16(const void* gy, const void* wt, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st);
+int conv_upconv_wgrad_bf16(const void* x, const void* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                           cudaStream_t st);
+int conv_downconv_fprop_bf16(const void* x, const void* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
+                             float bias_scale, int act, float slope, cudaStream_t st);
+int conv_downconv_dgrad_bf16(const void* gy, const void* wp, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st);
+int conv_downconv_wgrad_bf16(const void* x, const void* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                             cudaStream_t st);
+}  // namespace glb
+
+extern "C" int glb_upconv_bf16_covers(int kind, int N, int H, int W, int Ci, int Co) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return 0;
+  return glb::conv_upconv_covers(kind, N, H, W, Ci, Co, 64) ? 1 : 0;
+}
+extern "C" int glb_downconv_bf16_covers(int kind, int N, int H, int W, int Ci, int Co) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return 0;
+  return glb::conv_downconv_covers(kind, N, H, W, Ci, Co, 64) ? 1 : 0;
+}
+extern "C" int glb_upconv_fprop_bf16(const void* x_bf16, const void* wp_bf16, const float* bias, float* y, int N, int H, int W, int Ci,
+                                     int Co, float alpha, float bias_scale, int act, float slope, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("upconv_fprop_bf16");
+  return glb::conv_upconv_fprop_bf16(x_bf16, wp_bf16, bias, y, N, H, W, Ci, Co, alpha, bias_scale, act, slope, (cudaStream_t)stream);
+}
+extern "C" int glb_upconv_dgrad_bf16(const void* gy_bf16, const void* wt_bf16, float* gx, int N, int H, int W, int Ci, int Co, float alpha,
+                                     glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("upconv_dgrad_bf16");
+  return glb::conv_upconv_dgrad_bf16(gy_bf16, wt_bf16, gx, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
+}
+extern "C" int glb_upconv_wgrad_bf16(const void* x_bf16, const void* gy_bf16, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
+                                     float alpha, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("upconv_wgrad_bf16");
+  return glb::conv_upconv_wgrad_bf16(x_bf16, gy_bf16, gwp, gw, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
+}
+extern "C" int glb_downconv_fprop_bf16(const void* x_bf16, const void* wt_bf16, const float* bias, float* y, int N, int H, int W, int Ci,
+                                       int Co, float alpha, float bias_scale, int act, float slope, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("downconv_fprop_bf16");
+  return glb::conv_downconv_fprop_bf16(x_bf16, wt_bf16, bias, y, N, H, W, Ci, Co, alpha, bias_scale, act, slope, (cudaStream_t)stream);
+}
+extern "C" int glb_downconv_dgrad_bf16(const void* gy_bf16, const void* wp_bf16, float* gx, int N, int H, int W, int Ci, int Co,
+                                       float alpha, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("downconv_dgrad_bf16");
+  return glb::conv_downconv_dgrad_bf16(gy_bf16, wp_bf16, gx, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
+}
+extern "C" int glb_downconv_wgrad_bf16(const void* x_bf16, const void* gy_bf16, float* gwp, float* gw, int N, int H, int W, int Ci,
+                                       int Co, float alpha, glb_stream_t stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ci <= 0 || Co <= 0) return glb::shape_fail("downconv_wgrad_bf16");
+  return glb::conv_downconv_wgrad_bf16(x_bf16, gy_bf16, gwp, gw, N, H, W, Ci, Co, alpha, (cudaStream_t)stream);
+}

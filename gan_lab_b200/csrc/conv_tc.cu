@@ -1629,20 +1629,25 @@ bool conv_dgrad_tc_covers(int N, int H, int W, int Ci, int Co, int R, int S, int
 // (rows 2i-1 | 2i, 2i+1 of the upsampled map are rows i-1 | i, i of x, and so on; the zero padding of the upsampled map is
 // exactly the out-of-bounds zero fill on x).  glb_upconv_weights writes wp and, for the data gradient, wt[ci][ph*4+a'*2+b'][co] =
 // wp[ph][co][1-a'][1-b'][ci].
-bool conv_upconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
+// chunk = channels per 128-byte operand row: 32 (fp32 operands, kind::tf32) or 64 (bf16 operands, kind::f16)
+bool conv_upconv_covers(int kind, int N, int H, int W, int Ci, int Co, int chunk) {
   if (N <= 0 || H <= 0 || W <= 0) return false;
   const bool n_ok_co = (Co == 32 || Co == 64 || Co % 128 == 0), n_ok_ci = (Ci == 32 || Ci == 64 || Ci % 128 == 0);
   switch (kind) {
-    case 0: return Ci % 32 == 0 && n_ok_co;               // fprop: K = Ci, GEMM N = Co
-    case 1: return Co % 32 == 0 && n_ok_ci;               // dgrad: K = Co, GEMM N = Ci
-    case 2: return Ci % 32 == 0 && Co % 32 == 0;          // wgrad
+    case 0: return Ci % chunk == 0 && n_ok_co;               // fprop: K = Ci, GEMM N = Co
+    case 1: return Co % chunk == 0 && n_ok_ci;               // dgrad: K = Co, GEMM N = Ci
+    case 2: return Ci % chunk == 0 && Co % chunk == 0 && (chunk == 32 || Ci % 64 == 0);          // wgrad
   }
   return false;
 }
+bool conv_upconv_covers(int kind, int N, int H, int W, int Ci, int Co) { return conv_upconv_covers(kind, N, H, W, Ci, Co, 32); }
 
 // shared by the forward (up = 1) and the data gradient (up = 2): `kc` = channels of the reduction, `nc` = channels of the output
-static int upconv_launch(int up, const float* in, const float* wmat, const float* bias, float* out, int N, int H, int W, int kc, int nc,
+template <bool BF>
+static int upconv_launch(int up, const void* in, const void* wmat, const float* bias, float* out, int N, int H, int W, int kc, int nc,
                          float alpha, float bias_scale, int act, float slope, cudaStream_t st) {
+  constexpr int kChunk = BF ? 64 : 32;              // channels per 128-byte operand row (shadows the fp32 constant)
+  constexpr uint64_t ES = BF ? 2 : 4;               // operand element size
   FpropParams p;
   p.y = out; p.bias = bias;
   p.N = N; p.Ho = H; p.Wo = W; p.Co = nc;
@@ -1665,7 +1670,7 @@ static int upconv_launch(int up, const float* in, const float* wmat, const float
   p.ksplit = (k_iters + p.k_per - 1) / p.k_per;
   p.tiles_co = nc / BN;
   p.num_tiles = m_tiles * p.tiles_co * p.ksplit;
-  p.alpha = alpha * kTf32TruncComp; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
+  p.alpha = BF ? alpha : alpha * kTf32TruncComp; p.bias_scale = bias_scale; p.act = act; p.slope = slope;
   p.dbg = 0; p.trace = nullptr;
   const int64_t out_rows = (int64_t)N * p.OH * p.OW;
   const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
@@ -1678,17 +1683,17 @@ static int upconv_launch(int up, const float* in, const float* wmat, const float
   const uint32_t boxA[4] = {(uint32_t)kChunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
   if (up == 1) {
     const uint64_t dims[4] = {(uint64_t)kc, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint64_t strides[3] = {(uint64_t)kc * 4, (uint64_t)W * kc * 4, (uint64_t)H * W * kc * 4};
-    int rc = make_tmap_f32(&tmA.m[0], in, 4, dims, strides, boxA, "upconv input", false);
+    const uint64_t strides[3] = {(uint64_t)kc * ES, (uint64_t)W * kc * ES, (uint64_t)H * W * kc * ES};
+    int rc = make_tmap(&tmA.m[0], in, 4, dims, strides, boxA, "upconv input", false, BF);
     if (rc) return rc;
     tmA.m[1] = tmA.m[2] = tmA.m[3] = tmA.m[0];
   } else {
     // phase (dy, dx) of the high-resolution gradient [N][2H][2W][kc] as a strided [N][H][W][kc] view
     const uint64_t dims[4] = {(uint64_t)kc, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint64_t strides[3] = {(uint64_t)2 * kc * 4, (uint64_t)2 * (2 * W) * kc * 4, (uint64_t)(2 * H) * (2 * W) * kc * 4};
+    const uint64_t strides[3] = {(uint64_t)2 * kc * ES, (uint64_t)2 * (2 * W) * kc * ES, (uint64_t)(2 * H) * (2 * W) * kc * ES};
     for (int ph = 0; ph < 4; ++ph) {
-      const float* base = in + ((int64_t)(ph >> 1) * (2 * W) + (ph & 1)) * kc;
-      int rc = make_tmap_f32(&tmA.m[ph], base, 4, dims, strides, boxA, "upconv gradient (phase view)", false);
+      const char* base = (const char*)in + ((int64_t)(ph >> 1) * (2 * W) + (ph & 1)) * kc * ES;
+      int rc = make_tmap(&tmA.m[ph], base, 4, dims, strides, boxA, "upconv gradient (phase view)", false, BF);
       if (rc) return rc;
     }
   }
@@ -1696,19 +1701,19 @@ static int upconv_launch(int up, const float* in, const float* wmat, const float
     const int taps = p.R * p.S;
     const uint64_t rows = up == 1 ? (uint64_t)4 * nc : (uint64_t)nc;
     const uint64_t dims[3] = {(uint64_t)kc, (uint64_t)taps, rows};
-    const uint64_t strides[2] = {(uint64_t)kc * 4, (uint64_t)taps * kc * 4};
+    const uint64_t strides[2] = {(uint64_t)kc * ES, (uint64_t)taps * kc * ES};
     const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)(use_pair ? BN / 2 : BN)};
-    int rc = make_tmap_f32(&tmB, wmat, 3, dims, strides, box, "upconv weight", false);
+    int rc = make_tmap(&tmB, wmat, 3, dims, strides, box, "upconv weight", false, BF);
     if (rc) return rc;
   }
-  if (use_pair) return launch_fprop2<256, false>(tmA, tmB, p, st);
+  if (use_pair) return launch_fprop2<256, BF>(tmA, tmB, p, st);
   int rc = GLB_ERR_UNSUPPORTED;
   const bool kc2 = BN <= 128 && (kc / kChunk) % 2 == 0 && p.k_per % 2 == 0;
   switch (BN) {
-    case 256: rc = launch_fprop<256, 1, false>(tmA, tmB, p, st); break;
-    case 128: rc = kc2 ? launch_fprop<128, 2, false>(tmA, tmB, p, st) : launch_fprop<128, 1, false>(tmA, tmB, p, st); break;
-    case 64: rc = kc2 ? launch_fprop<64, 2, false>(tmA, tmB, p, st) : launch_fprop<64, 1, false>(tmA, tmB, p, st); break;
-    case 32: rc = kc2 ? launch_fprop<32, 2, false>(tmA, tmB, p, st) : launch_fprop<32, 1, false>(tmA, tmB, p, st); break;
+    case 256: rc = launch_fprop<256, 1, BF>(tmA, tmB, p, st); break;
+    case 128: rc = kc2 ? launch_fprop<128, 2, BF>(tmA, tmB, p, st) : launch_fprop<128, 1, BF>(tmA, tmB, p, st); break;
+    case 64: rc = kc2 ? launch_fprop<64, 2, BF>(tmA, tmB, p, st) : launch_fprop<64, 1, BF>(tmA, tmB, p, st); break;
+    case 32: rc = kc2 ? launch_fprop<32, 2, BF>(tmA, tmB, p, st) : launch_fprop<32, 1, BF>(tmA, tmB, p, st); break;
     default: set_error("upconv: no kernel for this N tile");
   }
   if (rc == GLB_OK && post_pass) rc = glb_bias_act_fwd(out, bias, out, out_rows, nc, bias_scale, act, slope, (glb_stream_t)st);
@@ -1721,7 +1726,15 @@ int conv_upconv_fprop_tc(const float* x, const float* wp, const float* bias, flo
     set_error("upconv fprop: shape not covered (Ci % 32 == 0, Co in {32, 64} or a multiple of 128)");
     return GLB_ERR_UNSUPPORTED;
   }
-  return upconv_launch(1, x, wp, bias, y, N, H, W, Ci, Co, alpha, bias_scale, act, slope, st);
+  return upconv_launch<false>(1, x, wp, bias, y, N, H, W, Ci, Co, alpha, bias_scale, act, slope, st);
+}
+int conv_upconv_fprop_bf16(const void* x, const void* wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
+                           float bias_scale, int act, float slope, cudaStream_t st) {
+  if (!conv_upconv_covers(0, N, H, W, Ci, Co, 64)) {
+    set_error("upconv fprop (bf16): shape not covered (Ci % 64 == 0, Co in {32, 64} or a multiple of 128)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch<true>(1, x, wp, bias, y, N, H, W, Ci, Co, alpha, bias_scale, act, slope, st);
 }
 
 // gx[n,i,j,ci] = alpha * sum_{ph,a',b',co} gy[n, 2(i + a' - dy) + dy, 2(j + b' - dx) + dx, co] * wt[ci][ph*4 + a'*2 + b'][co]
@@ -1730,7 +1743,14 @@ int conv_upconv_dgrad_tc(const float* gy, const float* wt, float* gx, int N, int
     set_error("upconv dgrad: shape not covered (Co % 32 == 0, Ci in {32, 64} or a multiple of 128)");
     return GLB_ERR_UNSUPPORTED;
   }
-  return upconv_launch(2, gy, wt, nullptr, gx, N, H, W, Co, Ci, alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+  return upconv_launch<false>(2, gy, wt, nullptr, gx, N, H, W, Co, Ci, alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+}
+int conv_upconv_dgrad_bf16(const void* gy, const void* wt, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st) {
+  if (!conv_upconv_covers(1, N, H, W, Ci, Co, 64)) {
+    set_error("upconv dgrad (bf16): shape not covered (Co % 64 == 0, Ci in {32, 64} or a multiple of 128)");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch<true>(2, gy, wt, nullptr, gx, N, H, W, Co, Ci, alpha, 0.f, GLB_ACT_NONE, 0.f, st);
 }
 
 namespace {
@@ -2335,9 +2355,12 @@ int conv_upconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, cu
 }
 
 // gw [Co][3][3][Ci] of conv3x3(upsample2x(x)); gwp = [Co][16][Ci] scratch (phase/tap gradients, folded at the end)
-static int upconv_wgrad_impl(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+template <bool BF>
+static int upconv_wgrad_impl(const void* x, const void* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
                              bool transposed_out, cudaStream_t st) {
-  if (!conv_upconv_covers(2, N, H, W, Ci, Co)) {
+  constexpr int CH = BF ? 64 : 32;
+  constexpr uint64_t ES = BF ? 2 : 4;
+  if (!conv_upconv_covers(2, N, H, W, Ci, Co, CH)) {
     set_error("upconv wgrad: shape not covered (Ci and Co multiples of 32)");
     return GLB_ERR_UNSUPPORTED;
   }
@@ -2345,7 +2368,7 @@ static int upconv_wgrad_impl(const float* x, const float* gy, float* gwp, float*
   p.gw = gwp; p.Co = Co; p.Ci = Ci; p.RS = 16; p.S = 4; p.pad = 1; p.up = 1;
   p.N = N; p.Ho = H; p.Wo = W;
   const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
-  const int PIX = BN >= 256 ? 32 : 64;
+  const int PIX = (BN >= 256 ? 32 : 64) * (BF ? 2 : 1);
   p.bw = next_pow2(W) < PIX ? next_pow2(W) : PIX;
   p.bh = next_pow2(H) < PIX / p.bw ? next_pow2(H) : PIX / p.bw;
   p.bn = PIX / (p.bw * p.bh);
@@ -2362,35 +2385,43 @@ static int upconv_wgrad_impl(const float* x, const float* gy, float* gwp, float*
   if (splits < 1) splits = 1;
   p.pb_per_split = (p.num_pb + splits - 1) / splits;
   p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;
-  p.alpha = alpha * kTf32TruncComp;
+  p.alpha = BF ? alpha : alpha * kTf32TruncComp;
   p.atomic = p.splits > 1 ? 1 : 0;
   if (p.atomic) GLB_CUDA(cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Co * 16 * Ci, st));
   TMapSet tmGy;
   CUtensorMap tmX;
   {
-    const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Co / 32)};
-    const uint64_t strides[4] = {(uint64_t)2 * Co * 4, (uint64_t)2 * (2 * W) * Co * 4, (uint64_t)(2 * H) * (2 * W) * Co * 4, 128u};
-    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 4u};
+    const uint64_t dims[5] = {(uint64_t)CH, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Co / CH)};
+    const uint64_t strides[4] = {(uint64_t)2 * Co * ES, (uint64_t)2 * (2 * W) * Co * ES, (uint64_t)(2 * H) * (2 * W) * Co * ES, 128u};
+    const uint32_t box[5] = {(uint32_t)CH, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(128 / CH)};
     for (int ph = 0; ph < 4; ++ph) {
-      const float* base = gy + ((int64_t)(ph >> 1) * (2 * W) + (ph & 1)) * Co;
-      int rc = make_tmap_f32(&tmGy.m[ph], base, 5, dims, strides, box, "upconv wgrad gy (phase view)", true);
+      const char* base = (const char*)gy + ((int64_t)(ph >> 1) * (2 * W) + (ph & 1)) * Co * ES;
+      int rc = make_tmap(&tmGy.m[ph], base, 5, dims, strides, box, "upconv wgrad gy (phase view)", !BF, BF);
       if (rc) return rc;
     }
   }
   {
-    const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / 32)};
-    const uint64_t strides[4] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4, 128u};
-    const uint32_t box[5] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BN / 32)};
-    int rc = make_tmap_f32(&tmX, x, 5, dims, strides, box, "upconv wgrad x", true);
+    const uint64_t dims[5] = {(uint64_t)CH, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / CH)};
+    const uint64_t strides[4] = {(uint64_t)Ci * ES, (uint64_t)W * Ci * ES, (uint64_t)H * W * Ci * ES, 128u};
+    const uint32_t box[5] = {(uint32_t)CH, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BN / CH)};
+    int rc = make_tmap(&tmX, x, 5, dims, strides, box, "upconv wgrad x", !BF, BF);
     if (rc) return rc;
   }
   const int grid = tiles * p.splits;
   int rc = GLB_ERR_UNSUPPORTED;
-  switch (BN) {
-    case 256: rc = launch_wgrad<256, 32>(tmGy, tmX, p, grid, st); break;
-    case 128: rc = launch_wgrad<128, 64>(tmGy, tmX, p, grid, st); break;
-    case 64: rc = launch_wgrad<64, 64>(tmGy, tmX, p, grid, st); break;
-    case 32: rc = launch_wgrad<32, 64>(tmGy, tmX, p, grid, st); break;
+  if (BF) {
+    switch (BN) {
+      case 256: rc = launch_wgrad<256, 64, true>(tmGy, tmX, p, grid, st); break;
+      case 128: rc = launch_wgrad<128, 128, true>(tmGy, tmX, p, grid, st); break;
+      case 64: rc = launch_wgrad<64, 128, true>(tmGy, tmX, p, grid, st); break;
+    }
+  } else {
+    switch (BN) {
+      case 256: rc = launch_wgrad<256, 32>(tmGy, tmX, p, grid, st); break;
+      case 128: rc = launch_wgrad<128, 64>(tmGy, tmX, p, grid, st); break;
+      case 64: rc = launch_wgrad<64, 64>(tmGy, tmX, p, grid, st); break;
+      case 32: rc = launch_wgrad<32, 64>(tmGy, tmX, p, grid, st); break;
+    }
   }
   if (rc != GLB_OK) return rc;
   if (transposed_out) {     // downconv: this problem's (Co, Ci) are the layer's (Ci, Co); gw is the layer's [Co_layer][3][3][Ci_layer]
@@ -2408,7 +2439,11 @@ static int upconv_wgrad_impl(const float* x, const float* gy, float* gwp, float*
 
 int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
                          cudaStream_t st) {
-  return upconv_wgrad_impl(x, gy, gwp, gw, N, H, W, Ci, Co, alpha, false, st);
+  return upconv_wgrad_impl<false>(x, gy, gwp, gw, N, H, W, Ci, Co, alpha, false, st);
+}
+int conv_upconv_wgrad_bf16(const void* x, const void* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                           cudaStream_t st) {
+  return upconv_wgrad_impl<true>(x, gy, gwp, gw, N, H, W, Ci, Co, alpha, false, st);
 }
 
 // ------------------------------------------------------------------------------------------------ 2x2 average pool folded into the conv
@@ -2421,14 +2456,15 @@ int conv_upconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* gw,
 //   wgrad  gw = 0.25 * transpose_flip(upconv_wgrad(x_lo := gy, gy_hi := x))
 // so the same three kernels serve it; H, W below are the LOW-resolution (output) dims, x / gx are [N,2H,2W,Ci].
 // glb_downconv_weights: wp [4*Ci][2][2][Co] (dgrad) and wt [Co][16][Ci] (fprop) = glb_upconv_weights of w' (fold_weights_kernel<true>).
-bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co) {
+bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co, int chunk) {
   switch (kind) {
-    case 0: return conv_upconv_covers(1, N, H, W, Co, Ci);
-    case 1: return conv_upconv_covers(0, N, H, W, Co, Ci);
-    case 2: return conv_upconv_covers(2, N, H, W, Co, Ci);
+    case 0: return conv_upconv_covers(1, N, H, W, Co, Ci, chunk);
+    case 1: return conv_upconv_covers(0, N, H, W, Co, Ci, chunk);
+    case 2: return conv_upconv_covers(2, N, H, W, Co, Ci, chunk);
   }
   return false;
 }
+bool conv_downconv_covers(int kind, int N, int H, int W, int Ci, int Co) { return conv_downconv_covers(kind, N, H, W, Ci, Co, 32); }
 
 int conv_downconv_weights(const float* w, float* wp, float* wt, int Co, int Ci, cudaStream_t st) {
   if (wp == nullptr && wt == nullptr) return GLB_OK;
@@ -2444,7 +2480,15 @@ int conv_downconv_fprop_tc(const float* x, const float* wt, const float* bias, f
     set_error("downconv fprop: shape not covered (Ci % 32 == 0, Co in {32, 64} or a multiple of 128)");
     return GLB_ERR_UNSUPPORTED;
   }
-  return upconv_launch(2, x, wt, bias, y, N, H, W, Ci, Co, 0.25f * alpha, bias_scale, act, slope, st);
+  return upconv_launch<false>(2, x, wt, bias, y, N, H, W, Ci, Co, 0.25f * alpha, bias_scale, act, slope, st);
+}
+int conv_downconv_fprop_bf16(const void* x, const void* wt, const float* bias, float* y, int N, int H, int W, int Ci, int Co, float alpha,
+                             float bias_scale, int act, float slope, cudaStream_t st) {
+  if (!conv_downconv_covers(0, N, H, W, Ci, Co, 64)) {
+    set_error("downconv fprop (bf16): shape not covered");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch<true>(2, x, wt, bias, y, N, H, W, Ci, Co, 0.25f * alpha, bias_scale, act, slope, st);
 }
 
 int conv_downconv_dgrad_tc(const float* gy, const float* wp, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st) {
@@ -2452,7 +2496,14 @@ int conv_downconv_dgrad_tc(const float* gy, const float* wp, float* gx, int N, i
     set_error("downconv dgrad: shape not covered (Co % 32 == 0, Ci in {32, 64} or a multiple of 128)");
     return GLB_ERR_UNSUPPORTED;
   }
-  return upconv_launch(1, gy, wp, nullptr, gx, N, H, W, Co, Ci, 0.25f * alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+  return upconv_launch<false>(1, gy, wp, nullptr, gx, N, H, W, Co, Ci, 0.25f * alpha, 0.f, GLB_ACT_NONE, 0.f, st);
+}
+int conv_downconv_dgrad_bf16(const void* gy, const void* wp, float* gx, int N, int H, int W, int Ci, int Co, float alpha, cudaStream_t st) {
+  if (!conv_downconv_covers(1, N, H, W, Ci, Co, 64)) {
+    set_error("downconv dgrad (bf16): shape not covered");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_launch<true>(1, gy, wp, nullptr, gx, N, H, W, Co, Ci, 0.25f * alpha, 0.f, GLB_ACT_NONE, 0.f, st);
 }
 
 // gwp [Ci][16][Co] is scratch
@@ -2462,7 +2513,15 @@ int conv_downconv_wgrad_tc(const float* x, const float* gy, float* gwp, float* g
     set_error("downconv wgrad: shape not covered (Ci and Co multiples of 32)");
     return GLB_ERR_UNSUPPORTED;
   }
-  return upconv_wgrad_impl(gy, x, gwp, gw, N, H, W, /*Ci' =*/Co, /*Co' =*/Ci, 0.25f * alpha, true, st);
+  return upconv_wgrad_impl<false>(gy, x, gwp, gw, N, H, W, /*Ci' =*/Co, /*Co' =*/Ci, 0.25f * alpha, true, st);
+}
+int conv_downconv_wgrad_bf16(const void* x, const void* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co, float alpha,
+                             cudaStream_t st) {
+  if (!conv_downconv_covers(2, N, H, W, Ci, Co, 64)) {
+    set_error("downconv wgrad (bf16): shape not covered");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  return upconv_wgrad_impl<true>(gy, x, gwp, gw, N, H, W, /*Ci' =*/Co, /*Co' =*/Ci, 0.25f * alpha, true, st);
 }
 
 }  // namespace glb

@@ -32,6 +32,11 @@ def run_fused(seq, x):
         elif isinstance(m, Upsample2x) and isinstance(nxt, Conv2dEx) and nxt.ks == 1 and nxt.padding == 0:
             x = m(nxt(x))                               # a 1x1 convolution commutes with nearest upsampling: same values, 1/4 of the work
             i += 2
+        elif isinstance(m, Conv2dEx) and m.ks == 3 and m.padding == 1 and isinstance(nxt, AvgPool2x) and x.dim() == 4:
+            # conv -> 2x2 average pool as one stride-2 4x4 convolution (ops.downconv2d falls back to the two kernels by itself);
+            # the bias commutes with the average
+            x = ops.downconv2d(x, m.conv2d.weight, m.conv2d.bias, m.alpha, m.lrmul if m.use_lrmul else 1., ops.ACT_NONE, 0.2)
+            i += 2
         elif fuse:
             x = m(x, act=ops.ACT_LRELU, slope=nxt.negative_slope)
             i += 2

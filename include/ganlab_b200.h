@@ -125,6 +125,24 @@ int glb_downconv_dgrad(const float* gy, const float* wp, float* gx, int N, int H
 int glb_downconv_wgrad(const float* x, const float* gy, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
                        float alpha, glb_stream_t stream);
 
+/* bf16-operand variants of glb_upconv_* / glb_downconv_* (opt-in: set_conv_impl("bf16")): activations / gradients and the
+ * re-laid-out weights (wp / wt of glb_upconv_weights / glb_downconv_weights) given as bf16 copies (glb_cvt_f32_bf16), fp32
+ * accumulation, bias, activation and outputs; channel counts multiples of 64. */
+int glb_upconv_bf16_covers(int kind, int N, int H, int W, int Ci, int Co);
+int glb_upconv_fprop_bf16(const void* x_bf16, const void* wp_bf16, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
+                          float alpha, float bias_scale, int act, float slope, glb_stream_t stream);
+int glb_upconv_dgrad_bf16(const void* gy_bf16, const void* wt_bf16, float* gx, int N, int H, int W, int Ci, int Co,
+                          float alpha, glb_stream_t stream);
+int glb_upconv_wgrad_bf16(const void* x_bf16, const void* gy_bf16, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
+                          float alpha, glb_stream_t stream);
+int glb_downconv_bf16_covers(int kind, int N, int H, int W, int Ci, int Co);
+int glb_downconv_fprop_bf16(const void* x_bf16, const void* wt_bf16, const float* bias, float* y, int N, int H, int W, int Ci, int Co,
+                            float alpha, float bias_scale, int act, float slope, glb_stream_t stream);
+int glb_downconv_dgrad_bf16(const void* gy_bf16, const void* wp_bf16, float* gx, int N, int H, int W, int Ci, int Co,
+                            float alpha, glb_stream_t stream);
+int glb_downconv_wgrad_bf16(const void* x_bf16, const void* gy_bf16, float* gwp, float* gw, int N, int H, int W, int Ci, int Co,
+                            float alpha, glb_stream_t stream);
+
 /* ---- RGB 1x1 convolutions (3 <-> C channels; pure bandwidth) ---------------------------------- *
  * fromRGB (progan/architectures.py:286-292) and toRGB (stylegan/architectures.py:338-341).
  * In all three the weight element (j = rgb channel, c = feature channel) lives at w[j*ws_j + c*ws_c], so the

@@ -167,6 +167,36 @@ def test_downconv_family_vs_contract(shape):
         K.set_conv_impl("fp32")
 
 
+FOLD_BF16_SHAPES = [  # N, H, W (low resolution), Ci, Co -- channel counts multiples of 64
+    (8, 4, 4, 512, 512), (2, 16, 16, 512, 512), (8, 16, 16, 512, 512), (2, 32, 32, 512, 256), (2, 64, 64, 256, 128), (2, 16, 16, 64, 64),
+]
+
+
+@pytest.mark.parametrize("shape", FOLD_BF16_SHAPES)
+def test_folded_conv_families_bf16_vs_contract(shape):
+    """bf16-operand variants of glb_upconv_* and glb_downconv_* (the layer's channel roles swapped for the latter)."""
+    N, H, W, Ci, Co = shape
+    x, w, b = cl(rn(N, Ci, H, W)), cl(rn(Co, Ci, 3, 3, seed=1)), rn(Co, seed=2)
+    gy = cl(rn(N, Co, 2 * H, 2 * W, seed=3))
+    xd, wd, bd = cl(rn(N, Co, 2 * H, 2 * W, seed=4)), cl(rn(Ci, Co, 3, 3, seed=5)), rn(Ci, seed=6)
+    gyd = cl(rn(N, Ci, H, W, seed=7))
+    K.set_conv_impl("bf16")
+    try:
+        for kind in ("fprop", "dgrad", "wgrad"):
+            assert K.upconv_covers(kind, N, H, W, Ci, Co), kind
+        assert K.downconv_covers(N, H, W, Co, Ci)
+        n0 = K.launch_count()
+        both("upconv_fprop", x, w, b, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_BF16)
+        both("upconv_dgrad", gy, w, 0.37, tol=TOL_BF16)
+        both("upconv_wgrad", x, gy, 0.37, tol=TOL_BF16)
+        both("downconv_fprop", xd, wd, bd, 0.37, 0.5, K.ACT_LRELU, 0.2, tol=TOL_BF16)
+        both("downconv_dgrad", gyd, wd, 0.37, tol=TOL_BF16)
+        both("downconv_wgrad", xd, gyd, 0.37, tol=TOL_BF16)
+        assert K.launch_count() > n0
+    finally:
+        K.set_conv_impl("fp32")
+
+
 def test_downconv_op_matches_two_kernel_sequence_incl_double_backward():
     """ops.downconv2d (fused) against conv2d -> pool_bias_act on the same TF32 path: output with the fused bias + LeakyReLU, and
     -- without the activation, whose mask would flip on outputs near zero between two differently rounded TF32 paths --

@@ -190,3 +190,36 @@ def test_resnet_compute_metrics_vs_reference(golden):
     L.compute_metrics(g["disc_metrics"], "Discriminator", z_dl, x_dl)
     for name, want in zip(g["disc_metrics"], g["raw_d"]):
         assert abs(L.last_metrics[name] - want) < 2e-4 * max(1.0, abs(want)), (name, L.last_metrics[name], want)
+
+
+def test_resnet_nets_with_folded_resampling_match_the_two_kernel_sequence(monkeypatch):
+    """TF32 path of the full-width ResNet nets (64 x 64, channels 512 ... 64): the upsample folded into the generator's 3x3
+    convolutions (glb_upconv_*), the average pool folded into the discriminator's (glb_downconv_*) and the 1x1 skip convolution
+    run before its upsample, against the literal two-kernel sequences (GLB_UPCONV=0 / GLB_DOWNCONV=0) on the same weights and
+    inputs; eval-mode nets (running statistics), so no batch statistic amplifies the TF32 rounding difference of the two orders."""
+    from gan_lab_b200.config import default_config
+    from gan_lab_b200.resnetgan.learner import GANLearner
+    torch.manual_seed(0)
+    cfg = default_config("ResNet GAN", res=64, batch_size=4, dev=DEV, len_latent=128)
+    L = GANLearner(cfg)
+    G, D = L.gen_model.to(DEV), L.disc_model.to(DEV)
+    G.eval(); D.eval()
+    z = torch.randn(4, 128, device=DEV)
+    x = torch.rand(4, 3, 64, 64, device=DEV) * 2 - 1
+    K.set_conv_impl("tf32")
+    try:
+        outs = []
+        for fold in ("1", "0"):
+            monkeypatch.setenv("GLB_UPCONV", fold); monkeypatch.setenv("GLB_DOWNCONV", fold)
+            K.weights_updated()
+            n0 = K.launch_count()
+            with torch.no_grad():
+                img = G(z)
+                d = D(x)
+            outs.append((img.float().clone(), d.float().clone(), K.launch_count() - n0))
+        (ia, da, na), (ib, db, nb) = outs
+        assert not torch.equal(ia, ib) and not torch.equal(da, db)  # the folded kernels really ran (same values to TF32 rounding, not bitwise)
+        assert float((ia - ib).abs().max()) < 5e-3 * float(ib.abs().max())
+        assert float((da - db).abs().max()) < 5e-3 * max(1.0, float(db.abs().max()))
+    finally:
+        K.set_conv_impl("fp32")
