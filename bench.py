@@ -514,7 +514,7 @@ def run_ours(args):
             "details": {"conv_impl": args.conv_impl, "cuda_graphs": use_graphs,
                        "r1_shares_real_forward": bool(getattr(L, "share_penalty_forward", False)),
                        "d_fake_real_one_pass": bool(getattr(L, "batch_d_passes", False)),
-                       "grad_allreduce": (f"NCCL all-reduce ({'in place, grouped, ncclAvg' if L.dp.inplace else 'packed buckets'}), "
+                       "grad_allreduce": (f"NCCL all-reduce ({('in place, grouped, ncclAvg; gradients below ' + str(L.dp.pack_below * 4 >> 10) + ' KiB packed into one message of the group') if L.dp.inplace else 'packed buckets'}), "
                                           f"{L.dp.bucket_bytes >> 20} MiB buckets launched from grad hooks as they fill"
                                           + ("; D's all-reduce + Adam overlapped with the generator forward of the G step" if getattr(L, "overlap_d_update", False) else "")
                                           if world > 1 else None), "l2": "8-batch input pool; activations per step (>1 GB) exceed the 126 MB L2",

@@ -13,7 +13,8 @@ Overlap with backward: every parameter carries a post-accumulate-grad hook; as s
 ready fill a bucket (in autograd order: last layers first) the bucket is all-reduced asynchronously -- NCCL runs on the process
 group's own stream while the compute stream keeps executing the rest of backward (including the R1 double-backward tail).  With
 NCCL the gradients of a bucket are reduced IN PLACE as one grouped call (ncclGroupStart / ncclAllReduce(ncclAvg) per tensor /
-ncclGroupEnd): no pack, pre-scale or scatter-back pass; other backends (the gloo CPU tests) pack the bucket with `torch.cat`,
+ncclGroupEnd): no pack, pre-scale or scatter-back pass for the large tensors; gradients below 1 MiB travel as ONE packed message
+inside the same group (per-collective latency, not bytes, is what they cost); other backends (the gloo CPU tests) pack the bucket with `torch.cat`,
 pre-scale by 1/world and copy back.  `allreduce_grads()` after backward only flushes the last partial bucket and makes the compute
 stream wait for the collectives.  All of this is stream-ordered, so it is captured into the step's CUDA graph as parallel branches.
 Default bucket size: 32 MiB on 2 GPUs, 128 MiB (= ONE group per network, issued when its backward has finished) on more: measured
@@ -47,6 +48,8 @@ class DataParallel(object):
         if inplace is None:
             inplace = dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
         self.inplace = bool(inplace)
+        import os
+        self.pack_below = int(os.environ.get("GLB_DP_PACK_BELOW", 262144))     # elements; 0 = every gradient in place
         self.enabled = True         # False: the hooks stay silent (rank-local passes such as bench.py's roofline replay)
         self._hooked = set()        # ids of parameters that carry our hook
         self._pending = []          # parameters whose gradient is ready but not yet in a bucket
@@ -86,11 +89,20 @@ class DataParallel(object):
         if not ps:
             return
         if self.inplace:
-            grads = [_flat_view(p.grad) for p in ps]
-            with dist._coalescing_manager(device=grads[0].device, async_ops=True) as cm:
-                for g in grads:
-                    dist.all_reduce(g, op=dist.ReduceOp.AVG)
-            self._inflight.append((cm, None, ps))
+            # large gradients are reduced where they are; the many SMALL ones (biases, noise weights, narrow layers: ~half of the
+            # tensors, ~1 % of the bytes) are packed into one message first -- every collective of a group costs its own
+            # latency, which grows with the rank count (measured on 8 B200s: +1.7 ms per cfg2 iteration with ~160 ops per step)
+            big = [p for p in ps if p.numel() >= self.pack_below]
+            small = [p for p in ps if p.numel() < self.pack_below]
+            flat = torch.cat([_flat_view(p.grad) for p in small]) if len(small) > 1 else None
+            if flat is None:
+                big, small = ps, []
+            with dist._coalescing_manager(device=ps[0].grad.device, async_ops=True) as cm:
+                if flat is not None:
+                    dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+                for p in big:
+                    dist.all_reduce(_flat_view(p.grad), op=dist.ReduceOp.AVG)
+            self._inflight.append((cm, flat, small))
             return
         flat = torch.cat([_flat_view(p.grad) for p in ps])
         flat.mul_(1.0 / self.world)
