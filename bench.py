@@ -728,7 +728,7 @@ def input_pipeline_roofline(peaks):
         ms = sorted(ts)[len(ts) // 2]
         gbs = (n * hs * hs * 3 + out.numel() * 4) / ms / 1e6
         del src, out
-        return {"bound": "hbm", "kernel": "box_resize_normalize_kernel (Pillow BOX resize + ToTensor + Normalize, uint8 1024x1024 -> "
+        return {"bound": "hbm", "kernel": "box_resize_normalize_grouped_kernel (Pillow BOX resize + ToTensor + Normalize, uint8 1024x1024 -> "
                 "fp32 128x128, 96 images per launch)", "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"],
                 "frac": gbs / peaks["hbm_gbs"], "traffic": None, "images_per_s": n / ms * 1e3, "launch_us": ms * 1e3}
     except Exception as e:       # noqa: BLE001 -- an auxiliary figure

@@ -225,7 +225,8 @@ def _cache_put(cache, key, version, tensor, w):
     """Cache entries remember the stream that produced them and an event recorded behind the producing kernels: a hit from
     ANOTHER stream (the learners run independent discriminator passes on two streams) waits for that event first."""
     ev = None
-    on_gpu = (tensor[0] if isinstance(tensor, tuple) else tensor).is_cuda
+    first = next(t for t in tensor if t is not None) if isinstance(tensor, tuple) else tensor
+    on_gpu = first.is_cuda
     if on_gpu:
         ev = torch.cuda.Event()
         ev.record()
@@ -500,15 +501,15 @@ def _fold16(t):
     return _to_bf16(t, "fold")
 
 
-def _folded_weights(w, down, want):
+def _folded_weights(w, down, want, both=False):
     """The two operand re-layouts of a folded convolution, cached per weight version: (forward operand, data-gradient operand).
-    One launch writes both when a backward pass can follow (grad mode on), only the forward one under no_grad; a missing one is
-    added on demand."""
+    One launch writes both when the caller knows the other one will be needed (`both`: the forward of a layer whose input
+    requires grad), else only the one asked for; a missing one is added on demand."""
     key = (w.data_ptr(), tuple(w.shape), "down" if down else "up")
     hit = _cache_get(_up_cache, key, w._version)
     fwd, bwd = hit if hit is not None else (None, None)
-    need_f = fwd is None and (want == "fwd" or torch.is_grad_enabled())
-    need_b = bwd is None and (want == "bwd" or torch.is_grad_enabled())
+    need_f = fwd is None and (want == "fwd" or both)
+    need_b = bwd is None and (want == "bwd" or both)
     if (want == "fwd" and fwd is not None) or (want == "bwd" and bwd is not None):
         return fwd, bwd
     Co, Ci, R, S = w.shape
@@ -530,19 +531,20 @@ def _folded_weights(w, down, want):
     return fwd, bwd
 
 
-def upconv_weights(w, want="fwd"):
+def upconv_weights(w, want="fwd", both=False):
     """(wp [4*Co,2,2,Ci] for the forward, wt [Ci,16,Co] for the data gradient) of w [Co,Ci,3,3]."""
-    return _folded_weights(w, False, want)
+    return _folded_weights(w, False, want, both)
 
 
-def upconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
+def upconv_fprop(x, w, bias, alpha, bias_scale, act, slope, need_dgrad=False):
+    """need_dgrad: the data-gradient operand will be needed as well (written by the same re-layout launch)"""
     _chk(x, w, bias)
     x, w = nhwc(x), nhwc(w)
     N, Ci, H, W = x.shape
     Co, Ci2, R, S = w.shape
     if Ci != Ci2 or R != 3 or S != 3:
         raise GlbError("upconv_fprop: needs a 3x3 weight with matching channels")
-    wp, _ = upconv_weights(w, "fwd")
+    wp, _ = upconv_weights(w, "fwd", need_dgrad)
     y = _new_nhwc(N, Co, 2 * H, 2 * W, x)
     if _state["conv_impl"] == "bf16":
         _call("glb_upconv_fprop_bf16", _p(bf16_operand(x)), _p(_fold16(wp)), _p(_flat(bias)), _p(y), N, H, W, Ci, Co, float(alpha),
@@ -595,12 +597,12 @@ def downconv_covers(N, H, W, Ci, Co) -> bool:
     return all(bool(f(k, N, H, W, Ci, Co)) for k in (0, 1, 2))
 
 
-def downconv_weights(w, want="fwd"):
+def downconv_weights(w, want="fwd", both=False):
     """(wt [Co,16,Ci] for the forward, wp [4*Ci,2,2,Co] for the data gradient) of w [Co,Ci,3,3]."""
-    return _folded_weights(w, True, want)
+    return _folded_weights(w, True, want, both)
 
 
-def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
+def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope, need_dgrad=False):
     """act(alpha * avgpool2x2(conv3x3_same(x, w)) + bias_scale * bias) -> [N, Co, H/2, W/2]"""
     _chk(x, w, bias)
     x, w = nhwc(x), nhwc(w)
@@ -608,7 +610,7 @@ def downconv_fprop(x, w, bias, alpha, bias_scale, act, slope):
     Co, Ci2, R, S = w.shape
     if Ci != Ci2 or R != 3 or S != 3 or H2 % 2 or W2 % 2:
         raise GlbError("downconv_fprop: needs a 3x3 weight with matching channels and an even map")
-    wt, _ = downconv_weights(w, "fwd")
+    wt, _ = downconv_weights(w, "fwd", need_dgrad)
     y = _new_nhwc(N, Co, H2 // 2, W2 // 2, x)
     if _state["conv_impl"] == "bf16":
         _call("glb_downconv_fprop_bf16", _p(bf16_operand(x)), _p(_fold16(wt)), _p(_flat(bias)), _p(y), N, H2 // 2, W2 // 2, Ci, Co,

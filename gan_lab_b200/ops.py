@@ -381,7 +381,7 @@ class _UpConvFprop(Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, alpha, bias_scale, act, slope):
-        y = K.upconv_fprop(x, w, bias, alpha, bias_scale, act, slope)
+        y = K.upconv_fprop(x, w, bias, alpha, bias_scale, act, slope, need_dgrad=ctx.needs_input_grad[0])
         ctx.cfg = (alpha, bias_scale, act, slope, bias is not None, x.shape, w.shape)
         ctx.bshape = None if bias is None else bias.shape
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
@@ -431,7 +431,7 @@ class _DownConvFprop(Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, alpha, bias_scale, act, slope):
-        y = K.downconv_fprop(x, w, bias, alpha, bias_scale, act, slope)
+        y = K.downconv_fprop(x, w, bias, alpha, bias_scale, act, slope, need_dgrad=ctx.needs_input_grad[0])
         ctx.cfg = (alpha, bias_scale, act, slope, bias is not None)
         ctx.bshape = None if bias is None else bias.shape
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)

@@ -43,7 +43,7 @@ def main():
         ]
         def prep(down):
             K._up_cache.clear()
-            K._folded_weights(w, down, "fwd")         # grad mode on: both operands in one launch
+            K._folded_weights(w, down, "fwd", both=True)   # both operands in one launch
         print(f"    operand re-layout (both operands, one launch): upconv {timed(lambda: prep(False)):6.1f} us   downconv {timed(lambda: prep(True)):6.1f} us"
               f"   ({(9 + 32) * Ci * Co * 4 / 1e6:.1f} MB)")
         for kind, fused, two in rows:
