@@ -15,7 +15,7 @@ from torch import nn
 from .. import ops
 from .. import _kernels as K
 from .._growth import GrowthState
-from ..utils.latent_utils import gen_rand_latent_vars, RANDOM
+from ..utils.latent_utils import gen_rand_latent_vars, RANDOM, RandomSource
 from ..utils.custom_layers import (Lambda, get_blur_op, NormalizeLayer, Conv2dEx, LinearEx, Conv2dBias, Blur3x3,
                                    Upsample2x, LeakyReLU, InstanceNorm2d, PixelNorm2d, as_native_nl,
                                    as_native_upsampler)
@@ -278,7 +278,12 @@ class StyleGenerator(StyleGAN):
         if fusable:
             nz = nw = None
             if self.use_noise:
-                nz = noise if (noise is not None and not self.training) else layer[1].draw(out)
+                if noise is not None and not self.training:
+                    nz = noise
+                elif getattr(self, '_noise_pool', None) is not None:
+                    nz = self._take_noise(out)
+                else:
+                    nz = layer[1].draw(out)
                 nw = layer[1].noise_weight
             return ops.style_epilogue(out, nz, nw, bias.bias, style, self.nl.negative_slope, 1.e-8)
         if self.use_noise:
@@ -286,6 +291,26 @@ class StyleGenerator(StyleGAN):
         out = tail(out)
         y = style.view(-1, 2, layer[3].nout_feat // 2, 1, 1)
         return out * (y[:, 0].contiguous().add(1)) + y[:, 1].contiguous()
+
+    # ------------------------------------------------------------------ pooled noise
+    # The reference draws one N(0,1) map per layer (`StyleAddNoise`, :112-119): 14 `normal_` launches per generator pass at 128^2.
+    # With the default random source the maps of a training pass are slices of ONE draw (same distribution, one launch); a taped
+    # source (parity tests) keeps the reference's per-layer draws.
+    def _begin_noise_pool(self, bs, device):
+        self._noise_pool = None
+        if not (self.training and self.use_noise and type(RANDOM.source) is RandomSource):
+            return
+        total = sum(bs * (4 << (n // 2)) ** 2 for n in range(len(self.gen_layers)))
+        self._noise_pool = RANDOM.source.randn((total,), device)
+        self._noise_off = 0
+
+    def _take_noise(self, out):
+        n_el = out.shape[0] * out.shape[2] * out.shape[3]
+        if self._noise_off + n_el > self._noise_pool.numel():          # (a layer list the pool was not sized for)
+            return RANDOM.source.randn((out.shape[0], 1, out.shape[2], out.shape[3]), out.device)
+        nz = self._noise_pool[self._noise_off:self._noise_off + n_el].view(out.shape[0], 1, out.shape[2], out.shape[3])
+        self._noise_off += n_el
+        return nz
 
     def _second_w(self, bs, device):
         z2 = gen_rand_latent_vars(num_samples=bs, length=self.len_latent, distribution=self.latent_distribution, device=device)
@@ -370,6 +395,7 @@ class StyleGenerator(StyleGAN):
                     ev.record(side)
                     styles.append((st, ev))
 
+        self._begin_noise_pool(bs, x.device)
         if self.fade_in_phase:
             for n, layer in enumerate(self.gen_layers[:-2]):
                 if n:
@@ -388,6 +414,7 @@ class StyleGenerator(StyleGAN):
                 x = self._second_w(bs, x.device)
             out = self._layer_conv(self.gen_layers[-1], out)
             out = self._layer_tail(self.gen_layers[-1], out, x if ws is None else ws[n], noise[-1] if noise is not None else None)
+            self._noise_pool = None                     # (the slices handed out keep the storage alive for backward)
             return ops.fade_up_blend(skip, self.torgb(out), self._state.blend_coefs()[0])
 
         for n, layer in enumerate(self.gen_layers):
@@ -410,6 +437,7 @@ class StyleGenerator(StyleGAN):
                     torch.cuda.current_stream().wait_event(ev)
                     st.record_stream(torch.cuda.current_stream())
             out = self._layer_tail(layer, out, x if ws is None else ws[n], noise[n] if noise is not None else None, style=st)
+        self._noise_pool = None
         return self.torgb(out)
 
 
