@@ -1044,6 +1044,204 @@ conv_fprop_tc2_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA pair + tap reuse for the folded layers
+// conv_fprop_tc2_halo_kernel's staging for the 2x2 phase taps of the upsample- / pool-folded convolutions (FpropParams::up):
+// per 32-channel chunk (and, for up = 2, input phase) a CTA loads TWO column-shifted boxes of 17 rows x 8 pixels once and the
+// four taps read them at row offsets of 1024 B -- 8.5 KB of A per tap instead of the 16 KB the generic pair kernel re-loads.
+// up = 1: the output phase is part of the M index (both tiles of a pair share it), pad = 1 - d per axis, strided output;
+// up = 2: K runs over (chunk, input phase, tap): A comes from the phase's strided view (TMapSet), offsets (a' - dy, b' - dx).
+template <int BN>
+struct Fprop2FoldCfg {
+  static constexpr int kBoxBytes = 17 * 1024;
+  static constexpr int kAStageBytes = 2 * kBoxBytes;
+  static constexpr int kTPS = (BN <= 128) ? 4 : 2;          // taps per B stage
+  static constexpr int kTapBytes = (BN / 2) * 128;
+  static constexpr int kBStageBytes = kTPS * kTapBytes;     // 32 KB either way
+  static constexpr int kAStages = 3;
+  static constexpr int kBStages = 3;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 256;
+};
+
+template <int BN, bool BF, int UP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
+conv_fprop_tc2_fold_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  using Cfg = Fprop2FoldCfg<BN>;
+  constexpr int NA = Cfg::kAStages, NB = Cfg::kBStages, TAPS = 4, TPS = Cfg::kTPS;
+  constexpr int kChunk = BF ? 64 : 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base, b_base = base + NA * Cfg::kAStageBytes;
+  const uint32_t bar0 = b_base + NB * Cfg::kBStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NA * Cfg::kAStageBytes + NB * Cfg::kBStageBytes);
+  auto afull = [&](int s) { return bar0 + 8u * s; };
+  auto aempty = [&](int s) { return bar0 + 8u * (NA + s); };
+  auto bfull = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+  auto bempty = [&](int s) { return bar0 + 8u * (2 * NA + NB + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NB + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA + 2 * NB + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int chunks = p.Ci / kChunk;
+  const int groups = UP == 2 ? 4 * chunks : chunks;      // A stages per item: (chunk) or (chunk, input phase)
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAs.m[0]);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's M tile of pair item `item` (16 x 8 pixels of the LOW-resolution grid) and, for up = 1, the output phase
+  auto my_tile = [&](int item, int& w0, int& h0, int& n0, int& ph) {
+    int u = item / p.tiles_co;
+    ph = 0;
+    if (UP == 1) { ph = u & 3; u >>= 2; }
+    int t = u * 2 + (int)rank;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    w0 = tw * 8; h0 = th * 16; n0 = t;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+        int w0, h0, n0, ph;
+        my_tile(item, w0, h0, n0, ph);
+        const int co0 = (item % p.tiles_co) * BN + (int)rank * (BN / 2) + ph * p.Co;   // this CTA's half of the weight tile
+        for (int g = 0; g < groups; ++g) {
+          const int ch = UP == 2 ? (g >> 2) : g, kph = UP == 2 ? (g & 3) : 0;
+          // first row / column of the boxes: up = 1: (h0 - pad_h, w0 + b - pad_w) with pad = 1 - d of the OUTPUT phase;
+          //                                  up = 2: (h0 - dy, w0 + b' - dx) with (dy, dx) of the INPUT phase kph
+          const int oy = UP == 1 ? (ph >> 1) - 1 : -(kph >> 1), ox = UP == 1 ? (ph & 1) - 1 : -(kph & 1);
+          mbar_wait(aempty(sa), pa ^ 1);
+          if (leader) mbar_expect_tx(afull(sa), 2 * Cfg::kAStageBytes);
+          const uint32_t lafull = mapa(afull(sa), 0);
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            tma2_load_4d(a_base + sa * Cfg::kAStageBytes + b * Cfg::kBoxBytes, &tmAs.m[kph], lafull, ch * kChunk, w0 + b + ox, h0 + oy, n0);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+#pragma unroll
+          for (int gq = 0; gq < TAPS / TPS; ++gq) {
+            mbar_wait(bempty(sb), pb ^ 1);
+            if (leader) mbar_expect_tx(bfull(sb), 2 * Cfg::kBStageBytes);
+            const uint32_t lbfull = mapa(bfull(sb), 0);
+#pragma unroll
+            for (int u = 0; u < TPS; ++u)
+              tma2_load_3d(b_base + sb * Cfg::kBStageBytes + u * Cfg::kTapBytes, &tmB, lbfull, ch * kChunk, kph * 4 + gq * TPS + u, co0);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BF>(2 * kBM, BN, 0, 0);
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(afull(sa), pa);
+          tc_fence_after();
+          const uint64_t ad0 = make_smem_desc(a_base + sa * Cfg::kAStageBytes, 16, 1024);
+#pragma unroll
+          for (int gq = 0; gq < TAPS / TPS; ++gq) {
+            mbar_wait(bfull(sb), pb);
+            tc_fence_after();
+            const uint64_t bd0 = make_smem_desc(b_base + sb * Cfg::kBStageBytes, 16, 1024);
+#pragma unroll
+            for (int u = 0; u < TPS; ++u) {
+              const int tap = gq * TPS + u, a = tap >> 1, b = tap & 1;       // row offset a (1024 B), column-shifted box b
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                mma2_ss<BF>(d_tmem, ad0 + (uint64_t)((b * Cfg::kBoxBytes + a * 1024 + kk * 32) >> 4),
+                            bd0 + (uint64_t)((u * Cfg::kTapBytes + kk * 32) >> 4), idesc, (g | tap | kk) ? 1u : 0u);
+            }
+            mma2_commit_mc(bempty(sb), 3);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+          mma2_commit_mc(aempty(sa), 3);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        mma2_commit_mc(tfull_bar(as), 3);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): own 128 rows of the pair's accumulator =====================
+    const int q = warp & 3;
+    const int c_begin = ((warp - 4) >> 2) * (BN / 2);
+    const int row = q * 32 + lane;
+    const int rw = row & 7, rh = row >> 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = pair_id; item < p.num_tiles; item += num_pairs) {
+      int w0, h0, n, ph;
+      my_tile(item, w0, h0, n, ph);
+      const int w = w0 + rw, h = h0 + rh, co0 = (item % p.tiles_co) * BN;
+      const bool valid = (w < p.Wo) && (h < p.Ho);
+      const int oh = UP == 1 ? 2 * h + (ph >> 1) : h, ow = UP == 1 ? 2 * w + (ph & 1) : w;
+      float* out = p.y + (((int64_t)n * p.OH + oh) * p.OW + ow) * p.Co + co0;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            float* oo = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = p.alpha * __uint_as_float(v[j + e]);
+              if (p.bias) a += p.bias_scale * __ldg(p.bias + co0 + c + j + e);
+              oo[e] = act_apply(a, p.act, p.slope);
+            }
+            *reinterpret_cast<float4*>(out + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ CTA pair, one-box tap reuse, MT tiles per B tile
 // What bounds the kernels above on the large layers is the L2 -> SM path (ncu: lts2xbar at 82 % of its peak while the tensor
 // pipe is 76 % active): per 32-channel chunk a CTA of conv_fprop_tc2_halo_kernel<256> pulls 54 KB of A (three column-shifted
@@ -1301,6 +1499,20 @@ int launch_fprop2_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Fpr
   const int pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
   conv_fprop_tc2_halo_kernel<BN, BF><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   GLB_CHECK_LAUNCH("conv_fprop_tc2_halo_kernel");
+  return GLB_OK;
+}
+
+template <int BN, bool BF, int UP>
+int launch_fprop2_fold(const TMapSet& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = Fprop2FoldCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_fold_kernel<BN, BF, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+  conv_fprop_tc2_fold_kernel<BN, BF, UP><<<2 * pairs, kFpropThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GLB_CHECK_LAUNCH("conv_fprop_tc2_fold_kernel");
   return GLB_OK;
 }
 
@@ -1675,12 +1887,22 @@ static int upconv_launch(int up, const void* in, const void* wmat, const float* 
   const int64_t out_rows = (int64_t)N * p.OH * p.OW;
   const bool post_pass = p.ksplit > 1 && (bias != nullptr || act != GLB_ACT_NONE);
   if (p.ksplit > 1) GLB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)out_rows * nc, st));
-  const bool use_pair = p.ksplit == 1 && BN == 256 && m_one % 2 == 0 && (m_tiles / 2) * p.tiles_co >= kNumSMs / 4;
+  // CTA pair + tap reuse (conv_fprop_tc2_fold_kernel): maps that tile into 16 x 8 pixel tiles, an even number of them per phase
+  const int m_fold = (H / 16) * (W / 8) * N;
+  bool use_fold = p.ksplit == 1 && (BN == 128 || BN == 256) && H % 16 == 0 && W % 8 == 0 && m_fold % 2 == 0 &&
+                  ((up == 1 ? 4 : 1) * (m_fold / 2)) * (nc / BN) >= kNumSMs / 8;
+  if (const char* e = getenv("GLB_FOLD_HALO")) use_fold = use_fold && atoi(e) != 0;      // A/B runs
+  if (use_fold) {
+    p.bw = 8; p.bh = 16; p.bn = 1;
+    p.tiles_w = W / 8; p.tiles_h = H / 16; p.tiles_n = N;
+    p.num_tiles = ((up == 1 ? 4 : 1) * (m_fold / 2)) * p.tiles_co;
+  }
+  const bool use_pair = !use_fold && p.ksplit == 1 && BN == 256 && m_one % 2 == 0 && (m_tiles / 2) * p.tiles_co >= kNumSMs / 4;
   if (use_pair) p.num_tiles = (m_tiles / 2) * p.tiles_co;
 
   TMapSet tmA;
   CUtensorMap tmB;
-  const uint32_t boxA[4] = {(uint32_t)kChunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  const uint32_t boxA[4] = {(uint32_t)kChunk, (uint32_t)(use_fold ? 8 : p.bw), (uint32_t)(use_fold ? 17 : p.bh), (uint32_t)(use_fold ? 1 : p.bn)};
   if (up == 1) {
     const uint64_t dims[4] = {(uint64_t)kc, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)kc * ES, (uint64_t)W * kc * ES, (uint64_t)H * W * kc * ES};
@@ -1702,9 +1924,13 @@ static int upconv_launch(int up, const void* in, const void* wmat, const float* 
     const uint64_t rows = up == 1 ? (uint64_t)4 * nc : (uint64_t)nc;
     const uint64_t dims[3] = {(uint64_t)kc, (uint64_t)taps, rows};
     const uint64_t strides[2] = {(uint64_t)kc * ES, (uint64_t)taps * kc * ES};
-    const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)(use_pair ? BN / 2 : BN)};
+    const uint32_t box[3] = {(uint32_t)kChunk, 1u, (uint32_t)((use_pair || use_fold) ? BN / 2 : BN)};
     int rc = make_tmap(&tmB, wmat, 3, dims, strides, box, "upconv weight", false, BF);
     if (rc) return rc;
+  }
+  if (use_fold) {
+    if (up == 1) return BN == 256 ? launch_fprop2_fold<256, BF, 1>(tmA, tmB, p, st) : launch_fprop2_fold<128, BF, 1>(tmA, tmB, p, st);
+    return BN == 256 ? launch_fprop2_fold<256, BF, 2>(tmA, tmB, p, st) : launch_fprop2_fold<128, BF, 2>(tmA, tmB, p, st);
   }
   if (use_pair) return launch_fprop2<256, BF>(tmA, tmB, p, st);
   int rc = GLB_ERR_UNSUPPORTED;
