@@ -127,13 +127,14 @@ def measured_mma_peaks():
     return out
 
 
-DOMINANT_KERNEL = "conv_fprop_tc2_kernel<256"     # CTA-pair implicit GEMM (plain 3x3 layers below one wave of halo tiles + the folded layers)
+DOMINANT_KERNEL = "conv_fprop_tc2_kernel<256"     # CTA-pair implicit GEMM: the largest share of the step when the committed ncu capture was taken
+                                                  # (since then conv_fprop_tc2_fold_kernel took its folded layers; the wgrad kernel leads the launch list)
 
 
 def ncu_traffic():
     """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant convolution kernel, read from
     the committed `ncu --set full` capture (profiles/r2_ncu_full_conv_family.csv, raw page, one row per launch; the rows of
-    DOMINANT_KERNEL, the kernel with the largest share of the step in profiles/r2_launches_cfg2_tf32_summary.txt)."""
+    DOMINANT_KERNEL)."""
     import csv
     p = ROOT / "profiles" / "r2_ncu_full_conv_family.csv"
     if not p.exists():
