@@ -2288,6 +2288,160 @@ conv_wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmGy, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad of the folded layers, two taps per CTA
+// conv_wgrad_tc3_kernel's idea for the 2x2 phase taps of the folded layers (WgradParams::up): one CTA per (phase, tap COLUMN b,
+// 128 co, BN ci, split) computes the two taps a = 0, 1 of that column at once: per K block (4 rows x 8 columns = 32 pixels of the
+// phase's low-resolution grid) it loads the gradient block once and ONE x box of (4 + 1) rows x 8 columns; tap row a is an offset
+// of 8 pixels = 1024 B into the box.  Two accumulators (2 x BN TMEM columns).  Per MMA 7 KB of TMA / L2 traffic instead of 12 KB.
+template <int BN>
+struct WgradFold2Cfg {
+  static constexpr int kPix = 32, kBoxPix = 40;              // 4 x 8 output pixels; (4 + 1) x 8 input pixels
+  static constexpr int kABlk = kPix * 128, kBBlk = kBoxPix * 128;
+  static constexpr int kABytes = 4 * kABlk;
+  static constexpr int kBBytes = (BN / 32) * kBBlk;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kTmemCols = (2 * BN < 64) ? 64 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad_fold2_kernel(const __grid_constant__ TMapSet tmGys, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  using Cfg = WgradFold2Cfg<BN>;
+  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  const uint32_t bar0 = base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int split = t % p.splits; t /= p.splits;
+  const int tci = t % p.tiles_ci; t /= p.tiles_ci;
+  const int tco = t % p.tiles_co; t /= p.tiles_co;
+  const int ph = t >> 1, b = t & 1;                  // phase (dy, dx) and tap column of this CTA; tap rows a = 0, 1 are its accumulators
+  const int dy = ph >> 1, dx = ph & 1;
+  const CUtensorMap& tmGy = tmGys.m[ph];
+  const int co0 = tco * 128, ci0 = tci * BN;
+  const int pb_begin = split * p.pb_per_split;
+  const int pb_end = min(p.num_pb, pb_begin + p.pb_per_split);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmGy);
+    prefetch_tmap(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        int u = pb;
+        const int tw = u % p.tiles_w; u /= p.tiles_w;
+        const int th = u % p.tiles_h; u /= p.tiles_h;
+        const int w0 = tw * 8, h0 = th * 4, n0 = u;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        tma_load_5d(a_dst, &tmGy, full_bar(stage), 0, w0, h0, n0, co0 / 32);
+        // x shift of tap (a, b) in phase (dy, dx): (a + dy - 1, b + dx - 1); the box starts at a = 0
+        tma_load_5d(a_dst + Cfg::kABytes, &tmX, full_bar(stage), 0, w0 + b + dx - 1, h0 + dy - 1, n0, ci0 / 32);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+        const uint64_t ad0 = make_smem_desc(a_addr, Cfg::kABlk, 512, kLayoutSw128Base32);
+        const uint64_t bd0 = make_smem_desc(a_addr + Cfg::kABytes, Cfg::kBBlk, 512, kLayoutSw128Base32);
+        const uint32_t acc = (pb > pb_begin) ? 1u : 0u;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+          for (int kg = 0; kg < Cfg::kPix / 8; ++kg)   // K = 8 pixels per MMA = 1024 B; tap row a = +8 pixels in the x box
+            mma_tf32(tmem_base + a * BN, ad0 + (uint64_t)((kg * 1024) >> 4), bd0 + (uint64_t)(((a + kg) * 1024) >> 4), idesc,
+                     kg > 0 ? 1u : acc);
+        }
+        mma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int co = co0 + q * 32 + lane;
+    const bool valid = co < p.Co;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int a = 0; a < 2; ++a) {
+      float* out = p.gw + ((int64_t)co * 16 + (ph * 4 + a * 2 + b)) * p.Ci + ci0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float a0 = p.alpha * __uint_as_float(v[j]), a1 = p.alpha * __uint_as_float(v[j + 1]);
+            const float a2 = p.alpha * __uint_as_float(v[j + 2]), a3 = p.alpha * __uint_as_float(v[j + 3]);
+            if (p.atomic) red_add_v4(out + c + j, a0, a1, a2, a3);
+            else *reinterpret_cast<float4*>(out + c + j) = make_float4(a0, a1, a2, a3);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_wgrad_fold2(const TMapSet& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
+  using Cfg = WgradFold2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GLB_CUDA(cudaFuncSetAttribute(conv_wgrad_fold2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  conv_wgrad_fold2_kernel<BN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmGy, tmX, p);
+  GLB_CHECK_LAUNCH("conv_wgrad_fold2_kernel");
+  return GLB_OK;
+}
+
 template <int BN>
 int launch_wgrad3(const CUtensorMap& tmGy, const CUtensorMap& tmX, const WgradParams& p, int grid, cudaStream_t st) {
   using Cfg = Wgrad3Cfg<BN>;
@@ -2593,6 +2747,69 @@ static int upconv_wgrad_impl(const void* x, const void* gy, float* gwp, float* g
   WgradParams p;
   p.gw = gwp; p.Co = Co; p.Ci = Ci; p.RS = 16; p.S = 4; p.pad = 1; p.up = 1;
   p.N = N; p.Ho = H; p.Wo = W;
+  // two taps per CTA (conv_wgrad_fold2_kernel): maps whose low-resolution grid tiles into 4 x 8 pixel K blocks, enough of them
+  {
+    // measured on B200 (cfg2 layers, batch 8): SLOWER than one tap per CTA -- 47 vs 37 us at 16^2 -> 32^2, 65 vs 61 us at
+    // 64^2 -> 128^2, whole step 809 vs 815 img/s: half as many CTAs with twice the red.add epilogue and three pipeline stages
+    // instead of four outweigh the saved operand traffic (the same finding as conv_wgrad_tc3_kernel below 128^2).  Kept for
+    // A/B runs only: GLB_WGRAD_FOLD2=1.
+    bool fold2 = false;
+    if (const char* e = getenv("GLB_WGRAD_FOLD2"))
+      fold2 = atoi(e) != 0 && !BF && W % 8 == 0 && H % 4 == 0 && (Ci % 128 == 0 || Ci == 64 || Ci == 32);
+    const int bn2 = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : Ci);
+    const int num_pb = (W / 8) * (H / 4) * N;
+    if (fold2 && num_pb >= 16) {
+      p.tiles_w = W / 8; p.tiles_h = H / 4; p.tiles_n = N;
+      p.num_pb = num_pb;
+      p.tiles_co = (Co + 127) / 128;
+      p.tiles_ci = Ci / bn2;
+      const int tiles2 = p.tiles_co * p.tiles_ci * 8;
+      int splits = kNumSMs / tiles2;
+      if (splits > num_pb / 8) splits = num_pb / 8;
+      if (splits < 1) splits = 1;
+      p.pb_per_split = (num_pb + splits - 1) / splits;
+      p.splits = (num_pb + p.pb_per_split - 1) / p.pb_per_split;
+      p.alpha = alpha * kTf32TruncComp;
+      p.atomic = p.splits > 1 ? 1 : 0;
+      p.bw = 8; p.bh = 4; p.bn = 1;
+      if (p.atomic) GLB_CUDA(cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Co * 16 * Ci, st));
+      TMapSet tmGy;
+      CUtensorMap tmX;
+      const uint64_t dg[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Co / 32)};
+      const uint64_t sg[4] = {(uint64_t)2 * Co * 4, (uint64_t)2 * (2 * W) * Co * 4, (uint64_t)(2 * H) * (2 * W) * Co * 4, 128u};
+      const uint32_t bg[5] = {32u, 8u, 4u, 1u, 4u};
+      for (int ph = 0; ph < 4; ++ph) {
+        const char* gbase = (const char*)gy + ((int64_t)(ph >> 1) * (2 * W) + (ph & 1)) * Co * 4;
+        int rc = make_tmap_f32(&tmGy.m[ph], gbase, 5, dg, sg, bg, "upconv wgrad gy (phase view, 4x8 blocks)", true);
+        if (rc) return rc;
+      }
+      const uint64_t dx[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Ci / 32)};
+      const uint64_t sx[4] = {(uint64_t)Ci * 4, (uint64_t)W * Ci * 4, (uint64_t)H * W * Ci * 4, 128u};
+      const uint32_t bx[5] = {32u, 8u, 5u, 1u, (uint32_t)(bn2 / 32)};
+      int rc = make_tmap_f32(&tmX, x, 5, dx, sx, bx, "upconv wgrad x (5x8 boxes)", true);
+      if (rc) return rc;
+      const int grid2 = tiles2 * p.splits;
+      switch (bn2) {
+        case 256: rc = launch_wgrad_fold2<256>(tmGy, tmX, p, grid2, st); break;
+        case 128: rc = launch_wgrad_fold2<128>(tmGy, tmX, p, grid2, st); break;
+        case 64: rc = launch_wgrad_fold2<64>(tmGy, tmX, p, grid2, st); break;
+        case 32: rc = launch_wgrad_fold2<32>(tmGy, tmX, p, grid2, st); break;
+        default: rc = GLB_ERR_UNSUPPORTED;
+      }
+      if (rc != GLB_OK) return rc;
+      if (transposed_out) {
+        dim3 tgrid((Co + 15) / 16, (Ci + 31) / 32);
+        fold_wgrad_transposed_kernel<<<tgrid, 512, 0, st>>>(gwp, gw, /*Co_layer =*/Ci, /*Ci_layer =*/Co);
+        GLB_CHECK_LAUNCH("fold_wgrad_transposed_kernel");
+        return GLB_OK;
+      }
+      const int64_t total = (int64_t)Co * 9 * (Ci / 4);
+      const int fgrid = (int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs);
+      upconv_wgrad_fold_kernel<<<fgrid, 256, 0, st>>>((const float4*)gwp, (float4*)gw, Co, Ci / 4);
+      GLB_CHECK_LAUNCH("upconv_wgrad_fold_kernel");
+      return GLB_OK;
+    }
+  }
   const int BN = Ci % 256 == 0 ? 256 : (Ci % 128 == 0 ? 128 : (Ci % 64 == 0 ? 64 : 32));
   const int PIX = (BN >= 256 ? 32 : 64) * (BF ? 2 : 1);
   p.bw = next_pow2(W) < PIX ? next_pow2(W) : PIX;
