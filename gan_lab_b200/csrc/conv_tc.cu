@@ -15,6 +15,16 @@
 //     thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> alpha/bias/act -> HBM).
 //     smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator stages (tmem_full/empty
 //     mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Kernel map (all in this file):
+//   conv_fprop_tc_kernel<BN,KC,BF>        single CTA, split-K; the low-resolution layers and every uncovered special case
+//   conv_fprop_tc2_kernel<BN,BF>          CTA pair (cta_group::2, M = 256)
+//   conv_fprop_tc_halo_kernel / conv_fprop_tc2_halo_kernel   3x3 tap reuse (three column-shifted boxes per chunk serve nine taps)
+//   conv_fprop_tc2_fold_kernel<BN,BF,UP>  tap reuse for the 2x2 phase taps of the upsample- / pool-folded layers
+//   conv_fprop_tc_m2_kernel, conv_fprop_tc2_h1_kernel          measured experiments (A/B switches, off by default)
+//   conv_wgrad_tc_kernel<BN,PIX,BF>, conv_wgrad_tc3_kernel<BN>, conv_wgrad_fold2_kernel<BN> (A/B)    weight gradients (MN-major operands)
+//   fold_weights_kernel<DOWN>, upconv_wgrad_fold_kernel, fold_wgrad_transposed_kernel    operand re-layouts of the folded layers
+// The folded layers (glb_upconv_* / glb_downconv_*, FpropParams::up, WgradParams::up) are documented above upconv_launch().
 #include <stdlib.h>
 
 #include "tc_common.cuh"
